@@ -1,0 +1,222 @@
+"""gl_slam_b200 — B200-native bundle-adjustment backend for GL-SLAM (host-side Python binding).
+
+Thin ctypes layer over the C ABI of include/glba.h (gl_slam_b200/libglba.so, built from csrc/ by
+`__graft_entry__.build()` or `make -C gl_slam_b200/csrc`).  The library is the product; this module
+only marshals numpy buffers.  There is NO CPU fallback: if the shared library is missing, or no CUDA
+device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import (HostProblem, LOSS_CAUCHY, LOSS_HUBER, LOSS_NONE, LINSOLVE_AUTO, LINSOLVE_DENSE,  # noqa: F401
+                   LINSOLVE_PCG, TERM_CONVERGENCE, TERM_FAILURE, TERM_NO_CONVERGENCE)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libglba.so")
+_LIB = None
+
+# every symbol include/glba.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = (
+    "glba_default_options", "glba_strerror", "glba_last_error", "glba_version", "glba_kernel_launch_count",
+    "glba_nccl_unique_id", "glba_create", "glba_destroy", "glba_solve", "glba_pose_only", "glba_pose_only_batch",
+    "glba_linearize", "glba_load", "glba_linearize_resident", "glba_solve_resident", "glba_reset_resident",
+    "glba_read_resident", "glba_synchronize", "glba_stream", "glba_cull_points",
+)
+
+
+class GlbaError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        msg = f"{where}: status {status}"
+        try:
+            msg += f" ({lib().glba_strerror(status).decode()})"
+        except Exception:
+            pass
+        if detail:
+            msg += f": {detail}"
+        super().__init__(msg)
+
+
+def lib():
+    """Load libglba.so; raises loudly if the CUDA library has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback for the BA kernels)")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
+    L.glba_default_options.argtypes = [C.POINTER(_abi.Options)]
+    L.glba_default_options.restype = None
+    L.glba_strerror.argtypes = [C.c_int]
+    L.glba_strerror.restype = C.c_char_p
+    L.glba_last_error.argtypes = [vp]
+    L.glba_last_error.restype = C.c_char_p
+    L.glba_version.restype = C.c_int
+    L.glba_kernel_launch_count.restype = C.c_int64
+    L.glba_nccl_unique_id.argtypes = [vp]
+    L.glba_create.argtypes = [C.POINTER(_abi.DeviceCfg), C.POINTER(vp)]
+    L.glba_destroy.argtypes = [vp]
+    L.glba_destroy.restype = None
+    L.glba_solve.argtypes = [vp, C.POINTER(_abi.Problem), C.POINTER(_abi.Options), C.POINTER(_abi.Summary)]
+    L.glba_pose_only.argtypes = [vp, vp, i32, vp, vp, f64, f64, f64, f64, C.POINTER(_abi.Options), C.POINTER(_abi.Summary)]
+    L.glba_pose_only_batch.argtypes = [vp, i32, vp, vp, vp, vp, f64, f64, f64, f64, C.POINTER(_abi.Options), vp, vp, vp]
+    L.glba_linearize.argtypes = [vp, C.POINTER(_abi.Problem), C.POINTER(_abi.Options), f64, C.POINTER(_abi.Linearization)]
+    L.glba_load.argtypes = [vp, C.POINTER(_abi.Problem), C.POINTER(_abi.Options)]
+    L.glba_linearize_resident.argtypes = [vp, C.POINTER(_abi.Options), f64, C.POINTER(f64)]
+    L.glba_solve_resident.argtypes = [vp, C.POINTER(_abi.Options), C.POINTER(_abi.Summary)]
+    L.glba_reset_resident.argtypes = [vp]
+    L.glba_read_resident.argtypes = [vp, vp, vp]
+    L.glba_synchronize.argtypes = [vp]
+    L.glba_stream.argtypes = [vp]
+    L.glba_stream.restype = vp
+    L.glba_cull_points.argtypes = [vp, C.POINTER(_abi.Problem), i32, f64, vp, vp]
+    _LIB = L
+    return L
+
+
+def options(**kw):
+    """glba_options with the reference's hard-coded values (slam_core.cpp:814, 842-847) as defaults."""
+    return _abi.make_options(lib().glba_default_options, **kw)
+
+
+def kernel_launch_count():
+    return int(lib().glba_kernel_launch_count())
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(_abi.GLBA_NCCL_ID_BYTES)
+    st = lib().glba_nccl_unique_id(buf)
+    if st:
+        raise GlbaError(st, "glba_nccl_unique_id")
+    return buf.raw
+
+
+class Context:
+    """One glba_ctx: a CUDA stream, workspaces and (world>1) an NCCL communicator.  Not thread-safe."""
+
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None, stream=None):
+        self._h = C.c_void_p()
+        self._id = C.create_string_buffer(nccl_id, _abi.GLBA_NCCL_ID_BYTES) if nccl_id is not None else None
+        cfg = _abi.DeviceCfg(device, rank, world, C.cast(self._id, C.c_void_p) if self._id is not None else None, stream)
+        st = lib().glba_create(C.byref(cfg), C.byref(self._h))
+        if st:
+            self._h = C.c_void_p()
+            raise GlbaError(st, "glba_create")
+        self.rank, self.world, self.device = rank, world, device
+
+    def close(self):
+        if self._h:
+            lib().glba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st, where):
+        if st:
+            raise GlbaError(st, where, lib().glba_last_error(self._h).decode(errors="replace"))
+
+    # -- full BA -------------------------------------------------------------------------------
+    def solve(self, prob, opt=None):
+        """Bundle-adjust a HostProblem.  Returns (refined copy, summary dict); input is not modified."""
+        opt = opt or options()
+        work = prob.copy()
+        summ = _abi.Summary()
+        st = lib().glba_solve(self._h, C.byref(work.struct()), C.byref(opt), C.byref(summ))
+        self._check(st, "glba_solve")
+        return work, summ.as_dict()
+
+    def linearize(self, prob, radius, opt=None, per_obs=True):
+        opt = opt or options()
+        out = _abi.LinearizationOut(prob.n_cam, prob.n_pt, prob.n_obs, per_obs)
+        s = out.struct()
+        st = lib().glba_linearize(self._h, C.byref(prob.struct()), C.byref(opt), float(radius), C.byref(s))
+        self._check(st, "glba_linearize")
+        out.take(s)
+        return out
+
+    # -- resident (device) problem -------------------------------------------------------------
+    def load(self, prob_struct, opt=None):
+        """prob_struct: _abi.Problem (host or device pointers).  Uploads and builds the device index."""
+        opt = opt or options()
+        self._check(lib().glba_load(self._h, C.byref(prob_struct), C.byref(opt)), "glba_load")
+
+    def linearize_resident(self, radius, opt=None, want_cost=True):
+        opt = opt or options()
+        c = C.c_double()
+        st = lib().glba_linearize_resident(self._h, C.byref(opt), float(radius), C.byref(c) if want_cost else None)
+        self._check(st, "glba_linearize_resident")
+        return c.value if want_cost else None
+
+    def solve_resident(self, opt=None):
+        opt = opt or options()
+        summ = _abi.Summary()
+        self._check(lib().glba_solve_resident(self._h, C.byref(opt), C.byref(summ)), "glba_solve_resident")
+        return summ.as_dict()
+
+    def reset_resident(self):
+        self._check(lib().glba_reset_resident(self._h), "glba_reset_resident")
+
+    def read_resident(self, n_cam, n_pt):
+        cam, pt = np.zeros((n_cam, 6)), np.zeros((n_pt, 3))
+        self._check(lib().glba_read_resident(self._h, cam.ctypes.data, pt.ctypes.data), "glba_read_resident")
+        return cam, pt
+
+    def synchronize(self):
+        self._check(lib().glba_synchronize(self._h), "glba_synchronize")
+
+    @property
+    def stream(self):
+        return lib().glba_stream(self._h)
+
+    # -- pose-only BA --------------------------------------------------------------------------
+    def pose_only(self, cam, X, uv, K, opt=None):
+        """Refine one camera [angle-axis, centre] against fixed points.  Returns (cam, summary dict)."""
+        opt = opt or options()
+        cam = np.ascontiguousarray(cam, dtype=np.float64).copy()
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        uv = np.ascontiguousarray(uv, dtype=np.float64)
+        if X.shape[0] != uv.shape[0]:
+            raise ValueError("p3d / p2d size mismatch")
+        summ = _abi.Summary()
+        st = lib().glba_pose_only(self._h, cam.ctypes.data, X.shape[0], X.ctypes.data, uv.ctypes.data,
+                                  *map(float, K), C.byref(opt), C.byref(summ))
+        self._check(st, "glba_pose_only")
+        return cam, summ.as_dict()
+
+    def pose_only_batch(self, cams, offsets, X, uv, K, opt=None):
+        opt = opt or options()
+        cams = np.ascontiguousarray(cams, dtype=np.float64).copy()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        uv = np.ascontiguousarray(uv, dtype=np.float64)
+        b = cams.shape[0]
+        usable, iters, cost = np.zeros(b, np.uint8), np.zeros(b, np.int32), np.zeros(b)
+        st = lib().glba_pose_only_batch(self._h, b, cams.ctypes.data, offsets.ctypes.data, X.ctypes.data, uv.ctypes.data,
+                                        *map(float, K), C.byref(opt), usable.ctypes.data, iters.ctypes.data,
+                                        cost.ctypes.data)
+        self._check(st, "glba_pose_only_batch")
+        return cams, usable.astype(bool), iters, cost
+
+    # -- post-BA culling -----------------------------------------------------------------------
+    def cull_points(self, prob, min_obs=3, max_mean_err=1.0):
+        bad = np.zeros(prob.n_pt, dtype=np.uint8)
+        err = np.zeros(prob.n_pt)
+        st = lib().glba_cull_points(self._h, C.byref(prob.struct()), min_obs, float(max_mean_err), bad.ctypes.data,
+                                    err.ctypes.data)
+        self._check(st, "glba_cull_points")
+        return bad, err

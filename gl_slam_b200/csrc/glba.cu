@@ -1,0 +1,914 @@
+// glba.cu — host side of the C ABI in include/glba.h: problem upload + index construction,
+// the Levenberg-Marquardt driver (Ceres trust-region semantics), PCG on the implicit
+// Schur complement, NCCL plumbing for sharded maps.  All arithmetic runs in the kernels of
+// glba_kernels.cuh / glba_pose.cuh; there is no CPU fallback: without a CUDA device every entry
+// point returns GLBA_E_NO_DEVICE.
+//
+// Reference boundary: slam_core::full_ba (src/core/slam_core.cpp:744-883) and
+// slam_core::pose_only_ba (:1092-1140) of GL-SLAM.
+#include "../../include/glba.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include "glba_kernels.cuh"
+#include "glba_pose.cuh"
+
+using namespace glba;
+
+// ---- minimal NCCL surface, resolved with dlopen so single-GPU use needs no NCCL at all ----------
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+}
+namespace {
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return false;
+    GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+std::atomic<long long> g_launches{0};
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum Phase { PH_SETUP = 0, PH_LIN, PH_SCHUR, PH_SOLVE, PH_UPDATE, PH_COUNT };
+}  // namespace
+
+struct glba_ctx {
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  ncclComm_t comm = nullptr;
+  std::string err;
+  // problem
+  bool loaded = false;
+  int n_cam = 0, n_pt = 0, n_chunks = 0, n_free_cam = 0;
+  long n_obs = 0;
+  Intr K{};
+  bool sorted_input = true;
+  // device buffers
+  Buf in_cam, in_pt, in_ocam, in_opt, in_u, in_v, in_cfix, in_pfix;                 // staging of host input
+  Buf pm_cam, pm_pt, pm_uv, pm2orig, pm2cm, pt_start, cm_pt, cm_uv, cm2pm, cam_start; // index
+  Buf chunk_cam, chunk_begin, chunk_end, cam_chunk_start, cam_free, pt_free, sort_tmp, keys_tmp, flags;
+  Buf cam[2], camtab[2], pt4[2], cam0, pt40;                                         // state (double-buffered)
+  Buf rec_pm, rec_cm, Craw, sp4, lam4, pblk, u4;
+  Buf part_pm, part_cm, acc27, yhat, Bc, gc, sc, lamc, Md, Minv, rhs, cg_x, cg_r, cg_p, cg_q, pg, yg, scal, cgst;
+  Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
+  int cur = 0;
+  double* h_scal = nullptr;    // pinned
+  CgState* h_cg = nullptr;     // pinned
+  int* h_flags = nullptr;      // pinned
+  // timing
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_phase;
+  int ev_used = 0;
+  double t_phase[PH_COUNT] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(glba_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? GLBA_E_OOM : GLBA_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                  cudaGetErrorString(e__));                                                              \
+  } while (0)
+
+#define LAUNCH(kernel, grid, block, ...)                                  \
+  do {                                                                    \
+    kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);             \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+  } while (0)
+
+template <typename T>
+int ensure(glba_ctx* ctx, Buf& b, size_t n) {
+  const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  if (b.cap >= bytes) return GLBA_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  const size_t want = bytes + bytes / 8 + 256;
+  CU(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return GLBA_OK;
+}
+#define ENSURE(T, buf, n) do { int s__ = ensure<T>(ctx, buf, n); if (s__) return s__; } while (0)
+
+void release(Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+inline int cdiv(long a, int b) { return (int)((a + b - 1) / b); }
+
+void mark(glba_ctx* ctx, int phase) {
+  if (ctx->ev_used == (int)ctx->ev.size()) {
+    cudaEvent_t e; cudaEventCreate(&e); ctx->ev.push_back(e); ctx->ev_phase.push_back(0);
+  }
+  cudaEventRecord(ctx->ev[ctx->ev_used], ctx->stream);
+  ctx->ev_phase[ctx->ev_used] = phase;
+  ctx->ev_used++;
+}
+// after a stream sync: attribute the time between consecutive markers to the earlier marker's phase
+void collect(glba_ctx* ctx) {
+  for (int i = 0; i + 1 < ctx->ev_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess && ctx->ev_phase[i] >= 0) ctx->t_phase[ctx->ev_phase[i]] += ms;
+  }
+  ctx->ev_used = 0;
+}
+
+int allreduce(glba_ctx* ctx, double* p, size_t n, int op) {
+  if (ctx->world <= 1) return GLBA_OK;
+  const int r = g_nccl.AllReduce(p, p, n, kNcclFloat64, op, ctx->comm, ctx->stream);
+  if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  return GLBA_OK;
+}
+#define AR(p, n, op) do { int s__ = allreduce(ctx, p, n, op); if (s__) return s__; } while (0)
+
+int validate_problem(glba_ctx* ctx, const glba_problem* p) {
+  if (!p) return fail(ctx, GLBA_E_INVALID_ARG, "problem is NULL");
+  if (p->n_cam < 0 || p->n_pt < 0 || p->n_obs < 0) return fail(ctx, GLBA_E_INVALID_ARG, "negative size");
+  if (p->n_obs > 0x7fffffffL) return fail(ctx, GLBA_E_UNSUPPORTED, "n_obs exceeds int32 indexing");
+  if (p->n_cam > 0 && !p->cam) return fail(ctx, GLBA_E_INVALID_ARG, "cam is NULL");
+  if (p->n_pt > 0 && !p->pt) return fail(ctx, GLBA_E_INVALID_ARG, "pt is NULL");
+  if (p->n_obs > 0 && (!p->obs_cam || !p->obs_pt || !p->obs_u || !p->obs_v)) return fail(ctx, GLBA_E_INVALID_ARG, "observation array is NULL");
+  if (p->n_obs > 0 && (p->n_cam == 0 || p->n_pt == 0)) return fail(ctx, GLBA_E_INVALID_ARG, "observations without cameras/points");
+  if (p->memspace != GLBA_MEM_HOST && p->memspace != GLBA_MEM_DEVICE) return fail(ctx, GLBA_E_INVALID_ARG, "bad memspace");
+  return GLBA_OK;
+}
+
+int validate_options(glba_ctx* ctx, const glba_options* o) {
+  if (!o) return fail(ctx, GLBA_E_INVALID_ARG, "options is NULL");
+  if (o->max_iters < 0 || o->max_iters > GLBA_MAX_ITERS) return fail(ctx, GLBA_E_INVALID_ARG, "max_iters out of [0,%d]", GLBA_MAX_ITERS);
+  if (o->loss < GLBA_LOSS_NONE || o->loss > GLBA_LOSS_CAUCHY) return fail(ctx, GLBA_E_INVALID_ARG, "unknown loss");
+  if (!(o->loss_scale > 0.0) || !(o->initial_radius > 0.0)) return fail(ctx, GLBA_E_INVALID_ARG, "loss_scale and initial_radius must be > 0");
+  return GLBA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Upload + index construction (the device-side restatement of the packing loop, slam_core.cpp:750-819)
+// ---------------------------------------------------------------------------------------------
+int load_problem(glba_ctx* ctx, const glba_problem* p) {
+  int st = validate_problem(ctx, p);
+  if (st) return st;
+  ctx->loaded = false;
+  ctx->ev_used = 0;
+  mark(ctx, PH_SETUP);
+  const int n_cam = p->n_cam, n_pt = p->n_pt;
+  const long n = p->n_obs;
+  ctx->n_cam = n_cam; ctx->n_pt = n_pt; ctx->n_obs = n;
+  ctx->K = Intr{p->fx, p->fy, p->cx, p->cy};
+  cudaStream_t s = ctx->stream;
+  const double *d_cam, *d_pt, *d_u, *d_v;
+  const int *d_ocam, *d_opt;
+  const uint8_t *d_cfix = nullptr, *d_pfix = nullptr;
+  if (p->memspace == GLBA_MEM_HOST) {
+    ENSURE(double, ctx->in_cam, 6 * (size_t)n_cam); ENSURE(double, ctx->in_pt, 3 * (size_t)n_pt);
+    ENSURE(int, ctx->in_ocam, n); ENSURE(int, ctx->in_opt, n); ENSURE(double, ctx->in_u, n); ENSURE(double, ctx->in_v, n);
+    CU(cudaMemcpyAsync(ctx->in_cam.p, p->cam, sizeof(double) * 6 * n_cam, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->in_pt.p, p->pt, sizeof(double) * 3 * n_pt, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->in_ocam.p, p->obs_cam, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->in_opt.p, p->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->in_u.p, p->obs_u, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->in_v.p, p->obs_v, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    if (p->cam_fixed) { ENSURE(uint8_t, ctx->in_cfix, n_cam); CU(cudaMemcpyAsync(ctx->in_cfix.p, p->cam_fixed, n_cam, cudaMemcpyHostToDevice, s)); d_cfix = ctx->in_cfix.as<uint8_t>(); }
+    if (p->pt_fixed) { ENSURE(uint8_t, ctx->in_pfix, n_pt); CU(cudaMemcpyAsync(ctx->in_pfix.p, p->pt_fixed, n_pt, cudaMemcpyHostToDevice, s)); d_pfix = ctx->in_pfix.as<uint8_t>(); }
+    d_cam = ctx->in_cam.as<double>(); d_pt = ctx->in_pt.as<double>(); d_ocam = ctx->in_ocam.as<int>(); d_opt = ctx->in_opt.as<int>();
+    d_u = ctx->in_u.as<double>(); d_v = ctx->in_v.as<double>();
+  } else {
+    d_cam = p->cam; d_pt = p->pt; d_ocam = p->obs_cam; d_opt = p->obs_pt; d_u = p->obs_u; d_v = p->obs_v;
+    d_cfix = p->cam_fixed; d_pfix = p->pt_fixed;
+  }
+  // state
+  for (int b = 0; b < 2; ++b) { ENSURE(double, ctx->cam[b], 6 * (size_t)n_cam); ENSURE(double, ctx->camtab[b], (size_t)CAMTAB * n_cam); ENSURE(double4, ctx->pt4[b], n_pt); }
+  ENSURE(double, ctx->cam0, 6 * (size_t)n_cam); ENSURE(double4, ctx->pt40, n_pt);
+  ctx->cur = 0;
+  CU(cudaMemcpyAsync(ctx->cam[0].p, d_cam, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
+  if (n_pt) LAUNCH(k_pack_pt, cdiv(n_pt, 256), 256, n_pt, d_pt, ctx->pt4[0].as<double4>());
+  CU(cudaMemcpyAsync(ctx->cam0.p, ctx->cam[0].p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(ctx->pt40.p, ctx->pt4[0].p, sizeof(double4) * n_pt, cudaMemcpyDeviceToDevice, s));
+  // index buffers
+  ENSURE(int, ctx->pm_cam, n); ENSURE(int, ctx->pm_pt, n); ENSURE(double2, ctx->pm_uv, n); ENSURE(int, ctx->pm2cm, n);
+  ENSURE(int, ctx->pt_start, (size_t)n_pt + 1); ENSURE(int, ctx->cm_pt, n); ENSURE(double2, ctx->cm_uv, n); ENSURE(int, ctx->cm2pm, n);
+  ENSURE(int, ctx->cam_start, (size_t)n_cam + 1); ENSURE(uint8_t, ctx->cam_free, n_cam); ENSURE(uint8_t, ctx->pt_free, n_pt);
+  ENSURE(int, ctx->keys_tmp, 2 * (size_t)n + 2); ENSURE(int, ctx->flags, 4);
+  ENSURE(int, ctx->pm2orig, n);
+  CU(cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), s));
+  const int gb = cdiv(n, 256);
+  if (n > 0) {
+    LAUNCH(k_check_sorted, gb, 256, n, d_opt, n_pt, ctx->flags.as<int>());
+    LAUNCH(k_check_range, gb, 256, n, d_ocam, n_cam, ctx->flags.as<int>() + 2);
+  }
+  CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (ctx->h_flags[1] || ctx->h_flags[2]) return fail(ctx, GLBA_E_INVALID_ARG, "observation index out of range");
+  ctx->sorted_input = (ctx->h_flags[0] == 0);
+  int bits_pt = 1; while ((1L << bits_pt) < (long)n_pt + 1 && bits_pt < 31) ++bits_pt;
+  int bits_cam = 1; while ((1L << bits_cam) < (long)n_cam + 1 && bits_cam < 31) ++bits_cam;
+  int* iota = ctx->keys_tmp.as<int>();          // [0,n): iota / sorted keys scratch; [n,2n): keys out
+  int* keys_out = ctx->keys_tmp.as<int>() + n + 1;
+  if (n > 0) {
+    if (ctx->sorted_input) {
+      LAUNCH(k_gather_obs, gb, 256, n, (const int*)nullptr, d_ocam, d_opt, d_u, d_v, ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), ctx->pm_uv.as<double2>());
+    } else {
+      LAUNCH(k_iota, gb, 256, n, iota);
+      size_t tmp_bytes = 0;
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_opt, keys_out, iota, ctx->pm2orig.as<int>(), (int)n, 0, bits_pt, s));
+      ENSURE(char, ctx->sort_tmp, tmp_bytes);
+      CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, d_opt, keys_out, iota, ctx->pm2orig.as<int>(), (int)n, 0, bits_pt, s));
+      g_launches.fetch_add(1);
+      LAUNCH(k_gather_obs, gb, 256, n, (const int*)ctx->pm2orig.as<int>(), d_ocam, d_opt, d_u, d_v, ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), ctx->pm_uv.as<double2>());
+    }
+    LAUNCH(k_segment_starts, cdiv(n_pt + 1, 256), 256, n, (const int*)ctx->pm_pt.as<int>(), n_pt, ctx->pt_start.as<int>());
+    // camera-major order: stable sort of point-major positions by camera
+    LAUNCH(k_iota, gb, 256, n, iota);
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->pm_cam.as<int>(), keys_out, iota, ctx->cm2pm.as<int>(), (int)n, 0, bits_cam, s));
+    ENSURE(char, ctx->sort_tmp, tmp_bytes);
+    CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->pm_cam.as<int>(), keys_out, iota, ctx->cm2pm.as<int>(), (int)n, 0, bits_cam, s));
+    g_launches.fetch_add(1);
+    LAUNCH(k_segment_starts, cdiv(n_cam + 1, 256), 256, n, (const int*)keys_out, n_cam, ctx->cam_start.as<int>());
+    LAUNCH(k_build_cm, gb, 256, n, (const int*)ctx->cm2pm.as<int>(), (const int*)ctx->pm_pt.as<int>(), (const double2*)ctx->pm_uv.as<double2>(),
+           ctx->cm_pt.as<int>(), ctx->cm_uv.as<double2>(), ctx->pm2cm.as<int>());
+  } else {
+    CU(cudaMemsetAsync(ctx->pt_start.p, 0, sizeof(int) * ((size_t)n_pt + 1), s));
+    CU(cudaMemsetAsync(ctx->cam_start.p, 0, sizeof(int) * ((size_t)n_cam + 1), s));
+  }
+  if (n_cam) LAUNCH(k_free_flags, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
+  if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, ctx->pt_free.as<uint8_t>());
+  // chunk list for the camera-major kernels (host, from cam_start)
+  std::vector<int> h_start((size_t)n_cam + 1);
+  std::vector<uint8_t> h_free(std::max(n_cam, 1));
+  CU(cudaMemcpyAsync(h_start.data(), ctx->cam_start.p, sizeof(int) * ((size_t)n_cam + 1), cudaMemcpyDeviceToHost, s));
+  if (n_cam) CU(cudaMemcpyAsync(h_free.data(), ctx->cam_free.p, n_cam, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  long per = (n + 148L * 8 - 1) / (148L * 8);
+  int chunk = (int)std::min<long>(4096, std::max<long>(NT_CM, ((per + NT_CM - 1) / NT_CM) * NT_CM));
+  std::vector<int> cc, cb, ce, ccs((size_t)n_cam + 1, 0);
+  ctx->n_free_cam = 0;
+  for (int i = 0; i < n_cam; ++i) {
+    ccs[i] = (int)cc.size();
+    if (h_free[i]) ctx->n_free_cam++;
+    for (int b = h_start[i]; b < h_start[i + 1]; b += chunk) { cc.push_back(i); cb.push_back(b); ce.push_back(std::min(h_start[i + 1], b + chunk)); }
+  }
+  ccs[n_cam] = (int)cc.size();
+  ctx->n_chunks = (int)cc.size();
+  ENSURE(int, ctx->chunk_cam, cc.size()); ENSURE(int, ctx->chunk_begin, cc.size()); ENSURE(int, ctx->chunk_end, cc.size());
+  ENSURE(int, ctx->cam_chunk_start, ccs.size());
+  if (!cc.empty()) {
+    CU(cudaMemcpyAsync(ctx->chunk_cam.p, cc.data(), sizeof(int) * cc.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->chunk_begin.p, cb.data(), sizeof(int) * cb.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->chunk_end.p, ce.data(), sizeof(int) * ce.size(), cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaMemcpyAsync(ctx->cam_chunk_start.p, ccs.data(), sizeof(int) * ccs.size(), cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));   // the host vectors go out of scope
+  // work buffers
+  const int grid_pm = cdiv(n_pt, NT_PM);
+  ENSURE(double4, ctx->rec_pm, n); ENSURE(double4, ctx->rec_cm, n);
+  ENSURE(double, ctx->Craw, 9 * (size_t)n_pt); ENSURE(double4, ctx->sp4, n_pt); ENSURE(double4, ctx->lam4, n_pt);
+  ENSURE(double, ctx->pblk, (size_t)PBLK * n_pt); ENSURE(double4, ctx->u4, n_pt);
+  ENSURE(double, ctx->part_pm, 5 * (size_t)std::max(grid_pm, 1)); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1));
+  ENSURE(double, ctx->acc27, 27 * (size_t)n_cam); ENSURE(double, ctx->yhat, 6 * (size_t)n_cam);
+  ENSURE(double, ctx->Bc, 36 * (size_t)n_cam); ENSURE(double, ctx->gc, 6 * (size_t)n_cam); ENSURE(double, ctx->sc, 6 * (size_t)n_cam);
+  ENSURE(double, ctx->lamc, 6 * (size_t)n_cam); ENSURE(double, ctx->Md, 36 * (size_t)n_cam); ENSURE(double, ctx->Minv, 36 * (size_t)n_cam);
+  ENSURE(double, ctx->rhs, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_x, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_r, 6 * (size_t)n_cam);
+  ENSURE(double, ctx->cg_p, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_q, 6 * (size_t)n_cam); ENSURE(double, ctx->pg, 6 * (size_t)n_cam);
+  ENSURE(double, ctx->yg, 6 * (size_t)n_cam); ENSURE(double, ctx->scal, NSCAL); ENSURE(CgState, ctx->cgst, 1);
+  CU(cudaMemsetAsync(ctx->scal.p, 0, sizeof(double) * NSCAL, s));
+  CU(cudaMemsetAsync(ctx->yhat.p, 0, sizeof(double) * 6 * n_cam, s));
+  CU(cudaMemsetAsync(ctx->acc27.p, 0, sizeof(double) * 27 * n_cam, s));
+  if (n_cam) LAUNCH(k_cam_prep, cdiv(n_cam, 128), 128, n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>());
+  mark(ctx, -1);
+  ctx->loaded = true;
+  return GLBA_OK;
+}
+
+PmArgs pm_args(glba_ctx* ctx, const glba_options* o) {
+  PmArgs A;
+  A.n_pt = ctx->n_pt; A.pt_start = ctx->pt_start.as<int>(); A.pm_cam = ctx->pm_cam.as<int>(); A.pm_uv = ctx->pm_uv.as<double2>();
+  A.pm2cm = ctx->pm2cm.as<int>(); A.pt_free = ctx->pt_free.as<uint8_t>(); A.K = ctx->K;
+  A.loss = LossP{o->loss, o->loss_scale};
+  return A;
+}
+CmArgs cm_args(glba_ctx* ctx) {
+  CmArgs A;
+  A.chunk_cam = ctx->chunk_cam.as<int>(); A.chunk_begin = ctx->chunk_begin.as<int>(); A.chunk_end = ctx->chunk_end.as<int>();
+  A.cm_pt = ctx->cm_pt.as<int>(); A.cm_uv = ctx->cm_uv.as<double2>(); A.cam_free = ctx->cam_free.as<uint8_t>(); A.K = ctx->K;
+  return A;
+}
+
+// residual / weight / Jacobian records + Hessian blocks at the current state (K_A + K_B blocks)
+int do_linearize(glba_ctx* ctx, const glba_options* o, int first, double radius) {
+  const int c = ctx->cur;
+  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  const int grid_pm = cdiv(n_pt, NT_PM);
+  mark(ctx, PH_LIN);
+  if (n_pt) {
+    LAUNCH(k_linearize_pm, grid_pm, NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(),
+           ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
+    ReduceMap M{}; M.n = 5;
+    const int slots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
+    for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = (q == 4); }
+    LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+  }
+  if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+                            (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
+  if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
+                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr);
+  if (ctx->world > 1) {
+    AR(ctx->acc27.as<double>(), 27 * (size_t)n_cam, kNcclSum);
+    AR(ctx->scal.as<double>() + S_COST, 4, kNcclSum);
+    AR(ctx->scal.as<double>() + S_GMAX_P, 1, kNcclMax);
+  }
+  if (n_cam) LAUNCH(k_cam_lin_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+                    (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->acc27.as<double>(), ctx->Bc.as<double>(), ctx->gc.as<double>(),
+                    ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, ctx->scal.as<double>());
+  mark(ctx, -1);
+  return GLBA_OK;
+}
+
+// re-damp point blocks for a new radius (after a rejected / invalid step)
+int do_redamp(glba_ctx* ctx, double radius) {
+  const int n_pt = ctx->n_pt;
+  if (!n_pt) return GLBA_OK;
+  const int grid_pm = cdiv(n_pt, NT_PM);
+  mark(ctx, PH_SCHUR);
+  LAUNCH(k_point_damp, grid_pm, NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
+         (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>());
+  ReduceMap M{}; M.n = 1; M.slot[0] = S_NOTPD_P; M.is_max[0] = 0;
+  LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 1, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+  if (ctx->world > 1) AR(ctx->scal.as<double>() + S_NOTPD_P, 1, kNcclSum);
+  mark(ctx, -1);
+  return GLBA_OK;
+}
+
+// Schur complement pieces: preconditioner blocks (= diagonal of S), reduced rhs
+int do_schur(glba_ctx* ctx, double radius) {
+  const int c = ctx->cur;
+  const int n_cam = ctx->n_cam;
+  mark(ctx, PH_SCHUR);
+  if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+                            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>());
+  if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
+                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr);
+  if (ctx->world > 1) AR(ctx->acc27.as<double>(), 27 * (size_t)n_cam, kNcclSum);
+  if (n_cam) LAUNCH(k_cam_schur_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+                    (const double*)ctx->acc27.as<double>(), (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(),
+                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->scal.as<double>());
+  mark(ctx, -1);
+  return GLBA_OK;
+}
+
+// Block-Jacobi PCG on the implicit Schur complement; solution in cg_x.  Returns iterations in *iters.
+int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
+  const int c = ctx->cur;
+  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  *iters = 0;
+  mark(ctx, PH_SOLVE);
+  if (ctx->n_free_cam == 0 || n_cam == 0) {
+    CU(cudaMemsetAsync(ctx->cg_x.p, 0, sizeof(double) * 6 * std::max(n_cam, 1), ctx->stream));
+    mark(ctx, -1);
+    return GLBA_OK;
+  }
+  const int dim = 6 * ctx->n_free_cam;
+  const int max_it = o->cg_max_iters > 0 ? o->cg_max_iters : std::min(4000, 4 * dim);
+  CgState* cg = ctx->cgst.as<CgState>();
+  LAUNCH(k_cg_init, 1, NT_CAM, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(), (const double*)ctx->rhs.as<double>(),
+         ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->pg.as<double>(), cg, o->cg_rel_tol, max_it);
+  const int grid_pm = cdiv(n_pt, NT_PM);
+  const PmArgs PA = pm_args(ctx, o);
+  const CmArgs CA = cm_args(ctx);
+  const int poll = 8;
+  int launched = 0;
+  for (;;) {
+    for (int b = 0; b < poll && launched < max_it; ++b, ++launched) {
+      LAUNCH(k_point_pass<0>, grid_pm, NT_PM, PA, (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+             (const double*)ctx->pg.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), (const CgState*)cg,
+             (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr);
+      LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+             (const double4*)ctx->u4.as<double4>(), (const CgState*)cg, ctx->part_cm.as<double>());
+      LAUNCH(k_chunk_sum<6>, cdiv((long)n_cam * 6, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
+             ctx->yhat.as<double>(), (const CgState*)cg);
+      if (ctx->world > 1) AR(ctx->yhat.as<double>(), 6 * (size_t)n_cam, kNcclSum);
+      LAUNCH(k_cg_update, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+             (const double*)ctx->Bc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const double*)ctx->Minv.as<double>(),
+             (const double*)ctx->yhat.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->cg_q.as<double>(),
+             ctx->pg.as<double>(), cg);
+    }
+    CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_cg->done || launched >= max_it) break;
+  }
+  *iters = ctx->h_cg->iters;
+  mark(ctx, -1);
+  return GLBA_OK;
+}
+
+// candidate state, back-substitution, candidate cost; leaves the scalars in h_scal (synchronises)
+int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
+  const int c = ctx->cur, d = c ^ 1;
+  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  const int grid_pm = cdiv(n_pt, NT_PM);
+  mark(ctx, PH_UPDATE);
+  if (n_cam) LAUNCH(k_cam_step, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+                    (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
+                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->yg.as<double>(),
+                    ctx->scal.as<double>());
+  if (n_pt) {
+    LAUNCH(k_point_pass<1>, grid_pm, NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->yg.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr,
+           (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
+           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>());
+    ReduceMap M{}; M.n = 5;
+    const int slots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
+    for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = 0; }
+    LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+  }
+  if (ctx->world > 1) AR(ctx->scal.as<double>() + S_COST_C, 5, kNcclSum);
+  mark(ctx, -1);
+  CU(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect(ctx);
+  return GLBA_OK;
+}
+
+int fetch_scal(glba_ctx* ctx) {
+  CU(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect(ctx);
+  return GLBA_OK;
+}
+
+// The trust-region loop (Ceres TrustRegionMinimizer semantics; see oracle/glba_oracle.cpp for the
+// statement-by-statement restatement this mirrors).
+int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
+  int st;
+  for (int q = 0; q < PH_COUNT; ++q) if (q != PH_SETUP) ctx->t_phase[q] = 0.0;
+  sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_NONE;
+  double radius = o->initial_radius, decrease_factor = 2.0;
+  int n_invalid = 0;
+  if ((st = do_linearize(ctx, o, 1, radius))) return st;
+  if ((st = fetch_scal(ctx))) return st;
+  const double* S = ctx->h_scal;
+  if (S[S_BAD] > 0.0 || !std::isfinite(S[S_COST])) {
+    sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; sum->status = GLBA_E_NUMERIC;
+    return fail(ctx, GLBA_E_NUMERIC, "non-finite residual at the initial point");
+  }
+  sum->n_linearizations = 1;
+  double cost = S[S_COST];
+  double gmax = std::max(S[S_GMAX_P], S[S_GMAX_C]);
+  double x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
+  sum->initial_cost = cost; sum->cost[0] = cost; sum->cost_candidate[0] = cost; sum->radius[0] = radius; sum->gradient_max_norm[0] = gmax;
+  int it = 0;
+  bool fresh = true;   // point blocks are damped for the current radius
+  // number of free parameters: free cameras + free points (host knows cameras; points: any observation => >0)
+  if (ctx->n_obs == 0) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
+  else for (;;) {
+    if (it >= o->max_iters) { sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_MAX_ITERS; break; }
+    if (gmax <= o->gradient_tol) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
+    if (radius <= o->min_radius) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_MIN_RADIUS; break; }
+    ++it;
+    if (!fresh) { if ((st = do_redamp(ctx, radius))) return st; }
+    fresh = true;
+    int cg_it = 0;
+    if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
+    if ((st = do_pcg(ctx, o, radius, &cg_it))) return st;
+    sum->cg_iters[it] = cg_it;
+    if ((st = do_step(ctx, o, radius))) return st;
+    const bool solver_ok = (S[S_NOTPD_P] + (ctx->n_free_cam > 0 ? S[S_NOTPD_C] : 0.0)) == 0.0;
+    const double model_cost_change = 0.5 * ((S[S_YG_P] + S[S_YG_C]) + (S[S_YLY_P] + S[S_YLY_C]));
+    const bool valid = solver_ok && (model_cost_change > 0.0);
+    if (o->verbose) fprintf(stderr, "[glba] it %d cost %.9e cand %.9e model %.3e radius %.3e cg %d\n", it, cost, S[S_COST_C], model_cost_change, radius, cg_it);
+    if (!valid) {
+      ++n_invalid;
+      sum->cost[it] = cost; sum->cost_candidate[it] = cost; sum->step_norm[it] = 0; sum->relative_decrease[it] = 0;
+      sum->gradient_max_norm[it] = gmax; sum->accepted[it] = 0;
+      if (n_invalid >= o->max_consecutive_invalid_steps) { sum->radius[it] = radius; sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_INVALID_STEPS; break; }
+      radius = radius / decrease_factor; decrease_factor *= 2.0; fresh = false;
+      sum->radius[it] = radius;
+      continue;
+    }
+    n_invalid = 0;
+    double cand = S[S_COST_C];
+    if (S[S_BAD_C] > 0.0 || !std::isfinite(cand)) cand = std::numeric_limits<double>::max();
+    const double step_norm = std::sqrt(S[S_YN2_P] + S[S_YN2_C]);
+    sum->cost_candidate[it] = cand; sum->step_norm[it] = step_norm; sum->cost[it] = cost; sum->radius[it] = radius; sum->gradient_max_norm[it] = gmax;
+    if (step_norm <= o->parameter_tol * (x_norm + o->parameter_tol)) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_PARAMETER_TOL; break; }
+    const double cost_change = cost - cand;
+    if (std::fabs(cost_change) <= o->function_tol * cost) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_FUNCTION_TOL; break; }
+    const double rel = (cand >= std::numeric_limits<double>::max()) ? std::numeric_limits<double>::lowest() : cost_change / model_cost_change;
+    sum->relative_decrease[it] = rel;
+    if (rel > o->min_relative_decrease) {
+      ctx->cur ^= 1;     // the candidate buffers (state + camera table) become current
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+      radius = std::min(o->max_radius, radius);
+      decrease_factor = 2.0;
+      if ((st = do_linearize(ctx, o, 0, radius))) return st;
+      if ((st = fetch_scal(ctx))) return st;
+      if (S[S_BAD] > 0.0 || !std::isfinite(S[S_COST])) { sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; break; }
+      cost = S[S_COST]; gmax = std::max(S[S_GMAX_P], S[S_GMAX_C]); x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
+      sum->n_linearizations++; sum->n_successful++; sum->accepted[it] = 1;
+      fresh = true;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0; fresh = false;
+      sum->accepted[it] = 0;
+    }
+    sum->cost[it] = cost; sum->radius[it] = radius; sum->gradient_max_norm[it] = gmax;
+  }
+  sum->n_iters = it; sum->final_cost = cost;
+  sum->t_setup_ms = ctx->t_phase[PH_SETUP]; sum->t_linearize_ms = ctx->t_phase[PH_LIN]; sum->t_schur_ms = ctx->t_phase[PH_SCHUR];
+  sum->t_solve_ms = ctx->t_phase[PH_SOLVE]; sum->t_update_ms = ctx->t_phase[PH_UPDATE];
+  sum->t_total_ms = sum->t_setup_ms + sum->t_linearize_ms + sum->t_schur_ms + sum->t_solve_ms + sum->t_update_ms;
+  sum->status = GLBA_OK;
+  return GLBA_OK;
+}
+
+int write_back(glba_ctx* ctx, double* cam, double* pt, int memspace) {
+  const int c = ctx->cur;
+  cudaStream_t s = ctx->stream;
+  if (memspace == GLBA_MEM_HOST) {
+    ENSURE(double, ctx->out_a, 3 * (size_t)ctx->n_pt);
+    if (ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), ctx->out_a.as<double>());
+    if (cam) CU(cudaMemcpyAsync(cam, ctx->cam[c].p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToHost, s));
+    if (pt) CU(cudaMemcpyAsync(pt, ctx->out_a.p, sizeof(double) * 3 * ctx->n_pt, cudaMemcpyDeviceToHost, s));
+  } else {
+    if (cam) CU(cudaMemcpyAsync(cam, ctx->cam[c].p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToDevice, s));
+    if (pt && ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), pt);
+  }
+  CU(cudaStreamSynchronize(s));
+  return GLBA_OK;
+}
+
+PoseOpts pose_opts(const glba_options* o) {
+  PoseOpts P;
+  P.loss = LossP{o->loss, o->loss_scale}; P.max_iters = o->max_iters;
+  P.function_tol = o->function_tol; P.gradient_tol = o->gradient_tol; P.parameter_tol = o->parameter_tol;
+  P.initial_radius = o->initial_radius; P.max_radius = o->max_radius; P.min_radius = o->min_radius;
+  P.min_relative_decrease = o->min_relative_decrease; P.min_diag = o->min_lm_diagonal; P.max_diag = o->max_lm_diagonal;
+  P.jacobi = o->jacobi_scaling; P.max_invalid = o->max_consecutive_invalid_steps;
+  return P;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+void glba_default_options(glba_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->loss = GLBA_LOSS_CAUCHY; o->loss_scale = 1.0; o->max_iters = 30;
+  o->function_tol = 1e-6; o->gradient_tol = 1e-10; o->parameter_tol = 1e-8;
+  o->initial_radius = 1e4; o->max_radius = 1e16; o->min_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->jacobi_scaling = 1; o->max_consecutive_invalid_steps = 5;
+  o->linsolve = GLBA_LINSOLVE_AUTO; o->dense_max_dim = 384; o->cg_rel_tol = 1e-13; o->cg_max_iters = 0; o->verbose = 0;
+}
+
+const char* glba_strerror(int status) {
+  switch (status) {
+    case GLBA_OK: return "ok";
+    case GLBA_E_INVALID_ARG: return "invalid argument";
+    case GLBA_E_CUDA: return "CUDA runtime error";
+    case GLBA_E_NO_DEVICE: return "no CUDA device (this backend has no CPU fallback)";
+    case GLBA_E_OOM: return "out of device memory";
+    case GLBA_E_NCCL: return "NCCL error";
+    case GLBA_E_NUMERIC: return "non-finite residuals at the initial point";
+    case GLBA_E_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+  }
+}
+
+const char* glba_last_error(const glba_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+int glba_version(void) { return GLBA_VERSION; }
+int64_t glba_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int glba_nccl_unique_id(void* out_id) {
+  if (!out_id) return GLBA_E_INVALID_ARG;
+  if (!g_nccl.load()) return GLBA_E_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return GLBA_E_NCCL;
+  static_assert(sizeof(id) == GLBA_NCCL_ID_BYTES, "ncclUniqueId size");
+  std::memcpy(out_id, &id, sizeof(id));
+  return GLBA_OK;
+}
+
+int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
+  if (!cfg || !out) return GLBA_E_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return GLBA_E_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GLBA_E_NO_DEVICE; }
+  if (cfg->device < 0 || cfg->device >= ndev) return GLBA_E_INVALID_ARG;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return GLBA_E_CUDA;
+  glba_ctx* ctx = new glba_ctx();
+  ctx->device = cfg->device; ctx->rank = cfg->rank; ctx->world = cfg->world;
+  if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
+  else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GLBA_E_CUDA; } ctx->own_stream = true; }
+  if (cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * NSCAL) != cudaSuccess || cudaMallocHost((void**)&ctx->h_cg, sizeof(CgState)) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_flags, 4 * sizeof(int)) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
+  if (cfg->world > 1) {
+    if (!cfg->nccl_unique_id || !g_nccl.load()) { glba_destroy(ctx); return GLBA_E_NCCL; }
+    ncclUniqueId id; std::memcpy(&id, cfg->nccl_unique_id, sizeof(id));
+    if (g_nccl.CommInitRank(&ctx->comm, cfg->world, id, cfg->rank) != 0) { ctx->comm = nullptr; glba_destroy(ctx); return GLBA_E_NCCL; }
+  }
+  *out = ctx;
+  return GLBA_OK;
+}
+
+void glba_destroy(glba_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  Buf* all[] = {&ctx->in_cam, &ctx->in_pt, &ctx->in_ocam, &ctx->in_opt, &ctx->in_u, &ctx->in_v, &ctx->in_cfix, &ctx->in_pfix, &ctx->pm_cam, &ctx->pm_pt,
+                &ctx->pm_uv, &ctx->pm2orig, &ctx->pm2cm, &ctx->pt_start, &ctx->cm_pt, &ctx->cm_uv, &ctx->cm2pm, &ctx->cam_start, &ctx->chunk_cam,
+                &ctx->chunk_begin, &ctx->chunk_end, &ctx->cam_chunk_start, &ctx->cam_free, &ctx->pt_free, &ctx->sort_tmp, &ctx->keys_tmp, &ctx->flags,
+                &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
+                &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
+                &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->scal, &ctx->cgst,
+                &ctx->out_a, &ctx->out_b, &ctx->out_c};
+  for (Buf* b : all) release(*b);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  if (ctx->h_cg) cudaFreeHost(ctx->h_cg);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void* glba_stream(glba_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int glba_synchronize(glba_ctx* ctx) {
+  if (!ctx) return GLBA_E_INVALID_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GLBA_OK;
+}
+
+int glba_load(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt) {
+  if (!ctx) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) return st;
+  ctx->t_phase[PH_SETUP] = 0.0;
+  st = load_problem(ctx, prob);
+  if (st) return st;
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect(ctx);
+  return GLBA_OK;
+}
+
+int glba_reset_resident(glba_ctx* ctx) {
+  if (!ctx || !ctx->loaded) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  ctx->cur = 0;
+  CU(cudaMemcpyAsync(ctx->cam[0].p, ctx->cam0.p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->pt4[0].p, ctx->pt40.p, sizeof(double4) * ctx->n_pt, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->n_cam) LAUNCH(k_cam_prep, cdiv(ctx->n_cam, 128), 128, ctx->n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>());
+  return GLBA_OK;
+}
+
+int glba_read_resident(glba_ctx* ctx, double* cam, double* pt) {
+  if (!ctx || !ctx->loaded) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  return write_back(ctx, cam, pt, GLBA_MEM_HOST);
+}
+
+int glba_linearize_resident(glba_ctx* ctx, const glba_options* opt, double radius, double* cost) {
+  if (!ctx || !ctx->loaded || !(radius > 0.0)) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) return st;
+  if ((st = do_linearize(ctx, opt, 1, radius))) return st;
+  if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
+  if (cost) {
+    if ((st = fetch_scal(ctx))) return st;
+    *cost = ctx->h_scal[S_COST];
+  } else {
+    ctx->ev_used = 0;   // no sync requested: drop the phase markers
+  }
+  return GLBA_OK;
+}
+
+int glba_solve_resident(glba_ctx* ctx, const glba_options* opt, glba_summary* summary) {
+  if (!ctx || !ctx->loaded || !summary) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) return st;
+  std::memset(summary, 0, sizeof(*summary));
+  st = run_lm(ctx, opt, summary);
+  summary->status = st;
+  return st;
+}
+
+int glba_solve(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt, glba_summary* summary) {
+  if (!ctx || !summary) return GLBA_E_INVALID_ARG;
+  std::memset(summary, 0, sizeof(*summary));
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) { summary->status = st; return st; }
+  ctx->t_phase[PH_SETUP] = 0.0;
+  st = load_problem(ctx, prob);
+  if (st) { summary->status = st; return st; }
+  st = run_lm(ctx, opt, summary);
+  summary->status = st;
+  if (st) return st;
+  if (summary->termination != GLBA_TERM_FAILURE) {
+    st = write_back(ctx, prob->cam, prob->pt, prob->memspace);
+    if (st) { summary->status = st; return st; }
+  }
+  return GLBA_OK;
+}
+
+int glba_linearize(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt, double radius, glba_linearization* out) {
+  if (!ctx || !out || !(radius > 0.0)) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) return st;
+  if ((st = load_problem(ctx, prob))) return st;
+  for (int q = 0; q < PH_COUNT; ++q) ctx->t_phase[q] = 0.0;
+  if ((st = do_linearize(ctx, opt, 1, radius))) return st;
+  if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
+  if ((st = fetch_scal(ctx))) return st;
+  out->cost = ctx->h_scal[S_COST];
+  out->t_linearize_ms = ctx->t_phase[PH_LIN]; out->t_schur_ms = ctx->t_phase[PH_SCHUR];
+  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt; const long n = ctx->n_obs;
+  cudaStream_t s = ctx->stream;
+  const int c = ctx->cur;
+  if ((out->residuals || out->jac_cam || out->jac_pt) && n > 0) {
+    ENSURE(double, ctx->out_a, 2 * (size_t)n); ENSURE(double, ctx->out_b, 12 * (size_t)n); ENSURE(double, ctx->out_c, 6 * (size_t)n);
+    LAUNCH(k_expand, cdiv(n, 256), 256, n, (const int*)ctx->pm_cam.as<int>(), (const double2*)ctx->pm_uv.as<double2>(),
+           ctx->sorted_input ? (const int*)nullptr : (const int*)ctx->pm2orig.as<int>(), (const double4*)ctx->rec_pm.as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), ctx->K, ctx->out_a.as<double>(), ctx->out_b.as<double>(), ctx->out_c.as<double>());
+    if (out->residuals) CU(cudaMemcpyAsync(out->residuals, ctx->out_a.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, s));
+    if (out->jac_cam) CU(cudaMemcpyAsync(out->jac_cam, ctx->out_b.p, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, s));
+    if (out->jac_pt) CU(cudaMemcpyAsync(out->jac_pt, ctx->out_c.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  if ((out->hess_pt || out->grad_pt) && n_pt > 0) {
+    ENSURE(double, ctx->out_b, 9 * (size_t)n_pt); ENSURE(double, ctx->out_c, 3 * (size_t)n_pt);
+    LAUNCH(k_unpack_pointblocks, cdiv(n_pt, 256), 256, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
+           ctx->out_b.as<double>(), ctx->out_c.as<double>());
+    if (out->hess_pt) CU(cudaMemcpyAsync(out->hess_pt, ctx->out_b.p, sizeof(double) * 9 * n_pt, cudaMemcpyDeviceToHost, s));
+    if (out->grad_pt) CU(cudaMemcpyAsync(out->grad_pt, ctx->out_c.p, sizeof(double) * 3 * n_pt, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  if (n_cam > 0) {
+    if (out->grad_cam) CU(cudaMemcpyAsync(out->grad_cam, ctx->gc.p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToHost, s));
+    if (out->hess_cam) CU(cudaMemcpyAsync(out->hess_cam, ctx->Bc.p, sizeof(double) * 36 * n_cam, cudaMemcpyDeviceToHost, s));
+    if (ctx->n_free_cam > 0) {
+      if (out->schur_diag) CU(cudaMemcpyAsync(out->schur_diag, ctx->Md.p, sizeof(double) * 36 * n_cam, cudaMemcpyDeviceToHost, s));
+      if (out->schur_rhs) CU(cudaMemcpyAsync(out->schur_rhs, ctx->rhs.p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToHost, s));
+    } else {
+      if (out->schur_diag) std::memset(out->schur_diag, 0, sizeof(double) * 36 * n_cam);
+      if (out->schur_rhs) std::memset(out->schur_rhs, 0, sizeof(double) * 6 * n_cam);
+    }
+    CU(cudaStreamSynchronize(s));
+  }
+  return GLBA_OK;
+}
+
+int glba_pose_only_batch(glba_ctx* ctx, int32_t batch, double* cams, const int32_t* offset, const double* X, const double* uv,
+                         double fx, double fy, double cx, double cy, const glba_options* opt, uint8_t* usable, int32_t* n_iters,
+                         double* final_cost) {
+  if (!ctx || batch <= 0 || !cams || !offset || !X || !uv) return fail(ctx, GLBA_E_INVALID_ARG, "pose_only_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) return st;
+  const long n = offset[batch];
+  for (int b = 0; b < batch; ++b) if (offset[b + 1] <= offset[b]) return fail(ctx, GLBA_E_INVALID_ARG, "pose_only_batch: empty problem %d", b);
+  cudaStream_t s = ctx->stream;
+  ENSURE(double, ctx->in_cam, 6 * (size_t)batch); ENSURE(int, ctx->in_ocam, (size_t)batch + 1); ENSURE(double, ctx->in_pt, 3 * (size_t)n);
+  ENSURE(double, ctx->in_u, 2 * (size_t)n); ENSURE(uint8_t, ctx->in_cfix, batch); ENSURE(int, ctx->in_opt, 3 * (size_t)batch); ENSURE(double, ctx->in_v, batch);
+  CU(cudaMemcpyAsync(ctx->in_cam.p, cams, sizeof(double) * 6 * batch, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->in_ocam.p, offset, sizeof(int) * ((size_t)batch + 1), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->in_pt.p, X, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->in_u.p, uv, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
+  PoseTrace tr{}; tr.cost = nullptr; tr.stride = 0;
+  LAUNCH(k_pose_only, batch, NT_POSE, batch, ctx->in_cam.as<double>(), (const int*)ctx->in_ocam.as<int>(), (const double*)ctx->in_pt.as<double>(),
+         (const double*)ctx->in_u.as<double>(), Intr{fx, fy, cx, cy}, pose_opts(opt), ctx->in_cfix.as<uint8_t>(), ctx->in_opt.as<int>(),
+         ctx->in_v.as<double>(), ctx->in_opt.as<int>() + batch, tr);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(cams, ctx->in_cam.p, sizeof(double) * 6 * batch, cudaMemcpyDeviceToHost, s));
+  if (usable) CU(cudaMemcpyAsync(usable, ctx->in_cfix.p, batch, cudaMemcpyDeviceToHost, s));
+  if (n_iters) CU(cudaMemcpyAsync(n_iters, ctx->in_opt.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+  if (final_cost) CU(cudaMemcpyAsync(final_cost, ctx->in_v.p, sizeof(double) * batch, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return GLBA_OK;
+}
+
+int glba_pose_only(glba_ctx* ctx, double* cam, int32_t n, const double* X, const double* uv, double fx, double fy, double cx, double cy,
+                   const glba_options* opt, glba_summary* summary) {
+  if (!ctx || !cam || n <= 0 || !X || !uv) return fail(ctx, GLBA_E_INVALID_ARG, "pose_only: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) return st;
+  if (summary) std::memset(summary, 0, sizeof(*summary));
+  cudaStream_t s = ctx->stream;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int NI = GLBA_MAX_ITERS + 1;
+  ENSURE(double, ctx->in_cam, 6); ENSURE(int, ctx->in_ocam, 2); ENSURE(double, ctx->in_pt, 3 * (size_t)n); ENSURE(double, ctx->in_u, 2 * (size_t)n);
+  ENSURE(uint8_t, ctx->in_cfix, 1); ENSURE(int, ctx->in_opt, 3); ENSURE(double, ctx->in_v, 1);
+  ENSURE(double, ctx->out_a, 6 * (size_t)NI); ENSURE(uint8_t, ctx->out_b, NI);
+  const int off[2] = {0, n};
+  CU(cudaMemcpyAsync(ctx->in_cam.p, cam, sizeof(double) * 6, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->in_ocam.p, off, sizeof(off), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->in_pt.p, X, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->in_u.p, uv, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(ctx->out_a.p, 0, sizeof(double) * 6 * NI, s));
+  CU(cudaMemsetAsync(ctx->out_b.p, 0, NI, s));
+  double* t = ctx->out_a.as<double>();
+  PoseTrace tr{t, t + NI, t + 2 * NI, t + 3 * NI, t + 4 * NI, t + 5 * NI, ctx->out_b.as<uint8_t>(), NI};
+  cudaEventRecord(e0, s);
+  LAUNCH(k_pose_only, 1, NT_POSE, 1, ctx->in_cam.as<double>(), (const int*)ctx->in_ocam.as<int>(), (const double*)ctx->in_pt.as<double>(),
+         (const double*)ctx->in_u.as<double>(), Intr{fx, fy, cx, cy}, pose_opts(opt), ctx->in_cfix.as<uint8_t>(), ctx->in_opt.as<int>(),
+         ctx->in_v.as<double>(), ctx->in_opt.as<int>() + 1, tr);
+  cudaEventRecord(e1, s);
+  CU(cudaGetLastError());
+  double out_cam[6]; uint8_t usable = 0; int meta[3] = {0, 0, 0}; double fcost = 0;
+  CU(cudaMemcpyAsync(out_cam, ctx->in_cam.p, sizeof(out_cam), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&usable, ctx->in_cfix.p, 1, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(meta, ctx->in_opt.p, sizeof(meta), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&fcost, ctx->in_v.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  std::vector<double> trace(6 * (size_t)NI); std::vector<uint8_t> acc(NI);
+  if (summary) {
+    CU(cudaMemcpyAsync(trace.data(), ctx->out_a.p, sizeof(double) * 6 * NI, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(acc.data(), ctx->out_b.p, NI, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (summary) {
+    summary->n_iters = meta[0]; summary->termination = meta[1]; summary->stop_reason = meta[2];
+    std::memcpy(summary->cost, &trace[0], sizeof(double) * NI); std::memcpy(summary->cost_candidate, &trace[NI], sizeof(double) * NI);
+    std::memcpy(summary->radius, &trace[2 * (size_t)NI], sizeof(double) * NI); std::memcpy(summary->step_norm, &trace[3 * (size_t)NI], sizeof(double) * NI);
+    std::memcpy(summary->relative_decrease, &trace[4 * (size_t)NI], sizeof(double) * NI); std::memcpy(summary->gradient_max_norm, &trace[5 * (size_t)NI], sizeof(double) * NI);
+    std::memcpy(summary->accepted, acc.data(), NI);
+    for (int i = 1; i <= meta[0] && i < NI; ++i) summary->n_successful += acc[i];
+    summary->n_linearizations = 1 + summary->n_successful;
+    summary->initial_cost = trace[0]; summary->final_cost = fcost; summary->t_total_ms = ms; summary->t_solve_ms = ms;
+    summary->status = (meta[2] == GLBA_STOP_NUMERIC) ? GLBA_E_NUMERIC : GLBA_OK;
+  }
+  if (meta[2] == GLBA_STOP_NUMERIC) return fail(ctx, GLBA_E_NUMERIC, "non-finite residual at the initial pose");
+  if (usable) std::memcpy(cam, out_cam, sizeof(out_cam));
+  return GLBA_OK;
+}
+
+int glba_cull_points(glba_ctx* ctx, const glba_problem* prob, int32_t min_obs, double max_mean_err, uint8_t* bad, double* mean_err) {
+  if (!ctx || !bad) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int st = load_problem(ctx, prob);
+  if (st) return st;
+  glba_options o; glba_default_options(&o);
+  const int n_pt = ctx->n_pt;
+  if (n_pt == 0) return GLBA_OK;
+  ENSURE(uint8_t, ctx->out_b, n_pt); ENSURE(double, ctx->out_c, n_pt);
+  LAUNCH(k_cull, cdiv(n_pt, NT_PM), NT_PM, pm_args(ctx, &o), (const double4*)ctx->pt4[0].as<double4>(), (const double*)ctx->camtab[0].as<double>(),
+         min_obs, max_mean_err, ctx->out_b.as<uint8_t>(), ctx->out_c.as<double>());
+  CU(cudaMemcpyAsync(bad, ctx->out_b.p, n_pt, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mean_err) CU(cudaMemcpyAsync(mean_err, ctx->out_c.p, sizeof(double) * n_pt, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->ev_used = 0;
+  return GLBA_OK;
+}
+
+}  // extern "C"

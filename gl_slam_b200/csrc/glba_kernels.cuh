@@ -1,0 +1,1017 @@
+// glba_kernels.cuh — sm_100a device code of the bundle-adjustment backend (FP64, HBM-bound).
+//
+// Replaces, on the GPU, the arithmetic Ceres performs for slam_core::full_ba (GL-SLAM
+// src/core/slam_core.cpp:799-849): per-observation residual / robust weight / Jacobians
+// (ReprojectionError, :699-733, CauchyLoss :814), Hessian block assembly, Schur complement,
+// PCG on the reduced camera system, back-substitution and candidate cost.
+//
+// Design: the Jacobian is never materialised.  Each observation keeps one 32-byte
+// record (xh, yh, 1/z, w): normalised image coordinates, inverse depth and sqrt(rho').  Every
+// Jacobian block is rebuilt from it and two per-camera 3x3 matrices that live in L1/L2:
+//     J~_p = w P R,   J~_c = J^ T,   J^ = w [Q | -P] (2x6),   T = blockdiag(G, R)
+//     P = 1/z [[fx,0,-fx xh],[0,fy,-fy yh]],  Q = [[fx,0,-fx xh],[0,fy,-fy yh]] [m]x
+//     R = R(-w) (world->camera),  G = J_r(w) (right Jacobian of SO(3); additive angle-axis),
+//     m = (xh,yh,1) + sv x (xh,yh,1)  with sv = w only on Ceres' small-angle branch, else 0.
+// Records exist in two orders: point-major (track-contiguous) for everything reduced per point,
+// camera-major for everything reduced per camera.  Both reductions are fixed-order (no atomics),
+// so results are bit-reproducible run to run.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace glba {
+
+constexpr int CAMTAB = 24;  // doubles per camera: R[9] G[9] c[3] sv[3]
+constexpr int PBLK = 12;    // doubles per point block: Cinv[6] (00,01,02,11,12,22) u0[3] pad[3]  (96 B = 3 sectors)
+constexpr int NT_PM = 128;  // threads per CTA, point-major kernels (one thread per point)
+constexpr int NT_CM = 256;  // threads per CTA, camera-major kernels (one CTA per chunk of one camera)
+constexpr int NT_CAM = 1024;  // threads of the single-CTA camera kernels
+
+// scalar slots (device array `scal`), written by fixed-order reductions
+enum Scal {
+  // [0..8] point-derived sums: allreduced (sum) across ranks when the map is sharded
+  S_COST = 0,     // 1/2 sum rho at the linearisation point
+  S_XN2_P,        // |x|^2 over free points
+  S_BAD,          // non-finite residuals at the linearisation point (count)
+  S_NOTPD_P,      // point blocks that failed LDL'
+  S_COST_C,       // candidate cost
+  S_YN2_P,        // |y_p|^2
+  S_YG_P,         // y_p . g_p
+  S_YLY_P,        // y_p' Lambda_p y_p
+  S_BAD_C,        // non-finite residuals at the candidate
+  // [9] point-derived max: allreduced (max)
+  S_GMAX_P,       // max |g| over free points
+  // [10..15] camera-derived, replicated on every rank
+  S_XN2_C, S_GMAX_C, S_YN2_C, S_YG_C, S_YLY_C, S_NOTPD_C,
+  S_COUNT
+};
+constexpr int NSCAL = 16;
+
+struct Intr { double fx, fy, cx, cy; };
+
+struct LossP { int kind; double a; };
+
+struct CgState {
+  double rz, rz0, pq;
+  int iters, done, max_iters, pad;
+  double tol;
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  // two 16-byte read-only loads; a 32-byte record never straddles a sector
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(double4* p, const double4 v) {
+  double2* q = reinterpret_cast<double2*>(p);
+  q[0] = make_double2(v.x, v.y);
+  q[1] = make_double2(v.z, v.w);
+}
+
+// rho(s): returns 1/2-free rho and sqrt(rho') (Ceres corrector with rho'' <= 0: plain IRLS scaling)
+__device__ __forceinline__ void loss_eval(const LossP L, const double s, double& rho, double& w) {
+  if (L.kind == 2) {  // Cauchy
+    const double b = L.a * L.a;
+    const double sum = 1.0 + s / b;
+    rho = b * log(sum);
+    w = rsqrt(sum);
+  } else if (L.kind == 1) {  // Huber
+    const double b = L.a * L.a;
+    if (s > b) {
+      const double r = sqrt(s);
+      rho = 2.0 * L.a * r - b;
+      w = sqrt(L.a / r);
+    } else { rho = s; w = 1.0; }
+  } else { rho = s; w = 1.0; }
+}
+
+// Residual at (camera table row, point).  Returns the record and the un-weighted residual.
+__device__ __forceinline__ void project_obs(const double* __restrict__ ct, const double X, const double Y,
+                                            const double Z, const Intr K, const double u, const double v,
+                                            double& xh, double& yh, double& iz, double& rx, double& ry) {
+  // plain loads: ct may live in shared memory (pose-only kernel); global callers pass __restrict__ const
+  const double qx = X - ct[18], qy = Y - ct[19], qz = Z - ct[20];
+  const double px = ct[0] * qx + ct[1] * qy + ct[2] * qz;
+  const double py = ct[3] * qx + ct[4] * qy + ct[5] * qz;
+  const double pz = ct[6] * qx + ct[7] * qy + ct[8] * qz;
+  iz = 1.0 / pz;
+  xh = px * iz; yh = py * iz;
+  rx = K.fx * xh + K.cx - u;
+  ry = K.fy * yh + K.cy - v;
+}
+
+// Rows of J^ = w [Q | -P] (2x6) from a record; sv = small-angle vector of the camera (usually 0).
+__device__ __forceinline__ void jhat_rows(const double4 rec, const double sv0, const double sv1, const double sv2,
+                                          const Intr K, double a[6], double b[6]) {
+  const double xh = rec.x, yh = rec.y, iz = rec.z, w = rec.w;
+  const double m0 = xh + (sv1 - sv2 * yh);
+  const double m1 = yh + (sv2 * xh - sv0);
+  const double m2 = 1.0 + (sv0 * yh - sv1 * xh);
+  const double wfx = w * K.fx, wfy = w * K.fy;
+  a[0] = wfx * (xh * m1); a[1] = -wfx * (m2 + xh * m0); a[2] = wfx * m1;
+  b[0] = wfy * (m2 + yh * m1); b[1] = -wfy * (yh * m0); b[2] = -wfy * m0;
+  const double pfx = wfx * iz, pfy = wfy * iz;
+  a[3] = -pfx; a[4] = 0.0; a[5] = pfx * xh;
+  b[3] = 0.0; b[4] = -pfy; b[5] = pfy * yh;
+}
+
+// Rows of J~_p = w P R (2x3) from a record and R (row-major 3x3).
+__device__ __forceinline__ void jp_rows(const double4 rec, const double* R, const Intr K, double ap[3], double bp[3]) {
+  const double pfx = rec.w * rec.z * K.fx, pfy = rec.w * rec.z * K.fy;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ap[c] = pfx * (R[c] - rec.x * R[6 + c]);
+    bp[c] = pfy * (R[3 + c] - rec.y * R[6 + c]);
+  }
+}
+
+// Symmetric 3x3 (00,01,02,11,12,22) positive definite inverse by LDL'.  Returns false if not PD.
+__device__ __forceinline__ bool inv3_sym(const double* C, double* Ci) {
+  const double d0 = C[0];
+  if (!(d0 > 0.0)) return false;
+  const double i0 = 1.0 / d0;
+  const double l10 = C[1] * i0, l20 = C[2] * i0;
+  const double d1 = C[3] - l10 * C[1];
+  if (!(d1 > 0.0)) return false;
+  const double i1 = 1.0 / d1;
+  const double t21 = C[4] - l20 * C[1];
+  const double l21 = t21 * i1;
+  const double d2 = C[5] - l20 * C[2] - l21 * t21;
+  if (!(d2 > 0.0)) return false;
+  const double i2 = 1.0 / d2;
+  // L^-1 = [[1,0,0],[-l10,1,0],[l10 l21 - l20, -l21, 1]];  Ci = L^-T D^-1 L^-1
+  const double m20 = l10 * l21 - l20;
+  Ci[0] = i0 + l10 * l10 * i1 + m20 * m20 * i2;
+  Ci[1] = -l10 * i1 - m20 * l21 * i2;
+  Ci[2] = m20 * i2;
+  Ci[3] = i1 + l21 * l21 * i2;
+  Ci[4] = -l21 * i2;
+  Ci[5] = i2;
+  return true;
+}
+
+// Dense 6x6 SPD inverse by Cholesky (row-major).  Returns false if not PD.
+__device__ inline bool inv6_spd(const double* A, double* Ai) {
+  double L[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) L[i] = 0.0;
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j * 6 + j];
+    for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
+    if (!(d > 0.0)) return false;
+    const double ljj = sqrt(d);
+    L[j * 6 + j] = ljj;
+    const double inv = 1.0 / ljj;
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i * 6 + j];
+      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
+      L[i * 6 + j] = s * inv;
+    }
+  }
+  for (int c = 0; c < 6; ++c) {
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
+      y[i] = s / L[i * 6 + i];
+    }
+    for (int i = 5; i >= 0; --i) {
+      double s = y[i];
+      for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k];
+      y[i] = s / L[i * 6 + i];
+    }
+    for (int i = 0; i < 6; ++i) Ai[i * 6 + c] = y[i];
+  }
+  return true;
+}
+
+// Fixed-order CTA reduction: every value goes through the same xor-butterfly and the same
+// warp-by-warp serial sum, so the result does not depend on scheduling.
+template <int NV, int NT, bool IS_MAX = false>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* sm /* NV * NT/32 */, double* out /* NV */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = IS_MAX ? fmax(x, y) : x + y;
+    }
+    if (lane == 0) sm[wid * NV + i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double x = sm[threadIdx.x];
+    for (int w = 1; w < NT / 32; ++w) x = IS_MAX ? fmax(x, sm[w * NV + threadIdx.x]) : x + sm[w * NV + threadIdx.x];
+    out[threadIdx.x] = x;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-camera table: R = R(-w) exactly as ceres::AngleAxisRotatePoint rotates (Rodrigues for
+// theta^2 > DBL_EPSILON, I + [v]x otherwise), G = J_r(w), centre, small-angle vector.
+// ---------------------------------------------------------------------------------------------
+__device__ inline void cam_table_row(const double* cam, double* ct) {
+  const double w0 = cam[0], w1 = cam[1], w2 = cam[2];
+  const double v0 = -w0, v1 = -w1, v2 = -w2;
+  const double th2 = v0 * v0 + v1 * v1 + v2 * v2;
+  double R[9], G[9], sv[3];
+  if (th2 > DBL_EPSILON) {
+    const double th = sqrt(th2);
+    double s, c;
+    sincos(th, &s, &c);
+    const double ith = 1.0 / th;
+    const double k0 = v0 * ith, k1 = v1 * ith, k2 = v2 * ith;
+    const double oc = 1.0 - c;
+    R[0] = c + oc * k0 * k0;      R[1] = oc * k0 * k1 - s * k2; R[2] = oc * k0 * k2 + s * k1;
+    R[3] = oc * k1 * k0 + s * k2; R[4] = c + oc * k1 * k1;      R[5] = oc * k1 * k2 - s * k0;
+    R[6] = oc * k2 * k0 - s * k1; R[7] = oc * k2 * k1 + s * k0; R[8] = c + oc * k2 * k2;
+    double a, b;
+    if (th < 1e-2) {
+      a = 0.5 - th2 * (1.0 / 24.0) + th2 * th2 * (1.0 / 720.0);
+      b = 1.0 / 6.0 - th2 * (1.0 / 120.0) + th2 * th2 * (1.0 / 5040.0);
+    } else {
+      a = oc / th2;
+      b = (th - s) / (th2 * th);
+    }
+    // G = I - a [w]x + b [w]x^2,  [w]x^2 = w w' - |w|^2 I
+    G[0] = 1.0 + b * (w0 * w0 - th2); G[1] = a * w2 + b * w0 * w1;      G[2] = -a * w1 + b * w0 * w2;
+    G[3] = -a * w2 + b * w1 * w0;     G[4] = 1.0 + b * (w1 * w1 - th2); G[5] = a * w0 + b * w1 * w2;
+    G[6] = a * w1 + b * w2 * w0;      G[7] = -a * w0 + b * w2 * w1;     G[8] = 1.0 + b * (w2 * w2 - th2);
+    sv[0] = sv[1] = sv[2] = 0.0;
+  } else {
+    R[0] = 1.0; R[1] = -v2; R[2] = v1;
+    R[3] = v2;  R[4] = 1.0; R[5] = -v0;
+    R[6] = -v1; R[7] = v0;  R[8] = 1.0;
+    G[0] = 1.0; G[1] = 0.0; G[2] = 0.0; G[3] = 0.0; G[4] = 1.0; G[5] = 0.0; G[6] = 0.0; G[7] = 0.0; G[8] = 1.0;
+    sv[0] = w0; sv[1] = w1; sv[2] = w2;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { ct[i] = R[i]; ct[9 + i] = G[i]; }
+  ct[18] = cam[3]; ct[19] = cam[4]; ct[20] = cam[5];
+  ct[21] = sv[0]; ct[22] = sv[1]; ct[23] = sv[2];
+}
+
+__global__ void k_cam_prep(const int n_cam, const double* __restrict__ cam, double* __restrict__ camtab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cam) cam_table_row(cam + 6 * i, camtab + (size_t)CAMTAB * i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Damped point block: Cinv = (C + lam/radius)^-1, u0 = Cinv g.  lam = clamp(s^2 h)/s^2 per axis.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool point_block(const double* C6, const double* g3, const double* lam3, const double inv_radius,
+                                            double* blk /* PBLK */) {
+  double Cd[6] = {C6[0] + lam3[0] * inv_radius, C6[1], C6[2], C6[3] + lam3[1] * inv_radius, C6[4],
+                  C6[5] + lam3[2] * inv_radius};
+  double Ci[6];
+  const bool ok = inv3_sym(Cd, Ci);
+  if (!ok) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Ci[i] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) blk[i] = Ci[i];
+  blk[6] = Ci[0] * g3[0] + Ci[1] * g3[1] + Ci[2] * g3[2];
+  blk[7] = Ci[1] * g3[0] + Ci[3] * g3[1] + Ci[4] * g3[2];
+  blk[8] = Ci[2] * g3[0] + Ci[4] * g3[1] + Ci[5] * g3[2];
+  blk[9] = blk[10] = blk[11] = 0.0;
+  return ok;
+}
+
+struct PmArgs {
+  int n_pt;
+  const int* pt_start;          // n_pt+1 (point-major CSR)
+  const int* pm_cam;            // camera of observation k
+  const double2* pm_uv;         // measurement
+  const int* pm2cm;             // position of observation k in camera-major order
+  const uint8_t* pt_free;
+  Intr K;
+  LossP loss;
+};
+
+// K_A + point half of K_B.  One thread per point walks its track: residual, robust weight, record
+// (written in both orders), C_j = sum J~p'J~p, g_j = sum J~p' r~, then the damped inverse.
+// first != 0: this is iteration 0, also fix the Jacobi scaling s = 1/(1+sqrt(h)).
+__global__ void __launch_bounds__(NT_PM)
+k_linearize_pm(const PmArgs A, const double4* __restrict__ pt, const double* __restrict__ camtab,
+               double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw /* 9 SoA */,
+               double4* __restrict__ sp4, double4* __restrict__ lam4, double* __restrict__ pblk, const int first,
+               const int jacobi, const double min_diag, const double max_diag, const double inv_radius,
+               double* __restrict__ part /* [grid][5] */) {
+  __shared__ double sm[5 * NT_PM / 32];
+  __shared__ double smo[5];
+  const int j = blockIdx.x * NT_PM + threadIdx.x;
+  double cost = 0.0, xn2 = 0.0, gmax = 0.0, bad = 0.0, notpd = 0.0;
+  if (j < A.n_pt) {
+    const int b = __ldg(A.pt_start + j), e = __ldg(A.pt_start + j + 1);
+    const double4 X = ldg4(pt + j);
+    double C[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int k = b; k < e; ++k) {
+      const int i = __ldg(A.pm_cam + k);
+      const double2 uv = __ldg(A.pm_uv + k);
+      const double* ct = camtab + (size_t)CAMTAB * i;
+      double xh, yh, iz, rx, ry;
+      project_obs(ct, X.x, X.y, X.z, A.K, uv.x, uv.y, xh, yh, iz, rx, ry);
+      double rho, w;
+      loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+      if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
+      cost += 0.5 * rho;
+      const double4 rec = make_double4(xh, yh, iz, w);
+      st4(rec_pm + k, rec);
+      st4(rec_cm + __ldg(A.pm2cm + k), rec);
+      double R[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) R[q] = __ldg(ct + q);
+      double ap[3], bp[3];
+      jp_rows(rec, R, A.K, ap, bp);
+      const double r0 = w * rx, r1 = w * ry;
+      C[0] += ap[0] * ap[0] + bp[0] * bp[0]; C[1] += ap[0] * ap[1] + bp[0] * bp[1]; C[2] += ap[0] * ap[2] + bp[0] * bp[2];
+      C[3] += ap[1] * ap[1] + bp[1] * bp[1]; C[4] += ap[1] * ap[2] + bp[1] * bp[2]; C[5] += ap[2] * ap[2] + bp[2] * bp[2];
+      g[0] += ap[0] * r0 + bp[0] * r1; g[1] += ap[1] * r0 + bp[1] * r1; g[2] += ap[2] * r0 + bp[2] * r1;
+    }
+    const bool free_pt = A.pt_free[j] != 0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Craw[(size_t)q * A.n_pt + j] = C[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) Craw[(size_t)(6 + q) * A.n_pt + j] = g[q];
+    double blk[PBLK];
+    if (free_pt) {
+      const double h[3] = {C[0], C[3], C[5]};
+      double s[3], lam[3];
+      if (first) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s[q] = jacobi ? 1.0 / (1.0 + sqrt(h[q])) : 1.0;
+        st4(sp4 + j, make_double4(s[0], s[1], s[2], 0.0));
+      } else {
+        const double4 s4 = ldg4(sp4 + j);
+        s[0] = s4.x; s[1] = s4.y; s[2] = s4.z;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const double s2 = s[q] * s[q];
+        lam[q] = fmin(fmax(s2 * h[q], min_diag), max_diag) / s2;
+      }
+      st4(lam4 + j, make_double4(lam[0], lam[1], lam[2], 0.0));
+      if (!point_block(C, g, lam, inv_radius, blk)) notpd += 1.0;
+      xn2 = X.x * X.x + X.y * X.y + X.z * X.z;
+      gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+    } else {
+#pragma unroll
+      for (int q = 0; q < PBLK; ++q) blk[q] = 0.0;
+      if (first) st4(sp4 + j, make_double4(1.0, 1.0, 1.0, 0.0));
+      st4(lam4 + j, make_double4(0.0, 0.0, 0.0, 0.0));
+    }
+    double* pb = pblk + (size_t)PBLK * j;
+#pragma unroll
+    for (int q = 0; q < PBLK; q += 2) *reinterpret_cast<double2*>(pb + q) = make_double2(blk[q], blk[q + 1]);
+  }
+  double v[4] = {cost, xn2, bad, notpd};
+  block_reduce<4, NT_PM>(v, sm, smo);
+  double m[1] = {gmax};
+  __shared__ double smm[NT_PM / 32];
+  __shared__ double smmo[1];
+  block_reduce<1, NT_PM, true>(m, smm, smmo);
+  if (threadIdx.x == 0) {
+    double* p = part + (size_t)5 * blockIdx.x;
+    p[0] = smo[0]; p[1] = smo[1]; p[2] = smo[2]; p[3] = smo[3]; p[4] = smmo[0];
+  }
+}
+
+// Re-damp the point blocks after the radius changed (rejected step): same C, g, lam.
+__global__ void __launch_bounds__(NT_PM)
+k_point_damp(const int n_pt, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw,
+             const double4* __restrict__ lam4, double* __restrict__ pblk, const double inv_radius,
+             double* __restrict__ part /* [grid][1] notpd */) {
+  __shared__ double sm[NT_PM / 32];
+  __shared__ double smo[1];
+  const int j = blockIdx.x * NT_PM + threadIdx.x;
+  double notpd = 0.0;
+  if (j < n_pt && pt_free[j]) {
+    double C[6], g[3];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) C[q] = Craw[(size_t)q * n_pt + j];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g[q] = Craw[(size_t)(6 + q) * n_pt + j];
+    const double4 l4 = ldg4(lam4 + j);
+    const double lam[3] = {l4.x, l4.y, l4.z};
+    double blk[PBLK];
+    if (!point_block(C, g, lam, inv_radius, blk)) notpd = 1.0;
+    double* pb = pblk + (size_t)PBLK * j;
+#pragma unroll
+    for (int q = 0; q < PBLK; q += 2) *reinterpret_cast<double2*>(pb + q) = make_double2(blk[q], blk[q + 1]);
+  }
+  double v[1] = {notpd};
+  block_reduce<1, NT_PM>(v, sm, smo);
+  if (threadIdx.x == 0) part[blockIdx.x] = smo[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Camera-major passes.  One CTA per chunk = (camera, [begin,end)) of the camera-major order.
+// ---------------------------------------------------------------------------------------------
+struct CmArgs {
+  const int* chunk_cam;
+  const int* chunk_begin;
+  const int* chunk_end;
+  const int* cm_pt;
+  const double2* cm_uv;
+  const uint8_t* cam_free;
+  Intr K;
+};
+
+// Camera half of K_B: A_i = sum J^'J^ (21 upper entries), ghat_i = sum J^' r~ (6), per chunk.
+__global__ void __launch_bounds__(NT_CM)
+k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
+               double* __restrict__ part /* [n_chunks][27] */) {
+  __shared__ double sm[27 * NT_CM / 32];
+  __shared__ double smo[27];
+  const int ch = blockIdx.x;
+  const int cam = A.chunk_cam[ch];
+  double acc[27];
+#pragma unroll
+  for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+  if (A.cam_free[cam]) {   // uniform per CTA
+    const double* ct = camtab + (size_t)CAMTAB * cam;
+    const double sv0 = ct[21], sv1 = ct[22], sv2 = ct[23];
+    const int b = A.chunk_begin[ch], e = A.chunk_end[ch];
+    for (int k = b + threadIdx.x; k < e; k += NT_CM) {
+      const double4 rec = ldg4(rec_cm + k);
+      const double2 uv = __ldg(A.cm_uv + k);
+      double a[6], bb[6];
+      jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+      const double r0 = rec.w * (A.K.fx * rec.x + A.K.cx - uv.x);
+      const double r1 = rec.w * (A.K.fy * rec.y + A.K.cy - uv.y);
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) acc[q++] += a[r] * a[c] + bb[r] * bb[c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[21 + r] += a[r] * r0 + bb[r] * r1;
+    }
+  }
+  block_reduce<27, NT_CM>(acc, sm, smo);
+  if (threadIdx.x < 27) part[(size_t)27 * ch + threadIdx.x] = smo[threadIdx.x];
+}
+
+// Schur half: for every observation of the camera, E = J~p Cinv J~p' (2x2) and f = J~p u0 (2):
+//   Mhat_i = sum J^' E J^ (21),  rhat_i = sum J^' f (6).
+__global__ void __launch_bounds__(NT_CM)
+k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
+           const double* __restrict__ pblk, double* __restrict__ part /* [n_chunks][27] */) {
+  __shared__ double sm[27 * NT_CM / 32];
+  __shared__ double smo[27];
+  const int ch = blockIdx.x;
+  const int cam = A.chunk_cam[ch];
+  double acc[27];
+#pragma unroll
+  for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+  if (A.cam_free[cam]) {
+    const double* ct = camtab + (size_t)CAMTAB * cam;
+    double R[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) R[q] = ct[q];
+    const double sv0 = ct[21], sv1 = ct[22], sv2 = ct[23];
+    const int b = A.chunk_begin[ch], e = A.chunk_end[ch];
+    for (int k = b + threadIdx.x; k < e; k += NT_CM) {
+      const double4 rec = ldg4(rec_cm + k);
+      const int j = __ldg(A.cm_pt + k);
+      const double2* pb = reinterpret_cast<const double2*>(pblk + (size_t)PBLK * j);
+      const double2 c01 = __ldg(pb), c23 = __ldg(pb + 1), c45 = __ldg(pb + 2), u01 = __ldg(pb + 3), u2_ = __ldg(pb + 4);
+      double ap[3], bp[3];
+      jp_rows(rec, R, A.K, ap, bp);
+      // t = Cinv ap, s = Cinv bp   (Cinv = [c01.x c01.y c23.x; . c23.y c45.x; . . c45.y])
+      const double ta0 = c01.x * ap[0] + c01.y * ap[1] + c23.x * ap[2];
+      const double ta1 = c01.y * ap[0] + c23.y * ap[1] + c45.x * ap[2];
+      const double ta2 = c23.x * ap[0] + c45.x * ap[1] + c45.y * ap[2];
+      const double tb0 = c01.x * bp[0] + c01.y * bp[1] + c23.x * bp[2];
+      const double tb1 = c01.y * bp[0] + c23.y * bp[1] + c45.x * bp[2];
+      const double tb2 = c23.x * bp[0] + c45.x * bp[1] + c45.y * bp[2];
+      const double E00 = ap[0] * ta0 + ap[1] * ta1 + ap[2] * ta2;
+      const double E01 = ap[0] * tb0 + ap[1] * tb1 + ap[2] * tb2;
+      const double E11 = bp[0] * tb0 + bp[1] * tb1 + bp[2] * tb2;
+      const double f0 = ap[0] * u01.x + ap[1] * u01.y + ap[2] * u2_.x;
+      const double f1 = bp[0] * u01.x + bp[1] * u01.y + bp[2] * u2_.x;
+      double a[6], bb[6];
+      jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+      // J^' E J^ = (E00 a + E01 b) a' + (E01 a + E11 b) b'
+      double ea[6], eb[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { ea[r] = E00 * a[r] + E01 * bb[r]; eb[r] = E01 * a[r] + E11 * bb[r]; }
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) acc[q++] += ea[r] * a[c] + eb[r] * bb[c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[21 + r] += a[r] * f0 + bb[r] * f1;
+    }
+  }
+  block_reduce<27, NT_CM>(acc, sm, smo);
+  if (threadIdx.x < 27) part[(size_t)27 * ch + threadIdx.x] = smo[threadIdx.x];
+}
+
+// Second half of the implicit product: yhat_i = sum_j J^' (J~p u_j), u_j from the point-major pass.
+__global__ void __launch_bounds__(NT_CM)
+k_spmv_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
+          const double4* __restrict__ u4, const CgState* __restrict__ cg, double* __restrict__ part /* [n_chunks][6] */) {
+  __shared__ double sm[6 * NT_CM / 32];
+  __shared__ double smo[6];
+  if (cg && cg->done) return;
+  const int ch = blockIdx.x;
+  const int cam = A.chunk_cam[ch];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  if (A.cam_free[cam]) {
+    const double* ct = camtab + (size_t)CAMTAB * cam;
+    double R[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) R[q] = ct[q];
+    const double sv0 = ct[21], sv1 = ct[22], sv2 = ct[23];
+    const int b = A.chunk_begin[ch], e = A.chunk_end[ch];
+    for (int k = b + threadIdx.x; k < e; k += NT_CM) {
+      const double4 rec = ldg4(rec_cm + k);
+      const int j = __ldg(A.cm_pt + k);
+      const double4 u = ldg4(u4 + j);
+      double ap[3], bp[3];
+      jp_rows(rec, R, A.K, ap, bp);
+      const double f0 = ap[0] * u.x + ap[1] * u.y + ap[2] * u.z;
+      const double f1 = bp[0] * u.x + bp[1] * u.y + bp[2] * u.z;
+      double a[6], bb[6];
+      jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[r] += a[r] * f0 + bb[r] * f1;
+    }
+  }
+  block_reduce<6, NT_CM>(acc, sm, smo);
+  if (threadIdx.x < 6) part[(size_t)6 * ch + threadIdx.x] = smo[threadIdx.x];
+}
+
+// Sum the chunk partials of every camera in chunk order (fixed): acc[cam][NV].
+template <int NV>
+__global__ void k_chunk_sum(const int n_cam, const int* __restrict__ cam_chunk_start, const double* __restrict__ part,
+                            double* __restrict__ acc, const CgState* __restrict__ cg) {
+  if (cg && cg->done) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cam * NV) return;
+  const int cam = t / NV, q = t - cam * NV;
+  double s = 0.0;
+  for (int ch = cam_chunk_start[cam]; ch < cam_chunk_start[cam + 1]; ++ch) s += part[(size_t)NV * ch + q];
+  acc[t] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Point-major half of the implicit product / back-substitution.
+//   t_j = sum_i J~p' (J~c x_i) = sum_i R_i' (w P)' (J^ . xg_i),   xg_i = T_i x_i  (per-camera table)
+//   MODE 0 (SpMV):    u_j = Cinv_j t_j
+//   MODE 1 (backsub): y_j = u0_j - Cinv_j t_j;  X+ = X - y_j;  then candidate cost over the track.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(NT_PM)
+k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* __restrict__ camtab,
+             const double* __restrict__ xg /* [n_cam][6] */, const double* __restrict__ pblk,
+             double4* __restrict__ u4, const CgState* __restrict__ cg,
+             // MODE 1 only:
+             const double4* __restrict__ pt, double4* __restrict__ pt_c, const double* __restrict__ camtab_c,
+             const double* __restrict__ Craw, const double4* __restrict__ lam4, const double inv_radius,
+             double* __restrict__ part /* [grid][5] */) {
+  if (MODE == 0 && cg && cg->done) return;
+  const int j = blockIdx.x * NT_PM + threadIdx.x;
+  double cost_c = 0.0, yn2 = 0.0, yg = 0.0, yly = 0.0, bad = 0.0;
+  if (j < A.n_pt) {
+    const int b = __ldg(A.pt_start + j), e = __ldg(A.pt_start + j + 1);
+    const bool free_pt = A.pt_free[j] != 0;
+    double t0 = 0, t1 = 0, t2 = 0;
+    if (free_pt) {
+      for (int k = b; k < e; ++k) {
+        const int i = __ldg(A.pm_cam + k);
+        const double4 rec = ldg4(rec_pm + k);
+        const double* ct = camtab + (size_t)CAMTAB * i;
+        const double* x = xg + 6 * (size_t)i;
+        double a[6], bb[6];
+        jhat_rows(rec, __ldg(ct + 21), __ldg(ct + 22), __ldg(ct + 23), A.K, a, bb);
+        double al0 = 0, al1 = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { const double xv = __ldg(x + r); al0 += a[r] * xv; al1 += bb[r] * xv; }
+        double R[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) R[q] = __ldg(ct + q);
+        double ap[3], bp[3];
+        jp_rows(rec, R, A.K, ap, bp);
+        t0 += ap[0] * al0 + bp[0] * al1; t1 += ap[1] * al0 + bp[1] * al1; t2 += ap[2] * al0 + bp[2] * al1;
+      }
+    }
+    const double2* pb = reinterpret_cast<const double2*>(pblk + (size_t)PBLK * j);
+    const double2 c01 = __ldg(pb), c23 = __ldg(pb + 1), c45 = __ldg(pb + 2);
+    const double v0 = c01.x * t0 + c01.y * t1 + c23.x * t2;
+    const double v1 = c01.y * t0 + c23.y * t1 + c45.x * t2;
+    const double v2 = c23.x * t0 + c45.x * t1 + c45.y * t2;
+    if (MODE == 0) {
+      st4(u4 + j, make_double4(v0, v1, v2, 0.0));
+    } else {
+      const double2 u01 = __ldg(pb + 3), u2_ = __ldg(pb + 4);
+      const double y0 = u01.x - v0, y1 = u01.y - v1, y2 = u2_.x - v2;
+      const double4 X = ldg4(pt + j);
+      const double4 Xc = make_double4(X.x - y0, X.y - y1, X.z - y2, 0.0);
+      st4(pt_c + j, Xc);
+      if (free_pt) {
+        const double4 l4 = ldg4(lam4 + j);
+        yn2 = y0 * y0 + y1 * y1 + y2 * y2;
+        yg = y0 * Craw[(size_t)6 * A.n_pt + j] + y1 * Craw[(size_t)7 * A.n_pt + j] + y2 * Craw[(size_t)8 * A.n_pt + j];
+        yly = (l4.x * y0 * y0 + l4.y * y1 * y1 + l4.z * y2 * y2) * inv_radius;
+      }
+      for (int k = b; k < e; ++k) {
+        const int i = __ldg(A.pm_cam + k);
+        const double2 uv = __ldg(A.pm_uv + k);
+        double xh, yh, iz, rx, ry;
+        project_obs(camtab_c + (size_t)CAMTAB * i, Xc.x, Xc.y, Xc.z, A.K, uv.x, uv.y, xh, yh, iz, rx, ry);
+        double rho, w;
+        loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+        if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
+        cost_c += 0.5 * rho;
+      }
+    }
+  }
+  if (MODE == 1) {
+    __shared__ double sm[5 * NT_PM / 32];
+    __shared__ double smo[5];
+    double v[5] = {cost_c, yn2, yg, yly, bad};
+    block_reduce<5, NT_PM>(v, sm, smo);
+    if (threadIdx.x < 5) part[(size_t)5 * blockIdx.x + threadIdx.x] = smo[threadIdx.x];
+  }
+}
+
+// Cost only at (camtab, pt): used for fixed-cost checks and by glba_cull (no records written).
+// ---------------------------------------------------------------------------------------------
+// Final fixed-order reduction of per-CTA partials: out[slot[q]] = sum/max over rows of part[:, q].
+// ---------------------------------------------------------------------------------------------
+struct ReduceMap { int n; int slot[8]; int is_max[8]; };
+
+__global__ void __launch_bounds__(NT_CAM)
+k_reduce_partials(const int rows, const int nv, const double* __restrict__ part, const ReduceMap M, double* __restrict__ scal) {
+  __shared__ double sm[NT_CAM / 32];
+  __shared__ double smo[1];
+  for (int q = 0; q < nv; ++q) {
+    const bool is_max = M.is_max[q] != 0;
+    double acc = 0.0;   // all reduced quantities are >= 0, so 0 is neutral for max as well
+    for (int r = threadIdx.x; r < rows; r += NT_CAM) {
+      const double x = part[(size_t)nv * r + q];
+      acc = is_max ? fmax(acc, x) : acc + x;
+    }
+    double v[1] = {acc};
+    if (is_max) block_reduce<1, NT_CAM, true>(v, sm, smo); else block_reduce<1, NT_CAM, false>(v, sm, smo);
+    if (threadIdx.x == 0) scal[M.slot[q]] = smo[0];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-CTA camera kernels (camera-sized vectors: <= 10^4 x 6 doubles).
+// ---------------------------------------------------------------------------------------------
+// upper-triangular index of (r,c), r<=c, in the 21-entry packing used above
+__device__ __forceinline__ int tri(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
+
+// B_i = T' A T, g_i = T' ghat from acc27; Jacobi scale (iteration 0), lam_c = clamp(s^2 h)/s^2.
+__global__ void __launch_bounds__(NT_CAM)
+k_cam_lin_finalize(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam,
+                   const double* __restrict__ camtab, const double* __restrict__ acc27, double* __restrict__ Bc /* 36 */,
+                   double* __restrict__ gc /* 6 */, double* __restrict__ sc /* 6 */, double* __restrict__ lamc /* 6 */,
+                   const int first, const int jacobi, const double min_diag, const double max_diag, double* __restrict__ scal) {
+  __shared__ double sm[2 * NT_CAM / 32];
+  __shared__ double smo[2];
+  double xn2 = 0.0, gmax = 0.0;
+  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
+    double* B = Bc + (size_t)36 * i;
+    if (!cam_free[i]) {
+      for (int q = 0; q < 36; ++q) B[q] = 0.0;
+      for (int q = 0; q < 6; ++q) { gc[6 * i + q] = 0.0; lamc[6 * i + q] = 0.0; if (first) sc[6 * i + q] = 1.0; }
+      continue;
+    }
+    const double* a = acc27 + (size_t)27 * i;
+    const double* ct = camtab + (size_t)CAMTAB * i;
+    // T = blockdiag(G, R): column block c of (A T) etc.  Work with full 6x6 for clarity.
+    double Af[36], T[36], AT[36];
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Af[r * 6 + c] = (r <= c) ? a[tri(r, c)] : a[tri(c, r)];
+    for (int q = 0; q < 36; ++q) T[q] = 0.0;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { T[r * 6 + c] = ct[9 + r * 3 + c]; T[(3 + r) * 6 + 3 + c] = ct[r * 3 + c]; }
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += Af[r * 6 + k] * T[k * 6 + c]; AT[r * 6 + c] = s; }
+    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) {
+      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * AT[k * 6 + c];
+      B[r * 6 + c] = s; B[c * 6 + r] = s; }
+    for (int r = 0; r < 6; ++r) {
+      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * a[21 + k];
+      gc[6 * i + r] = s; gmax = fmax(gmax, fabs(s));
+      const double h = B[r * 7];
+      double sv;
+      if (first) { sv = jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0; sc[6 * i + r] = sv; } else sv = sc[6 * i + r];
+      const double s2 = sv * sv;
+      lamc[6 * i + r] = fmin(fmax(s2 * h, min_diag), max_diag) / s2;
+      xn2 += cam[6 * i + r] * cam[6 * i + r];
+    }
+  }
+  double v[1] = {xn2};
+  block_reduce<1, NT_CAM>(v, sm, smo);
+  if (threadIdx.x == 0) scal[S_XN2_C] = smo[0];
+  double m[1] = {gmax};
+  block_reduce<1, NT_CAM, true>(m, sm, smo);
+  if (threadIdx.x == 0) scal[S_GMAX_C] = smo[0];
+}
+
+// M_i = B_i + lam_c/radius - T' Mhat T (block-Jacobi preconditioner = diagonal block of S),
+// rhs_i = g_i - T' rhat; Minv_i by Cholesky.  Then starts PCG: x=0, r=rhs, z=Minv r, p=z.
+__global__ void __launch_bounds__(NT_CAM)
+k_cam_schur_finalize(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab,
+                     const double* __restrict__ acc27, const double* __restrict__ Bc, const double* __restrict__ gc,
+                     const double* __restrict__ lamc, const double inv_radius, double* __restrict__ Md /* 36: S diag */,
+                     double* __restrict__ Minv, double* __restrict__ rhs, double* __restrict__ scal) {
+  __shared__ double sm[NT_CAM / 32];
+  __shared__ double smo[1];
+  double notpd = 0.0;
+  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
+    double* M = Md + (size_t)36 * i; double* Mi = Minv + (size_t)36 * i;
+    if (!cam_free[i]) {
+      for (int q = 0; q < 36; ++q) { M[q] = 0.0; Mi[q] = 0.0; }
+      for (int q = 0; q < 6; ++q) rhs[6 * i + q] = 0.0;
+      continue;
+    }
+    const double* a = acc27 + (size_t)27 * i;
+    const double* ct = camtab + (size_t)CAMTAB * i;
+    double Af[36], T[36], AT[36], Ml[36];
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Af[r * 6 + c] = (r <= c) ? a[tri(r, c)] : a[tri(c, r)];
+    for (int q = 0; q < 36; ++q) T[q] = 0.0;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { T[r * 6 + c] = ct[9 + r * 3 + c]; T[(3 + r) * 6 + 3 + c] = ct[r * 3 + c]; }
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += Af[r * 6 + k] * T[k * 6 + c]; AT[r * 6 + c] = s; }
+    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) {
+      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * AT[k * 6 + c];
+      double v = Bc[(size_t)36 * i + r * 6 + c] - s;
+      if (r == c) v += lamc[6 * i + r] * inv_radius;
+      Ml[r * 6 + c] = v; Ml[c * 6 + r] = v; }
+    for (int q = 0; q < 36; ++q) M[q] = Ml[q];
+    double Il[36];
+    if (!inv6_spd(Ml, Il)) { notpd += 1.0; for (int q = 0; q < 36; ++q) Il[q] = 0.0; }
+    for (int q = 0; q < 36; ++q) Mi[q] = Il[q];
+    for (int r = 0; r < 6; ++r) {
+      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * a[21 + k];
+      rhs[6 * i + r] = gc[6 * i + r] - s;
+    }
+  }
+  double v[1] = {notpd};
+  block_reduce<1, NT_CAM>(v, sm, smo);
+  if (threadIdx.x == 0) scal[S_NOTPD_C] = smo[0];
+}
+
+// xg_i = T_i x_i = (G x_w, R x_t): the per-camera 6-vector the point passes gather.
+__device__ __forceinline__ void apply_T(const double* ct, const double* x, double* out) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    out[r] = ct[9 + r * 3] * x[0] + ct[9 + r * 3 + 1] * x[1] + ct[9 + r * 3 + 2] * x[2];
+    out[3 + r] = ct[r * 3] * x[3] + ct[r * 3 + 1] * x[4] + ct[r * 3 + 2] * x[5];
+  }
+}
+__device__ __forceinline__ void apply_Tt(const double* ct, const double* y, double* out) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    out[r] = ct[9 + r] * y[0] + ct[9 + 3 + r] * y[1] + ct[9 + 6 + r] * y[2];
+    out[3 + r] = ct[r] * y[3] + ct[3 + r] * y[4] + ct[6 + r] * y[5];
+  }
+}
+
+__global__ void __launch_bounds__(NT_CAM)
+k_cg_init(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ Minv, const double* __restrict__ rhs,
+          double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double* __restrict__ pg,
+          CgState* __restrict__ cg, const double tol, const int max_iters) {
+  __shared__ double sm[NT_CAM / 32];
+  __shared__ double smo[1];
+  double rz = 0.0;
+  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
+    double rr[6], z[6];
+    for (int q = 0; q < 6; ++q) { rr[q] = rhs[6 * i + q]; x[6 * i + q] = 0.0; r[6 * i + q] = rr[q]; }
+    const double* Mi = Minv + (size_t)36 * i;
+    for (int a = 0; a < 6; ++a) { double s = 0; for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c]; z[a] = s; rz += s * rr[a]; p[6 * i + a] = s; }
+    double t[6];
+    apply_T(camtab + (size_t)CAMTAB * i, z, t);
+    for (int q = 0; q < 6; ++q) pg[6 * i + q] = t[q];
+  }
+  double v[1] = {rz};
+  block_reduce<1, NT_CAM>(v, sm, smo);
+  if (threadIdx.x == 0) {
+    cg->rz = smo[0]; cg->rz0 = smo[0]; cg->pq = 0.0; cg->iters = 0; cg->max_iters = max_iters; cg->tol = tol;
+    cg->done = (smo[0] > 0.0) ? 0 : 1;
+  }
+}
+
+// q_i = (B_i + lam/radius) p_i - T_i' yhat_i ; then the PCG update (alpha, x, r, z, beta, p, pg).
+__global__ void __launch_bounds__(NT_CAM)
+k_cg_update(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab,
+            const double* __restrict__ Bc, const double* __restrict__ lamc, const double inv_radius,
+            const double* __restrict__ Minv, const double* __restrict__ yhat /* [n_cam][6] */, double* __restrict__ x,
+            double* __restrict__ r, double* __restrict__ p, double* __restrict__ q, double* __restrict__ pg,
+            CgState* __restrict__ cg) {
+  __shared__ double sm[NT_CAM / 32];
+  __shared__ double smo[1];
+  __shared__ double s_alpha, s_beta, s_pq;
+  if (cg->done) return;
+  double pq = 0.0;
+  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
+    if (!cam_free[i]) { for (int a = 0; a < 6; ++a) q[6 * i + a] = 0.0; continue; }
+    double pi[6], ty[6];
+    for (int a = 0; a < 6; ++a) pi[a] = p[6 * i + a];
+    apply_Tt(camtab + (size_t)CAMTAB * i, yhat + 6 * (size_t)i, ty);
+    const double* B = Bc + (size_t)36 * i;
+    for (int a = 0; a < 6; ++a) {
+      double s = lamc[6 * i + a] * inv_radius * pi[a];
+      for (int c = 0; c < 6; ++c) s += B[a * 6 + c] * pi[c];
+      s -= ty[a];
+      q[6 * i + a] = s; pq += s * pi[a];
+    }
+  }
+  double v[1] = {pq};
+  block_reduce<1, NT_CAM>(v, sm, smo);
+  if (threadIdx.x == 0) { s_alpha = (smo[0] > 0.0) ? cg->rz / smo[0] : 0.0; s_pq = smo[0]; }
+  __syncthreads();
+  const double alpha = s_alpha;
+  const bool breakdown = !(s_pq > 0.0);
+  double rz1 = 0.0;
+  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
+    double rr[6];
+    for (int a = 0; a < 6; ++a) { x[6 * i + a] += alpha * p[6 * i + a]; rr[a] = r[6 * i + a] - alpha * q[6 * i + a]; r[6 * i + a] = rr[a]; }
+    const double* Mi = Minv + (size_t)36 * i;
+    for (int a = 0; a < 6; ++a) { double s = 0; for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c]; q[6 * i + a] = s; rz1 += s * rr[a]; }  // q now holds z
+  }
+  __syncthreads();
+  double v2[1] = {rz1};
+  block_reduce<1, NT_CAM>(v2, sm, smo);
+  if (threadIdx.x == 0) s_beta = (cg->rz > 0.0) ? smo[0] / cg->rz : 0.0;
+  __syncthreads();
+  const double beta = s_beta;
+  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
+    double pn[6], t[6];
+    for (int a = 0; a < 6; ++a) { pn[a] = q[6 * i + a] + beta * p[6 * i + a]; p[6 * i + a] = pn[a]; }
+    apply_T(camtab + (size_t)CAMTAB * i, pn, t);
+    for (int a = 0; a < 6; ++a) pg[6 * i + a] = t[a];
+  }
+  if (threadIdx.x == 0) {
+    cg->pq = s_pq;
+    cg->rz = smo[0];
+    cg->iters += 1;
+    if (breakdown) cg->done = 2;
+    else if (sqrt(smo[0]) <= cg->tol * sqrt(cg->rz0)) cg->done = 1;
+    else if (cg->iters >= cg->max_iters) cg->done = 3;
+  }
+}
+
+// Candidate cameras: cam_c = cam - y_c; table of the candidate; yg = T y_c for the back-substitution;
+// camera parts of |y|^2, y.g and y' Lambda y.
+__global__ void __launch_bounds__(NT_CAM)
+k_cam_step(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
+           const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+           double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ yg, double* __restrict__ scal) {
+  __shared__ double sm[3 * NT_CAM / 32];
+  __shared__ double smo[3];
+  double yn2 = 0, ygd = 0, yly = 0;
+  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
+    double yi[6], cc[6], t[6];
+    for (int a = 0; a < 6; ++a) {
+      yi[a] = cam_free[i] ? y[6 * i + a] : 0.0;
+      cc[a] = cam[6 * i + a] - yi[a];
+      cam_c[6 * i + a] = cc[a];
+      yn2 += yi[a] * yi[a]; ygd += yi[a] * gc[6 * i + a]; yly += lamc[6 * i + a] * inv_radius * yi[a] * yi[a];
+    }
+    cam_table_row(cc, camtab_c + (size_t)CAMTAB * i);
+    apply_T(camtab + (size_t)CAMTAB * i, yi, t);
+    for (int a = 0; a < 6; ++a) yg[6 * i + a] = t[a];
+  }
+  double v[3] = {yn2, ygd, yly};
+  block_reduce<3, NT_CAM>(v, sm, smo);
+  if (threadIdx.x == 0) { scal[S_YN2_C] = smo[0]; scal[S_YG_C] = smo[1]; scal[S_YLY_C] = smo[2]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inspection: expand records into explicit loss-corrected residual / Jacobian blocks (glba_linearize).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_expand(const long n_obs, const int* __restrict__ pm_cam, const double2* __restrict__ pm_uv,
+                         const int* __restrict__ pm2orig, const double4* __restrict__ rec_pm,
+                         const double* __restrict__ camtab, const Intr K, double* __restrict__ res,
+                         double* __restrict__ jc, double* __restrict__ jp) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_obs) return;
+  const int i = pm_cam[k];
+  const long o = pm2orig ? pm2orig[k] : k;
+  const double4 rec = rec_pm[k];
+  const double2 uv = pm_uv[k];
+  const double* ct = camtab + (size_t)CAMTAB * i;
+  double a[6], b[6], ap[3], bp[3], R[9], ta[6], tb[6];
+  for (int q = 0; q < 9; ++q) R[q] = ct[q];
+  jhat_rows(rec, ct[21], ct[22], ct[23], K, a, b);
+  jp_rows(rec, R, K, ap, bp);
+  // J~c rows = a' T, b' T  (T = blockdiag(G,R))  ->  T' a
+  apply_Tt(ct, a, ta);
+  apply_Tt(ct, b, tb);
+  if (res) { res[2 * o] = rec.w * (K.fx * rec.x + K.cx - uv.x); res[2 * o + 1] = rec.w * (K.fy * rec.y + K.cy - uv.y); }
+  if (jc) for (int q = 0; q < 6; ++q) { jc[12 * o + q] = ta[q]; jc[12 * o + 6 + q] = tb[q]; }
+  if (jp) for (int q = 0; q < 3; ++q) { jp[6 * o + q] = ap[q]; jp[6 * o + 3 + q] = bp[q]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Index construction helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void k_iota(const long n, int* out) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = (int)k;
+}
+__global__ void k_check_sorted(const long n, const int* __restrict__ key, const int n_key, int* flags /* [0]=unsorted, [1]=out of range */) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int v = key[k];
+  if (v < 0 || v >= n_key) flags[1] = 1;
+  if (k > 0 && key[k - 1] > v) flags[0] = 1;
+}
+__global__ void k_check_range(const long n, const int* __restrict__ key, const int n_key, int* flag) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && (key[k] < 0 || key[k] >= n_key)) *flag = 1;
+}
+// start[s] = first k with key[k] >= s (key sorted ascending); start[n_seg] = n
+__global__ void k_segment_starts(const long n, const int* __restrict__ key, const int n_seg, int* __restrict__ start) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n_seg) return;
+  long lo = 0, hi = n;
+  while (lo < hi) { const long mid = (lo + hi) >> 1; if (key[mid] < s) lo = mid + 1; else hi = mid; }
+  start[s] = (int)lo;
+}
+__global__ void k_gather_obs(const long n, const int* __restrict__ perm, const int* __restrict__ cam_in, const int* __restrict__ pt_in,
+                             const double* __restrict__ u_in, const double* __restrict__ v_in, int* __restrict__ cam_out,
+                             int* __restrict__ pt_out, double2* __restrict__ uv_out) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const long o = perm ? perm[k] : k;
+  cam_out[k] = cam_in[o];
+  if (pt_out) pt_out[k] = pt_in[o];
+  uv_out[k] = make_double2(u_in[o], v_in[o]);
+}
+__global__ void k_build_cm(const long n, const int* __restrict__ cm2pm, const int* __restrict__ pm_pt, const double2* __restrict__ pm_uv,
+                           int* __restrict__ cm_pt, double2* __restrict__ cm_uv, int* __restrict__ pm2cm) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int o = cm2pm[k];
+  cm_pt[k] = pm_pt[o];
+  cm_uv[k] = pm_uv[o];
+  pm2cm[o] = (int)k;
+}
+__global__ void k_free_flags(const int n, const int* __restrict__ start, const uint8_t* __restrict__ fixed, uint8_t* __restrict__ free_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool seen = start[i + 1] > start[i];
+  free_out[i] = (seen && !(fixed && fixed[i])) ? 1 : 0;
+}
+__global__ void k_pack_pt(const int n, const double* __restrict__ pt3, double4* __restrict__ pt4) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) pt4[j] = make_double4(pt3[3 * j], pt3[3 * j + 1], pt3[3 * j + 2], 0.0);
+}
+__global__ void k_unpack_pt(const int n, const double4* __restrict__ pt4, double* __restrict__ pt3) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) { const double4 v = pt4[j]; pt3[3 * j] = v.x; pt3[3 * j + 1] = v.y; pt3[3 * j + 2] = v.z; }
+}
+// Craw SoA (6 C + 3 g) -> explicit 3x3 / gradient in AoS for glba_linearize
+__global__ void k_unpack_pointblocks(const int n, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw,
+                                     double* __restrict__ hess /* 9 */, double* __restrict__ grad /* 3 */) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const bool f = pt_free[j] != 0;
+  double C[6], g[3];
+  for (int q = 0; q < 6; ++q) C[q] = f ? Craw[(size_t)q * n + j] : 0.0;
+  for (int q = 0; q < 3; ++q) g[q] = f ? Craw[(size_t)(6 + q) * n + j] : 0.0;
+  if (hess) { double* H = hess + 9 * (size_t)j; H[0] = C[0]; H[1] = C[1]; H[2] = C[2]; H[3] = C[1]; H[4] = C[3]; H[5] = C[4]; H[6] = C[2]; H[7] = C[4]; H[8] = C[5]; }
+  if (grad) { grad[3 * (size_t)j] = g[0]; grad[3 * (size_t)j + 1] = g[1]; grad[3 * (size_t)j + 2] = g[2]; }
+}
+
+// post_ba_map_point_culling arithmetic (slam_core.cpp:993-1035), one thread per point.
+__global__ void __launch_bounds__(NT_PM)
+k_cull(const PmArgs A, const double4* __restrict__ pt, const double* __restrict__ camtab, const int min_obs,
+       const double max_mean_err, uint8_t* __restrict__ bad, double* __restrict__ mean_err) {
+  const int j = blockIdx.x * NT_PM + threadIdx.x;
+  if (j >= A.n_pt) return;
+  const int b = A.pt_start[j], e = A.pt_start[j + 1];
+  const double4 X = ldg4(pt + j);
+  double tot = 0.0; int cnt = 0; bool isbad = false;
+  for (int k = b; k < e; ++k) {
+    const double* ct = camtab + (size_t)CAMTAB * A.pm_cam[k];
+    const double2 uv = A.pm_uv[k];
+    const double qx = X.x - ct[18], qy = X.y - ct[19], qz = X.z - ct[20];
+    const double px = ct[0] * qx + ct[1] * qy + ct[2] * qz;
+    const double py = ct[3] * qx + ct[4] * qy + ct[5] * qz;
+    const double pz = ct[6] * qx + ct[7] * qy + ct[8] * qz;
+    if (pz <= 0.0) { isbad = true; break; }
+    const double du = A.K.fx * px / pz + A.K.cx - uv.x, dv = A.K.fy * py / pz + A.K.cy - uv.y;
+    tot += sqrt(du * du + dv * dv); ++cnt;
+  }
+  const double avg = cnt ? tot / cnt : 0.0;
+  if (!isbad && (cnt < min_obs || avg > max_mean_err)) isbad = true;
+  bad[j] = isbad ? 1 : 0;
+  if (mean_err) mean_err[j] = avg;
+}
+
+}  // namespace glba

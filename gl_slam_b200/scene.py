@@ -1,0 +1,191 @@
+"""Seeded synthetic BA scenes for the configs in BASELINE.json / BASELINE.md §4 (C1..C5).
+
+All scenes use the intrinsics GL-SLAM reads from KITTI calib.txt (slam_core.cpp:38-57): fx=fy=718.856,
+cx=607.1928, cy=185.2157, 1241x376.  Cameras are camera-to-world [angle-axis(R_wc), centre], exactly the
+parameter block full_ba packs (slam_core.cpp:768-776).  Observations are emitted track-contiguous
+(sorted by point, then camera).  Pure numpy, vectorised: C5 (30 M observations) builds in seconds.
+"""
+import numpy as np
+
+from ._abi import HostProblem
+
+KITTI_K = (718.856, 718.856, 607.1928, 185.2157)
+IMG_W, IMG_H = 1241.0, 376.0
+
+
+def rodrigues(w):
+    """angle-axis (n,3) -> rotation matrices (n,3,3) (cv::Rodrigues semantics)."""
+    w = np.asarray(w, dtype=np.float64).reshape(-1, 3)
+    th = np.linalg.norm(w, axis=1)
+    small = th < 1e-12
+    k = w / np.where(small, 1.0, th)[:, None]
+    K = np.zeros((w.shape[0], 3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -k[:, 2], k[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = k[:, 2], -k[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -k[:, 1], k[:, 0]
+    s, c = np.sin(th)[:, None, None], np.cos(th)[:, None, None]
+    R = np.eye(3)[None] + s * K + (1 - c) * (K @ K)
+    R[small] = np.eye(3)
+    return R
+
+
+def rotation_to_angle_axis(R):
+    """rotation matrices (n,3,3) -> angle-axis (n,3); valid for angles < pi."""
+    R = np.asarray(R, dtype=np.float64).reshape(-1, 3, 3)
+    v = np.stack([R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]], axis=1) * 0.5
+    s = np.linalg.norm(v, axis=1)
+    c = np.clip((np.trace(R, axis1=1, axis2=2) - 1.0) * 0.5, -1.0, 1.0)
+    th = np.arctan2(s, c)
+    scale = np.where(s < 1e-12, 1.0, th / np.where(s < 1e-12, 1.0, s))
+    return v * scale[:, None]
+
+
+def project(cam, pt, obs_cam, obs_pt, K):
+    """Pinhole projection of the reference residual (slam_core.cpp:705-726): returns (u, v, depth)."""
+    fx, fy, cx, cy = K
+    R = rodrigues(cam[:, :3])                    # R_wc
+    q = pt[obs_pt] - cam[obs_cam, 3:6]
+    p = np.einsum("nji,nj->ni", R[obs_cam], q)   # R_wc^T q
+    return fx * p[:, 0] / p[:, 2] + cx, fy * p[:, 1] / p[:, 2] + cy, p[:, 2]
+
+
+def _trajectory(n_cam, step, yaw_per_frame, loop):
+    """Camera-to-world poses on a planar arc: camera looks along +z, yaw about +y (KITTI convention)."""
+    if loop:
+        yaw_per_frame = 2.0 * np.pi / n_cam
+    yaw = np.arange(n_cam) * yaw_per_frame
+    fwd = np.stack([np.sin(yaw), np.zeros(n_cam), np.cos(yaw)], axis=1)
+    c = np.concatenate([np.zeros((1, 3)), np.cumsum(fwd[:-1] * step, axis=0)], axis=0)
+    w = np.stack([np.zeros(n_cam), yaw, np.zeros(n_cam)], axis=1)
+    # keep |w| < pi so angle-axis stays in the principal branch
+    w[:, 1] = (w[:, 1] + np.pi) % (2 * np.pi) - np.pi
+    return np.concatenate([w, c], axis=1)
+
+
+def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2rad(0.5), loop=False,
+               pixel_sigma=0.5, outlier_frac=0.0, outlier_px=(10.0, 50.0), rot_sigma=0.02, pos_sigma=0.05,
+               pt_sigma=0.10, depth=(5.0, 50.0), n_fixed=2, K=KITTI_K, return_gt=False):
+    """track_len: int, or callable(rng, n_pt) -> int array (clipped to [2, n_cam]).
+
+    Returns a HostProblem whose cam/pt are the *initial guess* (ground truth + Gaussian noise; the first
+    n_fixed cameras stay at ground truth and are flagged fixed, slam_core.cpp:831-833).
+    """
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K
+    cam_gt = _trajectory(n_cam, step, yaw_per_frame, loop)
+    if callable(track_len):
+        tl = np.asarray(track_len(rng, n_pt), dtype=np.int64)
+    else:
+        tl = np.full(n_pt, int(track_len), dtype=np.int64)
+    tl = np.clip(tl, 2 if n_cam >= 2 else 1, n_cam)
+    if loop:
+        start = rng.integers(0, n_cam, size=n_pt)
+    else:
+        start = (rng.random(n_pt) * (n_cam - tl + 1)).astype(np.int64)
+    n_obs = int(tl.sum())
+    obs_pt = np.repeat(np.arange(n_pt, dtype=np.int64), tl)
+    first = np.cumsum(tl) - tl
+    within = np.arange(n_obs, dtype=np.int64) - np.repeat(first, tl)
+    obs_cam = (np.repeat(start, tl) + within) % n_cam
+    # anchor each point in the frustum of the middle camera of its track
+    anchor = (start + tl // 2) % n_cam
+    z = rng.uniform(depth[0], depth[1], size=n_pt)
+    ua = rng.uniform(0.05 * IMG_W, 0.95 * IMG_W, size=n_pt)
+    va = rng.uniform(0.05 * IMG_H, 0.95 * IMG_H, size=n_pt)
+    p_cam = np.stack([(ua - cx) / fx * z, (va - cy) / fy * z, z], axis=1)
+    Rg = rodrigues(cam_gt[:, :3])
+    pt_gt = np.einsum("nij,nj->ni", Rg[anchor], p_cam) + cam_gt[anchor, 3:6]
+    # sort each track by camera index (wrap-around tracks are not monotone)
+    order = np.lexsort((obs_cam, obs_pt))
+    obs_cam, obs_pt = obs_cam[order], obs_pt[order]
+    u, v, dep = project(cam_gt, pt_gt, obs_cam, obs_pt, K)
+    u = u + rng.normal(0.0, pixel_sigma, size=n_obs)
+    v = v + rng.normal(0.0, pixel_sigma, size=n_obs)
+    if outlier_frac > 0:
+        bad = rng.random(n_obs) < outlier_frac
+        mag = rng.uniform(outlier_px[0], outlier_px[1], size=n_obs)
+        ang = rng.uniform(0, 2 * np.pi, size=n_obs)
+        u = np.where(bad, u + mag * np.cos(ang), u)
+        v = np.where(bad, v + mag * np.sin(ang), v)
+    cam0 = cam_gt.copy()
+    cam0[n_fixed:, :3] += rng.normal(0.0, rot_sigma, size=(n_cam - n_fixed, 3)) if n_cam > n_fixed else 0.0
+    cam0[n_fixed:, 3:] += rng.normal(0.0, pos_sigma, size=(n_cam - n_fixed, 3)) if n_cam > n_fixed else 0.0
+    pt0 = pt_gt + rng.normal(0.0, pt_sigma, size=(n_pt, 3))
+    cam_fixed = np.zeros(n_cam, dtype=np.uint8)
+    cam_fixed[:n_fixed] = 1
+    prob = HostProblem(cam0, pt0, obs_cam.astype(np.int32), obs_pt.astype(np.int32), u, v, K, cam_fixed, None)
+    if return_gt:
+        return prob, cam_gt, pt_gt
+    return prob
+
+
+def _poisson_tracks(base, lam):
+    return lambda rng, n: base + rng.poisson(lam, size=n)
+
+
+def config(name, scale=1.0, **overrides):
+    """Named configs of BASELINE.md §4.  `scale` shrinks n_pt (and, for C4/C5, n_cam) for quick tests."""
+    name = name.upper()
+    s = float(scale)
+    if name == "C1":      # two-view pair, ~500 points, both cameras fixed in the live path
+        kw = dict(n_cam=2, n_pt=max(8, int(500 * s)), track_len=2, seed=1, step=1.0, yaw_per_frame=np.deg2rad(0.5),
+                  rot_sigma=0.0, pos_sigma=0.0, pt_sigma=0.3, n_fixed=2)
+    elif name == "C2":    # local window: 10 keyframes, 5 000 points, 20 000 observations, 5 % outliers
+        kw = dict(n_cam=10, n_pt=max(16, int(5000 * s)), track_len=4, seed=2, outlier_frac=0.05,
+                  rot_sigma=0.02, pos_sigma=0.05, pt_sigma=0.10)
+    elif name == "C3":    # 200 frames, 200 k points, mean track 5 -> 1 M observations (as one problem)
+        kw = dict(n_cam=200, n_pt=max(64, int(200000 * s)), track_len=_poisson_tracks(2, 3.0), seed=3,
+                  rot_sigma=0.005, pos_sigma=0.05, pt_sigma=0.10)
+    elif name == "C4":    # 1 800 cameras on a closed loop, 1 M points, ~5 M observations
+        kw = dict(n_cam=max(8, int(1800 * min(1.0, s * 4))), n_pt=max(64, int(1000000 * s)),
+                  track_len=_poisson_tracks(2, 3.0), seed=4, loop=True, rot_sigma=0.002, pos_sigma=0.03, pt_sigma=0.10)
+    elif name == "C5":    # 10 k cameras, 4 M points, ~30 M observations, 10 % outliers, Huber
+        kw = dict(n_cam=max(8, int(10000 * min(1.0, s * 4))), n_pt=max(64, int(4000000 * s)),
+                  track_len=_poisson_tracks(2, 5.5), seed=5, loop=True, outlier_frac=0.10,
+                  rot_sigma=0.002, pos_sigma=0.03, pt_sigma=0.10)
+    else:
+        raise KeyError(name)
+    kw.update(overrides)
+    return make_scene(**kw)
+
+
+def pose_only_scene(n, seed, K=KITTI_K, pixel_sigma=0.5, outlier_frac=0.05, rot_sigma=0.01, pos_sigma=0.05):
+    """One frame against n fixed 3-D points (tracking-thread input, thread_pool.cpp:149-199)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K
+    cam_gt = np.array([[0.01, 0.05, -0.02, 0.3, -0.1, 5.0]])
+    z = rng.uniform(5, 50, size=n)
+    ua = rng.uniform(0.02 * IMG_W, 0.98 * IMG_W, size=n)
+    va = rng.uniform(0.02 * IMG_H, 0.98 * IMG_H, size=n)
+    p_cam = np.stack([(ua - cx) / fx * z, (va - cy) / fy * z, z], axis=1)
+    R = rodrigues(cam_gt[:, :3])[0]
+    X = p_cam @ R.T + cam_gt[0, 3:]
+    uv = np.stack([ua, va], axis=1) + rng.normal(0, pixel_sigma, size=(n, 2))
+    bad = rng.random(n) < outlier_frac
+    uv[bad] += rng.uniform(-40, 40, size=(int(bad.sum()), 2))
+    cam0 = cam_gt[0].copy()
+    cam0[:3] += rng.normal(0, rot_sigma, 3)
+    cam0[3:] += rng.normal(0, pos_sigma, 3)
+    return cam0, X, uv, cam_gt[0]
+
+
+def shard_by_point(prob, world, rank):
+    """SURVEY §8e partitioning: whole point tracks per rank, balanced by observation count.
+
+    Points are dealt out in contiguous blocks whose observation counts are as equal as possible, so
+    every rank keeps a track-contiguous slice; cameras are replicated.  Returns (HostProblem, pt_index)
+    where pt_index maps the shard's local points back to the global ones.
+    """
+    n_pt = prob.n_pt
+    counts = np.bincount(prob.obs_pt, minlength=n_pt)
+    csum = np.concatenate([[0], np.cumsum(counts)])
+    total = csum[-1]
+    bounds = [int(np.searchsorted(csum, total * r / world, side="left")) for r in range(world + 1)]
+    bounds[0], bounds[-1] = 0, n_pt
+    lo, hi = bounds[rank], bounds[rank + 1]
+    sel = (prob.obs_pt >= lo) & (prob.obs_pt < hi)
+    pt_index = np.arange(lo, hi)
+    sub = HostProblem(prob.cam, prob.pt[lo:hi], prob.obs_cam[sel], prob.obs_pt[sel] - lo, prob.obs_u[sel],
+                      prob.obs_v[sel], prob.K, prob.cam_fixed,
+                      None if prob.pt_fixed is None else prob.pt_fixed[lo:hi])
+    return sub, pt_index

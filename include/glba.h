@@ -1,0 +1,236 @@
+/*
+ * glba.h — C ABI of the B200-native bundle-adjustment backend for GL-SLAM.
+ *
+ * This is the drop-in boundary for the two BA entry points of the reference
+ * (all file:line citations are relative to the GL-SLAM tree):
+ *
+ *   slam_core::full_ba(std::mutex&, Map&, cv::Mat& K, int window)  -> bool
+ *       include/core/slam_core.h:59, src/core/slam_core.cpp:744-883
+ *       (called from thread_pool::map_optimizing_thread, src/threading/thread_pool.cpp:351)
+ *   slam_core::pose_only_ba(cv::Mat& R, cv::Mat& t, p3d, p2d, K)     -> bool
+ *       include/core/slam_core.h:65-68, src/core/slam_core.cpp:1092-1140
+ *       (called from thread_pool::tracking_thread, src/threading/thread_pool.cpp:195)
+ *
+ * The reference has no FFI: those two C++ functions hand flat double arrays to
+ * Ceres (camera_params / point_params, slam_core.cpp:750-751, 1099) and read them
+ * back (slam_core.cpp:859-871, 1135-1137).  This header exposes exactly that flat
+ * hand-off: a camera block is [angle-axis(3), camera centre(3)] (camera-to-world,
+ * slam_core.cpp:771-776), a point block is [X,Y,Z] (slam_core.cpp:794-796), an
+ * observation is (camera index, point index, u, v) (slam_core.cpp:806-817).
+ * include/glba_slam.hpp restates the packing/unpacking around it.
+ *
+ * Conventions: plain C, no exceptions cross the boundary, every entry point
+ * returns GLBA_OK (0) or a negative glba_status; on failure the caller's
+ * cam/pt arrays are left untouched.  A glba_ctx is NOT thread-safe; create one
+ * per calling thread (the mapping thread and the tracking thread each own one,
+ * both may be in flight simultaneously on different CUDA streams).
+ */
+#ifndef GLBA_H_
+#define GLBA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLBA_VERSION 100          /* 0.1.0 */
+#define GLBA_MAX_ITERS 256        /* capacity of the per-iteration summary arrays */
+#define GLBA_NCCL_ID_BYTES 128
+
+typedef enum {
+  GLBA_OK = 0,
+  GLBA_E_INVALID_ARG = -1,       /* null pointer, negative size, index out of range */
+  GLBA_E_CUDA = -2,              /* CUDA runtime error (glba_last_error has the text) */
+  GLBA_E_NO_DEVICE = -3,         /* no CUDA device: there is NO CPU fallback */
+  GLBA_E_OOM = -4,
+  GLBA_E_NCCL = -5,
+  GLBA_E_NUMERIC = -6,           /* initial evaluation produced non-finite residuals */
+  GLBA_E_UNSUPPORTED = -7
+} glba_status;
+
+typedef enum { GLBA_LOSS_NONE = 0, GLBA_LOSS_HUBER = 1, GLBA_LOSS_CAUCHY = 2 } glba_loss;
+
+/* Linear solver for the reduced camera system. */
+typedef enum {
+  GLBA_LINSOLVE_AUTO = 0,        /* dense when 6*n_free_cam <= dense_max_dim, else PCG */
+  GLBA_LINSOLVE_PCG = 1,         /* block-Jacobi PCG on the implicit Schur complement */
+  GLBA_LINSOLVE_DENSE = 2        /* explicit S + on-device Cholesky (small windows)   */
+} glba_linsolve;
+
+/* ceres::TerminationType equivalents (slam_core.cpp:1132 IsSolutionUsable()). */
+typedef enum {
+  GLBA_TERM_CONVERGENCE = 0,
+  GLBA_TERM_NO_CONVERGENCE = 1,
+  GLBA_TERM_FAILURE = 2
+} glba_termination;
+
+/* Why the loop stopped (finer than glba_termination). */
+typedef enum {
+  GLBA_STOP_NONE = 0,
+  GLBA_STOP_MAX_ITERS = 1,
+  GLBA_STOP_GRADIENT_TOL = 2,
+  GLBA_STOP_PARAMETER_TOL = 3,
+  GLBA_STOP_FUNCTION_TOL = 4,
+  GLBA_STOP_MIN_RADIUS = 5,
+  GLBA_STOP_INVALID_STEPS = 6,
+  GLBA_STOP_NUMERIC = 7
+} glba_stop_reason;
+
+typedef enum { GLBA_MEM_HOST = 0, GLBA_MEM_DEVICE = 1 } glba_memspace;
+
+typedef struct glba_ctx glba_ctx;
+
+typedef struct {
+  int32_t device;                /* CUDA ordinal */
+  int32_t rank;                  /* this context's shard, 0 <= rank < world */
+  int32_t world;                 /* 1 = single GPU; >1 = point tracks partitioned over `world` contexts */
+  const void* nccl_unique_id;    /* GLBA_NCCL_ID_BYTES bytes from glba_nccl_unique_id(), same on every rank; NULL if world==1 */
+  void* stream;                  /* optional cudaStream_t to run on; NULL = context-owned non-blocking stream */
+} glba_device_cfg;
+
+/*
+ * A BA problem in the flat form the reference hands to Ceres.
+ *   cam[6*i..]  = [w0,w1,w2, c0,c1,c2]: angle-axis of R_wc and camera centre (in/out)
+ *   pt[3*j..]   = world point (in/out)
+ *   observation k ties camera obs_cam[k] to point obs_pt[k] with pixel (obs_u[k], obs_v[k]).
+ * Observations may come in any order; track-contiguous (sorted by point, then camera)
+ * input skips the on-device sort.  With world>1 every rank passes ALL cameras and its
+ * OWN shard of points/observations (whole tracks; point indices are local to the shard).
+ * cam_fixed / pt_fixed: non-zero = held constant (slam_core.cpp:831-833); NULL = none.
+ */
+typedef struct {
+  int32_t n_cam;
+  int32_t n_pt;
+  int64_t n_obs;
+  double* cam;
+  double* pt;
+  const int32_t* obs_cam;
+  const int32_t* obs_pt;
+  const double* obs_u;
+  const double* obs_v;
+  const uint8_t* cam_fixed;
+  const uint8_t* pt_fixed;
+  double fx, fy, cx, cy;         /* cameraMatrix(0,0),(1,1),(0,2),(1,2) — slam_core.cpp:720-723 */
+  int32_t memspace;              /* glba_memspace of every pointer above */
+} glba_problem;
+
+/* Defaults (glba_default_options) = the values hard-coded at slam_core.cpp:814, 842-847
+ * plus the Ceres 2.x defaults that call relies on. */
+typedef struct {
+  int32_t loss;                  /* glba_loss; reference: CauchyLoss(1.0) */
+  double loss_scale;             /* a in rho(s); 1.0 */
+  int32_t max_iters;             /* 30 */
+  double function_tol;           /* 1e-6 */
+  double gradient_tol;           /* 1e-10 */
+  double parameter_tol;          /* 1e-8 */
+  double initial_radius;         /* 1e4 */
+  double max_radius;             /* 1e16 */
+  double min_radius;             /* 1e-32 */
+  double min_relative_decrease;  /* 1e-3 */
+  double min_lm_diagonal;        /* 1e-6 */
+  double max_lm_diagonal;        /* 1e32 */
+  int32_t jacobi_scaling;        /* 1 */
+  int32_t max_consecutive_invalid_steps; /* 5 */
+  int32_t linsolve;              /* glba_linsolve */
+  int32_t dense_max_dim;         /* AUTO switches to PCG above this reduced dimension (default 384) */
+  double cg_rel_tol;             /* PCG stop: sqrt(r'M^-1 r) <= tol * sqrt(r0'M^-1 r0); 1e-13 = parity mode */
+  int32_t cg_max_iters;          /* 0 = 4*reduced dimension, capped at 4000 */
+  int32_t verbose;
+} glba_options;
+
+typedef struct {
+  int32_t status;                /* glba_status */
+  int32_t termination;           /* glba_termination */
+  int32_t stop_reason;           /* glba_stop_reason */
+  int32_t n_iters;               /* LM iterations started (trust-region steps computed) */
+  int32_t n_successful;          /* accepted steps */
+  int32_t n_linearizations;      /* Jacobian evaluations (1 + n_successful) */
+  double initial_cost;
+  double final_cost;
+  /* index 0 = state before the first step; index it = state after LM iteration it */
+  double cost[GLBA_MAX_ITERS + 1];            /* cost of the current (accepted) point */
+  double cost_candidate[GLBA_MAX_ITERS + 1];  /* cost evaluated at the trial point of iteration it */
+  double radius[GLBA_MAX_ITERS + 1];          /* trust-region radius after the iteration */
+  double step_norm[GLBA_MAX_ITERS + 1];
+  double relative_decrease[GLBA_MAX_ITERS + 1];
+  double gradient_max_norm[GLBA_MAX_ITERS + 1];
+  int32_t cg_iters[GLBA_MAX_ITERS + 1];
+  uint8_t accepted[GLBA_MAX_ITERS + 1];
+  /* device time, milliseconds, summed over the solve */
+  double t_setup_ms;             /* H2D + sort + index build */
+  double t_linearize_ms;         /* residual/weight/Jacobian records + Hessian blocks */
+  double t_schur_ms;             /* point-block inverses, preconditioner, reduced rhs */
+  double t_solve_ms;             /* PCG / dense solve */
+  double t_update_ms;            /* back-substitution, candidate cost, accept/reject */
+  double t_total_ms;
+} glba_summary;
+
+/* Output of glba_linearize: the reduced camera system of ONE linearisation at a given radius.
+ * Any pointer may be NULL (not copied out).  Host pointers. */
+typedef struct {
+  double cost;                   /* 1/2 sum rho(|r|^2) */
+  double* residuals;             /* [2*n_obs]  loss-corrected r~, caller's observation order */
+  double* jac_cam;               /* [12*n_obs] loss-corrected 2x6 block, row-major */
+  double* jac_pt;                /* [6*n_obs]  loss-corrected 2x3 block, row-major */
+  double* grad_cam;              /* [6*n_cam]  J~c' r~ (zero rows for fixed cameras) */
+  double* grad_pt;               /* [3*n_pt] */
+  double* hess_cam;              /* [36*n_cam] B_i = sum J~c'J~c, row-major, undamped */
+  double* hess_pt;               /* [9*n_pt]   C_j = sum J~p'J~p, undamped */
+  double* schur_diag;            /* [36*n_cam] diagonal blocks of S = B + D_c^2 - W (C+D_p^2)^-1 W' */
+  double* schur_rhs;             /* [6*n_cam]  g_c - W (C+D_p^2)^-1 g_p */
+  double t_linearize_ms;
+  double t_schur_ms;
+} glba_linearization;
+
+void glba_default_options(glba_options* opt);
+const char* glba_strerror(int status);
+const char* glba_last_error(const glba_ctx* ctx);
+int glba_version(void);
+/* Number of kernels this library has launched since the process started (bench evidence). */
+int64_t glba_kernel_launch_count(void);
+
+int glba_nccl_unique_id(void* out_id /* GLBA_NCCL_ID_BYTES */);
+int glba_create(const glba_device_cfg* cfg, glba_ctx** out);
+void glba_destroy(glba_ctx* ctx);
+
+/* Replaces the ceres::Problem build + ceres::Solve of slam_core.cpp:799-849. */
+int glba_solve(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt, glba_summary* summary);
+
+/* Replaces slam_core.cpp:1099-1137.  cam[6] in/out; X[3*n], uv[2*n] host arrays (points fixed). */
+int glba_pose_only(glba_ctx* ctx, double* cam, int32_t n, const double* X, const double* uv,
+                   double fx, double fy, double cx, double cy, const glba_options* opt,
+                   glba_summary* summary);
+
+/* `batch` independent pose-only problems in one launch; problem b owns
+ * observations [offset[b], offset[b+1]).  usable[b] = IsSolutionUsable(). */
+int glba_pose_only_batch(glba_ctx* ctx, int32_t batch, double* cams /* [6*batch] */,
+                         const int32_t* offset /* [batch+1] */, const double* X, const double* uv,
+                         double fx, double fy, double cx, double cy, const glba_options* opt,
+                         uint8_t* usable, int32_t* n_iters, double* final_cost);
+
+/* One pass of residual + robust weight + Jacobians + Hessian blocks + Schur complement
+ * (the kernels the headline metric times), state is NOT updated. */
+int glba_linearize(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt, double radius,
+                   glba_linearization* out);
+
+/* Benchmark/serving form: upload + index once, then run passes on the resident problem. */
+int glba_load(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt);
+/* cost == NULL: enqueue only (no host synchronisation) */
+int glba_linearize_resident(glba_ctx* ctx, const glba_options* opt, double radius, double* cost /* may be NULL */);
+int glba_solve_resident(glba_ctx* ctx, const glba_options* opt, glba_summary* summary);
+int glba_reset_resident(glba_ctx* ctx);     /* restore the parameters uploaded by glba_load */
+int glba_read_resident(glba_ctx* ctx, double* cam, double* pt); /* D2H of the current state */
+int glba_synchronize(glba_ctx* ctx);
+void* glba_stream(glba_ctx* ctx);            /* cudaStream_t the context launches on */
+
+/* Post-BA map maintenance on device (slam_core.cpp:977-1038, post_ba_map_point_culling):
+ * mean reprojection error and cheirality per point over ALL its observations.
+ * bad[j] = 1 if any depth <= 0, or n_obs_j < min_obs, or mean error > max_mean_err. */
+int glba_cull_points(glba_ctx* ctx, const glba_problem* prob, int32_t min_obs, double max_mean_err,
+                     uint8_t* bad /* [n_pt] */, double* mean_err /* [n_pt], may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLBA_H_ */
