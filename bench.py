@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 bundle-adjustment backend (contract: see the task statement).
+
+Metric (BASELINE.json): BA observations/s over residual + Jacobian + Schur, and LM iterations/s.
+A *step* is one pass of linearise + Schur (K_A + K_B: residuals, robust weights, Jacobian records,
+Hessian blocks, damped point-block inverses, Schur-complement diagonal and reduced rhs) over the whole
+synthetic map, resident in HBM.  The workload is C4 of BASELINE.md §4 (1 800 cameras, 1 M points,
+~5 M observations): the largest config that names 1/2/4/8 GPUs; with --gpus N its point tracks are
+sharded N ways (strong scaling, one NCCL all-reduce of the camera blocks per pass).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C5|C3|C2] [--impl reference]
+
+One JSON line on stdout (rank 0).  `--impl reference` times the CPU restatement of the reference's
+Ceres path (oracle/, all host threads) on the same workload/metric.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ba_observations_per_s_linearize_schur"
+UNIT = "obs/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_scene(workload, scale):
+    from gl_slam_b200 import scene
+    return scene.config(workload, scale=scale)
+
+
+def algorithmic_bytes(n_obs, n_pt, n_cam):
+    """Per-launch algorithmic bytes of each hot kernel in THIS layout; every array counted once."""
+    return {
+        # read cam idx 4 + uv 16 + pm2cm 4; write two 32-B records | per point: read X 32 + CSR 4 + s 32, write C,g 72 + lam 32 + block 96
+        "linearize_pm": 88 * n_obs + 268 * n_pt + 192 * n_cam,
+        "linearize_cm": 48 * n_obs + 216 * n_cam,                 # record 32 + uv 16
+        "schur_cm": 116 * n_obs + 216 * n_cam,                    # record 32 + pt idx 4 + gathered Cinv,u0 80
+        "spmv_pm": 36 * n_obs + 84 * n_pt + 240 * n_cam,          # record 32 + cam idx 4 | Cinv 48 + CSR 4 + u 32
+        "spmv_cm": 68 * n_obs + 48 * n_cam,                       # record 32 + pt idx 4 + gathered u 32
+        "backsub_cost": 56 * n_obs + 252 * n_pt + 432 * n_cam,    # record 32 + cam idx 4 (x2) + uv 16 | block 96, X 32+32, g 24, lam 32 ...
+    }
+
+
+def run_reference(args):
+    """CPU arm: the oracle's linearise + Schur (Ceres-semantics restatement) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    prob = build_scene(args.workload, args.scale)
+    from gl_slam_b200 import scene
+    frac = args.ref_fraction
+    if frac < 1.0:     # bounded sample: the first `frac` of the point tracks (whole tracks, all cameras)
+        sub, _ = scene.shard_by_point(prob, int(round(1.0 / frac)), 0)
+    else:
+        sub = prob
+    threads = oracle.num_threads()
+    for _ in range(args.warmup):
+        oracle.step(sub, 1e4)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.step(sub, 1e4)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sub.n_obs / dt
+    sample = f"{sub.n_obs} observations ({sub.n_pt} whole point tracks, all {sub.n_cam} cameras) of {args.workload}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "n_cam": prob.n_cam, "n_pt": prob.n_pt, "n_obs": prob.n_obs, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "restated CPU baseline (Ceres semantics, autodiff + exact Schur pieces), not libceres"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="glba", choices=["glba", "reference"])
+    ap.add_argument("--workload", default="C4")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--ref-fraction", type=float, default=0.25, help="fraction of the map the CPU reference arm times per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lm-iters", type=int, default=6)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "glba" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import gl_slam_b200 as g
+    from gl_slam_b200 import _abi, scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the BA kernels have no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        idt = torch.zeros(_abi.GLBA_NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(g.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    full = build_scene(args.workload, args.scale)
+    n_obs_total, n_pt_total, n_cam = full.n_obs, full.n_pt, full.n_cam
+    prob = scene.shard_by_point(full, world, rank)[0] if world > 1 else full
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = g.Context(device=local, rank=rank, world=world, nccl_id=nccl_id, stream=stream.cuda_stream)
+    opt = g.options()                                   # reference settings: Cauchy(1.0), Ceres LM defaults
+
+    # ---- inputs resident in HBM ---------------------------------------------------------------------
+    def dev_t(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = {k: dev_t(getattr(prob, k)) for k in ("cam", "pt", "obs_cam", "obs_pt", "obs_u", "obs_v", "cam_fixed")}
+    ps = _abi.Problem()
+    ps.n_cam, ps.n_pt, ps.n_obs = prob.n_cam, prob.n_pt, prob.n_obs
+    ps.cam, ps.pt = d["cam"].data_ptr(), d["pt"].data_ptr()
+    ps.obs_cam, ps.obs_pt, ps.obs_u, ps.obs_v = d["obs_cam"].data_ptr(), d["obs_pt"].data_ptr(), d["obs_u"].data_ptr(), d["obs_v"].data_ptr()
+    ps.cam_fixed, ps.pt_fixed = d["cam_fixed"].data_ptr(), None
+    ps.fx, ps.fy, ps.cx, ps.cy = prob.K
+    ps.memspace = _abi.MEM_DEVICE
+    ctx.load(ps, opt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    radius = opt.initial_radius
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            ctx.linearize_resident(radius, opt, want_cost=False)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = g.kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            ctx.linearize_resident(radius, opt, want_cost=False)
+        e1.record(stream)
+        barrier()
+        launches = g.kernel_launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = n_obs_total / (ms_step * 1e-3)
+    cost = ctx.linearize_resident(radius, opt, want_cost=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel roofline (device events inside the library, same stream) --------------------------
+    kt = ctx.time_kernels(radius, reps=max(3, args.steps // 2), opt=opt)
+    peak, peak_kind = measured_peak_gbs()
+    ab = algorithmic_bytes(prob.n_obs, prob.n_pt, prob.n_cam)
+    kernels = {}
+    for name, key in (("linearize_pm", "linearize_pm_ms"), ("linearize_cm", "linearize_cm_ms"), ("schur_cm", "schur_cm_ms"),
+                      ("spmv_pm", "spmv_pm_ms"), ("spmv_cm", "spmv_cm_ms"), ("backsub_cost", "backsub_cost_ms")):
+        if kt[key] > 0:
+            gbs = ab[name] / (kt[key] * 1e-3) / 1e9
+            kernels[name] = {"ms": kt[key], "algorithmic_bytes": ab[name], "gbs": gbs, "frac": gbs / peak}
+    step_kernels = ["linearize_pm", "linearize_cm", "schur_cm"]
+    dom = max(step_kernels, key=lambda k: kernels.get(k, {"ms": 0})["ms"]) if kernels else None
+    ncu_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ncu_traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    kernels["small_kernels"] = {"ms": kt["small_kernels_ms"]}
+    roofline = None
+    if dom:
+        roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": ncu_traffic, "peak_kind": peak_kind,
+                    "step_bytes": sum(ab[k] for k in step_kernels),
+                    "step_frac_of_peak": sum(ab[k] for k in step_kernels) / (ms_step * 1e-3) / 1e9 / peak,
+                    "survey_model_obs_per_s_at_peak": peak * 1e9 / 496.0}
+
+    # ---- LM iterations/s: full iterations (PCG solve, back-substitution, candidate cost, accept/reject) ------
+    lm = None
+    if args.lm_iters > 0:
+        lopt = g.options(max_iters=args.lm_iters, function_tol=0.0, parameter_tol=0.0, gradient_tol=0.0, cg_rel_tol=1e-2, cg_max_iters=40)
+        ctx.reset_resident()
+        barrier()
+        t0 = time.perf_counter()
+        s = ctx.solve_resident(lopt)
+        barrier()
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall = float(tw.item())
+        lm = {"lm_iters_per_s": s["n_iters"] / wall, "iters": s["n_iters"], "accepted": s["n_successful"], "wall_s": wall,
+              "cg_iters": s["cg_iters"][1:], "cost": [s["initial_cost"], s["final_cost"]],
+              "mode": "inexact Newton: PCG rel tol 1e-2, <= 40 iterations",
+              "device_ms": {k: s[k] for k in ("t_linearize_ms", "t_schur_ms", "t_solve_ms", "t_update_ms")}}
+        ctx.reset_resident()
+
+    # ---- e2e: the C-ABI call a GL-SLAM host makes, HOST buffers, copies inside the timed region ---------------
+    e2e = None
+    if world == 1:
+        host = {k: torch.from_numpy(np.ascontiguousarray(getattr(prob, k))).pin_memory() for k in
+                ("cam", "pt", "obs_cam", "obs_pt", "obs_u", "obs_v", "cam_fixed")}
+        hs = _abi.Problem()
+        hs.n_cam, hs.n_pt, hs.n_obs = prob.n_cam, prob.n_pt, prob.n_obs
+        hs.cam, hs.pt = host["cam"].data_ptr(), host["pt"].data_ptr()
+        hs.obs_cam, hs.obs_pt, hs.obs_u, hs.obs_v = (host[k].data_ptr() for k in ("obs_cam", "obs_pt", "obs_u", "obs_v"))
+        hs.cam_fixed, hs.pt_fixed = host["cam_fixed"].data_ptr(), None
+        hs.fx, hs.fy, hs.cx, hs.cy = prob.K
+        hs.memspace = _abi.MEM_HOST
+        out = _abi.LinearizationOut(prob.n_cam, prob.n_pt, prob.n_obs, per_obs=False)
+        out.grad_pt = out.hess_pt = None          # camera-sized results + cost come back to the host
+        ls = out.struct()
+        ctx2 = g.Context(device=local)
+        k_e2e = max(3, min(args.steps, 5))
+        g.lib().glba_linearize(ctx2._h, C.byref(hs), C.byref(opt), radius, C.byref(ls))   # warm-up (allocations)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            st = g.lib().glba_linearize(ctx2._h, C.byref(hs), C.byref(opt), radius, C.byref(ls))
+            assert st == 0, st
+        dt = (time.perf_counter() - t0) / k_e2e
+        h2d = 24 * prob.n_obs + 48 * prob.n_cam + 24 * prob.n_pt + prob.n_cam
+        d2h = 8 + (6 + 36 + 36 + 6) * 8 * prob.n_cam
+        e2e = {"value": prob.n_obs / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
+               "call": "glba_linearize(host problem) -> cost, grad_cam, hess_cam, schur_diag, schur_rhs", "steps": k_e2e,
+               "cost_matches_resident": bool(abs(ls.cost - cost) <= 1e-12 * abs(cost))}
+        ctx2.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1): the oracle on a bounded sample -----------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        sub, _ = scene.shard_by_point(full, 8, 0) if full.n_obs > 400000 else (full, None)
+        oracle.step(sub, radius)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 8.0 and reps < 50):
+            oracle.step(sub, radius)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": sub.n_obs / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+               "sample": f"{sub.n_obs} observations ({sub.n_pt} whole tracks) of {args.workload}, {reps} repetitions",
+               "note": "restated CPU baseline (Ceres semantics), not libceres"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "n_cam": n_cam, "n_pt": n_pt_total, "n_obs": n_obs_total, "loss": "cauchy(1.0)",
+                       "sharding": f"point tracks over {world} GPU(s), cameras replicated", "l2": "inputs larger than L2 (no flush needed)"
+                       if 116 * n_obs_total / world > 126e6 else "working set fits L2: latency-bound config",
+                       "step": "linearise (residual, weight, Jacobian records, Hessian blocks) + Schur (point inverses, S diagonal, reduced rhs)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "lm": lm,
+            "cost_at_initial_point": cost,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "glba_default_options", "glba_strerror", "glba_last_error", "glba_version", "glba_kernel_launch_count",
     "glba_nccl_unique_id", "glba_create", "glba_destroy", "glba_solve", "glba_pose_only", "glba_pose_only_batch",
     "glba_linearize", "glba_load", "glba_linearize_resident", "glba_solve_resident", "glba_reset_resident",
-    "glba_read_resident", "glba_synchronize", "glba_stream", "glba_cull_points",
+    "glba_read_resident", "glba_synchronize", "glba_stream", "glba_cull_points", "glba_time_kernels",
 )
 
 
@@ -69,6 +69,7 @@ def lib():
     L.glba_load.argtypes = [vp, C.POINTER(_abi.Problem), C.POINTER(_abi.Options)]
     L.glba_linearize_resident.argtypes = [vp, C.POINTER(_abi.Options), f64, C.POINTER(f64)]
     L.glba_solve_resident.argtypes = [vp, C.POINTER(_abi.Options), C.POINTER(_abi.Summary)]
+    L.glba_time_kernels.argtypes = [vp, C.POINTER(_abi.Options), f64, i32, C.POINTER(_abi.KernelTimes)]
     L.glba_reset_resident.argtypes = [vp]
     L.glba_read_resident.argtypes = [vp, vp, vp]
     L.glba_synchronize.argtypes = [vp]
@@ -167,6 +168,12 @@ class Context:
         summ = _abi.Summary()
         self._check(lib().glba_solve_resident(self._h, C.byref(opt), C.byref(summ)), "glba_solve_resident")
         return summ.as_dict()
+
+    def time_kernels(self, radius=1e4, reps=5, opt=None):
+        opt = opt or options()
+        kt = _abi.KernelTimes()
+        self._check(lib().glba_time_kernels(self._h, C.byref(opt), float(radius), int(reps), C.byref(kt)), "glba_time_kernels")
+        return kt.as_dict()
 
     def reset_resident(self):
         self._check(lib().glba_reset_resident(self._h), "glba_reset_resident")

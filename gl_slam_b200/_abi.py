@@ -1,7 +1,7 @@
 """ctypes mirror of include/glba.h (struct layouts, enums, prototypes).
 
 Shared by the product loader (gl_slam_b200/__init__.py -> libglba.so) and by the test-only
-oracle loader (oracle/oracle.py -> libglba_oracle.so): both libraries speak the same POD structs.
+checker under oracle/ (which re-uses these POD structs); nothing here depends on that checker.
 """
 import ctypes as C
 
@@ -81,6 +81,14 @@ class Linearization(C.Structure):
                 ("t_linearize_ms", C.c_double), ("t_schur_ms", C.c_double)]
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("linearize_pm_ms", "linearize_cm_ms", "schur_cm_ms", "spmv_pm_ms", "spmv_cm_ms",
+                                          "backsub_cost_ms", "point_damp_ms", "small_kernels_ms")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
@@ -130,7 +138,7 @@ class HostProblem:
 
 
 class LinearizationOut:
-    """Host buffers for glba_linearize / glbao_linearize."""
+    """Host buffers for a glba_linearization (outputs of one linearisation)."""
 
     def __init__(self, n_cam, n_pt, n_obs, per_obs=True):
         z = np.zeros

@@ -23,6 +23,7 @@
 
 #include "glba_kernels.cuh"
 #include "glba_pose.cuh"
+#include "glba_dense.cuh"
 
 using namespace glba;
 
@@ -85,6 +86,9 @@ struct glba_ctx {
   Buf rec_pm, rec_cm, Craw, sp4, lam4, pblk, u4;
   Buf part_pm, part_cm, acc27, yhat, Bc, gc, sc, lamc, Md, Minv, rhs, cg_x, cg_r, cg_p, cg_q, pg, yg, scal, cgst;
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
+  Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
+  bool has_dup = false;                                                              // some point is observed twice by one camera
+  int dn_grid = 0, dn_ppc = 0;
   int cur = 0;
   double* h_scal = nullptr;    // pinned
   CgState* h_cg = nullptr;     // pinned
@@ -273,12 +277,18 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   }
   if (n_cam) LAUNCH(k_free_flags, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
   if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, ctx->pt_free.as<uint8_t>());
+  ctx->has_dup = false;
+  if (n > 0 && n_cam <= DN_MAXCAM) {
+    LAUNCH(k_check_dup, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->flags.as<int>() + 3);
+    CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
   // chunk list for the camera-major kernels (host, from cam_start)
   std::vector<int> h_start((size_t)n_cam + 1);
   std::vector<uint8_t> h_free(std::max(n_cam, 1));
   CU(cudaMemcpyAsync(h_start.data(), ctx->cam_start.p, sizeof(int) * ((size_t)n_cam + 1), cudaMemcpyDeviceToHost, s));
   if (n_cam) CU(cudaMemcpyAsync(h_free.data(), ctx->cam_free.p, n_cam, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  ctx->has_dup = (n > 0 && n_cam <= DN_MAXCAM) ? (ctx->h_flags[3] != 0) : false;
   long per = (n + 148L * 8 - 1) / (148L * 8);
   int chunk = (int)std::min<long>(4096, std::max<long>(NT_CM, ((per + NT_CM - 1) / NT_CM) * NT_CM));
   std::vector<int> cc, cb, ce, ccs((size_t)n_cam + 1, 0);
@@ -311,6 +321,12 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->rhs, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_x, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_r, 6 * (size_t)n_cam);
   ENSURE(double, ctx->cg_p, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_q, 6 * (size_t)n_cam); ENSURE(double, ctx->pg, 6 * (size_t)n_cam);
   ENSURE(double, ctx->yg, 6 * (size_t)n_cam); ENSURE(double, ctx->scal, NSCAL); ENSURE(CgState, ctx->cgst, 1);
+  if (n_cam <= DN_MAXCAM && n_cam > 0) {
+    ctx->dn_grid = std::max(1, std::min(64, cdiv(n_pt, 128)));
+    ctx->dn_ppc = cdiv(n_pt, ctx->dn_grid);
+    const size_t len = (size_t)(n_cam * (n_cam + 1) / 2) * 36 + 6 * (size_t)n_cam;
+    ENSURE(double, ctx->dn_part, len * ctx->dn_grid); ENSURE(double, ctx->dn_red, len);
+  }
   CU(cudaMemsetAsync(ctx->scal.p, 0, sizeof(double) * NSCAL, s));
   CU(cudaMemsetAsync(ctx->yhat.p, 0, sizeof(double) * 6 * n_cam, s));
   CU(cudaMemsetAsync(ctx->acc27.p, 0, sizeof(double) * 27 * n_cam, s));
@@ -442,6 +458,42 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   return GLBA_OK;
 }
 
+// Exact solve of the reduced camera system for small windows: explicit S, Cholesky (glba_dense.cuh).
+int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
+  const int c = ctx->cur;
+  const int n_cam = ctx->n_cam;
+  static bool attr_set = false;
+  const size_t sm_schur = (size_t)DN_TP * n_cam * 24 * sizeof(double) + DN_TP * sizeof(unsigned) + 2 * (size_t)(n_cam * (n_cam + 1) / 2) + 16;
+  const size_t sm_solve = ((size_t)36 * n_cam * n_cam + 6 * (size_t)n_cam) * sizeof(double);
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 1024)));
+    CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)36 * DN_MAXCAM * DN_MAXCAM + 6 * DN_MAXCAM) * 8)));
+    attr_set = true;
+  }
+  const int len = (n_cam * (n_cam + 1) / 2) * 36 + 6 * n_cam;
+  mark(ctx, PH_SCHUR);
+  k_dense_schur<<<ctx->dn_grid, DN_NT, sm_schur, ctx->stream>>>(pm_args(ctx, o), n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(),
+      (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->dn_ppc,
+      ctx->dn_part.as<double>());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  LAUNCH(k_dense_reduce, cdiv(len, 256), 256, ctx->dn_grid, len, (const double*)ctx->dn_part.as<double>(), ctx->dn_red.as<double>());
+  if (ctx->world > 1) AR(ctx->dn_red.as<double>(), (size_t)len, kNcclSum);
+  mark(ctx, PH_SOLVE);
+  k_dense_solve<<<1, DN_NT, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_red.as<double>(),
+      (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius,
+      ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->scal.as<double>());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  mark(ctx, -1);
+  return GLBA_OK;
+}
+
+bool want_dense(const glba_ctx* ctx, const glba_options* o) {
+  if (ctx->n_free_cam == 0 || ctx->n_cam > DN_MAXCAM || ctx->has_dup) return false;
+  if (o->linsolve == GLBA_LINSOLVE_PCG) return false;
+  if (o->linsolve == GLBA_LINSOLVE_DENSE) return true;
+  return 6 * ctx->n_free_cam <= o->dense_max_dim;
+}
+
 // candidate state, back-substitution, candidate cost; leaves the scalars in h_scal (synchronises)
 int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
   const int c = ctx->cur, d = c ^ 1;
@@ -498,6 +550,9 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   double x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
   sum->initial_cost = cost; sum->cost[0] = cost; sum->cost_candidate[0] = cost; sum->radius[0] = radius; sum->gradient_max_norm[0] = gmax;
   int it = 0;
+  const bool dense = want_dense(ctx, o);
+  if (o->linsolve == GLBA_LINSOLVE_DENSE && !dense && ctx->n_free_cam > 0)
+    return fail(ctx, GLBA_E_UNSUPPORTED, "dense solve needs <= %d cameras and no duplicate (point,camera) observations", DN_MAXCAM);
   bool fresh = true;   // point blocks are damped for the current radius
   // number of free parameters: free cameras + free points (host knows cameras; points: any observation => >0)
   if (ctx->n_obs == 0) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
@@ -509,8 +564,11 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     if (!fresh) { if ((st = do_redamp(ctx, radius))) return st; }
     fresh = true;
     int cg_it = 0;
-    if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
-    if ((st = do_pcg(ctx, o, radius, &cg_it))) return st;
+    if (dense) { if ((st = do_dense(ctx, o, radius))) return st; }
+    else {
+      if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
+      if ((st = do_pcg(ctx, o, radius, &cg_it))) return st;
+    }
     sum->cg_iters[it] = cg_it;
     if ((st = do_step(ctx, o, radius))) return st;
     const bool solver_ok = (S[S_NOTPD_P] + (ctx->n_free_cam > 0 ? S[S_NOTPD_C] : 0.0)) == 0.0;
@@ -602,7 +660,7 @@ void glba_default_options(glba_options* o) {
   o->initial_radius = 1e4; o->max_radius = 1e16; o->min_radius = 1e-32;
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1; o->max_consecutive_invalid_steps = 5;
-  o->linsolve = GLBA_LINSOLVE_AUTO; o->dense_max_dim = 384; o->cg_rel_tol = 1e-13; o->cg_max_iters = 0; o->verbose = 0;
+  o->linsolve = GLBA_LINSOLVE_AUTO; o->dense_max_dim = 6 * DN_MAXCAM; o->cg_rel_tol = 1e-13; o->cg_max_iters = 0; o->verbose = 0;
 }
 
 const char* glba_strerror(int status) {
@@ -667,7 +725,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->scal, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -728,6 +786,82 @@ int glba_linearize_resident(glba_ctx* ctx, const glba_options* opt, double radiu
     ctx->ev_used = 0;   // no sync requested: drop the phase markers
   }
   return GLBA_OK;
+}
+
+int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int32_t reps, glba_kernel_times* out) {
+  if (!ctx || !ctx->loaded || !out || reps <= 0 || !(radius > 0.0)) return GLBA_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int st = validate_options(ctx, opt);
+  if (st) return st;
+  std::memset(out, 0, sizeof(*out));
+  const int c = ctx->cur, d = c ^ 1;
+  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  const int grid_pm = cdiv(n_pt, NT_PM);
+  if (n_pt == 0 || ctx->n_chunks == 0) return GLBA_OK;
+  // a complete pass first so every buffer the kernels read is valid
+  if ((st = do_linearize(ctx, opt, 1, radius))) return st;
+  if ((st = do_schur(ctx, radius))) return st;
+  CgState* cg = ctx->cgst.as<CgState>();
+  LAUNCH(k_cg_init, 1, NT_CAM, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(), (const double*)ctx->rhs.as<double>(),
+         ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->pg.as<double>(), cg, 0.0, 1 << 30);
+  LAUNCH(k_cam_step, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
+         (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->yg.as<double>(), ctx->scal.as<double>());
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->ev_used = 0;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const PmArgs PA = pm_args(ctx, opt);
+  const CmArgs CA = cm_args(ctx);
+  auto timed = [&](auto&& launch, double* ms_out) -> int {
+    launch();                                   // warm
+    cudaEventRecord(e0, ctx->stream);
+    for (int r = 0; r < reps; ++r) launch();
+    cudaEventRecord(e1, ctx->stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) return GLBA_E_CUDA;
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / reps;
+    return GLBA_OK;
+  };
+  st = timed([&] { LAUNCH(k_linearize_pm, grid_pm, NT_PM, PA, (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(),
+           ctx->pblk.as<double>(), 0, opt->jacobi_scaling, opt->min_lm_diagonal, opt->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>()); }, &out->linearize_pm_ms);
+  if (st) return st;
+  st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           ctx->part_cm.as<double>()); }, &out->linearize_cm_ms);
+  if (st) return st;
+  st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms);
+  if (st) return st;
+  st = timed([&] { LAUNCH(k_point_pass<0>, grid_pm, NT_PM, PA, (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->pg.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), (const CgState*)nullptr,
+           (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr); }, &out->spmv_pm_ms);
+  if (st) return st;
+  st = timed([&] { LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double4*)ctx->u4.as<double4>(), (const CgState*)nullptr, ctx->part_cm.as<double>()); }, &out->spmv_cm_ms);
+  if (st) return st;
+  st = timed([&] { LAUNCH(k_point_pass<1>, grid_pm, NT_PM, PA, (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->yg.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr,
+           (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
+           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->backsub_cost_ms);
+  if (st) return st;
+  st = timed([&] { LAUNCH(k_point_damp, grid_pm, NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
+           (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms);
+  if (st) return st;
+  st = timed([&] {
+    ReduceMap M{}; M.n = 5; const int slots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
+    for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = (q == 4); }
+    LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+    for (int rep2 = 0; rep2 < 2; ++rep2)
+      LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
+             ctx->acc27.as<double>(), (const CgState*)nullptr);
+    LAUNCH(k_cam_lin_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->acc27.as<double>(), ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(),
+           ctx->lamc.as<double>(), 0, opt->jacobi_scaling, opt->min_lm_diagonal, opt->max_lm_diagonal, ctx->scal.as<double>());
+    LAUNCH(k_cam_schur_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->acc27.as<double>(), (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(),
+           1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->scal.as<double>()); }, &out->small_kernels_ms);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return st;
 }
 
 int glba_solve_resident(glba_ctx* ctx, const glba_options* opt, glba_summary* summary) {

@@ -1,0 +1,241 @@
+// glba_dense.cuh — exact reduced-camera solve for small windows (<= DN_MAXCAM cameras), the regime
+// GL-SLAM's live BA runs in (7+3 keyframes: src/core/slam_types.cpp:8-9, thread_pool.cpp:319-323;
+// Ceres SPARSE_SCHUR = exact factorisation, slam_core.cpp:843).
+//
+//   S = blockdiag(B_i + Lambda_i) - sum_j V_j V_j',   V_ij = W_ij chol(Cinv_j),  W_ij = J~c' J~p
+//   rhs_i = g_i - sum_j W_ij u0_j
+// k_dense_schur: every CTA owns a fixed, contiguous range of points, stages their V blocks in shared
+// memory tile by tile and accumulates its private copy of the (block-upper) S in registers — a
+// block-sparse SYRK with no atomics.  k_dense_reduce sums the CTA copies in CTA order.
+// k_dense_solve: one CTA, S in shared memory, Cholesky + two triangular solves.
+// Everything is fixed-order, so the step is bit-reproducible.
+#pragma once
+#include "glba_kernels.cuh"
+
+namespace glba {
+
+constexpr int DN_MAXCAM = 16;            // reduced dimension <= 96
+constexpr int DN_NT = 256;
+constexpr int DN_TP = 16;                // points staged per tile
+constexpr int DN_SLOTS = 16;             // track slots staged in parallel per point
+constexpr int DN_PAIRS_PER_PASS = DN_NT / 36;                                                   // 7
+constexpr int DN_MAXQ = (DN_MAXCAM * (DN_MAXCAM + 1) / 2 + DN_PAIRS_PER_PASS - 1) / DN_PAIRS_PER_PASS;  // 20
+
+// lower Cholesky factor of a symmetric 3x3 (00,01,02,11,12,22); zeros if not PD
+__device__ __forceinline__ void chol3(const double* C, double* L /* l00 l10 l11 l20 l21 l22 */) {
+  const double l00 = sqrt(fmax(C[0], 0.0));
+  const double i00 = l00 > 0.0 ? 1.0 / l00 : 0.0;
+  const double l10 = C[1] * i00, l20 = C[2] * i00;
+  const double l11 = sqrt(fmax(C[3] - l10 * l10, 0.0));
+  const double i11 = l11 > 0.0 ? 1.0 / l11 : 0.0;
+  const double l21 = (C[4] - l20 * l10) * i11;
+  const double l22 = sqrt(fmax(C[5] - l20 * l20 - l21 * l21, 0.0));
+  L[0] = l00; L[1] = l10; L[2] = l11; L[3] = l20; L[4] = l21; L[5] = l22;
+}
+
+__global__ void __launch_bounds__(DN_NT)
+k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_free, const double4* __restrict__ rec_pm,
+              const double* __restrict__ camtab, const double* __restrict__ pblk, const int pts_per_cta,
+              double* __restrict__ part /* [grid][n_pairs*36 + 6*n_cam] */) {
+  extern __shared__ double dsm[];
+  const int n_pairs = n_cam * (n_cam + 1) / 2;
+  double* V = dsm;                                   // [DN_TP][n_cam][18]
+  double* Wu = V + (size_t)DN_TP * n_cam * 18;       // [DN_TP][n_cam][6]
+  unsigned* pres = reinterpret_cast<unsigned*>(Wu + (size_t)DN_TP * n_cam * 6);   // [DN_TP]
+  unsigned char* pair_i = reinterpret_cast<unsigned char*>(pres + DN_TP);         // [n_pairs]
+  unsigned char* pair_k = pair_i + n_pairs;
+  const int tid = threadIdx.x;
+  for (int p = tid; p < n_pairs; p += DN_NT) {       // pair p -> (i,k), i <= k, row-major upper
+    int i = 0, rem = p;
+    while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
+    pair_i[p] = (unsigned char)i; pair_k[p] = (unsigned char)(i + rem);
+  }
+  const int sub = tid / 36, ent = tid - sub * 36;    // sub-CTA of 36 threads: one 6x6 block
+  const int rr = ent / 6, cc = ent - rr * 6;
+  const bool acc_active = sub < DN_PAIRS_PER_PASS;
+  double acc[DN_MAXQ];
+#pragma unroll
+  for (int q = 0; q < DN_MAXQ; ++q) acc[q] = 0.0;
+  double racc = 0.0;                                 // thread t < 6*n_cam: rhs entry t
+  const int p_begin = blockIdx.x * pts_per_cta;
+  const int p_end = min(A.n_pt, p_begin + pts_per_cta);
+  const int pl = tid / DN_SLOTS, slot = tid - pl * DN_SLOTS;
+  for (int base = p_begin; base < p_end; base += DN_TP) {
+    __syncthreads();
+    if (tid < DN_TP) pres[tid] = 0u;
+    __syncthreads();
+    const int j = base + pl;
+    if (j < p_end && A.pt_free[j]) {
+      const int b = A.pt_start[j], e = A.pt_start[j + 1];
+      const double2* pb = reinterpret_cast<const double2*>(pblk + (size_t)PBLK * j);
+      for (int k = b + slot; k < e; k += DN_SLOTS) {
+        const int i = A.pm_cam[k];
+        if (!cam_free[i]) continue;
+        const double2 c01 = pb[0], c23 = pb[1], c45 = pb[2], u01 = pb[3], u2_ = pb[4];
+        const double Ci[6] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y};
+        double Lc[6];
+        chol3(Ci, Lc);
+        const double4 rec = rec_pm[k];
+        const double* ct = camtab + (size_t)CAMTAB * i;
+        double R[9], a[6], bb[6], ap[3], bp[3];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) R[q] = ct[q];
+        jhat_rows(rec, ct[21], ct[22], ct[23], A.K, a, bb);
+        jp_rows(rec, R, A.K, ap, bp);
+        double* Vo = V + ((size_t)pl * n_cam + i) * 18;
+        double* Wo = Wu + ((size_t)pl * n_cam + i) * 6;
+        // W = T' (a ap' + b bp')  (6x3);  column d of What, rotated by G' (rows 0-2) and R' (rows 3-5)
+        double W[18];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double wh[6], tw[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) wh[r] = a[r] * ap[d] + bb[r] * bp[d];
+          apply_Tt(ct, wh, tw);
+#pragma unroll
+          for (int r = 0; r < 6; ++r) W[r * 3 + d] = tw[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          // V = W Lc,  Lc = [[l00,0,0],[l10,l11,0],[l20,l21,l22]]
+          Vo[r * 3 + 0] = W[r * 3] * Lc[0] + W[r * 3 + 1] * Lc[1] + W[r * 3 + 2] * Lc[3];
+          Vo[r * 3 + 1] = W[r * 3 + 1] * Lc[2] + W[r * 3 + 2] * Lc[4];
+          Vo[r * 3 + 2] = W[r * 3 + 2] * Lc[5];
+          Wo[r] = W[r * 3] * u01.x + W[r * 3 + 1] * u01.y + W[r * 3 + 2] * u2_.x;
+        }
+        atomicOr(&pres[pl], 1u << i);
+      }
+    }
+    __syncthreads();
+    const int np = min(DN_TP, p_end - base);
+    for (int p = 0; p < np; ++p) {
+      const unsigned mask = pres[p];
+      if (!mask) continue;
+      if (acc_active) {
+#pragma unroll
+        for (int q = 0; q < DN_MAXQ; ++q) {
+          const int pr = sub + q * DN_PAIRS_PER_PASS;
+          if (pr < n_pairs) {
+            const int i = pair_i[pr], k = pair_k[pr];
+            if (((mask >> i) & 1u) && ((mask >> k) & 1u)) {
+              const double* vi = V + ((size_t)p * n_cam + i) * 18 + rr * 3;
+              const double* vk = V + ((size_t)p * n_cam + k) * 18 + cc * 3;
+              acc[q] += vi[0] * vk[0] + vi[1] * vk[1] + vi[2] * vk[2];
+            }
+          }
+        }
+      }
+      if (tid < 6 * n_cam) {
+        const int i = tid / 6;
+        if ((mask >> i) & 1u) racc += Wu[((size_t)p * n_cam + i) * 6 + (tid - 6 * i)];
+      }
+    }
+  }
+  double* out = part + (size_t)blockIdx.x * ((size_t)n_pairs * 36 + 6 * n_cam);
+  if (acc_active) {
+#pragma unroll
+    for (int q = 0; q < DN_MAXQ; ++q) {
+      const int pr = sub + q * DN_PAIRS_PER_PASS;
+      if (pr < n_pairs) out[(size_t)pr * 36 + ent] = acc[q];
+    }
+  }
+  if (tid < 6 * n_cam) out[(size_t)n_pairs * 36 + tid] = racc;
+}
+
+__global__ void k_dense_reduce(const int n_parts, const int len, const double* __restrict__ part, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len) return;
+  double s = 0.0;
+  for (int g = 0; g < n_parts; ++g) s += part[(size_t)g * len + t];
+  out[t] = s;
+}
+
+// One CTA: assemble S (n = 6 n_cam) in shared memory, Cholesky, solve S y = rhs.  Non-free cameras
+// become identity rows with zero rhs.  Outputs y (cg_x layout), the diagonal blocks and rhs.
+__global__ void __launch_bounds__(DN_NT)
+k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ Sred /* pairs*36 + 6 n_cam */,
+              const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+              double* __restrict__ y, double* __restrict__ Md, double* __restrict__ rhs_out, double* __restrict__ scal) {
+  extern __shared__ double dsm[];
+  const int n = 6 * n_cam;
+  const int n_pairs = n_cam * (n_cam + 1) / 2;
+  double* S = dsm;            // n x n, row-major, lower triangle is what the factorisation reads
+  double* b = S + (size_t)n * n;
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  // assemble
+  for (int t = tid; t < n_pairs * 36; t += DN_NT) {
+    const int pr = t / 36, ent = t - pr * 36;
+    int i = 0, rem = pr;
+    while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
+    const int k = i + rem;
+    const int rr = ent / 6, cc = ent - rr * 6;
+    double v = -Sred[t];
+    const bool fi = cam_free[i] != 0, fk = cam_free[k] != 0;
+    if (i == k) {
+      if (fi) { v += Bc[(size_t)36 * i + rr * 6 + cc]; if (rr == cc) v += lamc[6 * i + rr] * inv_radius; }
+      else v = (rr == cc) ? 1.0 : 0.0;
+    } else if (!fi || !fk) v = 0.0;
+    S[(size_t)(6 * i + rr) * n + 6 * k + cc] = v;
+    S[(size_t)(6 * k + cc) * n + 6 * i + rr] = v;
+  }
+  for (int t = tid; t < n; t += DN_NT) {
+    const int i = t / 6;
+    b[t] = cam_free[i] ? gc[t] - Sred[(size_t)n_pairs * 36 + t] : 0.0;
+  }
+  __syncthreads();
+  for (int t = tid; t < n_cam * 36; t += DN_NT) {
+    const int i = t / 36, ent = t - i * 36, rr = ent / 6, cc = ent - rr * 6;
+    Md[t] = cam_free[i] ? S[(size_t)(6 * i + rr) * n + 6 * i + cc] : 0.0;
+  }
+  for (int t = tid; t < n; t += DN_NT) rhs_out[t] = b[t];
+  __syncthreads();
+  // right-looking Cholesky on the lower triangle
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      const double d = S[(size_t)j * n + j];
+      if (!(d > 0.0)) { s_bad = 1; S[(size_t)j * n + j] = 1.0; } else S[(size_t)j * n + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double inv = 1.0 / S[(size_t)j * n + j];
+    for (int r = j + 1 + tid; r < n; r += DN_NT) S[(size_t)r * n + j] *= inv;
+    __syncthreads();
+    const int m = n - j - 1;           // trailing (r,c), r >= c > j
+    for (int t = tid; t < m * m; t += DN_NT) {
+      const int r = j + 1 + t / m, c = j + 1 + t % m;
+      if (c <= r) S[(size_t)r * n + c] -= S[(size_t)r * n + j] * S[(size_t)c * n + j];
+    }
+    __syncthreads();
+  }
+  // L z = b
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) b[j] /= S[(size_t)j * n + j];
+    __syncthreads();
+    const double zj = b[j];
+    for (int r = j + 1 + tid; r < n; r += DN_NT) b[r] -= S[(size_t)r * n + j] * zj;
+    __syncthreads();
+  }
+  // L' y = z
+  for (int j = n - 1; j >= 0; --j) {
+    if (tid == 0) b[j] /= S[(size_t)j * n + j];
+    __syncthreads();
+    const double yj = b[j];
+    for (int r = tid; r < j; r += DN_NT) b[r] -= S[(size_t)j * n + r] * yj;
+    __syncthreads();
+  }
+  for (int t = tid; t < n; t += DN_NT) y[t] = cam_free[t / 6] ? b[t] : 0.0;
+  if (tid == 0) scal[S_NOTPD_C] = s_bad ? 1.0 : 0.0;
+}
+
+// duplicate (point, camera) observations make two staging threads collide: detect them at load time
+__global__ void k_check_dup(const int n_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, int* flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pt) return;
+  const int b = pt_start[j], e = pt_start[j + 1];
+  for (int k = b; k < e; ++k)
+    for (int l = k + 1; l < e; ++l)
+      if (pm_cam[k] == pm_cam[l]) { *flag = 1; return; }
+}
+
+}  // namespace glba

@@ -64,7 +64,7 @@ def _trajectory(n_cam, step, yaw_per_frame, loop):
 
 def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2rad(0.5), loop=False,
                pixel_sigma=0.5, outlier_frac=0.0, outlier_px=(10.0, 50.0), rot_sigma=0.02, pos_sigma=0.05,
-               pt_sigma=0.10, depth=(5.0, 50.0), n_fixed=2, K=KITTI_K, return_gt=False):
+               pt_sigma=0.10, depth=(5.0, 50.0), n_fixed=2, K=KITTI_K, return_gt=False, min_parallax_deg=1.0):
     """track_len: int, or callable(rng, n_pt) -> int array (clipped to [2, n_cam]).
 
     Returns a HostProblem whose cam/pt are the *initial guess* (ground truth + Gaussian noise; the first
@@ -87,14 +87,32 @@ def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2r
     first = np.cumsum(tl) - tl
     within = np.arange(n_obs, dtype=np.int64) - np.repeat(first, tl)
     obs_cam = (np.repeat(start, tl) + within) % n_cam
-    # anchor each point in the frustum of the middle camera of its track
+    # anchor each point in the frustum of the middle camera of its track; like a real front-end's
+    # triangulation filter, re-draw points whose parallax between the first and last camera of the
+    # track is below min_parallax_deg (forward motion leaves the depth of points near the focus of
+    # expansion unobservable, which makes any BA chaotic at the 1e-16 level).
     anchor = (start + tl // 2) % n_cam
-    z = rng.uniform(depth[0], depth[1], size=n_pt)
-    ua = rng.uniform(0.05 * IMG_W, 0.95 * IMG_W, size=n_pt)
-    va = rng.uniform(0.05 * IMG_H, 0.95 * IMG_H, size=n_pt)
-    p_cam = np.stack([(ua - cx) / fx * z, (va - cy) / fy * z, z], axis=1)
+    last = (start + tl - 1) % n_cam
     Rg = rodrigues(cam_gt[:, :3])
-    pt_gt = np.einsum("nij,nj->ni", Rg[anchor], p_cam) + cam_gt[anchor, 3:6]
+    pt_gt = np.zeros((n_pt, 3))
+    todo = np.arange(n_pt)
+    cos_min = np.cos(np.deg2rad(min_parallax_deg))
+    for _round in range(40):
+        m = todo.shape[0]
+        if m == 0:
+            break
+        # keep the point in front of the last camera of its track as well (the rig moves towards it)
+        zmin = depth[0] + step * (tl[todo] - tl[todo] // 2)
+        z = zmin + rng.random(m) * np.maximum(depth[1] - zmin, 1.0)
+        ua = rng.uniform(0.05 * IMG_W, 0.95 * IMG_W, size=m)
+        va = rng.uniform(0.05 * IMG_H, 0.95 * IMG_H, size=m)
+        p_cam = np.stack([(ua - cx) / fx * z, (va - cy) / fy * z, z], axis=1)
+        X = np.einsum("nij,nj->ni", Rg[anchor[todo]], p_cam) + cam_gt[anchor[todo], 3:6]
+        pt_gt[todo] = X
+        r0 = X - cam_gt[start[todo], 3:6]
+        r1 = X - cam_gt[last[todo], 3:6]
+        cosang = (r0 * r1).sum(1) / (np.linalg.norm(r0, axis=1) * np.linalg.norm(r1, axis=1))
+        todo = todo[cosang > cos_min] if min_parallax_deg > 0 else todo[:0]
     # sort each track by camera index (wrap-around tracks are not monotone)
     order = np.lexsort((obs_cam, obs_pt))
     obs_cam, obs_pt = obs_cam[order], obs_pt[order]

@@ -133,7 +133,7 @@ typedef struct {
   int32_t jacobi_scaling;        /* 1 */
   int32_t max_consecutive_invalid_steps; /* 5 */
   int32_t linsolve;              /* glba_linsolve */
-  int32_t dense_max_dim;         /* AUTO switches to PCG above this reduced dimension (default 384) */
+  int32_t dense_max_dim;         /* AUTO switches to PCG above this reduced dimension (default 96 = 16 cameras, the dense kernels' limit) */
   double cg_rel_tol;             /* PCG stop: sqrt(r'M^-1 r) <= tol * sqrt(r0'M^-1 r0); 1e-13 = parity mode */
   int32_t cg_max_iters;          /* 0 = 4*reduced dimension, capped at 4000 */
   int32_t verbose;
@@ -183,6 +183,19 @@ typedef struct {
   double t_schur_ms;
 } glba_linearization;
 
+/* Average device time per launch (CUDA events on the context stream) of each hot kernel on the
+ * resident problem, for roofline accounting (bench.py).  Milliseconds. */
+typedef struct {
+  double linearize_pm_ms;   /* K_A + point half of K_B: residual, weight, records, C_j, g_j, damped inverse */
+  double linearize_cm_ms;   /* camera half of K_B: B_i, g_i */
+  double schur_cm_ms;       /* Schur diagonal blocks (preconditioner) + reduced rhs */
+  double spmv_pm_ms;        /* implicit S x, point-major half */
+  double spmv_cm_ms;        /* implicit S x, camera-major half */
+  double backsub_cost_ms;   /* back-substitution + candidate cost */
+  double point_damp_ms;     /* re-damping of the point blocks after a rejected step */
+  double small_kernels_ms;  /* all camera-sized / reduction kernels of one linearise+Schur pass */
+} glba_kernel_times;
+
 void glba_default_options(glba_options* opt);
 const char* glba_strerror(int status);
 const char* glba_last_error(const glba_ctx* ctx);
@@ -219,6 +232,7 @@ int glba_load(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt);
 /* cost == NULL: enqueue only (no host synchronisation) */
 int glba_linearize_resident(glba_ctx* ctx, const glba_options* opt, double radius, double* cost /* may be NULL */);
 int glba_solve_resident(glba_ctx* ctx, const glba_options* opt, glba_summary* summary);
+int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int32_t reps, glba_kernel_times* out);
 int glba_reset_resident(glba_ctx* ctx);     /* restore the parameters uploaded by glba_load */
 int glba_read_resident(glba_ctx* ctx, double* cam, double* pt); /* D2H of the current state */
 int glba_synchronize(glba_ctx* ctx);

@@ -585,7 +585,7 @@ void glbao_default_options(glba_options* o) {
   o->initial_radius = 1e4; o->max_radius = 1e16; o->min_radius = 1e-32;
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1; o->max_consecutive_invalid_steps = 5;
-  o->linsolve = GLBA_LINSOLVE_AUTO; o->dense_max_dim = 384; o->cg_rel_tol = 1e-13; o->cg_max_iters = 0; o->verbose = 0;
+  o->linsolve = GLBA_LINSOLVE_AUTO; o->dense_max_dim = 96; o->cg_rel_tol = 1e-13; o->cg_max_iters = 0; o->verbose = 0;
 }
 
 int glbao_num_threads(void) {
@@ -671,6 +671,63 @@ int glbao_linearize(const glba_problem* p, const glba_options* o, double radius,
     for (int i = 0; i < V.n_cam; ++i) { const int s = V.cam_slot[i]; if (s < 0) continue;
       for (int a = 0; a < 6; ++a) out->schur_rhs[6 * i + a] = S.rhs[6 * s + a] / sc[6 * i + a]; }
   }
+  return GLBA_OK;
+}
+
+// One linearise + Schur pass exactly as an LM iteration performs it, fully threaded, no outputs but the
+// cost: evaluate (autodiff) -> Jacobi column scaling -> LM diagonal -> Schur elimination (diagonal blocks of S
+// for block-Jacobi, reduced rhs).  This is what bench.py times as the CPU baseline of the headline metric.
+int glbao_step(const glba_problem* p, const glba_options* o, double radius, double* cost_out, double* t_eval_ms, double* t_schur_ms) {
+  View V; int st = build_view(p, V); if (st) return st;
+  Lin L; double cost;
+  Timer t0;
+  if (!evaluate(V, p->cam, p->pt, o->loss, o->loss_scale, &cost, &L)) return GLBA_E_NUMERIC;
+  if (t_eval_ms) *t_eval_ms = t0.ms();
+  Timer t1;
+  const long n = V.n_obs;
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  std::vector<double> dp((size_t)3 * V.n_pt, 0.0), dc((size_t)6 * V.n_cam, 0.0);
+  std::vector<std::vector<double>> tdc(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+    std::vector<double>& my = tdc[tid]; my.assign((size_t)6 * V.n_cam, 0.0);
+#pragma omp for schedule(static)
+    for (int j = 0; j < V.n_pt; ++j)
+      for (long t = V.trk_start[j]; t < V.trk_start[j + 1]; ++t) {
+        const long k = V.trk_obs[t]; const int i = V.obs_cam[k];
+        for (int a = 0; a < 6; ++a) my[6 * i + a] += L.jc[12 * k + a] * L.jc[12 * k + a] + L.jc[12 * k + 6 + a] * L.jc[12 * k + 6 + a];
+        for (int a = 0; a < 3; ++a) dp[3 * j + a] += L.jp[6 * k + a] * L.jp[6 * k + a] + L.jp[6 * k + 3 + a] * L.jp[6 * k + 3 + a];
+      }
+  }
+  for (int t = 0; t < nthreads; ++t) for (size_t i = 0; i < dc.size(); ++i) dc[i] += tdc[t][i];
+  std::vector<double> sc(dc.size(), 1.0), sp(dp.size(), 1.0);
+  if (o->jacobi_scaling) {
+    for (size_t i = 0; i < dc.size(); ++i) sc[i] = 1.0 / (1.0 + std::sqrt(dc[i]));
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)dp.size(); ++i) sp[i] = 1.0 / (1.0 + std::sqrt(dp[i]));
+  }
+#pragma omp parallel for schedule(static)
+  for (long k = 0; k < n; ++k) {
+    const int i = V.obs_cam[k], j = V.obs_pt[k];
+    for (int row = 0; row < 2; ++row) {
+      for (int a = 0; a < 6; ++a) L.jc[12 * k + row * 6 + a] *= sc[6 * i + a];
+      for (int a = 0; a < 3; ++a) L.jp[6 * k + row * 3 + a] *= sp[3 * j + a];
+    }
+  }
+  for (size_t i = 0; i < dc.size(); ++i) dc[i] = std::sqrt(std::min(std::max(dc[i] * sc[i] * sc[i], o->min_lm_diagonal), o->max_lm_diagonal) / radius);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)dp.size(); ++i) dp[i] = std::sqrt(std::min(std::max(dp[i] * sp[i] * sp[i], o->min_lm_diagonal), o->max_lm_diagonal) / radius);
+  Schur S;
+  if (!build_schur(V, L, dc, dp, false, S)) return GLBA_E_NUMERIC;
+  if (t_schur_ms) *t_schur_ms = t1.ms();
+  if (cost_out) *cost_out = cost;
   return GLBA_OK;
 }
 

@@ -39,6 +39,8 @@ def lib():
         L.glbao_cost.argtypes = [C.POINTER(_abi.Problem), C.POINTER(_abi.Options), C.POINTER(C.c_double)]
         L.glbao_linearize.argtypes = [C.POINTER(_abi.Problem), C.POINTER(_abi.Options), C.c_double,
                                       C.POINTER(_abi.Linearization)]
+        L.glbao_step.argtypes = [C.POINTER(_abi.Problem), C.POINTER(_abi.Options), C.c_double, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.glbao_solve.argtypes = [C.POINTER(_abi.Problem), C.POINTER(_abi.Options), C.POINTER(_abi.Summary)]
         L.glbao_pose_only.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                       C.c_double, C.c_double, C.POINTER(_abi.Options), C.POINTER(_abi.Summary)]
@@ -73,6 +75,16 @@ def linearize(prob, radius, opt=None, per_obs=True):
         raise RuntimeError(f"glbao_linearize -> {st}")
     out.take(s)
     return out
+
+
+def step(prob, radius, opt=None):
+    """One threaded linearise + Schur pass (what bench.py times on the CPU).  Returns (cost, t_eval_ms, t_schur_ms)."""
+    opt = opt or options()
+    c, te, ts = C.c_double(), C.c_double(), C.c_double()
+    st = lib().glbao_step(C.byref(prob.struct()), C.byref(opt), float(radius), C.byref(c), C.byref(te), C.byref(ts))
+    if st:
+        raise RuntimeError(f"glbao_step -> {st}")
+    return c.value, te.value, ts.value
 
 
 def solve(prob, opt=None):

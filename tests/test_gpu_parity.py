@@ -1,0 +1,205 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libglba.so), against the CPU oracle.
+
+Parity gates from BASELINE.json north_star (FP64): per-iteration cost within 1e-9 relative, same
+iteration count, final poses / points within 1e-6 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import gl_slam_b200 as g
+from gl_slam_b200 import scene
+from gl_slam_b200._abi import HostProblem
+
+from helpers import GOLDEN, check_state, check_trajectory, golden_names, load_golden, max_rel, rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("linsolve", [g.LINSOLVE_DENSE, g.LINSOLVE_PCG])
+def test_solve_matches_golden(ctx, name, linsolve):
+    """Committed fixtures: same trajectory with the exact (dense Cholesky) and the PCG reduced solve."""
+    prob, z = load_golden(name)
+    got, s = ctx.solve(prob, g.options(loss=int(z["loss"]), linsolve=linsolve))
+    check_trajectory(s, z)
+    assert max_rel(s["radius"], z["radius"]) < 1e-8
+    assert s["stop_reason"] == int(z["stop_reason"]) and s["termination"] == int(z["termination"])
+    check_state(prob, got.cam, got.pt, z["cam_final"], z["pt_final"])
+
+
+@pytest.mark.parametrize("loss", [0, 1, 2])
+def test_linearization_elementwise(ctx, oracle, loss):
+    """K_A / K_B outputs element by element: residuals, 2x6 / 2x3 blocks, gradients, Hessian blocks, Schur pieces."""
+    prob = scene.make_scene(7, 300, lambda rng, n: 2 + rng.poisson(2.0, size=n), seed=31, outlier_frac=0.1, rot_sigma=0.3,
+                            pos_sigma=0.1)
+    prob.cam[2, :3] = 0.0                 # exactly-identity keyframe: Ceres' small-angle branch
+    prob.cam[3, :3] = [3e-9, 1e-9, -2e-9]
+    prob.cam_fixed[:] = 0
+    prob.cam_fixed[0] = 1
+    o = dict(loss=loss)
+    G = ctx.linearize(prob, 1e4, g.options(**o))
+    O = oracle.linearize(prob, 1e4, oracle.options(**o))
+    assert abs(G.cost - O.cost) <= 1e-12 * abs(O.cost)
+    for k in ("residuals", "jac_cam", "jac_pt", "grad_cam", "grad_pt", "hess_cam", "hess_pt", "schur_rhs"):
+        assert rel_to_max(getattr(G, k), getattr(O, k)) < 1e-10, k
+    assert rel_to_max(G.schur_diag, O.schur_diag) < 1e-9
+
+
+@pytest.mark.parametrize("cfg,kw", [("C1", {}), ("C2", dict(rot_sigma=0.005, pos_sigma=0.03)), ("C2", dict(outlier_frac=0.0, loss=1)),
+                                    ("C2", dict(scale=0.2, loss=0, outlier_frac=0.0))])
+def test_configs_match_oracle(ctx, oracle, cfg, kw):
+    """BASELINE configs C1 (two-view, live semantics: both cameras fixed) and C2 (10 keyframes, 5k points, 20k obs)."""
+    kw = dict(kw)
+    loss = kw.pop("loss", 2)
+    prob = scene.config(cfg, **kw)
+    ref, so = oracle.solve(prob, oracle.options(loss=loss))
+    got, s = ctx.solve(prob, g.options(loss=loss))
+    check_trajectory(s, so)
+    check_state(prob, got.cam, got.pt, ref.cam, ref.pt)
+
+
+def test_medium_map_pcg(ctx, oracle):
+    """24 cameras (reduced dimension 132 > dense limit 96): AUTO picks PCG; gate against the oracle's exact Cholesky."""
+    prob = scene.make_scene(24, 3000, lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=41, rot_sigma=0.003, pos_sigma=0.03)
+    ref, so = oracle.solve(prob)
+    got, s = ctx.solve(prob)
+    assert max(s["cg_iters"]) > 0
+    check_trajectory(s, so)
+    check_state(prob, got.cam, got.pt, ref.cam, ref.pt)
+
+
+def test_long_chain_pcg_is_conditioning_limited(ctx, oracle):
+    """60-camera open chain anchored by two cameras, trust region wide open: cond(S)*eps ~ 1e-9, so an
+    iterative and a direct reduced solve cannot agree better than that (neither can two Cholesky orderings).
+    Same iteration count and accept/reject sequence are still required; cost tolerance here is 1e-7."""
+    prob = scene.make_scene(60, 6000, lambda rng, n: 2 + rng.poisson(3.0, size=n), seed=41, rot_sigma=0.003, pos_sigma=0.03)
+    ref, so = oracle.solve(prob)
+    got, s = ctx.solve(prob)
+    check_trajectory(s, so, rtol=1e-7)
+    assert np.allclose(got.cam, ref.cam, rtol=1e-5, atol=1e-7)
+
+
+def test_unsorted_input_and_fixed_points(ctx, oracle):
+    prob = scene.make_scene(8, 400, 4, seed=51, rot_sigma=0.004, pos_sigma=0.03)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(prob.n_obs)
+    pf = (rng.random(prob.n_pt) < 0.2).astype(np.uint8)
+    shuf = HostProblem(prob.cam, prob.pt, prob.obs_cam[perm], prob.obs_pt[perm], prob.obs_u[perm], prob.obs_v[perm], prob.K,
+                       prob.cam_fixed, pf)
+    ref, so = oracle.solve(shuf)
+    got, s = ctx.solve(shuf)
+    check_trajectory(s, so)
+    check_state(shuf, got.cam, got.pt, ref.cam, ref.pt)
+    assert np.array_equal(got.pt[pf == 1], prob.pt[pf == 1])
+    # per-observation outputs come back in the caller's order
+    G = ctx.linearize(shuf, 1e4)
+    O = oracle.linearize(shuf, 1e4)
+    assert rel_to_max(G.residuals, O.residuals) < 1e-10 and rel_to_max(G.jac_cam, O.jac_cam) < 1e-10
+
+
+def test_edge_cases(ctx):
+    prob = scene.make_scene(4, 30, 3, seed=9)
+    empty = HostProblem(prob.cam, prob.pt, [], [], [], [], prob.K, prob.cam_fixed)
+    got, s = ctx.solve(empty)
+    assert s["n_iters"] == 0 and s["final_cost"] == 0.0 and np.array_equal(got.cam, prob.cam)
+    # unobserved camera and point are left alone
+    cam = np.vstack([prob.cam, [[0.1, 0.2, 0.3, 50, 60, 70]]])
+    pt = np.vstack([prob.pt, [[7, 8, 9]]])
+    big = HostProblem(cam, pt, prob.obs_cam, prob.obs_pt, prob.obs_u, prob.obs_v, prob.K, np.r_[prob.cam_fixed, 0])
+    r1, s1 = ctx.solve(prob)
+    r2, s2 = ctx.solve(big)
+    assert max_rel(s1["cost"], s2["cost"]) < 1e-11 and np.array_equal(r2.cam[-1], cam[-1]) and np.array_equal(r2.pt[-1], pt[-1])
+    # bad index: rejected, caller's arrays untouched
+    bad = prob.copy()
+    bad.obs_pt = bad.obs_pt.copy()      # copy() shares the (read-only) observation arrays
+    bad.obs_pt[3] = 10 ** 6
+    before = bad.cam.copy()
+    with pytest.raises(g.GlbaError) as e:
+        ctx.solve(bad)
+    assert e.value.status == -1 and np.array_equal(bad.cam, before)
+    # non-finite initial residual (point on the camera plane): numeric failure, not garbage
+    nan = prob.copy()
+    k = 0
+    nan.pt[nan.obs_pt[k]] = nan.cam[nan.obs_cam[k], 3:6]
+    with pytest.raises(g.GlbaError) as e:
+        ctx.solve(nan)
+    assert e.value.status == -6
+
+
+def test_bitwise_reproducible(ctx):
+    """All reductions are fixed-order: two runs give identical bits (SURVEY §7 'deterministic FP64 reductions')."""
+    prob = scene.config("C2", scale=0.3)
+    for ls in (g.LINSOLVE_DENSE, g.LINSOLVE_PCG):
+        a, sa = ctx.solve(prob, g.options(linsolve=ls))
+        b, sb = ctx.solve(prob, g.options(linsolve=ls))
+        assert sa["cost"] == sb["cost"] and np.array_equal(a.cam, b.cam) and np.array_equal(a.pt, b.pt)
+
+
+def test_pose_only(ctx, oracle):
+    z = np.load(os.path.join(GOLDEN, "pose_only.npz"))
+    cam, s = ctx.pose_only(z["cam0"], z["X"], z["uv"], tuple(z["K"]))
+    assert s["n_iters"] == int(z["n_iters"]) and max_rel(s["cost"], z["cost"]) < 1e-9
+    assert np.allclose(cam, z["cam_final"], rtol=1e-6, atol=1e-9)
+    for loss in (0, 1, 2):
+        for seed in (1, 2, 3):
+            cam0, X, uv, _ = scene.pose_only_scene(100 + 300 * seed, seed=seed)
+            a, sa = ctx.pose_only(cam0, X, uv, scene.KITTI_K, g.options(loss=loss))
+            b, sb = oracle.pose_only(cam0, X, uv, scene.KITTI_K, oracle.options(loss=loss))
+            assert sa["n_iters"] == sb["n_iters"] and max_rel(sa["cost"], sb["cost"]) < 1e-9
+            assert sa["accepted"] == sb["accepted"] and sa["termination"] == sb["termination"]
+            assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
+    with pytest.raises(ValueError):      # p3d.size() != p2d.size() -> false (slam_core.cpp:1096)
+        ctx.pose_only(cam0, X, uv[:-1], scene.KITTI_K)
+
+
+def test_pose_only_batch(ctx, oracle):
+    cams, offs, Xs, uvs, want = [], [0], [], [], []
+    for seed in range(12):
+        cam0, X, uv, _ = scene.pose_only_scene(150 + 40 * seed, seed=100 + seed)
+        cams.append(cam0); Xs.append(X); uvs.append(uv); offs.append(offs[-1] + X.shape[0])
+        want.append(oracle.pose_only(cam0, X, uv, scene.KITTI_K))
+    out, usable, iters, cost = ctx.pose_only_batch(np.array(cams), offs, np.vstack(Xs), np.vstack(uvs), scene.KITTI_K)
+    assert usable.all()
+    for b, (cam, s) in enumerate(want):
+        assert iters[b] == s["n_iters"] and abs(cost[b] - s["final_cost"]) <= 1e-9 * s["final_cost"]
+        assert np.allclose(out[b], cam, rtol=1e-6, atol=1e-9)
+
+
+def test_cull_points(ctx, oracle):
+    prob = scene.make_scene(8, 500, lambda rng, n: 2 + rng.poisson(1.5, size=n), seed=17, outlier_frac=0.1)
+    prob.pt[5] = prob.cam[prob.obs_cam[prob.obs_pt == 5][0], 3:6] - [0, 0, 5.0]
+    bad, err = ctx.cull_points(prob, 3, 1.0)
+    obad, oerr = oracle.cull_points(prob, 3, 1.0)
+    assert np.array_equal(bad, obad) and bad[5] == 1
+    ok = obad == 0
+    assert np.allclose(err[ok], oerr[ok], rtol=1e-10)
+
+
+# ---- full-size properties (sizes the oracle would take too long on inside the GPU test budget) ------------------
+def test_c3_scale_properties(ctx):
+    """C3-as-one-problem (200 cameras, 200k points, ~1M observations): size-independent properties."""
+    prob, cam_gt, pt_gt = scene.make_scene(200, 200000, lambda rng, n: 2 + rng.poisson(3.0, size=n), seed=3, pixel_sigma=0.0,
+                                           rot_sigma=0.0, pos_sigma=0.0, pt_sigma=0.0, return_gt=True)
+    # (1) noise-free observations at ground truth: zero cost, zero gradient, nothing moves
+    L = ctx.linearize(prob, 1e4, per_obs=False)
+    assert L.cost < 1e-15 and np.abs(L.grad_cam).max() < 1e-6 and np.abs(L.grad_pt).max() < 1e-6
+    # (2) checksum of checksums: sum of per-camera Hessian traces == sum of per-point ones is NOT expected,
+    #     but J'J is symmetric PSD block by block and the Schur diagonal blocks are PSD too
+    H = L.hess_cam[prob.cam_fixed == 0]
+    assert np.allclose(H, np.swapaxes(H, 1, 2), rtol=0, atol=0)
+    assert (np.linalg.eigvalsh(H) > -1e-6 * np.abs(H).max()).all()
+    Sd = L.schur_diag[prob.cam_fixed == 0]
+    assert (np.linalg.eigvalsh(Sd) > 0).all()
+    # (3) perturb, solve (PCG path), recover ground truth: encode -> perturb -> decode round trip
+    rng = np.random.default_rng(1)
+    prob.cam[2:, :3] += rng.normal(0, 0.001, size=(198, 3))
+    prob.cam[2:, 3:] += rng.normal(0, 0.02, size=(198, 3))
+    prob.pt += rng.normal(0, 0.05, size=prob.pt.shape)
+    got, s = ctx.solve(prob, g.options(loss=0, function_tol=1e-12, cg_rel_tol=1e-10, max_iters=40))
+    assert s["final_cost"] < 1e-8 * s["initial_cost"]
+    assert np.abs(got.cam - cam_gt).max() < 1e-4
+    # (4) cost is monotone over accepted steps
+    c = np.array(s["cost"])
+    assert (np.diff(c) <= 1e-12 * c[:-1]).all()
