@@ -24,6 +24,8 @@
 #include "glba_kernels.cuh"
 #include "glba_pose.cuh"
 #include "glba_dense.cuh"
+#include "glba_tiles.cuh"
+#include "glba_cam.cuh"
 
 using namespace glba;
 
@@ -86,6 +88,9 @@ struct glba_ctx {
   Buf rec_pm, rec_cm, Craw, sp4, lam4, pblk, u4;
   Buf part_pm, part_cm, acc27, yhat, Bc, gc, sc, lamc, Md, Minv, rhs, cg_x, cg_r, cg_p, cg_q, pg, yg, scal, cgst;
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
+  Buf tile_pt, xtab, partA, partB, partc, counters;                                  // tiles, PCG gather table, camera-kernel partials
+  bool use_tiles = false;
+  int n_tiles = 0, max_track = 0, grid_c = 0;
   Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
   bool has_dup = false;                                                              // some point is observed twice by one camera
   int dn_grid = 0, dn_ppc = 0;
@@ -232,9 +237,9 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(int, ctx->pm_cam, n); ENSURE(int, ctx->pm_pt, n); ENSURE(double2, ctx->pm_uv, n); ENSURE(int, ctx->pm2cm, n);
   ENSURE(int, ctx->pt_start, (size_t)n_pt + 1); ENSURE(int, ctx->cm_pt, n); ENSURE(double2, ctx->cm_uv, n); ENSURE(int, ctx->cm2pm, n);
   ENSURE(int, ctx->cam_start, (size_t)n_cam + 1); ENSURE(uint8_t, ctx->cam_free, n_cam); ENSURE(uint8_t, ctx->pt_free, n_pt);
-  ENSURE(int, ctx->keys_tmp, 2 * (size_t)n + 2); ENSURE(int, ctx->flags, 4);
+  ENSURE(int, ctx->keys_tmp, 2 * (size_t)n + 2); ENSURE(int, ctx->flags, 8);
   ENSURE(int, ctx->pm2orig, n);
-  CU(cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), s));
+  CU(cudaMemsetAsync(ctx->flags.p, 0, 8 * sizeof(int), s));
   const int gb = cdiv(n, 256);
   if (n > 0) {
     LAUNCH(k_check_sorted, gb, 256, n, d_opt, n_pt, ctx->flags.as<int>());
@@ -278,10 +283,10 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   if (n_cam) LAUNCH(k_free_flags, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
   if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, ctx->pt_free.as<uint8_t>());
   ctx->has_dup = false;
-  if (n > 0 && n_cam <= DN_MAXCAM) {
+  if (n > 0 && n_cam <= DN_MAXCAM)
     LAUNCH(k_check_dup, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->flags.as<int>() + 3);
-    CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  }
+  if (n > 0) LAUNCH(k_max_track, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->flags.as<int>() + 4);
+  CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   // chunk list for the camera-major kernels (host, from cam_start)
   std::vector<int> h_start((size_t)n_cam + 1);
   std::vector<uint8_t> h_free(std::max(n_cam, 1));
@@ -289,6 +294,16 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   if (n_cam) CU(cudaMemcpyAsync(h_free.data(), ctx->cam_free.p, n_cam, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   ctx->has_dup = (n > 0 && n_cam <= DN_MAXCAM) ? (ctx->h_flags[3] != 0) : false;
+  ctx->max_track = ctx->h_flags[4];
+  ctx->use_tiles = (n > 0 && ctx->max_track <= NT_T / 2);
+  ctx->n_tiles = 0;
+  if (ctx->use_tiles) {
+    const int B = NT_T - ctx->max_track;
+    ctx->n_tiles = (int)((n + B - 1) / B);
+    ENSURE(int, ctx->tile_pt, (size_t)ctx->n_tiles + 1);
+    LAUNCH(k_tile_starts, cdiv(ctx->n_tiles + 1, 256), 256, ctx->n_tiles, B, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->tile_pt.as<int>());
+  }
+  ctx->grid_c = std::max(1, cdiv(n_cam, NT_C));
   long per = (n + 148L * 8 - 1) / (148L * 8);
   int chunk = (int)std::min<long>(4096, std::max<long>(NT_CM, ((per + NT_CM - 1) / NT_CM) * NT_CM));
   std::vector<int> cc, cb, ce, ccs((size_t)n_cam + 1, 0);
@@ -314,7 +329,10 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double4, ctx->rec_pm, n); ENSURE(double4, ctx->rec_cm, n);
   ENSURE(double, ctx->Craw, 9 * (size_t)n_pt); ENSURE(double4, ctx->sp4, n_pt); ENSURE(double4, ctx->lam4, n_pt);
   ENSURE(double, ctx->pblk, (size_t)PBLK * n_pt); ENSURE(double4, ctx->u4, n_pt);
-  ENSURE(double, ctx->part_pm, 5 * (size_t)std::max(grid_pm, 1)); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1));
+  ENSURE(double, ctx->part_pm, 5 * (size_t)std::max(std::max(grid_pm, ctx->n_tiles), 1));
+  ENSURE(double, ctx->xtab, (size_t)XTAB * n_cam); ENSURE(double, ctx->partA, ctx->grid_c); ENSURE(double, ctx->partB, ctx->grid_c);
+  ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8);
+  CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned), s)); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1));
   ENSURE(double, ctx->acc27, 27 * (size_t)n_cam); ENSURE(double, ctx->yhat, 6 * (size_t)n_cam);
   ENSURE(double, ctx->Bc, 36 * (size_t)n_cam); ENSURE(double, ctx->gc, 6 * (size_t)n_cam); ENSURE(double, ctx->sc, 6 * (size_t)n_cam);
   ENSURE(double, ctx->lamc, 6 * (size_t)n_cam); ENSURE(double, ctx->Md, 36 * (size_t)n_cam); ENSURE(double, ctx->Minv, 36 * (size_t)n_cam);
@@ -350,33 +368,81 @@ CmArgs cm_args(glba_ctx* ctx) {
   return A;
 }
 
+TileArgs tile_args(glba_ctx* ctx) { return TileArgs{ctx->tile_pt.as<int>(), ctx->pm_pt.as<int>()}; }
+
+int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
+  ReduceMap M{}; M.n = 5;
+  for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = (q == max_col); }
+  LAUNCH(k_reduce_partials, 1, NT_CAM, rows, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+  return GLBA_OK;
+}
+
+void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
+  const int c = ctx->cur;
+  if (ctx->use_tiles)
+    LAUNCH(k_linearize_tile, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
+           ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
+           o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
+  else
+    LAUNCH(k_linearize_pm, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
+           ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
+           o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
+}
+int pm_rows(const glba_ctx* ctx) { return ctx->use_tiles ? ctx->n_tiles : cdiv(ctx->n_pt, NT_PM); }
+
+void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg, int li) {
+  const int c = ctx->cur;
+  if (ctx->use_tiles)
+    LAUNCH(k_point_tile<0>, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), cg, li,
+           (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr);
+  else
+    LAUNCH(k_point_pass<0>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
+           ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr,
+           (const double4*)nullptr, 0.0, (double*)nullptr);
+}
+
+void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
+  const int c = ctx->cur, d = c ^ 1;
+  if (ctx->use_tiles)
+    LAUNCH(k_point_tile<1>, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr, 0,
+           (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
+           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>());
+  else
+    LAUNCH(k_point_pass<1>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
+           (double4*)nullptr, (const CgState*)nullptr, 0, (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(),
+           (const double*)ctx->camtab[d].as<double>(), (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(),
+           1.0 / radius, ctx->part_pm.as<double>());
+}
+
 // residual / weight / Jacobian records + Hessian blocks at the current state (K_A + K_B blocks)
 int do_linearize(glba_ctx* ctx, const glba_options* o, int first, double radius) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
-  const int grid_pm = cdiv(n_pt, NT_PM);
   mark(ctx, PH_LIN);
   if (n_pt) {
-    LAUNCH(k_linearize_pm, grid_pm, NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(),
-           ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
-    ReduceMap M{}; M.n = 5;
+    launch_linearize_points(ctx, o, first, radius);
     const int slots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
-    for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = (q == 4); }
-    LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+    reduce_pm_partials(ctx, pm_rows(ctx), slots, 4);
   }
   if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
   if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr);
+                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr, 0);
   if (ctx->world > 1) {
     AR(ctx->acc27.as<double>(), 27 * (size_t)n_cam, kNcclSum);
     AR(ctx->scal.as<double>() + S_COST, 4, kNcclSum);
     AR(ctx->scal.as<double>() + S_GMAX_P, 1, kNcclMax);
   }
-  if (n_cam) LAUNCH(k_cam_lin_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+  if (n_cam) LAUNCH(k_cam_lin_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->acc27.as<double>(), ctx->Bc.as<double>(), ctx->gc.as<double>(),
-                    ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, ctx->scal.as<double>());
+                    ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal,
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->scal.as<double>());
   mark(ctx, -1);
   return GLBA_OK;
 }
@@ -404,19 +470,46 @@ int do_schur(glba_ctx* ctx, double radius) {
   if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>());
   if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr);
+                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr, 0);
   if (ctx->world > 1) AR(ctx->acc27.as<double>(), 27 * (size_t)n_cam, kNcclSum);
-  if (n_cam) LAUNCH(k_cam_schur_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+  if (n_cam) LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
                     (const double*)ctx->acc27.as<double>(), (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(),
-                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->scal.as<double>());
+                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(),
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 1, ctx->scal.as<double>());
   mark(ctx, -1);
   return GLBA_OK;
+}
+
+void launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, CgState* cg, int li) {
+  const int c = ctx->cur;
+  const int n_cam = ctx->n_cam;
+  launch_point_pass0(ctx, o, cg, li);
+  LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+         (const double4*)ctx->u4.as<double4>(), (const CgState*)cg, li, ctx->part_cm.as<double>());
+  if (ctx->world > 1) {
+    LAUNCH(k_chunk_sum<6>, cdiv((long)n_cam * 6, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
+           ctx->yhat.as<double>(), (const CgState*)cg, li);
+    allreduce(ctx, ctx->yhat.as<double>(), 6 * (size_t)n_cam, kNcclSum);
+    LAUNCH(k_cg_q<false>, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->Bc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const double*)ctx->yhat.as<double>(),
+           (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), (const double*)ctx->cg_p.as<double>(),
+           ctx->cg_q.as<double>(), (const CgState*)cg, li, ctx->partA.as<double>());
+  } else {
+    LAUNCH(k_cg_q<true>, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->Bc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const double*)ctx->yhat.as<double>(),
+           (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), (const double*)ctx->cg_p.as<double>(),
+           ctx->cg_q.as<double>(), (const CgState*)cg, li, ctx->partA.as<double>());
+  }
+  LAUNCH(k_cg_xr, ctx->grid_c, NT_C, n_cam, (const double*)ctx->Minv.as<double>(), (const double*)ctx->cg_p.as<double>(), ctx->cg_q.as<double>(),
+         ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), (const CgState*)cg, li, (const double*)ctx->partA.as<double>(), ctx->partB.as<double>());
+  LAUNCH(k_cg_p, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
+         ctx->xtab.as<double>(), cg, li, (const double*)ctx->partA.as<double>(), (const double*)ctx->partB.as<double>());
 }
 
 // Block-Jacobi PCG on the implicit Schur complement; solution in cg_x.  Returns iterations in *iters.
 int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   const int c = ctx->cur;
-  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  const int n_cam = ctx->n_cam;
   *iters = 0;
   mark(ctx, PH_SOLVE);
   if (ctx->n_free_cam == 0 || n_cam == 0) {
@@ -427,31 +520,16 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   const int dim = 6 * ctx->n_free_cam;
   const int max_it = o->cg_max_iters > 0 ? o->cg_max_iters : std::min(4000, 4 * dim);
   CgState* cg = ctx->cgst.as<CgState>();
-  LAUNCH(k_cg_init, 1, NT_CAM, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(), (const double*)ctx->rhs.as<double>(),
-         ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->pg.as<double>(), cg, o->cg_rel_tol, max_it);
-  const int grid_pm = cdiv(n_pt, NT_PM);
-  const PmArgs PA = pm_args(ctx, o);
-  const CmArgs CA = cm_args(ctx);
+  LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
+         (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->xtab.as<double>(), cg,
+         o->cg_rel_tol, max_it, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
   const int poll = 8;
   int launched = 0;
   for (;;) {
-    for (int b = 0; b < poll && launched < max_it; ++b, ++launched) {
-      LAUNCH(k_point_pass<0>, grid_pm, NT_PM, PA, (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-             (const double*)ctx->pg.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), (const CgState*)cg,
-             (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr);
-      LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-             (const double4*)ctx->u4.as<double4>(), (const CgState*)cg, ctx->part_cm.as<double>());
-      LAUNCH(k_chunk_sum<6>, cdiv((long)n_cam * 6, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
-             ctx->yhat.as<double>(), (const CgState*)cg);
-      if (ctx->world > 1) AR(ctx->yhat.as<double>(), 6 * (size_t)n_cam, kNcclSum);
-      LAUNCH(k_cg_update, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-             (const double*)ctx->Bc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const double*)ctx->Minv.as<double>(),
-             (const double*)ctx->yhat.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->cg_q.as<double>(),
-             ctx->pg.as<double>(), cg);
-    }
+    for (int b = 0; b < poll && launched < max_it; ++b, ++launched) launch_cg_iteration(ctx, o, radius, cg, launched);
     CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_cg->done || launched >= max_it) break;
+    if (ctx->h_cg->done_at <= launched || launched >= max_it) break;
   }
   *iters = ctx->h_cg->iters;
   mark(ctx, -1);
@@ -498,21 +576,15 @@ bool want_dense(const glba_ctx* ctx, const glba_options* o) {
 int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
   const int c = ctx->cur, d = c ^ 1;
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
-  const int grid_pm = cdiv(n_pt, NT_PM);
   mark(ctx, PH_UPDATE);
-  if (n_cam) LAUNCH(k_cam_step, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+  if (n_cam) LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
-                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->yg.as<double>(),
-                    ctx->scal.as<double>());
+                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->scal.as<double>());
   if (n_pt) {
-    LAUNCH(k_point_pass<1>, grid_pm, NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->yg.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr,
-           (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
-           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>());
-    ReduceMap M{}; M.n = 5;
+    launch_point_pass1(ctx, o, radius);
     const int slots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
-    for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = 0; }
-    LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+    reduce_pm_partials(ctx, pm_rows(ctx), slots, -1);
   }
   if (ctx->world > 1) AR(ctx->scal.as<double>() + S_COST_C, 5, kNcclSum);
   mark(ctx, -1);
@@ -704,7 +776,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GLBA_E_CUDA; } ctx->own_stream = true; }
   if (cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * NSCAL) != cudaSuccess || cudaMallocHost((void**)&ctx->h_cg, sizeof(CgState)) != cudaSuccess ||
-      cudaMallocHost((void**)&ctx->h_flags, 4 * sizeof(int)) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
+      cudaMallocHost((void**)&ctx->h_flags, 8 * sizeof(int)) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   if (cfg->world > 1) {
     if (!cfg->nccl_unique_id || !g_nccl.load()) { glba_destroy(ctx); return GLBA_E_NCCL; }
     ncclUniqueId id; std::memcpy(&id, cfg->nccl_unique_id, sizeof(id));
@@ -725,7 +797,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->scal, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -794,23 +866,19 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   int st = validate_options(ctx, opt);
   if (st) return st;
   std::memset(out, 0, sizeof(*out));
-  const int c = ctx->cur, d = c ^ 1;
+  const int c = ctx->cur;
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
-  const int grid_pm = cdiv(n_pt, NT_PM);
   if (n_pt == 0 || ctx->n_chunks == 0) return GLBA_OK;
   // a complete pass first so every buffer the kernels read is valid
   if ((st = do_linearize(ctx, opt, 1, radius))) return st;
   if ((st = do_schur(ctx, radius))) return st;
   CgState* cg = ctx->cgst.as<CgState>();
-  LAUNCH(k_cg_init, 1, NT_CAM, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(), (const double*)ctx->rhs.as<double>(),
-         ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->pg.as<double>(), cg, 0.0, 1 << 30);
-  LAUNCH(k_cam_step, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
-         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
-         (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->yg.as<double>(), ctx->scal.as<double>());
+  LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
+         (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->xtab.as<double>(), cg,
+         0.0, 1 << 30, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->ev_used = 0;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const PmArgs PA = pm_args(ctx, opt);
   const CmArgs CA = cm_args(ctx);
   auto timed = [&](auto&& launch, double* ms_out) -> int {
     launch();                                   // warm
@@ -822,44 +890,38 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
     *ms_out = ms / reps;
     return GLBA_OK;
   };
-  st = timed([&] { LAUNCH(k_linearize_pm, grid_pm, NT_PM, PA, (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(),
-           ctx->pblk.as<double>(), 0, opt->jacobi_scaling, opt->min_lm_diagonal, opt->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>()); }, &out->linearize_pm_ms);
-  if (st) return st;
-  st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           ctx->part_cm.as<double>()); }, &out->linearize_cm_ms);
-  if (st) return st;
-  st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms);
-  if (st) return st;
-  st = timed([&] { LAUNCH(k_point_pass<0>, grid_pm, NT_PM, PA, (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->pg.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), (const CgState*)nullptr,
-           (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr); }, &out->spmv_pm_ms);
-  if (st) return st;
-  st = timed([&] { LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double4*)ctx->u4.as<double4>(), (const CgState*)nullptr, ctx->part_cm.as<double>()); }, &out->spmv_cm_ms);
-  if (st) return st;
-  st = timed([&] { LAUNCH(k_point_pass<1>, grid_pm, NT_PM, PA, (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->yg.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr,
-           (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
-           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->backsub_cost_ms);
-  if (st) return st;
-  st = timed([&] { LAUNCH(k_point_damp, grid_pm, NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
-           (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms);
-  if (st) return st;
+  if ((st = timed([&] { launch_linearize_points(ctx, opt, 0, radius); }, &out->linearize_pm_ms))) return st;
+  if ((st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           ctx->part_cm.as<double>()); }, &out->linearize_cm_ms))) return st;
+  if ((st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms))) return st;
+  if ((st = timed([&] { launch_point_pass0(ctx, opt, (const CgState*)nullptr, 0); }, &out->spmv_pm_ms))) return st;
+  if ((st = timed([&] { LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double4*)ctx->u4.as<double4>(), (const CgState*)nullptr, 0, ctx->part_cm.as<double>()); }, &out->spmv_cm_ms))) return st;
+  // candidate = current state + PCG start vector (any finite step exercises the same code)
+  const int d = c ^ 1;
+  LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
+         (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
+         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->scal.as<double>());
+  if ((st = timed([&] { launch_point_pass1(ctx, opt, radius); }, &out->backsub_cost_ms))) return st;
+  if ((st = timed([&] { LAUNCH(k_point_damp, cdiv(n_pt, NT_PM), NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
+           (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms))) return st;
+  // every camera-sized / reduction kernel of one linearise + Schur pass
   st = timed([&] {
-    ReduceMap M{}; M.n = 5; const int slots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
-    for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = (q == 4); }
-    LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+    const int slots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
+    reduce_pm_partials(ctx, pm_rows(ctx), slots, 4);
     for (int rep2 = 0; rep2 < 2; ++rep2)
       LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
-             ctx->acc27.as<double>(), (const CgState*)nullptr);
-    LAUNCH(k_cam_lin_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+             ctx->acc27.as<double>(), (const CgState*)nullptr, 0);
+    LAUNCH(k_cam_lin_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->acc27.as<double>(), ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(),
-           ctx->lamc.as<double>(), 0, opt->jacobi_scaling, opt->min_lm_diagonal, opt->max_lm_diagonal, ctx->scal.as<double>());
-    LAUNCH(k_cam_schur_finalize, 1, NT_CAM, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+           ctx->lamc.as<double>(), 0, opt->jacobi_scaling, opt->min_lm_diagonal, opt->max_lm_diagonal, ctx->partc.as<double>(),
+           ctx->counters.as<unsigned>() + 0, ctx->scal.as<double>());
+    LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
            (const double*)ctx->acc27.as<double>(), (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(),
-           1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->scal.as<double>()); }, &out->small_kernels_ms);
+           1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 1,
+           ctx->scal.as<double>()); }, &out->small_kernels_ms);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return st;
 }

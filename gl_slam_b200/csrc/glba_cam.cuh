@@ -1,0 +1,434 @@
+// glba_cam.cuh — camera-sized kernels (<= 10^4 cameras): Hessian-block finalisation, block-Jacobi
+// preconditioner, the vector half of PCG, candidate cameras.  One thread per camera, many small CTAs;
+// scalars are reduced per CTA and summed in CTA order by the last CTA to finish (fixed order).
+#pragma once
+#include <climits>
+#include "glba_kernels.cuh"
+#include "glba_tiles.cuh"
+
+namespace glba {
+
+constexpr int NT_C = 64;
+
+__device__ __forceinline__ void mm3(const double* A, const double* B, double* C) {        // C = A B
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+}
+__device__ __forceinline__ void mtm3(const double* A, const double* B, double* C) {       // C = A' B
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r] * B[c] + A[3 + r] * B[3 + c] + A[6 + r] * B[6 + c];
+}
+
+// Bout (6x6 row-major, full) = T' A T with T = blockdiag(G, R), A symmetric given by its 21 upper entries.
+__device__ __forceinline__ void congruence_T(const double* __restrict__ a21, const double* G, const double* R, double* Bout) {
+  double A11[9], A12[9], A22[9], t[9], o[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      A11[r * 3 + c] = (r <= c) ? a21[tri(r, c)] : a21[tri(c, r)];
+      A12[r * 3 + c] = a21[tri(r, 3 + c)];
+      A22[r * 3 + c] = (r <= c) ? a21[tri(3 + r, 3 + c)] : a21[tri(3 + c, 3 + r)];
+    }
+  mm3(A11, G, t); mtm3(G, t, o);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Bout[r * 6 + c] = o[r * 3 + c];
+  mm3(A12, R, t); mtm3(G, t, o);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { Bout[r * 6 + 3 + c] = o[r * 3 + c]; Bout[(3 + c) * 6 + r] = o[r * 3 + c]; }
+  mm3(A22, R, t); mtm3(R, t, o);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Bout[(3 + r) * 6 + 3 + c] = o[r * 3 + c];
+  // symmetrise exactly (the two triangular halves of a congruence differ in the last bit)
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = r + 1; c < 6; ++c) Bout[c * 6 + r] = Bout[r * 6 + c];
+}
+
+// fully unrolled 6x6 SPD inverse (registers only); false if not positive definite
+__device__ __forceinline__ bool inv6_spd_reg(const double* A, double* Ai) {
+  double L[21];      // lower triangle, row-major packed: L[r(r+1)/2 + c]
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    const double ljj = sqrt(d);
+    L[j * (j + 1) / 2 + j] = ljj;
+    const double inv = 1.0 / ljj;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+      L[i * (i + 1) / 2 + j] = s * inv;
+    }
+  }
+  // Linv (lower), then Ai = Linv' Linv
+  double Li[21];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    Li[c * (c + 1) / 2 + c] = 1.0 / L[c * (c + 1) / 2 + c];
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = c; k < r; ++k) s -= L[r * (r + 1) / 2 + k] * Li[k * (k + 1) / 2 + c];
+      Li[r * (r + 1) / 2 + c] = s / L[r * (r + 1) / 2 + r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = r; c < 6; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = c; k < 6; ++k) s += Li[k * (k + 1) / 2 + r] * Li[k * (k + 1) / 2 + c];
+      Ai[r * 6 + c] = s; Ai[c * 6 + r] = s;
+    }
+  return ok;
+}
+
+// CTA partials -> scalars, summed in CTA order by whichever CTA finishes last.
+template <int NV>
+__device__ __forceinline__ bool finish_scalars(const double (&v)[NV], const bool (&is_max)[NV], const int (&slot)[NV], double* part,
+                                               unsigned* counter, double* scal, double* sm /* NV*NT_C/32 */, double* smo /* NV */) {
+  // block reduce (sum or max per entry)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(0xffffffffu, x, o); x = is_max[i] ? fmax(x, y) : x + y; }
+    if (lane == 0) sm[wid * NV + i] = x;
+  }
+  __syncthreads();
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = sm[i];
+      for (int w = 1; w < NT_C / 32; ++w) x = is_max[i] ? fmax(x, sm[w * NV + i]) : x + sm[w * NV + i];
+      part[(size_t)blockIdx.x * NV + i] = x;
+    }
+    __threadfence();
+    const unsigned t = atomicInc(counter, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = __ldcg(part + i);
+      for (unsigned b = 1; b < gridDim.x; ++b) { const double y = __ldcg(part + (size_t)b * NV + i); x = is_max[i] ? fmax(x, y) : x + y; }
+      smo[i] = x;
+      if (slot[i] >= 0) scal[slot[i]] = x;
+    }
+  }
+  return s_last;     // true in every thread of the last CTA; its thread 0 has the totals in smo[]
+}
+
+// B_i = T' A T, g_i = T' ghat; Jacobi scale (iteration 0); lam_c = clamp(s^2 h)/s^2; |x_c|^2, max |g_c|.
+__global__ void __launch_bounds__(NT_C)
+k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
+              const double* __restrict__ acc27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
+              double* __restrict__ lamc, const int first, const int jacobi, const double min_diag, const double max_diag,
+              double* part, unsigned* counter, double* scal) {
+  __shared__ double sm[2 * NT_C / 32];
+  __shared__ double smo[2];
+  const int i = blockIdx.x * NT_C + threadIdx.x;
+  double xn2 = 0.0, gmax = 0.0;
+  if (i < n_cam) {
+    double* B = Bc + (size_t)36 * i;
+    if (!cam_free[i]) {
+#pragma unroll
+      for (int q = 0; q < 36; ++q) B[q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) { gc[6 * i + q] = 0.0; lamc[6 * i + q] = 0.0; if (first) sc[6 * i + q] = 1.0; }
+    } else {
+      const double* a = acc27 + (size_t)27 * i;
+      const double* ct = camtab + (size_t)CAMTAB * i;
+      double G[9], R[9], Bl[36], gh[6], g6[6];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { R[q] = ct[q]; G[q] = ct[CT_G + q]; }
+      congruence_T(a, G, R, Bl);
+#pragma unroll
+      for (int q = 0; q < 36; ++q) B[q] = Bl[q];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) gh[q] = a[21 + q];
+      apply_Tt(ct, gh, g6);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        gc[6 * i + r] = g6[r];
+        gmax = fmax(gmax, fabs(g6[r]));
+        const double h = Bl[r * 7];
+        double sv;
+        if (first) { sv = jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0; sc[6 * i + r] = sv; } else sv = sc[6 * i + r];
+        const double s2 = sv * sv;
+        lamc[6 * i + r] = fmin(fmax(s2 * h, min_diag), max_diag) / s2;
+        xn2 += cam[6 * i + r] * cam[6 * i + r];
+      }
+    }
+  }
+  const double v[2] = {xn2, gmax};
+  const bool mx[2] = {false, true};
+  const int slot[2] = {S_XN2_C, S_GMAX_C};
+  finish_scalars<2>(v, mx, slot, part, counter, scal, sm, smo);
+}
+
+// M_i = B_i + lam/radius - T' Mhat T (diagonal block of S), rhs_i = g_i - T' rhat, Minv_i.
+__global__ void __launch_bounds__(NT_C)
+k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ acc27,
+                const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+                double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal) {
+  __shared__ double sm[NT_C / 32];
+  __shared__ double smo[1];
+  const int i = blockIdx.x * NT_C + threadIdx.x;
+  double notpd = 0.0;
+  if (i < n_cam) {
+    double* M = Md + (size_t)36 * i; double* Mi = Minv + (size_t)36 * i;
+    if (!cam_free[i]) {
+#pragma unroll
+      for (int q = 0; q < 36; ++q) { M[q] = 0.0; Mi[q] = 0.0; }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) rhs[6 * i + q] = 0.0;
+    } else {
+      const double* a = acc27 + (size_t)27 * i;
+      const double* ct = camtab + (size_t)CAMTAB * i;
+      double G[9], R[9], Ml[36], Il[36], rh[6], r6[6];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { R[q] = ct[q]; G[q] = ct[CT_G + q]; }
+      congruence_T(a, G, R, Ml);
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double v = Bc[(size_t)36 * i + r * 6 + c] - Ml[r * 6 + c];
+          if (r == c) v += lamc[6 * i + r] * inv_radius;
+          Ml[r * 6 + c] = v;
+        }
+#pragma unroll
+      for (int q = 0; q < 36; ++q) M[q] = Ml[q];
+      if (!inv6_spd_reg(Ml, Il)) {
+        notpd = 1.0;
+#pragma unroll
+        for (int q = 0; q < 36; ++q) Il[q] = 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 36; ++q) Mi[q] = Il[q];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) rh[q] = a[21 + q];
+      apply_Tt(ct, rh, r6);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) rhs[6 * i + r] = gc[6 * i + r] - r6[r];
+    }
+  }
+  const double v[1] = {notpd};
+  const bool mx[1] = {false};
+  const int slot[1] = {S_NOTPD_C};
+  finish_scalars<1>(v, mx, slot, part, counter, scal, sm, smo);
+}
+
+__device__ __forceinline__ void write_xtab(double* __restrict__ xr, const double* ct, const double* x6) {
+  double t[6];
+  apply_T(ct, x6, t);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) xr[q] = t[q];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) xr[6 + q] = ct[q];
+  xr[15] = (ct[CT_SV] != 0.0 || ct[CT_SV + 1] != 0.0 || ct[CT_SV + 2] != 0.0) ? 1.0 : 0.0;
+}
+
+// PCG start: x = 0, r = rhs, z = Minv r, p = z, rz = r.z
+__global__ void __launch_bounds__(NT_C)
+k_cg_start(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ Minv, const double* __restrict__ rhs,
+           double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double* __restrict__ xtab, CgState* cg,
+           const double tol, const int max_iters, double* part, unsigned* counter) {
+  __shared__ double sm[NT_C / 32];
+  __shared__ double smo[1];
+  const int i = blockIdx.x * NT_C + threadIdx.x;
+  double rz = 0.0;
+  if (i < n_cam) {
+    double rr[6], z[6];
+    const double* Mi = Minv + (size_t)36 * i;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { rr[q] = rhs[6 * i + q]; x[6 * i + q] = 0.0; r[6 * i + q] = rr[q]; }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c];
+      z[a] = s; rz += s * rr[a]; p[6 * i + a] = s;
+    }
+    write_xtab(xtab + (size_t)XTAB * i, camtab + (size_t)CAMTAB * i, z);
+  }
+  const double v[1] = {rz};
+  const bool mx[1] = {false};
+  const int slot[1] = {-1};
+  const bool last = finish_scalars<1>(v, mx, slot, part, counter, nullptr, sm, smo);
+  if (last && threadIdx.x == 0) {
+    cg->rzbuf[0] = smo[0]; cg->rzbuf[1] = 0.0; cg->rz0 = smo[0]; cg->tol = tol;
+    cg->iters = 0; cg->max_iters = max_iters; cg->reason = 0;
+    cg->done_at = (smo[0] > 0.0) ? INT_MAX : 0;
+  }
+}
+
+// q_i = (B_i + lam/radius) p_i - T_i' yhat_i, partial p.q per CTA.  FUSE: yhat_i summed here from the chunk partials.
+template <bool FUSE>
+__global__ void __launch_bounds__(NT_C)
+k_cg_q(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ Bc,
+       const double* __restrict__ lamc, const double inv_radius, const double* __restrict__ yhat, const int* __restrict__ cam_chunk_start,
+       const double* __restrict__ part6, const double* __restrict__ p, double* __restrict__ q, const CgState* __restrict__ cg, const int li,
+       double* __restrict__ partA) {
+  __shared__ double sm[NT_C / 32];
+  __shared__ double smo[1];
+  if (cg->done_at <= li) return;
+  const int i = blockIdx.x * NT_C + threadIdx.x;
+  double pq = 0.0;
+  if (i < n_cam) {
+    if (!cam_free[i]) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) q[6 * i + a] = 0.0;
+    } else {
+      double yh[6], ty[6], pi[6];
+      if (FUSE) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) yh[a] = 0.0;
+        for (int ch = cam_chunk_start[i]; ch < cam_chunk_start[i + 1]; ++ch)
+#pragma unroll
+          for (int a = 0; a < 6; ++a) yh[a] += part6[(size_t)6 * ch + a];
+      } else {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) yh[a] = yhat[6 * (size_t)i + a];
+      }
+      apply_Tt(camtab + (size_t)CAMTAB * i, yh, ty);
+      const double* B = Bc + (size_t)36 * i;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) pi[a] = p[6 * i + a];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double s = lamc[6 * i + a] * inv_radius * pi[a];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s += B[a * 6 + c] * pi[c];
+        s -= ty[a];
+        q[6 * i + a] = s; pq += s * pi[a];
+      }
+    }
+  }
+  double v[1] = {pq};
+  block_reduce<1, NT_C>(v, sm, smo);
+  if (threadIdx.x == 0) partA[blockIdx.x] = smo[0];
+}
+
+__device__ __forceinline__ double sum_parts(const double* __restrict__ part, const int n, double* s_out) {
+  if (threadIdx.x == 0) { double s = 0.0; for (int b = 0; b < n; ++b) s += part[b]; *s_out = s; }
+  __syncthreads();
+  return *s_out;
+}
+
+// x += alpha p, r -= alpha q, z = Minv r (stored in q), partial r.z per CTA
+__global__ void __launch_bounds__(NT_C)
+k_cg_xr(const int n_cam, const double* __restrict__ Minv, const double* __restrict__ p, double* __restrict__ q, double* __restrict__ x,
+        double* __restrict__ r, const CgState* __restrict__ cg, const int li, const double* __restrict__ partA, double* __restrict__ partB) {
+  __shared__ double sm[NT_C / 32];
+  __shared__ double smo[1];
+  __shared__ double s_pq;
+  if (cg->done_at <= li) return;
+  const double pq = sum_parts(partA, gridDim.x, &s_pq);
+  const double alpha = (pq > 0.0) ? cg->rzbuf[li & 1] / pq : 0.0;
+  const int i = blockIdx.x * NT_C + threadIdx.x;
+  double rz = 0.0;
+  if (i < n_cam) {
+    double rr[6];
+    const double* Mi = Minv + (size_t)36 * i;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { x[6 * i + a] += alpha * p[6 * i + a]; rr[a] = r[6 * i + a] - alpha * q[6 * i + a]; r[6 * i + a] = rr[a]; }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c];
+      q[6 * i + a] = s; rz += s * rr[a];
+    }
+  }
+  double v[1] = {rz};
+  block_reduce<1, NT_C>(v, sm, smo);
+  if (threadIdx.x == 0) partB[blockIdx.x] = smo[0];
+}
+
+// p = z + beta p, gather table, stop test (CTA 0 publishes for launches li+1 onwards)
+__global__ void __launch_bounds__(NT_C)
+k_cg_p(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ z, double* __restrict__ p, double* __restrict__ xtab,
+       CgState* cg, const int li, const double* __restrict__ partA, const double* __restrict__ partB) {
+  __shared__ double s_rz, s_pq;
+  if (cg->done_at <= li) return;
+  const double rz1 = sum_parts(partB, gridDim.x, &s_rz);
+  const double rz_old = cg->rzbuf[li & 1];
+  const double beta = (rz_old > 0.0) ? rz1 / rz_old : 0.0;
+  const int i = blockIdx.x * NT_C + threadIdx.x;
+  if (i < n_cam) {
+    double pn[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { pn[a] = z[6 * i + a] + beta * p[6 * i + a]; p[6 * i + a] = pn[a]; }
+    double t[6];
+    apply_T(camtab + (size_t)CAMTAB * i, pn, t);
+    double* xr = xtab + (size_t)XTAB * i;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) xr[a] = t[a];
+  }
+  if (blockIdx.x == 0) {
+    const double pq = sum_parts(partA, gridDim.x, &s_pq);
+    if (threadIdx.x == 0) {
+      cg->rzbuf[(li + 1) & 1] = rz1;
+      cg->iters = li + 1;
+      if (!(pq > 0.0)) { cg->done_at = li + 1; cg->reason = 2; }
+      else if (sqrt(rz1) <= cg->tol * sqrt(cg->rz0)) { cg->done_at = li + 1; cg->reason = 1; }
+      else if (li + 1 >= cg->max_iters) { cg->done_at = li + 1; cg->reason = 3; }
+    }
+  }
+}
+
+// candidate cameras cam_c = cam - y, their table, gather table [T y | R | sv] for the back-substitution,
+// camera parts of |y|^2, y.g, y' Lambda y
+__global__ void __launch_bounds__(NT_C)
+k_cam_step2(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
+            const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+            double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ xtab, double* part, unsigned* counter, double* scal) {
+  __shared__ double sm[3 * NT_C / 32];
+  __shared__ double smo[3];
+  const int i = blockIdx.x * NT_C + threadIdx.x;
+  double yn2 = 0.0, ygd = 0.0, yly = 0.0;
+  if (i < n_cam) {
+    double yi[6], cc[6];
+    const bool f = cam_free[i] != 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      yi[a] = f ? y[6 * i + a] : 0.0;
+      cc[a] = cam[6 * i + a] - yi[a];
+      cam_c[6 * i + a] = cc[a];
+      yn2 += yi[a] * yi[a]; ygd += yi[a] * gc[6 * i + a]; yly += lamc[6 * i + a] * inv_radius * yi[a] * yi[a];
+    }
+    cam_table_row(cc, camtab_c + (size_t)CAMTAB * i);
+    write_xtab(xtab + (size_t)XTAB * i, camtab + (size_t)CAMTAB * i, yi);
+  }
+  const double v[3] = {yn2, ygd, yly};
+  const bool mx[3] = {false, false, false};
+  const int slot[3] = {S_YN2_C, S_YG_C, S_YLY_C};
+  finish_scalars<3>(v, mx, slot, part, counter, scal, sm, smo);
+}
+
+}  // namespace glba

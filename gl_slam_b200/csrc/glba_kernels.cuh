@@ -22,7 +22,8 @@
 
 namespace glba {
 
-constexpr int CAMTAB = 24;  // doubles per camera: R[9] G[9] c[3] sv[3]
+constexpr int CAMTAB = 24;  // doubles per camera: R[9] c[3] | G[9] sv[3]  (192 B; R,c = the first three 32-byte sectors)
+constexpr int CT_C = 9, CT_G = 12, CT_SV = 21;
 constexpr int PBLK = 12;    // doubles per point block: Cinv[6] (00,01,02,11,12,22) u0[3] pad[3]  (96 B = 3 sectors)
 constexpr int NT_PM = 128;  // threads per CTA, point-major kernels (one thread per point)
 constexpr int NT_CM = 256;  // threads per CTA, camera-major kernels (one CTA per chunk of one camera)
@@ -53,22 +54,42 @@ struct Intr { double fx, fy, cx, cy; };
 struct LossP { int kind; double a; };
 
 struct CgState {
-  double rz, rz0, pq;
-  int iters, done, max_iters, pad;
-  double tol;
+  double rzbuf[2];   // r.z before launch li is rzbuf[li & 1]
+  double rz0, tol;
+  int done_at;       // kernels of PCG launch li exit when done_at <= li (published by launch done_at-1)
+  int reason;        // 1 converged, 2 breakdown (p'Sp <= 0), 3 iteration cap
+  int iters, max_iters;
 };
+constexpr int XTAB = 16;   // per-camera gather row of the point passes (128 B): xg[6] = T x | R[9] | small-angle flag
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double4 ldg4(const double4* p) {
-  // two 16-byte read-only loads; a 32-byte record never straddles a sector
-  const double2* q = reinterpret_cast<const double2*>(p);
-  const double2 a = __ldg(q), b = __ldg(q + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
+// sm_100 256-bit global accesses (SASS LDG.E.ENL2.256 / STG.E.ENL2.256): one instruction, one L1 wavefront
+// per 32-byte record.  Every record / table row here is 32-byte aligned.
+__device__ __forceinline__ double4 ldg4(const double4* p) {           // read-only (non-coherent) path
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double4 ld4(const double4* p) {            // coherent (data written by this kernel)
+  double4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+  return r;
 }
 __device__ __forceinline__ void st4(double4* p, const double4 v) {
-  double2* q = reinterpret_cast<double2*>(p);
-  q[0] = make_double2(v.x, v.y);
-  q[1] = make_double2(v.z, v.w);
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+// first 96 bytes of a camera-table row: R (row-major) and the centre, as three 256-bit gathers
+__device__ __forceinline__ void load_Rc(const double* __restrict__ ct, double* R /*9*/, double* c /*3*/) {
+  const double4* q = reinterpret_cast<const double4*>(ct);
+  const double4 a = ldg4(q), b = ldg4(q + 1), d = ldg4(q + 2);
+  R[0] = a.x; R[1] = a.y; R[2] = a.z; R[3] = a.w; R[4] = b.x; R[5] = b.y; R[6] = b.z; R[7] = b.w; R[8] = d.x;
+  c[0] = d.y; c[1] = d.z; c[2] = d.w;
+}
+// damped point block row (96 B): Cinv[6], u0[3]
+__device__ __forceinline__ void load_pblk(const double* __restrict__ pb, double* Ci /*6*/, double* u0 /*3*/) {
+  const double4* q = reinterpret_cast<const double4*>(pb);
+  const double4 a = ldg4(q), b = ldg4(q + 1), d = ldg4(q + 2);
+  Ci[0] = a.x; Ci[1] = a.y; Ci[2] = a.z; Ci[3] = a.w; Ci[4] = b.x; Ci[5] = b.y; u0[0] = b.z; u0[1] = b.w; u0[2] = d.x;
 }
 
 // rho(s): returns 1/2-free rho and sqrt(rho') (Ceres corrector with rho'' <= 0: plain IRLS scaling)
@@ -93,7 +114,7 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ ct, const
                                             const double Z, const Intr K, const double u, const double v,
                                             double& xh, double& yh, double& iz, double& rx, double& ry) {
   // plain loads: ct may live in shared memory (pose-only kernel); global callers pass __restrict__ const
-  const double qx = X - ct[18], qy = Y - ct[19], qz = Z - ct[20];
+  const double qx = X - ct[CT_C], qy = Y - ct[CT_C + 1], qz = Z - ct[CT_C + 2];
   const double px = ct[0] * qx + ct[1] * qy + ct[2] * qz;
   const double py = ct[3] * qx + ct[4] * qy + ct[5] * qz;
   const double pz = ct[6] * qx + ct[7] * qy + ct[8] * qz;
@@ -252,9 +273,9 @@ __device__ inline void cam_table_row(const double* cam, double* ct) {
     sv[0] = w0; sv[1] = w1; sv[2] = w2;
   }
 #pragma unroll
-  for (int i = 0; i < 9; ++i) { ct[i] = R[i]; ct[9 + i] = G[i]; }
-  ct[18] = cam[3]; ct[19] = cam[4]; ct[20] = cam[5];
-  ct[21] = sv[0]; ct[22] = sv[1]; ct[23] = sv[2];
+  for (int i = 0; i < 9; ++i) { ct[i] = R[i]; ct[CT_G + i] = G[i]; }
+  ct[CT_C] = cam[3]; ct[CT_C + 1] = cam[4]; ct[CT_C + 2] = cam[5];
+  ct[CT_SV] = sv[0]; ct[CT_SV + 1] = sv[1]; ct[CT_SV + 2] = sv[2];
 }
 
 __global__ void k_cam_prep(const int n_cam, const double* __restrict__ cam, double* __restrict__ camtab) {
@@ -425,7 +446,7 @@ struct CmArgs {
 };
 
 // Camera half of K_B: A_i = sum J^'J^ (21 upper entries), ghat_i = sum J^' r~ (6), per chunk.
-__global__ void __launch_bounds__(NT_CM)
+__global__ void __launch_bounds__(NT_CM, 2)
 k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
                double* __restrict__ part /* [n_chunks][27] */) {
   __shared__ double sm[27 * NT_CM / 32];
@@ -461,7 +482,7 @@ k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double*
 
 // Schur half: for every observation of the camera, E = J~p Cinv J~p' (2x2) and f = J~p u0 (2):
 //   Mhat_i = sum J^' E J^ (21),  rhat_i = sum J^' f (6).
-__global__ void __launch_bounds__(NT_CM)
+__global__ void __launch_bounds__(NT_CM, 2)
 k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
            const double* __restrict__ pblk, double* __restrict__ part /* [n_chunks][27] */) {
   __shared__ double sm[27 * NT_CM / 32];
@@ -481,22 +502,22 @@ k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __r
     for (int k = b + threadIdx.x; k < e; k += NT_CM) {
       const double4 rec = ldg4(rec_cm + k);
       const int j = __ldg(A.cm_pt + k);
-      const double2* pb = reinterpret_cast<const double2*>(pblk + (size_t)PBLK * j);
-      const double2 c01 = __ldg(pb), c23 = __ldg(pb + 1), c45 = __ldg(pb + 2), u01 = __ldg(pb + 3), u2_ = __ldg(pb + 4);
+      double Ci[6], u0[3];
+      load_pblk(pblk + (size_t)PBLK * j, Ci, u0);
       double ap[3], bp[3];
       jp_rows(rec, R, A.K, ap, bp);
-      // t = Cinv ap, s = Cinv bp   (Cinv = [c01.x c01.y c23.x; . c23.y c45.x; . . c45.y])
-      const double ta0 = c01.x * ap[0] + c01.y * ap[1] + c23.x * ap[2];
-      const double ta1 = c01.y * ap[0] + c23.y * ap[1] + c45.x * ap[2];
-      const double ta2 = c23.x * ap[0] + c45.x * ap[1] + c45.y * ap[2];
-      const double tb0 = c01.x * bp[0] + c01.y * bp[1] + c23.x * bp[2];
-      const double tb1 = c01.y * bp[0] + c23.y * bp[1] + c45.x * bp[2];
-      const double tb2 = c23.x * bp[0] + c45.x * bp[1] + c45.y * bp[2];
+      // t = Cinv ap, s = Cinv bp   (Cinv packed 00,01,02,11,12,22)
+      const double ta0 = Ci[0] * ap[0] + Ci[1] * ap[1] + Ci[2] * ap[2];
+      const double ta1 = Ci[1] * ap[0] + Ci[3] * ap[1] + Ci[4] * ap[2];
+      const double ta2 = Ci[2] * ap[0] + Ci[4] * ap[1] + Ci[5] * ap[2];
+      const double tb0 = Ci[0] * bp[0] + Ci[1] * bp[1] + Ci[2] * bp[2];
+      const double tb1 = Ci[1] * bp[0] + Ci[3] * bp[1] + Ci[4] * bp[2];
+      const double tb2 = Ci[2] * bp[0] + Ci[4] * bp[1] + Ci[5] * bp[2];
       const double E00 = ap[0] * ta0 + ap[1] * ta1 + ap[2] * ta2;
       const double E01 = ap[0] * tb0 + ap[1] * tb1 + ap[2] * tb2;
       const double E11 = bp[0] * tb0 + bp[1] * tb1 + bp[2] * tb2;
-      const double f0 = ap[0] * u01.x + ap[1] * u01.y + ap[2] * u2_.x;
-      const double f1 = bp[0] * u01.x + bp[1] * u01.y + bp[2] * u2_.x;
+      const double f0 = ap[0] * u0[0] + ap[1] * u0[1] + ap[2] * u0[2];
+      const double f1 = bp[0] * u0[0] + bp[1] * u0[1] + bp[2] * u0[2];
       double a[6], bb[6];
       jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
       // J^' E J^ = (E00 a + E01 b) a' + (E01 a + E11 b) b'
@@ -519,10 +540,10 @@ k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __r
 // Second half of the implicit product: yhat_i = sum_j J^' (J~p u_j), u_j from the point-major pass.
 __global__ void __launch_bounds__(NT_CM)
 k_spmv_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
-          const double4* __restrict__ u4, const CgState* __restrict__ cg, double* __restrict__ part /* [n_chunks][6] */) {
+          const double4* __restrict__ u4, const CgState* __restrict__ cg, const int li, double* __restrict__ part /* [n_chunks][6] */) {
   __shared__ double sm[6 * NT_CM / 32];
   __shared__ double smo[6];
-  if (cg && cg->done) return;
+  if (cg && cg->done_at <= li) return;
   const int ch = blockIdx.x;
   const int cam = A.chunk_cam[ch];
   double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -554,8 +575,8 @@ k_spmv_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __re
 // Sum the chunk partials of every camera in chunk order (fixed): acc[cam][NV].
 template <int NV>
 __global__ void k_chunk_sum(const int n_cam, const int* __restrict__ cam_chunk_start, const double* __restrict__ part,
-                            double* __restrict__ acc, const CgState* __restrict__ cg) {
-  if (cg && cg->done) return;
+                            double* __restrict__ acc, const CgState* __restrict__ cg, const int li) {
+  if (cg && cg->done_at <= li) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_cam * NV) return;
   const int cam = t / NV, q = t - cam * NV;
@@ -573,13 +594,13 @@ __global__ void k_chunk_sum(const int n_cam, const int* __restrict__ cam_chunk_s
 template <int MODE>
 __global__ void __launch_bounds__(NT_PM)
 k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* __restrict__ camtab,
-             const double* __restrict__ xg /* [n_cam][6] */, const double* __restrict__ pblk,
-             double4* __restrict__ u4, const CgState* __restrict__ cg,
+             const double* __restrict__ xtab /* [n_cam][XTAB] */, const double* __restrict__ pblk,
+             double4* __restrict__ u4, const CgState* __restrict__ cg, const int li,
              // MODE 1 only:
              const double4* __restrict__ pt, double4* __restrict__ pt_c, const double* __restrict__ camtab_c,
              const double* __restrict__ Craw, const double4* __restrict__ lam4, const double inv_radius,
              double* __restrict__ part /* [grid][5] */) {
-  if (MODE == 0 && cg && cg->done) return;
+  if (MODE == 0 && cg && cg->done_at <= li) return;
   const int j = blockIdx.x * NT_PM + threadIdx.x;
   double cost_c = 0.0, yn2 = 0.0, yg = 0.0, yly = 0.0, bad = 0.0;
   if (j < A.n_pt) {
@@ -591,7 +612,7 @@ k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* _
         const int i = __ldg(A.pm_cam + k);
         const double4 rec = ldg4(rec_pm + k);
         const double* ct = camtab + (size_t)CAMTAB * i;
-        const double* x = xg + 6 * (size_t)i;
+        const double* x = xtab + (size_t)XTAB * i;
         double a[6], bb[6];
         jhat_rows(rec, __ldg(ct + 21), __ldg(ct + 22), __ldg(ct + 23), A.K, a, bb);
         double al0 = 0, al1 = 0;
@@ -675,219 +696,20 @@ k_reduce_partials(const int rows, const int nv, const double* __restrict__ part,
 // upper-triangular index of (r,c), r<=c, in the 21-entry packing used above
 __device__ __forceinline__ int tri(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
 
-// B_i = T' A T, g_i = T' ghat from acc27; Jacobi scale (iteration 0), lam_c = clamp(s^2 h)/s^2.
-__global__ void __launch_bounds__(NT_CAM)
-k_cam_lin_finalize(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam,
-                   const double* __restrict__ camtab, const double* __restrict__ acc27, double* __restrict__ Bc /* 36 */,
-                   double* __restrict__ gc /* 6 */, double* __restrict__ sc /* 6 */, double* __restrict__ lamc /* 6 */,
-                   const int first, const int jacobi, const double min_diag, const double max_diag, double* __restrict__ scal) {
-  __shared__ double sm[2 * NT_CAM / 32];
-  __shared__ double smo[2];
-  double xn2 = 0.0, gmax = 0.0;
-  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
-    double* B = Bc + (size_t)36 * i;
-    if (!cam_free[i]) {
-      for (int q = 0; q < 36; ++q) B[q] = 0.0;
-      for (int q = 0; q < 6; ++q) { gc[6 * i + q] = 0.0; lamc[6 * i + q] = 0.0; if (first) sc[6 * i + q] = 1.0; }
-      continue;
-    }
-    const double* a = acc27 + (size_t)27 * i;
-    const double* ct = camtab + (size_t)CAMTAB * i;
-    // T = blockdiag(G, R): column block c of (A T) etc.  Work with full 6x6 for clarity.
-    double Af[36], T[36], AT[36];
-    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Af[r * 6 + c] = (r <= c) ? a[tri(r, c)] : a[tri(c, r)];
-    for (int q = 0; q < 36; ++q) T[q] = 0.0;
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { T[r * 6 + c] = ct[9 + r * 3 + c]; T[(3 + r) * 6 + 3 + c] = ct[r * 3 + c]; }
-    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += Af[r * 6 + k] * T[k * 6 + c]; AT[r * 6 + c] = s; }
-    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) {
-      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * AT[k * 6 + c];
-      B[r * 6 + c] = s; B[c * 6 + r] = s; }
-    for (int r = 0; r < 6; ++r) {
-      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * a[21 + k];
-      gc[6 * i + r] = s; gmax = fmax(gmax, fabs(s));
-      const double h = B[r * 7];
-      double sv;
-      if (first) { sv = jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0; sc[6 * i + r] = sv; } else sv = sc[6 * i + r];
-      const double s2 = sv * sv;
-      lamc[6 * i + r] = fmin(fmax(s2 * h, min_diag), max_diag) / s2;
-      xn2 += cam[6 * i + r] * cam[6 * i + r];
-    }
-  }
-  double v[1] = {xn2};
-  block_reduce<1, NT_CAM>(v, sm, smo);
-  if (threadIdx.x == 0) scal[S_XN2_C] = smo[0];
-  double m[1] = {gmax};
-  block_reduce<1, NT_CAM, true>(m, sm, smo);
-  if (threadIdx.x == 0) scal[S_GMAX_C] = smo[0];
-}
-
-// M_i = B_i + lam_c/radius - T' Mhat T (block-Jacobi preconditioner = diagonal block of S),
-// rhs_i = g_i - T' rhat; Minv_i by Cholesky.  Then starts PCG: x=0, r=rhs, z=Minv r, p=z.
-__global__ void __launch_bounds__(NT_CAM)
-k_cam_schur_finalize(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab,
-                     const double* __restrict__ acc27, const double* __restrict__ Bc, const double* __restrict__ gc,
-                     const double* __restrict__ lamc, const double inv_radius, double* __restrict__ Md /* 36: S diag */,
-                     double* __restrict__ Minv, double* __restrict__ rhs, double* __restrict__ scal) {
-  __shared__ double sm[NT_CAM / 32];
-  __shared__ double smo[1];
-  double notpd = 0.0;
-  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
-    double* M = Md + (size_t)36 * i; double* Mi = Minv + (size_t)36 * i;
-    if (!cam_free[i]) {
-      for (int q = 0; q < 36; ++q) { M[q] = 0.0; Mi[q] = 0.0; }
-      for (int q = 0; q < 6; ++q) rhs[6 * i + q] = 0.0;
-      continue;
-    }
-    const double* a = acc27 + (size_t)27 * i;
-    const double* ct = camtab + (size_t)CAMTAB * i;
-    double Af[36], T[36], AT[36], Ml[36];
-    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Af[r * 6 + c] = (r <= c) ? a[tri(r, c)] : a[tri(c, r)];
-    for (int q = 0; q < 36; ++q) T[q] = 0.0;
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { T[r * 6 + c] = ct[9 + r * 3 + c]; T[(3 + r) * 6 + 3 + c] = ct[r * 3 + c]; }
-    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += Af[r * 6 + k] * T[k * 6 + c]; AT[r * 6 + c] = s; }
-    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) {
-      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * AT[k * 6 + c];
-      double v = Bc[(size_t)36 * i + r * 6 + c] - s;
-      if (r == c) v += lamc[6 * i + r] * inv_radius;
-      Ml[r * 6 + c] = v; Ml[c * 6 + r] = v; }
-    for (int q = 0; q < 36; ++q) M[q] = Ml[q];
-    double Il[36];
-    if (!inv6_spd(Ml, Il)) { notpd += 1.0; for (int q = 0; q < 36; ++q) Il[q] = 0.0; }
-    for (int q = 0; q < 36; ++q) Mi[q] = Il[q];
-    for (int r = 0; r < 6; ++r) {
-      double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * a[21 + k];
-      rhs[6 * i + r] = gc[6 * i + r] - s;
-    }
-  }
-  double v[1] = {notpd};
-  block_reduce<1, NT_CAM>(v, sm, smo);
-  if (threadIdx.x == 0) scal[S_NOTPD_C] = smo[0];
-}
-
 // xg_i = T_i x_i = (G x_w, R x_t): the per-camera 6-vector the point passes gather.
 __device__ __forceinline__ void apply_T(const double* ct, const double* x, double* out) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    out[r] = ct[9 + r * 3] * x[0] + ct[9 + r * 3 + 1] * x[1] + ct[9 + r * 3 + 2] * x[2];
+    out[r] = ct[CT_G + r * 3] * x[0] + ct[CT_G + r * 3 + 1] * x[1] + ct[CT_G + r * 3 + 2] * x[2];
     out[3 + r] = ct[r * 3] * x[3] + ct[r * 3 + 1] * x[4] + ct[r * 3 + 2] * x[5];
   }
 }
 __device__ __forceinline__ void apply_Tt(const double* ct, const double* y, double* out) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    out[r] = ct[9 + r] * y[0] + ct[9 + 3 + r] * y[1] + ct[9 + 6 + r] * y[2];
+    out[r] = ct[CT_G + r] * y[0] + ct[CT_G + 3 + r] * y[1] + ct[CT_G + 6 + r] * y[2];
     out[3 + r] = ct[r] * y[3] + ct[3 + r] * y[4] + ct[6 + r] * y[5];
   }
-}
-
-__global__ void __launch_bounds__(NT_CAM)
-k_cg_init(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ Minv, const double* __restrict__ rhs,
-          double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double* __restrict__ pg,
-          CgState* __restrict__ cg, const double tol, const int max_iters) {
-  __shared__ double sm[NT_CAM / 32];
-  __shared__ double smo[1];
-  double rz = 0.0;
-  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
-    double rr[6], z[6];
-    for (int q = 0; q < 6; ++q) { rr[q] = rhs[6 * i + q]; x[6 * i + q] = 0.0; r[6 * i + q] = rr[q]; }
-    const double* Mi = Minv + (size_t)36 * i;
-    for (int a = 0; a < 6; ++a) { double s = 0; for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c]; z[a] = s; rz += s * rr[a]; p[6 * i + a] = s; }
-    double t[6];
-    apply_T(camtab + (size_t)CAMTAB * i, z, t);
-    for (int q = 0; q < 6; ++q) pg[6 * i + q] = t[q];
-  }
-  double v[1] = {rz};
-  block_reduce<1, NT_CAM>(v, sm, smo);
-  if (threadIdx.x == 0) {
-    cg->rz = smo[0]; cg->rz0 = smo[0]; cg->pq = 0.0; cg->iters = 0; cg->max_iters = max_iters; cg->tol = tol;
-    cg->done = (smo[0] > 0.0) ? 0 : 1;
-  }
-}
-
-// q_i = (B_i + lam/radius) p_i - T_i' yhat_i ; then the PCG update (alpha, x, r, z, beta, p, pg).
-__global__ void __launch_bounds__(NT_CAM)
-k_cg_update(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab,
-            const double* __restrict__ Bc, const double* __restrict__ lamc, const double inv_radius,
-            const double* __restrict__ Minv, const double* __restrict__ yhat /* [n_cam][6] */, double* __restrict__ x,
-            double* __restrict__ r, double* __restrict__ p, double* __restrict__ q, double* __restrict__ pg,
-            CgState* __restrict__ cg) {
-  __shared__ double sm[NT_CAM / 32];
-  __shared__ double smo[1];
-  __shared__ double s_alpha, s_beta, s_pq;
-  if (cg->done) return;
-  double pq = 0.0;
-  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
-    if (!cam_free[i]) { for (int a = 0; a < 6; ++a) q[6 * i + a] = 0.0; continue; }
-    double pi[6], ty[6];
-    for (int a = 0; a < 6; ++a) pi[a] = p[6 * i + a];
-    apply_Tt(camtab + (size_t)CAMTAB * i, yhat + 6 * (size_t)i, ty);
-    const double* B = Bc + (size_t)36 * i;
-    for (int a = 0; a < 6; ++a) {
-      double s = lamc[6 * i + a] * inv_radius * pi[a];
-      for (int c = 0; c < 6; ++c) s += B[a * 6 + c] * pi[c];
-      s -= ty[a];
-      q[6 * i + a] = s; pq += s * pi[a];
-    }
-  }
-  double v[1] = {pq};
-  block_reduce<1, NT_CAM>(v, sm, smo);
-  if (threadIdx.x == 0) { s_alpha = (smo[0] > 0.0) ? cg->rz / smo[0] : 0.0; s_pq = smo[0]; }
-  __syncthreads();
-  const double alpha = s_alpha;
-  const bool breakdown = !(s_pq > 0.0);
-  double rz1 = 0.0;
-  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
-    double rr[6];
-    for (int a = 0; a < 6; ++a) { x[6 * i + a] += alpha * p[6 * i + a]; rr[a] = r[6 * i + a] - alpha * q[6 * i + a]; r[6 * i + a] = rr[a]; }
-    const double* Mi = Minv + (size_t)36 * i;
-    for (int a = 0; a < 6; ++a) { double s = 0; for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c]; q[6 * i + a] = s; rz1 += s * rr[a]; }  // q now holds z
-  }
-  __syncthreads();
-  double v2[1] = {rz1};
-  block_reduce<1, NT_CAM>(v2, sm, smo);
-  if (threadIdx.x == 0) s_beta = (cg->rz > 0.0) ? smo[0] / cg->rz : 0.0;
-  __syncthreads();
-  const double beta = s_beta;
-  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
-    double pn[6], t[6];
-    for (int a = 0; a < 6; ++a) { pn[a] = q[6 * i + a] + beta * p[6 * i + a]; p[6 * i + a] = pn[a]; }
-    apply_T(camtab + (size_t)CAMTAB * i, pn, t);
-    for (int a = 0; a < 6; ++a) pg[6 * i + a] = t[a];
-  }
-  if (threadIdx.x == 0) {
-    cg->pq = s_pq;
-    cg->rz = smo[0];
-    cg->iters += 1;
-    if (breakdown) cg->done = 2;
-    else if (sqrt(smo[0]) <= cg->tol * sqrt(cg->rz0)) cg->done = 1;
-    else if (cg->iters >= cg->max_iters) cg->done = 3;
-  }
-}
-
-// Candidate cameras: cam_c = cam - y_c; table of the candidate; yg = T y_c for the back-substitution;
-// camera parts of |y|^2, y.g and y' Lambda y.
-__global__ void __launch_bounds__(NT_CAM)
-k_cam_step(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
-           const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
-           double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ yg, double* __restrict__ scal) {
-  __shared__ double sm[3 * NT_CAM / 32];
-  __shared__ double smo[3];
-  double yn2 = 0, ygd = 0, yly = 0;
-  for (int i = threadIdx.x; i < n_cam; i += NT_CAM) {
-    double yi[6], cc[6], t[6];
-    for (int a = 0; a < 6; ++a) {
-      yi[a] = cam_free[i] ? y[6 * i + a] : 0.0;
-      cc[a] = cam[6 * i + a] - yi[a];
-      cam_c[6 * i + a] = cc[a];
-      yn2 += yi[a] * yi[a]; ygd += yi[a] * gc[6 * i + a]; yly += lamc[6 * i + a] * inv_radius * yi[a] * yi[a];
-    }
-    cam_table_row(cc, camtab_c + (size_t)CAMTAB * i);
-    apply_T(camtab + (size_t)CAMTAB * i, yi, t);
-    for (int a = 0; a < 6; ++a) yg[6 * i + a] = t[a];
-  }
-  double v[3] = {yn2, ygd, yly};
-  block_reduce<3, NT_CAM>(v, sm, smo);
-  if (threadIdx.x == 0) { scal[S_YN2_C] = smo[0]; scal[S_YG_C] = smo[1]; scal[S_YLY_C] = smo[2]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1000,7 +822,7 @@ k_cull(const PmArgs A, const double4* __restrict__ pt, const double* __restrict_
   for (int k = b; k < e; ++k) {
     const double* ct = camtab + (size_t)CAMTAB * A.pm_cam[k];
     const double2 uv = A.pm_uv[k];
-    const double qx = X.x - ct[18], qy = X.y - ct[19], qz = X.z - ct[20];
+    const double qx = X.x - ct[CT_C], qy = X.y - ct[CT_C + 1], qz = X.z - ct[CT_C + 2];
     const double px = ct[0] * qx + ct[1] * qy + ct[2] * qz;
     const double py = ct[3] * qx + ct[4] * qy + ct[5] * qz;
     const double pz = ct[6] * qx + ct[7] * qy + ct[8] * qz;

@@ -92,7 +92,7 @@ k_pose_only(const int batch, double* __restrict__ cams, const int* __restrict__ 
         double Af[36], T[36], AT[36];
         for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Af[r * 6 + c] = (r <= c) ? red[1 + tri(r, c)] : red[1 + tri(c, r)];
         for (int q = 0; q < 36; ++q) T[q] = 0.0;
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { T[r * 6 + c] = ct[9 + r * 3 + c]; T[(3 + r) * 6 + 3 + c] = ct[r * 3 + c]; }
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { T[r * 6 + c] = ct[CT_G + r * 3 + c]; T[(3 + r) * 6 + 3 + c] = ct[r * 3 + c]; }
         for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += Af[r * 6 + k] * T[k * 6 + c]; AT[r * 6 + c] = s; }
         for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double s = 0; for (int k = 0; k < 6; ++k) s += T[k * 6 + r] * AT[k * 6 + c]; s_H[r * 6 + c] = s; }
         double gmax = 0, xn = 0;

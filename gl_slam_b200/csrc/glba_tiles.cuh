@@ -1,0 +1,238 @@
+// glba_tiles.cuh — point-major kernels, tiled: the "warp-level segmented reduction over point tracks
+// with shared-memory staging" of the north star, done per CTA.
+//
+// A tile is a run of whole point tracks holding < NT_T observations (built at load time from the
+// track CSR: tile t owns the points whose first observation index lies in [t*B, (t+1)*B),
+// B = NT_T - longest track).  Phase 1: one thread per OBSERVATION — every per-observation array is read
+// with unit stride (coalesced), the per-observation contribution is staged in shared memory (SoA).
+// Phase 2: one thread per POINT sums its segment in observation order (fixed order => bit-reproducible),
+// then does the 3x3 work (damped inverse, Cinv t, back-substitution).
+// The thread-per-point kernels in glba_kernels.cuh stay as the fallback for tracks longer than NT_T/2.
+#pragma once
+#include "glba_kernels.cuh"
+
+namespace glba {
+
+constexpr int NT_T = 256;
+
+struct TileArgs {
+  const int* tile_pt;      // [n_tiles+1] first point of every tile
+  const int* pm_pt;        // point of observation k (point-major order)
+};
+
+// K_A + point half of K_B, tiled.  Same outputs as k_linearize_pm.
+__global__ void __launch_bounds__(NT_T)
+k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ pt, const double* __restrict__ camtab,
+                 double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
+                 double4* __restrict__ lam4, double* __restrict__ pblk, const int first, const int jacobi, const double min_diag,
+                 const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */) {
+  __shared__ double val[9][NT_T];
+  __shared__ double sm[4 * NT_T / 32];
+  __shared__ double smo[4];
+  __shared__ double smm[NT_T / 32];
+  __shared__ double smmo[1];
+  const int tid = threadIdx.x;
+  const int j0 = T.tile_pt[blockIdx.x], j1 = T.tile_pt[blockIdx.x + 1];
+  const int k0 = A.pt_start[j0], k1 = A.pt_start[j1];
+  const int k = k0 + tid;
+  double cost = 0.0, bad = 0.0;
+  if (k < k1) {
+    const int i = __ldg(A.pm_cam + k);
+    const int j = __ldg(T.pm_pt + k);
+    const double2 uv = __ldg(A.pm_uv + k);
+    const double4 X = ldg4(pt + j);
+    double R[9], cc[3];
+    load_Rc(camtab + (size_t)CAMTAB * i, R, cc);
+    const double qx = X.x - cc[0], qy = X.y - cc[1], qz = X.z - cc[2];
+    const double px = R[0] * qx + R[1] * qy + R[2] * qz;
+    const double py = R[3] * qx + R[4] * qy + R[5] * qz;
+    const double pz = R[6] * qx + R[7] * qy + R[8] * qz;
+    const double iz = 1.0 / pz;
+    const double xh = px * iz, yh = py * iz;
+    const double rx = A.K.fx * xh + A.K.cx - uv.x, ry = A.K.fy * yh + A.K.cy - uv.y;
+    double rho, w;
+    loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+    if (!isfinite(rx) || !isfinite(ry)) bad = 1.0;
+    cost = 0.5 * rho;
+    const double4 rec = make_double4(xh, yh, iz, w);
+    st4(rec_pm + k, rec);
+    st4(rec_cm + __ldg(A.pm2cm + k), rec);
+    double ap[3], bp[3];
+    jp_rows(rec, R, A.K, ap, bp);
+    const double r0 = w * rx, r1 = w * ry;
+    val[0][tid] = ap[0] * ap[0] + bp[0] * bp[0]; val[1][tid] = ap[0] * ap[1] + bp[0] * bp[1]; val[2][tid] = ap[0] * ap[2] + bp[0] * bp[2];
+    val[3][tid] = ap[1] * ap[1] + bp[1] * bp[1]; val[4][tid] = ap[1] * ap[2] + bp[1] * bp[2]; val[5][tid] = ap[2] * ap[2] + bp[2] * bp[2];
+    val[6][tid] = ap[0] * r0 + bp[0] * r1; val[7][tid] = ap[1] * r0 + bp[1] * r1; val[8][tid] = ap[2] * r0 + bp[2] * r1;
+  }
+  __syncthreads();
+  double xn2 = 0.0, gmax = 0.0, notpd = 0.0;
+  for (int j = j0 + tid; j < j1; j += NT_T) {
+    const int b = __ldg(A.pt_start + j) - k0, e = __ldg(A.pt_start + j + 1) - k0;
+    double C[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int m = b; m < e; ++m) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) C[q] += val[q][m];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) g[q] += val[6 + q][m];
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Craw[(size_t)q * A.n_pt + j] = C[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) Craw[(size_t)(6 + q) * A.n_pt + j] = g[q];
+    double blk[PBLK];
+    if (A.pt_free[j]) {
+      const double h[3] = {C[0], C[3], C[5]};
+      double s[3], lam[3];
+      if (first) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s[q] = jacobi ? 1.0 / (1.0 + sqrt(h[q])) : 1.0;
+        st4(sp4 + j, make_double4(s[0], s[1], s[2], 0.0));
+      } else {
+        const double4 s4 = ldg4(sp4 + j);
+        s[0] = s4.x; s[1] = s4.y; s[2] = s4.z;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const double s2 = s[q] * s[q];
+        lam[q] = fmin(fmax(s2 * h[q], min_diag), max_diag) / s2;
+      }
+      st4(lam4 + j, make_double4(lam[0], lam[1], lam[2], 0.0));
+      if (!point_block(C, g, lam, inv_radius, blk)) notpd += 1.0;
+      const double4 X = ldg4(pt + j);
+      xn2 += X.x * X.x + X.y * X.y + X.z * X.z;
+      gmax = fmax(gmax, fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2]))));
+    } else {
+#pragma unroll
+      for (int q = 0; q < PBLK; ++q) blk[q] = 0.0;
+      if (first) st4(sp4 + j, make_double4(1.0, 1.0, 1.0, 0.0));
+      st4(lam4 + j, make_double4(0.0, 0.0, 0.0, 0.0));
+    }
+    double* pb = pblk + (size_t)PBLK * j;
+#pragma unroll
+    for (int q = 0; q < PBLK; q += 2) *reinterpret_cast<double2*>(pb + q) = make_double2(blk[q], blk[q + 1]);
+  }
+  double v[4] = {cost, xn2, bad, notpd};
+  block_reduce<4, NT_T>(v, sm, smo);
+  double m[1] = {gmax};
+  block_reduce<1, NT_T, true>(m, smm, smmo);
+  if (tid == 0) {
+    double* p = part + (size_t)5 * blockIdx.x;
+    p[0] = smo[0]; p[1] = smo[1]; p[2] = smo[2]; p[3] = smo[3]; p[4] = smmo[0];
+  }
+}
+
+// Point-major half of the implicit product (MODE 0) / back-substitution + candidate cost (MODE 1), tiled.
+// xtab row of camera i: [xg(6) = T_i x_i | R_i (9) | sv_i (3)] — one contiguous 144-byte gather.
+template <int MODE>
+__global__ void __launch_bounds__(NT_T)
+k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_pm, const double* __restrict__ camtab,
+             const double* __restrict__ xtab,
+             const double* __restrict__ pblk, double4* __restrict__ u4, const CgState* __restrict__ cg, const int li,
+             // MODE 1 only:
+             const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
+             const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */) {
+  __shared__ double val[3][NT_T];
+  if (MODE == 0 && cg && cg->done_at <= li) return;
+  const int tid = threadIdx.x;
+  const int j0 = T.tile_pt[blockIdx.x], j1 = T.tile_pt[blockIdx.x + 1];
+  const int k0 = A.pt_start[j0], k1 = A.pt_start[j1];
+  const int k = k0 + tid;
+  int cam_i = 0, pt_j = 0;
+  double2 uv = make_double2(0.0, 0.0);
+  if (k < k1) {
+    cam_i = __ldg(A.pm_cam + k);
+    pt_j = __ldg(T.pm_pt + k);
+    if (MODE == 1) uv = __ldg(A.pm_uv + k);
+    const double4 rec = ldg4(rec_pm + k);
+    // one 128-byte row per camera: four 256-bit gathers
+    const double4* xr = reinterpret_cast<const double4*>(xtab + (size_t)XTAB * cam_i);
+    const double4 x0 = ldg4(xr), x1 = ldg4(xr + 1), x2 = ldg4(xr + 2), x3 = ldg4(xr + 3);
+    const double xg[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+    const double R[9] = {x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z};
+    double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
+    if (x3.w != 0.0) {                 // Ceres' small-angle branch: only an (almost) exactly-identity keyframe
+      const double* ct = camtab + (size_t)CAMTAB * cam_i;
+      sv0 = ct[CT_SV]; sv1 = ct[CT_SV + 1]; sv2 = ct[CT_SV + 2];
+    }
+    double a[6], bb[6];
+    jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+    double al0 = 0.0, al1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { al0 += a[r] * xg[r]; al1 += bb[r] * xg[r]; }
+    double ap[3], bp[3];
+    jp_rows(rec, R, A.K, ap, bp);
+    val[0][tid] = ap[0] * al0 + bp[0] * al1;
+    val[1][tid] = ap[1] * al0 + bp[1] * al1;
+    val[2][tid] = ap[2] * al0 + bp[2] * al1;
+  }
+  __syncthreads();
+  double yn2 = 0.0, yg = 0.0, yly = 0.0;
+  for (int j = j0 + tid; j < j1; j += NT_T) {
+    const int b = __ldg(A.pt_start + j) - k0, e = __ldg(A.pt_start + j + 1) - k0;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    const bool free_pt = A.pt_free[j] != 0;
+    if (free_pt)
+      for (int m = b; m < e; ++m) { t0 += val[0][m]; t1 += val[1][m]; t2 += val[2][m]; }
+    double Ci[6], u0[3];
+    load_pblk(pblk + (size_t)PBLK * j, Ci, u0);
+    const double v0 = Ci[0] * t0 + Ci[1] * t1 + Ci[2] * t2;
+    const double v1 = Ci[1] * t0 + Ci[3] * t1 + Ci[4] * t2;
+    const double v2 = Ci[2] * t0 + Ci[4] * t1 + Ci[5] * t2;
+    if (MODE == 0) {
+      st4(u4 + j, make_double4(v0, v1, v2, 0.0));
+    } else {
+      const double y0 = u0[0] - v0, y1 = u0[1] - v1, y2 = u0[2] - v2;
+      const double4 X = ldg4(pt + j);
+      st4(pt_c + j, make_double4(X.x - y0, X.y - y1, X.z - y2, 0.0));
+      if (free_pt) {
+        const double4 l4 = ldg4(lam4 + j);
+        yn2 += y0 * y0 + y1 * y1 + y2 * y2;
+        yg += y0 * Craw[(size_t)6 * A.n_pt + j] + y1 * Craw[(size_t)7 * A.n_pt + j] + y2 * Craw[(size_t)8 * A.n_pt + j];
+        yly += (l4.x * y0 * y0 + l4.y * y1 * y1 + l4.z * y2 * y2) * inv_radius;
+      }
+    }
+  }
+  if (MODE == 1) {
+    __shared__ double sm[5 * NT_T / 32];
+    __shared__ double smo[5];
+    __syncthreads();                  // pt_c of this tile is visible to the whole CTA
+    double cost_c = 0.0, bad = 0.0;
+    if (k < k1) {
+      const double4 xc = ld4(pt_c + pt_j);          // written by this CTA: coherent load
+      double Rc[9], cc[3];
+      load_Rc(camtab_c + (size_t)CAMTAB * cam_i, Rc, cc);
+      const double qx = xc.x - cc[0], qy = xc.y - cc[1], qz = xc.z - cc[2];
+      const double px = Rc[0] * qx + Rc[1] * qy + Rc[2] * qz, py = Rc[3] * qx + Rc[4] * qy + Rc[5] * qz, pz = Rc[6] * qx + Rc[7] * qy + Rc[8] * qz;
+      const double iz = 1.0 / pz;
+      const double rx = A.K.fx * (px * iz) + A.K.cx - uv.x, ry = A.K.fy * (py * iz) + A.K.cy - uv.y;
+      double rho, w;
+      loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+      if (!isfinite(rx) || !isfinite(ry)) bad = 1.0;
+      cost_c = 0.5 * rho;
+    }
+    double v[5] = {cost_c, yn2, yg, yly, bad};
+    block_reduce<5, NT_T>(v, sm, smo);
+    if (tid < 5) part[(size_t)5 * blockIdx.x + tid] = smo[tid];
+  }
+}
+
+// ---- load-time helpers ------------------------------------------------------------------------
+__global__ void k_max_track(const int n_pt, const int* __restrict__ pt_start, int* out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int len = (j < n_pt) ? pt_start[j + 1] - pt_start[j] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
+}
+// tile_pt[t] = first point whose first observation index is >= t*B  (t = 0..n_tiles), clamped to n_pt
+__global__ void k_tile_starts(const int n_tiles, const int B, const int n_pt, const int* __restrict__ pt_start, int* __restrict__ tile_pt) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  if (t == n_tiles) { tile_pt[t] = n_pt; return; }
+  const long target = (long)t * B;
+  int lo = 0, hi = n_pt;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (pt_start[mid] < target) lo = mid + 1; else hi = mid; }
+  tile_pt[t] = lo;
+}
+
+}  // namespace glba

@@ -64,7 +64,8 @@ def _trajectory(n_cam, step, yaw_per_frame, loop):
 
 def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2rad(0.5), loop=False,
                pixel_sigma=0.5, outlier_frac=0.0, outlier_px=(10.0, 50.0), rot_sigma=0.02, pos_sigma=0.05,
-               pt_sigma=0.10, depth=(5.0, 50.0), n_fixed=2, K=KITTI_K, return_gt=False, min_parallax_deg=1.0):
+               pt_sigma=0.10, depth=(5.0, 50.0), n_fixed=2, K=KITTI_K, return_gt=False, min_parallax_deg=1.0,
+               creation_order=True):
     """track_len: int, or callable(rng, n_pt) -> int array (clipped to [2, n_cam]).
 
     Returns a HostProblem whose cam/pt are the *initial guess* (ground truth + Gaussian noise; the first
@@ -82,6 +83,11 @@ def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2r
         start = rng.integers(0, n_cam, size=n_pt)
     else:
         start = (rng.random(n_pt) * (n_cam - tl + 1)).astype(np.int64)
+    if creation_order:
+        # GL-SLAM hands out map-point ids in creation order (next_point_id++ while the newest keyframe is inserted,
+        # slam_core.cpp:386-405), so point ids are sorted by their first-observing keyframe
+        order0 = np.argsort(start, kind="stable")
+        start, tl = start[order0], tl[order0]
     n_obs = int(tl.sum())
     obs_pt = np.repeat(np.arange(n_pt, dtype=np.int64), tl)
     first = np.cumsum(tl) - tl
