@@ -295,10 +295,10 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   CU(cudaStreamSynchronize(s));
   ctx->has_dup = (n > 0 && n_cam <= DN_MAXCAM) ? (ctx->h_flags[3] != 0) : false;
   ctx->max_track = ctx->h_flags[4];
-  ctx->use_tiles = (n > 0 && ctx->max_track <= NT_T / 2);
+  ctx->use_tiles = (n > 0 && ctx->max_track <= TILE_OBS / 2);
   ctx->n_tiles = 0;
   if (ctx->use_tiles) {
-    const int B = NT_T - ctx->max_track;
+    const int B = TILE_OBS - ctx->max_track;
     ctx->n_tiles = (int)((n + B - 1) / B);
     ENSURE(int, ctx->tile_pt, (size_t)ctx->n_tiles + 1);
     LAUNCH(k_tile_starts, cdiv(ctx->n_tiles + 1, 256), 256, ctx->n_tiles, B, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->tile_pt.as<int>());
@@ -379,12 +379,16 @@ int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
 
 void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
   const int c = ctx->cur;
-  if (ctx->use_tiles)
-    LAUNCH(k_linearize_tile, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(),
+  if (ctx->use_tiles) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)9 * TILE_OBS * sizeof(double);
+    if (!attr_set) { cudaFuncSetAttribute(k_linearize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_linearize_tile<<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
            ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
            o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
-  else
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else
     LAUNCH(k_linearize_pm, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
            ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,

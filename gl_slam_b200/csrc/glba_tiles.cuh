@@ -14,6 +14,11 @@
 namespace glba {
 
 constexpr int NT_T = 256;
+#ifndef GLBA_OPT
+#define GLBA_OPT 4
+#endif
+constexpr int OPT = GLBA_OPT;            // observations per thread in phase 1
+constexpr int TILE_OBS = NT_T * OPT;     // tile capacity; ~TILE_OBS/track_len points keep phase 2 busy
 
 struct TileArgs {
   const int* tile_pt;      // [n_tiles+1] first point of every tile
@@ -26,7 +31,8 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
                  double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
                  double4* __restrict__ lam4, double* __restrict__ pblk, const int first, const int jacobi, const double min_diag,
                  const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */) {
-  __shared__ double val[9][NT_T];
+  extern __shared__ double dsm[];
+  double (*val)[TILE_OBS] = reinterpret_cast<double (*)[TILE_OBS]>(dsm);     // [9][TILE_OBS]
   __shared__ double sm[4 * NT_T / 32];
   __shared__ double smo[4];
   __shared__ double smm[NT_T / 32];
@@ -34,35 +40,39 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
   const int tid = threadIdx.x;
   const int j0 = T.tile_pt[blockIdx.x], j1 = T.tile_pt[blockIdx.x + 1];
   const int k0 = A.pt_start[j0], k1 = A.pt_start[j1];
-  const int k = k0 + tid;
   double cost = 0.0, bad = 0.0;
-  if (k < k1) {
-    const int i = __ldg(A.pm_cam + k);
-    const int j = __ldg(T.pm_pt + k);
-    const double2 uv = __ldg(A.pm_uv + k);
-    const double4 X = ldg4(pt + j);
-    double R[9], cc[3];
-    load_Rc(camtab + (size_t)CAMTAB * i, R, cc);
-    const double qx = X.x - cc[0], qy = X.y - cc[1], qz = X.z - cc[2];
-    const double px = R[0] * qx + R[1] * qy + R[2] * qz;
-    const double py = R[3] * qx + R[4] * qy + R[5] * qz;
-    const double pz = R[6] * qx + R[7] * qy + R[8] * qz;
-    const double iz = 1.0 / pz;
-    const double xh = px * iz, yh = py * iz;
-    const double rx = A.K.fx * xh + A.K.cx - uv.x, ry = A.K.fy * yh + A.K.cy - uv.y;
-    double rho, w;
-    loss_eval(A.loss, rx * rx + ry * ry, rho, w);
-    if (!isfinite(rx) || !isfinite(ry)) bad = 1.0;
-    cost = 0.5 * rho;
-    const double4 rec = make_double4(xh, yh, iz, w);
-    st4(rec_pm + k, rec);
-    st4(rec_cm + __ldg(A.pm2cm + k), rec);
-    double ap[3], bp[3];
-    jp_rows(rec, R, A.K, ap, bp);
-    const double r0 = w * rx, r1 = w * ry;
-    val[0][tid] = ap[0] * ap[0] + bp[0] * bp[0]; val[1][tid] = ap[0] * ap[1] + bp[0] * bp[1]; val[2][tid] = ap[0] * ap[2] + bp[0] * bp[2];
-    val[3][tid] = ap[1] * ap[1] + bp[1] * bp[1]; val[4][tid] = ap[1] * ap[2] + bp[1] * bp[2]; val[5][tid] = ap[2] * ap[2] + bp[2] * bp[2];
-    val[6][tid] = ap[0] * r0 + bp[0] * r1; val[7][tid] = ap[1] * r0 + bp[1] * r1; val[8][tid] = ap[2] * r0 + bp[2] * r1;
+#pragma unroll
+  for (int m = 0; m < OPT; ++m) {
+    const int l = m * NT_T + tid;
+    const int k = k0 + l;
+    if (k < k1) {
+      const int i = __ldg(A.pm_cam + k);
+      const int j = __ldg(T.pm_pt + k);
+      const double2 uv = __ldg(A.pm_uv + k);
+      const double4 X = ldg4(pt + j);
+      double R[9], cc[3];
+      load_Rc(camtab + (size_t)CAMTAB * i, R, cc);
+      const double qx = X.x - cc[0], qy = X.y - cc[1], qz = X.z - cc[2];
+      const double px = R[0] * qx + R[1] * qy + R[2] * qz;
+      const double py = R[3] * qx + R[4] * qy + R[5] * qz;
+      const double pz = R[6] * qx + R[7] * qy + R[8] * qz;
+      const double iz = 1.0 / pz;
+      const double xh = px * iz, yh = py * iz;
+      const double rx = A.K.fx * xh + A.K.cx - uv.x, ry = A.K.fy * yh + A.K.cy - uv.y;
+      double rho, w;
+      loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+      if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
+      cost += 0.5 * rho;
+      const double4 rec = make_double4(xh, yh, iz, w);
+      st4(rec_pm + k, rec);
+      st4(rec_cm + __ldg(A.pm2cm + k), rec);
+      double ap[3], bp[3];
+      jp_rows(rec, R, A.K, ap, bp);
+      const double r0 = w * rx, r1 = w * ry;
+      val[0][l] = ap[0] * ap[0] + bp[0] * bp[0]; val[1][l] = ap[0] * ap[1] + bp[0] * bp[1]; val[2][l] = ap[0] * ap[2] + bp[0] * bp[2];
+      val[3][l] = ap[1] * ap[1] + bp[1] * bp[1]; val[4][l] = ap[1] * ap[2] + bp[1] * bp[2]; val[5][l] = ap[2] * ap[2] + bp[2] * bp[2];
+      val[6][l] = ap[0] * r0 + bp[0] * r1; val[7][l] = ap[1] * r0 + bp[1] * r1; val[8][l] = ap[2] * r0 + bp[2] * r1;
+    }
   }
   __syncthreads();
   double xn2 = 0.0, gmax = 0.0, notpd = 0.0;
@@ -131,39 +141,39 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
              // MODE 1 only:
              const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
              const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */) {
-  __shared__ double val[3][NT_T];
+  __shared__ double val[3][TILE_OBS];
   if (MODE == 0 && cg && cg->done_at <= li) return;
   const int tid = threadIdx.x;
   const int j0 = T.tile_pt[blockIdx.x], j1 = T.tile_pt[blockIdx.x + 1];
   const int k0 = A.pt_start[j0], k1 = A.pt_start[j1];
-  const int k = k0 + tid;
-  int cam_i = 0, pt_j = 0;
-  double2 uv = make_double2(0.0, 0.0);
-  if (k < k1) {
-    cam_i = __ldg(A.pm_cam + k);
-    pt_j = __ldg(T.pm_pt + k);
-    if (MODE == 1) uv = __ldg(A.pm_uv + k);
-    const double4 rec = ldg4(rec_pm + k);
-    // one 128-byte row per camera: four 256-bit gathers
-    const double4* xr = reinterpret_cast<const double4*>(xtab + (size_t)XTAB * cam_i);
-    const double4 x0 = ldg4(xr), x1 = ldg4(xr + 1), x2 = ldg4(xr + 2), x3 = ldg4(xr + 3);
-    const double xg[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
-    const double R[9] = {x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z};
-    double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-    if (x3.w != 0.0) {                 // Ceres' small-angle branch: only an (almost) exactly-identity keyframe
-      const double* ct = camtab + (size_t)CAMTAB * cam_i;
-      sv0 = ct[CT_SV]; sv1 = ct[CT_SV + 1]; sv2 = ct[CT_SV + 2];
-    }
-    double a[6], bb[6];
-    jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
-    double al0 = 0.0, al1 = 0.0;
 #pragma unroll
-    for (int r = 0; r < 6; ++r) { al0 += a[r] * xg[r]; al1 += bb[r] * xg[r]; }
-    double ap[3], bp[3];
-    jp_rows(rec, R, A.K, ap, bp);
-    val[0][tid] = ap[0] * al0 + bp[0] * al1;
-    val[1][tid] = ap[1] * al0 + bp[1] * al1;
-    val[2][tid] = ap[2] * al0 + bp[2] * al1;
+  for (int m = 0; m < OPT; ++m) {
+    const int l = m * NT_T + tid;
+    const int k = k0 + l;
+    if (k < k1) {
+      const int cam_i = __ldg(A.pm_cam + k);
+      const double4 rec = ldg4(rec_pm + k);
+      // one 128-byte row per camera: four 256-bit gathers
+      const double4* xr = reinterpret_cast<const double4*>(xtab + (size_t)XTAB * cam_i);
+      const double4 x0 = ldg4(xr), x1 = ldg4(xr + 1), x2 = ldg4(xr + 2), x3 = ldg4(xr + 3);
+      const double xg[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+      const double R[9] = {x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z};
+      double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
+      if (x3.w != 0.0) {               // Ceres' small-angle branch: only an (almost) exactly-identity keyframe
+        const double* ct = camtab + (size_t)CAMTAB * cam_i;
+        sv0 = ct[CT_SV]; sv1 = ct[CT_SV + 1]; sv2 = ct[CT_SV + 2];
+      }
+      double a[6], bb[6];
+      jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+      double al0 = 0.0, al1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { al0 += a[r] * xg[r]; al1 += bb[r] * xg[r]; }
+      double ap[3], bp[3];
+      jp_rows(rec, R, A.K, ap, bp);
+      val[0][l] = ap[0] * al0 + bp[0] * al1;
+      val[1][l] = ap[1] * al0 + bp[1] * al1;
+      val[2][l] = ap[2] * al0 + bp[2] * al1;
+    }
   }
   __syncthreads();
   double yn2 = 0.0, yg = 0.0, yly = 0.0;
@@ -197,18 +207,25 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
     __shared__ double smo[5];
     __syncthreads();                  // pt_c of this tile is visible to the whole CTA
     double cost_c = 0.0, bad = 0.0;
-    if (k < k1) {
-      const double4 xc = ld4(pt_c + pt_j);          // written by this CTA: coherent load
-      double Rc[9], cc[3];
-      load_Rc(camtab_c + (size_t)CAMTAB * cam_i, Rc, cc);
-      const double qx = xc.x - cc[0], qy = xc.y - cc[1], qz = xc.z - cc[2];
-      const double px = Rc[0] * qx + Rc[1] * qy + Rc[2] * qz, py = Rc[3] * qx + Rc[4] * qy + Rc[5] * qz, pz = Rc[6] * qx + Rc[7] * qy + Rc[8] * qz;
-      const double iz = 1.0 / pz;
-      const double rx = A.K.fx * (px * iz) + A.K.cx - uv.x, ry = A.K.fy * (py * iz) + A.K.cy - uv.y;
-      double rho, w;
-      loss_eval(A.loss, rx * rx + ry * ry, rho, w);
-      if (!isfinite(rx) || !isfinite(ry)) bad = 1.0;
-      cost_c = 0.5 * rho;
+#pragma unroll
+    for (int m = 0; m < OPT; ++m) {
+      const int k = k0 + m * NT_T + tid;
+      if (k < k1) {
+        const int cam_i = __ldg(A.pm_cam + k);
+        const int pt_j = __ldg(T.pm_pt + k);
+        const double2 uv = __ldg(A.pm_uv + k);
+        const double4 xc = ld4(pt_c + pt_j);          // written by this CTA: coherent load
+        double Rc[9], cc[3];
+        load_Rc(camtab_c + (size_t)CAMTAB * cam_i, Rc, cc);
+        const double qx = xc.x - cc[0], qy = xc.y - cc[1], qz = xc.z - cc[2];
+        const double px = Rc[0] * qx + Rc[1] * qy + Rc[2] * qz, py = Rc[3] * qx + Rc[4] * qy + Rc[5] * qz, pz = Rc[6] * qx + Rc[7] * qy + Rc[8] * qz;
+        const double iz = 1.0 / pz;
+        const double rx = A.K.fx * (px * iz) + A.K.cx - uv.x, ry = A.K.fy * (py * iz) + A.K.cy - uv.y;
+        double rho, w;
+        loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+        if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
+        cost_c += 0.5 * rho;
+      }
     }
     double v[5] = {cost_c, yn2, yg, yly, bad};
     block_reduce<5, NT_T>(v, sm, smo);

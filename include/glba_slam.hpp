@@ -1,0 +1,292 @@
+// glba_slam.hpp — header-only C++17 host adaptor: GL-SLAM's BA entry points over the C ABI of glba.h.
+//
+// Mirrors, without OpenCV (absent from this image), the structures and the two functions the reference's
+// tracking and mapping threads call:
+//   struct Observation / MapPoint / Frame / Map         include/core/slam_types.h:13-61
+//   bool slam_core::full_ba(map_mutex, map, K, window)  src/core/slam_core.cpp:744-883
+//   bool slam_core::pose_only_ba(R, t, p3d, p2d, K)     src/core/slam_core.cpp:1092-1140
+// Same names, argument meaning and error behaviour (false = "did nothing", inputs untouched); cv::Mat
+// 3x3 / 3x1 CV_64F become Mat33 / Vec3, cv::Point2d/3d become Point2d/3d.  The hidden global inputs of the
+// reference (slam_types::run_window, the two write-back mutexes, slam_core.cpp:758, 857-858) are explicit
+// arguments here.  A maintainer swaps the ceres::Problem/ceres::Solve block for these calls: INTEGRATION.md.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "glba.h"
+
+namespace glslam {
+
+struct Point2d { double x = 0, y = 0; };
+struct Point3d { double x = 0, y = 0, z = 0; };
+struct Mat33 {                 // row-major, stands in for a 3x3 CV_64F cv::Mat
+  double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double& at(int r, int c) { return m[r * 3 + c]; }
+  double at(int r, int c) const { return m[r * 3 + c]; }
+};
+struct Vec3 { double v[3] = {0, 0, 0}; };
+struct CameraMatrix { double fx = 0, fy = 0, cx = 0, cy = 0; };   // K(0,0), K(1,1), K(0,2), K(1,2) — slam_core.cpp:720-723
+
+// slam_types.h:13-19
+struct Observation {
+  int keyframe_id = 0;
+  Point2d point2D;
+  int kp_index = 0;
+};
+// slam_types.h:21-26
+struct MapPoint {
+  int id = 0;
+  Point3d position;
+  std::vector<Observation> obs;
+  bool is_bad = false;
+};
+// slam_types.h:28-54 (image, descriptors and the covisibility list are front-end state the BA never reads)
+struct Frame {
+  int id = 0;
+  Mat33 R;                        // camera-to-world rotation
+  Vec3 t;                         // camera centre
+  std::vector<int> map_point_ids; // one push per observation: may hold duplicates (slam_core.cpp:386-387, 405)
+  std::vector<int> kp_to_mpid;
+  bool is_keyframe = false;
+};
+// slam_types.h:56-61
+struct Map {
+  std::unordered_map<int, MapPoint> map_points;
+  std::unordered_map<int, Frame> keyframes;
+  int next_point_id = 0;
+  int next_keyframe_id = 0;
+};
+
+// ---- cv::Rodrigues, both directions (slam_core.cpp:769, 862, 1101, 1136) ---------------------------------------
+inline void rodrigues(const Mat33& R, double w[3]) {
+  const double rx = 0.5 * (R.at(2, 1) - R.at(1, 2)), ry = 0.5 * (R.at(0, 2) - R.at(2, 0)), rz = 0.5 * (R.at(1, 0) - R.at(0, 1));
+  const double s = std::sqrt(rx * rx + ry * ry + rz * rz);
+  const double c = std::min(1.0, std::max(-1.0, 0.5 * (R.at(0, 0) + R.at(1, 1) + R.at(2, 2) - 1.0)));
+  const double theta = std::atan2(s, c);
+  if (s < 1e-8) {
+    if (c > 0) { w[0] = rx; w[1] = ry; w[2] = rz; return; }          // theta ~ 0: w = skew part
+    // theta ~ pi: axis from the symmetric part
+    double ax = std::sqrt(std::max(0.0, 0.5 * (R.at(0, 0) + 1.0))), ay = std::sqrt(std::max(0.0, 0.5 * (R.at(1, 1) + 1.0))),
+           az = std::sqrt(std::max(0.0, 0.5 * (R.at(2, 2) + 1.0)));
+    if (R.at(0, 1) < 0) ay = -ay;
+    if (R.at(0, 2) < 0) az = -az;
+    if (std::fabs(ax) < std::fabs(ay) && std::fabs(ax) < std::fabs(az) && (R.at(1, 2) > 0) != (ay * az > 0)) az = -az;
+    const double n = std::sqrt(ax * ax + ay * ay + az * az);
+    w[0] = theta * ax / n; w[1] = theta * ay / n; w[2] = theta * az / n;
+    return;
+  }
+  const double k = theta / s;
+  w[0] = k * rx; w[1] = k * ry; w[2] = k * rz;
+}
+inline void rodrigues(const double w[3], Mat33& R) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = std::sqrt(th2);
+  if (th < 1e-300) { R = Mat33(); return; }
+  const double kx = w[0] / th, ky = w[1] / th, kz = w[2] / th;
+  const double c = std::cos(th), s = std::sin(th), oc = 1.0 - c;
+  R.m[0] = c + oc * kx * kx;      R.m[1] = oc * kx * ky - s * kz; R.m[2] = oc * kx * kz + s * ky;
+  R.m[3] = oc * ky * kx + s * kz; R.m[4] = c + oc * ky * ky;      R.m[5] = oc * ky * kz - s * kx;
+  R.m[6] = oc * kz * kx - s * ky; R.m[7] = oc * kz * ky + s * kx; R.m[8] = c + oc * kz * kz;
+}
+
+// ---- one glba context per calling thread (tracking thread / mapping thread) -------------------------------------
+class Backend {
+ public:
+  explicit Backend(int device = 0) {
+    glba_device_cfg cfg{};
+    cfg.device = device; cfg.rank = 0; cfg.world = 1; cfg.nccl_unique_id = nullptr; cfg.stream = nullptr;
+    status_ = glba_create(&cfg, &ctx_);
+  }
+  ~Backend() { if (ctx_) glba_destroy(ctx_); }
+  Backend(const Backend&) = delete;
+  Backend& operator=(const Backend&) = delete;
+  bool ok() const { return ctx_ != nullptr; }
+  int status() const { return status_; }
+  glba_ctx* ctx() const { return ctx_; }
+ private:
+  glba_ctx* ctx_ = nullptr;
+  int status_ = GLBA_OK;
+};
+
+// The flat problem full_ba hands to the solver (slam_core.cpp:750-819), kept for inspection / tests.
+struct PackedWindow {
+  std::vector<double> camera_params;              // 6 per keyframe: angle-axis(R), t
+  std::vector<double> point_params;               // 3 per map point
+  std::unordered_map<int, int> kf_to_param_idx;
+  std::unordered_map<int, int> point_to_param_idx;
+  std::vector<int> point_ids;                     // param idx -> map point id
+  std::vector<int32_t> obs_cam, obs_pt;
+  std::vector<double> obs_u, obs_v;
+  std::vector<uint8_t> cam_fixed;
+  int first_frame_idx = 0;
+};
+
+// Restates the packing of slam_core.cpp:750-838.  Returns false where the reference returns false (:746-749)
+// or would throw std::out_of_range from .at() (:760, 783, 790).  Deliberate, documented differences:
+//   * points are visited in increasing id (the reference iterates an unordered_set: arbitrary order, which only
+//     changes floating-point summation order);
+//   * the window test is kfid >= first+window (the reference's `>` lets an observation of keyframe first+window
+//     through and silently binds it to camera 0 via operator[], slam_core.cpp:808-810).
+inline bool pack_window(const Map& map, int window, int run_window, PackedWindow& out) {
+  if ((int)map.keyframes.size() < window || window <= 1) return false;
+  out = PackedWindow();
+  const int first = run_window + 1 - window;
+  out.first_frame_idx = first;
+  for (int i = first; i < first + window; ++i) {
+    auto it = map.keyframes.find(i);
+    if (it == map.keyframes.end()) return false;
+    out.kf_to_param_idx[i] = (int)out.camera_params.size() / 6;
+    double w[3];
+    rodrigues(it->second.R, w);
+    out.camera_params.insert(out.camera_params.end(), {w[0], w[1], w[2], it->second.t.v[0], it->second.t.v[1], it->second.t.v[2]});
+  }
+  std::vector<int> ids;
+  {
+    std::unordered_set<int> seen;
+    for (int i = first; i < first + window; ++i)
+      for (int mpid : map.keyframes.at(i).map_point_ids)
+        if (seen.insert(mpid).second) ids.push_back(mpid);
+    std::sort(ids.begin(), ids.end());
+  }
+  for (int mpid : ids) {
+    auto it = map.map_points.find(mpid);
+    if (it == map.map_points.end()) return false;
+    const MapPoint& mp = it->second;
+    if (mp.is_bad || mp.obs.empty()) continue;
+    const int pidx = (int)out.point_params.size() / 3;
+    out.point_to_param_idx[mpid] = pidx;
+    out.point_ids.push_back(mpid);
+    out.point_params.insert(out.point_params.end(), {mp.position.x, mp.position.y, mp.position.z});
+    for (const Observation& o : mp.obs) {
+      if (o.keyframe_id < first || o.keyframe_id >= first + window) continue;
+      out.obs_cam.push_back(out.kf_to_param_idx.at(o.keyframe_id));
+      out.obs_pt.push_back(pidx);
+      out.obs_u.push_back(o.point2D.x);
+      out.obs_v.push_back(o.point2D.y);
+    }
+  }
+  out.cam_fixed.assign(window, 0);
+  out.cam_fixed[0] = 1;           // SetParameterBlockConstant(camera 0) and (camera 1), slam_core.cpp:831-833
+  out.cam_fixed[1] = 1;
+  return true;
+}
+
+// Drop-in for slam_core::full_ba.  `run_window` = slam_types::run_window; tracking_mutex may be null.
+// On solver failure nothing is written back (the reference ignores ceres::Solver::Summary, slam_core.cpp:848-850;
+// leaving the map untouched is the safe reading of "inputs untouched on failure").
+inline bool full_ba(Backend& be, std::mutex& map_mutex, Map& map, const CameraMatrix& K, int window, int run_window,
+                    std::mutex* tracking_mutex = nullptr, const glba_options* options = nullptr, glba_summary* summary = nullptr) {
+  if (!be.ok()) return false;
+  PackedWindow pw;
+  if (!pack_window(map, window, run_window, pw)) return false;
+  glba_options opt;
+  if (options) opt = *options; else glba_default_options(&opt);      // CauchyLoss(1.0), 30 iterations, Ceres LM defaults
+  glba_problem p{};
+  p.n_cam = window; p.n_pt = (int32_t)pw.point_ids.size(); p.n_obs = (int64_t)pw.obs_cam.size();
+  p.cam = pw.camera_params.data(); p.pt = pw.point_params.data();
+  p.obs_cam = pw.obs_cam.data(); p.obs_pt = pw.obs_pt.data(); p.obs_u = pw.obs_u.data(); p.obs_v = pw.obs_v.data();
+  p.cam_fixed = pw.cam_fixed.data(); p.pt_fixed = nullptr;
+  p.fx = K.fx; p.fy = K.fy; p.cx = K.cx; p.cy = K.cy; p.memspace = GLBA_MEM_HOST;
+  glba_summary local;
+  glba_summary* s = summary ? summary : &local;
+  if (glba_solve(be.ctx(), &p, &opt, s) != GLBA_OK || s->termination == GLBA_TERM_FAILURE) return false;
+  // write-back, slam_core.cpp:856-871 (tracking lock first, then the map lock)
+  std::unique_lock<std::mutex> tl;
+  if (tracking_mutex) tl = std::unique_lock<std::mutex>(*tracking_mutex);
+  std::lock_guard<std::mutex> lk(map_mutex);
+  for (const auto& kv : pw.kf_to_param_idx) {
+    const double* cam = &pw.camera_params[(size_t)kv.second * 6];
+    Frame& kf = map.keyframes[kv.first];
+    rodrigues(cam, kf.R);
+    kf.t.v[0] = cam[3]; kf.t.v[1] = cam[4]; kf.t.v[2] = cam[5];
+  }
+  for (const auto& kv : pw.point_to_param_idx) {
+    const double* pt = &pw.point_params[(size_t)kv.second * 3];
+    map.map_points[kv.first].position = Point3d{pt[0], pt[1], pt[2]};
+  }
+  return true;
+}
+
+// Drop-in for slam_core::pose_only_ba (slam_core.cpp:1092-1140): R, t updated in place only on success.
+inline bool pose_only_ba(Backend& be, Mat33& R, Vec3& t, const std::vector<Point3d>& p3d, const std::vector<Point2d>& p2d,
+                         const CameraMatrix& K, const glba_options* options = nullptr, glba_summary* summary = nullptr) {
+  if (p3d.size() != p2d.size() || p3d.empty()) return false;          // slam_core.cpp:1096
+  if (!be.ok()) return false;
+  double cam[6];
+  rodrigues(R, cam);
+  cam[3] = t.v[0]; cam[4] = t.v[1]; cam[5] = t.v[2];
+  std::vector<double> X(3 * p3d.size()), uv(2 * p2d.size());
+  for (size_t i = 0; i < p3d.size(); ++i) {
+    X[3 * i] = p3d[i].x; X[3 * i + 1] = p3d[i].y; X[3 * i + 2] = p3d[i].z;
+    uv[2 * i] = p2d[i].x; uv[2 * i + 1] = p2d[i].y;
+  }
+  glba_options opt;
+  if (options) opt = *options; else glba_default_options(&opt);
+  glba_summary local;
+  glba_summary* s = summary ? summary : &local;
+  if (glba_pose_only(be.ctx(), cam, (int32_t)p3d.size(), X.data(), uv.data(), K.fx, K.fy, K.cx, K.cy, &opt, s) != GLBA_OK) return false;
+  if (s->termination == GLBA_TERM_FAILURE) return false;               // !summary.IsSolutionUsable(), slam_core.cpp:1132
+  rodrigues(cam, R);
+  t.v[0] = cam[3]; t.v[1] = cam[4]; t.v[2] = cam[5];
+  return true;
+}
+
+// post_ba_map_point_culling (slam_core.cpp:977-1038): candidates are the points first seen by keyframes
+// [run_window - local_ba_window, run_window - 4]; a point is flagged is_bad when it lies behind one of its
+// cameras, has fewer than `min_obs` observations or a mean reprojection error above `max_err` pixels.  The
+// per-point arithmetic over ALL of the point's observations runs on the GPU (glba_cull_points).
+inline int post_ba_map_point_culling(Backend& be, Map& map, const CameraMatrix& K, int run_window, int local_ba_window,
+                                     double max_err = 1.0, int min_obs = 3) {
+  if (!be.ok()) return -1;
+  std::vector<int> ids;
+  {
+    std::unordered_set<int> seen;
+    for (int i = run_window - local_ba_window; i <= run_window - 4; ++i) {
+      if (i < 0) continue;
+      auto kf = map.keyframes.find(i);
+      if (kf == map.keyframes.end()) continue;
+      for (int mp : kf->second.map_point_ids) {
+        auto it = map.map_points.find(mp);
+        if (it == map.map_points.end() || it->second.obs.empty() || it->second.is_bad) continue;
+        if (it->second.obs.front().keyframe_id == i && seen.insert(mp).second) ids.push_back(mp);
+      }
+    }
+    std::sort(ids.begin(), ids.end());
+  }
+  if (ids.empty()) return 0;
+  std::unordered_map<int, int> cam_idx;
+  std::vector<double> cams, pts;
+  std::vector<int32_t> oc, op;
+  std::vector<double> ou, ov;
+  for (size_t j = 0; j < ids.size(); ++j) {
+    const MapPoint& mp = map.map_points.at(ids[j]);
+    pts.insert(pts.end(), {mp.position.x, mp.position.y, mp.position.z});
+    for (const Observation& o : mp.obs) {
+      auto kf = map.keyframes.find(o.keyframe_id);
+      if (kf == map.keyframes.end()) return -1;                       // .at() would throw in the reference (:1004)
+      auto ins = cam_idx.emplace(o.keyframe_id, (int)cam_idx.size());
+      if (ins.second) {
+        double w[3];
+        rodrigues(kf->second.R, w);
+        cams.insert(cams.end(), {w[0], w[1], w[2], kf->second.t.v[0], kf->second.t.v[1], kf->second.t.v[2]});
+      }
+      oc.push_back(ins.first->second); op.push_back((int32_t)j); ou.push_back(o.point2D.x); ov.push_back(o.point2D.y);
+    }
+  }
+  glba_problem p{};
+  p.n_cam = (int32_t)cam_idx.size(); p.n_pt = (int32_t)ids.size(); p.n_obs = (int64_t)oc.size();
+  p.cam = cams.data(); p.pt = pts.data(); p.obs_cam = oc.data(); p.obs_pt = op.data(); p.obs_u = ou.data(); p.obs_v = ov.data();
+  p.fx = K.fx; p.fy = K.fy; p.cx = K.cx; p.cy = K.cy; p.memspace = GLBA_MEM_HOST;
+  std::vector<uint8_t> bad(ids.size());
+  if (glba_cull_points(be.ctx(), &p, min_obs, max_err, bad.data(), nullptr) != GLBA_OK) return -1;
+  int culled = 0;
+  for (size_t j = 0; j < ids.size(); ++j)
+    if (bad[j]) { map.map_points[ids[j]].is_bad = true; ++culled; }
+  return culled;
+}
+
+}  // namespace glslam

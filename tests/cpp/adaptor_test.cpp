@@ -1,0 +1,115 @@
+// Exercises include/glba_slam.hpp the way GL-SLAM's threads would: build a Map, call full_ba / pose_only_ba.
+//   adaptor_test pack  <scene.txt>            -> prints the packed problem (no GPU needed)
+//   adaptor_test solve <scene.txt>            -> runs full_ba on the GPU, prints refined keyframes / points
+//   adaptor_test pose  <pose.txt>             -> runs pose_only_ba, prints R, t
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+
+#include "glba_slam.hpp"
+
+using namespace glslam;
+
+static bool load_scene(const char* path, Map& map, CameraMatrix& K, int& window, int& run_window) {
+  std::ifstream f(path);
+  int n_cam, n_pt, n_obs, first;
+  if (!(f >> n_cam >> n_pt >> n_obs >> K.fx >> K.fy >> K.cx >> K.cy >> window >> run_window >> first)) return false;
+  for (int i = 0; i < n_cam; ++i) {
+    Frame fr; fr.id = first + i; fr.is_keyframe = true;
+    for (int q = 0; q < 9; ++q) f >> fr.R.m[q];
+    for (int q = 0; q < 3; ++q) f >> fr.t.v[q];
+    map.keyframes[fr.id] = fr;
+  }
+  for (int j = 0; j < n_pt; ++j) {
+    MapPoint mp; mp.id = 1000 + j;
+    int bad;
+    f >> mp.position.x >> mp.position.y >> mp.position.z >> bad;
+    mp.is_bad = bad != 0;
+    map.map_points[mp.id] = mp;
+  }
+  for (int k = 0; k < n_obs; ++k) {
+    int c, j; Observation o;
+    f >> c >> j >> o.point2D.x >> o.point2D.y;
+    o.keyframe_id = first + c; o.kp_index = k;
+    map.map_points[1000 + j].obs.push_back(o);
+    map.keyframes[o.keyframe_id].map_point_ids.push_back(1000 + j);   // one push per observation, like update_map_and_keyframe_data
+  }
+  map.next_keyframe_id = first + n_cam; map.next_point_id = 1000 + n_pt;
+  return (bool)f;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  const std::string mode = argv[1];
+  std::cout.precision(17);
+  if (mode == "pose") {
+    std::ifstream f(argv[2]);
+    int n; CameraMatrix K; Mat33 R; Vec3 t;
+    f >> n >> K.fx >> K.fy >> K.cx >> K.cy;
+    for (int q = 0; q < 9; ++q) f >> R.m[q];
+    for (int q = 0; q < 3; ++q) f >> t.v[q];
+    std::vector<Point3d> p3(n); std::vector<Point2d> p2(n);
+    for (int i = 0; i < n; ++i) f >> p3[i].x >> p3[i].y >> p3[i].z >> p2[i].x >> p2[i].y;
+    Backend be(0);
+    // size mismatch and empty input return false without touching R, t (slam_core.cpp:1096)
+    std::vector<Point2d> shorter(p2.begin(), p2.end() - 1);
+    Mat33 R0 = R;
+    if (pose_only_ba(be, R, t, p3, shorter, K) || std::memcmp(&R0, &R, sizeof(R)) != 0) { std::cout << "FAIL mismatch\n"; return 1; }
+    glba_summary s;
+    const bool ok = pose_only_ba(be, R, t, p3, p2, K, nullptr, &s);
+    std::cout << (ok ? "ok " : "false ") << s.n_iters << " " << s.final_cost << "\n";
+    for (int q = 0; q < 9; ++q) std::cout << R.m[q] << " ";
+    for (int q = 0; q < 3; ++q) std::cout << t.v[q] << " ";
+    std::cout << "\n";
+    return ok ? 0 : 1;
+  }
+  Map map; CameraMatrix K; int window = 0, run_window = 0;
+  if (!load_scene(argv[2], map, K, window, run_window)) { std::cerr << "bad scene file\n"; return 2; }
+  if (mode == "pack") {
+    PackedWindow pw;
+    // guards of slam_core.cpp:746-749
+    PackedWindow tmp;
+    if (pack_window(map, 1, run_window, tmp) || pack_window(map, (int)map.keyframes.size() + 1, run_window, tmp)) { std::cout << "FAIL guard\n"; return 1; }
+    if (!pack_window(map, window, run_window, pw)) { std::cout << "FAIL pack\n"; return 1; }
+    std::cout << pw.camera_params.size() / 6 << " " << pw.point_params.size() / 3 << " " << pw.obs_cam.size() << " " << pw.first_frame_idx << "\n";
+    for (double v : pw.camera_params) std::cout << v << " ";
+    std::cout << "\n";
+    for (int id : pw.point_ids) std::cout << id << " ";
+    std::cout << "\n";
+    for (size_t k = 0; k < pw.obs_cam.size(); ++k) std::cout << pw.obs_cam[k] << " " << pw.obs_pt[k] << " " << pw.obs_u[k] << " " << pw.obs_v[k] << " ";
+    std::cout << "\n";
+    for (uint8_t v : pw.cam_fixed) std::cout << (int)v << " ";
+    std::cout << "\n";
+    // Rodrigues round trip on every keyframe
+    double worst = 0;
+    for (auto& kv : map.keyframes) { double w[3]; Mat33 R2; rodrigues(kv.second.R, w); rodrigues(w, R2);
+      for (int q = 0; q < 9; ++q) worst = std::max(worst, std::fabs(R2.m[q] - kv.second.R.m[q])); }
+    std::cout << worst << "\n";
+    return 0;
+  }
+  if (mode == "solve") {
+    Backend be(0);
+    if (!be.ok()) { std::cout << "nodevice " << be.status() << "\n"; return 3; }
+    std::mutex map_mutex, tracking_mutex;
+    glba_summary s;
+    const bool ok = full_ba(be, map_mutex, map, K, window, run_window, &tracking_mutex, nullptr, &s);
+    std::cout << (ok ? "ok " : "false ") << s.n_iters << " " << s.initial_cost << " " << s.final_cost << "\n";
+    const int first = run_window + 1 - window;
+    for (int i = first; i < first + window; ++i) {
+      const Frame& fr = map.keyframes[i];
+      for (int q = 0; q < 9; ++q) std::cout << fr.R.m[q] << " ";
+      for (int q = 0; q < 3; ++q) std::cout << fr.t.v[q] << " ";
+      std::cout << "\n";
+    }
+    for (int j = 0; j < (int)map.map_points.size(); ++j) { const MapPoint& mp = map.map_points[1000 + j]; std::cout << mp.position.x << " " << mp.position.y << " " << mp.position.z << " "; }
+    std::cout << "\n";
+    const int culled = post_ba_map_point_culling(be, map, K, run_window, window, 1.0, 3);
+    std::cout << culled << "\n";
+    for (int j = 0; j < (int)map.map_points.size(); ++j) std::cout << (map.map_points[1000 + j].is_bad ? 1 : 0) << " ";
+    std::cout << "\n";
+    return ok ? 0 : 1;
+  }
+  return 2;
+}
