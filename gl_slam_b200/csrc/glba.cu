@@ -35,7 +35,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 }
 namespace {
-constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclSum = 0, kNcclMax = 2;
 struct NcclApi {
   void* h = nullptr;
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -86,9 +86,12 @@ struct glba_ctx {
   Buf chunk_cam, chunk_begin, chunk_end, cam_chunk_start, cam_free, pt_free, sort_tmp, keys_tmp, flags;
   Buf cam[2], camtab[2], pt4[2], cam0, pt40;                                         // state (double-buffered)
   Buf rec_pm, rec_cm, Craw, sp4, lam4, pblk, u4;
-  Buf part_pm, part_cm, acc27, yhat, Bc, gc, sc, lamc, Md, Minv, rhs, cg_x, cg_r, cg_p, cg_q, pg, yg, scal, cgst;
+  Buf part_pm, part_cm, acc27, yhat, Bc, gc, sc, lamc, Md, Minv, rhs, cg_x, cg_r, cg_p, cg_q, pg, yg, cgst;
+  double *d_accA = nullptr, *d_accB = nullptr;   // per-camera partial sums of the linearise / Schur passes
+  bool schur_fresh = false;                      // Schur pieces already built for the current linearisation and radius
+  double* d_scal = nullptr;   // NSCAL doubles at the tail of acc27 (one all-reduce carries camera sums + scalars)
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
-  Buf tile_pt, xtab, partA, partB, partc, counters;                                  // tiles, PCG gather table, camera-kernel partials
+  Buf tile_pt, xtab, partA, partB, partc, counters, cam_cnt;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
   int n_tiles = 0, max_track = 0, grid_c = 0;
   Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
@@ -163,9 +166,9 @@ void collect(glba_ctx* ctx) {
   ctx->ev_used = 0;
 }
 
-int allreduce(glba_ctx* ctx, double* p, size_t n, int op) {
+int allreduce(glba_ctx* ctx, void* p, size_t n, int op, int dtype = kNcclFloat64) {
   if (ctx->world <= 1) return GLBA_OK;
-  const int r = g_nccl.AllReduce(p, p, n, kNcclFloat64, op, ctx->comm, ctx->stream);
+  const int r = g_nccl.AllReduce(p, p, n, dtype, op, ctx->comm, ctx->stream);
   if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
   return GLBA_OK;
 }
@@ -280,20 +283,27 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
     CU(cudaMemsetAsync(ctx->pt_start.p, 0, sizeof(int) * ((size_t)n_pt + 1), s));
     CU(cudaMemsetAsync(ctx->cam_start.p, 0, sizeof(int) * ((size_t)n_cam + 1), s));
   }
-  if (n_cam) LAUNCH(k_free_flags, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
-  if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, ctx->pt_free.as<uint8_t>());
-  ctx->has_dup = false;
+  // a camera is part of the problem if ANY rank observes it: all-reduce the per-camera observation counts
+  // (and the duplicate flag) so every rank takes the same code path and issues the same collectives
+  ENSURE(int, ctx->cam_cnt, (size_t)n_cam + 2);
   if (n > 0 && n_cam <= DN_MAXCAM)
     LAUNCH(k_check_dup, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->flags.as<int>() + 3);
+  LAUNCH(k_counts, cdiv(n_cam + 2, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), (const int*)ctx->flags.as<int>() + 3, n > 0 ? 0 : 1, ctx->cam_cnt.as<int>());
+  if (ctx->world > 1) { int s__ = allreduce(ctx, ctx->cam_cnt.p, (size_t)n_cam + 2, kNcclSum, kNcclInt32); if (s__) return s__; }
+  if (n_cam) LAUNCH(k_free_flags_cnt, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_cnt.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
+  if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, ctx->pt_free.as<uint8_t>());
+  ctx->has_dup = false;
   if (n > 0) LAUNCH(k_max_track, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->flags.as<int>() + 4);
   CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(ctx->h_flags + 5, ctx->cam_cnt.as<int>() + n_cam, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));   // global duplicate flag, #empty shards
   // chunk list for the camera-major kernels (host, from cam_start)
   std::vector<int> h_start((size_t)n_cam + 1);
   std::vector<uint8_t> h_free(std::max(n_cam, 1));
   CU(cudaMemcpyAsync(h_start.data(), ctx->cam_start.p, sizeof(int) * ((size_t)n_cam + 1), cudaMemcpyDeviceToHost, s));
   if (n_cam) CU(cudaMemcpyAsync(h_free.data(), ctx->cam_free.p, n_cam, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  ctx->has_dup = (n > 0 && n_cam <= DN_MAXCAM) ? (ctx->h_flags[3] != 0) : false;
+  ctx->has_dup = (ctx->h_flags[5] != 0);
+  if (ctx->world > 1 && ctx->h_flags[6] != 0) return fail(ctx, GLBA_E_INVALID_ARG, "a rank holds an empty shard (%d of %d): every rank needs at least one observation", ctx->h_flags[6], ctx->world);
   ctx->max_track = ctx->h_flags[4];
   ctx->use_tiles = (n > 0 && ctx->max_track <= TILE_OBS / 2);
   ctx->n_tiles = 0;
@@ -333,21 +343,21 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->xtab, (size_t)XTAB * n_cam); ENSURE(double, ctx->partA, ctx->grid_c); ENSURE(double, ctx->partB, ctx->grid_c);
   ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8);
   CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned), s)); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1));
-  ENSURE(double, ctx->acc27, 27 * (size_t)n_cam); ENSURE(double, ctx->yhat, 6 * (size_t)n_cam);
+  ENSURE(double, ctx->acc27, 54 * (size_t)n_cam + NSCAL);     // [Schur sums 27C | Hessian sums 27C | scalars]: contiguous for one all-reduce
+  ctx->d_accB = ctx->acc27.as<double>(); ctx->d_accA = ctx->d_accB + 27 * (size_t)n_cam; ctx->d_scal = ctx->d_accA + 27 * (size_t)n_cam; ENSURE(double, ctx->yhat, 6 * (size_t)n_cam);
   ENSURE(double, ctx->Bc, 36 * (size_t)n_cam); ENSURE(double, ctx->gc, 6 * (size_t)n_cam); ENSURE(double, ctx->sc, 6 * (size_t)n_cam);
   ENSURE(double, ctx->lamc, 6 * (size_t)n_cam); ENSURE(double, ctx->Md, 36 * (size_t)n_cam); ENSURE(double, ctx->Minv, 36 * (size_t)n_cam);
   ENSURE(double, ctx->rhs, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_x, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_r, 6 * (size_t)n_cam);
   ENSURE(double, ctx->cg_p, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_q, 6 * (size_t)n_cam); ENSURE(double, ctx->pg, 6 * (size_t)n_cam);
-  ENSURE(double, ctx->yg, 6 * (size_t)n_cam); ENSURE(double, ctx->scal, NSCAL); ENSURE(CgState, ctx->cgst, 1);
+  ENSURE(double, ctx->yg, 6 * (size_t)n_cam); ENSURE(CgState, ctx->cgst, 1);
   if (n_cam <= DN_MAXCAM && n_cam > 0) {
     ctx->dn_grid = std::max(1, std::min(64, cdiv(n_pt, 128)));
     ctx->dn_ppc = cdiv(n_pt, ctx->dn_grid);
     const size_t len = (size_t)(n_cam * (n_cam + 1) / 2) * 36 + 6 * (size_t)n_cam;
     ENSURE(double, ctx->dn_part, len * ctx->dn_grid); ENSURE(double, ctx->dn_red, len);
   }
-  CU(cudaMemsetAsync(ctx->scal.p, 0, sizeof(double) * NSCAL, s));
   CU(cudaMemsetAsync(ctx->yhat.p, 0, sizeof(double) * 6 * n_cam, s));
-  CU(cudaMemsetAsync(ctx->acc27.p, 0, sizeof(double) * 27 * n_cam, s));
+  CU(cudaMemsetAsync(ctx->acc27.p, 0, sizeof(double) * (54 * (size_t)n_cam + NSCAL), s));
   if (n_cam) LAUNCH(k_cam_prep, cdiv(n_cam, 128), 128, n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>());
   mark(ctx, -1);
   ctx->loaded = true;
@@ -373,7 +383,7 @@ TileArgs tile_args(glba_ctx* ctx) { return TileArgs{ctx->tile_pt.as<int>(), ctx-
 int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
   ReduceMap M{}; M.n = 5;
   for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = (q == max_col); }
-  LAUNCH(k_reduce_partials, 1, NT_CAM, rows, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
+  LAUNCH(k_reduce_partials, 1, NT_CAM, rows, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal);
   return GLBA_OK;
 }
 
@@ -424,10 +434,13 @@ void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
            1.0 / radius, ctx->part_pm.as<double>());
 }
 
-// residual / weight / Jacobian records + Hessian blocks at the current state (K_A + K_B blocks)
-int do_linearize(glba_ctx* ctx, const glba_options* o, int first, double radius) {
+// Linearise (K_A + K_B blocks) and, if with_schur, the Schur pieces for `radius` in the same pass.  The Schur kernel
+// needs only point-local data, so when the map is sharded both sets of per-camera partial sums and the scalars travel
+// in ONE all-reduce, issued after both heavy kernels.
+int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double radius, bool with_schur) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  with_schur = with_schur && ctx->n_free_cam > 0;
   mark(ctx, PH_LIN);
   if (n_pt) {
     launch_linearize_points(ctx, o, first, radius);
@@ -437,19 +450,35 @@ int do_linearize(glba_ctx* ctx, const glba_options* o, int first, double radius)
   if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
   if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr, 0);
-  if (ctx->world > 1) {
-    AR(ctx->acc27.as<double>(), 27 * (size_t)n_cam, kNcclSum);
-    AR(ctx->scal.as<double>() + S_COST, 4, kNcclSum);
-    AR(ctx->scal.as<double>() + S_GMAX_P, 1, kNcclMax);
+                    (const double*)ctx->part_cm.as<double>(), ctx->d_accA, (const CgState*)nullptr, 0);
+  if (with_schur) {
+    mark(ctx, PH_SCHUR);
+    if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+                              (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>());
+    if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
+                      (const double*)ctx->part_cm.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
+  }
+  if (ctx->world > 1) {     // per-camera sums | cost, |x_p|^2, bad, notpd | per-rank gradient max slots
+    LAUNCH(k_gmax_scatter, 1, 32, ctx->rank, ctx->d_scal);
+    if (with_schur) AR(ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
+    else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
+    LAUNCH(k_gmax_gather, 1, 32, ctx->world, ctx->d_scal);
   }
   if (n_cam) LAUNCH(k_cam_lin_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
-                    (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->acc27.as<double>(), ctx->Bc.as<double>(), ctx->gc.as<double>(),
+                    (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, ctx->Bc.as<double>(), ctx->gc.as<double>(),
                     ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal,
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->scal.as<double>());
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->d_scal);
+  if (with_schur && n_cam)
+    LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double*)ctx->d_accB, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(),
+           1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->partc.as<double>(),
+           ctx->counters.as<unsigned>() + 1, ctx->d_scal);
+  ctx->schur_fresh = with_schur;
   mark(ctx, -1);
   return GLBA_OK;
 }
+int do_linearize(glba_ctx* ctx, const glba_options* o, int first, double radius) { return do_linearize_impl(ctx, o, first, radius, false); }
+int do_linearize_schur(glba_ctx* ctx, const glba_options* o, int first, double radius) { return do_linearize_impl(ctx, o, first, radius, true); }
 
 // re-damp point blocks for a new radius (after a rejected / invalid step)
 int do_redamp(glba_ctx* ctx, double radius) {
@@ -460,13 +489,13 @@ int do_redamp(glba_ctx* ctx, double radius) {
   LAUNCH(k_point_damp, grid_pm, NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
          (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>());
   ReduceMap M{}; M.n = 1; M.slot[0] = S_NOTPD_P; M.is_max[0] = 0;
-  LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 1, (const double*)ctx->part_pm.as<double>(), M, ctx->scal.as<double>());
-  if (ctx->world > 1) AR(ctx->scal.as<double>() + S_NOTPD_P, 1, kNcclSum);
+  LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 1, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal);
+  if (ctx->world > 1) AR(ctx->d_scal + S_NOTPD_P, 1, kNcclSum);
   mark(ctx, -1);
   return GLBA_OK;
 }
 
-// Schur complement pieces: preconditioner blocks (= diagonal of S), reduced rhs
+// Schur complement pieces alone (after the radius changed): preconditioner blocks (= diagonal of S), reduced rhs
 int do_schur(glba_ctx* ctx, double radius) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
@@ -474,12 +503,13 @@ int do_schur(glba_ctx* ctx, double radius) {
   if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>());
   if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                    (const double*)ctx->part_cm.as<double>(), ctx->acc27.as<double>(), (const CgState*)nullptr, 0);
-  if (ctx->world > 1) AR(ctx->acc27.as<double>(), 27 * (size_t)n_cam, kNcclSum);
+                    (const double*)ctx->part_cm.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
+  if (ctx->world > 1) AR(ctx->d_accB, 27 * (size_t)n_cam, kNcclSum);
   if (n_cam) LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-                    (const double*)ctx->acc27.as<double>(), (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(),
+                    (const double*)ctx->d_accB, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(),
                     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(),
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 1, ctx->scal.as<double>());
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 1, ctx->d_scal);
+  ctx->schur_fresh = true;
   mark(ctx, -1);
   return GLBA_OK;
 }
@@ -563,7 +593,7 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
   mark(ctx, PH_SOLVE);
   k_dense_solve<<<1, DN_NT, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_red.as<double>(),
       (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius,
-      ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->scal.as<double>());
+      ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->d_scal);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   mark(ctx, -1);
   return GLBA_OK;
@@ -584,22 +614,22 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
   if (n_cam) LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
                     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->scal.as<double>());
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal);
   if (n_pt) {
     launch_point_pass1(ctx, o, radius);
     const int slots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
     reduce_pm_partials(ctx, pm_rows(ctx), slots, -1);
   }
-  if (ctx->world > 1) AR(ctx->scal.as<double>() + S_COST_C, 5, kNcclSum);
+  if (ctx->world > 1) AR(ctx->d_scal + S_COST_C, 5, kNcclSum);
   mark(ctx, -1);
-  CU(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect(ctx);
   return GLBA_OK;
 }
 
 int fetch_scal(glba_ctx* ctx) {
-  CU(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect(ctx);
   return GLBA_OK;
@@ -613,7 +643,10 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_NONE;
   double radius = o->initial_radius, decrease_factor = 2.0;
   int n_invalid = 0;
-  if ((st = do_linearize(ctx, o, 1, radius))) return st;
+  const bool dense = want_dense(ctx, o);
+  if (o->linsolve == GLBA_LINSOLVE_DENSE && !dense && ctx->n_free_cam > 0)
+    return fail(ctx, GLBA_E_UNSUPPORTED, "dense solve needs <= %d cameras and no duplicate (point,camera) observations", DN_MAXCAM);
+  if ((st = do_linearize_impl(ctx, o, 1, radius, !dense))) return st;
   if ((st = fetch_scal(ctx))) return st;
   const double* S = ctx->h_scal;
   if (S[S_BAD] > 0.0 || !std::isfinite(S[S_COST])) {
@@ -626,9 +659,6 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   double x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
   sum->initial_cost = cost; sum->cost[0] = cost; sum->cost_candidate[0] = cost; sum->radius[0] = radius; sum->gradient_max_norm[0] = gmax;
   int it = 0;
-  const bool dense = want_dense(ctx, o);
-  if (o->linsolve == GLBA_LINSOLVE_DENSE && !dense && ctx->n_free_cam > 0)
-    return fail(ctx, GLBA_E_UNSUPPORTED, "dense solve needs <= %d cameras and no duplicate (point,camera) observations", DN_MAXCAM);
   bool fresh = true;   // point blocks are damped for the current radius
   // number of free parameters: free cameras + free points (host knows cameras; points: any observation => >0)
   if (ctx->n_obs == 0) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
@@ -637,12 +667,13 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     if (gmax <= o->gradient_tol) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
     if (radius <= o->min_radius) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_MIN_RADIUS; break; }
     ++it;
-    if (!fresh) { if ((st = do_redamp(ctx, radius))) return st; }
+    if (!fresh) { if ((st = do_redamp(ctx, radius))) return st; ctx->schur_fresh = false; }
     fresh = true;
     int cg_it = 0;
     if (dense) { if ((st = do_dense(ctx, o, radius))) return st; }
     else {
-      if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
+      if (ctx->n_free_cam > 0 && !ctx->schur_fresh) { if ((st = do_schur(ctx, radius))) return st; }
+      ctx->schur_fresh = false;
       if ((st = do_pcg(ctx, o, radius, &cg_it))) return st;
     }
     sum->cg_iters[it] = cg_it;
@@ -675,7 +706,7 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
       radius = std::min(o->max_radius, radius);
       decrease_factor = 2.0;
-      if ((st = do_linearize(ctx, o, 0, radius))) return st;
+      if ((st = do_linearize_impl(ctx, o, 0, radius, !dense))) return st;
       if ((st = fetch_scal(ctx))) return st;
       if (S[S_BAD] > 0.0 || !std::isfinite(S[S_COST])) { sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; break; }
       cost = S[S_COST]; gmax = std::max(S[S_GMAX_P], S[S_GMAX_C]); x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
@@ -770,7 +801,7 @@ int glba_nccl_unique_id(void* out_id) {
 int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (!cfg || !out) return GLBA_E_INVALID_ARG;
   *out = nullptr;
-  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return GLBA_E_INVALID_ARG;
+  if (cfg->world < 1 || cfg->world > MAX_WORLD || cfg->rank < 0 || cfg->rank >= cfg->world) return GLBA_E_INVALID_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GLBA_E_NO_DEVICE; }
   if (cfg->device < 0 || cfg->device >= ndev) return GLBA_E_INVALID_ARG;
@@ -800,8 +831,8 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->chunk_begin, &ctx->chunk_end, &ctx->cam_chunk_start, &ctx->cam_free, &ctx->pt_free, &ctx->sort_tmp, &ctx->keys_tmp, &ctx->flags,
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
-                &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->scal, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters};
+                &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -853,8 +884,7 @@ int glba_linearize_resident(glba_ctx* ctx, const glba_options* opt, double radiu
   CU(cudaSetDevice(ctx->device));
   int st = validate_options(ctx, opt);
   if (st) return st;
-  if ((st = do_linearize(ctx, opt, 1, radius))) return st;
-  if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
+  if ((st = do_linearize_schur(ctx, opt, 1, radius))) return st;
   if (cost) {
     if ((st = fetch_scal(ctx))) return st;
     *cost = ctx->h_scal[S_COST];
@@ -874,8 +904,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
   if (n_pt == 0 || ctx->n_chunks == 0) return GLBA_OK;
   // a complete pass first so every buffer the kernels read is valid
-  if ((st = do_linearize(ctx, opt, 1, radius))) return st;
-  if ((st = do_schur(ctx, radius))) return st;
+  if ((st = do_linearize_schur(ctx, opt, 1, radius))) return st;
   CgState* cg = ctx->cgst.as<CgState>();
   LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
          (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->xtab.as<double>(), cg,
@@ -907,7 +936,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
          (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
          (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->scal.as<double>());
+         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal);
   if ((st = timed([&] { launch_point_pass1(ctx, opt, radius); }, &out->backsub_cost_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_point_damp, cdiv(n_pt, NT_PM), NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
            (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms))) return st;
@@ -917,15 +946,15 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
     reduce_pm_partials(ctx, pm_rows(ctx), slots, 4);
     for (int rep2 = 0; rep2 < 2; ++rep2)
       LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
-             ctx->acc27.as<double>(), (const CgState*)nullptr, 0);
+             ctx->d_accB, (const CgState*)nullptr, 0);
     LAUNCH(k_cam_lin_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
-           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->acc27.as<double>(), ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(),
            ctx->lamc.as<double>(), 0, opt->jacobi_scaling, opt->min_lm_diagonal, opt->max_lm_diagonal, ctx->partc.as<double>(),
-           ctx->counters.as<unsigned>() + 0, ctx->scal.as<double>());
+           ctx->counters.as<unsigned>() + 0, ctx->d_scal);
     LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->acc27.as<double>(), (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(),
+           (const double*)ctx->d_accB, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(),
            1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 1,
-           ctx->scal.as<double>()); }, &out->small_kernels_ms);
+           ctx->d_scal); }, &out->small_kernels_ms);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return st;
 }
@@ -967,8 +996,7 @@ int glba_linearize(glba_ctx* ctx, const glba_problem* prob, const glba_options* 
   if (st) return st;
   if ((st = load_problem(ctx, prob))) return st;
   for (int q = 0; q < PH_COUNT; ++q) ctx->t_phase[q] = 0.0;
-  if ((st = do_linearize(ctx, opt, 1, radius))) return st;
-  if (ctx->n_free_cam > 0) { if ((st = do_schur(ctx, radius))) return st; }
+  if ((st = do_linearize_schur(ctx, opt, 1, radius))) return st;
   if ((st = fetch_scal(ctx))) return st;
   out->cost = ctx->h_scal[S_COST];
   out->t_linearize_ms = ctx->t_phase[PH_LIN]; out->t_schur_ms = ctx->t_phase[PH_SCHUR];

@@ -30,24 +30,26 @@ constexpr int NT_CM = 256;  // threads per CTA, camera-major kernels (one CTA pe
 constexpr int NT_CAM = 1024;  // threads of the single-CTA camera kernels
 
 // scalar slots (device array `scal`), written by fixed-order reductions
+constexpr int MAX_WORLD = 16;
 enum Scal {
-  // [0..8] point-derived sums: allreduced (sum) across ranks when the map is sharded
+  // [0..3] point-derived sums of a linearisation; they sit right behind the per-camera partial sums so ONE
+  // all-reduce carries both when the map is sharded
   S_COST = 0,     // 1/2 sum rho at the linearisation point
   S_XN2_P,        // |x|^2 over free points
   S_BAD,          // non-finite residuals at the linearisation point (count)
   S_NOTPD_P,      // point blocks that failed LDL'
-  S_COST_C,       // candidate cost
+  S_GSLOT0,       // [4..19] one slot per rank: max |g| over that rank's free points (sum-reduce, then max locally)
+  S_COST_C = S_GSLOT0 + MAX_WORLD,   // [20..24] candidate-step sums, one small all-reduce per LM iteration
   S_YN2_P,        // |y_p|^2
   S_YG_P,         // y_p . g_p
   S_YLY_P,        // y_p' Lambda_p y_p
   S_BAD_C,        // non-finite residuals at the candidate
-  // [9] point-derived max: allreduced (max)
-  S_GMAX_P,       // max |g| over free points
-  // [10..15] camera-derived, replicated on every rank
+  S_GMAX_P,       // max |g| over free points (all ranks)
+  // camera-derived, replicated on every rank
   S_XN2_C, S_GMAX_C, S_YN2_C, S_YG_C, S_YLY_C, S_NOTPD_C,
   S_COUNT
 };
-constexpr int NSCAL = 16;
+constexpr int NSCAL = 40;
 
 struct Intr { double fx, fy, cx, cy; };
 
@@ -690,6 +692,14 @@ k_reduce_partials(const int rows, const int nv, const double* __restrict__ part,
   }
 }
 
+__global__ void k_gmax_scatter(const int rank, double* __restrict__ scal) {
+  const int i = threadIdx.x;
+  if (i < MAX_WORLD) scal[S_GSLOT0 + i] = (i == rank) ? scal[S_GMAX_P] : 0.0;
+}
+__global__ void k_gmax_gather(const int world, double* __restrict__ scal) {
+  if (threadIdx.x == 0) { double m = 0.0; for (int i = 0; i < world; ++i) m = fmax(m, scal[S_GSLOT0 + i]); scal[S_GMAX_P] = m; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Single-CTA camera kernels (camera-sized vectors: <= 10^4 x 6 doubles).
 // ---------------------------------------------------------------------------------------------
@@ -788,6 +798,18 @@ __global__ void k_free_flags(const int n, const int* __restrict__ start, const u
   if (i >= n) return;
   const bool seen = start[i + 1] > start[i];
   free_out[i] = (seen && !(fixed && fixed[i])) ? 1 : 0;
+}
+// cnt[i] = local observations of camera i; cnt[n_cam] = local duplicate flag (all-reduced by the host when sharded)
+__global__ void k_counts(const int n_cam, const int* __restrict__ cam_start, const int* __restrict__ dup_flag, const int empty,
+                         int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cam) cnt[i] = cam_start[i + 1] - cam_start[i];
+  else if (i == n_cam) cnt[i] = (*dup_flag != 0) ? 1 : 0;
+  else if (i == n_cam + 1) cnt[i] = empty;
+}
+__global__ void k_free_flags_cnt(const int n, const int* __restrict__ cnt, const uint8_t* __restrict__ fixed, uint8_t* __restrict__ free_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) free_out[i] = (cnt[i] > 0 && !(fixed && fixed[i])) ? 1 : 0;
 }
 __global__ void k_pack_pt(const int n, const double* __restrict__ pt3, double4* __restrict__ pt4) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;

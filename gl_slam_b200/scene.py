@@ -65,13 +65,16 @@ def _trajectory(n_cam, step, yaw_per_frame, loop):
 def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2rad(0.5), loop=False,
                pixel_sigma=0.5, outlier_frac=0.0, outlier_px=(10.0, 50.0), rot_sigma=0.02, pos_sigma=0.05,
                pt_sigma=0.10, depth=(5.0, 50.0), n_fixed=2, K=KITTI_K, return_gt=False, min_parallax_deg=1.0,
-               creation_order=True):
+               creation_order=True, shard=0, start_range=None):
     """track_len: int, or callable(rng, n_pt) -> int array (clipped to [2, n_cam]).
 
     Returns a HostProblem whose cam/pt are the *initial guess* (ground truth + Gaussian noise; the first
     n_fixed cameras stay at ground truth and are flagged fixed, slam_core.cpp:831-833).
     """
-    rng = np.random.default_rng(seed)
+    # cameras (trajectory + initial-guess noise) depend on `seed` only, so every rank of a sharded run builds the
+    # same replicated camera set; points / observations additionally depend on `shard`
+    rng_cam = np.random.default_rng([seed, 0])
+    rng = np.random.default_rng([seed, 1, shard])
     fx, fy, cx, cy = K
     cam_gt = _trajectory(n_cam, step, yaw_per_frame, loop)
     if callable(track_len):
@@ -79,7 +82,9 @@ def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2r
     else:
         tl = np.full(n_pt, int(track_len), dtype=np.int64)
     tl = np.clip(tl, 2 if n_cam >= 2 else 1, n_cam)
-    if loop:
+    if start_range is not None:
+        start = rng.integers(start_range[0], start_range[1], size=n_pt)
+    elif loop:
         start = rng.integers(0, n_cam, size=n_pt)
     else:
         start = (rng.random(n_pt) * (n_cam - tl + 1)).astype(np.int64)
@@ -132,8 +137,8 @@ def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2r
         u = np.where(bad, u + mag * np.cos(ang), u)
         v = np.where(bad, v + mag * np.sin(ang), v)
     cam0 = cam_gt.copy()
-    cam0[n_fixed:, :3] += rng.normal(0.0, rot_sigma, size=(n_cam - n_fixed, 3)) if n_cam > n_fixed else 0.0
-    cam0[n_fixed:, 3:] += rng.normal(0.0, pos_sigma, size=(n_cam - n_fixed, 3)) if n_cam > n_fixed else 0.0
+    cam0[n_fixed:, :3] += rng_cam.normal(0.0, rot_sigma, size=(n_cam - n_fixed, 3)) if n_cam > n_fixed else 0.0
+    cam0[n_fixed:, 3:] += rng_cam.normal(0.0, pos_sigma, size=(n_cam - n_fixed, 3)) if n_cam > n_fixed else 0.0
     pt0 = pt_gt + rng.normal(0.0, pt_sigma, size=(n_pt, 3))
     cam_fixed = np.zeros(n_cam, dtype=np.uint8)
     cam_fixed[:n_fixed] = 1
@@ -171,6 +176,21 @@ def config(name, scale=1.0, **overrides):
         raise KeyError(name)
     kw.update(overrides)
     return make_scene(**kw)
+
+
+def config_weak(name, world, rank, scale=1.0):
+    """Weak-scaling family: an N-times larger loop map (N x cameras, N x points) of which rank r generates and owns
+    the arc whose tracks start at cameras [r*n_cam1, (r+1)*n_cam1) — the contiguous block shard_by_point would hand it.
+    Cameras are identical on every rank.  world=1 is the plain config."""
+    name = name.upper()
+    if name not in ("C4", "C5"):
+        raise KeyError("weak scaling is defined for the loop maps C4 / C5")
+    base = dict(C4=(1800, 1000000, 3.0, 4, 0.0), C5=(10000, 4000000, 5.5, 5, 0.10))[name]
+    n_cam1 = max(8, int(base[0] * min(1.0, scale * 4)))
+    n_pt1 = max(64, int(base[1] * scale))
+    return make_scene(n_cam=n_cam1 * world, n_pt=n_pt1, track_len=_poisson_tracks(2, base[2]), seed=base[3], loop=True,
+                      outlier_frac=base[4], rot_sigma=0.002, pos_sigma=0.03, pt_sigma=0.10, shard=rank,
+                      start_range=(rank * n_cam1, (rank + 1) * n_cam1) if world > 1 else None)
 
 
 def pose_only_scene(n, seed, K=KITTI_K, pixel_sigma=0.5, outlier_frac=0.05, rot_sigma=0.01, pos_sigma=0.05):

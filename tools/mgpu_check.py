@@ -1,0 +1,68 @@
+"""Multi-rank parity check (launch with torchrun, one rank per GPU): a sharded solve must reproduce the
+single-rank oracle trajectory; cameras identical on every rank; each rank returns its own points."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gl_slam_b200 as g  # noqa: E402
+from gl_slam_b200 import _abi, scene  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    idt = torch.zeros(_abi.GLBA_NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(g.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx = g.Context(device=local, rank=rank, world=world, nccl_id=bytes(idt.cpu().numpy().tobytes()))
+    results = {}
+    cases = {
+        "window_dense": (dict(n_cam=10, n_pt=2000, track_len=4, seed=2, outlier_frac=0.05, rot_sigma=0.005, pos_sigma=0.03), {}),
+        "map_pcg": (dict(n_cam=24, n_pt=3000, track_len=lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=41, rot_sigma=0.003, pos_sigma=0.03), {}),
+        "huber": (dict(n_cam=16, n_pt=1500, track_len=4, seed=8, outlier_frac=0.1, rot_sigma=0.004, pos_sigma=0.03), dict(loss=1)),
+    }
+    ok = True
+    for name, (kw, okw) in cases.items():
+        prob = scene.make_scene(**kw)
+        sub, idx = scene.shard_by_point(prob, world, rank)
+        got, s = ctx.solve(sub, g.options(**okw))
+        # cameras must be bit-identical across ranks (all-reduced sums are)
+        cam_t = torch.from_numpy(got.cam).to(dev)
+        cam0 = cam_t.clone()
+        dist.broadcast(cam0, 0)
+        same = bool(torch.equal(cam_t, cam0))
+        pts = torch.zeros(prob.n_pt, 3, dtype=torch.float64, device=dev)
+        pts[torch.from_numpy(idx).to(dev)] = torch.from_numpy(got.pt).to(dev)
+        dist.all_reduce(pts)
+        if rank == 0:
+            from oracle import oracle
+            ref, so = oracle.solve(prob, oracle.options(**okw))
+            n = min(len(s["cost"]), len(so["cost"]))
+            rel = max(abs(a - b) / abs(b) for a, b in zip(s["cost"][:n], so["cost"][:n]))
+            d = np.linalg.norm(ref.pt[prob.obs_pt] - prob.cam[prob.obs_cam, 3:6], axis=1)
+            far = np.zeros(prob.n_pt, bool); np.logical_or.at(far, prob.obs_pt, d > 150.0)
+            perr = float((np.linalg.norm(pts.cpu().numpy() - ref.pt, axis=1) / np.maximum(np.linalg.norm(ref.pt, axis=1), 1.0))[~far].max())
+            results[name] = dict(iters=[s["n_iters"], so["n_iters"]], cost_rel=rel, cam_err=float(np.abs(got.cam - ref.cam).max()), pt_err=perr,
+                                 cams_identical=same, cg=max(s["cg_iters"]))
+            ok &= s["n_iters"] == so["n_iters"] and rel < 1e-9 and np.allclose(got.cam, ref.cam, rtol=1e-6, atol=1e-8) and perr < 1e-6
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok &= bool(flag.item())
+    if rank == 0:
+        print(json.dumps({"world": world, "ok": bool(ok), "cases": results}))
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
