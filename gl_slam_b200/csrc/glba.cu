@@ -91,7 +91,7 @@ struct glba_ctx {
   bool schur_fresh = false;                      // Schur pieces already built for the current linearisation and radius
   double* d_scal = nullptr;   // NSCAL doubles at the tail of acc27 (one all-reduce carries camera sums + scalars)
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
-  Buf tile_pt, xtab, partA, partB, partc, counters, cam_cnt;                                  // tiles, PCG gather table, camera-kernel partials
+  Buf tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
   int n_tiles = 0, max_track = 0, grid_c = 0;
   Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
@@ -105,6 +105,7 @@ struct glba_ctx {
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_phase;
   int ev_used = 0;
+  bool timing = true;          // per-phase CUDA events (off for small problems: the event API calls rival the kernels)
   double t_phase[PH_COUNT] = {0, 0, 0, 0, 0};
 };
 
@@ -150,6 +151,7 @@ void release(Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 inline int cdiv(long a, int b) { return (int)((a + b - 1) / b); }
 
 void mark(glba_ctx* ctx, int phase) {
+  if (!ctx->timing) return;
   if (ctx->ev_used == (int)ctx->ev.size()) {
     cudaEvent_t e; cudaEventCreate(&e); ctx->ev.push_back(e); ctx->ev_phase.push_back(0);
   }
@@ -342,7 +344,8 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->part_pm, 5 * (size_t)std::max(std::max(grid_pm, ctx->n_tiles), 1));
   ENSURE(double, ctx->xtab, (size_t)XTAB * n_cam); ENSURE(double, ctx->partA, ctx->grid_c); ENSURE(double, ctx->partB, ctx->grid_c);
   ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8);
-  CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned), s)); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1));
+  CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned), s));
+  ctx->timing = (n >= 200000); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1)); ENSURE(double, ctx->part_cm2, 27 * (size_t)std::max(ctx->n_chunks, 1));
   ENSURE(double, ctx->acc27, 54 * (size_t)n_cam + NSCAL);     // [Schur sums 27C | Hessian sums 27C | scalars]: contiguous for one all-reduce
   ctx->d_accB = ctx->acc27.as<double>(); ctx->d_accA = ctx->d_accB + 27 * (size_t)n_cam; ctx->d_scal = ctx->d_accA + 27 * (size_t)n_cam; ENSURE(double, ctx->yhat, 6 * (size_t)n_cam);
   ENSURE(double, ctx->Bc, 36 * (size_t)n_cam); ENSURE(double, ctx->gc, 6 * (size_t)n_cam); ENSURE(double, ctx->sc, 6 * (size_t)n_cam);
@@ -351,7 +354,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->cg_p, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_q, 6 * (size_t)n_cam); ENSURE(double, ctx->pg, 6 * (size_t)n_cam);
   ENSURE(double, ctx->yg, 6 * (size_t)n_cam); ENSURE(CgState, ctx->cgst, 1);
   if (n_cam <= DN_MAXCAM && n_cam > 0) {
-    ctx->dn_grid = std::max(1, std::min(64, cdiv(n_pt, 128)));
+    ctx->dn_grid = std::max(1, std::min(148, cdiv(n_pt, 32)));
     ctx->dn_ppc = cdiv(n_pt, ctx->dn_grid);
     const size_t len = (size_t)(n_cam * (n_cam + 1) / 2) * 36 + 6 * (size_t)n_cam;
     ENSURE(double, ctx->dn_part, len * ctx->dn_grid); ENSURE(double, ctx->dn_red, len);
@@ -387,6 +390,15 @@ int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
   return GLBA_OK;
 }
 
+RedArgs red_args(glba_ctx* ctx, int counter, const int* slots) {
+  RedArgs R; R.counter = ctx->counters.as<unsigned>() + counter; R.scal = ctx->d_scal;
+  for (int q = 0; q < 5; ++q) R.slots[q] = slots[q];
+  return R;
+}
+const int kLinSlots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
+const int kStepSlots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
+
+// point-major half of a linearisation, INCLUDING the reduction of its scalars into d_scal
 void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
   const int c = ctx->cur;
   if (ctx->use_tiles) {
@@ -396,13 +408,15 @@ void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, do
     k_linearize_tile<<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
            ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
-           o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
+           o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-  } else
+  } else {
     LAUNCH(k_linearize_pm, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
            ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
            o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
+    reduce_pm_partials(ctx, cdiv(ctx->n_pt, NT_PM), kLinSlots, 4);
+  }
 }
 int pm_rows(const glba_ctx* ctx) { return ctx->use_tiles ? ctx->n_tiles : cdiv(ctx->n_pt, NT_PM); }
 
@@ -411,7 +425,8 @@ void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg,
   if (ctx->use_tiles)
     LAUNCH(k_point_tile<0>, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), cg, li,
-           (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr);
+           (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr,
+           RedArgs{});
   else
     LAUNCH(k_point_pass<0>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
@@ -425,13 +440,35 @@ void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
     LAUNCH(k_point_tile<1>, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr, 0,
            (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
-           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>());
-  else
+           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(),
+           red_args(ctx, 5, kStepSlots));
+  else {
     LAUNCH(k_point_pass<1>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
            (double4*)nullptr, (const CgState*)nullptr, 0, (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(),
            (const double*)ctx->camtab[d].as<double>(), (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(),
            1.0 / radius, ctx->part_pm.as<double>());
+    reduce_pm_partials(ctx, cdiv(ctx->n_pt, NT_PM), kStepSlots, -1);
+  }
+}
+
+#define CAM_LIN_FIN_ARGS n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(), \
+    (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), \
+    ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, \
+    o->max_lm_diagonal, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->d_scal
+void launch_cam_lin_fin(glba_ctx* ctx, const glba_options* o, int first) {
+  const int c = ctx->cur, n_cam = ctx->n_cam;
+  if (ctx->world > 1) LAUNCH(k_cam_lin_fin<false>, ctx->grid_c, NT_C, CAM_LIN_FIN_ARGS);
+  else LAUNCH(k_cam_lin_fin<true>, ctx->grid_c, NT_C, CAM_LIN_FIN_ARGS);
+}
+#define CAM_SCHUR_FIN_ARGS n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accB, \
+    (const int*)ctx->cam_chunk_start.as<int>(), (const double*)part27, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), \
+    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->partc.as<double>(), \
+    ctx->counters.as<unsigned>() + 1, ctx->d_scal
+void launch_cam_schur_fin(glba_ctx* ctx, double radius, const double* part27) {
+  const int c = ctx->cur, n_cam = ctx->n_cam;
+  if (ctx->world > 1) LAUNCH(k_cam_schur_fin<false>, ctx->grid_c, NT_C, CAM_SCHUR_FIN_ARGS);
+  else LAUNCH(k_cam_schur_fin<true>, ctx->grid_c, NT_C, CAM_SCHUR_FIN_ARGS);
 }
 
 // Linearise (K_A + K_B blocks) and, if with_schur, the Schur pieces for `radius` in the same pass.  The Schur kernel
@@ -442,21 +479,18 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
   with_schur = with_schur && ctx->n_free_cam > 0;
   mark(ctx, PH_LIN);
-  if (n_pt) {
-    launch_linearize_points(ctx, o, first, radius);
-    const int slots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
-    reduce_pm_partials(ctx, pm_rows(ctx), slots, 4);
-  }
+  const bool sharded = ctx->world > 1;
+  if (n_pt) launch_linearize_points(ctx, o, first, radius);
   if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
-  if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                    (const double*)ctx->part_cm.as<double>(), ctx->d_accA, (const CgState*)nullptr, 0);
+  if (n_cam && sharded) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
+                               (const double*)ctx->part_cm.as<double>(), ctx->d_accA, (const CgState*)nullptr, 0);
   if (with_schur) {
     mark(ctx, PH_SCHUR);
     if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
-                              (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>());
-    if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                      (const double*)ctx->part_cm.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
+                              (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
+    if (n_cam && sharded) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
+                                 (const double*)ctx->part_cm2.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
   }
   if (ctx->world > 1) {     // per-camera sums | cost, |x_p|^2, bad, notpd | per-rank gradient max slots
     LAUNCH(k_gmax_scatter, 1, 32, ctx->rank, ctx->d_scal);
@@ -464,15 +498,8 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
     else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     LAUNCH(k_gmax_gather, 1, 32, ctx->world, ctx->d_scal);
   }
-  if (n_cam) LAUNCH(k_cam_lin_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
-                    (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, ctx->Bc.as<double>(), ctx->gc.as<double>(),
-                    ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal,
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->d_scal);
-  if (with_schur && n_cam)
-    LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->d_accB, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(),
-           1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->partc.as<double>(),
-           ctx->counters.as<unsigned>() + 1, ctx->d_scal);
+  if (n_cam) launch_cam_lin_fin(ctx, o, first);
+  if (with_schur && n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
   ctx->schur_fresh = with_schur;
   mark(ctx, -1);
   return GLBA_OK;
@@ -501,14 +528,13 @@ int do_schur(glba_ctx* ctx, double radius) {
   const int n_cam = ctx->n_cam;
   mark(ctx, PH_SCHUR);
   if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
-                            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>());
-  if (n_cam) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                    (const double*)ctx->part_cm.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
-  if (ctx->world > 1) AR(ctx->d_accB, 27 * (size_t)n_cam, kNcclSum);
-  if (n_cam) LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-                    (const double*)ctx->d_accB, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(),
-                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(),
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 1, ctx->d_scal);
+                            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
+  if (ctx->world > 1) {
+    LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
+           (const double*)ctx->part_cm2.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
+    AR(ctx->d_accB, 27 * (size_t)n_cam, kNcclSum);
+  }
+  if (n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
   ctx->schur_fresh = true;
   mark(ctx, -1);
   return GLBA_OK;
@@ -576,10 +602,10 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
   const int n_cam = ctx->n_cam;
   static bool attr_set = false;
   const size_t sm_schur = (size_t)DN_TP * n_cam * 24 * sizeof(double) + DN_TP * sizeof(unsigned) + 2 * (size_t)(n_cam * (n_cam + 1) / 2) + 16;
-  const size_t sm_solve = ((size_t)36 * n_cam * n_cam + 6 * (size_t)n_cam) * sizeof(double);
+  const size_t sm_solve = ((size_t)(6 * n_cam) * ((6 * n_cam) | 1) + 12 * (size_t)n_cam) * sizeof(double) + 2 * (size_t)(n_cam * (n_cam + 1) / 2) + 16;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 1024)));
-    CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)36 * DN_MAXCAM * DN_MAXCAM + 6 * DN_MAXCAM) * 8)));
+    CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
     attr_set = true;
   }
   const int len = (n_cam * (n_cam + 1) / 2) * 36 + 6 * n_cam;
@@ -591,7 +617,7 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
   LAUNCH(k_dense_reduce, cdiv(len, 256), 256, ctx->dn_grid, len, (const double*)ctx->dn_part.as<double>(), ctx->dn_red.as<double>());
   if (ctx->world > 1) AR(ctx->dn_red.as<double>(), (size_t)len, kNcclSum);
   mark(ctx, PH_SOLVE);
-  k_dense_solve<<<1, DN_NT, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_red.as<double>(),
+  k_dense_solve<<<1, DN_NS, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_red.as<double>(),
       (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius,
       ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->d_scal);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -615,11 +641,7 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
                     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
                     ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal);
-  if (n_pt) {
-    launch_point_pass1(ctx, o, radius);
-    const int slots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
-    reduce_pm_partials(ctx, pm_rows(ctx), slots, -1);
-  }
+  if (n_pt) launch_point_pass1(ctx, o, radius);
   if (ctx->world > 1) AR(ctx->d_scal + S_COST_C, 5, kNcclSum);
   mark(ctx, -1);
   CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
@@ -636,7 +658,10 @@ int fetch_scal(glba_ctx* ctx) {
 }
 
 // The trust-region loop (Ceres TrustRegionMinimizer semantics; see oracle/glba_oracle.cpp for the
-// statement-by-statement restatement this mirrors).
+// statement-by-statement restatement this mirrors).  One host synchronisation per LM iteration: the scalars of the
+// re-linearisation that follows an accepted step (cost, |g|_inf, |x|) are read together with the NEXT step's
+// scalars; the loop-top tests that need them are applied retroactively (a step computed past a gradient-tolerance
+// stop is simply discarded), which is observationally identical to Ceres' order of tests.
 int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   int st;
   for (int q = 0; q < PH_COUNT; ++q) if (q != PH_SETUP) ctx->t_phase[q] = 0.0;
@@ -659,12 +684,18 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   double x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
   sum->initial_cost = cost; sum->cost[0] = cost; sum->cost_candidate[0] = cost; sum->radius[0] = radius; sum->gradient_max_norm[0] = gmax;
   int it = 0;
-  bool fresh = true;   // point blocks are damped for the current radius
-  // number of free parameters: free cameras + free points (host knows cameras; points: any observation => >0)
-  if (ctx->n_obs == 0) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
+  bool fresh = true;        // point blocks are damped for the current radius
+  bool pending = false;     // a re-linearisation was enqueued whose scalars have not been read yet
+  auto absorb_pending = [&]() {          // returns false on a non-finite re-linearisation
+    pending = false;
+    if (S[S_BAD] > 0.0 || !std::isfinite(S[S_COST])) return false;
+    cost = S[S_COST]; gmax = std::max(S[S_GMAX_P], S[S_GMAX_C]); x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
+    return true;
+  };
+  if (ctx->n_obs == 0 && ctx->world == 1) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
   else for (;;) {
     if (it >= o->max_iters) { sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_MAX_ITERS; break; }
-    if (gmax <= o->gradient_tol) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
+    if (!pending && gmax <= o->gradient_tol) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
     if (radius <= o->min_radius) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_MIN_RADIUS; break; }
     ++it;
     if (!fresh) { if ((st = do_redamp(ctx, radius))) return st; ctx->schur_fresh = false; }
@@ -678,6 +709,12 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     }
     sum->cg_iters[it] = cg_it;
     if ((st = do_step(ctx, o, radius))) return st;
+    if (pending) {
+      // scalars of the linearisation that followed the previous accepted step arrived with this read-back
+      if (!absorb_pending()) { --it; sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; break; }
+      sum->cost[it - 1] = cost; sum->gradient_max_norm[it - 1] = gmax;
+      if (gmax <= o->gradient_tol) { --it; sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
+    }
     const bool solver_ok = (S[S_NOTPD_P] + (ctx->n_free_cam > 0 ? S[S_NOTPD_C] : 0.0)) == 0.0;
     const double model_cost_change = 0.5 * ((S[S_YG_P] + S[S_YG_C]) + (S[S_YLY_P] + S[S_YLY_C]));
     const bool valid = solver_ok && (model_cost_change > 0.0);
@@ -706,10 +743,9 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
       radius = std::min(o->max_radius, radius);
       decrease_factor = 2.0;
-      if ((st = do_linearize_impl(ctx, o, 0, radius, !dense))) return st;
-      if ((st = fetch_scal(ctx))) return st;
-      if (S[S_BAD] > 0.0 || !std::isfinite(S[S_COST])) { sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; break; }
-      cost = S[S_COST]; gmax = std::max(S[S_GMAX_P], S[S_GMAX_C]); x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
+      if ((st = do_linearize_impl(ctx, o, 0, radius, !dense))) return st;    // enqueued only: read back with the next step
+      pending = true;
+      cost = cand;       // provisional (the re-evaluated value replaces it at the next read-back)
       sum->n_linearizations++; sum->n_successful++; sum->accepted[it] = 1;
       fresh = true;
     } else {
@@ -717,6 +753,11 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
       sum->accepted[it] = 0;
     }
     sum->cost[it] = cost; sum->radius[it] = radius; sum->gradient_max_norm[it] = gmax;
+  }
+  if (pending) {           // the loop ended right after an accepted step: fetch the scalars of its re-linearisation
+    if ((st = fetch_scal(ctx))) return st;
+    if (!absorb_pending()) { sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; }
+    else { sum->cost[it] = cost; sum->gradient_max_norm[it] = gmax; }
   }
   sum->n_iters = it; sum->final_cost = cost;
   sum->t_setup_ms = ctx->t_phase[PH_SETUP]; sum->t_linearize_ms = ctx->t_phase[PH_LIN]; sum->t_schur_ms = ctx->t_phase[PH_SCHUR];
@@ -832,7 +873,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -940,21 +981,10 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   if ((st = timed([&] { launch_point_pass1(ctx, opt, radius); }, &out->backsub_cost_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_point_damp, cdiv(n_pt, NT_PM), NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
            (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms))) return st;
-  // every camera-sized / reduction kernel of one linearise + Schur pass
+  // every camera-sized kernel of one linearise + Schur pass (the scalar reductions now run inside the tile kernels)
   st = timed([&] {
-    const int slots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
-    reduce_pm_partials(ctx, pm_rows(ctx), slots, 4);
-    for (int rep2 = 0; rep2 < 2; ++rep2)
-      LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
-             ctx->d_accB, (const CgState*)nullptr, 0);
-    LAUNCH(k_cam_lin_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
-           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(),
-           ctx->lamc.as<double>(), 0, opt->jacobi_scaling, opt->min_lm_diagonal, opt->max_lm_diagonal, ctx->partc.as<double>(),
-           ctx->counters.as<unsigned>() + 0, ctx->d_scal);
-    LAUNCH(k_cam_schur_fin, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->d_accB, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(),
-           1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 1,
-           ctx->d_scal); }, &out->small_kernels_ms);
+    launch_cam_lin_fin(ctx, opt, 0);
+    launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>()); }, &out->small_kernels_ms);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return st;
 }

@@ -142,10 +142,28 @@ __device__ __forceinline__ bool finish_scalars(const double (&v)[NV], const bool
   return s_last;     // true in every thread of the last CTA; its thread 0 has the totals in smo[]
 }
 
+// per-camera 27 partial sums: either already summed (acc27, sharded runs: all-reduced) or summed here from the chunk
+// partials in chunk order (single GPU: one launch less)
+template <bool FUSE>
+__device__ __forceinline__ void load_acc27(const int i, const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start,
+                                           const double* __restrict__ part27, double* a) {
+  if (FUSE) {
+#pragma unroll
+    for (int q = 0; q < 27; ++q) a[q] = 0.0;
+    for (int ch = cam_chunk_start[i]; ch < cam_chunk_start[i + 1]; ++ch)
+#pragma unroll
+      for (int q = 0; q < 27; ++q) a[q] += part27[(size_t)27 * ch + q];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 27; ++q) a[q] = acc27[(size_t)27 * i + q];
+  }
+}
+
 // B_i = T' A T, g_i = T' ghat; Jacobi scale (iteration 0); lam_c = clamp(s^2 h)/s^2; |x_c|^2, max |g_c|.
+template <bool FUSE>
 __global__ void __launch_bounds__(NT_C)
 k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
-              const double* __restrict__ acc27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
+              const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start, const double* __restrict__ part27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
               double* __restrict__ lamc, const int first, const int jacobi, const double min_diag, const double max_diag,
               double* part, unsigned* counter, double* scal) {
   __shared__ double sm[2 * NT_C / 32];
@@ -160,7 +178,8 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
 #pragma unroll
       for (int q = 0; q < 6; ++q) { gc[6 * i + q] = 0.0; lamc[6 * i + q] = 0.0; if (first) sc[6 * i + q] = 1.0; }
     } else {
-      const double* a = acc27 + (size_t)27 * i;
+      double a[27];
+      load_acc27<FUSE>(i, acc27, cam_chunk_start, part27, a);
       const double* ct = camtab + (size_t)CAMTAB * i;
       double G[9], R[9], Bl[36], gh[6], g6[6];
 #pragma unroll
@@ -191,8 +210,10 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
 }
 
 // M_i = B_i + lam/radius - T' Mhat T (diagonal block of S), rhs_i = g_i - T' rhat, Minv_i.
+template <bool FUSE>
 __global__ void __launch_bounds__(NT_C)
 k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ acc27,
+                const int* __restrict__ cam_chunk_start, const double* __restrict__ part27,
                 const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
                 double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal) {
   __shared__ double sm[NT_C / 32];
@@ -207,7 +228,8 @@ k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const dou
 #pragma unroll
       for (int q = 0; q < 6; ++q) rhs[6 * i + q] = 0.0;
     } else {
-      const double* a = acc27 + (size_t)27 * i;
+      double a[27];
+      load_acc27<FUSE>(i, acc27, cam_chunk_start, part27, a);
       const double* ct = camtab + (size_t)CAMTAB * i;
       double G[9], R[9], Ml[36], Il[36], rh[6], r6[6];
 #pragma unroll

@@ -150,26 +150,36 @@ __global__ void k_dense_reduce(const int n_parts, const int len, const double* _
   out[t] = s;
 }
 
-// One CTA: assemble S (n = 6 n_cam) in shared memory, Cholesky, solve S y = rhs.  Non-free cameras
-// become identity rows with zero rhs.  Outputs y (cg_x layout), the diagonal blocks and rhs.
-__global__ void __launch_bounds__(DN_NT)
+// One CTA: assemble S (n = 6 n_cam <= 96) in shared memory, Cholesky, solve S y = rhs.  Non-free cameras become
+// identity rows with zero rhs.  Thread r owns ROW r: left-looking factorisation where every thread recomputes the
+// pivot of column j itself, so each column (and each substitution step) costs exactly one barrier.
+// Row stride is odd (no shared-memory bank conflicts between rows).  Outputs y (cg_x layout), diagonal blocks, rhs.
+constexpr int DN_NS = 128;   // threads of the solve kernel (>= 6*DN_MAXCAM)
+__global__ void __launch_bounds__(DN_NS)
 k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ Sred /* pairs*36 + 6 n_cam */,
               const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
               double* __restrict__ y, double* __restrict__ Md, double* __restrict__ rhs_out, double* __restrict__ scal) {
   extern __shared__ double dsm[];
   const int n = 6 * n_cam;
+  const int ld = n | 1;
   const int n_pairs = n_cam * (n_cam + 1) / 2;
-  double* S = dsm;            // n x n, row-major, lower triangle is what the factorisation reads
-  double* b = S + (size_t)n * n;
+  double* S = dsm;                       // n x ld, lower triangle is what the factorisation reads
+  double* ys = S + (size_t)n * ld;       // n
+  double* dg = ys + n;                   // n: the original diagonal (S[j][j] itself is overwritten by thread j while others still need it)
+  unsigned char* pair_i = reinterpret_cast<unsigned char*>(dg + n);
+  unsigned char* pair_k = pair_i + n_pairs;
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   if (tid == 0) s_bad = 0;
-  // assemble
-  for (int t = tid; t < n_pairs * 36; t += DN_NT) {
-    const int pr = t / 36, ent = t - pr * 36;
-    int i = 0, rem = pr;
+  for (int p = tid; p < n_pairs; p += DN_NS) {
+    int i = 0, rem = p;
     while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
-    const int k = i + rem;
+    pair_i[p] = (unsigned char)i; pair_k[p] = (unsigned char)(i + rem);
+  }
+  __syncthreads();
+  for (int t = tid; t < n_pairs * 36; t += DN_NS) {
+    const int pr = t / 36, ent = t - pr * 36;
+    const int i = pair_i[pr], k = pair_k[pr];
     const int rr = ent / 6, cc = ent - rr * 6;
     double v = -Sred[t];
     const bool fi = cam_free[i] != 0, fk = cam_free[k] != 0;
@@ -177,54 +187,50 @@ k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
       if (fi) { v += Bc[(size_t)36 * i + rr * 6 + cc]; if (rr == cc) v += lamc[6 * i + rr] * inv_radius; }
       else v = (rr == cc) ? 1.0 : 0.0;
     } else if (!fi || !fk) v = 0.0;
-    S[(size_t)(6 * i + rr) * n + 6 * k + cc] = v;
-    S[(size_t)(6 * k + cc) * n + 6 * i + rr] = v;
+    S[(size_t)(6 * i + rr) * ld + 6 * k + cc] = v;
+    S[(size_t)(6 * k + cc) * ld + 6 * i + rr] = v;
   }
-  for (int t = tid; t < n; t += DN_NT) {
-    const int i = t / 6;
-    b[t] = cam_free[i] ? gc[t] - Sred[(size_t)n_pairs * 36 + t] : 0.0;
+  const int r = tid;
+  double b = 0.0;
+  if (r < n) {
+    b = cam_free[r / 6] ? gc[r] - Sred[(size_t)n_pairs * 36 + r] : 0.0;
+    rhs_out[r] = b;
   }
   __syncthreads();
-  for (int t = tid; t < n_cam * 36; t += DN_NT) {
+  for (int t = tid; t < n_cam * 36; t += DN_NS) {
     const int i = t / 36, ent = t - i * 36, rr = ent / 6, cc = ent - rr * 6;
-    Md[t] = cam_free[i] ? S[(size_t)(6 * i + rr) * n + 6 * i + cc] : 0.0;
+    Md[t] = cam_free[i] ? S[(size_t)(6 * i + rr) * ld + 6 * i + cc] : 0.0;
   }
-  for (int t = tid; t < n; t += DN_NT) rhs_out[t] = b[t];
+  if (r < n) dg[r] = S[(size_t)r * ld + r];
   __syncthreads();
-  // right-looking Cholesky on the lower triangle
+  // left-looking Cholesky
   for (int j = 0; j < n; ++j) {
-    if (tid == 0) {
-      const double d = S[(size_t)j * n + j];
-      if (!(d > 0.0)) { s_bad = 1; S[(size_t)j * n + j] = 1.0; } else S[(size_t)j * n + j] = sqrt(d);
-    }
-    __syncthreads();
-    const double inv = 1.0 / S[(size_t)j * n + j];
-    for (int r = j + 1 + tid; r < n; r += DN_NT) S[(size_t)r * n + j] *= inv;
-    __syncthreads();
-    const int m = n - j - 1;           // trailing (r,c), r >= c > j
-    for (int t = tid; t < m * m; t += DN_NT) {
-      const int r = j + 1 + t / m, c = j + 1 + t % m;
-      if (c <= r) S[(size_t)r * n + c] -= S[(size_t)r * n + j] * S[(size_t)c * n + j];
+    if (r >= j && r < n) {
+      const double* Sr = S + (size_t)r * ld;
+      const double* Sj = S + (size_t)j * ld;
+      double s = Sr[j], d = dg[j];
+      for (int k = 0; k < j; ++k) { const double ljk = Sj[k]; s -= Sr[k] * ljk; d -= ljk * ljk; }
+      if (!(d > 0.0)) { d = 1.0; if (r == j) s_bad = 1; }
+      const double ljj = sqrt(d);
+      S[(size_t)r * ld + j] = (r == j) ? ljj : s / ljj;
     }
     __syncthreads();
   }
-  // L z = b
+  // L z = b   (thread r carries b_r)
   for (int j = 0; j < n; ++j) {
-    if (tid == 0) b[j] /= S[(size_t)j * n + j];
+    if (r == j) ys[j] = b / S[(size_t)j * ld + j];
     __syncthreads();
-    const double zj = b[j];
-    for (int r = j + 1 + tid; r < n; r += DN_NT) b[r] -= S[(size_t)r * n + j] * zj;
-    __syncthreads();
+    if (r > j && r < n) b -= S[(size_t)r * ld + j] * ys[j];
   }
+  if (r < n) b = ys[r];
+  __syncthreads();
   // L' y = z
   for (int j = n - 1; j >= 0; --j) {
-    if (tid == 0) b[j] /= S[(size_t)j * n + j];
+    if (r == j) ys[j] = b / S[(size_t)j * ld + j];
     __syncthreads();
-    const double yj = b[j];
-    for (int r = tid; r < j; r += DN_NT) b[r] -= S[(size_t)j * n + r] * yj;
-    __syncthreads();
+    if (r < j) b -= S[(size_t)j * ld + r] * ys[j];
   }
-  for (int t = tid; t < n; t += DN_NT) y[t] = cam_free[t / 6] ? b[t] : 0.0;
+  if (r < n) y[r] = cam_free[r / 6] ? ys[r] : 0.0;
   if (tid == 0) scal[S_NOTPD_C] = s_bad ? 1.0 : 0.0;
 }
 

@@ -68,8 +68,8 @@ constexpr int XTAB = 16;   // per-camera gather row of the point passes (128 B):
 // sm_100 256-bit global accesses (SASS LDG.E.ENL2.256 / STG.E.ENL2.256): one instruction, one L1 wavefront
 // per 32-byte record.  Every record / table row here is 32-byte aligned.
 __device__ __forceinline__ double4 ldg4(const double4* p) {           // read-only (non-coherent) path
-  double4 r;
-  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  double4 r;      // not volatile, no memory clobber: read-only data, the compiler may hoist / batch these freely
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ double4 ld4(const double4* p) {            // coherent (data written by this kernel)
@@ -78,7 +78,8 @@ __device__ __forceinline__ double4 ld4(const double4* p) {            // coheren
   return r;
 }
 __device__ __forceinline__ void st4(double4* p, const double4 v) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+  // volatile (has no outputs) but no memory clobber: records are write-only here, later loads may pass the store
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w));
 }
 // first 96 bytes of a camera-table row: R (row-major) and the centre, as three 256-bit gathers
 __device__ __forceinline__ void load_Rc(const double* __restrict__ ct, double* R /*9*/, double* c /*3*/) {
@@ -139,6 +140,26 @@ __device__ __forceinline__ void jhat_rows(const double4 rec, const double sv0, c
   const double pfx = wfx * iz, pfy = wfy * iz;
   a[3] = -pfx; a[4] = 0.0; a[5] = pfx * xh;
   b[3] = 0.0; b[4] = -pfy; b[5] = pfy * yh;
+}
+
+// J^ has two structural zeros (a[4] = b[3] = 0: a pixel row does not see the other axis' translation).  The camera-major
+// kernels are FP64-pipe co-limited (ncu: 46 % pipe at 37 % DRAM), so the symmetric updates below skip those terms:
+//   acc(r,c) += x_r a_c + y_r b_c   with (x,y) = (a,b) for J^'J^  or (E a-ish, E b-ish) for J^' E J^
+// 31/30 FMAs instead of 42.  Upper-triangular packing order as tri(r,c).
+__device__ __forceinline__ void acc_sym_sparse(double* acc, const double* x, const double* y, const double* a, const double* b) {
+  acc[0] += x[0] * a[0] + y[0] * b[0];  acc[1] += x[0] * a[1] + y[0] * b[1];  acc[2] += x[0] * a[2] + y[0] * b[2];
+  acc[3] += x[0] * a[3];                acc[4] += y[0] * b[4];                acc[5] += x[0] * a[5] + y[0] * b[5];
+  acc[6] += x[1] * a[1] + y[1] * b[1];  acc[7] += x[1] * a[2] + y[1] * b[2];  acc[8] += x[1] * a[3];
+  acc[9] += y[1] * b[4];                acc[10] += x[1] * a[5] + y[1] * b[5];
+  acc[11] += x[2] * a[2] + y[2] * b[2]; acc[12] += x[2] * a[3];               acc[13] += y[2] * b[4];
+  acc[14] += x[2] * a[5] + y[2] * b[5];
+  acc[15] += x[3] * a[3];               acc[16] += y[3] * b[4];               acc[17] += x[5] * a[3];   // (3,5) taken as (5,3)
+  acc[18] += y[4] * b[4];               acc[19] += y[5] * b[4];                                           // (4,5) taken as (5,4)
+  acc[20] += x[5] * a[5] + y[5] * b[5];
+}
+__device__ __forceinline__ void acc_vec_sparse(double* acc, const double* a, const double* b, const double f0, const double f1) {
+  acc[0] += a[0] * f0 + b[0] * f1; acc[1] += a[1] * f0 + b[1] * f1; acc[2] += a[2] * f0 + b[2] * f1;
+  acc[3] += a[3] * f0;             acc[4] += b[4] * f1;             acc[5] += a[5] * f0 + b[5] * f1;
 }
 
 // Rows of J~_p = w P R (2x3) from a record and R (row-major 3x3).
@@ -469,13 +490,8 @@ k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double*
       jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
       const double r0 = rec.w * (A.K.fx * rec.x + A.K.cx - uv.x);
       const double r1 = rec.w * (A.K.fy * rec.y + A.K.cy - uv.y);
-      int q = 0;
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = r; c < 6; ++c) acc[q++] += a[r] * a[c] + bb[r] * bb[c];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) acc[21 + r] += a[r] * r0 + bb[r] * r1;
+      acc_sym_sparse(acc, a, bb, a, bb);
+      acc_vec_sparse(acc + 21, a, bb, r0, r1);
     }
   }
   block_reduce<27, NT_CM>(acc, sm, smo);
@@ -525,14 +541,12 @@ k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __r
       // J^' E J^ = (E00 a + E01 b) a' + (E01 a + E11 b) b'
       double ea[6], eb[6];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) { ea[r] = E00 * a[r] + E01 * bb[r]; eb[r] = E01 * a[r] + E11 * bb[r]; }
-      int q = 0;
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = r; c < 6; ++c) acc[q++] += ea[r] * a[c] + eb[r] * bb[c];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) acc[21 + r] += a[r] * f0 + bb[r] * f1;
+      for (int r = 0; r < 3; ++r) { ea[r] = E00 * a[r] + E01 * bb[r]; eb[r] = E01 * a[r] + E11 * bb[r]; }
+      ea[3] = E00 * a[3]; eb[3] = E01 * a[3];
+      ea[4] = E01 * bb[4]; eb[4] = E11 * bb[4];
+      ea[5] = E00 * a[5] + E01 * bb[5]; eb[5] = E01 * a[5] + E11 * bb[5];
+      acc_sym_sparse(acc, ea, eb, a, bb);
+      acc_vec_sparse(acc + 21, a, bb, f0, f1);
     }
   }
   block_reduce<27, NT_CM>(acc, sm, smo);
@@ -566,8 +580,7 @@ k_spmv_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __re
       const double f1 = bp[0] * u.x + bp[1] * u.y + bp[2] * u.z;
       double a[6], bb[6];
       jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
-#pragma unroll
-      for (int r = 0; r < 6; ++r) acc[r] += a[r] * f0 + bb[r] * f1;
+      acc_vec_sparse(acc, a, bb, f0, f1);
     }
   }
   block_reduce<6, NT_CM>(acc, sm, smo);

@@ -20,17 +20,51 @@ constexpr int NT_T = 256;
 constexpr int OPT = GLBA_OPT;            // observations per thread in phase 1
 constexpr int TILE_OBS = NT_T * OPT;     // tile capacity; ~TILE_OBS/track_len points keep phase 2 busy
 
+// The last CTA to finish folds the per-CTA partial rows [rows][5] into the scalar slots, in row order (fixed).
+// MAXCOL = column reduced with max (-1: none).  Saves a separate single-CTA reduction launch per pass.
+template <int MAXCOL>
+__device__ __forceinline__ void last_block_reduce5(const double* part, const int rows, const int* slots, unsigned* counter,
+                                                   double* __restrict__ scal, double* sm /* 5*NT_T/32 */, double* smo /* 5 */) {
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicInc(counter, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double mx[1] = {0.0};
+#pragma unroll 4
+  for (int r = threadIdx.x; r < rows; r += NT_T) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const double x = __ldcg(part + (size_t)5 * r + q);
+      if (q == MAXCOL) mx[0] = fmax(mx[0], x); else acc[q] += x;
+    }
+  }
+  block_reduce<5, NT_T>(acc, sm, smo);
+  if (threadIdx.x < 5 && (int)threadIdx.x != MAXCOL) scal[slots[threadIdx.x]] = smo[threadIdx.x];
+  if (MAXCOL >= 0) {
+    __syncthreads();
+    block_reduce<1, NT_T, true>(mx, sm, smo);
+    if (threadIdx.x == 0) scal[slots[MAXCOL]] = smo[0];
+  }
+}
+struct RedArgs { unsigned* counter; double* scal; int slots[5]; };
+
 struct TileArgs {
   const int* tile_pt;      // [n_tiles+1] first point of every tile
   const int* pm_pt;        // point of observation k (point-major order)
 };
 
 // K_A + point half of K_B, tiled.  Same outputs as k_linearize_pm.
-__global__ void __launch_bounds__(NT_T)
+__global__ void __launch_bounds__(NT_T, 3)
 k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ pt, const double* __restrict__ camtab,
                  double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
                  double4* __restrict__ lam4, double* __restrict__ pblk, const int first, const int jacobi, const double min_diag,
-                 const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */) {
+                 const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   extern __shared__ double dsm[];
   double (*val)[TILE_OBS] = reinterpret_cast<double (*)[TILE_OBS]>(dsm);     // [9][TILE_OBS]
   __shared__ double sm[4 * NT_T / 32];
@@ -41,17 +75,28 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
   const int j0 = T.tile_pt[blockIdx.x], j1 = T.tile_pt[blockIdx.x + 1];
   const int k0 = A.pt_start[j0], k1 = A.pt_start[j1];
   double cost = 0.0, bad = 0.0;
+  // stage 1: every first-level load of the thread's OPT observations is issued before anything is consumed,
+  // so one DRAM round trip covers OPT observations (indices clamped into the tile: no divergence, no OOB)
+  int ci[OPT], pj[OPT], cm[OPT];
+  double2 uvs[OPT];
+  const int klast = max(k1 - 1, k0);
+#pragma unroll
+  for (int m = 0; m < OPT; ++m) {
+    const int kc = min(k0 + m * NT_T + tid, klast);
+    ci[m] = __ldg(A.pm_cam + kc);
+    pj[m] = __ldg(T.pm_pt + kc);
+    cm[m] = __ldg(A.pm2cm + kc);
+    uvs[m] = __ldg(A.pm_uv + kc);
+  }
 #pragma unroll
   for (int m = 0; m < OPT; ++m) {
     const int l = m * NT_T + tid;
     const int k = k0 + l;
     if (k < k1) {
-      const int i = __ldg(A.pm_cam + k);
-      const int j = __ldg(T.pm_pt + k);
-      const double2 uv = __ldg(A.pm_uv + k);
-      const double4 X = ldg4(pt + j);
+      const double2 uv = uvs[m];
+      const double4 X = ldg4(pt + pj[m]);
       double R[9], cc[3];
-      load_Rc(camtab + (size_t)CAMTAB * i, R, cc);
+      load_Rc(camtab + (size_t)CAMTAB * ci[m], R, cc);
       const double qx = X.x - cc[0], qy = X.y - cc[1], qz = X.z - cc[2];
       const double px = R[0] * qx + R[1] * qy + R[2] * qz;
       const double py = R[3] * qx + R[4] * qy + R[5] * qz;
@@ -65,7 +110,7 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
       cost += 0.5 * rho;
       const double4 rec = make_double4(xh, yh, iz, w);
       st4(rec_pm + k, rec);
-      st4(rec_cm + __ldg(A.pm2cm + k), rec);
+      st4(rec_cm + cm[m], rec);
       double ap[3], bp[3];
       jp_rows(rec, R, A.K, ap, bp);
       const double r0 = w * rx, r1 = w * ry;
@@ -129,6 +174,9 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
     double* p = part + (size_t)5 * blockIdx.x;
     p[0] = smo[0]; p[1] = smo[1]; p[2] = smo[2]; p[3] = smo[3]; p[4] = smmo[0];
   }
+  __shared__ double rsm[5 * NT_T / 32];
+  __shared__ double rsmo[5];
+  last_block_reduce5<4>(part, gridDim.x, RA.slots, RA.counter, RA.scal, rsm, rsmo);
 }
 
 // Point-major half of the implicit product (MODE 0) / back-substitution + candidate cost (MODE 1), tiled.
@@ -140,7 +188,7 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
              const double* __restrict__ pblk, double4* __restrict__ u4, const CgState* __restrict__ cg, const int li,
              // MODE 1 only:
              const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
-             const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */) {
+             const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   __shared__ double val[3][TILE_OBS];
   if (MODE == 0 && cg && cg->done_at <= li) return;
   const int tid = threadIdx.x;
@@ -230,6 +278,8 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
     double v[5] = {cost_c, yn2, yg, yly, bad};
     block_reduce<5, NT_T>(v, sm, smo);
     if (tid < 5) part[(size_t)5 * blockIdx.x + tid] = smo[tid];
+    __syncthreads();
+    last_block_reduce5<-1>(part, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo);
   }
 }
 
