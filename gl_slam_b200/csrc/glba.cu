@@ -91,7 +91,7 @@ struct glba_ctx {
   bool schur_fresh = false;                      // Schur pieces already built for the current linearisation and radius
   double* d_scal = nullptr;   // NSCAL doubles at the tail of acc27 (one all-reduce carries camera sums + scalars)
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
-  Buf tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2;                                  // tiles, PCG gather table, camera-kernel partials
+  Buf tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
   int n_tiles = 0, max_track = 0, grid_c = 0;
   Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
@@ -343,7 +343,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->pblk, (size_t)PBLK * n_pt); ENSURE(double4, ctx->u4, n_pt);
   ENSURE(double, ctx->part_pm, 5 * (size_t)std::max(std::max(grid_pm, ctx->n_tiles), 1));
   ENSURE(double, ctx->xtab, (size_t)XTAB * n_cam); ENSURE(double, ctx->partA, ctx->grid_c); ENSURE(double, ctx->partB, ctx->grid_c);
-  ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8);
+  ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8); ENSURE(double, ctx->part_pm2, 5 * 64);
   CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned), s));
   ctx->timing = (n >= 200000); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1)); ENSURE(double, ctx->part_cm2, 27 * (size_t)std::max(ctx->n_chunks, 1));
   ENSURE(double, ctx->acc27, 54 * (size_t)n_cam + NSCAL);     // [Schur sums 27C | Hessian sums 27C | scalars]: contiguous for one all-reduce
@@ -390,8 +390,9 @@ int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
   return GLBA_OK;
 }
 
-RedArgs red_args(glba_ctx* ctx, int counter, const int* slots) {
-  RedArgs R; R.counter = ctx->counters.as<unsigned>() + counter; R.scal = ctx->d_scal;
+constexpr int kInKernelReduceMaxTiles = 256;   // above this the per-tile partials are folded by k_reduce_rows (64 CTAs)
+RedArgs red_args(glba_ctx* ctx, int counter, const int* slots, bool in_kernel = true) {
+  RedArgs R; R.counter = in_kernel ? ctx->counters.as<unsigned>() + counter : nullptr; R.scal = ctx->d_scal;
   for (int q = 0; q < 5; ++q) R.slots[q] = slots[q];
   return R;
 }
@@ -408,8 +409,10 @@ void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, do
     k_linearize_tile<<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
            ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
-           o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots));
+           o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles));
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (ctx->n_tiles > kInKernelReduceMaxTiles)
+      LAUNCH(k_reduce_rows<4>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 4, kLinSlots));
   } else {
     LAUNCH(k_linearize_pm, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
@@ -436,13 +439,15 @@ void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg,
 
 void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
   const int c = ctx->cur, d = c ^ 1;
-  if (ctx->use_tiles)
+  if (ctx->use_tiles) {
     LAUNCH(k_point_tile<1>, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr, 0,
            (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
            (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(),
-           red_args(ctx, 5, kStepSlots));
-  else {
+           red_args(ctx, 5, kStepSlots, ctx->n_tiles <= kInKernelReduceMaxTiles));
+    if (ctx->n_tiles > kInKernelReduceMaxTiles)
+      LAUNCH(k_reduce_rows<-1>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 5, kStepSlots));
+  } else {
     LAUNCH(k_point_pass<1>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
            (double4*)nullptr, (const CgState*)nullptr, 0, (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(),
@@ -873,7 +878,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);

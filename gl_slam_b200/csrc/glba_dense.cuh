@@ -201,35 +201,127 @@ k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
     const int i = t / 36, ent = t - i * 36, rr = ent / 6, cc = ent - rr * 6;
     Md[t] = cam_free[i] ? S[(size_t)(6 * i + rr) * ld + 6 * i + cc] : 0.0;
   }
-  if (r < n) dg[r] = S[(size_t)r * ld + r];
-  __syncthreads();
-  // left-looking Cholesky
-  for (int j = 0; j < n; ++j) {
-    if (r >= j && r < n) {
+  // ---- blocked (6x6 = one camera) left-looking Cholesky: per block column two barriers; every thread carries six
+  //      independent FMA chains, and factors the 6x6 pivot block redundantly in registers (no serial owner thread)
+  for (int J = 0; J < n_cam; ++J) {
+    const int c0 = 6 * J;
+    const bool act = (r >= c0 && r < n);
+    double t[6];
+    if (act) {
       const double* Sr = S + (size_t)r * ld;
-      const double* Sj = S + (size_t)j * ld;
-      double s = Sr[j], d = dg[j];
-      for (int k = 0; k < j; ++k) { const double ljk = Sj[k]; s -= Sr[k] * ljk; d -= ljk * ljk; }
-      if (!(d > 0.0)) { d = 1.0; if (r == j) s_bad = 1; }
-      const double ljj = sqrt(d);
-      S[(size_t)r * ld + j] = (r == j) ? ljj : s / ljj;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) t[q] = Sr[c0 + q];
+      for (int k = 0; k < c0; ++k) {
+        const double lrk = Sr[k];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) t[q] -= lrk * S[(size_t)(c0 + q) * ld + k];
+      }
+      double* Sw = S + (size_t)r * ld;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) Sw[c0 + q] = t[q];
+    }
+    __syncthreads();
+    if (act) {
+      double Lb[21], id[6];     // pivot block factor (lower, packed a(a+1)/2+b) and inverse diagonal
+#pragma unroll
+      for (int a2 = 0; a2 < 6; ++a2)
+#pragma unroll
+        for (int b2 = 0; b2 <= a2; ++b2) Lb[a2 * (a2 + 1) / 2 + b2] = S[(size_t)(c0 + a2) * ld + c0 + b2];
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        double d = Lb[j * (j + 1) / 2 + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= Lb[j * (j + 1) / 2 + k] * Lb[j * (j + 1) / 2 + k];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        const double ljj = sqrt(d);
+        const double inv = 1.0 / ljj;
+        Lb[j * (j + 1) / 2 + j] = ljj; id[j] = inv;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+          double v = Lb[i * (i + 1) / 2 + j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) v -= Lb[i * (i + 1) / 2 + k] * Lb[j * (j + 1) / 2 + k];
+          Lb[i * (i + 1) / 2 + j] = v * inv;
+        }
+      }
+      if (bad && r == c0) s_bad = 1;
+      double* Sw = S + (size_t)r * ld;
+      if (r < c0 + 6) {
+        const int a2 = r - c0;   // static indexing only (keeps Lb / id in registers)
+#pragma unroll
+        for (int a3 = 0; a3 < 6; ++a3)
+          if (a3 == a2) {
+#pragma unroll
+            for (int b2 = 0; b2 <= a3; ++b2) Sw[c0 + b2] = Lb[a3 * (a3 + 1) / 2 + b2];
+            dg[r] = id[a3];     // dg now holds 1/L[r][r]
+          }
+      } else {
+        // x Lb' = t  (row of the block column below the pivot block)
+        double x[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          double v = t[q];
+#pragma unroll
+          for (int p2 = 0; p2 < q; ++p2) v -= x[p2] * Lb[q * (q + 1) / 2 + p2];
+          x[q] = v * id[q];
+          Sw[c0 + q] = x[q];
+        }
+      }
     }
     __syncthreads();
   }
-  // L z = b   (thread r carries b_r)
-  for (int j = 0; j < n; ++j) {
-    if (r == j) ys[j] = b / S[(size_t)j * ld + j];
+  // ---- L z = b, blocked: thread r carries b_r; the six pivot rows publish their entries, everyone solves the 6x6
+  for (int J = 0; J < n_cam; ++J) {
+    const int c0 = 6 * J;
+    if (r >= c0 && r < c0 + 6) ys[r] = b;
     __syncthreads();
-    if (r > j && r < n) b -= S[(size_t)r * ld + j] * ys[j];
+    if (r >= c0 && r < n) {
+      double z[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double v = ys[c0 + q];
+#pragma unroll
+        for (int p2 = 0; p2 < q; ++p2) v -= S[(size_t)(c0 + q) * ld + c0 + p2] * z[p2];
+        z[q] = v * dg[c0 + q];
+      }
+      if (r < c0 + 6) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (q == r - c0) b = z[q];
+      } else {
+        const double* Sr = S + (size_t)r * ld;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) b -= Sr[c0 + q] * z[q];
+      }
+    }
+    __syncthreads();      // ys[c0..] is rewritten by nobody, but keeps the reads of block J ahead of block J+1's publishes
   }
-  if (r < n) b = ys[r];
+  // ---- L' y = z, blocked, bottom-up
+  for (int J = n_cam - 1; J >= 0; --J) {
+    const int c0 = 6 * J;
+    if (r >= c0 && r < c0 + 6) ys[r] = b;
+    __syncthreads();
+    if (r < c0 + 6 && r < n) {
+      double yb[6];
+#pragma unroll
+      for (int q = 5; q >= 0; --q) {
+        double v = ys[c0 + q];
+#pragma unroll
+        for (int p2 = 5; p2 > q; --p2) v -= S[(size_t)(c0 + p2) * ld + c0 + q] * yb[p2];
+        yb[q] = v * dg[c0 + q];
+      }
+      if (r >= c0) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (q == r - c0) b = yb[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) b -= S[(size_t)(c0 + q) * ld + r] * yb[q];
+      }
+    }
+    __syncthreads();
+  }
+  if (r < n) ys[r] = b;
   __syncthreads();
-  // L' y = z
-  for (int j = n - 1; j >= 0; --j) {
-    if (r == j) ys[j] = b / S[(size_t)j * ld + j];
-    __syncthreads();
-    if (r < j) b -= S[(size_t)j * ld + r] * ys[j];
-  }
   if (r < n) y[r] = cam_free[r / 6] ? ys[r] : 0.0;
   if (tid == 0) scal[S_NOTPD_C] = s_bad ? 1.0 : 0.0;
 }

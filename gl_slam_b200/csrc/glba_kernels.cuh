@@ -483,15 +483,30 @@ k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double*
     const double* ct = camtab + (size_t)CAMTAB * cam;
     const double sv0 = ct[21], sv1 = ct[22], sv2 = ct[23];
     const int b = A.chunk_begin[ch], e = A.chunk_end[ch];
-    for (int k = b + threadIdx.x; k < e; k += NT_CM) {
+    // two observations per trip: both records / measurements are requested before either is consumed
+    for (int k = b + threadIdx.x; k < e; k += 2 * NT_CM) {
+      const int k2 = k + NT_CM;
+      const bool has2 = k2 < e;
       const double4 rec = ldg4(rec_cm + k);
       const double2 uv = __ldg(A.cm_uv + k);
-      double a[6], bb[6];
-      jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
-      const double r0 = rec.w * (A.K.fx * rec.x + A.K.cx - uv.x);
-      const double r1 = rec.w * (A.K.fy * rec.y + A.K.cy - uv.y);
-      acc_sym_sparse(acc, a, bb, a, bb);
-      acc_vec_sparse(acc + 21, a, bb, r0, r1);
+      const double4 recb = ldg4(rec_cm + (has2 ? k2 : k));
+      const double2 uvb = __ldg(A.cm_uv + (has2 ? k2 : k));
+      {
+        double a[6], bb[6];
+        jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+        const double r0 = rec.w * (A.K.fx * rec.x + A.K.cx - uv.x);
+        const double r1 = rec.w * (A.K.fy * rec.y + A.K.cy - uv.y);
+        acc_sym_sparse(acc, a, bb, a, bb);
+        acc_vec_sparse(acc + 21, a, bb, r0, r1);
+      }
+      if (has2) {
+        double a[6], bb[6];
+        jhat_rows(recb, sv0, sv1, sv2, A.K, a, bb);
+        const double r0 = recb.w * (A.K.fx * recb.x + A.K.cx - uvb.x);
+        const double r1 = recb.w * (A.K.fy * recb.y + A.K.cy - uvb.y);
+        acc_sym_sparse(acc, a, bb, a, bb);
+        acc_vec_sparse(acc + 21, a, bb, r0, r1);
+      }
     }
   }
   block_reduce<27, NT_CM>(acc, sm, smo);
@@ -570,17 +585,31 @@ k_spmv_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __re
     for (int q = 0; q < 9; ++q) R[q] = ct[q];
     const double sv0 = ct[21], sv1 = ct[22], sv2 = ct[23];
     const int b = A.chunk_begin[ch], e = A.chunk_end[ch];
-    for (int k = b + threadIdx.x; k < e; k += NT_CM) {
+    for (int k = b + threadIdx.x; k < e; k += 2 * NT_CM) {
+      const int k2 = k + NT_CM;
+      const bool has2 = k2 < e;
       const double4 rec = ldg4(rec_cm + k);
       const int j = __ldg(A.cm_pt + k);
+      const double4 recb = ldg4(rec_cm + (has2 ? k2 : k));
+      const int jb = __ldg(A.cm_pt + (has2 ? k2 : k));
       const double4 u = ldg4(u4 + j);
-      double ap[3], bp[3];
-      jp_rows(rec, R, A.K, ap, bp);
-      const double f0 = ap[0] * u.x + ap[1] * u.y + ap[2] * u.z;
-      const double f1 = bp[0] * u.x + bp[1] * u.y + bp[2] * u.z;
-      double a[6], bb[6];
-      jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
-      acc_vec_sparse(acc, a, bb, f0, f1);
+      const double4 ub = ldg4(u4 + jb);
+      {
+        double ap[3], bp[3], a[6], bb[6];
+        jp_rows(rec, R, A.K, ap, bp);
+        const double f0 = ap[0] * u.x + ap[1] * u.y + ap[2] * u.z;
+        const double f1 = bp[0] * u.x + bp[1] * u.y + bp[2] * u.z;
+        jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+        acc_vec_sparse(acc, a, bb, f0, f1);
+      }
+      if (has2) {
+        double ap[3], bp[3], a[6], bb[6];
+        jp_rows(recb, R, A.K, ap, bp);
+        const double f0 = ap[0] * ub.x + ap[1] * ub.y + ap[2] * ub.z;
+        const double f1 = bp[0] * ub.x + bp[1] * ub.y + bp[2] * ub.z;
+        jhat_rows(recb, sv0, sv1, sv2, A.K, a, bb);
+        acc_vec_sparse(acc, a, bb, f0, f1);
+      }
     }
   }
   block_reduce<6, NT_CM>(acc, sm, smo);

@@ -26,6 +26,7 @@ template <int MAXCOL>
 __device__ __forceinline__ void last_block_reduce5(const double* part, const int rows, const int* slots, unsigned* counter,
                                                    double* __restrict__ scal, double* sm /* 5*NT_T/32 */, double* smo /* 5 */) {
   __shared__ bool s_last;
+  if (counter == nullptr) return;       // large grids: the host launches k_reduce_rows instead (uniform branch)
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned t = atomicInc(counter, gridDim.x - 1);
@@ -53,6 +54,34 @@ __device__ __forceinline__ void last_block_reduce5(const double* part, const int
   }
 }
 struct RedArgs { unsigned* counter; double* scal; int slots[5]; };
+
+// Large grids: 64 CTAs each fold a fixed, contiguous range of the per-tile partial rows, the last one folds the 64.
+template <int MAXCOL>
+__global__ void __launch_bounds__(NT_T)
+k_reduce_rows(const double* __restrict__ part, const int rows, double* __restrict__ part2 /* [grid][5] */, const RedArgs RA) {
+  __shared__ double sm[5 * NT_T / 32];
+  __shared__ double smo[5];
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double mx[1] = {0.0};
+  for (int r = r0 + threadIdx.x; r < r1; r += NT_T) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const double x = __ldg(part + (size_t)5 * r + q);
+      if (q == MAXCOL) mx[0] = fmax(mx[0], x); else acc[q] += x;
+    }
+  }
+  block_reduce<5, NT_T>(acc, sm, smo);
+  if (threadIdx.x < 5 && (int)threadIdx.x != MAXCOL) part2[(size_t)5 * blockIdx.x + threadIdx.x] = smo[threadIdx.x];
+  if (MAXCOL >= 0) {
+    __syncthreads();
+    block_reduce<1, NT_T, true>(mx, sm, smo);
+    if (threadIdx.x == 0) part2[(size_t)5 * blockIdx.x + MAXCOL] = smo[0];
+  }
+  __syncthreads();
+  last_block_reduce5<MAXCOL>(part2, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo);
+}
 
 struct TileArgs {
   const int* tile_pt;      // [n_tiles+1] first point of every tile

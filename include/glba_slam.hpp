@@ -235,6 +235,65 @@ inline bool pose_only_ba(Backend& be, Mat33& R, Vec3& t, const std::vector<Point
   return true;
 }
 
+// ---- post-BA propagation to keyframes / points created while BA ran (slam_core.cpp:885-973) ----------------------------
+inline Mat33 mul(const Mat33& A, const Mat33& B) {
+  Mat33 C;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C.m[r * 3 + c] = A.m[r * 3] * B.m[c] + A.m[r * 3 + 1] * B.m[3 + c] + A.m[r * 3 + 2] * B.m[6 + c];
+  return C;
+}
+inline Mat33 transpose(const Mat33& A) { Mat33 T; for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) T.m[r * 3 + c] = A.m[c * 3 + r]; return T; }
+inline double det(const Mat33& A) {
+  return A.m[0] * (A.m[4] * A.m[8] - A.m[5] * A.m[7]) - A.m[1] * (A.m[3] * A.m[8] - A.m[5] * A.m[6]) + A.m[2] * (A.m[3] * A.m[7] - A.m[4] * A.m[6]);
+}
+// ProjectToSO3 (slam_core.cpp:885-897): nearest rotation U V' of the SVD.  Computed as the orthogonal polar factor by
+// Newton's iteration X <- (X + X^-T)/2, which converges to exactly U V' for det > 0 (always the case for the drifted
+// rotations this is applied to); a reflection (det < 0) is returned unchanged, the reference flips a singular vector there.
+inline Mat33 project_to_so3(const Mat33& R_in) {
+  Mat33 X = R_in;
+  if (!(det(X) > 0.0)) return X;
+  for (int it = 0; it < 20; ++it) {
+    const double d = det(X);
+    Mat33 inv_t;   // X^-T = cofactor(X) / det
+    inv_t.m[0] = (X.m[4] * X.m[8] - X.m[5] * X.m[7]) / d; inv_t.m[1] = (X.m[5] * X.m[6] - X.m[3] * X.m[8]) / d; inv_t.m[2] = (X.m[3] * X.m[7] - X.m[4] * X.m[6]) / d;
+    inv_t.m[3] = (X.m[2] * X.m[7] - X.m[1] * X.m[8]) / d; inv_t.m[4] = (X.m[0] * X.m[8] - X.m[2] * X.m[6]) / d; inv_t.m[5] = (X.m[1] * X.m[6] - X.m[0] * X.m[7]) / d;
+    inv_t.m[6] = (X.m[1] * X.m[5] - X.m[2] * X.m[4]) / d; inv_t.m[7] = (X.m[2] * X.m[3] - X.m[0] * X.m[5]) / d; inv_t.m[8] = (X.m[0] * X.m[4] - X.m[1] * X.m[3]) / d;
+    double change = 0.0;
+    for (int q = 0; q < 9; ++q) { const double v = 0.5 * (X.m[q] + inv_t.m[q]); change = std::max(change, std::fabs(v - X.m[q])); X.m[q] = v; }
+    if (change < 1e-15) break;
+  }
+  return X;
+}
+// ComputeDeltaPose_SO3 (slam_core.cpp:899-912)
+inline void compute_delta_pose_so3(const Mat33& Rb_in, const Vec3& tb, const Mat33& Ra_in, const Vec3& ta, Mat33& dR, Vec3& dt) {
+  const Mat33 Rb = project_to_so3(Rb_in), Ra = project_to_so3(Ra_in);
+  dR = project_to_so3(mul(Ra, transpose(Rb)));
+  for (int r = 0; r < 3; ++r) dt.v[r] = ta.v[r] - (dR.m[r * 3] * tb.v[0] + dR.m[r * 3 + 1] * tb.v[1] + dR.m[r * 3 + 2] * tb.v[2]);
+}
+// post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973): the last window camera's pose change is applied to the
+// points / keyframes the tracking thread created while BA was running (slam_types::mpid_to_correct / kpid_to_correct,
+// both consumed).  R_before / t_before = pose of keyframe run_window before the write-back.
+inline void post_ba_map_update_for_new_keyframes(Map& map, const Mat33& R_before, const Vec3& t_before, int run_window,
+                                                 std::vector<int>& mpid_to_correct, std::vector<int>& kpid_to_correct) {
+  const Frame& last = map.keyframes[run_window];
+  Mat33 dR; Vec3 dt;
+  compute_delta_pose_so3(R_before, t_before, last.R, last.t, dR, dt);
+  while (!mpid_to_correct.empty()) {
+    Point3d& X = map.map_points[mpid_to_correct.back()].position;
+    const double x = X.x, y = X.y, z = X.z;
+    X.x = dR.m[0] * x + dR.m[1] * y + dR.m[2] * z + dt.v[0];
+    X.y = dR.m[3] * x + dR.m[4] * y + dR.m[5] * z + dt.v[1];
+    X.z = dR.m[6] * x + dR.m[7] * y + dR.m[8] * z + dt.v[2];
+    mpid_to_correct.pop_back();
+  }
+  while (!kpid_to_correct.empty()) {
+    Frame& kf = map.keyframes[kpid_to_correct.back()];
+    const Vec3 t = kf.t;
+    kf.R = mul(dR, kf.R);
+    for (int r = 0; r < 3; ++r) kf.t.v[r] = dR.m[r * 3] * t.v[0] + dR.m[r * 3 + 1] * t.v[1] + dR.m[r * 3 + 2] * t.v[2] + dt.v[r];
+    kpid_to_correct.pop_back();
+  }
+}
+
 // post_ba_map_point_culling (slam_core.cpp:977-1038): candidates are the points first seen by keyframes
 // [run_window - local_ba_window, run_window - 4]; a point is flagged is_bad when it lies behind one of its
 // cameras, has fewer than `min_obs` observations or a mean reprojection error above `max_err` pixels.  The

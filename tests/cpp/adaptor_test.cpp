@@ -87,6 +87,30 @@ int main(int argc, char** argv) {
     for (auto& kv : map.keyframes) { double w[3]; Mat33 R2; rodrigues(kv.second.R, w); rodrigues(w, R2);
       for (int q = 0; q < 9; ++q) worst = std::max(worst, std::fabs(R2.m[q] - kv.second.R.m[q])); }
     std::cout << worst << "\n";
+    // post_ba_map_update_for_new_keyframes: move the last window keyframe by a known rigid motion (with a little
+    // non-orthogonal drift on R, which ProjectToSO3 must remove) and check that a late keyframe / point follow it
+    {
+      Map m2 = map;
+      Frame& last = m2.keyframes[run_window];
+      const Mat33 R_before = last.R; const Vec3 t_before = last.t;
+      const double w[3] = {0.01, -0.02, 0.015};
+      Mat33 D; rodrigues(w, D);
+      const Vec3 d{{0.3, -0.1, 0.2}};
+      last.R = mul(D, R_before);
+      for (int r = 0; r < 3; ++r) last.t.v[r] = D.m[r * 3] * t_before.v[0] + D.m[r * 3 + 1] * t_before.v[1] + D.m[r * 3 + 2] * t_before.v[2] + d.v[r];
+      Mat33 noisy = R_before; noisy.m[1] += 1e-9; noisy.m[5] -= 2e-9;
+      Frame extra; extra.id = 999; extra.R = R_before; extra.t = t_before; m2.keyframes[999] = extra;
+      MapPoint mp; mp.id = 5000; mp.position = Point3d{1.0, 2.0, 3.0}; m2.map_points[5000] = mp;
+      std::vector<int> mpids{5000}, kpids{999};
+      post_ba_map_update_for_new_keyframes(m2, noisy, t_before, run_window, mpids, kpids);
+      double err = 0;
+      for (int q = 0; q < 9; ++q) err = std::max(err, std::fabs(m2.keyframes[999].R.m[q] - last.R.m[q]));
+      for (int q = 0; q < 3; ++q) err = std::max(err, std::fabs(m2.keyframes[999].t.v[q] - last.t.v[q]));
+      const Point3d& X = m2.map_points[5000].position;
+      const double ex = D.m[0] * 1 + D.m[1] * 2 + D.m[2] * 3 + d.v[0], ey = D.m[3] * 1 + D.m[4] * 2 + D.m[5] * 3 + d.v[1], ez = D.m[6] * 1 + D.m[7] * 2 + D.m[8] * 3 + d.v[2];
+      err = std::max(err, std::max(std::fabs(X.x - ex), std::max(std::fabs(X.y - ey), std::fabs(X.z - ez))));
+      std::cout << err << " " << (mpids.empty() && kpids.empty() ? 1 : 0) << "\n";
+    }
     return 0;
   }
   if (mode == "solve") {

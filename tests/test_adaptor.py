@@ -72,6 +72,8 @@ def test_pack_window_restates_reference_packing(exe, tmp_path):
     assert np.array_equal(obs[:, 2], sub.obs_u) and np.array_equal(obs[:, 3], sub.obs_v)
     assert out[4].split() == ["1", "1"] + ["0"] * 8               # cameras 0 and 1 constant (slam_core.cpp:831-833)
     assert float(out[5]) < 1e-14                                  # Rodrigues round trip
+    err, consumed = out[6].split()                                # post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973)
+    assert float(err) < 1e-7 and consumed == "1"
 
 
 @pytest.mark.gpu
