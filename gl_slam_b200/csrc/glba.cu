@@ -91,7 +91,7 @@ struct glba_ctx {
   bool schur_fresh = false;                      // Schur pieces already built for the current linearisation and radius
   double* d_scal = nullptr;   // NSCAL doubles at the tail of acc27 (one all-reduce carries camera sums + scalars)
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
-  Buf tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
+  Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
   int n_tiles = 0, max_track = 0, grid_c = 0;
   Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
@@ -314,6 +314,8 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
     ctx->n_tiles = (int)((n + B - 1) / B);
     ENSURE(int, ctx->tile_pt, (size_t)ctx->n_tiles + 1);
     LAUNCH(k_tile_starts, cdiv(ctx->n_tiles + 1, 256), 256, ctx->n_tiles, B, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->tile_pt.as<int>());
+    ENSURE(int, ctx->tile_cmin, (size_t)ctx->n_tiles);
+    LAUNCH(k_tile_cmin, ctx->n_tiles, NT_T, (const int*)ctx->tile_pt.as<int>(), (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->tile_cmin.as<int>());
   }
   ctx->grid_c = std::max(1, cdiv(n_cam, NT_C));
   long per = (n + 148L * 8 - 1) / (148L * 8);
@@ -381,7 +383,7 @@ CmArgs cm_args(glba_ctx* ctx) {
   return A;
 }
 
-TileArgs tile_args(glba_ctx* ctx) { return TileArgs{ctx->tile_pt.as<int>(), ctx->pm_pt.as<int>()}; }
+TileArgs tile_args(glba_ctx* ctx) { return TileArgs{ctx->tile_pt.as<int>(), ctx->pm_pt.as<int>(), ctx->tile_cmin.as<int>(), ctx->n_cam}; }
 
 int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
   ReduceMap M{}; M.n = 5;
@@ -404,7 +406,7 @@ void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, do
   const int c = ctx->cur;
   if (ctx->use_tiles) {
     static bool attr_set = false;
-    const size_t smem = (size_t)9 * TILE_OBS * sizeof(double);
+    const size_t smem = (size_t)8 * TILE_OBS * sizeof(double);
     if (!attr_set) { cudaFuncSetAttribute(k_linearize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     k_linearize_tile<<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
@@ -878,7 +880,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);

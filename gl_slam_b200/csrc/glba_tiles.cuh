@@ -83,19 +83,24 @@ k_reduce_rows(const double* __restrict__ part, const int rows, double* __restric
   last_block_reduce5<MAXCOL>(part2, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo);
 }
 
+constexpr int CWIN = 32;    // camera rows staged in shared memory per tile: [cmin, cmin + CWIN)
+constexpr int XROW = 18;    // padded row stride (doubles) of the staged gather rows: spreads rows over the banks
+constexpr int CROW = 14;    // padded stride of staged candidate rows (R, c)
 struct TileArgs {
   const int* tile_pt;      // [n_tiles+1] first point of every tile
   const int* pm_pt;        // point of observation k (point-major order)
+  const int* tile_cmin;    // [n_tiles] smallest camera index observed in the tile
+  int n_cam;
 };
 
 // K_A + point half of K_B, tiled.  Same outputs as k_linearize_pm.
-__global__ void __launch_bounds__(NT_T, 3)
+__global__ void __launch_bounds__(NT_T)
 k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ pt, const double* __restrict__ camtab,
                  double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
                  double4* __restrict__ lam4, double* __restrict__ pblk, const int first, const int jacobi, const double min_diag,
                  const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   extern __shared__ double dsm[];
-  double (*val)[TILE_OBS] = reinterpret_cast<double (*)[TILE_OBS]>(dsm);     // [9][TILE_OBS]
+  double (*val)[TILE_OBS] = reinterpret_cast<double (*)[TILE_OBS]>(dsm);     // [8][TILE_OBS]: J~p rows (3+3), r~ (2)
   __shared__ double sm[4 * NT_T / 32];
   __shared__ double smo[4];
   __shared__ double smm[NT_T / 32];
@@ -104,28 +109,36 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
   const int j0 = T.tile_pt[blockIdx.x], j1 = T.tile_pt[blockIdx.x + 1];
   const int k0 = A.pt_start[j0], k1 = A.pt_start[j1];
   double cost = 0.0, bad = 0.0;
-  // stage 1: every first-level load of the thread's OPT observations is issued before anything is consumed,
-  // so one DRAM round trip covers OPT observations (indices clamped into the tile: no divergence, no OOB)
-  int ci[OPT], pj[OPT], cm[OPT];
-  double2 uvs[OPT];
-  const int klast = max(k1 - 1, k0);
-#pragma unroll
-  for (int m = 0; m < OPT; ++m) {
-    const int kc = min(k0 + m * NT_T + tid, klast);
-    ci[m] = __ldg(A.pm_cam + kc);
-    pj[m] = __ldg(T.pm_pt + kc);
-    cm[m] = __ldg(A.pm2cm + kc);
-    uvs[m] = __ldg(A.pm_uv + kc);
+  // camera rows (R, centre) of the tile's camera window staged once, coalesced (see k_point_tile)
+  __shared__ __align__(16) double cs[CWIN * CROW];
+  const int cmin = T.tile_cmin[blockIdx.x];
+  for (int t = tid; t < CWIN * 6; t += NT_T) {
+    const int row = t / 6, part = t - row * 6, cam = cmin + row;
+    if (cam < T.n_cam) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(camtab + (size_t)CAMTAB * cam) + part);
+      *reinterpret_cast<double2*>(&cs[row * CROW + 2 * part]) = v;
+    }
   }
+  __syncthreads();
 #pragma unroll
   for (int m = 0; m < OPT; ++m) {
     const int l = m * NT_T + tid;
     const int k = k0 + l;
     if (k < k1) {
-      const double2 uv = uvs[m];
-      const double4 X = ldg4(pt + pj[m]);
+      const int ci = __ldg(A.pm_cam + k);
+      const int pj = __ldg(T.pm_pt + k);
+      const double2 uv = __ldg(A.pm_uv + k);
+      const double4 X = ldg4(pt + pj);
       double R[9], cc[3];
-      load_Rc(camtab + (size_t)CAMTAB * ci[m], R, cc);
+      const unsigned off = (unsigned)(ci - cmin);
+      if (off < (unsigned)CWIN) {
+        const double2* cr = reinterpret_cast<const double2*>(&cs[off * CROW]);
+        const double2 a0 = cr[0], a1 = cr[1], a2 = cr[2], a3 = cr[3], a4 = cr[4], a5 = cr[5];
+        R[0] = a0.x; R[1] = a0.y; R[2] = a1.x; R[3] = a1.y; R[4] = a2.x; R[5] = a2.y; R[6] = a3.x; R[7] = a3.y; R[8] = a4.x;
+        cc[0] = a4.y; cc[1] = a5.x; cc[2] = a5.y;
+      } else {
+        load_Rc(camtab + (size_t)CAMTAB * ci, R, cc);
+      }
       const double qx = X.x - cc[0], qy = X.y - cc[1], qz = X.z - cc[2];
       const double px = R[0] * qx + R[1] * qy + R[2] * qz;
       const double py = R[3] * qx + R[4] * qy + R[5] * qz;
@@ -139,13 +152,13 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
       cost += 0.5 * rho;
       const double4 rec = make_double4(xh, yh, iz, w);
       st4(rec_pm + k, rec);
-      st4(rec_cm + cm[m], rec);
+      st4(rec_cm + __ldg(A.pm2cm + k), rec);
       double ap[3], bp[3];
       jp_rows(rec, R, A.K, ap, bp);
       const double r0 = w * rx, r1 = w * ry;
-      val[0][l] = ap[0] * ap[0] + bp[0] * bp[0]; val[1][l] = ap[0] * ap[1] + bp[0] * bp[1]; val[2][l] = ap[0] * ap[2] + bp[0] * bp[2];
-      val[3][l] = ap[1] * ap[1] + bp[1] * bp[1]; val[4][l] = ap[1] * ap[2] + bp[1] * bp[2]; val[5][l] = ap[2] * ap[2] + bp[2] * bp[2];
-      val[6][l] = ap[0] * r0 + bp[0] * r1; val[7][l] = ap[1] * r0 + bp[1] * r1; val[8][l] = ap[2] * r0 + bp[2] * r1;
+      // stage the two rows of J~p and r~ (8 values, 64 KB per tile: three CTAs per SM still fit beside the camera window)
+      val[0][l] = ap[0]; val[1][l] = ap[1]; val[2][l] = ap[2]; val[3][l] = bp[0]; val[4][l] = bp[1]; val[5][l] = bp[2];
+      val[6][l] = r0; val[7][l] = r1;
     }
   }
   __syncthreads();
@@ -154,10 +167,11 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
     const int b = __ldg(A.pt_start + j) - k0, e = __ldg(A.pt_start + j + 1) - k0;
     double C[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
     for (int m = b; m < e; ++m) {
-#pragma unroll
-      for (int q = 0; q < 6; ++q) C[q] += val[q][m];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) g[q] += val[6 + q][m];
+      const double a0 = val[0][m], a1 = val[1][m], a2 = val[2][m], b0 = val[3][m], b1 = val[4][m], b2 = val[5][m];
+      const double r0 = val[6][m], r1 = val[7][m];
+      C[0] += a0 * a0 + b0 * b0; C[1] += a0 * a1 + b0 * b1; C[2] += a0 * a2 + b0 * b2;
+      C[3] += a1 * a1 + b1 * b1; C[4] += a1 * a2 + b1 * b2; C[5] += a2 * a2 + b2 * b2;
+      g[0] += a0 * r0 + b0 * r1; g[1] += a1 * r0 + b1 * r1; g[2] += a2 * r0 + b2 * r1;
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) Craw[(size_t)q * A.n_pt + j] = C[q];
@@ -219,10 +233,32 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
              const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
              const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   __shared__ double val[3][TILE_OBS];
+  __shared__ __align__(16) double xs[CWIN * XROW];                     // staged gather rows of cameras [cmin, cmin+CWIN)
+  __shared__ __align__(16) double cs[MODE == 1 ? CWIN * CROW : 2];     // staged candidate rows (R, c)
   if (MODE == 0 && cg && cg->done_at <= li) return;
   const int tid = threadIdx.x;
   const int j0 = T.tile_pt[blockIdx.x], j1 = T.tile_pt[blockIdx.x + 1];
   const int k0 = A.pt_start[j0], k1 = A.pt_start[j1];
+  const int cmin = T.tile_cmin[blockIdx.x];
+  // creation-ordered map points make a tile touch a narrow camera range: stage those rows once (coalesced), so the
+  // per-observation gathers below are shared-memory reads instead of L2 round trips; cameras outside the window
+  // (loop-closure wrap-around) fall back to the global gather
+  for (int t = tid; t < CWIN * 8; t += NT_T) {
+    const int row = t >> 3, part = t & 7, cam = cmin + row;
+    if (cam < T.n_cam) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(xtab + (size_t)XTAB * cam) + part);
+      *reinterpret_cast<double2*>(&xs[row * XROW + 2 * part]) = v;
+    }
+  }
+  if (MODE == 1)
+    for (int t = tid; t < CWIN * 6; t += NT_T) {
+      const int row = t / 6, part = t - row * 6, cam = cmin + row;
+      if (cam < T.n_cam) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(camtab_c + (size_t)CAMTAB * cam) + part);
+        *reinterpret_cast<double2*>(&cs[row * CROW + 2 * part]) = v;
+      }
+    }
+  __syncthreads();
 #pragma unroll
   for (int m = 0; m < OPT; ++m) {
     const int l = m * NT_T + tid;
@@ -230,13 +266,23 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
     if (k < k1) {
       const int cam_i = __ldg(A.pm_cam + k);
       const double4 rec = ldg4(rec_pm + k);
-      // one 128-byte row per camera: four 256-bit gathers
-      const double4* xr = reinterpret_cast<const double4*>(xtab + (size_t)XTAB * cam_i);
-      const double4 x0 = ldg4(xr), x1 = ldg4(xr + 1), x2 = ldg4(xr + 2), x3 = ldg4(xr + 3);
-      const double xg[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
-      const double R[9] = {x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z};
+      double xg[6], R[9], flag;
+      const unsigned off = (unsigned)(cam_i - cmin);
+      if (off < (unsigned)CWIN) {
+        const double2* xr = reinterpret_cast<const double2*>(&xs[off * XROW]);
+        const double2 a0 = xr[0], a1 = xr[1], a2 = xr[2], a3 = xr[3], a4 = xr[4], a5 = xr[5], a6 = xr[6], a7 = xr[7];
+        xg[0] = a0.x; xg[1] = a0.y; xg[2] = a1.x; xg[3] = a1.y; xg[4] = a2.x; xg[5] = a2.y;
+        R[0] = a3.x; R[1] = a3.y; R[2] = a4.x; R[3] = a4.y; R[4] = a5.x; R[5] = a5.y; R[6] = a6.x; R[7] = a6.y; R[8] = a7.x;
+        flag = a7.y;
+      } else {        // one 128-byte row per camera: four 256-bit gathers
+        const double4* xr = reinterpret_cast<const double4*>(xtab + (size_t)XTAB * cam_i);
+        const double4 x0 = ldg4(xr), x1 = ldg4(xr + 1), x2 = ldg4(xr + 2), x3 = ldg4(xr + 3);
+        xg[0] = x0.x; xg[1] = x0.y; xg[2] = x0.z; xg[3] = x0.w; xg[4] = x1.x; xg[5] = x1.y;
+        R[0] = x1.z; R[1] = x1.w; R[2] = x2.x; R[3] = x2.y; R[4] = x2.z; R[5] = x2.w; R[6] = x3.x; R[7] = x3.y; R[8] = x3.z;
+        flag = x3.w;
+      }
       double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-      if (x3.w != 0.0) {               // Ceres' small-angle branch: only an (almost) exactly-identity keyframe
+      if (flag != 0.0) {               // Ceres' small-angle branch: only an (almost) exactly-identity keyframe
         const double* ct = camtab + (size_t)CAMTAB * cam_i;
         sv0 = ct[CT_SV]; sv1 = ct[CT_SV + 1]; sv2 = ct[CT_SV + 2];
       }
@@ -293,7 +339,15 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
         const double2 uv = __ldg(A.pm_uv + k);
         const double4 xc = ld4(pt_c + pt_j);          // written by this CTA: coherent load
         double Rc[9], cc[3];
-        load_Rc(camtab_c + (size_t)CAMTAB * cam_i, Rc, cc);
+        const unsigned off = (unsigned)(cam_i - cmin);
+        if (off < (unsigned)CWIN) {
+          const double2* cr = reinterpret_cast<const double2*>(&cs[off * CROW]);
+          const double2 a0 = cr[0], a1 = cr[1], a2 = cr[2], a3 = cr[3], a4 = cr[4], a5 = cr[5];
+          Rc[0] = a0.x; Rc[1] = a0.y; Rc[2] = a1.x; Rc[3] = a1.y; Rc[4] = a2.x; Rc[5] = a2.y; Rc[6] = a3.x; Rc[7] = a3.y; Rc[8] = a4.x;
+          cc[0] = a4.y; cc[1] = a5.x; cc[2] = a5.y;
+        } else {
+          load_Rc(camtab_c + (size_t)CAMTAB * cam_i, Rc, cc);
+        }
         const double qx = xc.x - cc[0], qy = xc.y - cc[1], qz = xc.z - cc[2];
         const double px = Rc[0] * qx + Rc[1] * qy + Rc[2] * qz, py = Rc[3] * qx + Rc[4] * qy + Rc[5] * qz, pz = Rc[6] * qx + Rc[7] * qy + Rc[8] * qz;
         const double iz = 1.0 / pz;
@@ -310,6 +364,21 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
     __syncthreads();
     last_block_reduce5<-1>(part, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo);
   }
+}
+
+// smallest camera index among a tile's observations
+__global__ void __launch_bounds__(NT_T)
+k_tile_cmin(const int* __restrict__ tile_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, int* __restrict__ tile_cmin) {
+  __shared__ int sm[NT_T / 32];
+  const int j0 = tile_pt[blockIdx.x], j1 = tile_pt[blockIdx.x + 1];
+  const int k0 = pt_start[j0], k1 = pt_start[j1];
+  int m = 0x7fffffff;
+  for (int k = k0 + threadIdx.x; k < k1; k += NT_T) m = min(m, pm_cam[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 1; w < NT_T / 32; ++w) m = min(m, sm[w]); tile_cmin[blockIdx.x] = (m == 0x7fffffff) ? 0 : m; }
 }
 
 // ---- load-time helpers ------------------------------------------------------------------------
