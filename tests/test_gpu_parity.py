@@ -266,3 +266,26 @@ def test_sliding_window_schedule(ctx, oracle, min_obs):
         pt[keep] = ref.pt
         n_windows += 1
     assert n_windows == 9
+
+
+def test_long_tracks_use_fallback_kernels(ctx, oracle):
+    """A point observed by 600 cameras exceeds the tile capacity (TILE_OBS/2): the thread-per-point kernels take over.
+    Also the shape of a loop-closure landmark; parity gates unchanged."""
+    n_cam = 600
+    cam = np.zeros((n_cam, 6))
+    cam[:, 3] = np.linspace(0, 6, n_cam)
+    cam[:, 1] = np.linspace(0, 0.05, n_cam)
+    rng = np.random.default_rng(4)
+    pt = np.c_[rng.uniform(1, 5, 40), rng.uniform(-1, 1, 40), rng.uniform(8, 15, 40)]
+    oc = np.concatenate([np.arange(n_cam)] + [np.arange(j % 7, n_cam, 7 + j % 5) for j in range(1, 40)])
+    op = np.concatenate([np.zeros(n_cam, int)] + [np.full(len(np.arange(j % 7, n_cam, 7 + j % 5)), j) for j in range(1, 40)])
+    u, v, _ = scene.project(cam, pt, oc, op, scene.KITTI_K)
+    u += rng.normal(0, 0.3, u.shape); v += rng.normal(0, 0.3, v.shape)
+    cam0 = cam.copy()
+    cam0[2:, 3:] += rng.normal(0, 0.01, (n_cam - 2, 3))
+    prob = HostProblem(cam0, pt + rng.normal(0, 0.05, pt.shape), oc, op, u, v, scene.KITTI_K, (np.arange(n_cam) < 2).astype(np.uint8))
+    o = dict(max_iters=8)
+    ref, so = oracle.solve(prob, oracle.options(**o))
+    got, s = ctx.solve(prob, g.options(**o))
+    check_trajectory(s, so, rtol=1e-8)
+    assert np.allclose(got.cam, ref.cam, rtol=1e-5, atol=1e-7) and np.allclose(got.pt, ref.pt, rtol=1e-5, atol=1e-7)
