@@ -488,13 +488,13 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   mark(ctx, PH_LIN);
   const bool sharded = ctx->world > 1;
   if (n_pt) launch_linearize_points(ctx, o, first, radius);
-  if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+  if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
   if (n_cam && sharded) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
                                (const double*)ctx->part_cm.as<double>(), ctx->d_accA, (const CgState*)nullptr, 0);
   if (with_schur) {
     mark(ctx, PH_SCHUR);
-    if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+    if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                               (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
     if (n_cam && sharded) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
                                  (const double*)ctx->part_cm2.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
@@ -534,7 +534,7 @@ int do_schur(glba_ctx* ctx, double radius) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
   mark(ctx, PH_SCHUR);
-  if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+  if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
   if (ctx->world > 1) {
     LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
@@ -972,9 +972,9 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
     return GLBA_OK;
   };
   if ((st = timed([&] { launch_linearize_points(ctx, opt, 0, radius); }, &out->linearize_pm_ms))) return st;
-  if ((st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+  if ((st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            ctx->part_cm.as<double>()); }, &out->linearize_cm_ms))) return st;
-  if ((st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+  if ((st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms))) return st;
   if ((st = timed([&] { launch_point_pass0(ctx, opt, (const CgState*)nullptr, 0); }, &out->spmv_pm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),

@@ -26,7 +26,11 @@ constexpr int CAMTAB = 24;  // doubles per camera: R[9] c[3] | G[9] sv[3]  (192 
 constexpr int CT_C = 9, CT_G = 12, CT_SV = 21;
 constexpr int PBLK = 12;    // doubles per point block: Cinv[6] (00,01,02,11,12,22) u0[3] pad[3]  (96 B = 3 sectors)
 constexpr int NT_PM = 128;  // threads per CTA, point-major kernels (one thread per point)
-constexpr int NT_CM = 256;  // threads per CTA, camera-major kernels (one CTA per chunk of one camera)
+constexpr int NT_CM = 256;  // threads per CTA, k_spmv_cm (one CTA per chunk of one camera)
+#ifndef GLBA_NT_HCM
+#define GLBA_NT_HCM 128
+#endif
+constexpr int NT_HCM = GLBA_NT_HCM;  // threads per CTA of the two 27-accumulator kernels (k_linearize_cm, k_schur_cm)
 constexpr int NT_CAM = 1024;  // threads of the single-CTA camera kernels
 
 // scalar slots (device array `scal`), written by fixed-order reductions
@@ -469,10 +473,11 @@ struct CmArgs {
 };
 
 // Camera half of K_B: A_i = sum J^'J^ (21 upper entries), ghat_i = sum J^' r~ (6), per chunk.
-__global__ void __launch_bounds__(NT_CM, 2)
+// 5 CTAs/SM (96 registers, a few spilled accumulators) beat 4 (126 registers): measured 0.067 vs 0.076 ms on C4
+__global__ void __launch_bounds__(NT_HCM, 5)
 k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
                double* __restrict__ part /* [n_chunks][27] */) {
-  __shared__ double sm[27 * NT_CM / 32];
+  __shared__ double sm[27 * NT_HCM / 32];
   __shared__ double smo[27];
   const int ch = blockIdx.x;
   const int cam = A.chunk_cam[ch];
@@ -484,8 +489,8 @@ k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double*
     const double sv0 = ct[21], sv1 = ct[22], sv2 = ct[23];
     const int b = A.chunk_begin[ch], e = A.chunk_end[ch];
     // two observations per trip: both records / measurements are requested before either is consumed
-    for (int k = b + threadIdx.x; k < e; k += 2 * NT_CM) {
-      const int k2 = k + NT_CM;
+    for (int k = b + threadIdx.x; k < e; k += 2 * NT_HCM) {
+      const int k2 = k + NT_HCM;
       const bool has2 = k2 < e;
       const double4 rec = ldg4(rec_cm + k);
       const double2 uv = __ldg(A.cm_uv + k);
@@ -509,16 +514,17 @@ k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double*
       }
     }
   }
-  block_reduce<27, NT_CM>(acc, sm, smo);
+  block_reduce<27, NT_HCM>(acc, sm, smo);
   if (threadIdx.x < 27) part[(size_t)27 * ch + threadIdx.x] = smo[threadIdx.x];
 }
 
 // Schur half: for every observation of the camera, E = J~p Cinv J~p' (2x2) and f = J~p u0 (2):
 //   Mhat_i = sum J^' E J^ (21),  rhat_i = sum J^' f (6).
-__global__ void __launch_bounds__(NT_CM, 2)
+// here the spills cost more than the occupancy gains: 4 CTAs/SM
+__global__ void __launch_bounds__(NT_HCM, 4)
 k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
            const double* __restrict__ pblk, double* __restrict__ part /* [n_chunks][27] */) {
-  __shared__ double sm[27 * NT_CM / 32];
+  __shared__ double sm[27 * NT_HCM / 32];
   __shared__ double smo[27];
   const int ch = blockIdx.x;
   const int cam = A.chunk_cam[ch];
@@ -532,7 +538,7 @@ k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __r
     for (int q = 0; q < 9; ++q) R[q] = ct[q];
     const double sv0 = ct[21], sv1 = ct[22], sv2 = ct[23];
     const int b = A.chunk_begin[ch], e = A.chunk_end[ch];
-    for (int k = b + threadIdx.x; k < e; k += NT_CM) {
+    for (int k = b + threadIdx.x; k < e; k += NT_HCM) {
       const double4 rec = ldg4(rec_cm + k);
       const int j = __ldg(A.cm_pt + k);
       double Ci[6], u0[3];
@@ -564,7 +570,7 @@ k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __r
       acc_vec_sparse(acc + 21, a, bb, f0, f1);
     }
   }
-  block_reduce<27, NT_CM>(acc, sm, smo);
+  block_reduce<27, NT_HCM>(acc, sm, smo);
   if (threadIdx.x < 27) part[(size_t)27 * ch + threadIdx.x] = smo[threadIdx.x];
 }
 
