@@ -24,6 +24,7 @@ ABI_SYMBOLS = (
     "glba_nccl_unique_id", "glba_create", "glba_destroy", "glba_solve", "glba_pose_only", "glba_pose_only_batch",
     "glba_linearize", "glba_load", "glba_linearize_resident", "glba_solve_resident", "glba_reset_resident",
     "glba_read_resident", "glba_synchronize", "glba_stream", "glba_cull_points", "glba_time_kernels",
+    "glba_triangulate_filter",
 )
 
 
@@ -76,6 +77,7 @@ def lib():
     L.glba_stream.argtypes = [vp]
     L.glba_stream.restype = vp
     L.glba_cull_points.argtypes = [vp, C.POINTER(_abi.Problem), i32, f64, vp, vp]
+    L.glba_triangulate_filter.argtypes = [vp, vp, vp, vp, vp, f64, f64, f64, f64, i32, vp, vp, f64, f64, vp, vp]
     _LIB = L
     return L
 
@@ -218,6 +220,18 @@ class Context:
                                         cost.ctypes.data)
         self._check(st, "glba_pose_only_batch")
         return cams, usable.astype(bool), iters, cost
+
+    # -- two-view triangulation + filter (slam_core.cpp:173-256) ---------------------------------
+    def triangulate_filter(self, R1, t1, R2, t2, K, p0, p1, distance_threshold, reprojection_threshold):
+        """[R|t] world-to-camera; p0/p1 (n,2) matched pixels.  Returns (X (n,3) = X/w for every match, keep (n,) bool)."""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (R1, t1, R2, t2, p0, p1)]
+        n = a[4].shape[0]
+        X, keep = np.zeros((n, 3)), np.zeros(n, np.uint8)
+        st = lib().glba_triangulate_filter(self._h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
+                                           *map(float, K), n, a[4].ctypes.data, a[5].ctypes.data, float(distance_threshold),
+                                           float(reprojection_threshold), X.ctypes.data, keep.ctypes.data)
+        self._check(st, "glba_triangulate_filter")
+        return X, keep.astype(bool)
 
     # -- post-BA culling -----------------------------------------------------------------------
     def cull_points(self, prob, min_obs=3, max_mean_err=1.0):

@@ -26,6 +26,7 @@
 #include "glba_dense.cuh"
 #include "glba_tiles.cuh"
 #include "glba_cam.cuh"
+#include "glba_triang.cuh"
 
 using namespace glba;
 
@@ -1173,6 +1174,37 @@ int glba_cull_points(glba_ctx* ctx, const glba_problem* prob, int32_t min_obs, d
   if (mean_err) CU(cudaMemcpyAsync(mean_err, ctx->out_c.p, sizeof(double) * n_pt, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->ev_used = 0;
+  return GLBA_OK;
+}
+
+int glba_triangulate_filter(glba_ctx* ctx, const double* R1, const double* t1, const double* R2, const double* t2, double fx, double fy,
+                            double cx, double cy, int32_t n, const double* p0, const double* p1, double distance_threshold,
+                            double reprojection_threshold, double* X, uint8_t* keep) {
+  if (!ctx || !R1 || !t1 || !R2 || !t2 || n < 0 || (n > 0 && (!p0 || !p1 || !X || !keep))) return fail(ctx, GLBA_E_INVALID_ARG, "triangulate: bad argument");
+  if (n == 0) return GLBA_OK;
+  CU(cudaSetDevice(ctx->device));
+  TriArgs T;
+  const double Kmat[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) { T.T0[4 * r + c] = R1[3 * r + c]; T.T1[4 * r + c] = R2[3 * r + c]; }
+    T.T0[4 * r + 3] = t1[r]; T.T1[4 * r + 3] = t2[r];
+  }
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) {      // P = K [R|t]  (slam_core.cpp:182-183)
+    double a = 0, b = 0;
+    for (int k = 0; k < 3; ++k) { a += Kmat[3 * r + k] * T.T0[4 * k + c]; b += Kmat[3 * r + k] * T.T1[4 * k + c]; }
+    T.P0[4 * r + c] = a; T.P1[4 * r + c] = b;
+  }
+  T.K = Intr{fx, fy, cx, cy}; T.dist_thr = distance_threshold; T.reproj_thr = reprojection_threshold;
+  cudaStream_t s = ctx->stream;
+  ENSURE(double, ctx->in_u, 2 * (size_t)n); ENSURE(double, ctx->in_v, 2 * (size_t)n); ENSURE(double, ctx->out_a, 3 * (size_t)n); ENSURE(uint8_t, ctx->out_b, n);
+  CU(cudaMemcpyAsync(ctx->in_u.p, p0, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->in_v.p, p1, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
+  LAUNCH(k_triangulate, cdiv(n, 128), 128, n, T, (const double*)ctx->in_u.as<double>(), (const double*)ctx->in_v.as<double>(), ctx->out_a.as<double>(),
+         ctx->out_b.as<uint8_t>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(X, ctx->out_a.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(keep, ctx->out_b.p, n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   return GLBA_OK;
 }
 

@@ -244,6 +244,15 @@ void* glba_stream(glba_ctx* ctx);            /* cudaStream_t the context launche
 int glba_cull_points(glba_ctx* ctx, const glba_problem* prob, int32_t min_obs, double max_mean_err,
                      uint8_t* bad /* [n_pt] */, double* mean_err /* [n_pt], may be NULL */);
 
+/* Two-view triangulation + cheirality / reprojection filter on device, one thread per match
+ * (slam_core.cpp:173-256, triangulate_and_filter_3d_points; cv::triangulatePoints = DLT).  [R|t] are world-to-camera
+ * as that function receives them (row-major R1[9], t1[3], ...); p0/p1 = matched pixels [2n]; X[3n] receives X/w for every
+ * match, keep[n] = 1 where the reference would have kept the match (|w| >= 1e-9, 0 < depth <= distance_threshold in both
+ * views, reprojection error <= reprojection_threshold in both views).  Host pointers. */
+int glba_triangulate_filter(glba_ctx* ctx, const double* R1, const double* t1, const double* R2, const double* t2,
+                            double fx, double fy, double cx, double cy, int32_t n, const double* p0, const double* p1,
+                            double distance_threshold, double reprojection_threshold, double* X, uint8_t* keep);
+
 #ifdef __cplusplus
 }
 #endif

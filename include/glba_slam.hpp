@@ -235,6 +235,33 @@ inline bool pose_only_ba(Backend& be, Mat33& R, Vec3& t, const std::vector<Point
   return true;
 }
 
+// slam_types.h:64-69
+struct Match2D2D {
+  int idx0 = 0, idx1 = 0;
+  Point2d p0, p1;
+};
+
+// Drop-in for slam_core::triangulate_and_filter_3d_points (slam_core.cpp:173-256): [R|t] are the world-to-camera
+// poses the tracking thread passes; returns the kept 3-D points and their matches in input order.  The DLT
+// (cv::triangulatePoints, :194) and every filter (:213-241) run on the GPU, one thread per match.
+inline bool triangulate_and_filter_3d_points(Backend& be, const Mat33& R1, const Vec3& t1, const Mat33& R2, const Vec3& t2,
+                                             const CameraMatrix& K, const std::vector<Match2D2D>& matches, float distance_threshold,
+                                             float reprojection_threshold, std::vector<Point3d>& points3d,
+                                             std::vector<Match2D2D>& filteredPairs) {
+  points3d.clear(); filteredPairs.clear();
+  if (!be.ok()) return false;
+  const int32_t n = (int32_t)matches.size();
+  if (n == 0) return true;
+  std::vector<double> p0(2 * (size_t)n), p1(2 * (size_t)n), X(3 * (size_t)n);
+  std::vector<uint8_t> keep(n);
+  for (int32_t i = 0; i < n; ++i) { p0[2 * i] = matches[i].p0.x; p0[2 * i + 1] = matches[i].p0.y; p1[2 * i] = matches[i].p1.x; p1[2 * i + 1] = matches[i].p1.y; }
+  if (glba_triangulate_filter(be.ctx(), R1.m, t1.v, R2.m, t2.v, K.fx, K.fy, K.cx, K.cy, n, p0.data(), p1.data(), distance_threshold,
+                              reprojection_threshold, X.data(), keep.data()) != GLBA_OK) return false;
+  for (int32_t i = 0; i < n; ++i)
+    if (keep[i]) { points3d.push_back(Point3d{X[3 * i], X[3 * i + 1], X[3 * i + 2]}); filteredPairs.push_back(matches[i]); }
+  return true;
+}
+
 // ---- post-BA propagation to keyframes / points created while BA ran (slam_core.cpp:885-973) ----------------------------
 inline Mat33 mul(const Mat33& A, const Mat33& B) {
   Mat33 C;
