@@ -16,8 +16,10 @@
  *   fixed cameras             src/core/slam_core.cpp:831-833
  *   solver options            src/core/slam_core.cpp:842-847   (SPARSE_SCHUR, 30 iterations, 8 threads)
  *   pose-only variant         src/core/slam_core.cpp:1043-1140
- * It is cross-checked against an independent numpy/complex-step implementation
- * (oracle/py_oracle.py) and against cv2.Rodrigues; see tests/test_oracle.py.
+ * It is cross-checked against an independent numpy/complex-step implementation (oracle/py_oracle.py) and against
+ * OpenCV — the reference's own dependency, importable here as cv2: Rodrigues convention, analytic projectPoints
+ * Jacobians, solvePnPRefineLM optimum; see tests/test_oracle.py.  None of that replaces a run of libceres: the LM
+ * trajectory itself (accept/reject sequence, radii) remains unpinned.
  *
  * Ceres semantics encoded here (Ceres 2.x, documented behaviour):
  *   cost = 1/2 sum rho(|r|^2); corrector with rho'' <= 0: r~ = sqrt(rho') r, J~ = sqrt(rho') J;

@@ -138,3 +138,59 @@ def test_cull_points_matches_numpy(oracle):
     want = behind | (cnt < 3) | (mean > 1.0)
     assert np.array_equal(bad.astype(bool), want) and bad[5] == 1
     assert np.allclose(err[~behind], mean[~behind], rtol=1e-12)
+
+
+def test_jacobians_match_opencv_chain_rule(oracle):
+    """Third-party pin of row a1 (residual + 2x6 / 2x3 blocks): OpenCV's own analytic Jacobians.
+
+    The reference residual is  K * R(-w) (X - c)  (slam_core.cpp:705-726).  With rvec = -w, tvec = -R(rvec) c this is
+    cv2.projectPoints(X, rvec, tvec, K); OpenCV returns d(proj)/d(rvec), d(proj)/d(tvec), and cv2.Rodrigues returns dR/d(rvec).
+    Chain rule to the reference's parameters (w additive, c = camera centre):
+        d/dw = -( J_r + J_t * d(tvec)/d(rvec) ),  d(tvec)/d(rvec_i) = -(dR/d rvec_i) c,   d/dc = -J_t R,   d/dX = J_t R."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    K = scene.KITTI_K
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1.0]])
+    n = 40
+    cam = np.c_[rng.normal(0, 0.4, (n, 3)), rng.normal(0, 2.0, (n, 3))]
+    Rwc = scene.rodrigues(cam[:, :3])
+    pc = np.c_[rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(4, 30, n)]
+    X = np.einsum("nij,nj->ni", Rwc, pc) + cam[:, 3:]
+    u, v, _ = scene.project(cam, X, np.arange(n), np.arange(n), K)
+    prob = HostProblem(cam, X, np.arange(n), np.arange(n), u + 0.3, v - 0.2, K)
+    L = oracle.linearize(prob, 1e4, oracle.options(loss=0))
+    for i in range(n):
+        rvec = -cam[i, :3]
+        R, dR = cv2.Rodrigues(rvec.reshape(3, 1))          # dR: 3 x 9, row k = d vec(R) / d rvec_k
+        tvec = -R @ cam[i, 3:]
+        img, jac = cv2.projectPoints(X[i].reshape(1, 1, 3), rvec.reshape(3, 1), tvec.reshape(3, 1), Km, None)
+        assert np.allclose(img.ravel(), [u[i], v[i]], atol=1e-9)
+        Jr, Jt = jac[:, 0:3], jac[:, 3:6]
+        dt_dr = np.stack([-(dR[k].reshape(3, 3) @ cam[i, 3:]) for k in range(3)], axis=1)     # 3x3: column k = d tvec / d rvec_k
+        Jw = -(Jr + Jt @ dt_dr)
+        Jc = -Jt @ R
+        JX = Jt @ R
+        got_c, got_p = L.jac_cam[i], L.jac_pt[i]
+        scale = np.abs(got_c).max()
+        assert np.abs(got_c[:, :3] - Jw).max() < 1e-9 * scale, (i, np.abs(got_c[:, :3] - Jw).max())
+        assert np.abs(got_c[:, 3:] - Jc).max() < 1e-9 * scale
+        assert np.abs(got_p - JX).max() < 1e-9 * scale
+
+
+def test_pose_only_optimum_matches_opencv_pnp_refine(oracle):
+    """Without a robust loss pose_only_ba minimises the plain reprojection error: the optimum must coincide with
+    OpenCV's LM refinement of the same objective (cv2.solvePnPRefineLM), whatever path either solver takes."""
+    cv2 = pytest.importorskip("cv2")
+    cam0, X, uv, _ = scene.pose_only_scene(400, seed=11, outlier_frac=0.0)
+    K = scene.KITTI_K
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1.0]])
+    got, s = oracle.pose_only(cam0, X, uv, K, oracle.options(loss=0, function_tol=1e-15, parameter_tol=1e-14, max_iters=100))
+    assert s["termination"] == 0
+    R0 = scene.rodrigues(-cam0[:3])[0]
+    rvec, tvec = (-cam0[:3]).reshape(3, 1).copy(), (-R0 @ cam0[3:]).reshape(3, 1).copy()
+    rvec, tvec = cv2.solvePnPRefineLM(X.reshape(-1, 1, 3), uv.reshape(-1, 1, 2), Km, None, rvec, tvec,
+                                      criteria=(cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 200, 1e-15))
+    R = cv2.Rodrigues(rvec)[0]
+    c_cv = -R.T @ tvec.ravel()
+    w_cv = -rvec.ravel()
+    assert np.allclose(got[:3], w_cv, atol=2e-7) and np.allclose(got[3:], c_cv, atol=2e-6), (got, w_cv, c_cv)
