@@ -94,6 +94,7 @@ struct glba_ctx {
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
   Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
+  int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
   int n_tiles = 0, max_track = 0, grid_c = 0;
   Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
   bool has_dup = false;                                                              // some point is observed twice by one camera
@@ -308,10 +309,12 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ctx->has_dup = (ctx->h_flags[5] != 0);
   if (ctx->world > 1 && ctx->h_flags[6] != 0) return fail(ctx, GLBA_E_INVALID_ARG, "a rank holds an empty shard (%d of %d): every rank needs at least one observation", ctx->h_flags[6], ctx->world);
   ctx->max_track = ctx->h_flags[4];
-  ctx->use_tiles = (n > 0 && ctx->max_track <= TILE_OBS / 2);
+  ctx->opt = (n >= 400000) ? OPT_LARGE : OPT_SMALL;
+  if (ctx->max_track > NT_T * ctx->opt / 2) ctx->opt = OPT_LARGE;
+  ctx->use_tiles = (n > 0 && ctx->max_track <= NT_T * ctx->opt / 2);
   ctx->n_tiles = 0;
   if (ctx->use_tiles) {
-    const int B = TILE_OBS - ctx->max_track;
+    const int B = NT_T * ctx->opt - ctx->max_track;
     ctx->n_tiles = (int)((n + B - 1) / B);
     ENSURE(int, ctx->tile_pt, (size_t)ctx->n_tiles + 1);
     LAUNCH(k_tile_starts, cdiv(ctx->n_tiles + 1, 256), 256, ctx->n_tiles, B, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->tile_pt.as<int>());
@@ -407,12 +410,17 @@ void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, do
   const int c = ctx->cur;
   if (ctx->use_tiles) {
     static bool attr_set = false;
-    const size_t smem = (size_t)8 * TILE_OBS * sizeof(double);
-    if (!attr_set) { cudaFuncSetAttribute(k_linearize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_linearize_tile<<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(),
-           (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
-           ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
-           o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles));
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double)));
+      attr_set = true;
+    }
+    const size_t smem = (size_t)8 * NT_T * ctx->opt * sizeof(double);
+    const RedArgs RA = red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles);
+#define LIN_TILE_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
+    ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), \
+    ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), RA
+    if (ctx->opt == OPT_LARGE) k_linearize_tile<OPT_LARGE><<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(LIN_TILE_ARGS);
+    else k_linearize_tile<OPT_SMALL><<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(LIN_TILE_ARGS);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (ctx->n_tiles > kInKernelReduceMaxTiles)
       LAUNCH(k_reduce_rows<4>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 4, kLinSlots));
@@ -428,11 +436,13 @@ int pm_rows(const glba_ctx* ctx) { return ctx->use_tiles ? ctx->n_tiles : cdiv(c
 
 void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg, int li) {
   const int c = ctx->cur;
-  if (ctx->use_tiles)
-    LAUNCH(k_point_tile<0>, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(),
-           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), cg, li,
-           (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr,
-           RedArgs{});
+  if (ctx->use_tiles) {
+#define PT0_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
+    (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, \
+    (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr, RedArgs{}
+    if (ctx->opt == OPT_LARGE) LAUNCH((k_point_tile<0, OPT_LARGE>), ctx->n_tiles, NT_T, PT0_ARGS);
+    else LAUNCH((k_point_tile<0, OPT_SMALL>), ctx->n_tiles, NT_T, PT0_ARGS);
+  }
   else
     LAUNCH(k_point_pass<0>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
@@ -443,11 +453,13 @@ void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg,
 void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
   const int c = ctx->cur, d = c ^ 1;
   if (ctx->use_tiles) {
-    LAUNCH(k_point_tile<1>, ctx->n_tiles, NT_T, pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(),
-           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr, 0,
-           (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(),
-           (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(),
-           red_args(ctx, 5, kStepSlots, ctx->n_tiles <= kInKernelReduceMaxTiles));
+    const RedArgs RA = red_args(ctx, 5, kStepSlots, ctx->n_tiles <= kInKernelReduceMaxTiles);
+#define PT1_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
+    (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr, 0, \
+    (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(), \
+    (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), RA
+    if (ctx->opt == OPT_LARGE) LAUNCH((k_point_tile<1, OPT_LARGE>), ctx->n_tiles, NT_T, PT1_ARGS);
+    else LAUNCH((k_point_tile<1, OPT_SMALL>), ctx->n_tiles, NT_T, PT1_ARGS);
     if (ctx->n_tiles > kInKernelReduceMaxTiles)
       LAUNCH(k_reduce_rows<-1>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 5, kStepSlots));
   } else {

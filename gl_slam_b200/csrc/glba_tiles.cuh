@@ -14,11 +14,10 @@
 namespace glba {
 
 constexpr int NT_T = 256;
-#ifndef GLBA_OPT
-#define GLBA_OPT 4
-#endif
-constexpr int OPT = GLBA_OPT;            // observations per thread in phase 1
-constexpr int TILE_OBS = NT_T * OPT;     // tile capacity; ~TILE_OBS/track_len points keep phase 2 busy
+// Observations per thread in phase 1 (template parameter OPT): 4 for large maps (tile = 1024 observations, ~200 points:
+// phase 2 fills the CTA), 1 for small ones (tile = 256 observations: 4x more CTAs and a 4x shorter dependent chain per
+// thread — what matters when the whole map is a few tiles).
+constexpr int OPT_LARGE = 4, OPT_SMALL = 1;
 
 // The last CTA to finish folds the per-CTA partial rows [rows][5] into the scalar slots, in row order (fixed).
 // MAXCOL = column reduced with max (-1: none).  Saves a separate single-CTA reduction launch per pass.
@@ -94,11 +93,13 @@ struct TileArgs {
 };
 
 // K_A + point half of K_B, tiled.  Same outputs as k_linearize_pm.
+template <int OPT>
 __global__ void __launch_bounds__(NT_T)
 k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ pt, const double* __restrict__ camtab,
                  double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
                  double4* __restrict__ lam4, double* __restrict__ pblk, const int first, const int jacobi, const double min_diag,
                  const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+  constexpr int TILE_OBS = NT_T * OPT;
   extern __shared__ double dsm[];
   double (*val)[TILE_OBS] = reinterpret_cast<double (*)[TILE_OBS]>(dsm);     // [8][TILE_OBS]: J~p rows (3+3), r~ (2)
   __shared__ double sm[4 * NT_T / 32];
@@ -224,7 +225,7 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
 
 // Point-major half of the implicit product (MODE 0) / back-substitution + candidate cost (MODE 1), tiled.
 // xtab row of camera i: [xg(6) = T_i x_i | R_i (9) | sv_i (3)] — one contiguous 144-byte gather.
-template <int MODE>
+template <int MODE, int OPT>
 __global__ void __launch_bounds__(NT_T)
 k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_pm, const double* __restrict__ camtab,
              const double* __restrict__ xtab,
@@ -232,6 +233,7 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
              // MODE 1 only:
              const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
              const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+  constexpr int TILE_OBS = NT_T * OPT;
   __shared__ double val[3][TILE_OBS];
   __shared__ __align__(16) double xs[CWIN * XROW];                     // staged gather rows of cameras [cmin, cmin+CWIN)
   __shared__ __align__(16) double cs[MODE == 1 ? CWIN * CROW : 2];     // staged candidate rows (R, c)
