@@ -96,7 +96,7 @@ struct glba_ctx {
   bool use_tiles = false;
   int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
   int n_tiles = 0, max_track = 0, grid_c = 0;
-  Buf dn_part, dn_red;                                                               // dense path: per-CTA S copies, reduced S
+  Buf dn_part, dn_red, dn_full;                                                               // dense path: per-CTA S copies, reduced S
   bool has_dup = false;                                                              // some point is observed twice by one camera
   int dn_grid = 0, dn_ppc = 0;
   int cur = 0;
@@ -360,10 +360,10 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->cg_p, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_q, 6 * (size_t)n_cam); ENSURE(double, ctx->pg, 6 * (size_t)n_cam);
   ENSURE(double, ctx->yg, 6 * (size_t)n_cam); ENSURE(CgState, ctx->cgst, 1);
   if (n_cam <= DN_MAXCAM && n_cam > 0) {
-    ctx->dn_grid = std::max(1, std::min(148, cdiv(n_pt, 32)));
+    ctx->dn_grid = std::max(1, std::min(148, cdiv(n_pt, 16)));   // spread over all SMs; a CTA stages up to DN_TP points per barrier round
     ctx->dn_ppc = cdiv(n_pt, ctx->dn_grid);
     const size_t len = (size_t)(n_cam * (n_cam + 1) / 2) * 36 + 6 * (size_t)n_cam;
-    ENSURE(double, ctx->dn_part, len * ctx->dn_grid); ENSURE(double, ctx->dn_red, len);
+    ENSURE(double, ctx->dn_part, len * ctx->dn_grid); ENSURE(double, ctx->dn_red, len); ENSURE(double, ctx->dn_full, (size_t)36 * n_cam * n_cam + 6 * (size_t)n_cam);
   }
   CU(cudaMemsetAsync(ctx->yhat.p, 0, sizeof(double) * 6 * n_cam, s));
   CU(cudaMemsetAsync(ctx->acc27.p, 0, sizeof(double) * (54 * (size_t)n_cam + NSCAL), s));
@@ -621,24 +621,31 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
   static bool attr_set = false;
+  const int n = 6 * n_cam;
   const size_t sm_schur = (size_t)DN_TP * n_cam * 24 * sizeof(double) + DN_TP * sizeof(unsigned) + 2 * (size_t)(n_cam * (n_cam + 1) / 2) + 16;
-  const size_t sm_solve = ((size_t)(6 * n_cam) * ((6 * n_cam) | 1) + 12 * (size_t)n_cam) * sizeof(double) + 2 * (size_t)(n_cam * (n_cam + 1) / 2) + 16;
+  const size_t sm_solve = ((size_t)n * (n | 1) + 2 * (size_t)n) * sizeof(double);
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 1024)));
+    CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 2048)));
     CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
     attr_set = true;
   }
-  const int len = (n_cam * (n_cam + 1) / 2) * 36 + 6 * n_cam;
+  const int len = (n_cam * (n_cam + 1) / 2) * 36 + n;
   mark(ctx, PH_SCHUR);
   k_dense_schur<<<ctx->dn_grid, DN_NT, sm_schur, ctx->stream>>>(pm_args(ctx, o), n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(),
       (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->dn_ppc,
       ctx->dn_part.as<double>());
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  LAUNCH(k_dense_reduce, cdiv(len, 256), 256, ctx->dn_grid, len, (const double*)ctx->dn_part.as<double>(), ctx->dn_red.as<double>());
-  if (ctx->world > 1) AR(ctx->dn_red.as<double>(), (size_t)len, kNcclSum);
+#define DN_RED_ARGS n_cam, (const double*)ctx->dn_part.as<double>(), (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->Bc.as<double>(), \
+    (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->dn_red.as<double>(), ctx->dn_full.as<double>()
+  if (ctx->world > 1) {    // sum over this rank's CTAs, all-reduce the pair sums, then assemble
+    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, ctx->dn_grid, DN_RED_ARGS, 0);
+    AR(ctx->dn_red.as<double>(), (size_t)len, kNcclSum);
+    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, 0, DN_RED_ARGS, 1);
+  } else {
+    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, ctx->dn_grid, DN_RED_ARGS, 1);
+  }
   mark(ctx, PH_SOLVE);
-  k_dense_solve<<<1, DN_NS, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_red.as<double>(),
-      (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius,
+  k_dense_solve<<<1, DN_NS, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_full.as<double>(),
       ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->d_scal);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   mark(ctx, -1);
@@ -893,7 +900,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);

@@ -145,15 +145,25 @@ __device__ __forceinline__ bool finish_scalars(const double (&v)[NV], const bool
 // per-camera 27 partial sums: either already summed (acc27, sharded runs: all-reduced) or summed here from the chunk
 // partials in chunk order (single GPU: one launch less)
 template <bool FUSE>
-__device__ __forceinline__ void load_acc27(const int i, const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start,
-                                           const double* __restrict__ part27, double* a) {
+__device__ __forceinline__ void load_acc27(const int i, const int n_cam, const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start,
+                                           const double* __restrict__ part27, double* a, double (*stage)[27]) {
   if (FUSE) {
+    // the CTA's (camera, value) pairs are spread over all its threads, so a window of 10 cameras uses 64 lanes rather
+    // than 10; every sum still runs over the camera's chunks in chunk order (fixed)
+    const int cam0 = blockIdx.x * NT_C;
+    const int ncl = min(NT_C, n_cam - cam0);
+    for (int e = threadIdx.x; e < ncl * 27; e += NT_C) {
+      const int cl = e / 27, q = e - cl * 27;
+      double sacc = 0.0;
+      for (int ch = cam_chunk_start[cam0 + cl]; ch < cam_chunk_start[cam0 + cl + 1]; ++ch) sacc += part27[(size_t)27 * ch + q];
+      stage[cl][q] = sacc;
+    }
+    __syncthreads();
+    if (i < n_cam) {
 #pragma unroll
-    for (int q = 0; q < 27; ++q) a[q] = 0.0;
-    for (int ch = cam_chunk_start[i]; ch < cam_chunk_start[i + 1]; ++ch)
-#pragma unroll
-      for (int q = 0; q < 27; ++q) a[q] += part27[(size_t)27 * ch + q];
-  } else {
+      for (int q = 0; q < 27; ++q) a[q] = stage[threadIdx.x][q];
+    }
+  } else if (i < n_cam) {
 #pragma unroll
     for (int q = 0; q < 27; ++q) a[q] = acc27[(size_t)27 * i + q];
   }
@@ -168,8 +178,11 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
               double* part, unsigned* counter, double* scal) {
   __shared__ double sm[2 * NT_C / 32];
   __shared__ double smo[2];
+  __shared__ double stage[FUSE ? NT_C : 1][27];
   const int i = blockIdx.x * NT_C + threadIdx.x;
   double xn2 = 0.0, gmax = 0.0;
+  double a[27];
+  load_acc27<FUSE>(i, n_cam, acc27, cam_chunk_start, part27, a, stage);
   if (i < n_cam) {
     double* B = Bc + (size_t)36 * i;
     if (!cam_free[i]) {
@@ -178,8 +191,6 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
 #pragma unroll
       for (int q = 0; q < 6; ++q) { gc[6 * i + q] = 0.0; lamc[6 * i + q] = 0.0; if (first) sc[6 * i + q] = 1.0; }
     } else {
-      double a[27];
-      load_acc27<FUSE>(i, acc27, cam_chunk_start, part27, a);
       const double* ct = camtab + (size_t)CAMTAB * i;
       double G[9], R[9], Bl[36], gh[6], g6[6];
 #pragma unroll
@@ -218,8 +229,11 @@ k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const dou
                 double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal) {
   __shared__ double sm[NT_C / 32];
   __shared__ double smo[1];
+  __shared__ double stage[FUSE ? NT_C : 1][27];
   const int i = blockIdx.x * NT_C + threadIdx.x;
   double notpd = 0.0;
+  double a[27];
+  load_acc27<FUSE>(i, n_cam, acc27, cam_chunk_start, part27, a, stage);
   if (i < n_cam) {
     double* M = Md + (size_t)36 * i; double* Mi = Minv + (size_t)36 * i;
     if (!cam_free[i]) {
@@ -228,8 +242,6 @@ k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const dou
 #pragma unroll
       for (int q = 0; q < 6; ++q) rhs[6 * i + q] = 0.0;
     } else {
-      double a[27];
-      load_acc27<FUSE>(i, acc27, cam_chunk_start, part27, a);
       const double* ct = camtab + (size_t)CAMTAB * i;
       double G[9], R[9], Ml[36], Il[36], rh[6], r6[6];
 #pragma unroll

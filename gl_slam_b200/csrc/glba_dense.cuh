@@ -16,8 +16,8 @@ namespace glba {
 
 constexpr int DN_MAXCAM = 16;            // reduced dimension <= 96
 constexpr int DN_NT = 256;
-constexpr int DN_TP = 16;                // points staged per tile
-constexpr int DN_SLOTS = 16;             // track slots staged in parallel per point
+constexpr int DN_TP = 64;                // points staged per tile (64 x n_cam x 192 B of shared memory: 196 KB at 16 cameras)
+constexpr int DN_SLOTS = 4;              // threads that walk one point's track while staging
 constexpr int DN_PAIRS_PER_PASS = DN_NT / 36;                                                   // 7
 constexpr int DN_MAXQ = (DN_MAXCAM * (DN_MAXCAM + 1) / 2 + DN_PAIRS_PER_PASS - 1) / DN_PAIRS_PER_PASS;  // 20
 
@@ -142,12 +142,50 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
   if (tid < 6 * n_cam) out[(size_t)n_pairs * 36 + tid] = racc;
 }
 
-__global__ void k_dense_reduce(const int n_parts, const int len, const double* __restrict__ part, double* __restrict__ out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= len) return;
+// Sums the per-CTA copies in CTA order and emits the ASSEMBLED reduced system: S (n x n, row-major, symmetric, with
+// B + Lambda on the diagonal blocks and identity rows for non-free cameras) followed by rhs (n).
+__global__ void k_dense_reduce(const int n_parts, const int n_cam, const double* __restrict__ part, const uint8_t* __restrict__ cam_free,
+                               const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc,
+                               const double inv_radius, double* __restrict__ Sred /* pair sums (kept for the sharded all-reduce) */,
+                               double* __restrict__ Sfull /* n*n + n */, const int assemble) {
+  // 8 lanes per element: lane `sub` sums copies sub, sub+8, ... (8x shorter dependent load chains), the 8 partial sums
+  // are combined by a fixed xor butterfly, so the result is still order-deterministic
+  const int n_pairs = n_cam * (n_cam + 1) / 2;
+  const int len = n_pairs * 36 + 6 * n_cam;
+  const int sub = threadIdx.x & 7;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool valid = t < len;
   double s = 0.0;
-  for (int g = 0; g < n_parts; ++g) s += part[(size_t)g * len + t];
-  out[t] = s;
+  if (n_parts > 0) {
+    if (valid)
+      for (int g = sub; g < n_parts; g += 8) s += part[(size_t)g * len + t];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (valid && sub == 0) Sred[t] = s;
+  } else if (valid) {
+    s = Sred[t];          // already reduced (and all-reduced across ranks)
+  }
+  if (!valid || sub != 0) return;
+  if (!assemble) return;
+  const int n = 6 * n_cam;
+  if (t < n_pairs * 36) {
+    const int pr = t / 36, ent = t - pr * 36;
+    int i = 0, rem = pr;
+    while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
+    const int k = i + rem;
+    const int rr = ent / 6, cc = ent - rr * 6;
+    double v = -s;
+    const bool fi = cam_free[i] != 0, fk = cam_free[k] != 0;
+    if (i == k) {
+      if (fi) { v += Bc[(size_t)36 * i + rr * 6 + cc]; if (rr == cc) v += lamc[6 * i + rr] * inv_radius; }
+      else v = (rr == cc) ? 1.0 : 0.0;
+    } else if (!fi || !fk) v = 0.0;
+    Sfull[(size_t)(6 * i + rr) * n + 6 * k + cc] = v;
+    if (i != k) Sfull[(size_t)(6 * k + cc) * n + 6 * i + rr] = v;
+  } else {
+    const int r = t - n_pairs * 36;
+    Sfull[(size_t)n * n + r] = cam_free[r / 6] ? gc[r] - s : 0.0;
+  }
 }
 
 // One CTA: assemble S (n = 6 n_cam <= 96) in shared memory, Cholesky, solve S y = rhs.  Non-free cameras become
@@ -156,46 +194,21 @@ __global__ void k_dense_reduce(const int n_parts, const int len, const double* _
 // Row stride is odd (no shared-memory bank conflicts between rows).  Outputs y (cg_x layout), diagonal blocks, rhs.
 constexpr int DN_NS = 128;   // threads of the solve kernel (>= 6*DN_MAXCAM)
 __global__ void __launch_bounds__(DN_NS)
-k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ Sred /* pairs*36 + 6 n_cam */,
-              const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ Sfull /* n*n + n, assembled */,
               double* __restrict__ y, double* __restrict__ Md, double* __restrict__ rhs_out, double* __restrict__ scal) {
   extern __shared__ double dsm[];
   const int n = 6 * n_cam;
   const int ld = n | 1;
-  const int n_pairs = n_cam * (n_cam + 1) / 2;
   double* S = dsm;                       // n x ld, lower triangle is what the factorisation reads
   double* ys = S + (size_t)n * ld;       // n
-  double* dg = ys + n;                   // n: the original diagonal (S[j][j] itself is overwritten by thread j while others still need it)
-  unsigned char* pair_i = reinterpret_cast<unsigned char*>(dg + n);
-  unsigned char* pair_k = pair_i + n_pairs;
+  double* dg = ys + n;                   // n: 1/L[r][r]
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   if (tid == 0) s_bad = 0;
-  for (int p = tid; p < n_pairs; p += DN_NS) {
-    int i = 0, rem = p;
-    while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
-    pair_i[p] = (unsigned char)i; pair_k[p] = (unsigned char)(i + rem);
-  }
-  __syncthreads();
-  for (int t = tid; t < n_pairs * 36; t += DN_NS) {
-    const int pr = t / 36, ent = t - pr * 36;
-    const int i = pair_i[pr], k = pair_k[pr];
-    const int rr = ent / 6, cc = ent - rr * 6;
-    double v = -Sred[t];
-    const bool fi = cam_free[i] != 0, fk = cam_free[k] != 0;
-    if (i == k) {
-      if (fi) { v += Bc[(size_t)36 * i + rr * 6 + cc]; if (rr == cc) v += lamc[6 * i + rr] * inv_radius; }
-      else v = (rr == cc) ? 1.0 : 0.0;
-    } else if (!fi || !fk) v = 0.0;
-    S[(size_t)(6 * i + rr) * ld + 6 * k + cc] = v;
-    S[(size_t)(6 * k + cc) * ld + 6 * i + rr] = v;
-  }
+  for (int t = tid; t < n * n; t += DN_NS) { const int rr = t / n, cc = t - rr * n; S[(size_t)rr * ld + cc] = Sfull[t]; }
   const int r = tid;
   double b = 0.0;
-  if (r < n) {
-    b = cam_free[r / 6] ? gc[r] - Sred[(size_t)n_pairs * 36 + r] : 0.0;
-    rhs_out[r] = b;
-  }
+  if (r < n) { b = Sfull[(size_t)n * n + r]; rhs_out[r] = b; }
   __syncthreads();
   for (int t = tid; t < n_cam * 36; t += DN_NS) {
     const int i = t / 36, ent = t - i * 36, rr = ent / 6, cc = ent - rr * 6;
