@@ -36,7 +36,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 }
 namespace {
-constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values
 struct NcclApi {
   void* h = nullptr;
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -432,7 +432,6 @@ void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, do
     reduce_pm_partials(ctx, cdiv(ctx->n_pt, NT_PM), kLinSlots, 4);
   }
 }
-int pm_rows(const glba_ctx* ctx) { return ctx->use_tiles ? ctx->n_tiles : cdiv(ctx->n_pt, NT_PM); }
 
 void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg, int li) {
   const int c = ctx->cur;
@@ -524,7 +523,6 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   mark(ctx, -1);
   return GLBA_OK;
 }
-int do_linearize(glba_ctx* ctx, const glba_options* o, int first, double radius) { return do_linearize_impl(ctx, o, first, radius, false); }
 int do_linearize_schur(glba_ctx* ctx, const glba_options* o, int first, double radius) { return do_linearize_impl(ctx, o, first, radius, true); }
 
 // re-damp point blocks for a new radius (after a rejected / invalid step)

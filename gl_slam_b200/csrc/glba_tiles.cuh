@@ -46,7 +46,7 @@ __device__ __forceinline__ void last_block_reduce5(const double* part, const int
   }
   block_reduce<5, NT_T>(acc, sm, smo);
   if (threadIdx.x < 5 && (int)threadIdx.x != MAXCOL) scal[slots[threadIdx.x]] = smo[threadIdx.x];
-  if (MAXCOL >= 0) {
+  if constexpr (MAXCOL >= 0) {
     __syncthreads();
     block_reduce<1, NT_T, true>(mx, sm, smo);
     if (threadIdx.x == 0) scal[slots[MAXCOL]] = smo[0];
@@ -73,7 +73,7 @@ k_reduce_rows(const double* __restrict__ part, const int rows, double* __restric
   }
   block_reduce<5, NT_T>(acc, sm, smo);
   if (threadIdx.x < 5 && (int)threadIdx.x != MAXCOL) part2[(size_t)5 * blockIdx.x + threadIdx.x] = smo[threadIdx.x];
-  if (MAXCOL >= 0) {
+  if constexpr (MAXCOL >= 0) {
     __syncthreads();
     block_reduce<1, NT_T, true>(mx, sm, smo);
     if (threadIdx.x == 0) part2[(size_t)5 * blockIdx.x + MAXCOL] = smo[0];
