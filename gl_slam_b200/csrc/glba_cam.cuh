@@ -147,9 +147,19 @@ __device__ __forceinline__ bool finish_scalars(const double (&v)[NV], const bool
 template <bool FUSE>
 __device__ __forceinline__ void load_acc27(const int i, const int n_cam, const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start,
                                            const double* __restrict__ part27, double* a, double (*stage)[27]) {
-  if (FUSE) {
-    // the CTA's (camera, value) pairs are spread over all its threads, so a window of 10 cameras uses 64 lanes rather
-    // than 10; every sum still runs over the camera's chunks in chunk order (fixed)
+  if (FUSE && n_cam > 256) {
+    // many cameras: one thread per camera keeps every lane busy already (and measured faster than staging: 25 vs 43 us
+    // for both finalisers at 1 800 cameras)
+    if (i < n_cam) {
+#pragma unroll
+      for (int q = 0; q < 27; ++q) a[q] = 0.0;
+      for (int ch = cam_chunk_start[i]; ch < cam_chunk_start[i + 1]; ++ch)
+#pragma unroll
+        for (int q = 0; q < 27; ++q) a[q] += part27[(size_t)27 * ch + q];
+    }
+  } else if (FUSE) {
+    // few cameras: the CTA's (camera, value) pairs are spread over all its threads, so a window of 10 cameras uses 64
+    // lanes rather than 10; every sum still runs over the camera's chunks in chunk order (fixed)
     const int cam0 = blockIdx.x * NT_C;
     const int ncl = min(NT_C, n_cam - cam0);
     for (int e = threadIdx.x; e < ncl * 27; e += NT_C) {

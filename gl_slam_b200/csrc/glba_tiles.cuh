@@ -166,6 +166,11 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
   double xn2 = 0.0, gmax = 0.0, notpd = 0.0;
   for (int j = j0 + tid; j < j1; j += NT_T) {
     const int b = __ldg(A.pt_start + j) - k0, e = __ldg(A.pt_start + j + 1) - k0;
+    // the point's global operands are requested before the shared-memory summation so their latency hides behind it
+    const bool free_pt = A.pt_free[j] != 0;
+    const double4 Xp = ldg4(pt + j);
+    double4 s4 = make_double4(1.0, 1.0, 1.0, 0.0);
+    if (!first && free_pt) s4 = ldg4(sp4 + j);
     double C[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
     for (int m = b; m < e; ++m) {
       const double a0 = val[0][m], a1 = val[1][m], a2 = val[2][m], b0 = val[3][m], b1 = val[4][m], b2 = val[5][m];
@@ -179,7 +184,7 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
 #pragma unroll
     for (int q = 0; q < 3; ++q) Craw[(size_t)(6 + q) * A.n_pt + j] = g[q];
     double blk[PBLK];
-    if (A.pt_free[j]) {
+    if (free_pt) {
       const double h[3] = {C[0], C[3], C[5]};
       double s[3], lam[3];
       if (first) {
@@ -187,7 +192,6 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
         for (int q = 0; q < 3; ++q) s[q] = jacobi ? 1.0 / (1.0 + sqrt(h[q])) : 1.0;
         st4(sp4 + j, make_double4(s[0], s[1], s[2], 0.0));
       } else {
-        const double4 s4 = ldg4(sp4 + j);
         s[0] = s4.x; s[1] = s4.y; s[2] = s4.z;
       }
 #pragma unroll
@@ -197,8 +201,7 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
       }
       st4(lam4 + j, make_double4(lam[0], lam[1], lam[2], 0.0));
       if (!point_block(C, g, lam, inv_radius, blk)) notpd += 1.0;
-      const double4 X = ldg4(pt + j);
-      xn2 += X.x * X.x + X.y * X.y + X.z * X.z;
+      xn2 += Xp.x * Xp.x + Xp.y * Xp.y + Xp.z * Xp.z;
       gmax = fmax(gmax, fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2]))));
     } else {
 #pragma unroll
@@ -206,9 +209,10 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
       if (first) st4(sp4 + j, make_double4(1.0, 1.0, 1.0, 0.0));
       st4(lam4 + j, make_double4(0.0, 0.0, 0.0, 0.0));
     }
-    double* pb = pblk + (size_t)PBLK * j;
-#pragma unroll
-    for (int q = 0; q < PBLK; q += 2) *reinterpret_cast<double2*>(pb + q) = make_double2(blk[q], blk[q + 1]);
+    double4* pb = reinterpret_cast<double4*>(pblk + (size_t)PBLK * j);      // 96-byte row: three 256-bit stores
+    st4(pb, make_double4(blk[0], blk[1], blk[2], blk[3]));
+    st4(pb + 1, make_double4(blk[4], blk[5], blk[6], blk[7]));
+    st4(pb + 2, make_double4(blk[8], blk[9], blk[10], blk[11]));
   }
   double v[4] = {cost, xn2, bad, notpd};
   block_reduce<4, NT_T>(v, sm, smo);
