@@ -329,7 +329,30 @@ def main():
         for _ in range(20):
             _, sp = ctx3.pose_only(cam0, X, uv, scene.KITTI_K)
         dtp = (time.perf_counter() - t0) / 20
+        # C3 as GL-SLAM would run it: 200 frames, windows of 10 keyframes, stride 7 (28 sequentially dependent solves)
+        c3 = scene.config("C3")
+        def c3_windows(solver):
+            cam, pt = c3.cam.copy(), c3.pt.copy()
+            t_solve, iters, nobs = 0.0, 0, 0
+            for first in range(0, c3.n_cam - 10 + 1, 7):
+                in_win = (c3.obs_cam >= first) & (c3.obs_cam < first + 10)
+                keep = np.bincount(c3.obs_pt[in_win], minlength=c3.n_pt) >= 2
+                sel = in_win & keep[c3.obs_pt]
+                new_id = np.cumsum(keep) - 1
+                fixed = np.zeros(10, np.uint8); fixed[:2] = 1
+                sub = _abi.HostProblem(cam[first:first + 10], pt[keep], c3.obs_cam[sel] - first, new_id[c3.obs_pt[sel]], c3.obs_u[sel],
+                                       c3.obs_v[sel], c3.K, fixed)
+                t0 = time.perf_counter()
+                ref, ss = solver(sub)
+                t_solve += time.perf_counter() - t0
+                cam[first:first + 10] = ref.cam; pt[keep] = ref.pt
+                iters += ss["n_iters"]; nobs += sub.n_obs * ss["n_iters"]
+            return t_solve, iters, nobs
+        c3_windows(ctx3.solve)
+        c3_t, c3_it, c3_obs = c3_windows(ctx3.solve)
         window = {"workload": "C2 (10 keyframes, 5000 points, 20000 observations), glba_solve from host arrays", "solve_ms": dt * 1e3,
+                  "c3_sliding_windows": {"windows": len(range(0, c3.n_cam - 10 + 1, 7)), "solve_s": c3_t, "lm_iters": c3_it,
+                                         "lm_iters_per_s": c3_it / c3_t, "obs_x_iters_per_s": c3_obs / c3_t},
                   "lm_iters": s2["n_iters"], "lm_iters_per_s": s2["n_iters"] / dt, "obs_x_iters_per_s": c2.n_obs * s2["n_iters"] / dt,
                   "device_ms": {k: s2[k] for k in ("t_setup_ms", "t_linearize_ms", "t_schur_ms", "t_solve_ms", "t_update_ms")},
                   "pose_only_500pts_ms": dtp * 1e3, "pose_only_iters": sp["n_iters"], "pose_only_kernel_ms": sp["t_total_ms"]}
@@ -351,7 +374,12 @@ def main():
         t0 = time.perf_counter()
         _, so2 = oracle.solve(c2)
         dt2 = time.perf_counter() - t0
-        cpu = {"value": sub.n_obs / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+        c3w = None
+        if window is not None:
+            t0 = time.perf_counter()
+            o_t, o_it, o_obs = c3_windows(oracle.solve)
+            c3w = {"solve_s": o_t, "lm_iters": o_it, "lm_iters_per_s": o_it / o_t}
+        cpu = {"value": sub.n_obs / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "c3_sliding_windows": c3w,
                "window_C2_solve_ms": dt2 * 1e3, "window_C2_lm_iters": so2["n_iters"], "window_C2_lm_iters_per_s": so2["n_iters"] / dt2,
                "sample": f"{sub.n_obs} observations ({sub.n_pt} whole tracks) of {args.workload}, {reps} repetitions",
                "note": "restated CPU baseline (Ceres semantics), not libceres"}

@@ -67,6 +67,14 @@ struct Buf {
 };
 
 enum Phase { PH_SETUP = 0, PH_LIN, PH_SCHUR, PH_SOLVE, PH_UPDATE, PH_COUNT };
+
+struct EventPair {     // two CUDA events, destroyed on every exit path
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  EventPair(const EventPair&) = delete;
+  EventPair& operator=(const EventPair&) = delete;
+};
 }  // namespace
 
 struct glba_ctx {
@@ -406,12 +414,12 @@ const int kLinSlots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
 const int kStepSlots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
 
 // point-major half of a linearisation, INCLUDING the reduction of its scalars into d_scal
-void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
+int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
   const int c = ctx->cur;
   if (ctx->use_tiles) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double)));
+      CU(cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double))));
       attr_set = true;
     }
     const size_t smem = (size_t)8 * NT_T * ctx->opt * sizeof(double);
@@ -431,6 +439,7 @@ void launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, do
            o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
     reduce_pm_partials(ctx, cdiv(ctx->n_pt, NT_PM), kLinSlots, 4);
   }
+  return GLBA_OK;
 }
 
 void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg, int li) {
@@ -499,7 +508,7 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   with_schur = with_schur && ctx->n_free_cam > 0;
   mark(ctx, PH_LIN);
   const bool sharded = ctx->world > 1;
-  if (n_pt) launch_linearize_points(ctx, o, first, radius);
+  if (n_pt) { const int s__ = launch_linearize_points(ctx, o, first, radius); if (s__) return s__; }
   if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
   if (n_cam && sharded) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
@@ -977,7 +986,8 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
          0.0, 1 << 30, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->ev_used = 0;
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   const CmArgs CA = cm_args(ctx);
   auto timed = [&](auto&& launch, double* ms_out) -> int {
     launch();                                   // warm
@@ -989,7 +999,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
     *ms_out = ms / reps;
     return GLBA_OK;
   };
-  if ((st = timed([&] { launch_linearize_points(ctx, opt, 0, radius); }, &out->linearize_pm_ms))) return st;
+  if ((st = timed([&] { (void)launch_linearize_points(ctx, opt, 0, radius); }, &out->linearize_pm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            ctx->part_cm.as<double>()); }, &out->linearize_cm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
@@ -1010,7 +1020,6 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   st = timed([&] {
     launch_cam_lin_fin(ctx, opt, 0);
     launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>()); }, &out->small_kernels_ms);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return st;
 }
 
@@ -1128,7 +1137,8 @@ int glba_pose_only(glba_ctx* ctx, double* cam, int32_t n, const double* X, const
   if (st) return st;
   if (summary) std::memset(summary, 0, sizeof(*summary));
   cudaStream_t s = ctx->stream;
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   const int NI = GLBA_MAX_ITERS + 1;
   ENSURE(double, ctx->in_cam, 6); ENSURE(int, ctx->in_ocam, 2); ENSURE(double, ctx->in_pt, 3 * (size_t)n); ENSURE(double, ctx->in_u, 2 * (size_t)n);
   ENSURE(uint8_t, ctx->in_cfix, 1); ENSURE(int, ctx->in_opt, 3); ENSURE(double, ctx->in_v, 1);
@@ -1159,7 +1169,7 @@ int glba_pose_only(glba_ctx* ctx, double* cam, int32_t n, const double* X, const
     CU(cudaMemcpyAsync(acc.data(), ctx->out_b.p, NI, cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
-  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
   if (summary) {
     summary->n_iters = meta[0]; summary->termination = meta[1]; summary->stop_reason = meta[2];
     std::memcpy(summary->cost, &trace[0], sizeof(double) * NI); std::memcpy(summary->cost_candidate, &trace[NI], sizeof(double) * NI);

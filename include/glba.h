@@ -157,7 +157,8 @@ typedef struct {
   double gradient_max_norm[GLBA_MAX_ITERS + 1];
   int32_t cg_iters[GLBA_MAX_ITERS + 1];
   uint8_t accepted[GLBA_MAX_ITERS + 1];
-  /* device time, milliseconds, summed over the solve */
+  /* device time, milliseconds, summed over the solve.  The per-phase figures are recorded only for problems with
+   * >= 200 000 observations: below that the CUDA-event calls themselves rival the kernels and are skipped (fields = 0). */
   double t_setup_ms;             /* H2D + sort + index build */
   double t_linearize_ms;         /* residual/weight/Jacobian records + Hessian blocks */
   double t_schur_ms;             /* point-block inverses, preconditioner, reduced rhs */

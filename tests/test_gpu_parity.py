@@ -289,3 +289,38 @@ def test_long_tracks_use_fallback_kernels(ctx, oracle):
     got, s = ctx.solve(prob, g.options(**o))
     check_trajectory(s, so, rtol=1e-8)
     assert np.allclose(got.cam, ref.cam, rtol=1e-5, atol=1e-7) and np.allclose(got.pt, ref.pt, rtol=1e-5, atol=1e-7)
+
+
+def test_two_threads_two_contexts():
+    """GL-SLAM runs full_ba on the mapping thread while the tracking thread calls pose_only_ba
+    (thread_pool.cpp:74, 348): one context per thread, both in flight at once, results identical to running alone."""
+    import threading
+    win = scene.config("C2", scale=0.4)
+    cam0, X, uv, _ = scene.pose_only_scene(400, seed=9)
+    with g.Context(0) as a, g.Context(0) as b:
+        ref_win = a.solve(win)
+        ref_pose = b.pose_only(cam0, X, uv, scene.KITTI_K)
+        out = {"win": [], "pose": [], "err": []}
+
+        def mapping():
+            try:
+                for _ in range(6):
+                    out["win"].append(a.solve(win))
+            except Exception as e:      # pragma: no cover
+                out["err"].append(e)
+
+        def tracking():
+            try:
+                for _ in range(150):
+                    out["pose"].append(b.pose_only(cam0, X, uv, scene.KITTI_K))
+            except Exception as e:      # pragma: no cover
+                out["err"].append(e)
+
+        ts = [threading.Thread(target=mapping), threading.Thread(target=tracking)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not out["err"], out["err"]
+        for r, s in out["win"]:
+            assert s["cost"] == ref_win[1]["cost"] and np.array_equal(r.cam, ref_win[0].cam) and np.array_equal(r.pt, ref_win[0].pt)
+        for c, s in out["pose"]:
+            assert np.array_equal(c, ref_pose[0]) and s["n_iters"] == ref_pose[1]["n_iters"]
