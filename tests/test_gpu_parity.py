@@ -324,3 +324,40 @@ def test_two_threads_two_contexts():
             assert s["cost"] == ref_win[1]["cost"] and np.array_equal(r.cam, ref_win[0].cam) and np.array_equal(r.pt, ref_win[0].pt)
         for c, s in out["pose"]:
             assert np.array_equal(c, ref_pose[0]) and s["n_iters"] == ref_pose[1]["n_iters"]
+
+
+def test_control_flow_edge_cases(ctx, oracle):
+    """Loop guards and degenerate problems: same termination as the oracle, state untouched where nothing may move."""
+    prob = scene.make_scene(5, 60, 3, seed=21, rot_sigma=0.004, pos_sigma=0.03)
+    # max_iters = 0: evaluate only (NO_CONVERGENCE at the first loop guard)
+    got, s = ctx.solve(prob, g.options(max_iters=0))
+    ref, so = oracle.solve(prob, oracle.options(max_iters=0))
+    assert s["n_iters"] == so["n_iters"] == 0 and s["termination"] == so["termination"] == 1
+    assert np.array_equal(got.cam, prob.cam) and np.array_equal(got.pt, prob.pt)
+    assert abs(s["initial_cost"] - so["initial_cost"]) <= 1e-12 * so["initial_cost"]
+    # everything constant: no free parameter
+    allfix = HostProblem(prob.cam, prob.pt, prob.obs_cam, prob.obs_pt, prob.obs_u, prob.obs_v, prob.K, np.ones(5, np.uint8), np.ones(60, np.uint8))
+    got, s = ctx.solve(allfix)
+    assert np.array_equal(got.cam, prob.cam) and np.array_equal(got.pt, prob.pt) and s["termination"] != 2
+    # a single observation (one fixed camera, one free point: rank-2 block rescued by the LM diagonal)
+    one = HostProblem(prob.cam[:1], prob.pt[:1], [0], [0], prob.obs_u[:1], prob.obs_v[:1], prob.K, np.ones(1, np.uint8))
+    got, s = ctx.solve(one)
+    ref, so = oracle.solve(one)
+    assert s["termination"] == so["termination"] and abs(s["n_iters"] - so["n_iters"]) <= 2
+    assert s["final_cost"] <= max(1e-12, 1e-6 * s["initial_cost"])
+    # trust region pinned small: every step is tiny but valid; accept/reject sequence and radii must match exactly
+    tight = dict(initial_radius=1e-2, max_radius=1e-1, max_iters=12)
+    got, s = ctx.solve(prob, g.options(**tight))
+    ref, so = oracle.solve(prob, oracle.options(**tight))
+    check_trajectory(s, so)
+    assert max_rel(s["radius"], so["radius"]) < 1e-8
+    # gradient tolerance stop: a loose tolerance ends the loop before the first step is counted
+    got, s = ctx.solve(prob, g.options(gradient_tol=1e12))
+    ref, so = oracle.solve(prob, oracle.options(gradient_tol=1e12))
+    assert s["n_iters"] == so["n_iters"] == 0 and s["stop_reason"] == so["stop_reason"] == 2
+    # ... and the lagged read-back path: the tolerance is met only AFTER an accepted step
+    for gt in (50.0, 5.0, 0.5):
+        got, s = ctx.solve(prob, g.options(gradient_tol=gt))
+        ref, so = oracle.solve(prob, oracle.options(gradient_tol=gt))
+        assert (s["n_iters"], s["stop_reason"], s["termination"]) == (so["n_iters"], so["stop_reason"], so["termination"]), gt
+        assert np.allclose(got.cam, ref.cam, rtol=1e-6, atol=1e-9)
