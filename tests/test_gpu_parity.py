@@ -361,3 +361,23 @@ def test_control_flow_edge_cases(ctx, oracle):
         ref, so = oracle.solve(prob, oracle.options(gradient_tol=gt))
         assert (s["n_iters"], s["stop_reason"], s["termination"]) == (so["n_iters"], so["stop_reason"], so["termination"]), gt
         assert np.allclose(got.cam, ref.cam, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("n_pt", [3000, 120000])
+def test_arbitrary_point_numbering(ctx, oracle, n_pt):
+    """Map points numbered at random (not in creation order) over 100 cameras: every tile touches cameras far outside its
+    32-row shared-memory window, so the global-gather fallback of the tile kernels carries most of the work.
+    n_pt=3000 uses 256-observation tiles, n_pt=120000 (~600k observations) the 1024-observation tiles."""
+    prob = scene.make_scene(100, n_pt, lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=61, rot_sigma=0.002, pos_sigma=0.02,
+                            creation_order=False, loop=True)
+    o = dict(max_iters=5, cg_rel_tol=1e-13)
+    L = ctx.linearize(prob, 1e4, per_obs=False)
+    Lo = oracle.linearize(prob, 1e4, per_obs=False)
+    assert abs(L.cost - Lo.cost) <= 1e-12 * Lo.cost
+    for k in ("grad_cam", "grad_pt", "hess_cam", "hess_pt", "schur_rhs"):
+        assert rel_to_max(getattr(L, k), getattr(Lo, k)) < 1e-10, k
+    if n_pt <= 3000:
+        ref, so = oracle.solve(prob, oracle.options(**o))
+        got, s = ctx.solve(prob, g.options(**o))
+        check_trajectory(s, so, rtol=1e-8)
+        assert np.allclose(got.cam, ref.cam, rtol=1e-6, atol=1e-8)
