@@ -81,9 +81,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_scene(workload, scale):
+def build_scene(workload, scale, **kw):
     from gl_slam_b200 import scene
-    return scene.config(workload, scale=scale)
+    return scene.config(workload, scale=scale, **kw)
 
 
 def algorithmic_bytes(n_obs, n_pt, n_cam):
@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--ref-fraction", type=float, default=0.25, help="fraction of the map the CPU reference arm times per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lm-iters", type=int, default=6)
+    ap.add_argument("--random-point-ids", action="store_true", help="diagnostic: number the map points at random instead of in creation order")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every GPU owns a workload-sized arc of an N-times larger loop map (default); "
                          "strong = the fixed workload map sharded N ways")
@@ -182,7 +183,7 @@ def main():
         dist.all_reduce(tot)
         n_obs_total, n_pt_total, n_cam = int(tot[0]), int(tot[1]), prob.n_cam
     else:
-        full = build_scene(args.workload, args.scale)
+        full = build_scene(args.workload, args.scale, **({"creation_order": False} if args.random_point_ids else {}))
         n_obs_total, n_pt_total, n_cam = full.n_obs, full.n_pt, full.n_cam
         prob = scene.shard_by_point(full, world, rank)[0] if world > 1 else full
 

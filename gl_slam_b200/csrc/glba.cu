@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -100,6 +101,8 @@ struct glba_ctx {
   bool schur_fresh = false;                      // Schur pieces already built for the current linearisation and radius
   double* d_scal = nullptr;   // NSCAL doubles at the tail of acc27 (one all-reduce carries camera sums + scalars)
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
+  Buf first_cam, new2old, old2new, opt_relab;                                         // locality relabelling of the points
+  bool relabelled = false, allow_relabel = true, env_relabel = true;
   Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
   int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
@@ -245,9 +248,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->cam0, 6 * (size_t)n_cam); ENSURE(double4, ctx->pt40, n_pt);
   ctx->cur = 0;
   CU(cudaMemcpyAsync(ctx->cam[0].p, d_cam, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
-  if (n_pt) LAUNCH(k_pack_pt, cdiv(n_pt, 256), 256, n_pt, d_pt, ctx->pt4[0].as<double4>());
   CU(cudaMemcpyAsync(ctx->cam0.p, ctx->cam[0].p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(ctx->pt40.p, ctx->pt4[0].p, sizeof(double4) * n_pt, cudaMemcpyDeviceToDevice, s));
   // index buffers
   ENSURE(int, ctx->pm_cam, n); ENSURE(int, ctx->pm_pt, n); ENSURE(double2, ctx->pm_uv, n); ENSURE(int, ctx->pm2cm, n);
   ENSURE(int, ctx->pt_start, (size_t)n_pt + 1); ENSURE(int, ctx->cm_pt, n); ENSURE(double2, ctx->cm_uv, n); ENSURE(int, ctx->cm2pm, n);
@@ -264,6 +265,39 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   CU(cudaStreamSynchronize(s));
   if (ctx->h_flags[1] || ctx->h_flags[2]) return fail(ctx, GLBA_E_INVALID_ARG, "observation index out of range");
   ctx->sorted_input = (ctx->h_flags[0] == 0);
+  // ---- locality relabelling: the tile kernels stage a narrow window of cameras per tile and the camera-major gathers
+  // want neighbouring observations to touch neighbouring points, both of which hold when point ids are ordered by their
+  // first-observing camera (how GL-SLAM numbers map points).  If the caller's numbering is not like that (measured: 13 %
+  // slower steps, 1.9x slower point-major products on C4), renumber internally; results are mapped back on exit.
+  ctx->relabelled = false;
+  if (n > 0 && n_pt > 1 && ctx->allow_relabel && ctx->env_relabel) {
+    ENSURE(int, ctx->first_cam, n_pt);
+    LAUNCH(k_fill_int, cdiv(n_pt, 256), 256, n_pt, ctx->first_cam.as<int>(), 0x7fffffff);
+    LAUNCH(k_first_cam, gb, 256, n, d_ocam, d_opt, ctx->first_cam.as<int>());
+    CU(cudaMemsetAsync(ctx->flags.as<int>() + 7, 0, sizeof(int), s));
+    LAUNCH(k_count_descents, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->first_cam.as<int>(), ctx->flags.as<int>() + 7);
+    CU(cudaMemcpyAsync(ctx->h_flags + 7, ctx->flags.as<int>() + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (ctx->h_flags[7] > n_pt / 20) {
+      ENSURE(int, ctx->new2old, n_pt); ENSURE(int, ctx->old2new, n_pt); ENSURE(int, ctx->opt_relab, n);
+      int* iota_p = ctx->keys_tmp.as<int>();
+      int* keys_sorted = ctx->keys_tmp.as<int>() + n + 1;
+      LAUNCH(k_iota, cdiv(n_pt, 256), 256, (long)n_pt, iota_p);
+      size_t tmp_bytes = 0;
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->first_cam.as<int>(), keys_sorted, iota_p, ctx->new2old.as<int>(), n_pt, 0, 32, s));
+      ENSURE(char, ctx->sort_tmp, tmp_bytes);
+      CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->first_cam.as<int>(), keys_sorted, iota_p, ctx->new2old.as<int>(), n_pt, 0, 32, s));
+      g_launches.fetch_add(1);
+      LAUNCH(k_invert_perm, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->new2old.as<int>(), ctx->old2new.as<int>());
+      LAUNCH(k_relabel, gb, 256, n, d_opt, (const int*)ctx->old2new.as<int>(), ctx->opt_relab.as<int>());
+      d_opt = ctx->opt_relab.as<int>();
+      ctx->relabelled = true;
+      ctx->sorted_input = false;       // the relabelled observation list is re-sorted by (new) point below
+    }
+  }
+  const int* n2o = ctx->relabelled ? ctx->new2old.as<int>() : nullptr;
+  if (n_pt) LAUNCH(k_pack_pt, cdiv(n_pt, 256), 256, n_pt, d_pt, n2o, ctx->pt4[0].as<double4>());
+  CU(cudaMemcpyAsync(ctx->pt40.p, ctx->pt4[0].p, sizeof(double4) * n_pt, cudaMemcpyDeviceToDevice, s));
   int bits_pt = 1; while ((1L << bits_pt) < (long)n_pt + 1 && bits_pt < 31) ++bits_pt;
   int bits_cam = 1; while ((1L << bits_cam) < (long)n_cam + 1 && bits_cam < 31) ++bits_cam;
   int* iota = ctx->keys_tmp.as<int>();          // [0,n): iota / sorted keys scratch; [n,2n): keys out
@@ -303,7 +337,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   LAUNCH(k_counts, cdiv(n_cam + 2, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), (const int*)ctx->flags.as<int>() + 3, n > 0 ? 0 : 1, ctx->cam_cnt.as<int>());
   if (ctx->world > 1) { int s__ = allreduce(ctx, ctx->cam_cnt.p, (size_t)n_cam + 2, kNcclSum, kNcclInt32); if (s__) return s__; }
   if (n_cam) LAUNCH(k_free_flags_cnt, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_cnt.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
-  if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, ctx->pt_free.as<uint8_t>());
+  if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, n2o, ctx->pt_free.as<uint8_t>());
   ctx->has_dup = false;
   if (n > 0) LAUNCH(k_max_track, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->flags.as<int>() + 4);
   CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -806,12 +840,12 @@ int write_back(glba_ctx* ctx, double* cam, double* pt, int memspace) {
   cudaStream_t s = ctx->stream;
   if (memspace == GLBA_MEM_HOST) {
     ENSURE(double, ctx->out_a, 3 * (size_t)ctx->n_pt);
-    if (ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), ctx->out_a.as<double>());
+    if (ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), ctx->relabelled ? (const int*)ctx->new2old.as<int>() : nullptr, ctx->out_a.as<double>());
     if (cam) CU(cudaMemcpyAsync(cam, ctx->cam[c].p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToHost, s));
     if (pt) CU(cudaMemcpyAsync(pt, ctx->out_a.p, sizeof(double) * 3 * ctx->n_pt, cudaMemcpyDeviceToHost, s));
   } else {
     if (cam) CU(cudaMemcpyAsync(cam, ctx->cam[c].p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToDevice, s));
-    if (pt && ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), pt);
+    if (pt && ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), ctx->relabelled ? (const int*)ctx->new2old.as<int>() : nullptr, pt);
   }
   CU(cudaStreamSynchronize(s));
   return GLBA_OK;
@@ -883,6 +917,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) return GLBA_E_CUDA;
   glba_ctx* ctx = new glba_ctx();
   ctx->device = cfg->device; ctx->rank = cfg->rank; ctx->world = cfg->world;
+  if (const char* e = std::getenv("GLBA_RELABEL")) ctx->env_relabel = (e[0] != '0');   // diagnostic: GLBA_RELABEL=0 keeps the caller's point order
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GLBA_E_CUDA; } ctx->own_stream = true; }
   if (cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * NSCAL) != cudaSuccess || cudaMallocHost((void**)&ctx->h_cg, sizeof(CgState)) != cudaSuccess ||
@@ -907,7 +942,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1080,7 +1115,7 @@ int glba_linearize(glba_ctx* ctx, const glba_problem* prob, const glba_options* 
   if ((out->hess_pt || out->grad_pt) && n_pt > 0) {
     ENSURE(double, ctx->out_b, 9 * (size_t)n_pt); ENSURE(double, ctx->out_c, 3 * (size_t)n_pt);
     LAUNCH(k_unpack_pointblocks, cdiv(n_pt, 256), 256, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
-           ctx->out_b.as<double>(), ctx->out_c.as<double>());
+           ctx->relabelled ? (const int*)ctx->new2old.as<int>() : nullptr, ctx->out_b.as<double>(), ctx->out_c.as<double>());
     if (out->hess_pt) CU(cudaMemcpyAsync(out->hess_pt, ctx->out_b.p, sizeof(double) * 9 * n_pt, cudaMemcpyDeviceToHost, s));
     if (out->grad_pt) CU(cudaMemcpyAsync(out->grad_pt, ctx->out_c.p, sizeof(double) * 3 * n_pt, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -1189,7 +1224,9 @@ int glba_pose_only(glba_ctx* ctx, double* cam, int32_t n, const double* X, const
 int glba_cull_points(glba_ctx* ctx, const glba_problem* prob, int32_t min_obs, double max_mean_err, uint8_t* bad, double* mean_err) {
   if (!ctx || !bad) return GLBA_E_INVALID_ARG;
   CU(cudaSetDevice(ctx->device));
+  ctx->allow_relabel = false;            // one pass over the tracks: renumbering would cost more than it saves
   int st = load_problem(ctx, prob);
+  ctx->allow_relabel = true;
   if (st) return st;
   glba_options o; glba_default_options(&o);
   const int n_pt = ctx->n_pt;

@@ -841,11 +841,12 @@ __global__ void k_build_cm(const long n, const int* __restrict__ cm2pm, const in
   cm_uv[k] = pm_uv[o];
   pm2cm[o] = (int)k;
 }
-__global__ void k_free_flags(const int n, const int* __restrict__ start, const uint8_t* __restrict__ fixed, uint8_t* __restrict__ free_out) {
+__global__ void k_free_flags(const int n, const int* __restrict__ start, const uint8_t* __restrict__ fixed, const int* __restrict__ new2old,
+                             uint8_t* __restrict__ free_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool seen = start[i + 1] > start[i];
-  free_out[i] = (seen && !(fixed && fixed[i])) ? 1 : 0;
+  free_out[i] = (seen && !(fixed && fixed[new2old ? new2old[i] : i])) ? 1 : 0;
 }
 // cnt[i] = local observations of camera i; cnt[n_cam] = local duplicate flag (all-reduced by the host when sharded)
 __global__ void k_counts(const int n_cam, const int* __restrict__ cam_start, const int* __restrict__ dup_flag, const int empty,
@@ -859,25 +860,62 @@ __global__ void k_free_flags_cnt(const int n, const int* __restrict__ cnt, const
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) free_out[i] = (cnt[i] > 0 && !(fixed && fixed[i])) ? 1 : 0;
 }
-__global__ void k_pack_pt(const int n, const double* __restrict__ pt3, double4* __restrict__ pt4) {
+// Internal point j corresponds to the caller's point new2old[j] (nullptr = identity): see the locality relabelling
+// in load_problem.
+__global__ void k_pack_pt(const int n, const double* __restrict__ pt3, const int* __restrict__ new2old, double4* __restrict__ pt4) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) pt4[j] = make_double4(pt3[3 * j], pt3[3 * j + 1], pt3[3 * j + 2], 0.0);
+  if (j >= n) return;
+  const size_t o = new2old ? new2old[j] : j;
+  pt4[j] = make_double4(pt3[3 * o], pt3[3 * o + 1], pt3[3 * o + 2], 0.0);
 }
-__global__ void k_unpack_pt(const int n, const double4* __restrict__ pt4, double* __restrict__ pt3) {
+__global__ void k_unpack_pt(const int n, const double4* __restrict__ pt4, const int* __restrict__ new2old, double* __restrict__ pt3) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) { const double4 v = pt4[j]; pt3[3 * j] = v.x; pt3[3 * j + 1] = v.y; pt3[3 * j + 2] = v.z; }
+  if (j >= n) return;
+  const size_t o = new2old ? new2old[j] : j;
+  const double4 v = pt4[j]; pt3[3 * o] = v.x; pt3[3 * o + 1] = v.y; pt3[3 * o + 2] = v.z;
+}
+// first (smallest) camera index observing each point, from the caller's (possibly unsorted) observation list
+__global__ void k_first_cam(const long n, const int* __restrict__ obs_cam, const int* __restrict__ obs_pt, int* __restrict__ first_cam) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) atomicMin(first_cam + obs_pt[k], obs_cam[k]);
+}
+__global__ void k_fill_int(const int n, int* __restrict__ a, const int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+// number of points whose first camera is smaller than the previous observed point's (0 for creation-ordered ids)
+__global__ void k_count_descents(const int n, const int* __restrict__ first_cam, int* __restrict__ count) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > 0 && j < n && first_cam[j] < first_cam[j - 1]) atomicAdd(count, 1);
+}
+__global__ void k_invert_perm(const int n, const int* __restrict__ new2old, int* __restrict__ old2new) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) old2new[new2old[j]] = j;
+}
+__global__ void k_relabel(const long n, const int* __restrict__ obs_pt, const int* __restrict__ old2new, int* __restrict__ out) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = old2new[obs_pt[k]];
+}
+__global__ void k_scatter_u8(const int n, const uint8_t* __restrict__ in, const int* __restrict__ new2old, uint8_t* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[new2old ? new2old[j] : j] = in[j];
+}
+__global__ void k_scatter_f64(const int n, const double* __restrict__ in, const int* __restrict__ new2old, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[new2old ? new2old[j] : j] = in[j];
 }
 // Craw SoA (6 C + 3 g) -> explicit 3x3 / gradient in AoS for glba_linearize
 __global__ void k_unpack_pointblocks(const int n, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw,
-                                     double* __restrict__ hess /* 9 */, double* __restrict__ grad /* 3 */) {
+                                     const int* __restrict__ new2old, double* __restrict__ hess /* 9 */, double* __restrict__ grad /* 3 */) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  const size_t o = new2old ? new2old[j] : j;
   const bool f = pt_free[j] != 0;
   double C[6], g[3];
   for (int q = 0; q < 6; ++q) C[q] = f ? Craw[(size_t)q * n + j] : 0.0;
   for (int q = 0; q < 3; ++q) g[q] = f ? Craw[(size_t)(6 + q) * n + j] : 0.0;
-  if (hess) { double* H = hess + 9 * (size_t)j; H[0] = C[0]; H[1] = C[1]; H[2] = C[2]; H[3] = C[1]; H[4] = C[3]; H[5] = C[4]; H[6] = C[2]; H[7] = C[4]; H[8] = C[5]; }
-  if (grad) { grad[3 * (size_t)j] = g[0]; grad[3 * (size_t)j + 1] = g[1]; grad[3 * (size_t)j + 2] = g[2]; }
+  if (hess) { double* H = hess + 9 * o; H[0] = C[0]; H[1] = C[1]; H[2] = C[2]; H[3] = C[1]; H[4] = C[3]; H[5] = C[4]; H[6] = C[2]; H[7] = C[4]; H[8] = C[5]; }
+  if (grad) { grad[3 * o] = g[0]; grad[3 * o + 1] = g[1]; grad[3 * o + 2] = g[2]; }
 }
 
 // post_ba_map_point_culling arithmetic (slam_core.cpp:993-1035), one thread per point.

@@ -363,11 +363,16 @@ def test_control_flow_edge_cases(ctx, oracle):
         assert np.allclose(got.cam, ref.cam, rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize("relabel", ["1", "0"])
 @pytest.mark.parametrize("n_pt", [3000, 120000])
-def test_arbitrary_point_numbering(ctx, oracle, n_pt):
-    """Map points numbered at random (not in creation order) over 100 cameras: every tile touches cameras far outside its
-    32-row shared-memory window, so the global-gather fallback of the tile kernels carries most of the work.
+def test_arbitrary_point_numbering(oracle, n_pt, relabel, monkeypatch):
+    """Map points numbered at random (not in creation order) over 100 cameras.  relabel=1 (the default): the loader
+    renumbers the points by first-observing camera and maps every per-point output back.  relabel=0 (diagnostic
+    GLBA_RELABEL=0): every tile touches cameras far outside its 32-row shared-memory window, so the global-gather
+    fallback of the tile kernels carries most of the work.
     n_pt=3000 uses 256-observation tiles, n_pt=120000 (~600k observations) the 1024-observation tiles."""
+    monkeypatch.setenv("GLBA_RELABEL", relabel)
+    ctx = g.Context()
     prob = scene.make_scene(100, n_pt, lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=61, rot_sigma=0.002, pos_sigma=0.02,
                             creation_order=False, loop=True)
     o = dict(max_iters=5, cg_rel_tol=1e-13)
@@ -381,3 +386,12 @@ def test_arbitrary_point_numbering(ctx, oracle, n_pt):
         got, s = ctx.solve(prob, g.options(**o))
         check_trajectory(s, so, rtol=1e-8)
         assert np.allclose(got.cam, ref.cam, rtol=1e-6, atol=1e-8)
+        assert np.allclose(got.pt, ref.pt, rtol=1e-6, atol=1e-7)
+        # fixed points keep their caller-side identity through the renumbering
+        prob2 = prob.copy(); prob2.pt_fixed = (np.arange(n_pt) % 7 == 0).astype(np.uint8)
+        ref2, so2 = oracle.solve(prob2, oracle.options(**o))
+        got2, s2 = ctx.solve(prob2, g.options(**o))
+        check_trajectory(s2, so2, rtol=1e-8)
+        assert np.array_equal(got2.pt[::7], prob.pt[::7])
+        assert np.allclose(got2.pt, ref2.pt, rtol=1e-6, atol=1e-7)
+    ctx.close()
