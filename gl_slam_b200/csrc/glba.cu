@@ -365,7 +365,9 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   }
   ctx->grid_c = std::max(1, cdiv(n_cam, NT_C));
   long per = (n + 148L * 8 - 1) / (148L * 8);
-  int chunk = (int)std::min<long>(4096, std::max<long>(NT_CM, ((per + NT_CM - 1) / NT_CM) * NT_CM));
+  long chunk_cap = 4096;
+  if (const char* e = std::getenv("GLBA_CHUNK")) chunk_cap = std::max(256L, std::atol(e));    // diagnostic
+  int chunk = (int)std::min<long>(chunk_cap, std::max<long>(NT_CM, ((per + NT_CM - 1) / NT_CM) * NT_CM));
   std::vector<int> cc, cb, ce, ccs((size_t)n_cam + 1, 0);
   ctx->n_free_cam = 0;
   for (int i = 0; i < n_cam; ++i) {
@@ -545,20 +547,17 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   if (n_pt) { const int s__ = launch_linearize_points(ctx, o, first, radius); if (s__) return s__; }
   if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
-  if (n_cam && sharded) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                               (const double*)ctx->part_cm.as<double>(), ctx->d_accA, (const CgState*)nullptr, 0);
   if (with_schur) {
     mark(ctx, PH_SCHUR);
     if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                               (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
-    if (n_cam && sharded) LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
-                                 (const double*)ctx->part_cm2.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
   }
-  if (ctx->world > 1) {     // per-camera sums | cost, |x_p|^2, bad, notpd | per-rank gradient max slots
-    LAUNCH(k_gmax_scatter, 1, 32, ctx->rank, ctx->d_scal);
+  if (sharded) {     // one payload: per-camera sums | cost, |x_p|^2, bad, notpd | per-rank gradient max slots
+    LAUNCH(k_chunk_sum_lin, cdiv((long)n_cam * (with_schur ? 54 : 27), 256) + (n_cam ? 0 : 1), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
+           (const double*)ctx->part_cm.as<double>(), with_schur ? (const double*)ctx->part_cm2.as<double>() : (const double*)nullptr,
+           ctx->d_accA, ctx->d_accB, ctx->rank, ctx->d_scal);
     if (with_schur) AR(ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
-    LAUNCH(k_gmax_gather, 1, 32, ctx->world, ctx->d_scal);
   }
   if (n_cam) launch_cam_lin_fin(ctx, o, first);
   if (with_schur && n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
@@ -721,6 +720,11 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
 int fetch_scal(glba_ctx* ctx) {
   CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->world > 1) {        // max |g_point| over all ranks: one slot per rank in the all-reduced payload
+    double m = 0.0;
+    for (int r = 0; r < ctx->world; ++r) m = std::max(m, ctx->h_scal[S_GSLOT0 + r]);
+    ctx->h_scal[S_GMAX_P] = m;
+  }
   collect(ctx);
   return GLBA_OK;
 }
@@ -1055,6 +1059,12 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   st = timed([&] {
     launch_cam_lin_fin(ctx, opt, 0);
     launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>()); }, &out->small_kernels_ms);
+  if (st || ctx->world == 1) return st;
+  // collective: every rank calls glba_time_kernels with the same reps
+  if ((st = timed([&] { (void)allreduce(ctx, ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum); }, &out->allreduce_ms))) return st;
+  st = timed([&] {
+    LAUNCH(k_chunk_sum_lin, cdiv((long)n_cam * 54, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
+           (const double*)ctx->part_cm2.as<double>(), ctx->d_accA, ctx->d_accB, ctx->rank, ctx->d_scal); }, &out->chunk_sum_ms);
   return st;
 }
 

@@ -740,12 +740,22 @@ k_reduce_partials(const int rows, const int nv, const double* __restrict__ part,
   }
 }
 
-__global__ void k_gmax_scatter(const int rank, double* __restrict__ scal) {
-  const int i = threadIdx.x;
-  if (i < MAX_WORLD) scal[S_GSLOT0 + i] = (i == rank) ? scal[S_GMAX_P] : 0.0;
-}
-__global__ void k_gmax_gather(const int world, double* __restrict__ scal) {
-  if (threadIdx.x == 0) { double m = 0.0; for (int i = 0; i < world; ++i) m = fmax(m, scal[S_GSLOT0 + i]); scal[S_GMAX_P] = m; }
+// Sharded runs, one launch in front of the fused all-reduce of a linearisation: per-camera sums of the chunk partials of
+// k_linearize_cm (partA -> accA) and k_schur_cm (partB -> accB, may be null), and this rank's max |g_point| into its
+// own slot of the payload (a sum over ranks of one non-zero per slot; the host takes the max over the slots).
+__global__ void k_chunk_sum_lin(const int n_cam, const int* __restrict__ cam_chunk_start, const double* __restrict__ partA,
+                                const double* __restrict__ partB, double* __restrict__ accA, double* __restrict__ accB,
+                                const int rank, double* __restrict__ scal) {
+  if (blockIdx.x == 0 && threadIdx.x < MAX_WORLD) scal[S_GSLOT0 + threadIdx.x] = ((int)threadIdx.x == rank) ? scal[S_GMAX_P] : 0.0;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_cam * 27;
+  const double* part = partA;
+  double* acc = accA;
+  if (t >= n) { if (!partB || t >= 2 * n) return; t -= n; part = partB; acc = accB; }
+  const int cam = t / 27, q = t - cam * 27;
+  double s = 0.0;
+  for (int ch = cam_chunk_start[cam]; ch < cam_chunk_start[cam + 1]; ++ch) s += part[(size_t)27 * ch + q];
+  acc[t] = s;
 }
 
 // ---------------------------------------------------------------------------------------------

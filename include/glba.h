@@ -195,6 +195,8 @@ typedef struct {
   double backsub_cost_ms;   /* back-substitution + candidate cost */
   double point_damp_ms;     /* re-damping of the point blocks after a rejected step */
   double small_kernels_ms;  /* all camera-sized / reduction kernels of one linearise+Schur pass */
+  double allreduce_ms;      /* world > 1: the one fused NCCL all-reduce of a linearise+Schur pass ([accB|accA|scalars]) */
+  double chunk_sum_ms;      /* world > 1: the two per-camera chunk sums that feed it */
 } glba_kernel_times;
 
 void glba_default_options(glba_options* opt);
