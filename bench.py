@@ -364,9 +364,25 @@ def main():
             return t_solve, iters, nobs
         c3_windows(ctx3.solve)
         c3_t, c3_it, c3_obs = c3_windows(ctx3.solve)
+        # the same schedule on the persistent device-resident map (glba_map_*): no host packing, no upload per window
+        def c3_resident():
+            dm = g.DeviceMap(ctx3, c3.K)
+            dm.add_keyframes(c3.cam)
+            dm.add_points(c3.pt)
+            dm.add_observations(c3.obs_cam, c3.obs_pt, np.stack([c3.obs_u, c3.obs_v], axis=1))
+            t0 = time.perf_counter()
+            iters = 0
+            for first in range(0, c3.n_cam - 10 + 1, 7):
+                iters += dm.solve_window(first, 10, min_obs=2)["n_iters"]
+            t = time.perf_counter() - t0
+            dm.close()
+            return t, iters
+        c3_resident()
+        c3m_t, c3m_it = c3_resident()
         window = {"workload": "C2 (10 keyframes, 5000 points, 20000 observations), glba_solve from host arrays", "solve_ms": dt * 1e3,
                   "c3_sliding_windows": {"windows": len(range(0, c3.n_cam - 10 + 1, 7)), "solve_s": c3_t, "lm_iters": c3_it,
-                                         "lm_iters_per_s": c3_it / c3_t, "obs_x_iters_per_s": c3_obs / c3_t},
+                                         "lm_iters_per_s": c3_it / c3_t, "obs_x_iters_per_s": c3_obs / c3_t,
+                                         "resident_map_solve_s": c3m_t, "resident_map_lm_iters": c3m_it},
                   "lm_iters": s2["n_iters"], "lm_iters_per_s": s2["n_iters"] / dt, "obs_x_iters_per_s": c2.n_obs * s2["n_iters"] / dt,
                   "device_ms": {k: s2[k] for k in ("t_setup_ms", "t_linearize_ms", "t_schur_ms", "t_solve_ms", "t_update_ms")},
                   "pose_only_500pts_ms": dtp * 1e3, "pose_only_iters": sp["n_iters"], "pose_only_kernel_ms": sp["t_total_ms"]}

@@ -25,6 +25,9 @@ ABI_SYMBOLS = (
     "glba_linearize", "glba_load", "glba_linearize_resident", "glba_solve_resident", "glba_reset_resident",
     "glba_read_resident", "glba_synchronize", "glba_stream", "glba_cull_points", "glba_time_kernels",
     "glba_triangulate_filter",
+    "glba_map_create", "glba_map_destroy", "glba_map_size", "glba_map_add_keyframes", "glba_map_add_points",
+    "glba_map_add_observations", "glba_map_set_bad", "glba_map_write_keyframes", "glba_map_read_keyframes",
+    "glba_map_write_points", "glba_map_read_points", "glba_map_solve_window",
 )
 
 
@@ -78,6 +81,20 @@ def lib():
     L.glba_stream.restype = vp
     L.glba_cull_points.argtypes = [vp, C.POINTER(_abi.Problem), i32, f64, vp, vp]
     L.glba_triangulate_filter.argtypes = [vp, vp, vp, vp, vp, f64, f64, f64, f64, i32, vp, vp, f64, f64, vp, vp]
+    L.glba_map_create.argtypes = [vp, f64, f64, f64, f64, C.POINTER(vp)]
+    L.glba_map_destroy.argtypes = [vp]
+    L.glba_map_destroy.restype = None
+    L.glba_map_size.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_int64)]
+    L.glba_map_add_keyframes.argtypes = [vp, i32, vp, C.POINTER(i32)]
+    L.glba_map_add_points.argtypes = [vp, i32, vp, C.POINTER(i32)]
+    L.glba_map_add_observations.argtypes = [vp, i32, vp, vp, vp]
+    L.glba_map_set_bad.argtypes = [vp, i32, vp, C.c_uint8]
+    L.glba_map_write_keyframes.argtypes = [vp, i32, i32, vp]
+    L.glba_map_read_keyframes.argtypes = [vp, i32, i32, vp]
+    L.glba_map_write_points.argtypes = [vp, i32, i32, vp]
+    L.glba_map_read_points.argtypes = [vp, i32, i32, vp, vp]
+    L.glba_map_solve_window.argtypes = [vp, i32, i32, i32, i32, C.POINTER(_abi.Options), C.POINTER(_abi.Summary), C.POINTER(i32),
+                                        C.POINTER(C.c_int64)]
     _LIB = L
     return L
 
@@ -241,3 +258,91 @@ class Context:
                                     err.ctypes.data)
         self._check(st, "glba_cull_points")
         return bad, err
+
+
+class DeviceMap:
+    """glba_map: the persistent device-resident mirror of GL-SLAM's Map (keyframes, points, observation log).
+
+    Grown where the reference grows its map (slam_core.cpp:287-426); `solve_window` is full_ba (slam_core.cpp:744-883)
+    with the window selected and packed on the device."""
+
+    def __init__(self, ctx, K):
+        self._ctx = ctx                     # keeps the context alive: the map must go first
+        self._h = C.c_void_p()
+        st = lib().glba_map_create(ctx._h, *(float(k) for k in K), C.byref(self._h))
+        if st:
+            self._h = C.c_void_p()
+            ctx._check(st, "glba_map_create")
+
+    def close(self):
+        if self._h:
+            lib().glba_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int64()
+        self._ctx._check(lib().glba_map_size(self._h, C.byref(a), C.byref(b), C.byref(c)), "glba_map_size")
+        return a.value, b.value, c.value
+
+    def add_keyframes(self, cam):
+        cam = np.ascontiguousarray(cam, dtype=np.float64).reshape(-1, 6)
+        first = C.c_int32()
+        self._ctx._check(lib().glba_map_add_keyframes(self._h, len(cam), cam.ctypes.data, C.byref(first)), "glba_map_add_keyframes")
+        return first.value
+
+    def add_points(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        first = C.c_int32()
+        self._ctx._check(lib().glba_map_add_points(self._h, len(xyz), xyz.ctypes.data, C.byref(first)), "glba_map_add_points")
+        return first.value
+
+    def add_observations(self, kf, pt, uv):
+        kf = np.ascontiguousarray(kf, dtype=np.int32)
+        pt = np.ascontiguousarray(pt, dtype=np.int32)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        if not (len(kf) == len(pt) == len(uv)):
+            raise ValueError("observation arrays differ in length")
+        self._ctx._check(lib().glba_map_add_observations(self._h, len(kf), kf.ctypes.data, pt.ctypes.data, uv.ctypes.data),
+                         "glba_map_add_observations")
+
+    def set_bad(self, pt_ids, value=True):
+        ids = np.ascontiguousarray(pt_ids, dtype=np.int32)
+        self._ctx._check(lib().glba_map_set_bad(self._h, len(ids), ids.ctypes.data, 1 if value else 0), "glba_map_set_bad")
+
+    def write_keyframes(self, first, cam):
+        cam = np.ascontiguousarray(cam, dtype=np.float64).reshape(-1, 6)
+        self._ctx._check(lib().glba_map_write_keyframes(self._h, int(first), len(cam), cam.ctypes.data), "glba_map_write_keyframes")
+
+    def read_keyframes(self, first=0, n=None):
+        n = self.size()[0] - first if n is None else n
+        cam = np.zeros((n, 6))
+        self._ctx._check(lib().glba_map_read_keyframes(self._h, int(first), int(n), cam.ctypes.data), "glba_map_read_keyframes")
+        return cam
+
+    def write_points(self, first, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        self._ctx._check(lib().glba_map_write_points(self._h, int(first), len(xyz), xyz.ctypes.data), "glba_map_write_points")
+
+    def read_points(self, first=0, n=None):
+        n = self.size()[1] - first if n is None else n
+        xyz, bad = np.zeros((n, 3)), np.zeros(n, np.uint8)
+        self._ctx._check(lib().glba_map_read_points(self._h, int(first), int(n), xyz.ctypes.data, bad.ctypes.data), "glba_map_read_points")
+        return xyz, bad
+
+    def solve_window(self, first_kf, window, opt=None, n_fixed=2, min_obs=1):
+        """Returns the summary dict, with the window's size under 'n_pt' / 'n_obs'."""
+        opt = opt or options()
+        summ = _abi.Summary()
+        npt, nobs = C.c_int32(), C.c_int64()
+        st = lib().glba_map_solve_window(self._h, int(first_kf), int(window), int(n_fixed), int(min_obs), C.byref(opt), C.byref(summ),
+                                         C.byref(npt), C.byref(nobs))
+        self._ctx._check(st, "glba_map_solve_window")
+        d = summ.as_dict()
+        d["n_pt"], d["n_obs"] = npt.value, nobs.value
+        return d

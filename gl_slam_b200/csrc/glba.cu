@@ -1283,3 +1283,5 @@ int glba_triangulate_filter(glba_ctx* ctx, const double* R1, const double* t1, c
 }
 
 }  // extern "C"
+
+#include "glba_map.cuh"

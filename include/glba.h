@@ -256,6 +256,30 @@ int glba_triangulate_filter(glba_ctx* ctx, const double* R1, const double* t1, c
                             double fx, double fy, double cx, double cy, int32_t n, const double* p0, const double* p1,
                             double distance_threshold, double reprojection_threshold, double* X, uint8_t* keep);
 
+/* ---- Persistent device-resident map -------------------------------------------------------------------
+ * An append-only SoA mirror of slam_types.h:13-61 kept in HBM, so that a local BA no longer re-walks the host hash maps
+ * and re-uploads the window (slam_core.cpp:750-819).  Feed it where GL-SLAM grows its map
+ * (update_map_and_keyframe_data, slam_core.cpp:287-426): keyframe ids and point ids are the dense counters GL-SLAM
+ * already uses (run_window / next_point_id), handed back in *first_id.  One map per context, one GPU; host pointers.
+ * The map must be destroyed before its context. */
+typedef struct glba_map glba_map;
+int glba_map_create(glba_ctx* ctx, double fx, double fy, double cx, double cy, glba_map** out);
+void glba_map_destroy(glba_map* map);
+int glba_map_size(const glba_map* map, int32_t* n_kf, int32_t* n_pt, int64_t* n_obs);
+int glba_map_add_keyframes(glba_map* map, int32_t n, const double* cam /* [6n] camera-to-world (w, centre) */, int32_t* first_id);
+int glba_map_add_points(glba_map* map, int32_t n, const double* xyz /* [3n] */, int32_t* first_id);
+int glba_map_add_observations(glba_map* map, int32_t n, const int32_t* kf, const int32_t* pt, const double* uv /* [2n] u,v interleaved */);
+int glba_map_set_bad(glba_map* map, int32_t n, const int32_t* pt_ids, uint8_t value);   /* MapPoint::is_bad */
+int glba_map_write_keyframes(glba_map* map, int32_t first, int32_t n, const double* cam);   /* host edits, e.g. slam_core.cpp:916-973 */
+int glba_map_read_keyframes(glba_map* map, int32_t first, int32_t n, double* cam);
+int glba_map_write_points(glba_map* map, int32_t first, int32_t n, const double* xyz);
+int glba_map_read_points(glba_map* map, int32_t first, int32_t n, double* xyz, uint8_t* bad /* may be NULL */);
+/* full_ba (slam_core.cpp:744-883) on the resident map: keyframes [first_kf, first_kf+window), the first n_fixed constant
+ * (2 in the reference), all non-bad points with >= min_obs observations inside the window (reference: 1).  Refined poses
+ * and points are written into the map unless the solve FAILED.  n_pt_used / n_obs_used (may be NULL) = window size. */
+int glba_map_solve_window(glba_map* map, int32_t first_kf, int32_t window, int32_t n_fixed, int32_t min_obs,
+                          const glba_options* opt, glba_summary* summary, int32_t* n_pt_used, int64_t* n_obs_used);
+
 #ifdef __cplusplus
 }
 #endif

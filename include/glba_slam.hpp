@@ -211,6 +211,133 @@ inline bool full_ba(Backend& be, std::mutex& map_mutex, Map& map, const CameraMa
   return true;
 }
 
+// ---- persistent device-resident map (glba_map_*) ---------------------------------------------------------
+// Mirrors a Map into HBM incrementally, so that full_ba_resident() below does not repeat the packing walk of
+// slam_core.cpp:750-819 on every local BA.  Call sync() wherever the reference has just grown the map
+// (update_map_and_keyframe_data, slam_core.cpp:287-426).  Keyframe ids must be consecutive (they are: GL-SLAM numbers
+// keyframes with run_window); point ids are arbitrary.
+class ResidentMap {
+ public:
+  ResidentMap(Backend& be, const CameraMatrix& K) : be_(be) { if (be.ok()) glba_map_create(be.ctx(), K.fx, K.fy, K.cx, K.cy, &map_); }
+  ~ResidentMap() { if (map_) glba_map_destroy(map_); }
+  ResidentMap(const ResidentMap&) = delete;
+  ResidentMap& operator=(const ResidentMap&) = delete;
+  bool ok() const { return map_ != nullptr; }
+  glba_map* handle() const { return map_; }
+  int first_keyframe_id() const { return kf_base_; }
+  int device_point(int mpid) const { auto it = pt_index_.find(mpid); return it == pt_index_.end() ? -1 : it->second; }
+  const std::vector<int>& point_ids() const { return pt_ids_; }        // device point index -> map point id
+
+  // Appends the keyframes the device has not seen (ascending id), the points they observe that are new, every
+  // observation of the touched points not pushed before, and the touched points' is_bad flags.
+  bool sync(const Map& map) {
+    if (!map_) return false;
+    if (n_kf_ == 0) {
+      if (map.keyframes.empty()) return true;
+      kf_base_ = map.keyframes.begin()->first;
+      for (const auto& kv : map.keyframes) kf_base_ = std::min(kf_base_, kv.first);
+    }
+    std::vector<int> touched;
+    const int first_new = kf_base_ + n_kf_;
+    if (n_kf_ > 0) collect(map, first_new - 1, touched);     // a new keyframe also adds observations of the one before it (:386-405)
+    std::vector<double> cams;
+    int next = first_new;
+    for (auto it = map.keyframes.find(next); it != map.keyframes.end(); it = map.keyframes.find(++next)) {
+      double w[3];
+      rodrigues(it->second.R, w);
+      cams.insert(cams.end(), {w[0], w[1], w[2], it->second.t.v[0], it->second.t.v[1], it->second.t.v[2]});
+      collect(map, next, touched);
+    }
+    if (!cams.empty() && glba_map_add_keyframes(map_, (int32_t)(cams.size() / 6), cams.data(), nullptr) != GLBA_OK) return false;
+    n_kf_ += (int)(cams.size() / 6);
+    std::sort(touched.begin(), touched.end());
+    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+    std::vector<double> xyz, uv;
+    std::vector<int32_t> okf, opt, bad_ids, good_ids;
+    for (int mpid : touched) {
+      const MapPoint& mp = map.map_points.at(mpid);
+      auto ins = pt_index_.emplace(mpid, (int)pt_ids_.size());
+      if (ins.second) {
+        pt_ids_.push_back(mpid); pushed_.push_back(0); bad_.push_back(0);
+        xyz.insert(xyz.end(), {mp.position.x, mp.position.y, mp.position.z});
+      }
+      const int d = ins.first->second;
+      for (size_t k = pushed_[d]; k < mp.obs.size(); ++k) {
+        const Observation& o = mp.obs[k];
+        if (o.keyframe_id < kf_base_ || o.keyframe_id >= kf_base_ + n_kf_) return false;     // observation of an unknown keyframe
+        okf.push_back(o.keyframe_id - kf_base_); opt.push_back(d); uv.push_back(o.point2D.x); uv.push_back(o.point2D.y);
+      }
+      pushed_[d] = mp.obs.size();
+      if ((uint8_t)mp.is_bad != bad_[d]) { (mp.is_bad ? bad_ids : good_ids).push_back(d); bad_[d] = mp.is_bad ? 1 : 0; }
+    }
+    if (!xyz.empty() && glba_map_add_points(map_, (int32_t)(xyz.size() / 3), xyz.data(), nullptr) != GLBA_OK) return false;
+    if (!okf.empty() && glba_map_add_observations(map_, (int32_t)okf.size(), okf.data(), opt.data(), uv.data()) != GLBA_OK) return false;
+    if (!bad_ids.empty() && glba_map_set_bad(map_, (int32_t)bad_ids.size(), bad_ids.data(), 1) != GLBA_OK) return false;
+    if (!good_ids.empty() && glba_map_set_bad(map_, (int32_t)good_ids.size(), good_ids.data(), 0) != GLBA_OK) return false;
+    return true;
+  }
+
+  // is_bad flags set by the host since the last sync (post_ba_map_point_culling, slam_core.cpp:977-1038)
+  bool mark_bad(const std::vector<int>& mpids) {
+    std::vector<int32_t> ids;
+    for (int mpid : mpids) { const int d = device_point(mpid); if (d >= 0 && !bad_[d]) { ids.push_back(d); bad_[d] = 1; } }
+    return ids.empty() || glba_map_set_bad(map_, (int32_t)ids.size(), ids.data(), 1) == GLBA_OK;
+  }
+
+ private:
+  static void collect(const Map& map, int kfid, std::vector<int>& out) {
+    auto it = map.keyframes.find(kfid);
+    if (it != map.keyframes.end()) out.insert(out.end(), it->second.map_point_ids.begin(), it->second.map_point_ids.end());
+  }
+  Backend& be_;
+  glba_map* map_ = nullptr;
+  int kf_base_ = 0, n_kf_ = 0;
+  std::unordered_map<int, int> pt_index_;
+  std::vector<int> pt_ids_;
+  std::vector<size_t> pushed_;
+  std::vector<uint8_t> bad_;
+};
+
+// full_ba on the resident map: same window rule, fixed cameras, options and write-back as full_ba() above, but the
+// window is selected and packed on the device; the host only copies the refined window back into `map`.
+inline bool full_ba_resident(Backend& be, ResidentMap& rm, std::mutex& map_mutex, Map& map, int window, int run_window,
+                             std::mutex* tracking_mutex = nullptr, const glba_options* options = nullptr, glba_summary* summary = nullptr) {
+  if (!be.ok() || !rm.ok()) return false;
+  if ((int)map.keyframes.size() < window || window <= 1) return false;            // slam_core.cpp:746-749
+  const int first = run_window + 1 - window;
+  const int first_dev = first - rm.first_keyframe_id();
+  glba_options opt;
+  if (options) opt = *options; else glba_default_options(&opt);
+  glba_summary local;
+  glba_summary* s = summary ? summary : &local;
+  if (glba_map_solve_window(rm.handle(), first_dev, window, 2, 1, &opt, s, nullptr, nullptr) != GLBA_OK || s->termination == GLBA_TERM_FAILURE)
+    return false;
+  std::vector<double> cams(6 * (size_t)window);
+  if (glba_map_read_keyframes(rm.handle(), first_dev, window, cams.data()) != GLBA_OK) return false;
+  int lo = (int)rm.point_ids().size(), hi = -1;          // device range covering the window's points (ids are creation-ordered)
+  for (int i = first; i < first + window; ++i)
+    for (int mpid : map.keyframes.at(i).map_point_ids) { const int d = rm.device_point(mpid); if (d >= 0) { lo = std::min(lo, d); hi = std::max(hi, d); } }
+  std::vector<double> xyz;
+  std::vector<uint8_t> bad;
+  if (hi >= lo) {
+    xyz.resize(3 * (size_t)(hi - lo + 1)); bad.resize((size_t)(hi - lo + 1));
+    if (glba_map_read_points(rm.handle(), lo, hi - lo + 1, xyz.data(), bad.data()) != GLBA_OK) return false;
+  }
+  std::unique_lock<std::mutex> tl;
+  if (tracking_mutex) tl = std::unique_lock<std::mutex>(*tracking_mutex);
+  std::lock_guard<std::mutex> lk(map_mutex);
+  for (int i = 0; i < window; ++i) {
+    Frame& kf = map.keyframes[first + i];
+    rodrigues(&cams[6 * (size_t)i], kf.R);
+    kf.t.v[0] = cams[6 * i + 3]; kf.t.v[1] = cams[6 * i + 4]; kf.t.v[2] = cams[6 * i + 5];
+  }
+  for (int d = lo; d <= hi; ++d) {
+    if (bad[d - lo]) continue;
+    map.map_points[rm.point_ids()[d]].position = Point3d{xyz[3 * (size_t)(d - lo)], xyz[3 * (size_t)(d - lo) + 1], xyz[3 * (size_t)(d - lo) + 2]};
+  }
+  return true;
+}
+
 // Drop-in for slam_core::pose_only_ba (slam_core.cpp:1092-1140): R, t updated in place only on success.
 inline bool pose_only_ba(Backend& be, Mat33& R, Vec3& t, const std::vector<Point3d>& p3d, const std::vector<Point2d>& p2d,
                          const CameraMatrix& K, const glba_options* options = nullptr, glba_summary* summary = nullptr) {

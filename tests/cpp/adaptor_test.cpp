@@ -113,12 +113,33 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
-  if (mode == "solve") {
+  if (mode == "solve" || mode == "resident") {
     Backend be(0);
     if (!be.ok()) { std::cout << "nodevice " << be.status() << "\n"; return 3; }
     std::mutex map_mutex, tracking_mutex;
     glba_summary s;
-    const bool ok = full_ba(be, map_mutex, map, K, window, run_window, &tracking_mutex, nullptr, &s);
+    bool ok = false;
+    if (mode == "resident") {
+      // grow the mirror the way the mapping thread would: keyframe by keyframe, a sync after each
+      ResidentMap rm(be, K);
+      Map grown;
+      std::vector<int> kfids;
+      for (const auto& kv : map.keyframes) kfids.push_back(kv.first);
+      std::sort(kfids.begin(), kfids.end());
+      for (int kfid : kfids) {
+        grown.keyframes[kfid] = map.keyframes[kfid];
+        for (int mpid : map.keyframes[kfid].map_point_ids) {
+          MapPoint& g = grown.map_points[mpid];
+          const MapPoint& src = map.map_points[mpid];
+          g.id = src.id; g.position = src.position; g.is_bad = src.is_bad;
+          for (const Observation& o : src.obs) if (o.keyframe_id == kfid) g.obs.push_back(o);
+        }
+        if (!rm.sync(grown)) { std::cout << "FAIL sync\n"; return 1; }
+      }
+      ok = full_ba_resident(be, rm, map_mutex, map, window, run_window, &tracking_mutex, nullptr, &s);
+    } else {
+      ok = full_ba(be, map_mutex, map, K, window, run_window, &tracking_mutex, nullptr, &s);
+    }
     std::cout << (ok ? "ok " : "false ") << s.n_iters << " " << s.initial_cost << " " << s.final_cost << "\n";
     const int first = run_window + 1 - window;
     for (int i = first; i < first + window; ++i) {

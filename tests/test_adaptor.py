@@ -103,6 +103,25 @@ def test_full_ba_adaptor_matches_c_abi(exe, tmp_path, ctx, oracle):
 
 
 @pytest.mark.gpu
+def test_full_ba_resident_matches_full_ba(exe, tmp_path):
+    """ResidentMap + full_ba_resident (the map mirrored into HBM keyframe by keyframe, window packed on the device) must
+    leave the host Map exactly where full_ba (host packing) leaves it."""
+    prob = window_scene()
+    bad = np.zeros(prob.n_pt, bool)
+    bad[[3, 50]] = True
+    path = tmp_path / "scene.txt"
+    write_scene(path, prob, window=10, run_window=16, first=5, bad=bad)
+    a = subprocess.check_output([exe, "solve", str(path)]).decode().split("\n")
+    b = subprocess.check_output([exe, "resident", str(path)]).decode().split("\n")
+    assert a[0].split()[0] == b[0].split()[0] == "ok"
+    assert a[0].split()[1] == b[0].split()[1]                                         # iterations
+    for la, lb in zip(a[:12], b[:12]):
+        assert np.allclose(np.array(la.split()[1 if la.startswith("ok") else 0:], float),
+                           np.array(lb.split()[1 if lb.startswith("ok") else 0:], float), rtol=1e-9, atol=1e-12)
+    assert a[12:14] == b[12:14]                                                        # culling result
+
+
+@pytest.mark.gpu
 def test_pose_only_adaptor(exe, tmp_path, oracle):
     cam0, X, uv, _ = scene.pose_only_scene(400, seed=5)
     R = scene.rodrigues(cam0[:3])[0]
