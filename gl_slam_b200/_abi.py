@@ -22,6 +22,7 @@ TERM_CONVERGENCE, TERM_NO_CONVERGENCE, TERM_FAILURE = 0, 1, 2
 (STOP_NONE, STOP_MAX_ITERS, STOP_GRADIENT_TOL, STOP_PARAMETER_TOL, STOP_FUNCTION_TOL, STOP_MIN_RADIUS,
  STOP_INVALID_STEPS, STOP_NUMERIC) = range(8)
 MEM_HOST, MEM_DEVICE = 0, 1
+MODE_CERES, MODE_G2O = 0, 1
 
 _N = GLBA_MAX_ITERS + 1
 
@@ -48,7 +49,7 @@ class Options(C.Structure):
                 ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int32),
                 ("max_consecutive_invalid_steps", C.c_int32), ("linsolve", C.c_int32),
                 ("dense_max_dim", C.c_int32), ("cg_rel_tol", C.c_double), ("cg_max_iters", C.c_int32),
-                ("verbose", C.c_int32)]
+                ("verbose", C.c_int32), ("mode", C.c_int32), ("g2o_tau", C.c_double), ("g2o_max_trials", C.c_int32)]
 
 
 class Summary(C.Structure):

@@ -37,7 +37,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 }
 namespace {
-constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values
+constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclSum = 0, kNcclMax = 2;   // ncclDataType_t / ncclRedOp_t values
 struct NcclApi {
   void* h = nullptr;
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -103,6 +103,8 @@ struct glba_ctx {
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
   Buf first_cam, new2old, old2new, opt_relab;                                         // locality relabelling of the points
   bool relabelled = false, allow_relabel = true, env_relabel = true;
+  int mode = GLBA_MODE_CERES;                 // formulation the loaded problem's poses are in (glba_mode)
+  Buf hmax;                                   // GLBA_MODE_G2O: max Hessian diagonal (bit pattern of a double)
   Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
   int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
@@ -206,6 +208,8 @@ int validate_options(glba_ctx* ctx, const glba_options* o) {
   if (o->max_iters < 0 || o->max_iters > GLBA_MAX_ITERS) return fail(ctx, GLBA_E_INVALID_ARG, "max_iters out of [0,%d]", GLBA_MAX_ITERS);
   if (o->loss < GLBA_LOSS_NONE || o->loss > GLBA_LOSS_CAUCHY) return fail(ctx, GLBA_E_INVALID_ARG, "unknown loss");
   if (!(o->loss_scale > 0.0) || !(o->initial_radius > 0.0)) return fail(ctx, GLBA_E_INVALID_ARG, "loss_scale and initial_radius must be > 0");
+  if (o->mode != GLBA_MODE_CERES && o->mode != GLBA_MODE_G2O) return fail(ctx, GLBA_E_INVALID_ARG, "unknown mode");
+  if (o->mode == GLBA_MODE_G2O && (!(o->g2o_tau > 0.0) || o->g2o_max_trials < 1)) return fail(ctx, GLBA_E_INVALID_ARG, "g2o_tau must be > 0 and g2o_max_trials >= 1");
   return GLBA_OK;
 }
 
@@ -411,7 +415,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   }
   CU(cudaMemsetAsync(ctx->yhat.p, 0, sizeof(double) * 6 * n_cam, s));
   CU(cudaMemsetAsync(ctx->acc27.p, 0, sizeof(double) * (54 * (size_t)n_cam + NSCAL), s));
-  if (n_cam) LAUNCH(k_cam_prep, cdiv(n_cam, 128), 128, n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>());
+  if (n_cam) LAUNCH(k_cam_prep, cdiv(n_cam, 128), 128, n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>(), ctx->mode);
   mark(ctx, -1);
   ctx->loaded = true;
   return GLBA_OK;
@@ -707,7 +711,7 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
   if (n_cam) LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
                     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal);
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode);
   if (n_pt) launch_point_pass1(ctx, o, radius);
   if (ctx->world > 1) AR(ctx->d_scal + S_COST_C, 5, kNcclSum);
   mark(ctx, -1);
@@ -738,12 +742,42 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   int st;
   for (int q = 0; q < PH_COUNT; ++q) if (q != PH_SETUP) ctx->t_phase[q] = 0.0;
   sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_NONE;
-  double radius = o->initial_radius, decrease_factor = 2.0;
-  int n_invalid = 0;
+  // GLBA_MODE_G2O runs the same loop: with no Jacobi scaling and the LM diagonal clamped to [1, 1] the damping is
+  // lambda I with lambda = 1 / radius, and g2o's lambda update (x clamp(1-(2 rho-1)^3, 1/3, .) on accept; x nu, nu x 2 on
+  // reject) is the radius update below.  What differs: lambda0 from the Hessian diagonal, the +1e-3 guard in rho,
+  // acceptance on rho > 0, no tolerance / invalid-step tests, trials-per-iteration and iteration counting.
+  const bool g2o = (o->mode == GLBA_MODE_G2O);
+  if (g2o != (ctx->mode == GLBA_MODE_G2O)) return fail(ctx, GLBA_E_INVALID_ARG, "options.mode differs from the mode the problem was loaded with");
+  glba_options og;
+  if (g2o) {
+    og = *o;
+    og.jacobi_scaling = 0; og.min_lm_diagonal = 1.0; og.max_lm_diagonal = 1.0;
+    og.function_tol = 0.0; og.parameter_tol = 0.0; og.gradient_tol = 0.0; og.min_relative_decrease = 0.0;
+    og.min_radius = 0.0; og.max_radius = std::numeric_limits<double>::infinity();
+    o = &og;
+  }
+  double radius = g2o ? 1.0 : o->initial_radius, decrease_factor = 2.0;
+  int n_invalid = 0, n_rejected = 0;
   const bool dense = want_dense(ctx, o);
   if (o->linsolve == GLBA_LINSOLVE_DENSE && !dense && ctx->n_free_cam > 0)
     return fail(ctx, GLBA_E_UNSUPPORTED, "dense solve needs <= %d cameras and no duplicate (point,camera) observations", DN_MAXCAM);
-  if ((st = do_linearize_impl(ctx, o, 1, radius, !dense))) return st;
+  if ((st = do_linearize_impl(ctx, o, 1, radius, !dense && !g2o))) return st;
+  bool fresh = true;        // point blocks are damped for the current radius
+  if (g2o) {                // computeLambdaInit: lambda0 = tau * max diag H over the free vertices
+    ENSURE(unsigned long long, ctx->hmax, 1);
+    CU(cudaMemsetAsync(ctx->hmax.p, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->n_pt + ctx->n_cam > 0)
+      LAUNCH(k_hmax, cdiv((long)ctx->n_pt + ctx->n_cam, 256), 256, ctx->n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
+             ctx->n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->Bc.as<double>(), (const double*)ctx->camtab[ctx->cur].as<double>(),
+             ctx->hmax.as<unsigned long long>());
+    if (ctx->world > 1) AR(ctx->hmax.p, 1, kNcclMax);
+    double hm = 0.0;
+    CU(cudaMemcpyAsync(ctx->h_flags, ctx->hmax.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(&hm, ctx->h_flags, sizeof(double));
+    radius = (hm > 0.0) ? 1.0 / (o->g2o_tau * hm) : 0.0;
+    fresh = false; ctx->schur_fresh = false;
+  }
   if ((st = fetch_scal(ctx))) return st;
   const double* S = ctx->h_scal;
   if (S[S_BAD] > 0.0 || !std::isfinite(S[S_COST])) {
@@ -756,7 +790,6 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   double x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
   sum->initial_cost = cost; sum->cost[0] = cost; sum->cost_candidate[0] = cost; sum->radius[0] = radius; sum->gradient_max_norm[0] = gmax;
   int it = 0;
-  bool fresh = true;        // point blocks are damped for the current radius
   bool pending = false;     // a re-linearisation was enqueued whose scalars have not been read yet
   auto absorb_pending = [&]() {          // returns false on a non-finite re-linearisation
     pending = false;
@@ -765,10 +798,16 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     return true;
   };
   if (ctx->n_obs == 0 && ctx->world == 1) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
+  else if (g2o && !(radius > 0.0)) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }   // nothing free
   else for (;;) {
-    if (it >= o->max_iters) { sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_MAX_ITERS; break; }
-    if (!pending && gmax <= o->gradient_tol) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
-    if (radius <= o->min_radius) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_MIN_RADIUS; break; }
+    if (g2o) {
+      if (sum->n_successful >= o->max_iters) { sum->stop_reason = GLBA_STOP_MAX_ITERS; break; }
+      if (it >= GLBA_MAX_ITERS || !(radius > 0.0)) { sum->stop_reason = GLBA_STOP_TRIALS; break; }
+    } else {
+      if (it >= o->max_iters) { sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_MAX_ITERS; break; }
+      if (!pending && gmax <= o->gradient_tol) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
+      if (radius <= o->min_radius) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_MIN_RADIUS; break; }
+    }
     ++it;
     if (!fresh) { if ((st = do_redamp(ctx, radius))) return st; ctx->schur_fresh = false; }
     fresh = true;
@@ -785,11 +824,11 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
       // scalars of the linearisation that followed the previous accepted step arrived with this read-back
       if (!absorb_pending()) { --it; sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; break; }
       sum->cost[it - 1] = cost; sum->gradient_max_norm[it - 1] = gmax;
-      if (gmax <= o->gradient_tol) { --it; sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
+      if (!g2o && gmax <= o->gradient_tol) { --it; sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; break; }
     }
     const bool solver_ok = (S[S_NOTPD_P] + (ctx->n_free_cam > 0 ? S[S_NOTPD_C] : 0.0)) == 0.0;
     const double model_cost_change = 0.5 * ((S[S_YG_P] + S[S_YG_C]) + (S[S_YLY_P] + S[S_YLY_C]));
-    const bool valid = solver_ok && (model_cost_change > 0.0);
+    const bool valid = g2o || (solver_ok && (model_cost_change > 0.0));       // g2o: a failed solve is just a rejected trial
     if (o->verbose) fprintf(stderr, "[glba] it %d cost %.9e cand %.9e model %.3e radius %.3e cg %d\n", it, cost, S[S_COST_C], model_cost_change, radius, cg_it);
     if (!valid) {
       ++n_invalid;
@@ -802,19 +841,23 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     }
     n_invalid = 0;
     double cand = S[S_COST_C];
-    if (S[S_BAD_C] > 0.0 || !std::isfinite(cand)) cand = std::numeric_limits<double>::max();
+    if (S[S_BAD_C] > 0.0 || !std::isfinite(cand) || !solver_ok) cand = std::numeric_limits<double>::max();
     const double step_norm = std::sqrt(S[S_YN2_P] + S[S_YN2_C]);
     sum->cost_candidate[it] = cand; sum->step_norm[it] = step_norm; sum->cost[it] = cost; sum->radius[it] = radius; sum->gradient_max_norm[it] = gmax;
-    if (step_norm <= o->parameter_tol * (x_norm + o->parameter_tol)) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_PARAMETER_TOL; break; }
+    if (!g2o && step_norm <= o->parameter_tol * (x_norm + o->parameter_tol)) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_PARAMETER_TOL; break; }
     const double cost_change = cost - cand;
-    if (std::fabs(cost_change) <= o->function_tol * cost) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_FUNCTION_TOL; break; }
-    const double rel = (cand >= std::numeric_limits<double>::max()) ? std::numeric_limits<double>::lowest() : cost_change / model_cost_change;
+    if (!g2o && std::fabs(cost_change) <= o->function_tol * cost) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_FUNCTION_TOL; break; }
+    // g2o: rho = (chi2 - chi2') / (d'(lambda d + b) + 1e-3), here in half-chi2 units
+    const double rel = (cand >= std::numeric_limits<double>::max()) ? (g2o ? -1.0 : std::numeric_limits<double>::lowest())
+                                                                     : cost_change / (model_cost_change + (g2o ? 0.5e-3 : 0.0));
     sum->relative_decrease[it] = rel;
     if (rel > o->min_relative_decrease) {
       ctx->cur ^= 1;     // the candidate buffers (state + camera table) become current
-      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+      double shrink = 1.0 - std::pow(2.0 * rel - 1.0, 3);
+      if (g2o) shrink = std::min(shrink, 2.0 / 3.0);                 // _goodStepUpperScale
+      radius = radius / std::max(1.0 / 3.0, shrink);
       radius = std::min(o->max_radius, radius);
-      decrease_factor = 2.0;
+      decrease_factor = 2.0; n_rejected = 0;
       if ((st = do_linearize_impl(ctx, o, 0, radius, !dense))) return st;    // enqueued only: read back with the next step
       pending = true;
       cost = cand;       // provisional (the re-evaluated value replaces it at the next read-back)
@@ -823,8 +866,11 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     } else {
       radius = radius / decrease_factor; decrease_factor *= 2.0; fresh = false;
       sum->accepted[it] = 0;
+      ++n_rejected;
     }
     sum->cost[it] = cost; sum->radius[it] = radius; sum->gradient_max_norm[it] = gmax;
+    // g2o "Terminate": trials exhausted, a trial with rho == 0, or lambda no longer finite
+    if (g2o && !sum->accepted[it] && (n_rejected >= o->g2o_max_trials || rel == 0.0 || !(radius > 0.0))) { sum->stop_reason = GLBA_STOP_TRIALS; break; }
   }
   if (pending) {           // the loop ended right after an accepted step: fetch the scalars of its re-linearisation
     if ((st = fetch_scal(ctx))) return st;
@@ -881,6 +927,7 @@ void glba_default_options(glba_options* o) {
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1; o->max_consecutive_invalid_steps = 5;
   o->linsolve = GLBA_LINSOLVE_AUTO; o->dense_max_dim = 6 * DN_MAXCAM; o->cg_rel_tol = 1e-13; o->cg_max_iters = 0; o->verbose = 0;
+  o->mode = GLBA_MODE_CERES; o->g2o_tau = 1e-5; o->g2o_max_trials = 10;
 }
 
 const char* glba_strerror(int status) {
@@ -946,7 +993,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -970,6 +1017,7 @@ int glba_load(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt) 
   int st = validate_options(ctx, opt);
   if (st) return st;
   ctx->t_phase[PH_SETUP] = 0.0;
+  ctx->mode = opt->mode;
   st = load_problem(ctx, prob);
   if (st) return st;
   CU(cudaStreamSynchronize(ctx->stream));
@@ -983,7 +1031,7 @@ int glba_reset_resident(glba_ctx* ctx) {
   ctx->cur = 0;
   CU(cudaMemcpyAsync(ctx->cam[0].p, ctx->cam0.p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->pt4[0].p, ctx->pt40.p, sizeof(double4) * ctx->n_pt, cudaMemcpyDeviceToDevice, ctx->stream));
-  if (ctx->n_cam) LAUNCH(k_cam_prep, cdiv(ctx->n_cam, 128), 128, ctx->n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>());
+  if (ctx->n_cam) LAUNCH(k_cam_prep, cdiv(ctx->n_cam, 128), 128, ctx->n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>(), ctx->mode);
   return GLBA_OK;
 }
 
@@ -1051,7 +1099,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
          (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
          (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal);
+         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode);
   if ((st = timed([&] { launch_point_pass1(ctx, opt, radius); }, &out->backsub_cost_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_point_damp, cdiv(n_pt, NT_PM), NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
            (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms))) return st;
@@ -1086,6 +1134,7 @@ int glba_solve(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt,
   int st = validate_options(ctx, opt);
   if (st) { summary->status = st; return st; }
   ctx->t_phase[PH_SETUP] = 0.0;
+  ctx->mode = opt->mode;
   st = load_problem(ctx, prob);
   if (st) { summary->status = st; return st; }
   st = run_lm(ctx, opt, summary);
@@ -1103,6 +1152,8 @@ int glba_linearize(glba_ctx* ctx, const glba_problem* prob, const glba_options* 
   CU(cudaSetDevice(ctx->device));
   int st = validate_options(ctx, opt);
   if (st) return st;
+  if (opt->mode != GLBA_MODE_CERES) return fail(ctx, GLBA_E_UNSUPPORTED, "glba_linearize reports blocks in the CERES formulation only");
+  ctx->mode = GLBA_MODE_CERES;
   if ((st = load_problem(ctx, prob))) return st;
   for (int q = 0; q < PH_COUNT; ++q) ctx->t_phase[q] = 0.0;
   if ((st = do_linearize_schur(ctx, opt, 1, radius))) return st;
@@ -1234,6 +1285,7 @@ int glba_pose_only(glba_ctx* ctx, double* cam, int32_t n, const double* X, const
 int glba_cull_points(glba_ctx* ctx, const glba_problem* prob, int32_t min_obs, double max_mean_err, uint8_t* bad, double* mean_err) {
   if (!ctx || !bad) return GLBA_E_INVALID_ARG;
   CU(cudaSetDevice(ctx->device));
+  ctx->mode = GLBA_MODE_CERES;
   ctx->allow_relabel = false;            // one pass over the tracks: renumbering would cost more than it saves
   int st = load_problem(ctx, prob);
   ctx->allow_relabel = true;

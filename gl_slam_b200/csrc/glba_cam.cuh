@@ -451,7 +451,8 @@ k_cg_p(const int n_cam, const double* __restrict__ camtab, const double* __restr
 __global__ void __launch_bounds__(NT_C)
 k_cam_step2(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
             const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
-            double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ xtab, double* part, unsigned* counter, double* scal) {
+            double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ xtab, double* part, unsigned* counter, double* scal,
+            const int mode) {
   __shared__ double sm[3 * NT_C / 32];
   __shared__ double smo[3];
   const int i = blockIdx.x * NT_C + threadIdx.x;
@@ -463,11 +464,41 @@ k_cam_step2(const int n_cam, const uint8_t* __restrict__ cam_free, const double*
     for (int a = 0; a < 6; ++a) {
       yi[a] = f ? y[6 * i + a] : 0.0;
       cc[a] = cam[6 * i + a] - yi[a];
-      cam_c[6 * i + a] = cc[a];
       yn2 += yi[a] * yi[a]; ygd += yi[a] * gc[6 * i + a]; yly += lamc[6 * i + a] * inv_radius * yi[a] * yi[a];
     }
-    cam_table_row(cc, camtab_c + (size_t)CAMTAB * i);
-    write_xtab(xtab + (size_t)XTAB * i, camtab + (size_t)CAMTAB * i, yi);
+    const double* ct = camtab + (size_t)CAMTAB * i;
+    if (mode == 0) {
+      cam_table_row(cc, camtab_c + (size_t)CAMTAB * i);
+    } else if (!f) {              // constant vertex: state and table row carried over bit for bit
+#pragma unroll
+      for (int a = 0; a < 6; ++a) cc[a] = cam[6 * i + a];
+      for (int q = 0; q < CAMTAB; ++q) camtab_c[(size_t)CAMTAB * i + q] = ct[q];
+    } else {
+      // g2o oplus: the step is x = -y with dw = x_w, dv = -R x_t;  T <- exp([dw, dv]) T  (SE3Quat::exp: t' = V dv)
+      double dw[3], dv[3], dR[9], Rn[9], tn[3], B;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { dw[r] = -yi[r]; dv[r] = ct[r * 3] * yi[3] + ct[r * 3 + 1] * yi[4] + ct[r * 3 + 2] * yi[5]; }
+      so3_exp(dw, dR, &B);
+      const double th2 = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
+      double Cc;
+      if (th2 < 1e-8) Cc = 1.0 / 6.0 - th2 * (1.0 / 120.0) + th2 * th2 * (1.0 / 5040.0);
+      else { const double th = sqrt(th2); Cc = (th - sin(th)) / (th2 * th); }
+      const double a1[3] = {dw[1] * dv[2] - dw[2] * dv[1], dw[2] * dv[0] - dw[0] * dv[2], dw[0] * dv[1] - dw[1] * dv[0]};
+      const double a2[3] = {dw[1] * a1[2] - dw[2] * a1[1], dw[2] * a1[0] - dw[0] * a1[2], dw[0] * a1[1] - dw[1] * a1[0]};
+      const double* t = cam + 6 * i + 3;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = dR[r * 3] * ct[c] + dR[r * 3 + 1] * ct[3 + c] + dR[r * 3 + 2] * ct[6 + c];
+        tn[r] = dR[r * 3] * t[0] + dR[r * 3 + 1] * t[1] + dR[r * 3 + 2] * t[2] + dv[r] + B * a1[r] + Cc * a2[r];
+      }
+      so3_log(Rn, cc);
+      cc[3] = tn[0]; cc[4] = tn[1]; cc[5] = tn[2];
+      cam_table_row_Rt(Rn, tn, camtab_c + (size_t)CAMTAB * i);
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) cam_c[6 * i + a] = cc[a];
+    write_xtab(xtab + (size_t)XTAB * i, ct, yi);
   }
   const double v[3] = {yn2, ygd, yly};
   const bool mx[3] = {false, false, false};

@@ -305,9 +305,79 @@ __device__ inline void cam_table_row(const double* cam, double* ct) {
   ct[CT_SV] = sv[0]; ct[CT_SV + 1] = sv[1]; ct[CT_SV + 2] = sv[2];
 }
 
-__global__ void k_cam_prep(const int n_cam, const double* __restrict__ cam, double* __restrict__ camtab) {
+// ---- GLBA_MODE_G2O (world-to-camera SE(3), T <- exp([dw, dv]) T) --------------------------------------------------
+// The per-observation kernels only ever see the table row [R | c | G | sv] with p = R (X - c) and J~c = J^ blockdiag(G, R).
+// For g2o's left perturbation, d(obs - proj)/d[dw, dv] = J^ exactly, and (H + lambda I) is invariant under the orthogonal
+// change of variables  dw = x_w,  dv = -R x_t:  so the g2o system is solved in x with G = -I and the existing
+// translation block R, and the update maps x back (k_cam_step2).  R = exp([w_cw]x), c = -R' t.
+__device__ inline void so3_exp(const double* w, double* R, double* B_out) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double A, B;
+  if (th2 < 1e-8) { A = 1.0 - th2 * (1.0 / 6.0) + th2 * th2 * (1.0 / 120.0); B = 0.5 - th2 * (1.0 / 24.0) + th2 * th2 * (1.0 / 720.0); }
+  else { const double th = sqrt(th2); double sn, cs; sincos(th, &sn, &cs); A = sn / th; B = (1.0 - cs) / th2; }
+  const double x = w[0], y = w[1], z = w[2];
+  R[0] = 1.0 - B * (y * y + z * z); R[1] = -A * z + B * x * y;        R[2] = A * y + B * x * z;
+  R[3] = A * z + B * x * y;         R[4] = 1.0 - B * (x * x + z * z); R[5] = -A * x + B * y * z;
+  R[6] = -A * y + B * x * z;        R[7] = A * x + B * y * z;         R[8] = 1.0 - B * (x * x + y * y);
+  if (B_out) *B_out = B;
+}
+__device__ inline void so3_log(const double* R, double* w) {
+  double q0, q1, q2, q3;
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0.0) { const double s = sqrt(tr + 1.0) * 2.0; q0 = 0.25 * s; q1 = (R[7] - R[5]) / s; q2 = (R[2] - R[6]) / s; q3 = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0; q0 = (R[7] - R[5]) / s; q1 = 0.25 * s; q2 = (R[1] + R[3]) / s; q3 = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0; q0 = (R[2] - R[6]) / s; q1 = (R[1] + R[3]) / s; q2 = 0.25 * s; q3 = (R[5] + R[7]) / s; }
+  else { const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0; q0 = (R[3] - R[1]) / s; q1 = (R[2] + R[6]) / s; q2 = (R[5] + R[7]) / s; q3 = 0.25 * s; }
+  if (q0 < 0.0) { q0 = -q0; q1 = -q1; q2 = -q2; q3 = -q3; }
+  const double n = sqrt(q1 * q1 + q2 * q2 + q3 * q3);
+  const double k = (n < 1e-10) ? 2.0 / q0 : 2.0 * atan2(n, q0) / n;
+  w[0] = k * q1; w[1] = k * q2; w[2] = k * q3;
+}
+__device__ inline void cam_table_row_Rt(const double* R, const double* t, double* ct) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { ct[i] = R[i]; ct[CT_G + i] = (i % 4 == 0) ? -1.0 : 0.0; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) ct[CT_C + r] = -(R[r] * t[0] + R[3 + r] * t[1] + R[6 + r] * t[2]);
+  ct[CT_SV] = ct[CT_SV + 1] = ct[CT_SV + 2] = 0.0;
+}
+__device__ inline void cam_table_row_g2o(const double* cam, double* ct) {
+  double R[9];
+  so3_exp(cam, R, nullptr);
+  cam_table_row_Rt(R, cam + 3, ct);
+}
+
+__global__ void k_cam_prep(const int n_cam, const double* __restrict__ cam, double* __restrict__ camtab, const int mode) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_cam) cam_table_row(cam + 6 * i, camtab + (size_t)CAMTAB * i);
+  if (i >= n_cam) return;
+  if (mode) cam_table_row_g2o(cam + 6 * i, camtab + (size_t)CAMTAB * i);
+  else cam_table_row(cam + 6 * i, camtab + (size_t)CAMTAB * i);
+}
+
+// GLBA_MODE_G2O, computeLambdaInit: max over the free vertices of the Hessian diagonal in g2o's own coordinates
+// (points: diag C_j; cameras: rotation part diag B_ww, translation part diag(R B_tt R')).  Non-negative doubles order
+// like their bit patterns, so an integer atomicMax is exact and order-independent.
+__global__ void k_hmax(const int n_pt, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw, const int n_cam,
+                       const uint8_t* __restrict__ cam_free, const double* __restrict__ Bc, const double* __restrict__ camtab,
+                       unsigned long long* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (t < n_pt) {
+    if (pt_free[t]) m = fmax(Craw[t], fmax(Craw[(size_t)3 * n_pt + t], Craw[(size_t)5 * n_pt + t]));
+  } else if (t < n_pt + n_cam) {
+    const int i = t - n_pt;
+    if (cam_free[i]) {
+      const double* B = Bc + (size_t)36 * i;
+      const double* R = camtab + (size_t)CAMTAB * i;
+      m = fmax(B[0], fmax(B[7], B[14]));
+      for (int r = 0; r < 3; ++r) {
+        double d = 0.0;
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) d += R[r * 3 + a] * B[(3 + a) * 6 + 3 + b] * R[r * 3 + b];
+        m = fmax(m, d);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -295,6 +295,7 @@ int glba_map_solve_window(glba_map* m, int32_t first_kf, int32_t window, int32_t
   p.memspace = GLBA_MEM_DEVICE;
   cudaEventRecord(ev.b, s);
   ctx->t_phase[PH_SETUP] = 0.0;
+  ctx->mode = opt->mode;
   if ((st = load_problem(ctx, &p))) return summary->status = st;
   st = run_lm(ctx, opt, summary);
   summary->status = st;

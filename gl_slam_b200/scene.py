@@ -233,3 +233,25 @@ def shard_by_point(prob, world, rank):
                       prob.obs_v[sel], prob.K, prob.cam_fixed,
                       None if prob.pt_fixed is None else prob.pt_fixed[lo:hi])
     return sub, pt_index
+
+
+def to_world_to_camera(cam):
+    """[angle-axis of R_wc | centre] (the live Ceres path, slam_core.cpp:703-713) -> [angle-axis of R_cw | t] with
+    p = R_cw X + t (g2o VertexSE3Expmap, docs/old_unorganized/4image_pnp_ba.txt:350-357).  R_cw = R_wc', t = -R_cw c."""
+    cam = np.asarray(cam, float).reshape(-1, 6)
+    R_cw = np.transpose(rodrigues(cam[:, :3]), (0, 2, 1))
+    return np.concatenate([-cam[:, :3], -np.einsum("nij,nj->ni", R_cw, cam[:, 3:])], axis=1)
+
+
+def to_camera_to_world(cam):
+    """Inverse of to_world_to_camera."""
+    cam = np.asarray(cam, float).reshape(-1, 6)
+    R_cw = rodrigues(cam[:, :3])
+    return np.concatenate([-cam[:, :3], -np.einsum("nji,nj->ni", R_cw, cam[:, 3:])], axis=1)
+
+
+def as_g2o(prob):
+    """The same scene with poses in the GLBA_MODE_G2O convention."""
+    q = prob.copy()
+    q.cam = to_world_to_camera(prob.cam)
+    return q

@@ -74,8 +74,24 @@ typedef enum {
   GLBA_STOP_FUNCTION_TOL = 4,
   GLBA_STOP_MIN_RADIUS = 5,
   GLBA_STOP_INVALID_STEPS = 6,
-  GLBA_STOP_NUMERIC = 7
+  GLBA_STOP_NUMERIC = 7,
+  GLBA_STOP_TRIALS = 8           /* GLBA_MODE_G2O: g2o_max_trials rejected trials in a row, or a trial with rho == 0 ("Terminate") */
 } glba_stop_reason;
+
+/* Which of the reference's two BA formulations:
+ *  CERES — the live path, slam_core.cpp:699-849: cam = [angle-axis of R_wc | centre], additive update, residual =
+ *          projection - observation, Ceres trust-region LM (Jacobi scaling, D = sqrt(clamp(diag)/radius), tolerances).
+ *  G2O   — the archived path, Old/mult_img_recoverpose_single_ba:258-314, docs/old_unorganized/4image_pnp_ba.txt:321-430:
+ *          cam = [angle-axis of R_cw | t] WORLD-TO-CAMERA (VertexSE3Expmap), update T <- exp([dw, dv]) * T, error =
+ *          observation - projection with unit information, robust kernel as rho' reweighting, g2o's Levenberg: (H + lambda I),
+ *          lambda0 = g2o_tau * max diag H, rho = (chi2 - chi2') / (d'(lambda d + b) + 1e-3), accept on rho > 0 with
+ *          lambda *= clamp(1 - (2 rho - 1)^3, 1/3, 2/3), else lambda *= nu, nu *= 2, at most g2o_max_trials trials per
+ *          iteration; max_iters counts g2o iterations (= accepted steps), no tolerance stops.  In the summary every TRIAL
+ *          is one entry (radius[] = 1 / lambda), n_successful = completed g2o iterations.  The Ceres-only option fields
+ *          (tolerances, radii, lm diagonal bounds, jacobi_scaling, min_relative_decrease) are ignored.
+ *          Applies to glba_solve / glba_load + glba_solve_resident / glba_map_solve_window (a map holds poses in the
+ *          convention of the mode it is solved with); glba_linearize, pose-only BA and culling are CERES-convention only. */
+typedef enum { GLBA_MODE_CERES = 0, GLBA_MODE_G2O = 1 } glba_mode;
 
 typedef enum { GLBA_MEM_HOST = 0, GLBA_MEM_DEVICE = 1 } glba_memspace;
 
@@ -137,6 +153,9 @@ typedef struct {
   double cg_rel_tol;             /* PCG stop: sqrt(r'M^-1 r) <= tol * sqrt(r0'M^-1 r0); 1e-13 = parity mode */
   int32_t cg_max_iters;          /* 0 = 4*reduced dimension, capped at 4000 */
   int32_t verbose;
+  int32_t mode;                  /* glba_mode; GLBA_MODE_CERES */
+  double g2o_tau;                /* 1e-5  (OptimizationAlgorithmLevenberg::_tau) */
+  int32_t g2o_max_trials;        /* 10    (maxTrialsAfterFailure) */
 } glba_options;
 
 typedef struct {

@@ -338,6 +338,53 @@ inline bool full_ba_resident(Backend& be, ResidentMap& rm, std::mutex& map_mutex
   return true;
 }
 
+// ---- the archived g2o bundle adjustment (Old/mult_img_recoverpose_single_ba:251-326) --------------------------------
+// Same signature and semantics: world-to-camera poses (Rs_est[i], Ts_est[i]) as recoverPose chains them, camera 0 fixed,
+// every point free, unit information, no robust kernel, CameraParameters(fx, (cx, cy), 0) — one focal length —,
+// OptimizationAlgorithmLevenberg for `iterations` iterations (100 there; 50 in docs/old_unorganized/4image_pnp_ba.txt:420,
+// which also sets a Huber kernel: pass loss = GLBA_LOSS_HUBER, loss_scale = delta).  Runs GLBA_MODE_G2O.
+struct Observation2D { int camera_idx = 0; Point2d point2D; };
+struct Point3D { Point3d position; std::vector<Observation2D> observations; };
+
+inline bool bundleAdjustment(Backend& be, std::vector<Mat33>& Rs_est, std::vector<Vec3>& Ts_est, std::vector<Point3D>& points3D,
+                             const CameraMatrix& K, int iterations = 100, int loss = GLBA_LOSS_NONE, double loss_scale = 1.0,
+                             glba_summary* summary = nullptr) {
+  if (!be.ok() || Rs_est.size() != Ts_est.size() || Rs_est.empty()) return false;
+  const int n_cam = (int)Rs_est.size(), n_pt = (int)points3D.size();
+  std::vector<double> cams(6 * (size_t)n_cam), pts(3 * (size_t)n_pt), ou, ov;
+  std::vector<int32_t> oc, op;
+  for (int i = 0; i < n_cam; ++i) {
+    rodrigues(Rs_est[i], &cams[6 * (size_t)i]);
+    for (int r = 0; r < 3; ++r) cams[6 * (size_t)i + 3 + r] = Ts_est[i].v[r];
+  }
+  for (int j = 0; j < n_pt; ++j) {
+    pts[3 * (size_t)j] = points3D[j].position.x; pts[3 * (size_t)j + 1] = points3D[j].position.y; pts[3 * (size_t)j + 2] = points3D[j].position.z;
+    for (const Observation2D& o : points3D[j].observations) {
+      if (o.camera_idx < 0 || o.camera_idx >= n_cam) return false;
+      oc.push_back(o.camera_idx); op.push_back(j); ou.push_back(o.point2D.x); ov.push_back(o.point2D.y);
+    }
+  }
+  std::vector<uint8_t> fixed(n_cam, 0);
+  fixed[0] = 1;                                                      // "Fix first camera", :277
+  glba_problem p{};
+  p.n_cam = n_cam; p.n_pt = n_pt; p.n_obs = (int64_t)oc.size();
+  p.cam = cams.data(); p.pt = pts.data(); p.obs_cam = oc.data(); p.obs_pt = op.data(); p.obs_u = ou.data(); p.obs_v = ov.data();
+  p.cam_fixed = fixed.data(); p.pt_fixed = nullptr;
+  p.fx = K.fx; p.fy = K.fx; p.cx = K.cx; p.cy = K.cy; p.memspace = GLBA_MEM_HOST;      // single focal length, :294-295
+  glba_options opt;
+  glba_default_options(&opt);
+  opt.mode = GLBA_MODE_G2O; opt.max_iters = iterations; opt.loss = loss; opt.loss_scale = loss_scale;
+  glba_summary local;
+  glba_summary* s = summary ? summary : &local;
+  if (glba_solve(be.ctx(), &p, &opt, s) != GLBA_OK || s->termination == GLBA_TERM_FAILURE) return false;
+  for (int i = 0; i < n_cam; ++i) {
+    rodrigues(&cams[6 * (size_t)i], Rs_est[i]);
+    for (int r = 0; r < 3; ++r) Ts_est[i].v[r] = cams[6 * (size_t)i + 3 + r];
+  }
+  for (int j = 0; j < n_pt; ++j) points3D[j].position = Point3d{pts[3 * (size_t)j], pts[3 * (size_t)j + 1], pts[3 * (size_t)j + 2]};
+  return true;
+}
+
 // Drop-in for slam_core::pose_only_ba (slam_core.cpp:1092-1140): R, t updated in place only on success.
 inline bool pose_only_ba(Backend& be, Mat33& R, Vec3& t, const std::vector<Point3d>& p3d, const std::vector<Point2d>& p2d,
                          const CameraMatrix& K, const glba_options* options = nullptr, glba_summary* summary = nullptr) {

@@ -562,6 +562,89 @@ int pcg_solve(const View& V, const Lin& L, const Schur& sc, double tol, int max_
   return it;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// g2o formulation (GLBA_MODE_G2O): the archived BA of the reference, Old/mult_img_recoverpose_single_ba:258-314 and
+// docs/old_unorganized/4image_pnp_ba.txt:321-430 — VertexSE3Expmap / VertexSBAPointXYZ / EdgeProjectXYZ2UV with
+// OptimizationAlgorithmLevenberg.  g2o itself is absent from /root/reference; what follows restates its
+// published algorithm: world-to-camera pose T = (R, t), p = R X + t, error = observation - projection, update
+// T <- exp([dw, dv]) T with SE3Quat::exp (rotation-first 6-vector), closed-form Jacobians of
+// EdgeProjectXYZ2UV::linearizeOplus, robust kernels as rho' reweighting.
+// ---------------------------------------------------------------------------------------------------------------
+inline void so3_exp(const double w[3], double R[9], double* A_out = nullptr, double* B_out = nullptr) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double A, B;       // R = I + A [w]x + B [w]x^2
+  if (th2 < 1e-8) { A = 1.0 - th2 / 6.0 + th2 * th2 / 120.0; B = 0.5 - th2 / 24.0 + th2 * th2 / 720.0; }
+  else { const double th = std::sqrt(th2); A = std::sin(th) / th; B = (1.0 - std::cos(th)) / th2; }
+  const double x = w[0], y = w[1], z = w[2];
+  R[0] = 1.0 - B * (y * y + z * z); R[1] = -A * z + B * x * y;        R[2] = A * y + B * x * z;
+  R[3] = A * z + B * x * y;         R[4] = 1.0 - B * (x * x + z * z); R[5] = -A * x + B * y * z;
+  R[6] = -A * y + B * x * z;        R[7] = A * x + B * y * z;         R[8] = 1.0 - B * (x * x + y * y);
+  if (A_out) *A_out = A;
+  if (B_out) *B_out = B;
+}
+// exp of se(3): rotation exp([w]x), translation V v with V = I + B [w]x + C [w]x^2, C = (th - sin th)/th^3
+inline void se3_exp(const double d[6], double R[9], double t[3]) {
+  double B;
+  so3_exp(d, R, nullptr, &B);
+  const double th2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  double Cc;
+  if (th2 < 1e-8) Cc = 1.0 / 6.0 - th2 / 120.0 + th2 * th2 / 5040.0;
+  else { const double th = std::sqrt(th2); Cc = (th - std::sin(th)) / (th2 * th); }
+  const double* w = d; const double* v = d + 3;
+  const double wxv[3] = {w[1] * v[2] - w[2] * v[1], w[2] * v[0] - w[0] * v[2], w[0] * v[1] - w[1] * v[0]};
+  const double wxwxv[3] = {w[1] * wxv[2] - w[2] * wxv[1], w[2] * wxv[0] - w[0] * wxv[2], w[0] * wxv[1] - w[1] * wxv[0]};
+  for (int i = 0; i < 3; ++i) t[i] = v[i] + B * wxv[i] + Cc * wxwxv[i];
+}
+// log of a rotation matrix through its unit quaternion (stable for every angle in [0, pi])
+inline void so3_log(const double R[9], double w[3]) {
+  double q[4];   // w, x, y, z
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0.0) { const double s = std::sqrt(tr + 1.0) * 2.0; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { const double s = std::sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { const double s = std::sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
+  else { const double s = std::sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+  if (q[0] < 0.0) for (double& v : q) v = -v;
+  const double n = std::sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double k = (n < 1e-10) ? 2.0 / q[0] : 2.0 * std::atan2(n, q[0]) / n;
+  w[0] = k * q[1]; w[1] = k * q[2]; w[2] = k * q[3];
+}
+
+// poses as [R row-major 9 | t 3] per camera
+bool evaluate_g2o(const View& V, const double* Rt, const double* pt, int loss, double loss_a, double* cost_out, Lin* lin) {
+  const long n = V.n_obs;
+  if (lin) { lin->r.resize(2 * n); lin->jc.resize(12 * n); lin->jp.resize(6 * n); }
+  double cost = 0.0; int anybad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : cost) reduction(| : anybad)
+  for (long k = 0; k < n; ++k) {
+    const double* R = Rt + 12 * (long)V.obs_cam[k]; const double* t = R + 9;
+    const double* X = pt + 3 * (long)V.obs_pt[k];
+    const double x = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
+    const double y = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
+    const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
+    const double iz = 1.0 / z, iz2 = iz * iz;
+    const double e0 = V.obs_u[k] - (V.fx * x * iz + V.cx), e1 = V.obs_v[k] - (V.fy * y * iz + V.cy);
+    double rho[3]; loss_eval(loss, loss_a, e0 * e0 + e1 * e1, rho);
+    cost += 0.5 * rho[0];
+    if (!std::isfinite(e0) || !std::isfinite(e1)) anybad |= 1;
+    if (!lin) continue;
+    const double sq = std::sqrt(rho[1]);
+    lin->r[2 * k] = sq * e0; lin->r[2 * k + 1] = sq * e1;
+    // EdgeProjectXYZ2UV::linearizeOplus: d e / d X = -1/z [[fx,0,-fx x/z],[0,fy,-fy y/z]] R ;  d e / d [dw, dv]
+    const double P[6] = {V.fx * iz, 0.0, -V.fx * x * iz2, 0.0, V.fy * iz, -V.fy * y * iz2};
+    double* Jp = &lin->jp[6 * k]; double* Jc = &lin->jc[12 * k];
+    for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c)
+      Jp[r * 3 + c] = -sq * (P[r * 3] * R[c] + P[r * 3 + 1] * R[3 + c] + P[r * 3 + 2] * R[6 + c]);
+    Jc[0] = sq * (x * y * iz2 * V.fx);          Jc[1] = sq * (-(1.0 + x * x * iz2) * V.fx); Jc[2] = sq * (y * iz * V.fx);
+    Jc[3] = sq * (-iz * V.fx);                  Jc[4] = 0.0;                                Jc[5] = sq * (x * iz2 * V.fx);
+    Jc[6] = sq * ((1.0 + y * y * iz2) * V.fy);  Jc[7] = sq * (-x * y * iz2 * V.fy);         Jc[8] = sq * (-x * iz * V.fy);
+    Jc[9] = 0.0;                                Jc[10] = sq * (-iz * V.fy);                 Jc[11] = sq * (y * iz2 * V.fy);
+    for (int q = 0; q < 12; ++q) if (!std::isfinite(Jc[q])) anybad |= 1;
+  }
+  *cost_out = cost;
+  return !anybad && std::isfinite(cost);
+}
+
 struct Timer {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -576,6 +659,140 @@ bool use_dense(const glba_options& o, int nfc) {
 // Column scaling + LM diagonal + Schur + solve.  step (scaled space, = -y) for cams (6*n_cam) and points (3*n_pt).
 struct StepOut { std::vector<double> sc, sp; int cg_iters = 0; bool ok = true; };
 
+// OptimizationAlgorithmLevenberg::solve, run for o->max_iters iterations (SparseOptimizer::optimize(N) as called at
+// docs/old_unorganized/4image_pnp_ba.txt:419-420).  Every TRIAL is recorded as one summary entry.
+int solve_g2o(const glba_problem* p, const glba_options* o, glba_summary* sum) {
+  Timer ttotal;
+  std::memset(sum, 0, sizeof(*sum));
+  View V; int st = build_view(p, V); if (st) { sum->status = st; return st; }
+  const long n = V.n_obs;
+  std::vector<double> Rt((size_t)12 * V.n_cam), pt(p->pt, p->pt + (size_t)3 * V.n_pt);
+  for (int i = 0; i < V.n_cam; ++i) { so3_exp(p->cam + 6 * i, &Rt[12 * i]); for (int a = 0; a < 3; ++a) Rt[12 * i + 9 + a] = p->cam[6 * i + 3 + a]; }
+  std::vector<double> Rt_c(Rt), pt_c(pt);
+  Lin L; double cost;
+  if (!evaluate_g2o(V, Rt.data(), pt.data(), o->loss, o->loss_scale, &cost, &L)) {
+    sum->status = GLBA_E_NUMERIC; sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; return GLBA_E_NUMERIC; }
+  sum->n_linearizations = 1;
+  std::vector<double> gc, gp;          // J' r  (= -b)
+  auto gradient = [&]() {
+    gc.assign((size_t)6 * V.n_cam, 0.0); gp.assign((size_t)3 * V.n_pt, 0.0);
+    for (long k = 0; k < n; ++k) {
+      const int i = V.obs_cam[k], j = V.obs_pt[k];
+      const double* Jc = &L.jc[12 * k]; const double* Jp = &L.jp[6 * k]; const double* r = &L.r[2 * k];
+      if (V.cam_free[i]) for (int a = 0; a < 6; ++a) gc[6 * i + a] += Jc[a] * r[0] + Jc[6 + a] * r[1];
+      if (V.pt_free[j]) for (int a = 0; a < 3; ++a) gp[3 * j + a] += Jp[a] * r[0] + Jp[3 + a] * r[1];
+    }
+    double m = 0; for (double v : gc) m = std::max(m, std::fabs(v)); for (double v : gp) m = std::max(m, std::fabs(v)); return m; };
+  double gmax = gradient();
+  // computeLambdaInit: tau * max over the non-fixed vertices of the Hessian diagonal
+  double hmax = 0.0;
+  {
+    std::vector<double> dc((size_t)6 * V.n_cam, 0.0), dp((size_t)3 * V.n_pt, 0.0);
+    for (long k = 0; k < n; ++k) {
+      const int i = V.obs_cam[k], j = V.obs_pt[k];
+      for (int a = 0; a < 6; ++a) dc[6 * i + a] += L.jc[12 * k + a] * L.jc[12 * k + a] + L.jc[12 * k + 6 + a] * L.jc[12 * k + 6 + a];
+      for (int a = 0; a < 3; ++a) dp[3 * j + a] += L.jp[6 * k + a] * L.jp[6 * k + a] + L.jp[6 * k + 3 + a] * L.jp[6 * k + 3 + a];
+    }
+    for (int i = 0; i < V.n_cam; ++i) if (V.cam_free[i]) for (int a = 0; a < 6; ++a) hmax = std::max(hmax, dc[6 * i + a]);
+    for (int j = 0; j < V.n_pt; ++j) if (V.pt_free[j]) for (int a = 0; a < 3; ++a) hmax = std::max(hmax, dp[3 * j + a]);
+  }
+  double lambda = o->g2o_tau * hmax, nu = 2.0;
+  sum->initial_cost = cost; sum->cost[0] = cost; sum->cost_candidate[0] = cost; sum->radius[0] = lambda > 0 ? 1.0 / lambda : 0.0;
+  sum->gradient_max_norm[0] = gmax;
+  const bool dense = use_dense(*o, V.n_free_cam);
+  int n_free_params = 6 * V.n_free_cam; for (int j = 0; j < V.n_pt; ++j) n_free_params += 3 * V.pt_free[j];
+  int it = 0;
+  sum->termination = GLBA_TERM_NO_CONVERGENCE; sum->stop_reason = GLBA_STOP_NONE;
+  if (n_free_params == 0 || !(lambda > 0.0)) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
+  else for (;;) {
+    if (sum->n_successful >= o->max_iters) { sum->stop_reason = GLBA_STOP_MAX_ITERS; break; }
+    int n_rej = 0; bool terminate = false; double rho = 0.0;
+    do {                                                     // trials of one g2o iteration
+      if (it >= GLBA_MAX_ITERS) { terminate = true; break; }
+      ++it;
+      std::vector<double> Dc((size_t)6 * V.n_cam, std::sqrt(lambda)), Dp((size_t)3 * V.n_pt, std::sqrt(lambda));
+      Schur S; bool ok = build_schur(V, L, Dc, Dp, dense, S);
+      std::vector<double> yc((size_t)6 * V.n_free_cam, 0.0);
+      int cg_it = 0;
+      if (ok && V.n_free_cam > 0) {
+        if (dense) { yc = S.rhs; ok = cholesky_solve(S.S, 6 * V.n_free_cam, yc); }
+        else { int mi = o->cg_max_iters > 0 ? o->cg_max_iters : std::min(4000, 4 * 6 * V.n_free_cam);
+               cg_it = pcg_solve(V, L, S, o->cg_rel_tol, mi, yc); if (cg_it < 0) { ok = false; cg_it = 0; } }
+      }
+      sum->cg_iters[it] = cg_it;
+      std::vector<double> dc((size_t)6 * V.n_cam, 0.0), dp((size_t)3 * V.n_pt, 0.0);      // the update  d = -y
+      double cand = std::numeric_limits<double>::max(), scale = 0.0, sn = 0.0;
+      if (ok) {
+        for (int i = 0; i < V.n_cam; ++i) { const int sl = V.cam_slot[i]; if (sl < 0) continue;
+          for (int a = 0; a < 6; ++a) dc[6 * i + a] = -yc[6 * sl + a]; }
+        for (int j = 0; j < V.n_pt; ++j) {
+          if (!V.pt_free[j]) continue;
+          double t3[3] = {S.gp[3 * j], S.gp[3 * j + 1], S.gp[3 * j + 2]};
+          for (long t = V.trk_start[j]; t < V.trk_start[j + 1]; ++t) {
+            const long k = V.trk_obs[t]; const int sl = V.cam_slot[V.obs_cam[k]]; if (sl < 0) continue;
+            const double* Jc = &L.jc[12 * k]; const double* Jp = &L.jp[6 * k];
+            double a0 = 0, a1 = 0;
+            for (int a = 0; a < 6; ++a) { a0 += Jc[a] * yc[6 * sl + a]; a1 += Jc[6 + a] * yc[6 * sl + a]; }
+            for (int c = 0; c < 3; ++c) t3[c] -= Jp[c] * a0 + Jp[3 + c] * a1;
+          }
+          const double* Ci = &S.Cinv[(size_t)9 * j];
+          for (int a = 0; a < 3; ++a) dp[3 * j + a] = -(Ci[a * 3] * t3[0] + Ci[a * 3 + 1] * t3[1] + Ci[a * 3 + 2] * t3[2]);
+        }
+        // computeScale: sum d (lambda d + b), b = -J'r
+        for (int i = 0; i < V.n_cam; ++i) if (V.cam_free[i]) for (int a = 0; a < 6; ++a) { const double d = dc[6 * i + a]; scale += d * (lambda * d - gc[6 * i + a]); sn += d * d; }
+        for (int j = 0; j < V.n_pt; ++j) if (V.pt_free[j]) for (int a = 0; a < 3; ++a) { const double d = dp[3 * j + a]; scale += d * (lambda * d - gp[3 * j + a]); sn += d * d; }
+        // oplus: T <- exp(d) T ; X <- X + d
+        for (int i = 0; i < V.n_cam; ++i) {
+          if (!V.cam_free[i]) { std::memcpy(&Rt_c[12 * i], &Rt[12 * i], 12 * sizeof(double)); continue; }
+          double dR[9], dt[3];
+          se3_exp(&dc[6 * i], dR, dt);
+          const double* R = &Rt[12 * i]; const double* t = R + 9; double* Rn = &Rt_c[12 * i];
+          for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = dR[r * 3] * R[c] + dR[r * 3 + 1] * R[3 + c] + dR[r * 3 + 2] * R[6 + c];
+            Rn[9 + r] = dR[r * 3] * t[0] + dR[r * 3 + 1] * t[1] + dR[r * 3 + 2] * t[2] + dt[r];
+          }
+        }
+        for (int j = 0; j < V.n_pt; ++j) for (int a = 0; a < 3; ++a) pt_c[3 * j + a] = pt[3 * j + a] + (V.pt_free[j] ? dp[3 * j + a] : 0.0);
+        if (!evaluate_g2o(V, Rt_c.data(), pt_c.data(), o->loss, o->loss_scale, &cand, nullptr)) cand = std::numeric_limits<double>::max();
+      }
+      // rho = (chi2 - chi2') / (scale + 1e-3), in half-chi2 units
+      rho = (cand >= std::numeric_limits<double>::max()) ? -1.0 : (cost - cand) / (0.5 * scale + 0.5e-3);
+      sum->cost_candidate[it] = cand; sum->step_norm[it] = std::sqrt(sn); sum->relative_decrease[it] = rho;
+      if (rho > 0.0 && std::isfinite(cand)) {
+        Rt = Rt_c; pt = pt_c;
+        if (!evaluate_g2o(V, Rt.data(), pt.data(), o->loss, o->loss_scale, &cost, &L)) {
+          sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; terminate = true; }
+        gmax = gradient();
+        sum->n_linearizations++; sum->n_successful++; sum->accepted[it] = 1;
+        const double alpha = std::min(1.0 - std::pow(2.0 * rho - 1.0, 3), 2.0 / 3.0);
+        lambda *= std::max(1.0 / 3.0, alpha);
+        nu = 2.0;
+      } else {
+        lambda *= nu; nu *= 2.0; ++n_rej;
+        sum->accepted[it] = 0;
+        if (!std::isfinite(lambda)) terminate = true;
+      }
+      sum->cost[it] = cost; sum->radius[it] = 1.0 / lambda; sum->gradient_max_norm[it] = gmax;
+    } while (rho < 0.0 && n_rej < o->g2o_max_trials && !terminate);
+    if (terminate || n_rej >= o->g2o_max_trials || rho == 0.0) {
+      if (sum->stop_reason == GLBA_STOP_NONE) sum->stop_reason = GLBA_STOP_TRIALS;
+      break;
+    }
+  }
+  sum->n_iters = it; sum->final_cost = cost;
+  sum->status = GLBA_OK;
+  if (sum->termination != GLBA_TERM_FAILURE) {
+    for (int i = 0; i < V.n_cam; ++i) {
+      if (!V.cam_free[i]) continue;                   // constant vertices keep their input bits
+      so3_log(&Rt[12 * i], p->cam + 6 * i);
+      for (int a = 0; a < 3; ++a) p->cam[6 * i + 3 + a] = Rt[12 * i + 9 + a];
+    }
+    std::memcpy(p->pt, pt.data(), sizeof(double) * pt.size());
+  }
+  sum->t_total_ms = ttotal.ms();
+  return GLBA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -588,6 +805,7 @@ void glbao_default_options(glba_options* o) {
   o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1; o->max_consecutive_invalid_steps = 5;
   o->linsolve = GLBA_LINSOLVE_AUTO; o->dense_max_dim = 96; o->cg_rel_tol = 1e-13; o->cg_max_iters = 0; o->verbose = 0;
+  o->mode = GLBA_MODE_CERES; o->g2o_tau = 1e-5; o->g2o_max_trials = 10;
 }
 
 int glbao_num_threads(void) {
@@ -735,6 +953,7 @@ int glbao_step(const glba_problem* p, const glba_options* o, double radius, doub
 
 // Ceres-semantics LM (replaces ceres::Solve at slam_core.cpp:849).
 int glbao_solve(const glba_problem* p, const glba_options* o, glba_summary* sum) {
+  if (o->mode == GLBA_MODE_G2O) return solve_g2o(p, o, sum);
   Timer ttotal;
   std::memset(sum, 0, sizeof(*sum));
   View V; int st = build_view(p, V); if (st) { sum->status = st; return st; }

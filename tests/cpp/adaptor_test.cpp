@@ -113,6 +113,41 @@ int main(int argc, char** argv) {
     }
     return 0;
   }
+  if (mode == "g2o") {
+    // the archived entry point: world-to-camera poses of every keyframe in the file, all points, camera 0 fixed
+    Backend be(0);
+    if (!be.ok()) { std::cout << "nodevice " << be.status() << "\n"; return 3; }
+    std::vector<int> kfids;
+    for (const auto& kv : map.keyframes) kfids.push_back(kv.first);
+    std::sort(kfids.begin(), kfids.end());
+    std::unordered_map<int, int> cam_idx;
+    std::vector<Mat33> Rs; std::vector<Vec3> Ts;
+    for (int kfid : kfids) {
+      cam_idx[kfid] = (int)Rs.size();
+      const Frame& fr = map.keyframes[kfid];
+      const Mat33 Rcw = transpose(fr.R);
+      Vec3 t;
+      for (int r = 0; r < 3; ++r) t.v[r] = -(Rcw.m[r * 3] * fr.t.v[0] + Rcw.m[r * 3 + 1] * fr.t.v[1] + Rcw.m[r * 3 + 2] * fr.t.v[2]);
+      Rs.push_back(Rcw); Ts.push_back(t);
+    }
+    std::vector<Point3D> pts(map.map_points.size());
+    for (int j = 0; j < (int)pts.size(); ++j) {
+      const MapPoint& mp = map.map_points[1000 + j];
+      pts[j].position = mp.position;
+      for (const Observation& o : mp.obs) { Observation2D q; q.camera_idx = cam_idx[o.keyframe_id]; q.point2D = o.point2D; pts[j].observations.push_back(q); }
+    }
+    glba_summary s;
+    const bool ok = bundleAdjustment(be, Rs, Ts, pts, K, 12, GLBA_LOSS_NONE, 1.0, &s);
+    std::cout << (ok ? "ok " : "false ") << s.n_iters << " " << s.n_successful << " " << s.initial_cost << " " << s.final_cost << "\n";
+    for (size_t i = 0; i < Rs.size(); ++i) {
+      for (int q = 0; q < 9; ++q) std::cout << Rs[i].m[q] << " ";
+      for (int q = 0; q < 3; ++q) std::cout << Ts[i].v[q] << " ";
+      std::cout << "\n";
+    }
+    for (const Point3D& P : pts) std::cout << P.position.x << " " << P.position.y << " " << P.position.z << " ";
+    std::cout << "\n";
+    return ok ? 0 : 1;
+  }
   if (mode == "solve" || mode == "resident") {
     Backend be(0);
     if (!be.ok()) { std::cout << "nodevice " << be.status() << "\n"; return 3; }

@@ -122,6 +122,31 @@ def test_full_ba_resident_matches_full_ba(exe, tmp_path):
 
 
 @pytest.mark.gpu
+def test_g2o_bundle_adjustment_adaptor(exe, tmp_path, oracle):
+    """glslam::bundleAdjustment (the archived g2o entry point, Old/mult_img_recoverpose_single_ba:251-326) against the
+    oracle's g2o restatement on the same world-to-camera poses."""
+    from gl_slam_b200._abi import MODE_G2O
+    prob = window_scene()
+    path = tmp_path / "scene.txt"
+    write_scene(path, prob, window=10, run_window=16, first=5)
+    out = subprocess.check_output([exe, "g2o", str(path)]).decode().split("\n")
+    head = out[0].split()
+    assert head[0] == "ok"
+    gp = scene.as_g2o(prob)
+    gp.cam_fixed = np.zeros(prob.n_cam, np.uint8)
+    gp.cam_fixed[0] = 1
+    gp.K = (prob.K[0], prob.K[0], prob.K[2], prob.K[3])
+    ref, so = oracle.solve(gp, oracle.options(mode=MODE_G2O, loss=0, max_iters=12))
+    assert (int(head[1]), int(head[2])) == (so["n_iters"], so["n_successful"])
+    assert abs(float(head[4]) - so["final_cost"]) <= 1e-9 * so["final_cost"]
+    got = np.array([l.split() for l in out[1:1 + prob.n_cam]], float)
+    assert np.allclose(got[:, :9].reshape(-1, 3, 3), scene.rodrigues(ref.cam[:, :3]), atol=1e-7)
+    assert np.allclose(got[:, 9:], ref.cam[:, 3:], rtol=1e-6, atol=1e-7)
+    pts = np.array(out[1 + prob.n_cam].split(), float).reshape(-1, 3)
+    assert np.allclose(pts, ref.pt, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
 def test_pose_only_adaptor(exe, tmp_path, oracle):
     cam0, X, uv, _ = scene.pose_only_scene(400, seed=5)
     R = scene.rodrigues(cam0[:3])[0]
