@@ -82,6 +82,9 @@ struct glba_ctx {
   int device = 0, rank = 0, world = 1;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;          // host uploads of load_problem, overlapped with the index construction
+  cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool copies_in_flight = false;
   ncclComm_t comm = nullptr;
   std::string err;
   // problem
@@ -216,7 +219,7 @@ int validate_options(glba_ctx* ctx, const glba_options* o) {
 // ---------------------------------------------------------------------------------------------
 // Upload + index construction (the device-side restatement of the packing loop, slam_core.cpp:750-819)
 // ---------------------------------------------------------------------------------------------
-int load_problem(glba_ctx* ctx, const glba_problem* p) {
+int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   int st = validate_problem(ctx, p);
   if (st) return st;
   ctx->loaded = false;
@@ -230,17 +233,29 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   const double *d_cam, *d_pt, *d_u, *d_v;
   const int *d_ocam, *d_opt;
   const uint8_t *d_cfix = nullptr, *d_pfix = nullptr;
-  if (p->memspace == GLBA_MEM_HOST) {
+  const bool staged = (p->memspace == GLBA_MEM_HOST);
+  if (staged) {
     ENSURE(double, ctx->in_cam, 6 * (size_t)n_cam); ENSURE(double, ctx->in_pt, 3 * (size_t)n_pt);
     ENSURE(int, ctx->in_ocam, n); ENSURE(int, ctx->in_opt, n); ENSURE(double, ctx->in_u, n); ENSURE(double, ctx->in_v, n);
-    CU(cudaMemcpyAsync(ctx->in_cam.p, p->cam, sizeof(double) * 6 * n_cam, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->in_pt.p, p->pt, sizeof(double) * 3 * n_pt, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->in_ocam.p, p->obs_cam, sizeof(int) * n, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->in_opt.p, p->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->in_u.p, p->obs_u, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->in_v.p, p->obs_v, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-    if (p->cam_fixed) { ENSURE(uint8_t, ctx->in_cfix, n_cam); CU(cudaMemcpyAsync(ctx->in_cfix.p, p->cam_fixed, n_cam, cudaMemcpyHostToDevice, s)); d_cfix = ctx->in_cfix.as<uint8_t>(); }
-    if (p->pt_fixed) { ENSURE(uint8_t, ctx->in_pfix, n_pt); CU(cudaMemcpyAsync(ctx->in_pfix.p, p->pt_fixed, n_pt, cudaMemcpyHostToDevice, s)); d_pfix = ctx->in_pfix.as<uint8_t>(); }
+    if (p->cam_fixed) { ENSURE(uint8_t, ctx->in_cfix, n_cam); d_cfix = ctx->in_cfix.as<uint8_t>(); }
+    if (p->pt_fixed) { ENSURE(uint8_t, ctx->in_pfix, n_pt); d_pfix = ctx->in_pfix.as<uint8_t>(); }
+    // uploads on their own stream, in the order the index construction needs them: indices | parameters | measurements
+    cudaStream_t cs = ctx->copy_stream;
+    CU(cudaEventRecord(ctx->ev_copy[3], s));
+    CU(cudaStreamWaitEvent(cs, ctx->ev_copy[3], 0));       // earlier work on the compute stream may still read the staging buffers
+    ctx->copies_in_flight = true;
+    CU(cudaMemcpyAsync(ctx->in_opt.p, p->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(ctx->in_ocam.p, p->obs_cam, sizeof(int) * n, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(ctx->ev_copy[0], cs));
+    if (p->cam_fixed) CU(cudaMemcpyAsync(ctx->in_cfix.p, p->cam_fixed, n_cam, cudaMemcpyHostToDevice, cs));
+    if (p->pt_fixed) CU(cudaMemcpyAsync(ctx->in_pfix.p, p->pt_fixed, n_pt, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(ctx->in_cam.p, p->cam, sizeof(double) * 6 * n_cam, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(ctx->in_pt.p, p->pt, sizeof(double) * 3 * n_pt, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(ctx->ev_copy[1], cs));
+    CU(cudaMemcpyAsync(ctx->in_u.p, p->obs_u, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(ctx->in_v.p, p->obs_v, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(ctx->ev_copy[2], cs));
+    CU(cudaStreamWaitEvent(s, ctx->ev_copy[0], 0));        // the index kernels below need obs_pt / obs_cam only
     d_cam = ctx->in_cam.as<double>(); d_pt = ctx->in_pt.as<double>(); d_ocam = ctx->in_ocam.as<int>(); d_opt = ctx->in_opt.as<int>();
     d_u = ctx->in_u.as<double>(); d_v = ctx->in_v.as<double>();
   } else {
@@ -251,8 +266,6 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   for (int b = 0; b < 2; ++b) { ENSURE(double, ctx->cam[b], 6 * (size_t)n_cam); ENSURE(double, ctx->camtab[b], (size_t)CAMTAB * n_cam); ENSURE(double4, ctx->pt4[b], n_pt); }
   ENSURE(double, ctx->cam0, 6 * (size_t)n_cam); ENSURE(double4, ctx->pt40, n_pt);
   ctx->cur = 0;
-  CU(cudaMemcpyAsync(ctx->cam[0].p, d_cam, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
-  CU(cudaMemcpyAsync(ctx->cam0.p, ctx->cam[0].p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
   // index buffers
   ENSURE(int, ctx->pm_cam, n); ENSURE(int, ctx->pm_pt, n); ENSURE(double2, ctx->pm_uv, n); ENSURE(int, ctx->pm2cm, n);
   ENSURE(int, ctx->pt_start, (size_t)n_pt + 1); ENSURE(int, ctx->cm_pt, n); ENSURE(double2, ctx->cm_uv, n); ENSURE(int, ctx->cm2pm, n);
@@ -300,15 +313,13 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
     }
   }
   const int* n2o = ctx->relabelled ? ctx->new2old.as<int>() : nullptr;
-  if (n_pt) LAUNCH(k_pack_pt, cdiv(n_pt, 256), 256, n_pt, d_pt, n2o, ctx->pt4[0].as<double4>());
-  CU(cudaMemcpyAsync(ctx->pt40.p, ctx->pt4[0].p, sizeof(double4) * n_pt, cudaMemcpyDeviceToDevice, s));
   int bits_pt = 1; while ((1L << bits_pt) < (long)n_pt + 1 && bits_pt < 31) ++bits_pt;
   int bits_cam = 1; while ((1L << bits_cam) < (long)n_cam + 1 && bits_cam < 31) ++bits_cam;
   int* iota = ctx->keys_tmp.as<int>();          // [0,n): iota / sorted keys scratch; [n,2n): keys out
   int* keys_out = ctx->keys_tmp.as<int>() + n + 1;
   if (n > 0) {
     if (ctx->sorted_input) {
-      LAUNCH(k_gather_obs, gb, 256, n, (const int*)nullptr, d_ocam, d_opt, d_u, d_v, ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), ctx->pm_uv.as<double2>());
+      LAUNCH(k_gather_obs, gb, 256, n, (const int*)nullptr, d_ocam, d_opt, d_u, d_v, ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), (double2*)nullptr);
     } else {
       LAUNCH(k_iota, gb, 256, n, iota);
       size_t tmp_bytes = 0;
@@ -316,7 +327,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
       ENSURE(char, ctx->sort_tmp, tmp_bytes);
       CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, d_opt, keys_out, iota, ctx->pm2orig.as<int>(), (int)n, 0, bits_pt, s));
       g_launches.fetch_add(1);
-      LAUNCH(k_gather_obs, gb, 256, n, (const int*)ctx->pm2orig.as<int>(), d_ocam, d_opt, d_u, d_v, ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), ctx->pm_uv.as<double2>());
+      LAUNCH(k_gather_obs, gb, 256, n, (const int*)ctx->pm2orig.as<int>(), d_ocam, d_opt, d_u, d_v, ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), (double2*)nullptr);
     }
     LAUNCH(k_segment_starts, cdiv(n_pt + 1, 256), 256, n, (const int*)ctx->pm_pt.as<int>(), n_pt, ctx->pt_start.as<int>());
     // camera-major order: stable sort of point-major positions by camera
@@ -328,7 +339,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
     g_launches.fetch_add(1);
     LAUNCH(k_segment_starts, cdiv(n_cam + 1, 256), 256, n, (const int*)keys_out, n_cam, ctx->cam_start.as<int>());
     LAUNCH(k_build_cm, gb, 256, n, (const int*)ctx->cm2pm.as<int>(), (const int*)ctx->pm_pt.as<int>(), (const double2*)ctx->pm_uv.as<double2>(),
-           ctx->cm_pt.as<int>(), ctx->cm_uv.as<double2>(), ctx->pm2cm.as<int>());
+           ctx->cm_pt.as<int>(), (double2*)nullptr, ctx->pm2cm.as<int>());
   } else {
     CU(cudaMemsetAsync(ctx->pt_start.p, 0, sizeof(int) * ((size_t)n_pt + 1), s));
     CU(cudaMemsetAsync(ctx->cam_start.p, 0, sizeof(int) * ((size_t)n_cam + 1), s));
@@ -340,6 +351,7 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
     LAUNCH(k_check_dup, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->flags.as<int>() + 3);
   LAUNCH(k_counts, cdiv(n_cam + 2, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), (const int*)ctx->flags.as<int>() + 3, n > 0 ? 0 : 1, ctx->cam_cnt.as<int>());
   if (ctx->world > 1) { int s__ = allreduce(ctx, ctx->cam_cnt.p, (size_t)n_cam + 2, kNcclSum, kNcclInt32); if (s__) return s__; }
+  if (staged) CU(cudaStreamWaitEvent(s, ctx->ev_copy[1], 0));   // cam_fixed / pt_fixed / cam / pt have arrived
   if (n_cam) LAUNCH(k_free_flags_cnt, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_cnt.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
   if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, n2o, ctx->pt_free.as<uint8_t>());
   ctx->has_dup = false;
@@ -415,10 +427,29 @@ int load_problem(glba_ctx* ctx, const glba_problem* p) {
   }
   CU(cudaMemsetAsync(ctx->yhat.p, 0, sizeof(double) * 6 * n_cam, s));
   CU(cudaMemsetAsync(ctx->acc27.p, 0, sizeof(double) * (54 * (size_t)n_cam + NSCAL), s));
+  // state (after the parameter upload) and measurements (after theirs, the last to arrive)
+  CU(cudaMemcpyAsync(ctx->cam[0].p, d_cam, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(ctx->cam0.p, ctx->cam[0].p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
+  if (n_pt) LAUNCH(k_pack_pt, cdiv(n_pt, 256), 256, n_pt, d_pt, n2o, ctx->pt4[0].as<double4>());
+  CU(cudaMemcpyAsync(ctx->pt40.p, ctx->pt4[0].p, sizeof(double4) * n_pt, cudaMemcpyDeviceToDevice, s));
   if (n_cam) LAUNCH(k_cam_prep, cdiv(n_cam, 128), 128, n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>(), ctx->mode);
+  if (staged) CU(cudaStreamWaitEvent(s, ctx->ev_copy[2], 0));
+  if (n > 0) LAUNCH(k_gather_uv, gb, 256, n, ctx->sorted_input ? (const int*)nullptr : (const int*)ctx->pm2orig.as<int>(), (const int*)ctx->cm2pm.as<int>(),
+                    d_u, d_v, ctx->pm_uv.as<double2>(), ctx->cm_uv.as<double2>());
   mark(ctx, -1);
   ctx->loaded = true;
   return GLBA_OK;
+}
+
+// The uploads read the caller's buffers: whatever happened above, they have finished when this returns.
+int load_problem(glba_ctx* ctx, const glba_problem* p) {
+  const int st = load_problem_impl(ctx, p);
+  if (ctx->copies_in_flight) {
+    ctx->copies_in_flight = false;
+    const cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    if (e != cudaSuccess && st == GLBA_OK) return fail(ctx, GLBA_E_CUDA, "upload: %s", cudaGetErrorString(e));
+  }
+  return st;
 }
 
 PmArgs pm_args(glba_ctx* ctx, const glba_options* o) {
@@ -971,6 +1002,8 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (const char* e = std::getenv("GLBA_RELABEL")) ctx->env_relabel = (e[0] != '0');   // diagnostic: GLBA_RELABEL=0 keeps the caller's point order
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GLBA_E_CUDA; } ctx->own_stream = true; }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
+  for (auto& e : ctx->ev_copy) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   if (cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * NSCAL) != cudaSuccess || cudaMallocHost((void**)&ctx->h_cg, sizeof(CgState)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_flags, 8 * sizeof(int)) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   if (cfg->world > 1) {
@@ -999,6 +1032,8 @@ void glba_destroy(glba_ctx* ctx) {
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
   if (ctx->h_cg) cudaFreeHost(ctx->h_cg);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& e : ctx->ev_copy) if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -910,7 +910,18 @@ __global__ void k_gather_obs(const long n, const int* __restrict__ perm, const i
   const long o = perm ? perm[k] : k;
   cam_out[k] = cam_in[o];
   if (pt_out) pt_out[k] = pt_in[o];
-  uv_out[k] = make_double2(u_in[o], v_in[o]);
+  if (uv_out) uv_out[k] = make_double2(u_in[o], v_in[o]);
+}
+// measurements in both orders, once they have arrived (the upload of u, v overlaps the index construction)
+__global__ void k_gather_uv(const long n, const int* __restrict__ pm2orig, const int* __restrict__ cm2pm, const double* __restrict__ u_in,
+                            const double* __restrict__ v_in, double2* __restrict__ pm_uv, double2* __restrict__ cm_uv) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const long o = pm2orig ? pm2orig[k] : k;
+  pm_uv[k] = make_double2(u_in[o], v_in[o]);
+  const long q = cm2pm[k];
+  const long oq = pm2orig ? pm2orig[q] : q;
+  cm_uv[k] = make_double2(u_in[oq], v_in[oq]);
 }
 __global__ void k_build_cm(const long n, const int* __restrict__ cm2pm, const int* __restrict__ pm_pt, const double2* __restrict__ pm_uv,
                            int* __restrict__ cm_pt, double2* __restrict__ cm_uv, int* __restrict__ pm2cm) {
@@ -918,7 +929,7 @@ __global__ void k_build_cm(const long n, const int* __restrict__ cm2pm, const in
   if (k >= n) return;
   const int o = cm2pm[k];
   cm_pt[k] = pm_pt[o];
-  cm_uv[k] = pm_uv[o];
+  if (cm_uv) cm_uv[k] = pm_uv[o];
   pm2cm[o] = (int)k;
 }
 __global__ void k_free_flags(const int n, const int* __restrict__ start, const uint8_t* __restrict__ fixed, const int* __restrict__ new2old,
