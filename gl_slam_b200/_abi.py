@@ -38,7 +38,7 @@ class Problem(C.Structure):
                 ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_u", C.c_void_p), ("obs_v", C.c_void_p),
                 ("cam_fixed", C.c_void_p), ("pt_fixed", C.c_void_p),
                 ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
-                ("memspace", C.c_int32)]
+                ("memspace", C.c_int32), ("pt_info", C.c_void_p)]
 
 
 class Options(C.Structure):
@@ -97,7 +97,7 @@ def _ptr(a):
 class HostProblem:
     """Numpy arrays in the layout of glba_problem; keeps them alive while the ctypes struct is in use."""
 
-    def __init__(self, cam, pt, obs_cam, obs_pt, obs_u, obs_v, K, cam_fixed=None, pt_fixed=None):
+    def __init__(self, cam, pt, obs_cam, obs_pt, obs_u, obs_v, K, cam_fixed=None, pt_fixed=None, pt_info=None):
         self.cam = np.ascontiguousarray(cam, dtype=np.float64).reshape(-1, 6).copy()
         self.pt = np.ascontiguousarray(pt, dtype=np.float64).reshape(-1, 3).copy()
         self.obs_cam = np.ascontiguousarray(obs_cam, dtype=np.int32)
@@ -106,6 +106,7 @@ class HostProblem:
         self.obs_v = np.ascontiguousarray(obs_v, dtype=np.float64)
         self.cam_fixed = None if cam_fixed is None else np.ascontiguousarray(cam_fixed, dtype=np.uint8)
         self.pt_fixed = None if pt_fixed is None else np.ascontiguousarray(pt_fixed, dtype=np.uint8)
+        self.pt_info = None if pt_info is None else np.ascontiguousarray(pt_info, dtype=np.float64)
         self.K = tuple(float(x) for x in K)  # fx, fy, cx, cy
         n = self.obs_cam.shape[0]
         if not (self.obs_pt.shape[0] == n == self.obs_u.shape[0] == self.obs_v.shape[0]):
@@ -125,7 +126,7 @@ class HostProblem:
 
     def copy(self):
         return HostProblem(self.cam, self.pt, self.obs_cam, self.obs_pt, self.obs_u, self.obs_v, self.K,
-                           self.cam_fixed, self.pt_fixed)
+                           self.cam_fixed, self.pt_fixed, self.pt_info)
 
     def struct(self):
         p = Problem()
@@ -135,6 +136,7 @@ class HostProblem:
         p.cam_fixed, p.pt_fixed = _ptr(self.cam_fixed), _ptr(self.pt_fixed)
         p.fx, p.fy, p.cx, p.cy = self.K
         p.memspace = MEM_HOST
+        p.pt_info = _ptr(self.pt_info)
         return p
 
 

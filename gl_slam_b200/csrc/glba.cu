@@ -94,7 +94,7 @@ struct glba_ctx {
   Intr K{};
   bool sorted_input = true;
   // device buffers
-  Buf in_cam, in_pt, in_ocam, in_opt, in_u, in_v, in_cfix, in_pfix;                 // staging of host input
+  Buf in_cam, in_pt, in_ocam, in_opt, in_u, in_v, in_cfix, in_pfix, in_info;               // staging of host input
   Buf pm_cam, pm_pt, pm_uv, pm2orig, pm2cm, pt_start, cm_pt, cm_uv, cm2pm, cam_start; // index
   Buf chunk_cam, chunk_begin, chunk_end, cam_chunk_start, cam_free, pt_free, sort_tmp, keys_tmp, flags;
   Buf cam[2], camtab[2], pt4[2], cam0, pt40;                                         // state (double-buffered)
@@ -233,12 +233,14 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   const double *d_cam, *d_pt, *d_u, *d_v;
   const int *d_ocam, *d_opt;
   const uint8_t *d_cfix = nullptr, *d_pfix = nullptr;
+  const double* d_info = nullptr;
   const bool staged = (p->memspace == GLBA_MEM_HOST);
   if (staged) {
     ENSURE(double, ctx->in_cam, 6 * (size_t)n_cam); ENSURE(double, ctx->in_pt, 3 * (size_t)n_pt);
     ENSURE(int, ctx->in_ocam, n); ENSURE(int, ctx->in_opt, n); ENSURE(double, ctx->in_u, n); ENSURE(double, ctx->in_v, n);
     if (p->cam_fixed) { ENSURE(uint8_t, ctx->in_cfix, n_cam); d_cfix = ctx->in_cfix.as<uint8_t>(); }
     if (p->pt_fixed) { ENSURE(uint8_t, ctx->in_pfix, n_pt); d_pfix = ctx->in_pfix.as<uint8_t>(); }
+    if (p->pt_info) { ENSURE(double, ctx->in_info, n_pt); d_info = ctx->in_info.as<double>(); }
     // uploads on their own stream, in the order the index construction needs them: indices | parameters | measurements
     cudaStream_t cs = ctx->copy_stream;
     CU(cudaEventRecord(ctx->ev_copy[3], s));
@@ -249,6 +251,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
     CU(cudaEventRecord(ctx->ev_copy[0], cs));
     if (p->cam_fixed) CU(cudaMemcpyAsync(ctx->in_cfix.p, p->cam_fixed, n_cam, cudaMemcpyHostToDevice, cs));
     if (p->pt_fixed) CU(cudaMemcpyAsync(ctx->in_pfix.p, p->pt_fixed, n_pt, cudaMemcpyHostToDevice, cs));
+    if (p->pt_info) CU(cudaMemcpyAsync(ctx->in_info.p, p->pt_info, sizeof(double) * n_pt, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(ctx->in_cam.p, p->cam, sizeof(double) * 6 * n_cam, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(ctx->in_pt.p, p->pt, sizeof(double) * 3 * n_pt, cudaMemcpyHostToDevice, cs));
     CU(cudaEventRecord(ctx->ev_copy[1], cs));
@@ -260,7 +263,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
     d_u = ctx->in_u.as<double>(); d_v = ctx->in_v.as<double>();
   } else {
     d_cam = p->cam; d_pt = p->pt; d_ocam = p->obs_cam; d_opt = p->obs_pt; d_u = p->obs_u; d_v = p->obs_v;
-    d_cfix = p->cam_fixed; d_pfix = p->pt_fixed;
+    d_cfix = p->cam_fixed; d_pfix = p->pt_fixed; d_info = p->pt_info;
   }
   // state
   for (int b = 0; b < 2; ++b) { ENSURE(double, ctx->cam[b], 6 * (size_t)n_cam); ENSURE(double, ctx->camtab[b], (size_t)CAMTAB * n_cam); ENSURE(double4, ctx->pt4[b], n_pt); }
@@ -430,7 +433,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   // state (after the parameter upload) and measurements (after theirs, the last to arrive)
   CU(cudaMemcpyAsync(ctx->cam[0].p, d_cam, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
   CU(cudaMemcpyAsync(ctx->cam0.p, ctx->cam[0].p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToDevice, s));
-  if (n_pt) LAUNCH(k_pack_pt, cdiv(n_pt, 256), 256, n_pt, d_pt, n2o, ctx->pt4[0].as<double4>());
+  if (n_pt) LAUNCH(k_pack_pt, cdiv(n_pt, 256), 256, n_pt, d_pt, d_info, n2o, ctx->pt4[0].as<double4>());
   CU(cudaMemcpyAsync(ctx->pt40.p, ctx->pt4[0].p, sizeof(double4) * n_pt, cudaMemcpyDeviceToDevice, s));
   if (n_cam) LAUNCH(k_cam_prep, cdiv(n_cam, 128), 128, n_cam, (const double*)ctx->cam[0].as<double>(), ctx->camtab[0].as<double>(), ctx->mode);
   if (staged) CU(cudaStreamWaitEvent(s, ctx->ev_copy[2], 0));
@@ -1020,7 +1023,7 @@ void glba_destroy(glba_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-  Buf* all[] = {&ctx->in_cam, &ctx->in_pt, &ctx->in_ocam, &ctx->in_opt, &ctx->in_u, &ctx->in_v, &ctx->in_cfix, &ctx->in_pfix, &ctx->pm_cam, &ctx->pm_pt,
+  Buf* all[] = {&ctx->in_cam, &ctx->in_pt, &ctx->in_ocam, &ctx->in_opt, &ctx->in_u, &ctx->in_v, &ctx->in_cfix, &ctx->in_pfix, &ctx->in_info, &ctx->pm_cam, &ctx->pm_pt,
                 &ctx->pm_uv, &ctx->pm2orig, &ctx->pm2cm, &ctx->pt_start, &ctx->cm_pt, &ctx->cm_uv, &ctx->cm2pm, &ctx->cam_start, &ctx->chunk_cam,
                 &ctx->chunk_begin, &ctx->chunk_end, &ctx->cam_chunk_start, &ctx->cam_free, &ctx->pt_free, &ctx->sort_tmp, &ctx->keys_tmp, &ctx->flags,
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,

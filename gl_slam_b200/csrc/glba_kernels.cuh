@@ -437,7 +437,8 @@ k_linearize_pm(const PmArgs A, const double4* __restrict__ pt, const double* __r
       double xh, yh, iz, rx, ry;
       project_obs(ct, X.x, X.y, X.z, A.K, uv.x, uv.y, xh, yh, iz, rx, ry);
       double rho, w;
-      loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+      loss_eval(A.loss, (X.w * X.w) * (rx * rx + ry * ry), rho, w);
+      w *= X.w;
       if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
       cost += 0.5 * rho;
       const double4 rec = make_double4(xh, yh, iz, w);
@@ -757,7 +758,7 @@ k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* _
       const double2 u01 = __ldg(pb + 3), u2_ = __ldg(pb + 4);
       const double y0 = u01.x - v0, y1 = u01.y - v1, y2 = u2_.x - v2;
       const double4 X = ldg4(pt + j);
-      const double4 Xc = make_double4(X.x - y0, X.y - y1, X.z - y2, 0.0);
+      const double4 Xc = make_double4(X.x - y0, X.y - y1, X.z - y2, X.w);
       st4(pt_c + j, Xc);
       if (free_pt) {
         const double4 l4 = ldg4(lam4 + j);
@@ -771,7 +772,7 @@ k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* _
         double xh, yh, iz, rx, ry;
         project_obs(camtab_c + (size_t)CAMTAB * i, Xc.x, Xc.y, Xc.z, A.K, uv.x, uv.y, xh, yh, iz, rx, ry);
         double rho, w;
-        loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+        loss_eval(A.loss, (Xc.w * Xc.w) * (rx * rx + ry * ry), rho, w);
         if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
         cost_c += 0.5 * rho;
       }
@@ -953,11 +954,13 @@ __global__ void k_free_flags_cnt(const int n, const int* __restrict__ cnt, const
 }
 // Internal point j corresponds to the caller's point new2old[j] (nullptr = identity): see the locality relabelling
 // in load_problem.
-__global__ void k_pack_pt(const int n, const double* __restrict__ pt3, const int* __restrict__ new2old, double4* __restrict__ pt4) {
+// .w carries sqrt(information weight) of the point's observations (1 when the caller gives none)
+__global__ void k_pack_pt(const int n, const double* __restrict__ pt3, const double* __restrict__ info, const int* __restrict__ new2old,
+                          double4* __restrict__ pt4) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const size_t o = new2old ? new2old[j] : j;
-  pt4[j] = make_double4(pt3[3 * o], pt3[3 * o + 1], pt3[3 * o + 2], 0.0);
+  pt4[j] = make_double4(pt3[3 * o], pt3[3 * o + 1], pt3[3 * o + 2], info ? sqrt(fmax(info[o], 0.0)) : 1.0);
 }
 __global__ void k_unpack_pt(const int n, const double4* __restrict__ pt4, const int* __restrict__ new2old, double* __restrict__ pt3) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;

@@ -17,7 +17,10 @@ constexpr int NT_T = 256;
 // Observations per thread in phase 1 (template parameter OPT): 4 for large maps (tile = 1024 observations, ~200 points:
 // phase 2 fills the CTA), 1 for small ones (tile = 256 observations: 4x more CTAs and a 4x shorter dependent chain per
 // thread — what matters when the whole map is a few tiles).
-constexpr int OPT_LARGE = 4, OPT_SMALL = 1;
+#ifndef GLBA_OPT_LARGE
+#define GLBA_OPT_LARGE 4
+#endif
+constexpr int OPT_LARGE = GLBA_OPT_LARGE, OPT_SMALL = 1;
 
 // The last CTA to finish folds the per-CTA partial rows [rows][5] into the scalar slots, in row order (fixed).
 // MAXCOL = column reduced with max (-1: none).  Saves a separate single-CTA reduction launch per pass.
@@ -148,7 +151,8 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
       const double xh = px * iz, yh = py * iz;
       const double rx = A.K.fx * xh + A.K.cx - uv.x, ry = A.K.fy * yh + A.K.cy - uv.y;
       double rho, w;
-      loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+      loss_eval(A.loss, (X.w * X.w) * (rx * rx + ry * ry), rho, w);      // X.w = sqrt(information) of the point, 1 by default
+      w *= X.w;
       if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
       cost += 0.5 * rho;
       const double4 rec = make_double4(xh, yh, iz, w);
@@ -322,7 +326,7 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
     } else {
       const double y0 = u0[0] - v0, y1 = u0[1] - v1, y2 = u0[2] - v2;
       const double4 X = ldg4(pt + j);
-      st4(pt_c + j, make_double4(X.x - y0, X.y - y1, X.z - y2, 0.0));
+      st4(pt_c + j, make_double4(X.x - y0, X.y - y1, X.z - y2, X.w));
       if (free_pt) {
         const double4 l4 = ldg4(lam4 + j);
         yn2 += y0 * y0 + y1 * y1 + y2 * y2;
@@ -359,7 +363,7 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
         const double iz = 1.0 / pz;
         const double rx = A.K.fx * (px * iz) + A.K.cx - uv.x, ry = A.K.fy * (py * iz) + A.K.cy - uv.y;
         double rho, w;
-        loss_eval(A.loss, rx * rx + ry * ry, rho, w);
+        loss_eval(A.loss, (xc.w * xc.w) * (rx * rx + ry * ry), rho, w);
         if (!isfinite(rx) || !isfinite(ry)) bad += 1.0;
         cost_c += 0.5 * rho;
       }

@@ -128,7 +128,10 @@ typedef struct {
   const uint8_t* cam_fixed;
   const uint8_t* pt_fixed;
   double fx, fy, cx, cy;         /* cameraMatrix(0,0),(1,1),(0,2),(1,2) — slam_core.cpp:720-723 */
-  int32_t memspace;              /* glba_memspace of every pointer above */
+  int32_t memspace;              /* glba_memspace of every pointer above and below */
+  const double* pt_info;         /* optional [n_pt]: information weight of every observation of point j (residual' Omega residual with
+                                  * Omega = pt_info[j] * I, robust kernel applied to the weighted square); NULL = 1.  The archived g2o BA
+                                  * uses 1 / z^2 of the point (docs/old_unorganized/4image_pnp_ba.txt:400-403). */
 } glba_problem;
 
 /* Defaults (glba_default_options) = the values hard-coded at slam_core.cpp:814, 842-847

@@ -167,6 +167,7 @@ struct View {
   const double* obs_u;
   const double* obs_v;
   double fx, fy, cx, cy;
+  const double* pt_info;           // optional per-point information weight (glba_problem::pt_info), nullptr = 1
   std::vector<uint8_t> cam_free;   // not fixed and observed
   std::vector<uint8_t> pt_free;    // not fixed and observed
   std::vector<uint8_t> pt_seen;
@@ -184,6 +185,7 @@ int build_view(const glba_problem* p, View& V) {
   V.n_cam = p->n_cam; V.n_pt = p->n_pt; V.n_obs = (long)p->n_obs;
   V.obs_cam = p->obs_cam; V.obs_pt = p->obs_pt; V.obs_u = p->obs_u; V.obs_v = p->obs_v;
   V.fx = p->fx; V.fy = p->fy; V.cx = p->cx; V.cy = p->cy;
+  V.pt_info = p->pt_info;
   std::vector<uint8_t> cam_seen(V.n_cam, 0);
   V.pt_seen.assign(V.n_pt, 0);
   V.trk_start.assign(V.n_pt + 1, 0);
@@ -246,10 +248,11 @@ bool evaluate(const View& V, const double* cam, const double* pt, int loss, doub
         for (int i = 0; i < 3; ++i) jx[i] = J(x[i], 6 + i);
         reprojection_residual<J>(jc, jx, V.fx, V.fy, V.cx, V.cy, V.obs_u[k], V.obs_v[k], jr);
         r[0] = jr[0].a; r[1] = jr[1].a;
-        s = r[0] * r[0] + r[1] * r[1];
+        const double info = V.pt_info ? std::max(V.pt_info[V.obs_pt[k]], 0.0) : 1.0;     // r' Omega r, Omega = info * I
+        s = info * (r[0] * r[0] + r[1] * r[1]);
         double rho[3]; loss_eval(loss, loss_a, s, rho);
         acc += 0.5 * rho[0];
-        const double sq = std::sqrt(rho[1]);   // corrector, rho'' <= 0 branch for all three losses
+        const double sq = std::sqrt(info) * std::sqrt(rho[1]);   // corrector, rho'' <= 0 branch for all three losses
         double* Jc = &lin->jc[12 * k]; double* Jp = &lin->jp[6 * k];
         for (int row = 0; row < 2; ++row) {
           for (int i = 0; i < 6; ++i) { Jc[row * 6 + i] = sq * jr[row].v[i]; if (!std::isfinite(Jc[row * 6 + i])) isbad = 1; }
@@ -258,7 +261,7 @@ bool evaluate(const View& V, const double* cam, const double* pt, int loss, doub
         lin->r[2 * k] = sq * r[0]; lin->r[2 * k + 1] = sq * r[1];
       } else {
         reprojection_residual<double>(c, x, V.fx, V.fy, V.cx, V.cy, V.obs_u[k], V.obs_v[k], r);
-        s = r[0] * r[0] + r[1] * r[1];
+        s = (V.pt_info ? std::max(V.pt_info[V.obs_pt[k]], 0.0) : 1.0) * (r[0] * r[0] + r[1] * r[1]);
         double rho[3]; loss_eval(loss, loss_a, s, rho);
         acc += 0.5 * rho[0];
       }
@@ -624,11 +627,12 @@ bool evaluate_g2o(const View& V, const double* Rt, const double* pt, int loss, d
     const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
     const double iz = 1.0 / z, iz2 = iz * iz;
     const double e0 = V.obs_u[k] - (V.fx * x * iz + V.cx), e1 = V.obs_v[k] - (V.fy * y * iz + V.cy);
-    double rho[3]; loss_eval(loss, loss_a, e0 * e0 + e1 * e1, rho);
+    const double info = V.pt_info ? std::max(V.pt_info[V.obs_pt[k]], 0.0) : 1.0;          // edge->setInformation(info * I)
+    double rho[3]; loss_eval(loss, loss_a, info * (e0 * e0 + e1 * e1), rho);
     cost += 0.5 * rho[0];
     if (!std::isfinite(e0) || !std::isfinite(e1)) anybad |= 1;
     if (!lin) continue;
-    const double sq = std::sqrt(rho[1]);
+    const double sq = std::sqrt(info) * std::sqrt(rho[1]);
     lin->r[2 * k] = sq * e0; lin->r[2 * k + 1] = sq * e1;
     // EdgeProjectXYZ2UV::linearizeOplus: d e / d X = -1/z [[fx,0,-fx x/z],[0,fy,-fy y/z]] R ;  d e / d [dw, dv]
     const double P[6] = {V.fx * iz, 0.0, -V.fx * x * iz2, 0.0, V.fy * iz, -V.fy * y * iz2};

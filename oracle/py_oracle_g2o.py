@@ -57,9 +57,13 @@ def solve(prob, loss_kind=2, loss_a=1.0, max_iters=30, tau=1e-5, max_trials=10):
     nc, nv = 6 * len(free_c), 6 * len(free_c) + 3 * len(free_p)
     n = prob.n_obs
 
+    info = np.ones(prob.n_pt) if getattr(prob, "pt_info", None) is None else prob.pt_info
+    om = info[prob.obs_pt]                   # edge information = om * I
+
     def linearize(R, t, pt):
         e, p = _errors(R, t, pt, prob)
-        rho, w = loss_fn(loss_kind, loss_a, (e * e).sum(axis=1))
+        rho, w = loss_fn(loss_kind, loss_a, om * (e * e).sum(axis=1))
+        w = w * om
         Jc, Jp = _jacobians(R[prob.obs_cam], p, prob.K)
         J = np.zeros((2 * n, nv))
         for k in range(n):
@@ -74,7 +78,7 @@ def solve(prob, loss_kind=2, loss_a=1.0, max_iters=30, tau=1e-5, max_trials=10):
 
     def chi(R, t, pt):
         e, _ = _errors(R, t, pt, prob)
-        return 0.5 * loss_fn(loss_kind, loss_a, (e * e).sum(axis=1))[0].sum()
+        return 0.5 * loss_fn(loss_kind, loss_a, om * (e * e).sum(axis=1))[0].sum()
 
     cost, H, b = linearize(R, t, pt)
     lam, nu = tau * np.max(np.diag(H)), 2.0

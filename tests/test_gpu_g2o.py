@@ -83,3 +83,27 @@ def test_resident_and_mode_mismatch(ctx):
         ctx.solve_resident(g.options(max_iters=5))            # loaded in the g2o convention, solved as Ceres
     with pytest.raises(g.GlbaError):
         ctx.linearize(prob, 1e4, g.options(mode=MODE_G2O))
+
+
+@pytest.mark.parametrize("mode", [MODE_G2O, 0])
+def test_information_weights(ctx, oracle, mode):
+    """glba_problem::pt_info: edge information I/z^2 with Huber(3) as in docs/old_unorganized/4image_pnp_ba.txt:400-406
+    (g2o mode), and the same weighting through the Ceres formulation."""
+    prob = g2o_scene(10, 400, seed=2) if mode == MODE_G2O else scene.make_scene(n_cam=10, n_pt=400, track_len=4, seed=2, outlier_frac=0.05,
+                                                                                rot_sigma=0.005, pos_sigma=0.03)
+    z = prob.pt[:, 2]
+    prob.pt_info = np.where(z > 0.1, 1.0 / np.maximum(z, 0.1) ** 2, 100.0)
+    o = dict(loss=1, loss_scale=3.0, max_iters=10, mode=mode)
+    ref, so = oracle.solve(prob, oracle.options(**o))
+    got, s = ctx.solve(prob, g.options(**o))
+    assert s["n_iters"] == so["n_iters"] and list(s["accepted"]) == list(so["accepted"])
+    assert np.allclose(s["cost"], so["cost"], rtol=1e-9, atol=0)
+    assert np.allclose(got.cam, ref.cam, rtol=1e-6, atol=1e-8)
+    plain = prob.copy()
+    plain.pt_info = None
+    _, s0 = ctx.solve(plain, g.options(**o))
+    assert abs(s0["initial_cost"] - s["initial_cost"]) > 0.1 * s["initial_cost"]       # the weights do something
+    ones = prob.copy()
+    ones.pt_info = np.ones(prob.n_pt)
+    _, s1 = ctx.solve(ones, g.options(**o))
+    assert s1["cost"] == s0["cost"]                                                     # unit information is bit-for-bit the default

@@ -72,3 +72,27 @@ def test_same_minimum_as_ceres_formulation(oracle):
     assert abs(sa["final_cost"] - sb["final_cost"]) <= 1e-9 * sa["final_cost"]
     assert np.allclose(scene.to_camera_to_world(b.cam), a.cam, rtol=1e-6, atol=1e-7)
     assert np.allclose(b.pt, a.pt, rtol=1e-6, atol=1e-6)
+
+
+def inv_depth2_information(prob):
+    """docs/old_unorganized/4image_pnp_ba.txt:400-401: weight = 1/z^2 of the point (world z), 1/0.1^2 below 0.1."""
+    z = prob.pt[:, 2]
+    return np.where(z > 0.1, 1.0 / np.maximum(z, 0.1) ** 2, 1.0 / 0.01)
+
+
+@pytest.mark.parametrize("loss,delta", [(1, 3.0), (0, 1.0)])
+def test_information_weights_match_numpy_g2o(oracle, loss, delta):
+    """The archived variant with edge information I/z^2 and RobustKernelHuber(delta = 3) (4image_pnp_ba.txt:400-406)."""
+    g = scene.as_g2o(small())
+    g.pt_info = inv_depth2_information(g)
+    ref, s = oracle.solve(g, oracle.options(loss=loss, loss_scale=delta, mode=MODE_G2O, max_iters=10))
+    q = py_oracle_g2o.solve(g, loss_kind=loss, loss_a=delta, max_iters=10)
+    assert list(s["accepted"]) == q["accepted"]
+    assert np.allclose(s["cost"], q["cost"], rtol=1e-10, atol=0)
+    assert np.allclose(ref.cam, q["cam"], rtol=1e-7, atol=1e-9)
+    # uniform information c is the same as scaling the residuals by sqrt(c): cost scales by c when there is no kernel
+    g1 = scene.as_g2o(small())
+    g1.pt_info = np.full(g1.n_pt, 4.0)
+    g0 = scene.as_g2o(small())
+    assert np.isclose(oracle.solve(g1, oracle.options(loss=0, mode=MODE_G2O, max_iters=0))[1]["initial_cost"],
+                      4.0 * oracle.solve(g0, oracle.options(loss=0, mode=MODE_G2O, max_iters=0))[1]["initial_cost"], rtol=1e-14)
