@@ -44,7 +44,7 @@ def main():
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k[:70]}` | {v[0]} | {v[1] / 1e3:.1f} | {v[1] / 1e3 / v[0]:.1f} | {100 * v[1] / tot:.1f}% |")
     if rep:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        raw = (open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         out += ["", f"## `ncu --set full --clock-control none` ({rep.split('/')[-1]}), per launch", "",

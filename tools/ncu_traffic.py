@@ -1,5 +1,5 @@
 """profiles/traffic.json: mean DRAM bytes (read+write) per launch of each hot kernel, from an `ncu --set full` report.
-Usage: python tools/ncu_traffic.py gpurun_out/prof.ncu-rep"""
+Usage: python tools/ncu_traffic.py gpurun_out/prof.ncu-rep   (or the `ncu -i ... --page raw --csv` dump of one)"""
 import collections
 import csv
 import io
@@ -12,7 +12,7 @@ NAMES = {"k_linearize_tile": "linearize_pm", "k_linearize_pm": "linearize_pm", "
          "k_spmv_cm": "spmv_cm"}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
-raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = (open(sys.argv[1]).read() if sys.argv[1].endswith(".csv") else subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
