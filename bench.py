@@ -264,7 +264,10 @@ def main():
                     "frac": kernels[dom]["frac"], "traffic": ncu_traffic, "peak_kind": peak_kind,
                     "step_bytes": sum(ab[k] for k in step_kernels),
                     "step_frac_of_peak": sum(ab[k] for k in step_kernels) / (ms_step * 1e-3) / 1e9 / peak,
-                    "survey_model_obs_per_s_at_peak": peak * 1e9 / 496.0}
+                    "survey_model_obs_per_s_at_peak": peak * 1e9 / 496.0,
+                    # SURVEY 8d asks for both denominators: the measured copy bandwidth above and the nominal 8 TB/s
+                    "frac_of_nominal_8tbs": kernels[dom]["gbs"] / 8000.0,
+                    "step_frac_of_nominal_8tbs": sum(ab[k] for k in step_kernels) / (ms_step * 1e-3) / 1e9 / 8000.0}
 
     # ---- LM iterations/s: full iterations (PCG solve, back-substitution, candidate cost, accept/reject) ------
     lm = None

@@ -231,7 +231,8 @@ def shard_by_point(prob, world, rank):
     pt_index = np.arange(lo, hi)
     sub = HostProblem(prob.cam, prob.pt[lo:hi], prob.obs_cam[sel], prob.obs_pt[sel] - lo, prob.obs_u[sel],
                       prob.obs_v[sel], prob.K, prob.cam_fixed,
-                      None if prob.pt_fixed is None else prob.pt_fixed[lo:hi])
+                      None if prob.pt_fixed is None else prob.pt_fixed[lo:hi],
+                      None if getattr(prob, "pt_info", None) is None else prob.pt_info[lo:hi])
     return sub, pt_index
 
 

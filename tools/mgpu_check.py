@@ -29,10 +29,19 @@ def main():
         "window_dense": (dict(n_cam=10, n_pt=2000, track_len=4, seed=2, outlier_frac=0.05, rot_sigma=0.005, pos_sigma=0.03), {}),
         "map_pcg": (dict(n_cam=24, n_pt=3000, track_len=lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=41, rot_sigma=0.003, pos_sigma=0.03), {}),
         "huber": (dict(n_cam=16, n_pt=1500, track_len=4, seed=8, outlier_frac=0.1, rot_sigma=0.004, pos_sigma=0.03), dict(loss=1)),
+        # the archived g2o formulation, sharded: lambda0 needs the max Hessian diagonal over ALL ranks' points
+        "g2o_pcg": (dict(n_cam=24, n_pt=3000, track_len=lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=43, rot_sigma=0.003, pos_sigma=0.03),
+                    dict(mode=_abi.MODE_G2O, loss=1, max_iters=8)),
+        "g2o_dense_info": (dict(n_cam=10, n_pt=2000, track_len=4, seed=5, outlier_frac=0.05, rot_sigma=0.005, pos_sigma=0.03),
+                           dict(mode=_abi.MODE_G2O, loss=1, loss_scale=3.0, max_iters=8)),
     }
     ok = True
     for name, (kw, okw) in cases.items():
         prob = scene.make_scene(**kw)
+        if okw.get("mode") == _abi.MODE_G2O:
+            prob = scene.as_g2o(prob)
+        if name.endswith("_info"):
+            prob.pt_info = 1.0 / np.maximum(prob.pt[:, 2], 0.1) ** 2
         sub, idx = scene.shard_by_point(prob, world, rank)
         got, s = ctx.solve(sub, g.options(**okw))
         # cameras must be bit-identical across ranks (all-reduced sums are)
@@ -48,7 +57,8 @@ def main():
             ref, so = oracle.solve(prob, oracle.options(**okw))
             n = min(len(s["cost"]), len(so["cost"]))
             rel = max(abs(a - b) / abs(b) for a, b in zip(s["cost"][:n], so["cost"][:n]))
-            d = np.linalg.norm(ref.pt[prob.obs_pt] - prob.cam[prob.obs_cam, 3:6], axis=1)
+            centres = scene.to_camera_to_world(prob.cam)[:, 3:6] if okw.get("mode") == _abi.MODE_G2O else prob.cam[:, 3:6]
+            d = np.linalg.norm(ref.pt[prob.obs_pt] - centres[prob.obs_cam], axis=1)
             far = np.zeros(prob.n_pt, bool); np.logical_or.at(far, prob.obs_pt, d > 150.0)
             perr = float((np.linalg.norm(pts.cpu().numpy() - ref.pt, axis=1) / np.maximum(np.linalg.norm(ref.pt, axis=1), 1.0))[~far].max())
             results[name] = dict(iters=[s["n_iters"], so["n_iters"]], cost_rel=rel, cam_err=float(np.abs(got.cam - ref.cam).max()), pt_err=perr,
