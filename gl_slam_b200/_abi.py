@@ -61,14 +61,14 @@ class Summary(C.Structure):
                 ("gradient_max_norm", C.c_double * _N), ("cg_iters", C.c_int32 * _N),
                 ("accepted", C.c_uint8 * _N),
                 ("t_setup_ms", C.c_double), ("t_linearize_ms", C.c_double), ("t_schur_ms", C.c_double),
-                ("t_solve_ms", C.c_double), ("t_update_ms", C.c_double), ("t_total_ms", C.c_double)]
+                ("t_solve_ms", C.c_double), ("t_update_ms", C.c_double), ("t_total_ms", C.c_double), ("t_comm_ms", C.c_double)]
 
     def as_dict(self):
         n = self.n_iters + 1
         d = {k: getattr(self, k) for k in ("status", "termination", "stop_reason", "n_iters", "n_successful",
                                             "n_linearizations", "initial_cost", "final_cost", "t_setup_ms",
                                             "t_linearize_ms", "t_schur_ms", "t_solve_ms", "t_update_ms",
-                                            "t_total_ms")}
+                                            "t_total_ms", "t_comm_ms")}
         for k in ("cost", "cost_candidate", "radius", "step_norm", "relative_decrease", "gradient_max_norm",
                   "cg_iters", "accepted"):
             d[k] = list(getattr(self, k)[:n])

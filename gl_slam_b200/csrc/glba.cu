@@ -67,7 +67,7 @@ struct Buf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Phase { PH_SETUP = 0, PH_LIN, PH_SCHUR, PH_SOLVE, PH_UPDATE, PH_COUNT };
+enum Phase { PH_SETUP = 0, PH_LIN, PH_SCHUR, PH_SOLVE, PH_UPDATE, PH_COMM, PH_COUNT };
 
 struct EventPair {     // two CUDA events, destroyed on every exit path
   cudaEvent_t a = nullptr, b = nullptr;
@@ -124,7 +124,7 @@ struct glba_ctx {
   std::vector<int> ev_phase;
   int ev_used = 0;
   bool timing = true;          // per-phase CUDA events (off for small problems: the event API calls rival the kernels)
-  double t_phase[PH_COUNT] = {0, 0, 0, 0, 0};
+  double t_phase[PH_COUNT] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -591,11 +591,13 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
                               (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
   }
   if (sharded) {     // one payload: per-camera sums | cost, |x_p|^2, bad, notpd | per-rank gradient max slots
+    mark(ctx, PH_COMM);          // in situ: includes waiting for the slowest rank
     LAUNCH(k_chunk_sum_lin, cdiv((long)n_cam * (with_schur ? 54 : 27), 256) + (n_cam ? 0 : 1), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
            (const double*)ctx->part_cm.as<double>(), with_schur ? (const double*)ctx->part_cm2.as<double>() : (const double*)nullptr,
            ctx->d_accA, ctx->d_accB, ctx->rank, ctx->d_scal);
     if (with_schur) AR(ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
+    mark(ctx, with_schur ? PH_SCHUR : PH_LIN);
   }
   if (n_cam) launch_cam_lin_fin(ctx, o, first);
   if (with_schur && n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
@@ -914,7 +916,8 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   sum->n_iters = it; sum->final_cost = cost;
   sum->t_setup_ms = ctx->t_phase[PH_SETUP]; sum->t_linearize_ms = ctx->t_phase[PH_LIN]; sum->t_schur_ms = ctx->t_phase[PH_SCHUR];
   sum->t_solve_ms = ctx->t_phase[PH_SOLVE]; sum->t_update_ms = ctx->t_phase[PH_UPDATE];
-  sum->t_total_ms = sum->t_setup_ms + sum->t_linearize_ms + sum->t_schur_ms + sum->t_solve_ms + sum->t_update_ms;
+  sum->t_comm_ms = ctx->t_phase[PH_COMM];
+  sum->t_total_ms = sum->t_setup_ms + sum->t_linearize_ms + sum->t_schur_ms + sum->t_solve_ms + sum->t_update_ms + sum->t_comm_ms;
   sum->status = GLBA_OK;
   return GLBA_OK;
 }

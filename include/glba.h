@@ -187,6 +187,8 @@ typedef struct {
   double t_solve_ms;             /* PCG / dense solve */
   double t_update_ms;            /* back-substitution, candidate cost, accept/reject */
   double t_total_ms;
+  double t_comm_ms;              /* world > 1: the fused all-reduce of every linearisation with its chunk sum, measured in place
+                                  * (so it includes waiting for the slowest rank); part of t_total_ms, not of the fields above */
 } glba_summary;
 
 /* Output of glba_linearize: the reduced camera system of ONE linearisation at a given radius.
