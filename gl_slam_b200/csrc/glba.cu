@@ -105,7 +105,7 @@ struct glba_ctx {
   double* d_scal = nullptr;   // NSCAL doubles at the tail of acc27 (one all-reduce carries camera sums + scalars)
   Buf out_a, out_b, out_c;                                                           // glba_linearize outputs
   Buf first_cam, new2old, old2new, opt_relab;                                         // locality relabelling of the points
-  bool relabelled = false, allow_relabel = true, env_relabel = true;
+  bool relabelled = false, allow_relabel = true, env_relabel = true, env_timing = false;
   int mode = GLBA_MODE_CERES;                 // formulation the loaded problem's poses are in (glba_mode)
   Buf hmax;                                   // GLBA_MODE_G2O: max Hessian diagonal (bit pattern of a double)
   Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
@@ -414,7 +414,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->xtab, (size_t)XTAB * n_cam); ENSURE(double, ctx->partA, ctx->grid_c); ENSURE(double, ctx->partB, ctx->grid_c);
   ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8); ENSURE(double, ctx->part_pm2, 5 * 64);
   CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned), s));
-  ctx->timing = (n >= 200000); ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1)); ENSURE(double, ctx->part_cm2, 27 * (size_t)std::max(ctx->n_chunks, 1));
+  ctx->timing = (n >= 200000) || ctx->env_timing; ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1)); ENSURE(double, ctx->part_cm2, 27 * (size_t)std::max(ctx->n_chunks, 1));
   ENSURE(double, ctx->acc27, 54 * (size_t)n_cam + NSCAL);     // [Schur sums 27C | Hessian sums 27C | scalars]: contiguous for one all-reduce
   ctx->d_accB = ctx->acc27.as<double>(); ctx->d_accA = ctx->d_accB + 27 * (size_t)n_cam; ctx->d_scal = ctx->d_accA + 27 * (size_t)n_cam; ENSURE(double, ctx->yhat, 6 * (size_t)n_cam);
   ENSURE(double, ctx->Bc, 36 * (size_t)n_cam); ENSURE(double, ctx->gc, 6 * (size_t)n_cam); ENSURE(double, ctx->sc, 6 * (size_t)n_cam);
@@ -1005,6 +1005,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) return GLBA_E_CUDA;
   glba_ctx* ctx = new glba_ctx();
   ctx->device = cfg->device; ctx->rank = cfg->rank; ctx->world = cfg->world;
+  if (const char* e = std::getenv("GLBA_TIMING")) ctx->env_timing = (e[0] == '1');          // diagnostic: phase timings for small problems too
   if (const char* e = std::getenv("GLBA_RELABEL")) ctx->env_relabel = (e[0] != '0');   // diagnostic: GLBA_RELABEL=0 keeps the caller's point order
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GLBA_E_CUDA; } ctx->own_stream = true; }

@@ -23,13 +23,16 @@ constexpr int DN_MAXQ = (DN_MAXCAM * (DN_MAXCAM + 1) / 2 + DN_PAIRS_PER_PASS - 1
 
 // lower Cholesky factor of a symmetric 3x3 (00,01,02,11,12,22); zeros if not PD
 __device__ __forceinline__ void chol3(const double* C, double* L /* l00 l10 l11 l20 l21 l22 */) {
-  const double l00 = sqrt(fmax(C[0], 0.0));
-  const double i00 = l00 > 0.0 ? 1.0 / l00 : 0.0;
+  // reciprocal square roots: one special-function chain per pivot instead of a square root and a divide
+  const double i00 = C[0] > 0.0 ? rsqrt(C[0]) : 0.0;
+  const double l00 = C[0] > 0.0 ? C[0] * i00 : 0.0;
   const double l10 = C[1] * i00, l20 = C[2] * i00;
-  const double l11 = sqrt(fmax(C[3] - l10 * l10, 0.0));
-  const double i11 = l11 > 0.0 ? 1.0 / l11 : 0.0;
+  const double d1 = C[3] - l10 * l10;
+  const double i11 = d1 > 0.0 ? rsqrt(d1) : 0.0;
+  const double l11 = d1 > 0.0 ? d1 * i11 : 0.0;
   const double l21 = (C[4] - l20 * l10) * i11;
-  const double l22 = sqrt(fmax(C[5] - l20 * l20 - l21 * l21, 0.0));
+  const double d2 = C[5] - l20 * l20 - l21 * l21;
+  const double l22 = d2 > 0.0 ? d2 * rsqrt(d2) : 0.0;
   L[0] = l00; L[1] = l10; L[2] = l11; L[3] = l20; L[4] = l21; L[5] = l22;
 }
 
@@ -42,20 +45,23 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
   double* V = dsm;                                   // [DN_TP][n_cam][18]
   double* Wu = V + (size_t)DN_TP * n_cam * 18;       // [DN_TP][n_cam][6]
   unsigned* pres = reinterpret_cast<unsigned*>(Wu + (size_t)DN_TP * n_cam * 6);   // [DN_TP]
-  unsigned char* pair_i = reinterpret_cast<unsigned char*>(pres + DN_TP);         // [n_pairs]
-  unsigned char* pair_k = pair_i + n_pairs;
   const int tid = threadIdx.x;
-  for (int p = tid; p < n_pairs; p += DN_NT) {       // pair p -> (i,k), i <= k, row-major upper
-    int i = 0, rem = p;
-    while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
-    pair_i[p] = (unsigned char)i; pair_k[p] = (unsigned char)(i + rem);
-  }
   const int sub = tid / 36, ent = tid - sub * 36;    // sub-CTA of 36 threads: one 6x6 block
   const int rr = ent / 6, cc = ent - rr * 6;
   const bool acc_active = sub < DN_PAIRS_PER_PASS;
   double acc[DN_MAXQ];
+  unsigned pk_need[DN_MAXQ], pk_off[DN_MAXQ];        // per (thread, q): presence bits of the pair's two cameras, offsets of its two V rows
 #pragma unroll
-  for (int q = 0; q < DN_MAXQ; ++q) acc[q] = 0.0;
+  for (int q = 0; q < DN_MAXQ; ++q) {
+    acc[q] = 0.0;
+    const int pr = sub + q * DN_PAIRS_PER_PASS;
+    int i = 0, rem = pr;
+    const bool ok = acc_active && pr < n_pairs;
+    if (ok) while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
+    const int k = i + rem;
+    pk_need[q] = ok ? ((1u << i) | (1u << k)) : 0xffffffffu;     // never satisfied: a mask has at most DN_MAXCAM bits
+    pk_off[q] = ok ? ((unsigned)(i * 18 + rr * 3) | ((unsigned)(k * 18 + cc * 3) << 16)) : 0u;
+  }
   double racc = 0.0;                                 // thread t < 6*n_cam: rhs entry t
   const int p_begin = blockIdx.x * pts_per_cta;
   const int p_end = min(A.n_pt, p_begin + pts_per_cta);
@@ -112,16 +118,15 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
       const unsigned mask = pres[p];
       if (!mask) continue;
       if (acc_active) {
+        const double* Vp = V + (size_t)p * n_cam * 18;
 #pragma unroll
         for (int q = 0; q < DN_MAXQ; ++q) {
-          const int pr = sub + q * DN_PAIRS_PER_PASS;
-          if (pr < n_pairs) {
-            const int i = pair_i[pr], k = pair_k[pr];
-            if (((mask >> i) & 1u) && ((mask >> k) & 1u)) {
-              const double* vi = V + ((size_t)p * n_cam + i) * 18 + rr * 3;
-              const double* vk = V + ((size_t)p * n_cam + k) * 18 + cc * 3;
-              acc[q] += vi[0] * vk[0] + vi[1] * vk[1] + vi[2] * vk[2];
-            }
+          // the pair of this (thread, q) is the same for every point: it lives in a register (pk[q]), not in a shared table
+          const unsigned need = pk_need[q];
+          if ((mask & need) == need) {
+            const double* vi = Vp + (pk_off[q] & 0xffffu);
+            const double* vk = Vp + (pk_off[q] >> 16);
+            acc[q] += vi[0] * vk[0] + vi[1] * vk[1] + vi[2] * vk[2];
           }
         }
       }
@@ -247,8 +252,8 @@ k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
 #pragma unroll
         for (int k = 0; k < j; ++k) d -= Lb[j * (j + 1) / 2 + k] * Lb[j * (j + 1) / 2 + k];
         if (!(d > 0.0)) { bad = true; d = 1.0; }
-        const double ljj = sqrt(d);
-        const double inv = 1.0 / ljj;
+        const double inv = rsqrt(d);          // one reciprocal square root instead of sqrt + divide: the pivot chain is
+        const double ljj = d * inv;           // the serial part of this kernel (6 dependent pivots per block column)
         Lb[j * (j + 1) / 2 + j] = ljj; id[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {

@@ -258,9 +258,16 @@ def test_sliding_window_schedule(ctx, oracle, min_obs):
             assert rel[damped].max() <= 1e-9, (first, rel[damped].max())
             assert abs(s["final_cost"] - so["final_cost"]) <= 1e-3 * so["final_cost"], (first, s["final_cost"], so["final_cost"])
         else:
-            # rank-deficient point blocks: trajectories agree early (first 5 iterations to 1e-8) and then drift; both must
-            # still descend to a comparable optimum (measured worst case: 3.5 % apart mid-way on one window)
-            assert rel[:min(n, 5)].max() <= 1e-8, (first, rel[:5])
+            # rank-deficient point blocks: trajectories agree early and then drift (every iteration amplifies rounding
+            # differences 10-100x); both must still descend to a comparable optimum (measured worst case: 3.5 % apart
+            # mid-way on one window).  "Early" is gated against the window's own sensitivity: the oracle re-run with the
+            # points moved by a few ulp sets the floor, as in tests/test_gpu_fuzz.py
+            jig = sub.copy()
+            jig.pt = sub.pt * (1.0 + 1e-15 * np.random.default_rng(first).standard_normal(sub.pt.shape))
+            _, sj = oracle.solve(jig)
+            m = min(n, 5, len(sj["cost"]))
+            floor = float((np.abs(np.array(sj["cost"][:m]) - np.array(so["cost"][:m])) / np.array(so["cost"][:m])).max())
+            assert rel[:m].max() <= max(1e-8, 100.0 * floor), (first, rel[:5], floor)
             assert s["final_cost"] <= s["initial_cost"] and abs(s["final_cost"] - so["final_cost"]) <= 0.1 * so["final_cost"], first
         cam[first:first + 10] = ref.cam
         pt[keep] = ref.pt
