@@ -113,6 +113,11 @@ def run_reference(args):
         sub, _ = scene.shard_by_point(prob, int(round(1.0 / frac)), 0)
     else:
         sub = prob
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)          # all host threads, whatever OMP_NUM_THREADS the launcher exported
     threads = oracle.num_threads()
     for _ in range(args.warmup):
         oracle.step(sub, 1e4)

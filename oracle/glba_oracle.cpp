@@ -812,6 +812,15 @@ void glbao_default_options(glba_options* o) {
   o->mode = GLBA_MODE_CERES; o->g2o_tau = 1e-5; o->g2o_max_trials = 10;
 }
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline arm asks for the box's cores explicitly
+void glbao_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int glbao_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -57,6 +57,11 @@ def num_threads():
     return lib().glbao_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().glbao_set_num_threads(int(n))
+
+
 def cost(prob, opt=None):
     opt = opt or options()
     c = C.c_double()
