@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "glba_triangulate_filter",
     "glba_map_create", "glba_map_destroy", "glba_map_size", "glba_map_add_keyframes", "glba_map_add_points",
     "glba_map_add_observations", "glba_map_set_bad", "glba_map_write_keyframes", "glba_map_read_keyframes",
-    "glba_map_write_points", "glba_map_read_points", "glba_map_solve_window",
+    "glba_map_write_points", "glba_map_read_points", "glba_map_solve_window", "glba_map_cull_points",
 )
 
 
@@ -95,6 +95,7 @@ def lib():
     L.glba_map_read_points.argtypes = [vp, i32, i32, vp, vp]
     L.glba_map_solve_window.argtypes = [vp, i32, i32, i32, i32, C.POINTER(_abi.Options), C.POINTER(_abi.Summary), C.POINTER(i32),
                                         C.POINTER(C.c_int64)]
+    L.glba_map_cull_points.argtypes = [vp, i32, i32, i32, f64, C.POINTER(i32), C.POINTER(i32), vp, i32]
     _LIB = L
     return L
 
@@ -346,3 +347,13 @@ class DeviceMap:
         d = summ.as_dict()
         d["n_pt"], d["n_obs"] = npt.value, nobs.value
         return d
+
+    def cull_points(self, first_kf, last_kf, min_obs=3, max_mean_err=1.0):
+        """post_ba_map_point_culling on the resident map.  Returns (n_candidates, culled point ids)."""
+        ncand, ncull = C.c_int32(), C.c_int32()
+        cap = self.size()[1]
+        ids = np.zeros(max(cap, 1), np.int32)
+        st = lib().glba_map_cull_points(self._h, int(first_kf), int(last_kf), int(min_obs), float(max_mean_err), C.byref(ncand),
+                                        C.byref(ncull), ids.ctypes.data, cap)
+        self._ctx._check(st, "glba_map_cull_points")
+        return ncand.value, ids[:ncull.value].copy()

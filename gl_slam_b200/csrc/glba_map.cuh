@@ -59,6 +59,20 @@ __global__ void k_map_scatter_pt(const int n, const int* __restrict__ w_id, cons
   const size_t j = w_id[l];
   pt[3 * j] = w_pt[3 * (size_t)l]; pt[3 * j + 1] = w_pt[3 * (size_t)l + 1]; pt[3 * j + 2] = w_pt[3 * (size_t)l + 2];
 }
+// culling candidates: non-bad points whose earliest observation lies in keyframes [a, b]
+__global__ void k_map_first_kf(const long n, const int* __restrict__ o_kf, const int* __restrict__ o_pt, int* __restrict__ first) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) atomicMin(first + o_pt[k], o_kf[k]);
+}
+__global__ void k_map_keep_first(const int n_pt, const int* __restrict__ first, const uint8_t* __restrict__ bad, const int a, const int b,
+                                 int* __restrict__ keep) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j <= n_pt) keep[j] = (j < n_pt && !bad[j] && first[j] >= a && first[j] <= b) ? 1 : 0;
+}
+__global__ void k_map_sel_kept(const long n, const int* __restrict__ o_pt, const int* __restrict__ keep, int* __restrict__ sel) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= n) sel[k] = (k < n && keep[o_pt[k]]) ? 1 : 0;
+}
 __global__ void k_map_set_u8(const int n, const int* __restrict__ ids, const uint8_t v, uint8_t* __restrict__ a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[ids[i]] = v;
@@ -308,6 +322,72 @@ int glba_map_solve_window(glba_map* m, int32_t first_kf, int32_t window, int32_t
   if (wp) LAUNCH(k_map_scatter_pt, cdiv(wp, 256), 256, wp, (const int*)m->w_id.as<int>(), (const double*)m->w_pt.as<double>(), m->pt.as<double>());
   CU(cudaStreamSynchronize(s));
   return GLBA_OK;
+}
+
+// post_ba_map_point_culling (slam_core.cpp:977-1038) on the resident map: candidates are the non-bad points first observed
+// by keyframes [first_kf, last_kf] (the reference: [run_window - local_ba_window, run_window - 4], :981-992); a candidate
+// is flagged bad when it lies behind one of its cameras, has fewer than min_obs observations or a mean reprojection
+// error above max_mean_err over ALL its observations (:993-1035).  Flags are set in the map; the culled ids come back.
+int glba_map_cull_points(glba_map* m, int32_t first_kf, int32_t last_kf, int32_t min_obs, double max_mean_err, int32_t* n_candidates,
+                         int32_t* n_culled, int32_t* culled_ids, int32_t cap) {
+  if (!m) return GLBA_E_INVALID_ARG;
+  glba_ctx* ctx = m->ctx;
+  if (n_candidates) *n_candidates = 0;
+  if (n_culled) *n_culled = 0;
+  if (cap < 0 || (cap > 0 && !culled_ids)) return fail(ctx, GLBA_E_INVALID_ARG, "map_cull_points: bad argument");
+  first_kf = std::max(first_kf, 0); last_kf = std::min(last_kf, m->n_kf - 1);
+  if (first_kf > last_kf || m->n_pt == 0 || m->n_obs == 0) return GLBA_OK;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int n_pt = m->n_pt;
+  const long n = m->n_obs;
+  ENSURE(int, m->cnt, (size_t)n_pt + 1); ENSURE(int, m->keep, (size_t)n_pt + 1); ENSURE(int, m->local, (size_t)n_pt + 1);
+  ENSURE(int, m->sel, (size_t)n + 1); ENSURE(int, m->pos, (size_t)n + 1);
+  CU(cudaMemsetAsync(m->cnt.p, 0x7f, sizeof(int) * ((size_t)n_pt + 1), s));            // "first keyframe" = +large
+  LAUNCH(k_map_first_kf, cdiv(n, 256), 256, n, (const int*)m->o_kf.as<int>(), (const int*)m->o_pt.as<int>(), m->cnt.as<int>());
+  LAUNCH(k_map_keep_first, cdiv(n_pt + 1, 256), 256, n_pt, (const int*)m->cnt.as<int>(), (const uint8_t*)m->bad.as<uint8_t>(), first_kf, last_kf,
+         m->keep.as<int>());
+  LAUNCH(k_map_sel_kept, cdiv(n + 1, 256), 256, n, (const int*)m->o_pt.as<int>(), (const int*)m->keep.as<int>(), m->sel.as<int>());
+  size_t tb1 = 0, tb2 = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb1, m->keep.as<int>(), m->local.as<int>(), n_pt + 1, s));
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb2, m->sel.as<int>(), m->pos.as<int>(), (int)(n + 1), s));
+  ENSURE(char, m->scan_tmp, std::max(tb1, tb2));
+  tb1 = tb2 = m->scan_tmp.cap;
+  CU(cub::DeviceScan::ExclusiveSum(m->scan_tmp.p, tb1, m->keep.as<int>(), m->local.as<int>(), n_pt + 1, s));
+  CU(cub::DeviceScan::ExclusiveSum(m->scan_tmp.p, tb2, m->sel.as<int>(), m->pos.as<int>(), (int)(n + 1), s));
+  g_launches.fetch_add(2);
+  CU(cudaMemcpyAsync(ctx->h_flags, m->local.as<int>() + n_pt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(ctx->h_flags + 1, m->pos.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const int wp = ctx->h_flags[0];
+  const long wn = ctx->h_flags[1];
+  if (n_candidates) *n_candidates = wp;
+  if (wp == 0) return GLBA_OK;
+  ENSURE(double, m->w_pt, 3 * (size_t)wp); ENSURE(int, m->w_id, wp);
+  ENSURE(int, m->w_ocam, wn); ENSURE(int, m->w_opt, wn); ENSURE(double, m->w_u, wn); ENSURE(double, m->w_v, wn);
+  LAUNCH(k_map_gather_pt, cdiv(n_pt, 256), 256, n_pt, (const int*)m->keep.as<int>(), (const int*)m->local.as<int>(), (const double*)m->pt.as<double>(),
+         m->w_pt.as<double>(), m->w_id.as<int>());
+  LAUNCH(k_map_gather_obs, cdiv(n, 256), 256, n, (const int*)m->o_kf.as<int>(), (const int*)m->o_pt.as<int>(), (const double2*)m->o_uv.as<double2>(),
+         (const int*)m->sel.as<int>(), (const int*)m->pos.as<int>(), (const int*)m->local.as<int>(), 0, m->w_ocam.as<int>(), m->w_opt.as<int>(),
+         m->w_u.as<double>(), m->w_v.as<double>());
+  glba_problem p{};
+  p.n_cam = m->n_kf; p.n_pt = wp; p.n_obs = wn;            // every keyframe: a candidate's observations may lie anywhere
+  p.cam = m->cam.as<double>(); p.pt = m->w_pt.as<double>();
+  p.obs_cam = m->w_ocam.as<int>(); p.obs_pt = m->w_opt.as<int>(); p.obs_u = m->w_u.as<double>(); p.obs_v = m->w_v.as<double>();
+  p.fx = m->K[0]; p.fy = m->K[1]; p.cx = m->K[2]; p.cy = m->K[3];
+  p.memspace = GLBA_MEM_DEVICE;
+  std::vector<uint8_t> flags((size_t)wp);
+  std::vector<int> ids((size_t)wp);
+  int st = glba_cull_points(ctx, &p, min_obs, max_mean_err, flags.data(), nullptr);
+  if (st) return st;
+  CU(cudaMemcpyAsync(ids.data(), m->w_id.p, sizeof(int) * (size_t)wp, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  std::vector<int32_t> culled;
+  for (int l = 0; l < wp; ++l) if (flags[l]) culled.push_back(ids[l]);
+  if (n_culled) *n_culled = (int32_t)culled.size();
+  for (size_t q = 0; q < culled.size() && (int32_t)q < cap; ++q) culled_ids[q] = culled[q];
+  if (culled.empty()) return GLBA_OK;
+  return glba_map_set_bad(m, (int32_t)culled.size(), culled.data(), 1);
 }
 
 }  // extern "C"

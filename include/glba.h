@@ -303,6 +303,12 @@ int glba_map_read_points(glba_map* map, int32_t first, int32_t n, double* xyz, u
  * and points are written into the map unless the solve FAILED.  n_pt_used / n_obs_used (may be NULL) = window size. */
 int glba_map_solve_window(glba_map* map, int32_t first_kf, int32_t window, int32_t n_fixed, int32_t min_obs,
                           const glba_options* opt, glba_summary* summary, int32_t* n_pt_used, int64_t* n_obs_used);
+/* post_ba_map_point_culling (slam_core.cpp:977-1038) on the resident map: candidates = non-bad points first observed by
+ * keyframes [first_kf, last_kf] (reference: [run_window - local_ba_window, run_window - 4]); a candidate becomes bad if it
+ * lies behind one of its cameras, has < min_obs observations, or a mean reprojection error > max_mean_err over ALL its
+ * observations.  The flags are set in the map; up to `cap` culled point ids are written to culled_ids (may be NULL). */
+int glba_map_cull_points(glba_map* map, int32_t first_kf, int32_t last_kf, int32_t min_obs, double max_mean_err,
+                         int32_t* n_candidates, int32_t* n_culled, int32_t* culled_ids, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -277,6 +277,19 @@ class ResidentMap {
     return true;
   }
 
+  // post_ba_map_point_culling (slam_core.cpp:977-1038) entirely on the resident map: candidates first seen by keyframes
+  // [run_window - local_ba_window, run_window - 4]; sets MapPoint::is_bad in `map` for the culled points.  Returns the
+  // number of points culled, -1 on error.
+  int cull(Map& map, int run_window, int local_ba_window, double max_err = 1.0, int min_obs = 3) {
+    if (!map_) return -1;
+    std::vector<int32_t> ids(pt_ids_.size());
+    int32_t n_cand = 0, n_culled = 0;
+    if (glba_map_cull_points(map_, run_window - local_ba_window - kf_base_, run_window - 4 - kf_base_, min_obs, max_err, &n_cand, &n_culled,
+                             ids.data(), (int32_t)ids.size()) != GLBA_OK) return -1;
+    for (int32_t q = 0; q < n_culled; ++q) { bad_[ids[q]] = 1; map.map_points[pt_ids_[ids[q]]].is_bad = true; }
+    return n_culled;
+  }
+
   // is_bad flags set by the host since the last sync (post_ba_map_point_culling, slam_core.cpp:977-1038)
   bool mark_bad(const std::vector<int>& mpids) {
     std::vector<int32_t> ids;

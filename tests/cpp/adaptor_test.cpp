@@ -154,6 +154,7 @@ int main(int argc, char** argv) {
     std::mutex map_mutex, tracking_mutex;
     glba_summary s;
     bool ok = false;
+    int resident_culled = -2;
     if (mode == "resident") {
       // grow the mirror the way the mapping thread would: keyframe by keyframe, a sync after each
       ResidentMap rm(be, K);
@@ -172,6 +173,7 @@ int main(int argc, char** argv) {
         if (!rm.sync(grown)) { std::cout << "FAIL sync\n"; return 1; }
       }
       ok = full_ba_resident(be, rm, map_mutex, map, window, run_window, &tracking_mutex, nullptr, &s);
+      resident_culled = rm.cull(map, run_window, window, 1.0, 3);
     } else {
       ok = full_ba(be, map_mutex, map, K, window, run_window, &tracking_mutex, nullptr, &s);
     }
@@ -185,7 +187,7 @@ int main(int argc, char** argv) {
     }
     for (int j = 0; j < (int)map.map_points.size(); ++j) { const MapPoint& mp = map.map_points[1000 + j]; std::cout << mp.position.x << " " << mp.position.y << " " << mp.position.z << " "; }
     std::cout << "\n";
-    const int culled = post_ba_map_point_culling(be, map, K, run_window, window, 1.0, 3);
+    const int culled = (mode == "resident") ? resident_culled : post_ba_map_point_culling(be, map, K, run_window, window, 1.0, 3);
     std::cout << culled << "\n";
     for (int j = 0; j < (int)map.map_points.size(); ++j) std::cout << (map.map_points[1000 + j].is_bad ? 1 : 0) << " ";
     std::cout << "\n";

@@ -153,3 +153,44 @@ def test_empty_window(ctx):
     s = m.solve_window(0, 4)
     assert (s["n_pt"], s["n_obs"]) == (0, 0)
     m.close()
+
+
+def test_map_cull_points(ctx):
+    """post_ba_map_point_culling on the resident map against the same rule in numpy (slam_core.cpp:977-1038)."""
+    prob = scene.make_scene(30, 3000, lambda rng, n: 3 + rng.poisson(2.0, size=n), seed=12, rot_sigma=0.0, pos_sigma=0.0, pt_sigma=0.0,
+                            outlier_frac=0.02)                       # a converged map: 0.5 px noise, a few outliers
+    rng = np.random.default_rng(4)
+    wrong = rng.choice(prob.n_pt, 200, replace=False)
+    prob.pt[wrong[:150]] += rng.normal(0.0, 0.5, (150, 3))            # large reprojection error
+    prob.pt[wrong[150:]] -= np.array([0.0, 0.0, 80.0])                # behind their cameras
+    m, n_added = replay(ctx, prob)
+    pre_bad = np.zeros(n_added, bool)
+    pre_bad[::17] = True
+    m.set_bad(np.nonzero(pre_bad)[0])
+    first_kf, last_kf, min_obs, max_err = 5, 20, 4, 1.0
+    ncand, culled = m.cull_points(first_kf, last_kf, min_obs=min_obs, max_mean_err=max_err)
+    # reference rule
+    sel = prob.obs_pt < n_added
+    oc, op = prob.obs_cam[sel], prob.obs_pt[sel]
+    u, v, z = scene.project(prob.cam, prob.pt, oc, op, prob.K)
+    err = np.hypot(u - prob.obs_u[sel], v - prob.obs_v[sel])
+    first = np.full(n_added, 10 ** 9)
+    np.minimum.at(first, op, oc)
+    cnt = np.bincount(op, minlength=n_added)
+    behind = np.zeros(n_added, bool)
+    np.logical_or.at(behind, op, z <= 0.0)
+    mean = np.bincount(op, weights=err, minlength=n_added) / np.maximum(cnt, 1)
+    cand = ~pre_bad & (first >= first_kf) & (first <= last_kf)
+    want = cand & (behind | (cnt < min_obs) | (mean > max_err))
+    near = cand & ~behind & (np.abs(mean - max_err) < 1e-9)           # ties at the threshold would be rounding-dependent
+    assert not near.any()
+    assert ncand == int(cand.sum())
+    assert sorted(culled.tolist()) == np.nonzero(want)[0].tolist()
+    assert want.sum() > 50 and (cand & ~want).sum() > 50
+    _, bad_dev = m.read_points()
+    assert np.array_equal(bad_dev.astype(bool), pre_bad | want)
+    # a second pass finds nothing new among the same candidates; an empty range is a no-op
+    ncand2, culled2 = m.cull_points(first_kf, last_kf, min_obs=min_obs, max_mean_err=max_err)
+    assert ncand2 == int((cand & ~want).sum()) and len(culled2) == 0
+    assert m.cull_points(25, 20)[0] == 0
+    m.close()
