@@ -84,3 +84,15 @@ def test_product_never_touches_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), os.path.join(dirpath, f)
     out = subprocess.check_output(["ldd", g.LIB_PATH]).decode()
     assert "oracle" not in out
+
+
+def test_docs_name_only_exported_symbols():
+    """Every glba_* function INTEGRATION.md / README.md / DESIGN.md mention exists in include/glba.h (docs do not drift)."""
+    import re
+    header = open(os.path.join(ROOT, "include", "glba.h")).read()
+    declared = set(re.findall(r"\b(glba_[a-z0-9_]+)\s*\(", header))
+    types = set(re.findall(r"\b(glba_[a-z0-9_]+)\b", header)) - declared
+    for doc in ("INTEGRATION.md", "README.md", "DESIGN.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        for name in set(re.findall(r"\b(glba_[a-z0-9_]+)\s*\(", text)):
+            assert name in declared or name in types, f"{doc} mentions {name}(), which include/glba.h does not declare"
