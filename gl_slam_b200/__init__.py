@@ -6,6 +6,7 @@ only marshals numpy buffers.  There is NO CPU fallback: if the shared library is
 device is present, calls raise.
 """
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -129,9 +130,12 @@ class Context:
             self._h = C.c_void_p()
             raise GlbaError(st, "glba_create")
         self.rank, self.world, self.device = rank, world, device
+        self._maps = weakref.WeakSet()      # resident maps created on this context: they must be destroyed first
 
     def close(self):
         if self._h:
+            for m in list(getattr(self, "_maps", ())):
+                m.close()
             lib().glba_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -274,6 +278,7 @@ class DeviceMap:
         if st:
             self._h = C.c_void_p()
             ctx._check(st, "glba_map_create")
+        ctx._maps.add(self)
 
     def close(self):
         if self._h:

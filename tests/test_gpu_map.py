@@ -194,3 +194,13 @@ def test_map_cull_points(ctx):
     assert ncand2 == int((cand & ~want).sum()) and len(culled2) == 0
     assert m.cull_points(25, 20)[0] == 0
     m.close()
+
+
+def test_context_closed_before_its_map():
+    """Closing a context destroys the maps created on it first; closing such a map afterwards is a no-op, not a crash."""
+    c = g.Context()
+    m = g.DeviceMap(c, scene.KITTI_K)
+    m.add_keyframes(np.zeros((2, 6)))
+    c.close()
+    m.close()
+    assert not m._h
