@@ -13,10 +13,16 @@
 
 namespace glba {
 
-constexpr int NT_T = 256;
-// Observations per thread in phase 1 (template parameter OPT): 4 for large maps (tile = 1024 observations, ~200 points:
-// phase 2 fills the CTA), 1 for small ones (tile = 256 observations: 4x more CTAs and a 4x shorter dependent chain per
-// thread — what matters when the whole map is a few tiles).
+#ifndef GLBA_NT_T
+#define GLBA_NT_T 128
+#endif
+constexpr int NT_T = GLBA_NT_T;
+// 128 threads per tile CTA: measured on C4 against 64 / 256 / 512 threads at 2..8 observations per thread, 128 x 4 is the
+// best shape for all three tile kernels (k_linearize_tile 0.219 vs 0.226 ms, k_point_tile<0> 0.077 vs 0.081, <1> 0.162 vs
+// 0.169 for 256 x 4): more, smaller CTAs per SM interleave their barrier-separated phases better.
+// Observations per thread in phase 1 (template parameter OPT): 4 for large maps (tile = 512 observations, ~100 points),
+// 1 for small ones (tile = 128 observations: more CTAs and a 4x shorter dependent chain per thread — what matters when
+// the whole map is a few tiles).
 #ifndef GLBA_OPT_LARGE
 #define GLBA_OPT_LARGE 4
 #endif
