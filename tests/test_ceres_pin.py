@@ -60,3 +60,55 @@ def test_gpu_matches_ceres(ctx, path):
     prob, loss, c, cost_ceres, _ = _load(path)
     got, s = ctx.solve(prob, g.options(loss=loss))
     _check(c, cost_ceres, s, got.cam, got.pt)
+
+
+# ---- the same for the g2o formulation: tools/g2o_crosscheck.cpp -> tests/golden/g2o/<name>.json ------------------------
+G2O = sorted(glob.glob(os.path.join(GOLDEN_DIR, "g2o", "*.json")))
+
+
+def _load_g2o(path):
+    from gl_slam_b200 import scene
+    with open(path) as f:
+        c = json.load(f)
+    prob, _ = load_golden(os.path.splitext(os.path.basename(path))[0])
+    prob = scene.as_g2o(prob)
+    prob.cam_fixed = np.zeros(prob.n_cam, np.uint8)
+    prob.cam_fixed[0] = 1                                   # the archived code fixes camera 0 only
+    prob.K = (prob.K[0], prob.K[0], prob.K[2], prob.K[3])   # CameraParameters: one focal length
+    opt = dict(mode=1, loss=1 if c["huber"] > 0 else 0, loss_scale=c["huber"] if c["huber"] > 0 else 1.0, max_iters=c["iterations_requested"])
+    return prob, opt, c
+
+
+def _check_g2o(c, s, cam, pt):
+    # g2o reports chi2 (not halved) after every iteration and the number of Levenberg trials it took; every trial is one
+    # entry of our summary, accepted ones close an iteration
+    acc = np.nonzero(np.asarray(s["accepted"]))[0]
+    chi2 = 2.0 * np.asarray(s["cost"])[acc]
+    want = np.array([i["chi2"] for i in c["iterations"]])
+    assert len(chi2) == len(want) == s["n_successful"]
+    assert np.max(np.abs(chi2 - want) / want) < 1e-9
+    trials = np.diff(np.concatenate([[0], acc]))
+    assert trials.tolist() == [i["levenberg_trials"] for i in c["iterations"]]
+    assert abs(2.0 * s["initial_cost"] - c["chi2_initial"]) <= 1e-12 * c["chi2_initial"]
+    assert np.allclose(cam.ravel(), np.asarray(c["cam"]), rtol=1e-6, atol=1e-8)
+    assert np.allclose(pt.ravel(), np.asarray(c["pt"]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("path", G2O or [None])
+def test_oracle_matches_g2o(oracle, path):
+    if path is None:
+        pytest.skip("parity UNPINNED for GLBA_MODE_G2O: no tests/golden/g2o/*.json (run tools/g2o_crosscheck.cpp where g2o is installed)")
+    prob, opt, c = _load_g2o(path)
+    ref, s = oracle.solve(prob, oracle.options(**opt))
+    _check_g2o(c, s, ref.cam, ref.pt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", G2O or [None])
+def test_gpu_matches_g2o(ctx, path):
+    if path is None:
+        pytest.skip("no g2o trajectories committed")
+    import gl_slam_b200 as g
+    prob, opt, c = _load_g2o(path)
+    got, s = ctx.solve(prob, g.options(**opt))
+    _check_g2o(c, s, got.cam, got.pt)
