@@ -116,6 +116,8 @@ struct glba_ctx {
   bool has_dup = false;                                                              // some point is observed twice by one camera
   int dn_grid = 0, dn_ppc = 0;
   int cur = 0;
+  int n_sm = 148;              // multiprocessors of ctx->device (queried in glba_create)
+  bool attr_done = false;      // cudaFuncSetAttribute is per DEVICE: done once per context, after cudaSetDevice
   double* h_scal = nullptr;    // pinned
   CgState* h_cg = nullptr;     // pinned
   int* h_flags = nullptr;      // pinned
@@ -194,6 +196,13 @@ int allreduce(glba_ctx* ctx, void* p, size_t n, int op, int dtype = kNcclFloat64
 }
 #define AR(p, n, op) do { int s__ = allreduce(ctx, p, n, op); if (s__) return s__; } while (0)
 
+// launches are asynchronous and unchecked one by one; every phase ends with this (sticky launch-configuration errors)
+int check_launches(glba_ctx* ctx) {
+  CU(cudaGetLastError());
+  return GLBA_OK;
+}
+#define CHECK_LAUNCHES() do { int s__ = check_launches(ctx); if (s__) return s__; } while (0)
+
 int validate_problem(glba_ctx* ctx, const glba_problem* p) {
   if (!p) return fail(ctx, GLBA_E_INVALID_ARG, "problem is NULL");
   if (p->n_cam < 0 || p->n_pt < 0 || p->n_obs < 0) return fail(ctx, GLBA_E_INVALID_ARG, "negative size");
@@ -213,6 +222,16 @@ int validate_options(glba_ctx* ctx, const glba_options* o) {
   if (!(o->loss_scale > 0.0) || !(o->initial_radius > 0.0)) return fail(ctx, GLBA_E_INVALID_ARG, "loss_scale and initial_radius must be > 0");
   if (o->mode != GLBA_MODE_CERES && o->mode != GLBA_MODE_G2O) return fail(ctx, GLBA_E_INVALID_ARG, "unknown mode");
   if (o->mode == GLBA_MODE_G2O && (!(o->g2o_tau > 0.0) || o->g2o_max_trials < 1)) return fail(ctx, GLBA_E_INVALID_ARG, "g2o_tau must be > 0 and g2o_max_trials >= 1");
+  return GLBA_OK;
+}
+
+// Opt-in shared-memory sizes are a per-DEVICE property of a kernel: set them for the context's device when the
+// context is created (a process may hold contexts on several devices, and on several threads).
+int set_func_attributes(glba_ctx* ctx) {
+  CU(cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double))));
+  CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 2048)));
+  CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
+  ctx->attr_done = true;
   return GLBA_OK;
 }
 
@@ -383,7 +402,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
     LAUNCH(k_tile_cmin, ctx->n_tiles, NT_T, (const int*)ctx->tile_pt.as<int>(), (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->tile_cmin.as<int>());
   }
   ctx->grid_c = std::max(1, cdiv(n_cam, NT_C));
-  long per = (n + 148L * 8 - 1) / (148L * 8);
+  long per = (n + (long)ctx->n_sm * 8 - 1) / ((long)ctx->n_sm * 8);
   long chunk_cap = 4096;
   if (const char* e = std::getenv("GLBA_CHUNK")) chunk_cap = std::max(256L, std::atol(e));    // diagnostic
   int chunk = (int)std::min<long>(chunk_cap, std::max<long>(NT_CM, ((per + NT_CM - 1) / NT_CM) * NT_CM));
@@ -423,7 +442,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->cg_p, 6 * (size_t)n_cam); ENSURE(double, ctx->cg_q, 6 * (size_t)n_cam); ENSURE(double, ctx->pg, 6 * (size_t)n_cam);
   ENSURE(double, ctx->yg, 6 * (size_t)n_cam); ENSURE(CgState, ctx->cgst, 1);
   if (n_cam <= DN_MAXCAM && n_cam > 0) {
-    ctx->dn_grid = std::max(1, std::min(148, cdiv(n_pt, 16)));   // spread over all SMs; a CTA stages up to DN_TP points per barrier round
+    ctx->dn_grid = std::max(1, std::min(ctx->n_sm, cdiv(n_pt, 16)));   // spread over all SMs; a CTA stages up to DN_TP points per barrier round
     ctx->dn_ppc = cdiv(n_pt, ctx->dn_grid);
     const size_t len = (size_t)(n_cam * (n_cam + 1) / 2) * 36 + 6 * (size_t)n_cam;
     ENSURE(double, ctx->dn_part, len * ctx->dn_grid); ENSURE(double, ctx->dn_red, len); ENSURE(double, ctx->dn_full, (size_t)36 * n_cam * n_cam + 6 * (size_t)n_cam);
@@ -491,11 +510,6 @@ const int kStepSlots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
 int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
   const int c = ctx->cur;
   if (ctx->use_tiles) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CU(cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double))));
-      attr_set = true;
-    }
     const size_t smem = (size_t)8 * NT_T * ctx->opt * sizeof(double);
     const RedArgs RA = red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles);
 #define LIN_TILE_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
@@ -603,6 +617,7 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   if (with_schur && n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
   ctx->schur_fresh = with_schur;
   mark(ctx, -1);
+  CHECK_LAUNCHES();
   return GLBA_OK;
 }
 int do_linearize_schur(glba_ctx* ctx, const glba_options* o, int first, double radius) { return do_linearize_impl(ctx, o, first, radius, true); }
@@ -619,6 +634,7 @@ int do_redamp(glba_ctx* ctx, double radius) {
   LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 1, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal);
   if (ctx->world > 1) AR(ctx->d_scal + S_NOTPD_P, 1, kNcclSum);
   mark(ctx, -1);
+  CHECK_LAUNCHES();
   return GLBA_OK;
 }
 
@@ -637,10 +653,11 @@ int do_schur(glba_ctx* ctx, double radius) {
   if (n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
   ctx->schur_fresh = true;
   mark(ctx, -1);
+  CHECK_LAUNCHES();
   return GLBA_OK;
 }
 
-void launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, CgState* cg, int li) {
+int launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, CgState* cg, int li) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
   launch_point_pass0(ctx, o, cg, li);
@@ -649,7 +666,7 @@ void launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, Cg
   if (ctx->world > 1) {
     LAUNCH(k_chunk_sum<6>, cdiv((long)n_cam * 6, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
            ctx->yhat.as<double>(), (const CgState*)cg, li);
-    allreduce(ctx, ctx->yhat.as<double>(), 6 * (size_t)n_cam, kNcclSum);
+    AR(ctx->yhat.as<double>(), 6 * (size_t)n_cam, kNcclSum);
     LAUNCH(k_cg_q<false>, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
            (const double*)ctx->Bc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const double*)ctx->yhat.as<double>(),
            (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), (const double*)ctx->cg_p.as<double>(),
@@ -664,6 +681,7 @@ void launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, Cg
          ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), (const CgState*)cg, li, (const double*)ctx->partA.as<double>(), ctx->partB.as<double>());
   LAUNCH(k_cg_p, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
          ctx->xtab.as<double>(), cg, li, (const double*)ctx->partA.as<double>(), (const double*)ctx->partB.as<double>());
+  return GLBA_OK;
 }
 
 // Block-Jacobi PCG on the implicit Schur complement; solution in cg_x.  Returns iterations in *iters.
@@ -686,7 +704,8 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   const int poll = 8;
   int launched = 0;
   for (;;) {
-    for (int b = 0; b < poll && launched < max_it; ++b, ++launched) launch_cg_iteration(ctx, o, radius, cg, launched);
+    for (int b = 0; b < poll && launched < max_it; ++b, ++launched) { const int s__ = launch_cg_iteration(ctx, o, radius, cg, launched); if (s__) return s__; }
+    CHECK_LAUNCHES();
     CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_cg->done_at <= launched || launched >= max_it) break;
@@ -700,15 +719,9 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
 int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
-  static bool attr_set = false;
   const int n = 6 * n_cam;
   const size_t sm_schur = (size_t)DN_TP * n_cam * 24 * sizeof(double) + DN_TP * sizeof(unsigned) + 2 * (size_t)(n_cam * (n_cam + 1) / 2) + 16;
   const size_t sm_solve = ((size_t)n * (n | 1) + 2 * (size_t)n) * sizeof(double);
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 2048)));
-    CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
-    attr_set = true;
-  }
   const int len = (n_cam * (n_cam + 1) / 2) * 36 + n;
   mark(ctx, PH_SCHUR);
   k_dense_schur<<<ctx->dn_grid, DN_NT, sm_schur, ctx->stream>>>(pm_args(ctx, o), n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(),
@@ -729,6 +742,7 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
       ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->d_scal);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   mark(ctx, -1);
+  CHECK_LAUNCHES();
   return GLBA_OK;
 }
 
@@ -737,6 +751,22 @@ bool want_dense(const glba_ctx* ctx, const glba_options* o) {
   if (o->linsolve == GLBA_LINSOLVE_PCG) return false;
   if (o->linsolve == GLBA_LINSOLVE_DENSE) return true;
   return 6 * ctx->n_free_cam <= o->dense_max_dim;
+}
+
+// Sharded runs: d_scal[S_GMAX_P] holds only this rank's max |g_point|; the global value is the max over the per-rank
+// slots of the all-reduced payload.  EVERY read-back of the scalars goes through here, so all ranks take the same
+// gradient-tolerance decision (a rank leaving the loop alone would hang the others in their next collective).
+int read_scalars(glba_ctx* ctx) {
+  CHECK_LAUNCHES();
+  CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->world > 1) {
+    double m = 0.0;
+    for (int r = 0; r < ctx->world; ++r) m = std::max(m, ctx->h_scal[S_GSLOT0 + r]);
+    ctx->h_scal[S_GMAX_P] = m;
+  }
+  collect(ctx);
+  return GLBA_OK;
 }
 
 // candidate state, back-substitution, candidate cost; leaves the scalars in h_scal (synchronises)
@@ -751,23 +781,10 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
   if (n_pt) launch_point_pass1(ctx, o, radius);
   if (ctx->world > 1) AR(ctx->d_scal + S_COST_C, 5, kNcclSum);
   mark(ctx, -1);
-  CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  collect(ctx);
-  return GLBA_OK;
+  return read_scalars(ctx);
 }
 
-int fetch_scal(glba_ctx* ctx) {
-  CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (ctx->world > 1) {        // max |g_point| over all ranks: one slot per rank in the all-reduced payload
-    double m = 0.0;
-    for (int r = 0; r < ctx->world; ++r) m = std::max(m, ctx->h_scal[S_GSLOT0 + r]);
-    ctx->h_scal[S_GMAX_P] = m;
-  }
-  collect(ctx);
-  return GLBA_OK;
-}
+int fetch_scal(glba_ctx* ctx) { return read_scalars(ctx); }
 
 // The trust-region loop (Ceres TrustRegionMinimizer semantics; see oracle/glba_oracle.cpp for the
 // statement-by-statement restatement this mirrors).  One host synchronisation per LM iteration: the scalars of the
@@ -1005,6 +1022,8 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) return GLBA_E_CUDA;
   glba_ctx* ctx = new glba_ctx();
   ctx->device = cfg->device; ctx->rank = cfg->rank; ctx->world = cfg->world;
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0) ctx->n_sm = v; }
+  if (set_func_attributes(ctx) != GLBA_OK) { delete ctx; return GLBA_E_CUDA; }
   if (const char* e = std::getenv("GLBA_TIMING")) ctx->env_timing = (e[0] == '1');          // diagnostic: phase timings for small problems too
   if (const char* e = std::getenv("GLBA_RELABEL")) ctx->env_relabel = (e[0] != '0');   // diagnostic: GLBA_RELABEL=0 keeps the caller's point order
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
