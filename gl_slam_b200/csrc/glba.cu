@@ -26,6 +26,7 @@
 #include "glba_pose.cuh"
 #include "glba_dense.cuh"
 #include "glba_tiles.cuh"
+#include "glba_pipe.cuh"
 #include "glba_cam.cuh"
 #include "glba_triang.cuh"
 
@@ -98,7 +99,7 @@ struct glba_ctx {
   Buf pm_cam, pm_pt, pm_uv, pm2orig, pm2cm, pt_start, cm_pt, cm_uv, cm2pm, cam_start; // index
   Buf chunk_cam, chunk_begin, chunk_end, cam_chunk_start, cam_free, pt_free, sort_tmp, keys_tmp, flags;
   Buf cam[2], camtab[2], pt4[2], cam0, pt40;                                         // state (double-buffered)
-  Buf rec_pm, rec_cm, Craw, sp4, lam4, pblk, u4;
+  Buf rec_pm, rec_cm, Craw, sp4, lam4, cinv, u0p, u4;
   Buf part_pm, part_cm, acc27, yhat, Bc, gc, sc, lamc, Md, Minv, rhs, cg_x, cg_r, cg_p, cg_q, pg, yg, cgst;
   double *d_accA = nullptr, *d_accB = nullptr;   // per-camera partial sums of the linearise / Schur passes
   bool schur_fresh = false;                      // Schur pieces already built for the current linearisation and radius
@@ -110,6 +111,10 @@ struct glba_ctx {
   Buf hmax;                                   // GLBA_MODE_G2O: max Hessian diagonal (bit pattern of a double)
   Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
+  bool use_pipe = false;        // large maps: persistent TMA-fed tile kernels (glba_pipe.cuh)
+  bool env_pipe = true, env_force_large = false;
+  Buf tile_desc, tile_cams, pm_slot;
+  int occ_lin = 0, occ_pt0 = 0, occ_pt1 = 0;   // resident CTAs per SM of the pipelined kernels (occupancy API, per context)
   int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
   int n_tiles = 0, max_track = 0, grid_c = 0;
   Buf dn_part, dn_red, dn_full;                                                               // dense path: per-CTA S copies, reduced S
@@ -231,6 +236,20 @@ int set_func_attributes(glba_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double))));
   CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 2048)));
   CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
+  CU(cudaFuncSetAttribute(k_lin_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinSmem)));
+  CU(cudaFuncSetAttribute(k_pt_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<0>)));
+  CU(cudaFuncSetAttribute(k_pt_pipe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<1>)));
+  CU(cudaFuncSetAttribute(k_lin_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(k_pt_pipe<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(k_pt_pipe<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_lin, k_lin_pipe, P_NT, sizeof(LinSmem)));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_pt0, k_pt_pipe<0>, P_NT, sizeof(PtSmem<0>)));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_pt1, k_pt_pipe<1>, P_NT, sizeof(PtSmem<1>)));
+  if (ctx->occ_lin < 1 || ctx->occ_pt0 < 1 || ctx->occ_pt1 < 1) return fail(ctx, GLBA_E_CUDA, "pipelined tile kernels do not fit an SM");
+  if (const char* e = std::getenv("GLBA_OCC")) {          // diagnostic: cap the resident CTAs per SM of the pipelined kernels
+    const int cap = std::max(1, std::atoi(e));
+    ctx->occ_lin = std::min(ctx->occ_lin, cap); ctx->occ_pt0 = std::min(ctx->occ_pt0, cap); ctx->occ_pt1 = std::min(ctx->occ_pt1, cap);
+  }
   ctx->attr_done = true;
   return GLBA_OK;
 }
@@ -389,7 +408,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   ctx->has_dup = (ctx->h_flags[5] != 0);
   if (ctx->world > 1 && ctx->h_flags[6] != 0) return fail(ctx, GLBA_E_INVALID_ARG, "a rank holds an empty shard (%d of %d): every rank needs at least one observation", ctx->h_flags[6], ctx->world);
   ctx->max_track = ctx->h_flags[4];
-  ctx->opt = (n >= 400000) ? OPT_LARGE : OPT_SMALL;
+  ctx->opt = (n >= 400000 || ctx->env_force_large) ? OPT_LARGE : OPT_SMALL;
   if (ctx->max_track > NT_T * ctx->opt / 2) ctx->opt = OPT_LARGE;
   ctx->use_tiles = (n > 0 && ctx->max_track <= NT_T * ctx->opt / 2);
   ctx->n_tiles = 0;
@@ -400,6 +419,13 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
     LAUNCH(k_tile_starts, cdiv(ctx->n_tiles + 1, 256), 256, ctx->n_tiles, B, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->tile_pt.as<int>());
     ENSURE(int, ctx->tile_cmin, (size_t)ctx->n_tiles);
     LAUNCH(k_tile_cmin, ctx->n_tiles, NT_T, (const int*)ctx->tile_pt.as<int>(), (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->tile_cmin.as<int>());
+  }
+  ctx->use_pipe = ctx->use_tiles && ctx->opt == OPT_LARGE && ctx->env_pipe;
+  if (ctx->use_pipe) {      // per-tile descriptor, distinct-camera list and per-observation camera slot of the pipelined kernels
+    ENSURE(int4, ctx->tile_desc, (size_t)ctx->n_tiles); ENSURE(int, ctx->tile_cams, (size_t)TSLOTS * ctx->n_tiles); ENSURE(uint8_t, ctx->pm_slot, n);
+    CU(cudaMemsetAsync(ctx->tile_cams.p, 0xff, sizeof(int) * (size_t)TSLOTS * ctx->n_tiles, s));
+    LAUNCH(k_tile_meta, ctx->n_tiles, NT_T, (const int*)ctx->tile_pt.as<int>(), (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), n_cam,
+           ctx->tile_desc.as<int4>(), ctx->tile_cams.as<int>(), ctx->pm_slot.as<uint8_t>());
   }
   ctx->grid_c = std::max(1, cdiv(n_cam, NT_C));
   long per = (n + (long)ctx->n_sm * 8 - 1) / ((long)ctx->n_sm * 8);
@@ -428,7 +454,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   const int grid_pm = cdiv(n_pt, NT_PM);
   ENSURE(double4, ctx->rec_pm, n); ENSURE(double4, ctx->rec_cm, n);
   ENSURE(double, ctx->Craw, 9 * (size_t)n_pt); ENSURE(double4, ctx->sp4, n_pt); ENSURE(double4, ctx->lam4, n_pt);
-  ENSURE(double, ctx->pblk, (size_t)PBLK * n_pt); ENSURE(double4, ctx->u4, n_pt);
+  ENSURE(double, ctx->cinv, (size_t)PBLK * n_pt); ENSURE(double4, ctx->u4, n_pt);
   ENSURE(double, ctx->part_pm, 5 * (size_t)std::max(std::max(grid_pm, ctx->n_tiles), 1));
   ENSURE(double, ctx->xtab, (size_t)XTAB * n_cam); ENSURE(double, ctx->partA, ctx->grid_c); ENSURE(double, ctx->partB, ctx->grid_c);
   ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8); ENSURE(double, ctx->part_pm2, 5 * 64);
@@ -488,6 +514,10 @@ CmArgs cm_args(glba_ctx* ctx) {
   return A;
 }
 
+TileMeta tile_meta(glba_ctx* ctx) {
+  return TileMeta{ctx->tile_desc.as<int4>(), ctx->tile_cams.as<int>(), ctx->pm_slot.as<uint8_t>(), ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), ctx->n_tiles};
+}
+int pipe_grid(const glba_ctx* ctx, int occ) { return std::max(1, std::min(ctx->n_tiles, ctx->n_sm * occ)); }
 TileArgs tile_args(glba_ctx* ctx) { return TileArgs{ctx->tile_pt.as<int>(), ctx->pm_pt.as<int>(), ctx->tile_cmin.as<int>(), ctx->n_cam}; }
 
 int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
@@ -509,12 +539,18 @@ const int kStepSlots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
 // point-major half of a linearisation, INCLUDING the reduction of its scalars into d_scal
 int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
   const int c = ctx->cur;
-  if (ctx->use_tiles) {
+  if (ctx->use_pipe) {
+    k_lin_pipe<<<pipe_grid(ctx, ctx->occ_lin), P_NT, sizeof(LinSmem), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->pt4[c].as<double4>(),
+        (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(),
+        ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal,
+        1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots, true));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else if (ctx->use_tiles) {
     const size_t smem = (size_t)8 * NT_T * ctx->opt * sizeof(double);
     const RedArgs RA = red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles);
 #define LIN_TILE_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
     ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), \
-    ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), RA
+    ctx->cinv.as<double>(), ctx->u0p.as<double4>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), RA
     if (ctx->opt == OPT_LARGE) k_linearize_tile<OPT_LARGE><<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(LIN_TILE_ARGS);
     else k_linearize_tile<OPT_SMALL><<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(LIN_TILE_ARGS);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -523,7 +559,7 @@ int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, dou
   } else {
     LAUNCH(k_linearize_pm, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
-           ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->pblk.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal,
+           ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), first, o->jacobi_scaling, o->min_lm_diagonal,
            o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>());
     reduce_pm_partials(ctx, cdiv(ctx->n_pt, NT_PM), kLinSlots, 4);
   }
@@ -532,26 +568,39 @@ int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, dou
 
 void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg, int li) {
   const int c = ctx->cur;
-  if (ctx->use_tiles) {
+  if (ctx->use_pipe) {
+    k_pt_pipe<0><<<pipe_grid(ctx, ctx->occ_pt0), P_NT, sizeof(PtSmem<0>), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
+        (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(),
+        (const double4*)ctx->u0p.as<double4>(), ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr,
+        (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr, RedArgs{});
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else if (ctx->use_tiles) {
 #define PT0_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
-    (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, \
+    (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, \
     (double4*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr, RedArgs{}
     if (ctx->opt == OPT_LARGE) LAUNCH((k_point_tile<0, OPT_LARGE>), ctx->n_tiles, NT_T, PT0_ARGS);
     else LAUNCH((k_point_tile<0, OPT_SMALL>), ctx->n_tiles, NT_T, PT0_ARGS);
   }
   else
     LAUNCH(k_point_pass<0>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
-           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(),
            ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr,
            (const double4*)nullptr, 0.0, (double*)nullptr);
 }
 
 void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
   const int c = ctx->cur, d = c ^ 1;
-  if (ctx->use_tiles) {
+  if (ctx->use_pipe) {
+    k_pt_pipe<1><<<pipe_grid(ctx, ctx->occ_pt1), P_NT, sizeof(PtSmem<1>), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
+        (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(),
+        (const double4*)ctx->u0p.as<double4>(), (double4*)nullptr, (const CgState*)nullptr, 0, (const double4*)ctx->pt4[c].as<double4>(),
+        ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(), (const double*)ctx->Craw.as<double>(),
+        (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 5, kStepSlots, true));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else if (ctx->use_tiles) {
     const RedArgs RA = red_args(ctx, 5, kStepSlots, ctx->n_tiles <= kInKernelReduceMaxTiles);
 #define PT1_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
-    (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(), (double4*)nullptr, (const CgState*)nullptr, 0, \
+    (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), (double4*)nullptr, (const CgState*)nullptr, 0, \
     (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(), \
     (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), RA
     if (ctx->opt == OPT_LARGE) LAUNCH((k_point_tile<1, OPT_LARGE>), ctx->n_tiles, NT_T, PT1_ARGS);
@@ -560,7 +609,7 @@ void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
       LAUNCH(k_reduce_rows<-1>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 5, kStepSlots));
   } else {
     LAUNCH(k_point_pass<1>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
-           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->pblk.as<double>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(),
            (double4*)nullptr, (const CgState*)nullptr, 0, (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(),
            (const double*)ctx->camtab[d].as<double>(), (const double*)ctx->Craw.as<double>(), (const double4*)ctx->lam4.as<double4>(),
            1.0 / radius, ctx->part_pm.as<double>());
@@ -602,7 +651,7 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   if (with_schur) {
     mark(ctx, PH_SCHUR);
     if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
-                              (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
+                              (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->part_cm2.as<double>());
   }
   if (sharded) {     // one payload: per-camera sums | cost, |x_p|^2, bad, notpd | per-rank gradient max slots
     mark(ctx, PH_COMM);          // in situ: includes waiting for the slowest rank
@@ -629,7 +678,7 @@ int do_redamp(glba_ctx* ctx, double radius) {
   const int grid_pm = cdiv(n_pt, NT_PM);
   mark(ctx, PH_SCHUR);
   LAUNCH(k_point_damp, grid_pm, NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
-         (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>());
+         (const double4*)ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>());
   ReduceMap M{}; M.n = 1; M.slot[0] = S_NOTPD_P; M.is_max[0] = 0;
   LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 1, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal);
   if (ctx->world > 1) AR(ctx->d_scal + S_NOTPD_P, 1, kNcclSum);
@@ -644,7 +693,7 @@ int do_schur(glba_ctx* ctx, double radius) {
   const int n_cam = ctx->n_cam;
   mark(ctx, PH_SCHUR);
   if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
-                            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->part_cm2.as<double>());
+                            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->part_cm2.as<double>());
   if (ctx->world > 1) {
     LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
            (const double*)ctx->part_cm2.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
@@ -725,7 +774,7 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
   const int len = (n_cam * (n_cam + 1) / 2) * 36 + n;
   mark(ctx, PH_SCHUR);
   k_dense_schur<<<ctx->dn_grid, DN_NT, sm_schur, ctx->stream>>>(pm_args(ctx, o), n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(),
-      (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->pblk.as<double>(), ctx->dn_ppc,
+      (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->dn_ppc,
       ctx->dn_part.as<double>());
   g_launches.fetch_add(1, std::memory_order_relaxed);
 #define DN_RED_ARGS n_cam, (const double*)ctx->dn_part.as<double>(), (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->Bc.as<double>(), \
@@ -1026,6 +1075,8 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (set_func_attributes(ctx) != GLBA_OK) { delete ctx; return GLBA_E_CUDA; }
   if (const char* e = std::getenv("GLBA_TIMING")) ctx->env_timing = (e[0] == '1');          // diagnostic: phase timings for small problems too
   if (const char* e = std::getenv("GLBA_RELABEL")) ctx->env_relabel = (e[0] != '0');   // diagnostic: GLBA_RELABEL=0 keeps the caller's point order
+  if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
+  if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GLBA_E_CUDA; } ctx->own_stream = true; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
@@ -1050,9 +1101,9 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->pm_uv, &ctx->pm2orig, &ctx->pm2cm, &ctx->pt_start, &ctx->cm_pt, &ctx->cm_uv, &ctx->cm2pm, &ctx->cam_start, &ctx->chunk_cam,
                 &ctx->chunk_begin, &ctx->chunk_end, &ctx->cam_chunk_start, &ctx->cam_free, &ctx->pt_free, &ctx->sort_tmp, &ctx->keys_tmp, &ctx->flags,
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
-                &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->pblk, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
+                &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->cinv, &ctx->u0p, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1151,7 +1202,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   if ((st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            ctx->part_cm.as<double>()); }, &out->linearize_cm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->pblk.as<double>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms))) return st;
+           (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms))) return st;
   if ((st = timed([&] { launch_point_pass0(ctx, opt, (const CgState*)nullptr, 0); }, &out->spmv_pm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            (const double4*)ctx->u4.as<double4>(), (const CgState*)nullptr, 0, ctx->part_cm.as<double>()); }, &out->spmv_cm_ms))) return st;
@@ -1163,7 +1214,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
          ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode);
   if ((st = timed([&] { launch_point_pass1(ctx, opt, radius); }, &out->backsub_cost_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_point_damp, cdiv(n_pt, NT_PM), NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
-           (const double4*)ctx->lam4.as<double4>(), ctx->pblk.as<double>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms))) return st;
+           (const double4*)ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms))) return st;
   // every camera-sized kernel of one linearise + Schur pass (the scalar reductions now run inside the tile kernels)
   st = timed([&] {
     launch_cam_lin_fin(ctx, opt, 0);

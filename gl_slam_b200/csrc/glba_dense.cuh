@@ -38,7 +38,7 @@ __device__ __forceinline__ void chol3(const double* C, double* L /* l00 l10 l11 
 
 __global__ void __launch_bounds__(DN_NT)
 k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_free, const double4* __restrict__ rec_pm,
-              const double* __restrict__ camtab, const double* __restrict__ pblk, const int pts_per_cta,
+              const double* __restrict__ camtab, const double* __restrict__ cinv, const double4* __restrict__ u0p, const int pts_per_cta,
               double* __restrict__ part /* [grid][n_pairs*36 + 6*n_cam] */) {
   extern __shared__ double dsm[];
   const int n_pairs = n_cam * (n_cam + 1) / 2;
@@ -73,12 +73,11 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
     const int j = base + pl;
     if (j < p_end && A.pt_free[j]) {
       const int b = A.pt_start[j], e = A.pt_start[j + 1];
-      const double2* pb = reinterpret_cast<const double2*>(pblk + (size_t)PBLK * j);
       for (int k = b + slot; k < e; k += DN_SLOTS) {
         const int i = A.pm_cam[k];
         if (!cam_free[i]) continue;
-        const double2 c01 = pb[0], c23 = pb[1], c45 = pb[2], u01 = pb[3], u2_ = pb[4];
-        const double Ci[6] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y};
+        double Ci[6], u0[3];
+        load_pblk(cinv, u0p, j, Ci, u0);
         double Lc[6];
         chol3(Ci, Lc);
         const double4 rec = rec_pm[k];
@@ -107,7 +106,7 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
           Vo[r * 3 + 0] = W[r * 3] * Lc[0] + W[r * 3 + 1] * Lc[1] + W[r * 3 + 2] * Lc[3];
           Vo[r * 3 + 1] = W[r * 3 + 1] * Lc[2] + W[r * 3 + 2] * Lc[4];
           Vo[r * 3 + 2] = W[r * 3 + 2] * Lc[5];
-          Wo[r] = W[r * 3] * u01.x + W[r * 3 + 1] * u01.y + W[r * 3 + 2] * u2_.x;
+          Wo[r] = W[r * 3] * u0[0] + W[r * 3 + 1] * u0[1] + W[r * 3 + 2] * u0[2];
         }
         atomicOr(&pres[pl], 1u << i);
       }

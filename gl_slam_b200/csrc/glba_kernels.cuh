@@ -92,11 +92,26 @@ __device__ __forceinline__ void load_Rc(const double* __restrict__ ct, double* R
   R[0] = a.x; R[1] = a.y; R[2] = a.z; R[3] = a.w; R[4] = b.x; R[5] = b.y; R[6] = b.z; R[7] = b.w; R[8] = d.x;
   c[0] = d.y; c[1] = d.z; c[2] = d.w;
 }
-// damped point block row (96 B): Cinv[6], u0[3]
-__device__ __forceinline__ void load_pblk(const double* __restrict__ pb, double* Ci /*6*/, double* u0 /*3*/) {
-  const double4* q = reinterpret_cast<const double4*>(pb);
+// Damped point block, one 96-byte row per point in ONE plane: [Cinv(6) u0x u0y | u0z pad(3)] = three sectors, three 256-bit
+// accesses.  (A split into a 48-byte Cinv plane + a u0 plane was measured: the gather of k_schur_cm then needs four L1
+// requests per observation instead of three and ran 17 % slower.)  The PCG product reads the first two sectors only.
+// `u0p` is kept in the signatures as an alias of the same plane (rows of three double4).
+__device__ __forceinline__ void load_cinv(const double* __restrict__ cinv, const int j, double* Ci /*6*/) {
+  const double4* q = reinterpret_cast<const double4*>(cinv + (size_t)PBLK * j);
+  const double4 a = ldg4(q), b = ldg4(q + 1);
+  Ci[0] = a.x; Ci[1] = a.y; Ci[2] = a.z; Ci[3] = a.w; Ci[4] = b.x; Ci[5] = b.y;
+}
+__device__ __forceinline__ void load_pblk(const double* __restrict__ cinv, const double4* __restrict__ /*u0p*/, const int j, double* Ci /*6*/,
+                                          double* u0 /*3*/) {
+  const double4* q = reinterpret_cast<const double4*>(cinv + (size_t)PBLK * j);
   const double4 a = ldg4(q), b = ldg4(q + 1), d = ldg4(q + 2);
   Ci[0] = a.x; Ci[1] = a.y; Ci[2] = a.z; Ci[3] = a.w; Ci[4] = b.x; Ci[5] = b.y; u0[0] = b.z; u0[1] = b.w; u0[2] = d.x;
+}
+__device__ __forceinline__ void store_pblk(double* __restrict__ cinv, double4* __restrict__ /*u0p*/, const int j, const double* blk /* PBLK */) {
+  double4* q = reinterpret_cast<double4*>(cinv + (size_t)PBLK * j);
+  st4(q, make_double4(blk[0], blk[1], blk[2], blk[3]));
+  st4(q + 1, make_double4(blk[4], blk[5], blk[6], blk[7]));
+  st4(q + 2, make_double4(blk[8], blk[9], blk[10], blk[11]));
 }
 
 // rho(s): returns 1/2-free rho and sqrt(rho') (Ceres corrector with rho'' <= 0: plain IRLS scaling)
@@ -419,7 +434,7 @@ struct PmArgs {
 __global__ void __launch_bounds__(NT_PM)
 k_linearize_pm(const PmArgs A, const double4* __restrict__ pt, const double* __restrict__ camtab,
                double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw /* 9 SoA */,
-               double4* __restrict__ sp4, double4* __restrict__ lam4, double* __restrict__ pblk, const int first,
+               double4* __restrict__ sp4, double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const int first,
                const int jacobi, const double min_diag, const double max_diag, const double inv_radius,
                double* __restrict__ part /* [grid][5] */) {
   __shared__ double sm[5 * NT_PM / 32];
@@ -486,9 +501,7 @@ k_linearize_pm(const PmArgs A, const double4* __restrict__ pt, const double* __r
       if (first) st4(sp4 + j, make_double4(1.0, 1.0, 1.0, 0.0));
       st4(lam4 + j, make_double4(0.0, 0.0, 0.0, 0.0));
     }
-    double* pb = pblk + (size_t)PBLK * j;
-#pragma unroll
-    for (int q = 0; q < PBLK; q += 2) *reinterpret_cast<double2*>(pb + q) = make_double2(blk[q], blk[q + 1]);
+    store_pblk(cinv, u0p, j, blk);
   }
   double v[4] = {cost, xn2, bad, notpd};
   block_reduce<4, NT_PM>(v, sm, smo);
@@ -505,7 +518,7 @@ k_linearize_pm(const PmArgs A, const double4* __restrict__ pt, const double* __r
 // Re-damp the point blocks after the radius changed (rejected step): same C, g, lam.
 __global__ void __launch_bounds__(NT_PM)
 k_point_damp(const int n_pt, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw,
-             const double4* __restrict__ lam4, double* __restrict__ pblk, const double inv_radius,
+             const double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const double inv_radius,
              double* __restrict__ part /* [grid][1] notpd */) {
   __shared__ double sm[NT_PM / 32];
   __shared__ double smo[1];
@@ -521,9 +534,7 @@ k_point_damp(const int n_pt, const uint8_t* __restrict__ pt_free, const double* 
     const double lam[3] = {l4.x, l4.y, l4.z};
     double blk[PBLK];
     if (!point_block(C, g, lam, inv_radius, blk)) notpd = 1.0;
-    double* pb = pblk + (size_t)PBLK * j;
-#pragma unroll
-    for (int q = 0; q < PBLK; q += 2) *reinterpret_cast<double2*>(pb + q) = make_double2(blk[q], blk[q + 1]);
+    store_pblk(cinv, u0p, j, blk);
   }
   double v[1] = {notpd};
   block_reduce<1, NT_PM>(v, sm, smo);
@@ -594,7 +605,7 @@ k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double*
 // here the spills cost more than the occupancy gains: 4 CTAs/SM
 __global__ void __launch_bounds__(NT_HCM, 4)
 k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
-           const double* __restrict__ pblk, double* __restrict__ part /* [n_chunks][27] */) {
+           const double* __restrict__ cinv, const double4* __restrict__ u0p, double* __restrict__ part /* [n_chunks][27] */) {
   __shared__ double sm[27 * NT_HCM / 32];
   __shared__ double smo[27];
   const int ch = blockIdx.x;
@@ -613,7 +624,7 @@ k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __r
       const double4 rec = ldg4(rec_cm + k);
       const int j = __ldg(A.cm_pt + k);
       double Ci[6], u0[3];
-      load_pblk(pblk + (size_t)PBLK * j, Ci, u0);
+      load_pblk(cinv, u0p, j, Ci, u0);
       double ap[3], bp[3];
       jp_rows(rec, R, A.K, ap, bp);
       // t = Cinv ap, s = Cinv bp   (Cinv packed 00,01,02,11,12,22)
@@ -715,7 +726,7 @@ __global__ void k_chunk_sum(const int n_cam, const int* __restrict__ cam_chunk_s
 template <int MODE>
 __global__ void __launch_bounds__(NT_PM)
 k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* __restrict__ camtab,
-             const double* __restrict__ xtab /* [n_cam][XTAB] */, const double* __restrict__ pblk,
+             const double* __restrict__ xtab /* [n_cam][XTAB] */, const double* __restrict__ cinv, const double4* __restrict__ u0p,
              double4* __restrict__ u4, const CgState* __restrict__ cg, const int li,
              // MODE 1 only:
              const double4* __restrict__ pt, double4* __restrict__ pt_c, const double* __restrict__ camtab_c,
@@ -747,16 +758,17 @@ k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* _
         t0 += ap[0] * al0 + bp[0] * al1; t1 += ap[1] * al0 + bp[1] * al1; t2 += ap[2] * al0 + bp[2] * al1;
       }
     }
-    const double2* pb = reinterpret_cast<const double2*>(pblk + (size_t)PBLK * j);
-    const double2 c01 = __ldg(pb), c23 = __ldg(pb + 1), c45 = __ldg(pb + 2);
-    const double v0 = c01.x * t0 + c01.y * t1 + c23.x * t2;
-    const double v1 = c01.y * t0 + c23.y * t1 + c45.x * t2;
-    const double v2 = c23.x * t0 + c45.x * t1 + c45.y * t2;
+    double Ci[6];
+    load_cinv(cinv, j, Ci);
+    const double v0 = Ci[0] * t0 + Ci[1] * t1 + Ci[2] * t2;
+    const double v1 = Ci[1] * t0 + Ci[3] * t1 + Ci[4] * t2;
+    const double v2 = Ci[2] * t0 + Ci[4] * t1 + Ci[5] * t2;
     if (MODE == 0) {
       st4(u4 + j, make_double4(v0, v1, v2, 0.0));
     } else {
-      const double2 u01 = __ldg(pb + 3), u2_ = __ldg(pb + 4);
-      const double y0 = u01.x - v0, y1 = u01.y - v1, y2 = u2_.x - v2;
+      double Cj[6], u0[3];
+      load_pblk(cinv, u0p, j, Cj, u0);
+      const double y0 = u0[0] - v0, y1 = u0[1] - v1, y2 = u0[2] - v2;
       const double4 X = ldg4(pt + j);
       const double4 Xc = make_double4(X.x - y0, X.y - y1, X.z - y2, X.w);
       st4(pt_c + j, Xc);

@@ -30,9 +30,9 @@ constexpr int OPT_LARGE = GLBA_OPT_LARGE, OPT_SMALL = 1;
 
 // The last CTA to finish folds the per-CTA partial rows [rows][5] into the scalar slots, in row order (fixed).
 // MAXCOL = column reduced with max (-1: none).  Saves a separate single-CTA reduction launch per pass.
-template <int MAXCOL>
+template <int MAXCOL, int NT = GLBA_NT_T>
 __device__ __forceinline__ void last_block_reduce5(const double* part, const int rows, const int* slots, unsigned* counter,
-                                                   double* __restrict__ scal, double* sm /* 5*NT_T/32 */, double* smo /* 5 */) {
+                                                   double* __restrict__ scal, double* sm /* 5*NT/32 */, double* smo /* 5 */) {
   __shared__ bool s_last;
   if (counter == nullptr) return;       // large grids: the host launches k_reduce_rows instead (uniform branch)
   if (threadIdx.x == 0) {
@@ -46,18 +46,18 @@ __device__ __forceinline__ void last_block_reduce5(const double* part, const int
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   double mx[1] = {0.0};
 #pragma unroll 4
-  for (int r = threadIdx.x; r < rows; r += NT_T) {
+  for (int r = threadIdx.x; r < rows; r += NT) {
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
       const double x = __ldcg(part + (size_t)5 * r + q);
       if (q == MAXCOL) mx[0] = fmax(mx[0], x); else acc[q] += x;
     }
   }
-  block_reduce<5, NT_T>(acc, sm, smo);
+  block_reduce<5, NT>(acc, sm, smo);
   if (threadIdx.x < 5 && (int)threadIdx.x != MAXCOL) scal[slots[threadIdx.x]] = smo[threadIdx.x];
   if constexpr (MAXCOL >= 0) {
     __syncthreads();
-    block_reduce<1, NT_T, true>(mx, sm, smo);
+    block_reduce<1, NT, true>(mx, sm, smo);
     if (threadIdx.x == 0) scal[slots[MAXCOL]] = smo[0];
   }
 }
@@ -106,7 +106,7 @@ template <int OPT>
 __global__ void __launch_bounds__(NT_T)
 k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ pt, const double* __restrict__ camtab,
                  double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
-                 double4* __restrict__ lam4, double* __restrict__ pblk, const int first, const int jacobi, const double min_diag,
+                 double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const int first, const int jacobi, const double min_diag,
                  const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   constexpr int TILE_OBS = NT_T * OPT;
   extern __shared__ double dsm[];
@@ -219,10 +219,7 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
       if (first) st4(sp4 + j, make_double4(1.0, 1.0, 1.0, 0.0));
       st4(lam4 + j, make_double4(0.0, 0.0, 0.0, 0.0));
     }
-    double4* pb = reinterpret_cast<double4*>(pblk + (size_t)PBLK * j);      // 96-byte row: three 256-bit stores
-    st4(pb, make_double4(blk[0], blk[1], blk[2], blk[3]));
-    st4(pb + 1, make_double4(blk[4], blk[5], blk[6], blk[7]));
-    st4(pb + 2, make_double4(blk[8], blk[9], blk[10], blk[11]));
+    store_pblk(cinv, u0p, j, blk);
   }
   double v[4] = {cost, xn2, bad, notpd};
   block_reduce<4, NT_T>(v, sm, smo);
@@ -243,7 +240,7 @@ template <int MODE, int OPT>
 __global__ void __launch_bounds__(NT_T)
 k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_pm, const double* __restrict__ camtab,
              const double* __restrict__ xtab,
-             const double* __restrict__ pblk, double4* __restrict__ u4, const CgState* __restrict__ cg, const int li,
+             const double* __restrict__ cinv, const double4* __restrict__ u0p, double4* __restrict__ u4, const CgState* __restrict__ cg, const int li,
              // MODE 1 only:
              const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
              const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
@@ -322,8 +319,8 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
     const bool free_pt = A.pt_free[j] != 0;
     if (free_pt)
       for (int m = b; m < e; ++m) { t0 += val[0][m]; t1 += val[1][m]; t2 += val[2][m]; }
-    double Ci[6], u0[3];
-    load_pblk(pblk + (size_t)PBLK * j, Ci, u0);
+    double Ci[6], u0[3] = {0.0, 0.0, 0.0};
+    if (MODE == 1) load_pblk(cinv, u0p, j, Ci, u0); else load_cinv(cinv, j, Ci);
     const double v0 = Ci[0] * t0 + Ci[1] * t1 + Ci[2] * t2;
     const double v1 = Ci[1] * t0 + Ci[3] * t1 + Ci[4] * t2;
     const double v2 = Ci[2] * t0 + Ci[4] * t1 + Ci[5] * t2;

@@ -73,3 +73,58 @@ def test_inexact_mode_reaches_the_parity_mode_optimum(ctx):
     assert (np.diff(c) <= 1e-12 * c[:-1]).all(), c
     assert inexact["final_cost"] <= 1.01 * exact["final_cost"], (inexact["final_cost"], exact["final_cost"])
     assert inexact["final_cost"] < 0.2 * inexact["initial_cost"]
+
+
+# ---- the persistent TMA-fed tile kernels (glba_pipe.cuh) on shapes that reach their fall-backs -------------------------
+@pytest.fixture(scope="module")
+def ctx_large():
+    """A context that uses the large-map tile path (512-observation tiles, pipelined kernels) whatever the problem size."""
+    import os
+    os.environ["GLBA_TILE"] = "large"
+    try:
+        c = g.Context(device=0)
+    finally:
+        del os.environ["GLBA_TILE"]
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name,kw,okw", [
+    # ~100 points per tile, banded covisibility: everything staged
+    ("banded", dict(n_cam=24, n_pt=3000, track_len=lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=41, rot_sigma=0.003, pos_sigma=0.03), {}),
+    # two-view tracks: 256 points per 512-observation tile, beyond the NPCAP staged points (global fall-back per point)
+    ("short_tracks", dict(n_cam=6, n_pt=4000, track_len=2, seed=5, rot_sigma=0.003, pos_sigma=0.03), dict(loss=1)),
+    # tracks that start anywhere on a 90-camera loop, points numbered at random and NOT renumbered: a tile sees far more than
+    # 32 distinct cameras (slot 255: global gather of the camera rows)
+    ("scattered_cameras", dict(n_cam=90, n_pt=4000, track_len=lambda rng, n: 2 + rng.poisson(2.0, size=n), seed=9, loop=True,
+                               creation_order=False, rot_sigma=0.002, pos_sigma=0.02), dict(max_iters=6)),
+])
+def test_pipelined_tile_kernels_match_oracle(oracle, name, kw, okw):
+    import os
+    prob = scene.make_scene(**kw)
+    if name == "banded":
+        prob.cam[2, :3] = 0.0                     # exactly-identity keyframe: the small-angle branch inside the tile kernels
+    ref, so = oracle.solve(prob, oracle.options(**okw))
+    os.environ["GLBA_TILE"] = "large"
+    if name == "scattered_cameras":
+        os.environ["GLBA_RELABEL"] = "0"
+    try:
+        with g.Context(device=0) as c:
+            got, s = c.solve(prob, g.options(linsolve=g.LINSOLVE_PCG, **okw))
+            L = c.linearize(prob, 1e4, g.options(**okw), per_obs=False)
+    finally:
+        os.environ.pop("GLBA_TILE", None)
+        os.environ.pop("GLBA_RELABEL", None)
+    check_trajectory(s, so, rtol=1e-9 if name != "scattered_cameras" else 1e-8)
+    check_state(prob, got.cam, got.pt, ref.cam, ref.pt)
+    O = oracle.linearize(prob, 1e4, oracle.options(**okw), per_obs=False)
+    assert abs(L.cost - O.cost) <= 1e-12 * abs(O.cost)
+    for k in ("grad_cam", "grad_pt", "hess_cam", "hess_pt", "schur_rhs"):
+        assert rel_to_max(getattr(L, k), getattr(O, k)) < 1e-10, k
+
+
+def test_pipelined_kernels_bitwise_reproducible(ctx_large):
+    prob = scene.make_scene(30, 6000, lambda rng, n: 2 + rng.poisson(3.0, size=n), seed=77, rot_sigma=0.003, pos_sigma=0.03)
+    a, sa = ctx_large.solve(prob, g.options(linsolve=g.LINSOLVE_PCG, max_iters=5))
+    b, sb = ctx_large.solve(prob, g.options(linsolve=g.LINSOLVE_PCG, max_iters=5))
+    assert np.array_equal(a.cam, b.cam) and np.array_equal(a.pt, b.pt) and sa["cost"] == sb["cost"]
