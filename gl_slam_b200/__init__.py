@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "glba_triangulate_filter",
     "glba_map_create", "glba_map_destroy", "glba_map_size", "glba_map_add_keyframes", "glba_map_add_points",
     "glba_map_add_observations", "glba_map_set_bad", "glba_map_write_keyframes", "glba_map_read_keyframes",
-    "glba_map_write_points", "glba_map_read_points", "glba_map_solve_window", "glba_map_cull_points",
+    "glba_map_write_points", "glba_map_read_points", "glba_map_solve_window", "glba_map_cull_points", "glba_map_propagate",
 )
 
 
@@ -97,6 +97,7 @@ def lib():
     L.glba_map_solve_window.argtypes = [vp, i32, i32, i32, i32, C.POINTER(_abi.Options), C.POINTER(_abi.Summary), C.POINTER(i32),
                                         C.POINTER(C.c_int64)]
     L.glba_map_cull_points.argtypes = [vp, i32, i32, i32, f64, C.POINTER(i32), C.POINTER(i32), vp, i32]
+    L.glba_map_propagate.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, vp, vp]
     _LIB = L
     return L
 
@@ -340,6 +341,18 @@ class DeviceMap:
         xyz, bad = np.zeros((n, 3)), np.zeros(n, np.uint8)
         self._ctx._check(lib().glba_map_read_points(self._h, int(first), int(n), xyz.ctypes.data, bad.ctypes.data), "glba_map_read_points")
         return xyz, bad
+
+    def propagate(self, R_before, t_before, kf_last, kf_ids, pt_ids):
+        """post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973) on the device; returns (dR, dt)."""
+        Rb = np.ascontiguousarray(R_before, dtype=np.float64).reshape(3, 3)
+        tb = np.ascontiguousarray(t_before, dtype=np.float64).reshape(3)
+        kf = np.ascontiguousarray(kf_ids, dtype=np.int32)
+        pt = np.ascontiguousarray(pt_ids, dtype=np.int32)
+        dR, dt = np.zeros((3, 3)), np.zeros(3)
+        st = lib().glba_map_propagate(self._h, Rb.ctypes.data, tb.ctypes.data, int(kf_last), len(kf), kf.ctypes.data if len(kf) else None,
+                                      len(pt), pt.ctypes.data if len(pt) else None, dR.ctypes.data, dt.ctypes.data)
+        self._ctx._check(st, "glba_map_propagate")
+        return dR, dt
 
     def solve_window(self, first_kf, window, opt=None, n_fixed=2, min_obs=1):
         """Returns the summary dict, with the window's size under 'n_pt' / 'n_obs'."""

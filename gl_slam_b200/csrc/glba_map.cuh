@@ -13,6 +13,8 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include "../../include/glba_so3.hpp"
+
 namespace {
 
 __global__ void k_map_count(const long n, const int* __restrict__ o_kf, const int* __restrict__ o_pt, const uint8_t* __restrict__ bad,
@@ -76,6 +78,41 @@ __global__ void k_map_sel_kept(const long n, const int* __restrict__ o_pt, const
 __global__ void k_map_set_u8(const int n, const int* __restrict__ ids, const uint8_t v, uint8_t* __restrict__ a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[ids[i]] = v;
+}
+
+// post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973) on the resident map.
+// k_map_delta: one thread computes the clean pose change of keyframe kf_last, ComputeDeltaPose_SO3 (:899-912), from the
+// pose the caller saved before the write-back and the pose now in the map.  out[0..8] = dR (row-major), out[9..11] = dt.
+__global__ void k_map_delta(const double* __restrict__ cam, const int kf_last, const double* __restrict__ before /* R[9] t[3] */,
+                            double* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double* c = cam + 6 * (size_t)kf_last;
+  double Ra[9];
+  glba::so3_exp(c, Ra, nullptr);                   // keyframe rotation R_wc = exp([w]x), as cv::Rodrigues builds it
+  glba_so3::compute_delta_pose_so3(before, before + 9, Ra, c + 3, out, out + 9);
+}
+// points X <- dR X + dt (:931-944); keyframes R <- dR R, t <- dR t + dt (:945-968), stored back as (angle-axis, centre)
+__global__ void k_map_apply_delta(const double* __restrict__ d, const int n_kf, const int* __restrict__ kf_ids, double* __restrict__ cam,
+                                  const int n_pt, const int* __restrict__ pt_ids, double* __restrict__ pt) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_pt) {
+    double* X = pt + 3 * (size_t)pt_ids[t];
+    const double x = X[0], y = X[1], z = X[2];
+    X[0] = d[0] * x + d[1] * y + d[2] * z + d[9];
+    X[1] = d[3] * x + d[4] * y + d[5] * z + d[10];
+    X[2] = d[6] * x + d[7] * y + d[8] * z + d[11];
+  } else if (t < n_pt + n_kf) {
+    double* c = cam + 6 * (size_t)kf_ids[t - n_pt];
+    double R[9], Rn[9], w[3];
+    glba::so3_exp(c, R, nullptr);
+    glba_so3::mul3(d, R, Rn);
+    glba::so3_log(Rn, w);
+    const double x = c[3], y = c[4], z = c[5];
+    c[0] = w[0]; c[1] = w[1]; c[2] = w[2];
+    c[3] = d[0] * x + d[1] * y + d[2] * z + d[9];
+    c[4] = d[3] * x + d[4] * y + d[5] * z + d[10];
+    c[5] = d[6] * x + d[7] * y + d[8] * z + d[11];
+  }
 }
 
 // append-only device array: capacity doubles, contents survive growth
@@ -388,6 +425,46 @@ int glba_map_cull_points(glba_map* m, int32_t first_kf, int32_t last_kf, int32_t
   for (size_t q = 0; q < culled.size() && (int32_t)q < cap; ++q) culled_ids[q] = culled[q];
   if (culled.empty()) return GLBA_OK;
   return glba_map_set_bad(m, (int32_t)culled.size(), culled.data(), 1);
+}
+
+// post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973) on the resident map: the pose change of keyframe kf_last
+// between (R_before, t_before) — what the caller saved before the BA write-back, :853-854 — and its pose now in the map is
+// projected to SO(3) as ComputeDeltaPose_SO3 does (:885-912, including the reflection flip) and applied to the listed
+// keyframes (kpid_to_correct) and points (mpid_to_correct).  dR_out[9] / dt_out[3] (may be NULL) receive the delta.
+int glba_map_propagate(glba_map* m, const double* R_before, const double* t_before, int32_t kf_last, int32_t n_kf, const int32_t* kf_ids,
+                       int32_t n_pt, const int32_t* pt_ids, double* dR_out, double* dt_out) {
+  if (!m) return GLBA_E_INVALID_ARG;
+  glba_ctx* ctx = m->ctx;
+  if (!R_before || !t_before || kf_last < 0 || kf_last >= m->n_kf || n_kf < 0 || n_pt < 0 || (n_kf > 0 && !kf_ids) || (n_pt > 0 && !pt_ids))
+    return fail(ctx, GLBA_E_INVALID_ARG, "map_propagate: bad argument");
+  for (int32_t i = 0; i < n_kf; ++i) if (kf_ids[i] < 0 || kf_ids[i] >= m->n_kf) return fail(ctx, GLBA_E_INVALID_ARG, "map_propagate: keyframe %d not in the map", kf_ids[i]);
+  for (int32_t i = 0; i < n_pt; ++i) if (pt_ids[i] < 0 || pt_ids[i] >= m->n_pt) return fail(ctx, GLBA_E_INVALID_ARG, "map_propagate: point %d not in the map", pt_ids[i]);
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // staging: [before 12 doubles | delta 12 doubles | kf ids | pt ids]
+  const size_t bytes = 24 * sizeof(double) + sizeof(int) * ((size_t)n_kf + n_pt);
+  ENSURE(char, m->stage, bytes);
+  double* d_before = m->stage.as<double>();
+  double* d_delta = d_before + 12;
+  int* d_kf = reinterpret_cast<int*>(d_delta + 12);
+  int* d_pt = d_kf + n_kf;
+  double hb[12];
+  for (int q = 0; q < 9; ++q) hb[q] = R_before[q];
+  for (int q = 0; q < 3; ++q) hb[9 + q] = t_before[q];
+  CU(cudaMemcpyAsync(d_before, hb, sizeof(hb), cudaMemcpyHostToDevice, s));
+  if (n_kf) CU(cudaMemcpyAsync(d_kf, kf_ids, sizeof(int) * (size_t)n_kf, cudaMemcpyHostToDevice, s));
+  if (n_pt) CU(cudaMemcpyAsync(d_pt, pt_ids, sizeof(int) * (size_t)n_pt, cudaMemcpyHostToDevice, s));
+  LAUNCH(k_map_delta, 1, 32, (const double*)m->cam.as<double>(), kf_last, (const double*)d_before, d_delta);
+  if (n_kf + n_pt > 0)
+    LAUNCH(k_map_apply_delta, cdiv((long)n_kf + n_pt, 128), 128, (const double*)d_delta, n_kf, (const int*)d_kf, m->cam.as<double>(), n_pt, (const int*)d_pt,
+           m->pt.as<double>());
+  double hd[12];
+  CU(cudaMemcpyAsync(hd, d_delta, sizeof(hd), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));          // hb / the id arrays are the caller's: the copies have completed
+  CU(cudaGetLastError());
+  if (dR_out) for (int q = 0; q < 9; ++q) dR_out[q] = hd[q];
+  if (dt_out) for (int q = 0; q < 3; ++q) dt_out[q] = hd[9 + q];
+  return GLBA_OK;
 }
 
 }  // extern "C"

@@ -310,6 +310,14 @@ int glba_map_solve_window(glba_map* map, int32_t first_kf, int32_t window, int32
 int glba_map_cull_points(glba_map* map, int32_t first_kf, int32_t last_kf, int32_t min_obs, double max_mean_err,
                          int32_t* n_candidates, int32_t* n_culled, int32_t* culled_ids, int32_t cap);
 
+/* post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973) on the resident map.  (R_before[9] row-major, t_before[3]) =
+ * pose of keyframe kf_last saved before the BA write-back (slam_core.cpp:853-854); its pose NOW in the map is "after".
+ * delta = ComputeDeltaPose_SO3 (slam_core.cpp:885-912: SVD projection to SO(3) with the reflection flip) is applied on the
+ * device to keyframes kf_ids (R <- dR R, t <- dR t + dt: kpid_to_correct) and points pt_ids (X <- dR X + dt:
+ * mpid_to_correct).  dR_out[9] / dt_out[3] may be NULL.  Host pointers. */
+int glba_map_propagate(glba_map* map, const double* R_before, const double* t_before, int32_t kf_last, int32_t n_kf,
+                       const int32_t* kf_ids, int32_t n_pt, const int32_t* pt_ids, double* dR_out, double* dt_out);
+
 #ifdef __cplusplus
 }
 #endif

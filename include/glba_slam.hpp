@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "glba.h"
+#include "glba_so3.hpp"
 
 namespace glslam {
 
@@ -175,11 +176,30 @@ inline bool pack_window(const Map& map, int window, int run_window, PackedWindow
   return true;
 }
 
+// What the reference does INSIDE the critical section of the write-back, right after it (slam_core.cpp:853-879): propagate the
+// pose change of keyframe run_window to the keyframes / points the tracking thread created while BA ran
+// (post_ba_map_update_for_new_keyframes, :873) and cull old points (post_ba_map_point_culling, :875-879).  Passing a PostBa to
+// full_ba / full_ba_resident runs both while tracking_mutex and map_mutex are still held, as the reference does: released in
+// between, the tracking thread could read refined window poses next to uncorrected new keyframes, or push ids that then get
+// the delta applied twice.
+struct PostBa {
+  std::vector<int>* mpid_to_correct = nullptr;   // slam_types::mpid_to_correct (consumed)
+  std::vector<int>* kpid_to_correct = nullptr;   // slam_types::kpid_to_correct (consumed)
+  bool cull_map_points = false;                  // slam_types::cull_map_points
+  int local_ba_window = 0;                       // slam_types::local_ba_window: culling covers keyframes [run_window - it, run_window - 4]
+  int n_culled = 0;                              // out: points flagged is_bad (-1: culling failed)
+};
+inline void post_ba_map_update_for_new_keyframes(Map& map, const Mat33& R_before, const Vec3& t_before, int run_window,
+                                                 std::vector<int>& mpid_to_correct, std::vector<int>& kpid_to_correct);
+inline int post_ba_map_point_culling(Backend& be, Map& map, const CameraMatrix& K, int run_window, int local_ba_window, double max_err = 1.0,
+                                     int min_obs = 3);
+
 // Drop-in for slam_core::full_ba.  `run_window` = slam_types::run_window; tracking_mutex may be null.
 // On solver failure nothing is written back (the reference ignores ceres::Solver::Summary, slam_core.cpp:848-850;
 // leaving the map untouched is the safe reading of "inputs untouched on failure").
 inline bool full_ba(Backend& be, std::mutex& map_mutex, Map& map, const CameraMatrix& K, int window, int run_window,
-                    std::mutex* tracking_mutex = nullptr, const glba_options* options = nullptr, glba_summary* summary = nullptr) {
+                    std::mutex* tracking_mutex = nullptr, const glba_options* options = nullptr, glba_summary* summary = nullptr,
+                    PostBa* post = nullptr) {
   if (!be.ok()) return false;
   PackedWindow pw;
   if (!pack_window(map, window, run_window, pw)) return false;
@@ -198,6 +218,8 @@ inline bool full_ba(Backend& be, std::mutex& map_mutex, Map& map, const CameraMa
   std::unique_lock<std::mutex> tl;
   if (tracking_mutex) tl = std::unique_lock<std::mutex>(*tracking_mutex);
   std::lock_guard<std::mutex> lk(map_mutex);
+  const Mat33 R_before = map.keyframes[run_window].R;       // slam_core.cpp:853-854 (read under the locks here)
+  const Vec3 t_before = map.keyframes[run_window].t;
   for (const auto& kv : pw.kf_to_param_idx) {
     const double* cam = &pw.camera_params[(size_t)kv.second * 6];
     Frame& kf = map.keyframes[kv.first];
@@ -207,6 +229,12 @@ inline bool full_ba(Backend& be, std::mutex& map_mutex, Map& map, const CameraMa
   for (const auto& kv : pw.point_to_param_idx) {
     const double* pt = &pw.point_params[(size_t)kv.second * 3];
     map.map_points[kv.first].position = Point3d{pt[0], pt[1], pt[2]};
+  }
+  if (post) {                                               // still holding both locks, slam_core.cpp:873-879
+    std::vector<int> none;
+    post_ba_map_update_for_new_keyframes(map, R_before, t_before, run_window, post->mpid_to_correct ? *post->mpid_to_correct : none,
+                                         post->kpid_to_correct ? *post->kpid_to_correct : none);
+    if (post->cull_map_points) post->n_culled = post_ba_map_point_culling(be, map, K, run_window, post->local_ba_window, 1.0, 3);
   }
   return true;
 }
@@ -232,14 +260,15 @@ class ResidentMap {
   // observation of the touched points not pushed before, and the touched points' is_bad flags.
   bool sync(const Map& map) {
     if (!map_) return false;
-    if (n_kf_ == 0) {
+    int kf_base = kf_base_, n_kf = n_kf_;
+    if (n_kf == 0) {
       if (map.keyframes.empty()) return true;
-      kf_base_ = map.keyframes.begin()->first;
-      for (const auto& kv : map.keyframes) kf_base_ = std::min(kf_base_, kv.first);
+      kf_base = map.keyframes.begin()->first;
+      for (const auto& kv : map.keyframes) kf_base = std::min(kf_base, kv.first);
     }
     std::vector<int> touched;
-    const int first_new = kf_base_ + n_kf_;
-    if (n_kf_ > 0) collect(map, first_new - 1, touched);     // a new keyframe also adds observations of the one before it (:386-405)
+    const int first_new = kf_base + n_kf;
+    if (n_kf > 0) collect(map, first_new - 1, touched);     // a new keyframe also adds observations of the one before it (:386-405)
     std::vector<double> cams;
     int next = first_new;
     for (auto it = map.keyframes.find(next); it != map.keyframes.end(); it = map.keyframes.find(++next)) {
@@ -248,32 +277,50 @@ class ResidentMap {
       cams.insert(cams.end(), {w[0], w[1], w[2], it->second.t.v[0], it->second.t.v[1], it->second.t.v[2]});
       collect(map, next, touched);
     }
-    if (!cams.empty() && glba_map_add_keyframes(map_, (int32_t)(cams.size() / 6), cams.data(), nullptr) != GLBA_OK) return false;
-    n_kf_ += (int)(cams.size() / 6);
+    n_kf += (int)(cams.size() / 6);
     std::sort(touched.begin(), touched.end());
     touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+    // everything is STAGED first: the host-side index (pt_index_, pt_ids_, pushed_, bad_, n_kf_) is committed only after every
+    // device append has succeeded, so a failure cannot leave it ahead of the device
     std::vector<double> xyz, uv;
     std::vector<int32_t> okf, opt, bad_ids, good_ids;
+    std::vector<int> new_ids;                                  // map point ids appended by this call, in device order
+    std::vector<std::pair<int, size_t>> new_pushed;            // (device point, observations pushed so far)
+    std::vector<std::pair<int, uint8_t>> new_bad;
+    const int n_known = (int)pt_ids_.size();
+    std::unordered_map<int, int> staged_index;
     for (int mpid : touched) {
-      const MapPoint& mp = map.map_points.at(mpid);
-      auto ins = pt_index_.emplace(mpid, (int)pt_ids_.size());
-      if (ins.second) {
-        pt_ids_.push_back(mpid); pushed_.push_back(0); bad_.push_back(0);
+      auto mp_it = map.map_points.find(mpid);
+      if (mp_it == map.map_points.end()) return false;
+      const MapPoint& mp = mp_it->second;
+      int d;
+      auto known = pt_index_.find(mpid);
+      if (known != pt_index_.end()) d = known->second;
+      else {
+        d = n_known + (int)new_ids.size();
+        staged_index.emplace(mpid, d);
+        new_ids.push_back(mpid);
         xyz.insert(xyz.end(), {mp.position.x, mp.position.y, mp.position.z});
       }
-      const int d = ins.first->second;
-      for (size_t k = pushed_[d]; k < mp.obs.size(); ++k) {
+      const size_t done = d < n_known ? pushed_[d] : 0;
+      for (size_t k = done; k < mp.obs.size(); ++k) {
         const Observation& o = mp.obs[k];
-        if (o.keyframe_id < kf_base_ || o.keyframe_id >= kf_base_ + n_kf_) return false;     // observation of an unknown keyframe
-        okf.push_back(o.keyframe_id - kf_base_); opt.push_back(d); uv.push_back(o.point2D.x); uv.push_back(o.point2D.y);
+        if (o.keyframe_id < kf_base || o.keyframe_id >= kf_base + n_kf) return false;     // observation of an unknown keyframe
+        okf.push_back(o.keyframe_id - kf_base); opt.push_back(d); uv.push_back(o.point2D.x); uv.push_back(o.point2D.y);
       }
-      pushed_[d] = mp.obs.size();
-      if ((uint8_t)mp.is_bad != bad_[d]) { (mp.is_bad ? bad_ids : good_ids).push_back(d); bad_[d] = mp.is_bad ? 1 : 0; }
+      new_pushed.emplace_back(d, mp.obs.size());
+      const uint8_t was = d < n_known ? bad_[d] : 0;
+      if ((uint8_t)mp.is_bad != was) { (mp.is_bad ? bad_ids : good_ids).push_back(d); new_bad.emplace_back(d, mp.is_bad ? 1 : 0); }
     }
+    if (!cams.empty() && glba_map_add_keyframes(map_, (int32_t)(cams.size() / 6), cams.data(), nullptr) != GLBA_OK) return false;
+    kf_base_ = kf_base; n_kf_ = n_kf;                          // the device has them: commit step by step from here on
     if (!xyz.empty() && glba_map_add_points(map_, (int32_t)(xyz.size() / 3), xyz.data(), nullptr) != GLBA_OK) return false;
+    for (int mpid : new_ids) { pt_index_.emplace(mpid, (int)pt_ids_.size()); pt_ids_.push_back(mpid); pushed_.push_back(0); bad_.push_back(0); }
     if (!okf.empty() && glba_map_add_observations(map_, (int32_t)okf.size(), okf.data(), opt.data(), uv.data()) != GLBA_OK) return false;
+    for (const auto& pr : new_pushed) pushed_[pr.first] = pr.second;
     if (!bad_ids.empty() && glba_map_set_bad(map_, (int32_t)bad_ids.size(), bad_ids.data(), 1) != GLBA_OK) return false;
     if (!good_ids.empty() && glba_map_set_bad(map_, (int32_t)good_ids.size(), good_ids.data(), 0) != GLBA_OK) return false;
+    for (const auto& pr : new_bad) bad_[pr.first] = pr.second;
     return true;
   }
 
@@ -288,6 +335,44 @@ class ResidentMap {
                              ids.data(), (int32_t)ids.size()) != GLBA_OK) return -1;
     for (int32_t q = 0; q < n_culled; ++q) { bad_[ids[q]] = 1; map.map_points[pt_ids_[ids[q]]].is_bad = true; }
     return n_culled;
+  }
+
+  // Host edits of poses / positions since the last BA (the tracking thread initialising a pose, a host-side propagation):
+  // push them, or the next window starts from stale device values and a later write-back restores them.
+  bool push_keyframes(const Map& map, const std::vector<int>& kfids) {
+    for (int id : kfids) {
+      auto it = map.keyframes.find(id);
+      const int d = id - kf_base_;
+      if (it == map.keyframes.end() || d < 0 || d >= n_kf_) return false;
+      double cam[6];
+      rodrigues(it->second.R, cam);
+      cam[3] = it->second.t.v[0]; cam[4] = it->second.t.v[1]; cam[5] = it->second.t.v[2];
+      if (glba_map_write_keyframes(map_, d, 1, cam) != GLBA_OK) return false;
+    }
+    return true;
+  }
+  bool push_points(const Map& map, const std::vector<int>& mpids) {
+    for (int id : mpids) {
+      auto it = map.map_points.find(id);
+      const int d = device_point(id);
+      if (it == map.map_points.end() || d < 0) return false;
+      const double xyz[3] = {it->second.position.x, it->second.position.y, it->second.position.z};
+      if (glba_map_write_points(map_, d, 1, xyz) != GLBA_OK) return false;
+    }
+    return true;
+  }
+  // post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973) on the device mirror (glba_map_propagate): the listed
+  // keyframes / points must have been sync()ed.  The host map is updated by glslam::post_ba_map_update_for_new_keyframes
+  // with the same arithmetic (include/glba_so3.hpp); ids the device does not know yet are skipped (they arrive, already
+  // corrected, with the next sync()).
+  bool propagate(const Mat33& R_before, const Vec3& t_before, int run_window, const std::vector<int>& mpids, const std::vector<int>& kfids) {
+    if (!map_) return false;
+    std::vector<int32_t> dk, dp;
+    for (int id : kfids) { const int d = id - kf_base_; if (d >= 0 && d < n_kf_) dk.push_back(d); }
+    for (int id : mpids) { const int d = device_point(id); if (d >= 0) dp.push_back(d); }
+    const int last = run_window - kf_base_;
+    if (last < 0 || last >= n_kf_) return false;
+    return glba_map_propagate(map_, R_before.m, t_before.v, last, (int32_t)dk.size(), dk.data(), (int32_t)dp.size(), dp.data(), nullptr, nullptr) == GLBA_OK;
   }
 
   // is_bad flags set by the host since the last sync (post_ba_map_point_culling, slam_core.cpp:977-1038)
@@ -314,7 +399,8 @@ class ResidentMap {
 // full_ba on the resident map: same window rule, fixed cameras, options and write-back as full_ba() above, but the
 // window is selected and packed on the device; the host only copies the refined window back into `map`.
 inline bool full_ba_resident(Backend& be, ResidentMap& rm, std::mutex& map_mutex, Map& map, int window, int run_window,
-                             std::mutex* tracking_mutex = nullptr, const glba_options* options = nullptr, glba_summary* summary = nullptr) {
+                             std::mutex* tracking_mutex = nullptr, const glba_options* options = nullptr, glba_summary* summary = nullptr,
+                             PostBa* post = nullptr) {
   if (!be.ok() || !rm.ok()) return false;
   if ((int)map.keyframes.size() < window || window <= 1) return false;            // slam_core.cpp:746-749
   const int first = run_window + 1 - window;
@@ -328,8 +414,14 @@ inline bool full_ba_resident(Backend& be, ResidentMap& rm, std::mutex& map_mutex
   std::vector<double> cams(6 * (size_t)window);
   if (glba_map_read_keyframes(rm.handle(), first_dev, window, cams.data()) != GLBA_OK) return false;
   int lo = (int)rm.point_ids().size(), hi = -1;          // device range covering the window's points (ids are creation-ordered)
+  std::vector<uint8_t> in_window;                        // ... of which only the points the window observes are written back
   for (int i = first; i < first + window; ++i)
     for (int mpid : map.keyframes.at(i).map_point_ids) { const int d = rm.device_point(mpid); if (d >= 0) { lo = std::min(lo, d); hi = std::max(hi, d); } }
+  if (hi >= lo) {
+    in_window.assign((size_t)(hi - lo + 1), 0);
+    for (int i = first; i < first + window; ++i)
+      for (int mpid : map.keyframes.at(i).map_point_ids) { const int d = rm.device_point(mpid); if (d >= 0) in_window[d - lo] = 1; }
+  }
   std::vector<double> xyz;
   std::vector<uint8_t> bad;
   if (hi >= lo) {
@@ -339,14 +431,25 @@ inline bool full_ba_resident(Backend& be, ResidentMap& rm, std::mutex& map_mutex
   std::unique_lock<std::mutex> tl;
   if (tracking_mutex) tl = std::unique_lock<std::mutex>(*tracking_mutex);
   std::lock_guard<std::mutex> lk(map_mutex);
+  const Mat33 R_before = map.keyframes[run_window].R;       // slam_core.cpp:853-854
+  const Vec3 t_before = map.keyframes[run_window].t;
   for (int i = 0; i < window; ++i) {
     Frame& kf = map.keyframes[first + i];
     rodrigues(&cams[6 * (size_t)i], kf.R);
     kf.t.v[0] = cams[6 * i + 3]; kf.t.v[1] = cams[6 * i + 4]; kf.t.v[2] = cams[6 * i + 5];
   }
   for (int d = lo; d <= hi; ++d) {
-    if (bad[d - lo]) continue;
+    if (bad[d - lo] || !in_window[d - lo]) continue;       // points outside the window keep their host values
     map.map_points[rm.point_ids()[d]].position = Point3d{xyz[3 * (size_t)(d - lo)], xyz[3 * (size_t)(d - lo) + 1], xyz[3 * (size_t)(d - lo) + 2]};
+  }
+  if (post) {                                               // still holding both locks, slam_core.cpp:873-879
+    std::vector<int> none;
+    std::vector<int>& mp = post->mpid_to_correct ? *post->mpid_to_correct : none;
+    std::vector<int>& kp = post->kpid_to_correct ? *post->kpid_to_correct : none;
+    // the device applies the delta to its mirror with the pose it holds (the refined one), the host to the host map
+    rm.propagate(R_before, t_before, run_window, mp, kp);
+    post_ba_map_update_for_new_keyframes(map, R_before, t_before, run_window, mp, kp);
+    if (post->cull_map_points) post->n_culled = rm.cull(map, run_window, post->local_ba_window, 1.0, 3);
   }
   return true;
 }
@@ -459,29 +562,16 @@ inline Mat33 transpose(const Mat33& A) { Mat33 T; for (int r = 0; r < 3; ++r) fo
 inline double det(const Mat33& A) {
   return A.m[0] * (A.m[4] * A.m[8] - A.m[5] * A.m[7]) - A.m[1] * (A.m[3] * A.m[8] - A.m[5] * A.m[6]) + A.m[2] * (A.m[3] * A.m[7] - A.m[4] * A.m[6]);
 }
-// ProjectToSO3 (slam_core.cpp:885-897): nearest rotation U V' of the SVD.  Computed as the orthogonal polar factor by
-// Newton's iteration X <- (X + X^-T)/2, which converges to exactly U V' for det > 0 (always the case for the drifted
-// rotations this is applied to); a reflection (det < 0) is returned unchanged, the reference flips a singular vector there.
+// ProjectToSO3 (slam_core.cpp:885-897): U V' of the SVD, last column of U flipped when det(U V') < 0.  The arithmetic is
+// include/glba_so3.hpp, shared with the device kernel behind glba_map_propagate.
 inline Mat33 project_to_so3(const Mat33& R_in) {
-  Mat33 X = R_in;
-  if (!(det(X) > 0.0)) return X;
-  for (int it = 0; it < 20; ++it) {
-    const double d = det(X);
-    Mat33 inv_t;   // X^-T = cofactor(X) / det
-    inv_t.m[0] = (X.m[4] * X.m[8] - X.m[5] * X.m[7]) / d; inv_t.m[1] = (X.m[5] * X.m[6] - X.m[3] * X.m[8]) / d; inv_t.m[2] = (X.m[3] * X.m[7] - X.m[4] * X.m[6]) / d;
-    inv_t.m[3] = (X.m[2] * X.m[7] - X.m[1] * X.m[8]) / d; inv_t.m[4] = (X.m[0] * X.m[8] - X.m[2] * X.m[6]) / d; inv_t.m[5] = (X.m[1] * X.m[6] - X.m[0] * X.m[7]) / d;
-    inv_t.m[6] = (X.m[1] * X.m[5] - X.m[2] * X.m[4]) / d; inv_t.m[7] = (X.m[2] * X.m[3] - X.m[0] * X.m[5]) / d; inv_t.m[8] = (X.m[0] * X.m[4] - X.m[1] * X.m[3]) / d;
-    double change = 0.0;
-    for (int q = 0; q < 9; ++q) { const double v = 0.5 * (X.m[q] + inv_t.m[q]); change = std::max(change, std::fabs(v - X.m[q])); X.m[q] = v; }
-    if (change < 1e-15) break;
-  }
-  return X;
+  Mat33 R;
+  glba_so3::project_to_so3(R_in.m, R.m);
+  return R;
 }
 // ComputeDeltaPose_SO3 (slam_core.cpp:899-912)
 inline void compute_delta_pose_so3(const Mat33& Rb_in, const Vec3& tb, const Mat33& Ra_in, const Vec3& ta, Mat33& dR, Vec3& dt) {
-  const Mat33 Rb = project_to_so3(Rb_in), Ra = project_to_so3(Ra_in);
-  dR = project_to_so3(mul(Ra, transpose(Rb)));
-  for (int r = 0; r < 3; ++r) dt.v[r] = ta.v[r] - (dR.m[r * 3] * tb.v[0] + dR.m[r * 3 + 1] * tb.v[1] + dR.m[r * 3 + 2] * tb.v[2]);
+  glba_so3::compute_delta_pose_so3(Rb_in.m, tb.v, Ra_in.m, ta.v, dR.m, dt.v);
 }
 // post_ba_map_update_for_new_keyframes (slam_core.cpp:916-973): the last window camera's pose change is applied to the
 // points / keyframes the tracking thread created while BA was running (slam_types::mpid_to_correct / kpid_to_correct,
@@ -513,7 +603,7 @@ inline void post_ba_map_update_for_new_keyframes(Map& map, const Mat33& R_before
 // cameras, has fewer than `min_obs` observations or a mean reprojection error above `max_err` pixels.  The
 // per-point arithmetic over ALL of the point's observations runs on the GPU (glba_cull_points).
 inline int post_ba_map_point_culling(Backend& be, Map& map, const CameraMatrix& K, int run_window, int local_ba_window,
-                                     double max_err = 1.0, int min_obs = 3) {
+                                     double max_err, int min_obs) {
   if (!be.ok()) return -1;
   std::vector<int> ids;
   {

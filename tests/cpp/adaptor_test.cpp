@@ -154,7 +154,21 @@ int main(int argc, char** argv) {
     std::mutex map_mutex, tracking_mutex;
     glba_summary s;
     bool ok = false;
-    int resident_culled = -2;
+    // what the tracking thread created while BA ran (slam_types::kpid_to_correct / mpid_to_correct): keyframe run_window+1 starts
+    // at keyframe run_window's pose, one new point seen only by it
+    const int n_orig = (int)map.map_points.size();
+    const int kf_new = run_window + 1, mp_new = 1000 + n_orig;
+    {
+      Frame extra = map.keyframes[run_window]; extra.id = kf_new; extra.map_point_ids.clear(); extra.map_point_ids.push_back(mp_new);
+      map.keyframes[kf_new] = extra;
+      MapPoint mp; mp.id = mp_new; mp.position = Point3d{1.0, 2.0, 30.0};
+      Observation o; o.keyframe_id = kf_new; o.point2D = Point2d{600.0, 180.0}; mp.obs.push_back(o);
+      map.map_points[mp_new] = mp;
+    }
+    const Mat33 R16_before = map.keyframes[run_window].R; const Vec3 t16_before = map.keyframes[run_window].t;
+    std::vector<int> mpids{mp_new}, kpids{kf_new};
+    PostBa post; post.mpid_to_correct = &mpids; post.kpid_to_correct = &kpids; post.cull_map_points = true; post.local_ba_window = window;
+    double mirror_err = 0.0;
     if (mode == "resident") {
       // grow the mirror the way the mapping thread would: keyframe by keyframe, a sync after each
       ResidentMap rm(be, K);
@@ -172,10 +186,26 @@ int main(int argc, char** argv) {
         }
         if (!rm.sync(grown)) { std::cout << "FAIL sync\n"; return 1; }
       }
-      ok = full_ba_resident(be, rm, map_mutex, map, window, run_window, &tracking_mutex, nullptr, &s);
-      resident_culled = rm.cull(map, run_window, window, 1.0, 3);
+      ok = full_ba_resident(be, rm, map_mutex, map, window, run_window, &tracking_mutex, nullptr, &s, &post);
+      // the device mirror followed the host: keyframe kf_new and point mp_new after glba_map_propagate
+      double cam[6], xyz[3];
+      if (glba_map_read_keyframes(rm.handle(), kf_new - rm.first_keyframe_id(), 1, cam) != GLBA_OK ||
+          glba_map_read_points(rm.handle(), rm.device_point(mp_new), 1, xyz, nullptr) != GLBA_OK) { std::cout << "FAIL mirror read\n"; return 1; }
+      Mat33 Rm; rodrigues(cam, Rm);
+      const Frame& h = map.keyframes[kf_new];
+      for (int q = 0; q < 9; ++q) mirror_err = std::max(mirror_err, std::fabs(Rm.m[q] - h.R.m[q]));
+      for (int q = 0; q < 3; ++q) mirror_err = std::max(mirror_err, std::fabs(cam[3 + q] - h.t.v[q]));
+      const Point3d& X = map.map_points[mp_new].position;
+      mirror_err = std::max(mirror_err, std::max(std::fabs(xyz[0] - X.x), std::max(std::fabs(xyz[1] - X.y), std::fabs(xyz[2] - X.z))));
+      // host edits reach the mirror through the push wrappers
+      map.keyframes[kf_new].t.v[0] += 0.5; map.map_points[mp_new].position.x += 0.25;
+      if (!rm.push_keyframes(map, {kf_new}) || !rm.push_points(map, {mp_new})) { std::cout << "FAIL push\n"; return 1; }
+      glba_map_read_keyframes(rm.handle(), kf_new - rm.first_keyframe_id(), 1, cam);
+      glba_map_read_points(rm.handle(), rm.device_point(mp_new), 1, xyz, nullptr);
+      mirror_err = std::max(mirror_err, std::max(std::fabs(cam[3] - map.keyframes[kf_new].t.v[0]), std::fabs(xyz[0] - map.map_points[mp_new].position.x)));
+      map.keyframes[kf_new].t.v[0] -= 0.5; map.map_points[mp_new].position.x -= 0.25;
     } else {
-      ok = full_ba(be, map_mutex, map, K, window, run_window, &tracking_mutex, nullptr, &s);
+      ok = full_ba(be, map_mutex, map, K, window, run_window, &tracking_mutex, nullptr, &s, &post);
     }
     std::cout << (ok ? "ok " : "false ") << s.n_iters << " " << s.initial_cost << " " << s.final_cost << "\n";
     const int first = run_window + 1 - window;
@@ -185,12 +215,24 @@ int main(int argc, char** argv) {
       for (int q = 0; q < 3; ++q) std::cout << fr.t.v[q] << " ";
       std::cout << "\n";
     }
-    for (int j = 0; j < (int)map.map_points.size(); ++j) { const MapPoint& mp = map.map_points[1000 + j]; std::cout << mp.position.x << " " << mp.position.y << " " << mp.position.z << " "; }
+    for (int j = 0; j < n_orig; ++j) { const MapPoint& mp = map.map_points[1000 + j]; std::cout << mp.position.x << " " << mp.position.y << " " << mp.position.z << " "; }
     std::cout << "\n";
-    const int culled = (mode == "resident") ? resident_culled : post_ba_map_point_culling(be, map, K, run_window, window, 1.0, 3);
-    std::cout << culled << "\n";
-    for (int j = 0; j < (int)map.map_points.size(); ++j) std::cout << (map.map_points[1000 + j].is_bad ? 1 : 0) << " ";
+    std::cout << post.n_culled << "\n";              // culling ran inside the critical section (PostBa)
+    for (int j = 0; j < n_orig; ++j) std::cout << (map.map_points[1000 + j].is_bad ? 1 : 0) << " ";
     std::cout << "\n";
+    // propagation (slam_core.cpp:916-973): the new keyframe started at keyframe run_window's pose, so it must end at its refined
+    // pose; the new point moved by the same rigid delta; both lists consumed
+    double perr = 0.0;
+    const Frame& a = map.keyframes[run_window]; const Frame& b = map.keyframes[kf_new];
+    for (int q = 0; q < 9; ++q) perr = std::max(perr, std::fabs(a.R.m[q] - b.R.m[q]));
+    for (int q = 0; q < 3; ++q) perr = std::max(perr, std::fabs(a.t.v[q] - b.t.v[q]));
+    Mat33 dR; Vec3 dt;
+    compute_delta_pose_so3(R16_before, t16_before, a.R, a.t, dR, dt);
+    const Point3d& X = map.map_points[mp_new].position;
+    const double e0 = dR.m[0] * 1.0 + dR.m[1] * 2.0 + dR.m[2] * 30.0 + dt.v[0], e1 = dR.m[3] * 1.0 + dR.m[4] * 2.0 + dR.m[5] * 30.0 + dt.v[1],
+                 e2 = dR.m[6] * 1.0 + dR.m[7] * 2.0 + dR.m[8] * 30.0 + dt.v[2];
+    perr = std::max(perr, std::max(std::fabs(X.x - e0), std::max(std::fabs(X.y - e1), std::fabs(X.z - e2))));
+    std::cout << perr << " " << (mpids.empty() && kpids.empty() ? 1 : 0) << " " << mirror_err << "\n";
     return ok ? 0 : 1;
   }
   return 2;

@@ -100,6 +100,9 @@ def test_full_ba_adaptor_matches_c_abi(exe, tmp_path, ctx, oracle):
     culled = int(out[12])
     flags = np.array(out[13].split(), int)
     assert culled == flags.sum() - 2 and flags[3] == 1 and flags[50] == 1
+    # post-BA propagation ran inside full_ba's critical section (PostBa): keyframe 17 follows keyframe 16, the late point moved
+    perr, consumed, _ = out[14].split()
+    assert float(perr) < 1e-9 and consumed == "1"
 
 
 @pytest.mark.gpu
@@ -119,6 +122,8 @@ def test_full_ba_resident_matches_full_ba(exe, tmp_path):
         assert np.allclose(np.array(la.split()[1 if la.startswith("ok") else 0:], float),
                            np.array(lb.split()[1 if lb.startswith("ok") else 0:], float), rtol=1e-9, atol=1e-12)
     assert a[12:14] == b[12:14]                                                        # culling result
+    perr, consumed, mirror = b[14].split()                                             # propagation: host map and device mirror agree
+    assert float(perr) < 1e-9 and consumed == "1" and float(mirror) < 1e-9
 
 
 @pytest.mark.gpu

@@ -204,3 +204,51 @@ def test_context_closed_before_its_map():
     c.close()
     m.close()
     assert not m._h
+
+
+def _project_to_so3_ref(A):
+    """ProjectToSO3 (slam_core.cpp:885-897) with numpy's SVD (singular values descending, as cv::SVD)."""
+    U, _, Vt = np.linalg.svd(A)
+    R = U @ Vt
+    if np.linalg.det(R) < 0:
+        U = U.copy()
+        U[:, 2] *= -1.0
+        R = U @ Vt
+    return R
+
+
+@pytest.mark.parametrize("case", ["drifted_rotation", "reflection"])
+def test_propagate_matches_numpy_restatement(ctx, case):
+    """glba_map_propagate (device) against a numpy restatement of ComputeDeltaPose_SO3 / post_ba_map_update_for_new_keyframes
+    (slam_core.cpp:885-973): a `before` rotation with numerical drift, and one with det < 0 (the U.col(2) flip)."""
+    rng = np.random.default_rng(5)
+    prob = scene.make_scene(8, 200, 3, seed=12)
+    dm = g.DeviceMap(ctx, prob.K)
+    dm.add_keyframes(prob.cam)
+    dm.add_points(prob.pt)
+    kf_last = 5
+    Ra = scene.rodrigues(prob.cam[kf_last, :3])[0]
+    ta = prob.cam[kf_last, 3:]
+    Rb = scene.rodrigues(prob.cam[kf_last, :3] + np.array([0.01, -0.02, 0.005]))[0] + 1e-7 * rng.normal(size=(3, 3))
+    if case == "reflection":
+        Rb = Rb @ np.diag([1.05, 1.0, -0.95])             # det < 0 with distinct singular values: the flip is well defined
+    tb = ta + np.array([0.2, -0.1, 0.05])
+    kf_ids, pt_ids = np.array([6, 7]), np.array([3, 50, 199])
+    dR, dt = dm.propagate(Rb, tb, kf_last, kf_ids, pt_ids)
+    dR_ref = _project_to_so3_ref(_project_to_so3_ref(Ra) @ _project_to_so3_ref(Rb).T)
+    dt_ref = ta - dR_ref @ tb
+    assert np.abs(dR - dR_ref).max() < 1e-12 and np.abs(dt - dt_ref).max() < 1e-11
+    cams = dm.read_keyframes()
+    pts, _ = dm.read_points()
+    for i in range(8):
+        if i in kf_ids:
+            R_new = dR_ref @ scene.rodrigues(prob.cam[i, :3])[0]
+            assert np.abs(scene.rodrigues(cams[i, :3])[0] - R_new).max() < 1e-11
+            assert np.abs(cams[i, 3:] - (dR_ref @ prob.cam[i, 3:] + dt_ref)).max() < 1e-11
+        else:
+            assert np.array_equal(cams[i], prob.cam[i])
+    moved = np.zeros(prob.n_pt, bool)
+    moved[pt_ids] = True
+    assert np.abs(pts[moved] - (prob.pt[moved] @ dR_ref.T + dt_ref)).max() < 1e-11
+    assert np.array_equal(pts[~moved], prob.pt[~moved])
+    dm.close()
