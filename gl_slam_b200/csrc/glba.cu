@@ -111,6 +111,8 @@ struct glba_ctx {
   Buf hmax;                                   // GLBA_MODE_G2O: max Hessian diagonal (bit pattern of a double)
   Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
+  Buf lmctl, dsum;              // device-resident LM control (LmCtl) and summary trace (glba_summary) of the on-device loop
+  bool env_host_lm = false;     // diagnostic: GLBA_HOST_LM=1 keeps the decisions on the host for small windows too
   bool use_pipe = false;        // large maps: persistent TMA-fed tile kernels (glba_pipe.cuh)
   bool env_pipe = true, env_force_large = false;
   Buf tile_desc, tile_cams, pm_slot;
@@ -528,26 +530,29 @@ int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
 }
 
 constexpr int kInKernelReduceMaxTiles = 256;   // above this the per-tile partials are folded by k_reduce_rows (64 CTAs)
-RedArgs red_args(glba_ctx* ctx, int counter, const int* slots, bool in_kernel = true) {
-  RedArgs R; R.counter = in_kernel ? ctx->counters.as<unsigned>() + counter : nullptr; R.scal = ctx->d_scal;
+RedArgs red_args(glba_ctx* ctx, int counter, const int* slots, bool in_kernel = true, const LmCtl* ctl = nullptr, int gate = GATE_ALWAYS,
+                 const LmHook* hook = nullptr) {
+  RedArgs R{}; R.counter = in_kernel ? ctx->counters.as<unsigned>() + counter : nullptr; R.scal = ctx->d_scal;
   for (int q = 0; q < 5; ++q) R.slots[q] = slots[q];
+  R.ctl = ctl; R.gate = gate;
+  if (hook) R.hook = *hook;
   return R;
 }
 const int kLinSlots[5] = {S_COST, S_XN2_P, S_BAD, S_NOTPD_P, S_GMAX_P};
 const int kStepSlots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
 
 // point-major half of a linearisation, INCLUDING the reduction of its scalars into d_scal
-int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius) {
+int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius, const LmCtl* ctl = nullptr) {
   const int c = ctx->cur;
   if (ctx->use_pipe) {
     k_lin_pipe<<<pipe_grid(ctx, ctx->occ_lin), P_NT, sizeof(LinSmem), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->pt4[c].as<double4>(),
         (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(),
         ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal,
-        1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots, true));
+        1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots, true, ctl, GATE_ACCEPTED));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   } else if (ctx->use_tiles) {
     const size_t smem = (size_t)8 * NT_T * ctx->opt * sizeof(double);
-    const RedArgs RA = red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles);
+    const RedArgs RA = red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles, ctl, GATE_ACCEPTED);
 #define LIN_TILE_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
     ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), \
     ctx->cinv.as<double>(), ctx->u0p.as<double4>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), RA
@@ -555,7 +560,7 @@ int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, dou
     else k_linearize_tile<OPT_SMALL><<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(LIN_TILE_ARGS);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (ctx->n_tiles > kInKernelReduceMaxTiles)
-      LAUNCH(k_reduce_rows<4>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 4, kLinSlots));
+      LAUNCH(k_reduce_rows<4>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 4, kLinSlots, true, ctl, GATE_ACCEPTED));
   } else {
     LAUNCH(k_linearize_pm, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->pt4[c].as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(),
@@ -588,17 +593,17 @@ void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg,
            (const double4*)nullptr, 0.0, (double*)nullptr);
 }
 
-void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
+void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius, const LmCtl* ctl = nullptr, const LmHook* hook = nullptr) {
   const int c = ctx->cur, d = c ^ 1;
   if (ctx->use_pipe) {
     k_pt_pipe<1><<<pipe_grid(ctx, ctx->occ_pt1), P_NT, sizeof(PtSmem<1>), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(),
         (const double4*)ctx->u0p.as<double4>(), (double4*)nullptr, (const CgState*)nullptr, 0, (const double4*)ctx->pt4[c].as<double4>(),
         ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(), (const double*)ctx->Craw.as<double>(),
-        (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 5, kStepSlots, true));
+        (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 5, kStepSlots, true, ctl, GATE_ALWAYS, hook));
     g_launches.fetch_add(1, std::memory_order_relaxed);
   } else if (ctx->use_tiles) {
-    const RedArgs RA = red_args(ctx, 5, kStepSlots, ctx->n_tiles <= kInKernelReduceMaxTiles);
+    const RedArgs RA = red_args(ctx, 5, kStepSlots, ctx->n_tiles <= kInKernelReduceMaxTiles, ctl, GATE_ALWAYS, hook);
 #define PT1_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
     (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), (double4*)nullptr, (const CgState*)nullptr, 0, \
     (const double4*)ctx->pt4[c].as<double4>(), ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(), \
@@ -606,7 +611,7 @@ void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
     if (ctx->opt == OPT_LARGE) LAUNCH((k_point_tile<1, OPT_LARGE>), ctx->n_tiles, NT_T, PT1_ARGS);
     else LAUNCH((k_point_tile<1, OPT_SMALL>), ctx->n_tiles, NT_T, PT1_ARGS);
     if (ctx->n_tiles > kInKernelReduceMaxTiles)
-      LAUNCH(k_reduce_rows<-1>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 5, kStepSlots));
+      LAUNCH(k_reduce_rows<-1>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 5, kStepSlots, true, ctl, GATE_ALWAYS, hook));
   } else {
     LAUNCH(k_point_pass<1>, cdiv(ctx->n_pt, NT_PM), NT_PM, pm_args(ctx, o), (const double4*)ctx->rec_pm.as<double4>(),
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(),
@@ -620,8 +625,9 @@ void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius) {
 #define CAM_LIN_FIN_ARGS n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(), \
     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), \
     ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, \
-    o->max_lm_diagonal, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->d_scal
-void launch_cam_lin_fin(glba_ctx* ctx, const glba_options* o, int first) {
+    o->max_lm_diagonal, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->d_scal, ctl, hk
+void launch_cam_lin_fin(glba_ctx* ctx, const glba_options* o, int first, const LmCtl* ctl = nullptr, const LmHook* hook = nullptr) {
+  const LmHook hk = hook ? *hook : LmHook{};
   const int c = ctx->cur, n_cam = ctx->n_cam;
   if (ctx->world > 1) LAUNCH(k_cam_lin_fin<false>, ctx->grid_c, NT_C, CAM_LIN_FIN_ARGS);
   else LAUNCH(k_cam_lin_fin<true>, ctx->grid_c, NT_C, CAM_LIN_FIN_ARGS);
@@ -672,15 +678,15 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
 int do_linearize_schur(glba_ctx* ctx, const glba_options* o, int first, double radius) { return do_linearize_impl(ctx, o, first, radius, true); }
 
 // re-damp point blocks for a new radius (after a rejected / invalid step)
-int do_redamp(glba_ctx* ctx, double radius) {
+int do_redamp(glba_ctx* ctx, double radius, const LmCtl* ctl = nullptr) {
   const int n_pt = ctx->n_pt;
   if (!n_pt) return GLBA_OK;
   const int grid_pm = cdiv(n_pt, NT_PM);
   mark(ctx, PH_SCHUR);
   LAUNCH(k_point_damp, grid_pm, NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
-         (const double4*)ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>());
+         (const double4*)ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), ctl);
   ReduceMap M{}; M.n = 1; M.slot[0] = S_NOTPD_P; M.is_max[0] = 0;
-  LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 1, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal);
+  LAUNCH(k_reduce_partials, 1, NT_CAM, grid_pm, 1, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal, ctl, (int)GATE_REDAMP);
   if (ctx->world > 1) AR(ctx->d_scal + S_NOTPD_P, 1, kNcclSum);
   mark(ctx, -1);
   CHECK_LAUNCHES();
@@ -765,7 +771,7 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
 }
 
 // Exact solve of the reduced camera system for small windows: explicit S, Cholesky (glba_dense.cuh).
-int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
+int do_dense(glba_ctx* ctx, const glba_options* o, double radius, const LmCtl* ctl = nullptr) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
   const int n = 6 * n_cam;
@@ -775,7 +781,7 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
   mark(ctx, PH_SCHUR);
   k_dense_schur<<<ctx->dn_grid, DN_NT, sm_schur, ctx->stream>>>(pm_args(ctx, o), n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(),
       (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->dn_ppc,
-      ctx->dn_part.as<double>());
+      ctx->dn_part.as<double>(), ctl);
   g_launches.fetch_add(1, std::memory_order_relaxed);
 #define DN_RED_ARGS n_cam, (const double*)ctx->dn_part.as<double>(), (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->Bc.as<double>(), \
     (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->dn_red.as<double>(), ctx->dn_full.as<double>()
@@ -784,11 +790,11 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius) {
     AR(ctx->dn_red.as<double>(), (size_t)len, kNcclSum);
     LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, 0, DN_RED_ARGS, 1);
   } else {
-    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, ctx->dn_grid, DN_RED_ARGS, 1);
+    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, ctx->dn_grid, DN_RED_ARGS, 1, ctl);
   }
   mark(ctx, PH_SOLVE);
   k_dense_solve<<<1, DN_NS, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_full.as<double>(),
-      ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->d_scal);
+      ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->d_scal, ctl);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   mark(ctx, -1);
   CHECK_LAUNCHES();
@@ -834,6 +840,66 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
 }
 
 int fetch_scal(glba_ctx* ctx) { return read_scalars(ctx); }
+
+// Small windows (exact dense reduced solve, one GPU, Ceres semantics): the whole trust-region loop runs on the device.
+// The host enqueues LM iterations WITHOUT knowing their outcome — every kernel is gated by the LmCtl the decision kernels
+// maintain (glba_lm.cuh) — and synchronises once per kPollIters iterations to read one flag.  Entered after the initial
+// linearisation (cost, |g|, |x| already on the host, sum[0] filled, loop-top tests of iteration 1 passed).
+constexpr int kPollIters = 4;
+bool device_lm_eligible(const glba_ctx* ctx, const glba_options* o, bool dense, bool g2o) {
+  return dense && !g2o && ctx->world == 1 && ctx->use_tiles && !o->verbose && !ctx->env_host_lm && ctx->n_obs > 0;
+}
+int enqueue_lm_iteration(glba_ctx* ctx, const glba_options* o, const LmCtl* ctl, const LmParams& P) {
+  const int c = ctx->cur, d = c ^ 1;
+  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  const double radius = 1.0;        // by-value radii are ignored: the kernels read ctl->inv_radius
+  int st;
+  if ((st = do_redamp(ctx, radius, ctl))) return st;                                    // runs only after a rejected / invalid step
+  if ((st = do_dense(ctx, o, radius, ctl))) return st;
+  if (n_cam) LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+                    (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
+                    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, ctl);
+  LmHook hook; hook.ctl = ctx->lmctl.as<LmCtl>(); hook.sum = ctx->dsum.as<glba_summary>(); hook.P = P;
+  if (n_pt) launch_point_pass1(ctx, o, radius, ctl, &hook);      // its last CTA takes the accept / reject decision (lm_decide)
+  // accepted: candidate -> current, re-linearise (all three exit at once otherwise)
+  LAUNCH(k_accept_copy, std::max(1, std::min(4 * ctx->n_sm, cdiv((long)30 * n_cam + n_pt, 256))), 256, ctl, n_cam, n_pt,
+         (const double*)ctx->cam[d].as<double>(), (const double*)ctx->camtab[d].as<double>(), (const double4*)ctx->pt4[d].as<double4>(),
+         ctx->cam[c].as<double>(), ctx->camtab[c].as<double>(), ctx->pt4[c].as<double4>());
+  if (n_pt) { if ((st = launch_linearize_points(ctx, o, 0, radius, ctl))) return st; }
+  if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+                            (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>(), ctl);
+  if (n_cam) launch_cam_lin_fin(ctx, o, 0, ctl, &hook);          // its last CTA absorbs the re-linearisation (lm_absorb)
+  return GLBA_OK;
+}
+int run_lm_device(glba_ctx* ctx, const glba_options* o, glba_summary* sum, double radius, double cost, double gmax, double x_norm) {
+  ENSURE(LmCtl, ctx->lmctl, 1); ENSURE(glba_summary, ctx->dsum, 1);
+  LmCtl h{};
+  h.inv_radius = 1.0 / radius; h.done = 0; h.accepted = 0; h.need_redamp = 0;
+  h.radius = radius; h.decrease_factor = 2.0; h.cost = cost; h.gmax = gmax; h.x_norm = x_norm;
+  h.it = 0; h.n_invalid = 0; h.n_rejected = 0;
+  LmParams P;
+  P.max_iters = o->max_iters; P.max_invalid = o->max_consecutive_invalid_steps; P.n_free_cam = ctx->n_free_cam;
+  P.function_tol = o->function_tol; P.gradient_tol = o->gradient_tol; P.parameter_tol = o->parameter_tol;
+  P.max_radius = o->max_radius; P.min_radius = o->min_radius; P.min_rel = o->min_relative_decrease;
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->lmctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->dsum.p, sum, sizeof(*sum), cudaMemcpyHostToDevice, s));       // trace so far (index 0), counters
+  const LmCtl* ctl = ctx->lmctl.as<LmCtl>();
+  int enq = 0, st;
+  for (;;) {
+    for (int b = 0; b < kPollIters && enq < o->max_iters; ++b, ++enq)
+      if ((st = enqueue_lm_iteration(ctx, o, ctl, P))) return st;
+    CU(cudaMemcpyAsync(ctx->h_flags, &ctx->lmctl.as<LmCtl>()->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (ctx->h_flags[0] != 0) break;
+    if (enq >= o->max_iters) return fail(ctx, GLBA_E_CUDA, "device LM loop did not terminate within max_iters");
+  }
+  CU(cudaMemcpyAsync(sum, ctx->dsum.p, sizeof(*sum), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  collect(ctx);
+  return GLBA_OK;
+}
 
 // The trust-region loop (Ceres TrustRegionMinimizer semantics; see oracle/glba_oracle.cpp for the
 // statement-by-statement restatement this mirrors).  One host synchronisation per LM iteration: the scalars of the
@@ -899,8 +965,14 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     cost = S[S_COST]; gmax = std::max(S[S_GMAX_P], S[S_GMAX_C]); x_norm = std::sqrt(S[S_XN2_P] + S[S_XN2_C]);
     return true;
   };
+  bool on_device = false;
   if (ctx->n_obs == 0 && ctx->world == 1) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }
   else if (g2o && !(radius > 0.0)) { sum->termination = GLBA_TERM_CONVERGENCE; sum->stop_reason = GLBA_STOP_GRADIENT_TOL; }   // nothing free
+  else if (device_lm_eligible(ctx, o, dense, g2o) && o->max_iters > 0 && gmax > o->gradient_tol && radius > o->min_radius) {
+    // small window: decisions on the device, no host synchronisation inside the iteration (run_lm_device)
+    if ((st = run_lm_device(ctx, o, sum, radius, cost, gmax, x_norm))) return st;
+    on_device = true;
+  }
   else for (;;) {
     if (g2o) {
       if (sum->n_successful >= o->max_iters) { sum->stop_reason = GLBA_STOP_MAX_ITERS; break; }
@@ -955,7 +1027,8 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     sum->relative_decrease[it] = rel;
     if (rel > o->min_relative_decrease) {
       ctx->cur ^= 1;     // the candidate buffers (state + camera table) become current
-      double shrink = 1.0 - std::pow(2.0 * rel - 1.0, 3);
+      const double tq = 2.0 * rel - 1.0;
+      double shrink = 1.0 - tq * tq * tq;          // (the device-resident loop, glba_lm.cuh, cubes the same way)
       if (g2o) shrink = std::min(shrink, 2.0 / 3.0);                 // _goodStepUpperScale
       radius = radius / std::max(1.0 / 3.0, shrink);
       radius = std::min(o->max_radius, radius);
@@ -979,7 +1052,7 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     if (!absorb_pending()) { sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; }
     else { sum->cost[it] = cost; sum->gradient_max_norm[it] = gmax; }
   }
-  sum->n_iters = it; sum->final_cost = cost;
+  if (!on_device) { sum->n_iters = it; sum->final_cost = cost; }
   sum->t_setup_ms = ctx->t_phase[PH_SETUP]; sum->t_linearize_ms = ctx->t_phase[PH_LIN]; sum->t_schur_ms = ctx->t_phase[PH_SCHUR];
   sum->t_solve_ms = ctx->t_phase[PH_SOLVE]; sum->t_update_ms = ctx->t_phase[PH_UPDATE];
   sum->t_comm_ms = ctx->t_phase[PH_COMM];
@@ -1075,6 +1148,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (set_func_attributes(ctx) != GLBA_OK) { delete ctx; return GLBA_E_CUDA; }
   if (const char* e = std::getenv("GLBA_TIMING")) ctx->env_timing = (e[0] == '1');          // diagnostic: phase timings for small problems too
   if (const char* e = std::getenv("GLBA_RELABEL")) ctx->env_relabel = (e[0] != '0');   // diagnostic: GLBA_RELABEL=0 keeps the caller's point order
+  if (const char* e = std::getenv("GLBA_HOST_LM")) ctx->env_host_lm = (e[0] == '1');   // diagnostic: host-side accept/reject for small windows
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
@@ -1103,7 +1177,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->cinv, &ctx->u0p, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);

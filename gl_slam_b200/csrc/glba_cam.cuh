@@ -164,8 +164,17 @@ __device__ __forceinline__ void load_acc27(const int i, const int n_cam, const d
     const int ncl = min(NT_C, n_cam - cam0);
     for (int e = threadIdx.x; e < ncl * 27; e += NT_C) {
       const int cl = e / 27, q = e - cl * 27;
+      // same summation order as a plain loop, but four loads in flight at a time (the dependent L2 round trips of the
+      // one-at-a-time loop were most of this kernel on a 10-camera window)
       double sacc = 0.0;
-      for (int ch = cam_chunk_start[cam0 + cl]; ch < cam_chunk_start[cam0 + cl + 1]; ++ch) sacc += part27[(size_t)27 * ch + q];
+      int ch = cam_chunk_start[cam0 + cl];
+      const int ce = cam_chunk_start[cam0 + cl + 1];
+      for (; ch + 4 <= ce; ch += 4) {
+        const double v0 = part27[(size_t)27 * ch + q], v1 = part27[(size_t)27 * (ch + 1) + q], v2 = part27[(size_t)27 * (ch + 2) + q],
+                     v3 = part27[(size_t)27 * (ch + 3) + q];
+        sacc += v0; sacc += v1; sacc += v2; sacc += v3;
+      }
+      for (; ch < ce; ++ch) sacc += part27[(size_t)27 * ch + q];
       stage[cl][q] = sacc;
     }
     __syncthreads();
@@ -185,8 +194,9 @@ __global__ void __launch_bounds__(NT_C)
 k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
               const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start, const double* __restrict__ part27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
               double* __restrict__ lamc, const int first, const int jacobi, const double min_diag, const double max_diag,
-              double* part, unsigned* counter, double* scal) {
+              double* part, unsigned* counter, double* scal, const LmCtl* __restrict__ ctl = nullptr, const LmHook hook = LmHook{}) {
   __shared__ double sm[2 * NT_C / 32];
+  if (ctl_skip(ctl, GATE_ACCEPTED)) return;
   __shared__ double smo[2];
   __shared__ double stage[FUSE ? NT_C : 1][27];
   const int i = blockIdx.x * NT_C + threadIdx.x;
@@ -227,7 +237,9 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
   const double v[2] = {xn2, gmax};
   const bool mx[2] = {false, true};
   const int slot[2] = {S_XN2_C, S_GMAX_C};
-  finish_scalars<2>(v, mx, slot, part, counter, scal, sm, smo);
+  const bool last = finish_scalars<2>(v, mx, slot, part, counter, scal, sm, smo);
+  // device-resident LM loop: this was the last kernel of the re-linearisation after an accepted step
+  if (last && threadIdx.x == 0 && hook.ctl != nullptr) { __threadfence(); lm_absorb(hook.ctl, hook.P, scal, hook.sum); }
 }
 
 // M_i = B_i + lam/radius - T' Mhat T (diagonal block of S), rhs_i = g_i - T' rhat, Minv_i.
@@ -450,10 +462,12 @@ k_cg_p(const int n_cam, const double* __restrict__ camtab, const double* __restr
 // camera parts of |y|^2, y.g, y' Lambda y
 __global__ void __launch_bounds__(NT_C)
 k_cam_step2(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
-            const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+            const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius_arg,
             double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ xtab, double* part, unsigned* counter, double* scal,
-            const int mode) {
+            const int mode, const LmCtl* __restrict__ ctl = nullptr) {
   __shared__ double sm[3 * NT_C / 32];
+  if (ctl_skip(ctl, GATE_ALWAYS)) return;
+  const double inv_radius = ctl_inv_radius(ctl, inv_radius_arg);
   __shared__ double smo[3];
   const int i = blockIdx.x * NT_C + threadIdx.x;
   double yn2 = 0.0, ygd = 0.0, yly = 0.0;

@@ -39,8 +39,9 @@ __device__ __forceinline__ void chol3(const double* C, double* L /* l00 l10 l11 
 __global__ void __launch_bounds__(DN_NT)
 k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_free, const double4* __restrict__ rec_pm,
               const double* __restrict__ camtab, const double* __restrict__ cinv, const double4* __restrict__ u0p, const int pts_per_cta,
-              double* __restrict__ part /* [grid][n_pairs*36 + 6*n_cam] */) {
+              double* __restrict__ part /* [grid][n_pairs*36 + 6*n_cam] */, const LmCtl* __restrict__ ctl = nullptr) {
   extern __shared__ double dsm[];
+  if (ctl_skip(ctl, GATE_ALWAYS)) return;
   const int n_pairs = n_cam * (n_cam + 1) / 2;
   double* V = dsm;                                   // [DN_TP][n_cam][18]
   double* Wu = V + (size_t)DN_TP * n_cam * 18;       // [DN_TP][n_cam][6]
@@ -150,8 +151,10 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
 // B + Lambda on the diagonal blocks and identity rows for non-free cameras) followed by rhs (n).
 __global__ void k_dense_reduce(const int n_parts, const int n_cam, const double* __restrict__ part, const uint8_t* __restrict__ cam_free,
                                const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc,
-                               const double inv_radius, double* __restrict__ Sred /* pair sums (kept for the sharded all-reduce) */,
-                               double* __restrict__ Sfull /* n*n + n */, const int assemble) {
+                               const double inv_radius_arg, double* __restrict__ Sred /* pair sums (kept for the sharded all-reduce) */,
+                               double* __restrict__ Sfull /* n*n + n */, const int assemble, const LmCtl* __restrict__ ctl = nullptr) {
+  if (ctl_skip(ctl, GATE_ALWAYS)) return;
+  const double inv_radius = ctl_inv_radius(ctl, inv_radius_arg);
   // 8 lanes per element: lane `sub` sums copies sub, sub+8, ... (8x shorter dependent load chains), the 8 partial sums
   // are combined by a fixed xor butterfly, so the result is still order-deterministic
   const int n_pairs = n_cam * (n_cam + 1) / 2;
@@ -199,8 +202,10 @@ __global__ void k_dense_reduce(const int n_parts, const int n_cam, const double*
 constexpr int DN_NS = 128;   // threads of the solve kernel (>= 6*DN_MAXCAM)
 __global__ void __launch_bounds__(DN_NS)
 k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ Sfull /* n*n + n, assembled */,
-              double* __restrict__ y, double* __restrict__ Md, double* __restrict__ rhs_out, double* __restrict__ scal) {
+              double* __restrict__ y, double* __restrict__ Md, double* __restrict__ rhs_out, double* __restrict__ scal,
+              const LmCtl* __restrict__ ctl = nullptr) {
   extern __shared__ double dsm[];
+  if (ctl_skip(ctl, GATE_ALWAYS)) return;
   const int n = 6 * n_cam;
   const int ld = n | 1;
   double* S = dsm;                       // n x ld, lower triangle is what the factorisation reads

@@ -66,6 +66,23 @@ struct CgState {
   int reason;        // 1 converged, 2 breakdown (p'Sp <= 0), 3 iteration cap
   int iters, max_iters;
 };
+// Device-resident trust-region control (glba_lm.cuh): the decision kernel writes it, every kernel of an LM iteration that the
+// host enqueues WITHOUT knowing the decision reads it.  A null pointer means "host-driven": run, and use the by-value radius.
+struct LmCtl {
+  double inv_radius;       // 1 / trust-region radius of the step being computed
+  int done;                // the loop has terminated: everything enqueued behind exits at once
+  int accepted;            // last step accepted: the candidate becomes current and is re-linearised
+  int need_redamp;         // last step rejected / invalid: point blocks are re-damped for the new radius
+  // trust-region state (k_lm_decide / k_lm_absorb only)
+  double radius, decrease_factor, cost, gmax, x_norm;
+  int it, n_invalid, n_rejected, pad;
+};
+enum LmGate { GATE_ALWAYS = 0, GATE_ACCEPTED = 1, GATE_REDAMP = 2 };
+__device__ __forceinline__ bool ctl_skip(const LmCtl* c, const int gate) {
+  return c != nullptr && (c->done != 0 || (gate == GATE_ACCEPTED && c->accepted == 0) || (gate == GATE_REDAMP && c->need_redamp == 0));
+}
+__device__ __forceinline__ double ctl_inv_radius(const LmCtl* c, const double by_value) { return c != nullptr ? c->inv_radius : by_value; }
+
 constexpr int XTAB = 16;   // per-camera gather row of the point passes (128 B): xg[6] = T x | R[9] | small-angle flag
 
 // ---------------------------------------------------------------------------------------------
@@ -518,10 +535,12 @@ k_linearize_pm(const PmArgs A, const double4* __restrict__ pt, const double* __r
 // Re-damp the point blocks after the radius changed (rejected step): same C, g, lam.
 __global__ void __launch_bounds__(NT_PM)
 k_point_damp(const int n_pt, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw,
-             const double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const double inv_radius,
-             double* __restrict__ part /* [grid][1] notpd */) {
+             const double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const double inv_radius_arg,
+             double* __restrict__ part /* [grid][1] notpd */, const LmCtl* __restrict__ ctl = nullptr) {
   __shared__ double sm[NT_PM / 32];
   __shared__ double smo[1];
+  if (ctl_skip(ctl, GATE_REDAMP)) return;
+  const double inv_radius = ctl_inv_radius(ctl, inv_radius_arg);
   const int j = blockIdx.x * NT_PM + threadIdx.x;
   double notpd = 0.0;
   if (j < n_pt && pt_free[j]) {
@@ -558,9 +577,10 @@ struct CmArgs {
 // 5 CTAs/SM (96 registers, a few spilled accumulators) beat 4 (126 registers): measured 0.067 vs 0.076 ms on C4
 __global__ void __launch_bounds__(NT_HCM, 5)
 k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
-               double* __restrict__ part /* [n_chunks][27] */) {
+               double* __restrict__ part /* [n_chunks][27] */, const LmCtl* __restrict__ ctl = nullptr) {
   __shared__ double sm[27 * NT_HCM / 32];
   __shared__ double smo[27];
+  if (ctl_skip(ctl, GATE_ACCEPTED)) return;
   const int ch = blockIdx.x;
   const int cam = A.chunk_cam[ch];
   double acc[27];
@@ -806,9 +826,11 @@ k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* _
 struct ReduceMap { int n; int slot[8]; int is_max[8]; };
 
 __global__ void __launch_bounds__(NT_CAM)
-k_reduce_partials(const int rows, const int nv, const double* __restrict__ part, const ReduceMap M, double* __restrict__ scal) {
+k_reduce_partials(const int rows, const int nv, const double* __restrict__ part, const ReduceMap M, double* __restrict__ scal,
+                  const LmCtl* __restrict__ ctl = nullptr, const int gate = GATE_ALWAYS) {
   __shared__ double sm[NT_CAM / 32];
   __shared__ double smo[1];
+  if (ctl_skip(ctl, gate)) return;
   for (int q = 0; q < nv; ++q) {
     const bool is_max = M.is_max[q] != 0;
     double acc = 0.0;   // all reduced quantities are >= 0, so 0 is neutral for max as well

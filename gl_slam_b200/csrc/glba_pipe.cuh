@@ -229,10 +229,12 @@ __global__ void __launch_bounds__(P_NT)
 k_lin_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ pt, const double* __restrict__ camtab,
            double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
            double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const int first, const int jacobi,
-           const double min_diag, const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */,
+           const double min_diag, const double max_diag, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */,
            const RedArgs RA) {
   extern __shared__ __align__(128) unsigned char dsm_raw[];
   LinSmem& S = *reinterpret_cast<LinSmem*>(dsm_raw);
+  if (ctl_skip(RA.ctl, RA.gate)) return;
+  const double inv_radius = ctl_inv_radius(RA.ctl, inv_radius_arg);
   const int tid = threadIdx.x;
   const int n_my = (M.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (tid == 0) { mbar_init(&S.full[0], 1); mbar_init(&S.full[1], 1); mbar_fence_init(); }
@@ -428,10 +430,12 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
           const CgState* __restrict__ cg, const int li,
           // MODE 1 only:
           const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
-          const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+          const double4* __restrict__ lam4, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   extern __shared__ __align__(128) unsigned char dsm_raw[];
   PtSmem<MODE>& S = *reinterpret_cast<PtSmem<MODE>*>(dsm_raw);
   if (MODE == 0 && cg && cg->done_at <= li) return;
+  if (MODE == 1 && ctl_skip(RA.ctl, RA.gate)) return;
+  const double inv_radius = (MODE == 1) ? ctl_inv_radius(RA.ctl, inv_radius_arg) : inv_radius_arg;
   const int tid = threadIdx.x;
   const int n_my = (M.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (tid == 0) { mbar_init(&S.full[0], 1); mbar_init(&S.full[1], 1); mbar_fence_init(); }
@@ -625,7 +629,7 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
     block_reduce<5, P_NT>(v, S.red, S.red + 5 * P_NT / 32);
     if (tid < 5) part[(size_t)5 * blockIdx.x + tid] = S.red[5 * P_NT / 32 + tid];
     __syncthreads();
-    last_block_reduce5<-1, P_NT>(part, gridDim.x, RA.slots, RA.counter, RA.scal, S.red, S.red + 5 * P_NT / 32);
+    last_block_reduce5<-1, P_NT>(part, gridDim.x, RA.slots, RA.counter, RA.scal, S.red, S.red + 5 * P_NT / 32, &RA.hook);
   }
 }
 

@@ -10,6 +10,7 @@
 // The thread-per-point kernels in glba_kernels.cuh stay as the fallback for tracks longer than NT_T/2.
 #pragma once
 #include "glba_kernels.cuh"
+#include "glba_lm.cuh"
 
 namespace glba {
 
@@ -32,7 +33,8 @@ constexpr int OPT_LARGE = GLBA_OPT_LARGE, OPT_SMALL = 1;
 // MAXCOL = column reduced with max (-1: none).  Saves a separate single-CTA reduction launch per pass.
 template <int MAXCOL, int NT = GLBA_NT_T>
 __device__ __forceinline__ void last_block_reduce5(const double* part, const int rows, const int* slots, unsigned* counter,
-                                                   double* __restrict__ scal, double* sm /* 5*NT/32 */, double* smo /* 5 */) {
+                                                   double* scal, double* sm /* 5*NT/32 */, double* smo /* 5 */,
+                                                   const LmHook* hook = nullptr) {
   __shared__ bool s_last;
   if (counter == nullptr) return;       // large grids: the host launches k_reduce_rows instead (uniform branch)
   if (threadIdx.x == 0) {
@@ -59,9 +61,17 @@ __device__ __forceinline__ void last_block_reduce5(const double* part, const int
     __syncthreads();
     block_reduce<1, NT, true>(mx, sm, smo);
     if (threadIdx.x == 0) scal[slots[MAXCOL]] = smo[0];
+  } else if (hook != nullptr && hook->ctl != nullptr) {
+    // back-substitution pass of a device-resident LM loop: its scalars are final, take the trust-region decision
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); lm_decide(hook->ctl, hook->P, scal, hook->sum); }
   }
 }
-struct RedArgs { unsigned* counter; double* scal; int slots[5]; };
+struct RedArgs {
+  unsigned* counter; double* scal; int slots[5];
+  const LmCtl* ctl; int gate;      // device-resident LM loop: skip / radius (glba_kernels.cuh)
+  LmHook hook;                     // ... and the decision to take once the scalars of this pass are final (MAXCOL == -1 passes)
+};
 
 // Large grids: 64 CTAs each fold a fixed, contiguous range of the per-tile partial rows, the last one folds the 64.
 template <int MAXCOL>
@@ -69,6 +79,7 @@ __global__ void __launch_bounds__(NT_T)
 k_reduce_rows(const double* __restrict__ part, const int rows, double* __restrict__ part2 /* [grid][5] */, const RedArgs RA) {
   __shared__ double sm[5 * NT_T / 32];
   __shared__ double smo[5];
+  if (ctl_skip(RA.ctl, RA.gate)) return;
   const int per = (rows + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -88,7 +99,7 @@ k_reduce_rows(const double* __restrict__ part, const int rows, double* __restric
     if (threadIdx.x == 0) part2[(size_t)5 * blockIdx.x + MAXCOL] = smo[0];
   }
   __syncthreads();
-  last_block_reduce5<MAXCOL>(part2, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo);
+  last_block_reduce5<MAXCOL>(part2, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo, &RA.hook);
 }
 
 constexpr int CWIN = 32;    // camera rows staged in shared memory per tile: [cmin, cmin + CWIN)
@@ -107,9 +118,11 @@ __global__ void __launch_bounds__(NT_T)
 k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ pt, const double* __restrict__ camtab,
                  double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
                  double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const int first, const int jacobi, const double min_diag,
-                 const double max_diag, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+                 const double max_diag, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   constexpr int TILE_OBS = NT_T * OPT;
   extern __shared__ double dsm[];
+  if (ctl_skip(RA.ctl, RA.gate)) return;
+  const double inv_radius = ctl_inv_radius(RA.ctl, inv_radius_arg);
   double (*val)[TILE_OBS] = reinterpret_cast<double (*)[TILE_OBS]>(dsm);     // [8][TILE_OBS]: J~p rows (3+3), r~ (2)
   __shared__ double sm[4 * NT_T / 32];
   __shared__ double smo[4];
@@ -243,9 +256,11 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
              const double* __restrict__ cinv, const double4* __restrict__ u0p, double4* __restrict__ u4, const CgState* __restrict__ cg, const int li,
              // MODE 1 only:
              const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
-             const double4* __restrict__ lam4, const double inv_radius, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+             const double4* __restrict__ lam4, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
   constexpr int TILE_OBS = NT_T * OPT;
   __shared__ double val[3][TILE_OBS];
+  if (MODE == 1 && ctl_skip(RA.ctl, RA.gate)) return;
+  const double inv_radius = (MODE == 1) ? ctl_inv_radius(RA.ctl, inv_radius_arg) : inv_radius_arg;
   __shared__ __align__(16) double xs[CWIN * XROW];                     // staged gather rows of cameras [cmin, cmin+CWIN)
   __shared__ __align__(16) double cs[MODE == 1 ? CWIN * CROW : 2];     // staged candidate rows (R, c)
   if (MODE == 0 && cg && cg->done_at <= li) return;
@@ -375,7 +390,7 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
     block_reduce<5, NT_T>(v, sm, smo);
     if (tid < 5) part[(size_t)5 * blockIdx.x + tid] = smo[tid];
     __syncthreads();
-    last_block_reduce5<-1>(part, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo);
+    last_block_reduce5<-1>(part, gridDim.x, RA.slots, RA.counter, RA.scal, sm, smo, &RA.hook);
   }
 }
 
