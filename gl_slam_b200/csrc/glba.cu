@@ -155,11 +155,31 @@ int fail(glba_ctx* c, int code, const char* fmt, ...) {
                   cudaGetErrorString(e__));                                                              \
   } while (0)
 
-#define LAUNCH(kernel, grid, block, ...)                                  \
-  do {                                                                    \
-    kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);             \
-    g_launches.fetch_add(1, std::memory_order_relaxed);                   \
-  } while (0)
+// Every kernel is launched with programmatic stream serialisation allowed (PDL, see pdl_grid_sync in glba_kernels.cuh): the
+// launch latency of kernel N+1 hides behind kernel N, which is what the small-window solves and the PCG iteration are made
+// of (8-13 dependent launches of 5-35 us each).  GLBA_PDL=0 launches plainly (diagnostic).
+// Measured on C4 (tools/ab_pdl.sh): a kernel allowed to start early behind a multi-wave or persistent kernel makes that
+// transition 10-18 us SLOWER (step 0.389 -> 0.425 ms, LM 165 -> 127 it/s with every launch flagged), while chains of small
+// kernels gain ~2 us per launch (C2 window 3.5 -> 3.0 ms).  So a launch takes the attribute only when it AND the kernel
+// launched before it are small (at most two CTAs per SM): that is the small-window solve; large maps launch plainly.
+bool g_pdl = true;
+unsigned g_pdl_max_grid = 296;
+thread_local bool g_prev_small = false;
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(cudaStream_t stream, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool small = grid.x * grid.y * grid.z <= g_pdl_max_grid;
+  cfg.attrs = attr; cfg.numAttrs = (g_pdl && small && g_prev_small) ? 1 : 0;
+  g_prev_small = small;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);       // launch errors are sticky: check_launches() per phase
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+#define LAUNCH(kernel, grid, block, ...) launch_kernel(ctx->stream, kernel, dim3(grid), dim3(block), 0, __VA_ARGS__)
+#define LAUNCH_SMEM(kernel, grid, block, smem, ...) launch_kernel(ctx->stream, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
 
 template <typename T>
 int ensure(glba_ctx* ctx, Buf& b, size_t n) {
@@ -525,7 +545,7 @@ TileArgs tile_args(glba_ctx* ctx) { return TileArgs{ctx->tile_pt.as<int>(), ctx-
 int reduce_pm_partials(glba_ctx* ctx, int rows, const int* slots, int max_col) {
   ReduceMap M{}; M.n = 5;
   for (int q = 0; q < 5; ++q) { M.slot[q] = slots[q]; M.is_max[q] = (q == max_col); }
-  LAUNCH(k_reduce_partials, 1, NT_CAM, rows, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal);
+  LAUNCH(k_reduce_partials, 1, NT_CAM, rows, 5, (const double*)ctx->part_pm.as<double>(), M, ctx->d_scal, (const LmCtl*)nullptr, (int)GATE_ALWAYS);
   return GLBA_OK;
 }
 
@@ -545,20 +565,18 @@ const int kStepSlots[5] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C};
 int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, double radius, const LmCtl* ctl = nullptr) {
   const int c = ctx->cur;
   if (ctx->use_pipe) {
-    k_lin_pipe<<<pipe_grid(ctx, ctx->occ_lin), P_NT, sizeof(LinSmem), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->pt4[c].as<double4>(),
+    LAUNCH_SMEM(k_lin_pipe, pipe_grid(ctx, ctx->occ_lin), P_NT, sizeof(LinSmem), pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->pt4[c].as<double4>(),
         (const double*)ctx->camtab[c].as<double>(), ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(),
         ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal,
         1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 4, kLinSlots, true, ctl, GATE_ACCEPTED));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
   } else if (ctx->use_tiles) {
     const size_t smem = (size_t)8 * NT_T * ctx->opt * sizeof(double);
     const RedArgs RA = red_args(ctx, 4, kLinSlots, ctx->n_tiles <= kInKernelReduceMaxTiles, ctl, GATE_ACCEPTED);
 #define LIN_TILE_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->pt4[c].as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
     ctx->rec_pm.as<double4>(), ctx->rec_cm.as<double4>(), ctx->Craw.as<double>(), ctx->sp4.as<double4>(), ctx->lam4.as<double4>(), \
     ctx->cinv.as<double>(), ctx->u0p.as<double4>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->part_pm.as<double>(), RA
-    if (ctx->opt == OPT_LARGE) k_linearize_tile<OPT_LARGE><<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(LIN_TILE_ARGS);
-    else k_linearize_tile<OPT_SMALL><<<ctx->n_tiles, NT_T, smem, ctx->stream>>>(LIN_TILE_ARGS);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (ctx->opt == OPT_LARGE) LAUNCH_SMEM(k_linearize_tile<OPT_LARGE>, ctx->n_tiles, NT_T, smem, LIN_TILE_ARGS);
+    else LAUNCH_SMEM(k_linearize_tile<OPT_SMALL>, ctx->n_tiles, NT_T, smem, LIN_TILE_ARGS);
     if (ctx->n_tiles > kInKernelReduceMaxTiles)
       LAUNCH(k_reduce_rows<4>, 64, NT_T, (const double*)ctx->part_pm.as<double>(), ctx->n_tiles, ctx->part_pm2.as<double>(), red_args(ctx, 4, kLinSlots, true, ctl, GATE_ACCEPTED));
   } else {
@@ -574,11 +592,10 @@ int launch_linearize_points(glba_ctx* ctx, const glba_options* o, int first, dou
 void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg, int li) {
   const int c = ctx->cur;
   if (ctx->use_pipe) {
-    k_pt_pipe<0><<<pipe_grid(ctx, ctx->occ_pt0), P_NT, sizeof(PtSmem<0>), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
+    LAUNCH_SMEM(k_pt_pipe<0>, pipe_grid(ctx, ctx->occ_pt0), P_NT, sizeof(PtSmem<0>), pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(),
         (const double4*)ctx->u0p.as<double4>(), ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr,
         (const double*)nullptr, (const double4*)nullptr, 0.0, (double*)nullptr, RedArgs{});
-    g_launches.fetch_add(1, std::memory_order_relaxed);
   } else if (ctx->use_tiles) {
 #define PT0_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
     (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, \
@@ -596,12 +613,11 @@ void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg,
 void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius, const LmCtl* ctl = nullptr, const LmHook* hook = nullptr) {
   const int c = ctx->cur, d = c ^ 1;
   if (ctx->use_pipe) {
-    k_pt_pipe<1><<<pipe_grid(ctx, ctx->occ_pt1), P_NT, sizeof(PtSmem<1>), ctx->stream>>>(pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
+    LAUNCH_SMEM(k_pt_pipe<1>, pipe_grid(ctx, ctx->occ_pt1), P_NT, sizeof(PtSmem<1>), pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(),
         (const double4*)ctx->u0p.as<double4>(), (double4*)nullptr, (const CgState*)nullptr, 0, (const double4*)ctx->pt4[c].as<double4>(),
         ctx->pt4[d].as<double4>(), (const double*)ctx->camtab[d].as<double>(), (const double*)ctx->Craw.as<double>(),
         (const double4*)ctx->lam4.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), red_args(ctx, 5, kStepSlots, true, ctl, GATE_ALWAYS, hook));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
   } else if (ctx->use_tiles) {
     const RedArgs RA = red_args(ctx, 5, kStepSlots, ctx->n_tiles <= kInKernelReduceMaxTiles, ctl, GATE_ALWAYS, hook);
 #define PT1_ARGS pm_args(ctx, o), tile_args(ctx), (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), \
@@ -653,7 +669,7 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   const bool sharded = ctx->world > 1;
   if (n_pt) { const int s__ = launch_linearize_points(ctx, o, first, radius); if (s__) return s__; }
   if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
-                            (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>());
+                            (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>(), (const LmCtl*)nullptr);
   if (with_schur) {
     mark(ctx, PH_SCHUR);
     if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
@@ -779,23 +795,21 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius, const LmCtl* c
   const size_t sm_solve = ((size_t)n * (n | 1) + 2 * (size_t)n) * sizeof(double);
   const int len = (n_cam * (n_cam + 1) / 2) * 36 + n;
   mark(ctx, PH_SCHUR);
-  k_dense_schur<<<ctx->dn_grid, DN_NT, sm_schur, ctx->stream>>>(pm_args(ctx, o), n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(),
+  LAUNCH_SMEM(k_dense_schur, ctx->dn_grid, DN_NT, sm_schur, pm_args(ctx, o), n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(),
       (const double4*)ctx->rec_pm.as<double4>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->dn_ppc,
       ctx->dn_part.as<double>(), ctl);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
 #define DN_RED_ARGS n_cam, (const double*)ctx->dn_part.as<double>(), (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->Bc.as<double>(), \
     (const double*)ctx->gc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->dn_red.as<double>(), ctx->dn_full.as<double>()
   if (ctx->world > 1) {    // sum over this rank's CTAs, all-reduce the pair sums, then assemble
-    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, ctx->dn_grid, DN_RED_ARGS, 0);
+    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, ctx->dn_grid, DN_RED_ARGS, 0, ctl);
     AR(ctx->dn_red.as<double>(), (size_t)len, kNcclSum);
-    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, 0, DN_RED_ARGS, 1);
+    LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, 0, DN_RED_ARGS, 1, ctl);
   } else {
     LAUNCH(k_dense_reduce, cdiv(len * 8, 256), 256, ctx->dn_grid, DN_RED_ARGS, 1, ctl);
   }
   mark(ctx, PH_SOLVE);
-  k_dense_solve<<<1, DN_NS, sm_solve, ctx->stream>>>(n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_full.as<double>(),
+  LAUNCH_SMEM(k_dense_solve, 1, DN_NS, sm_solve, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->dn_full.as<double>(),
       ctx->cg_x.as<double>(), ctx->Md.as<double>(), ctx->rhs.as<double>(), ctx->d_scal, ctl);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   mark(ctx, -1);
   CHECK_LAUNCHES();
   return GLBA_OK;
@@ -832,7 +846,7 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
   if (n_cam) LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
                     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode);
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, (const LmCtl*)nullptr);
   if (n_pt) launch_point_pass1(ctx, o, radius);
   if (ctx->world > 1) AR(ctx->d_scal + S_COST_C, 5, kNcclSum);
   mark(ctx, -1);
@@ -1148,6 +1162,8 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (set_func_attributes(ctx) != GLBA_OK) { delete ctx; return GLBA_E_CUDA; }
   if (const char* e = std::getenv("GLBA_TIMING")) ctx->env_timing = (e[0] == '1');          // diagnostic: phase timings for small problems too
   if (const char* e = std::getenv("GLBA_RELABEL")) ctx->env_relabel = (e[0] != '0');   // diagnostic: GLBA_RELABEL=0 keeps the caller's point order
+  g_pdl_max_grid = 2u * (unsigned)ctx->n_sm;
+  if (const char* e = std::getenv("GLBA_PDL")) { g_pdl = (e[0] != '0'); if (e[0] == '2') g_pdl_max_grid = 0x7fffffffu; }   // diagnostic: 0 = plain launches, 2 = every launch
   if (const char* e = std::getenv("GLBA_HOST_LM")) ctx->env_host_lm = (e[0] == '1');   // diagnostic: host-side accept/reject for small windows
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
@@ -1274,7 +1290,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   };
   if ((st = timed([&] { (void)launch_linearize_points(ctx, opt, 0, radius); }, &out->linearize_pm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-           ctx->part_cm.as<double>()); }, &out->linearize_cm_ms))) return st;
+           ctx->part_cm.as<double>(), (const LmCtl*)nullptr); }, &out->linearize_cm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms))) return st;
   if ((st = timed([&] { launch_point_pass0(ctx, opt, (const CgState*)nullptr, 0); }, &out->spmv_pm_ms))) return st;
@@ -1285,10 +1301,10 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
          (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
          (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode);
+         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, (const LmCtl*)nullptr);
   if ((st = timed([&] { launch_point_pass1(ctx, opt, radius); }, &out->backsub_cost_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_point_damp, cdiv(n_pt, NT_PM), NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
-           (const double4*)ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>()); }, &out->point_damp_ms))) return st;
+           (const double4*)ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), (const LmCtl*)nullptr); }, &out->point_damp_ms))) return st;
   // every camera-sized kernel of one linearise + Schur pass (the scalar reductions now run inside the tile kernels)
   st = timed([&] {
     launch_cam_lin_fin(ctx, opt, 0);

@@ -195,6 +195,7 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
               const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start, const double* __restrict__ part27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
               double* __restrict__ lamc, const int first, const int jacobi, const double min_diag, const double max_diag,
               double* part, unsigned* counter, double* scal, const LmCtl* __restrict__ ctl = nullptr, const LmHook hook = LmHook{}) {
+  pdl_grid_sync();
   __shared__ double sm[2 * NT_C / 32];
   if (ctl_skip(ctl, GATE_ACCEPTED)) return;
   __shared__ double smo[2];
@@ -249,6 +250,7 @@ k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const dou
                 const int* __restrict__ cam_chunk_start, const double* __restrict__ part27,
                 const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
                 double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal) {
+  pdl_grid_sync();
   __shared__ double sm[NT_C / 32];
   __shared__ double smo[1];
   __shared__ double stage[FUSE ? NT_C : 1][27];
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(NT_C)
 k_cg_start(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ Minv, const double* __restrict__ rhs,
            double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double* __restrict__ xtab, CgState* cg,
            const double tol, const int max_iters, double* part, unsigned* counter) {
+  pdl_grid_sync();
   __shared__ double sm[NT_C / 32];
   __shared__ double smo[1];
   const int i = blockIdx.x * NT_C + threadIdx.x;
@@ -350,6 +353,7 @@ k_cg_q(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __re
        const double* __restrict__ lamc, const double inv_radius, const double* __restrict__ yhat, const int* __restrict__ cam_chunk_start,
        const double* __restrict__ part6, const double* __restrict__ p, double* __restrict__ q, const CgState* __restrict__ cg, const int li,
        double* __restrict__ partA) {
+  pdl_grid_sync();
   __shared__ double sm[NT_C / 32];
   __shared__ double smo[1];
   if (cg->done_at <= li) return;
@@ -400,6 +404,7 @@ __device__ __forceinline__ double sum_parts(const double* __restrict__ part, con
 __global__ void __launch_bounds__(NT_C)
 k_cg_xr(const int n_cam, const double* __restrict__ Minv, const double* __restrict__ p, double* __restrict__ q, double* __restrict__ x,
         double* __restrict__ r, const CgState* __restrict__ cg, const int li, const double* __restrict__ partA, double* __restrict__ partB) {
+  pdl_grid_sync();
   __shared__ double sm[NT_C / 32];
   __shared__ double smo[1];
   __shared__ double s_pq;
@@ -430,6 +435,7 @@ k_cg_xr(const int n_cam, const double* __restrict__ Minv, const double* __restri
 __global__ void __launch_bounds__(NT_C)
 k_cg_p(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ z, double* __restrict__ p, double* __restrict__ xtab,
        CgState* cg, const int li, const double* __restrict__ partA, const double* __restrict__ partB) {
+  pdl_grid_sync();
   __shared__ double s_rz, s_pq;
   if (cg->done_at <= li) return;
   const double rz1 = sum_parts(partB, gridDim.x, &s_rz);
@@ -465,6 +471,7 @@ k_cam_step2(const int n_cam, const uint8_t* __restrict__ cam_free, const double*
             const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius_arg,
             double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ xtab, double* part, unsigned* counter, double* scal,
             const int mode, const LmCtl* __restrict__ ctl = nullptr) {
+  pdl_grid_sync();
   __shared__ double sm[3 * NT_C / 32];
   if (ctl_skip(ctl, GATE_ALWAYS)) return;
   const double inv_radius = ctl_inv_radius(ctl, inv_radius_arg);

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(DN_NT)
 k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_free, const double4* __restrict__ rec_pm,
               const double* __restrict__ camtab, const double* __restrict__ cinv, const double4* __restrict__ u0p, const int pts_per_cta,
               double* __restrict__ part /* [grid][n_pairs*36 + 6*n_cam] */, const LmCtl* __restrict__ ctl = nullptr) {
+  pdl_grid_sync();
   extern __shared__ double dsm[];
   if (ctl_skip(ctl, GATE_ALWAYS)) return;
   const int n_pairs = n_cam * (n_cam + 1) / 2;
@@ -153,6 +154,7 @@ __global__ void k_dense_reduce(const int n_parts, const int n_cam, const double*
                                const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc,
                                const double inv_radius_arg, double* __restrict__ Sred /* pair sums (kept for the sharded all-reduce) */,
                                double* __restrict__ Sfull /* n*n + n */, const int assemble, const LmCtl* __restrict__ ctl = nullptr) {
+  pdl_grid_sync();
   if (ctl_skip(ctl, GATE_ALWAYS)) return;
   const double inv_radius = ctl_inv_radius(ctl, inv_radius_arg);
   // 8 lanes per element: lane `sub` sums copies sub, sub+8, ... (8x shorter dependent load chains), the 8 partial sums
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(DN_NS)
 k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ Sfull /* n*n + n, assembled */,
               double* __restrict__ y, double* __restrict__ Md, double* __restrict__ rhs_out, double* __restrict__ scal,
               const LmCtl* __restrict__ ctl = nullptr) {
+  pdl_grid_sync();
   extern __shared__ double dsm[];
   if (ctl_skip(ctl, GATE_ALWAYS)) return;
   const int n = 6 * n_cam;
@@ -350,6 +353,7 @@ k_dense_solve(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
 
 // duplicate (point, camera) observations make two staging threads collide: detect them at load time
 __global__ void k_check_dup(const int n_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, int* flag) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_pt) return;
   const int b = pt_start[j], e = pt_start[j + 1];

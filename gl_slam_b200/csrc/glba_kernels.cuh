@@ -55,6 +55,16 @@ enum Scal {
 };
 constexpr int NSCAL = 40;
 
+// Programmatic dependent launch (sm_90+): every kernel of this library starts with pdl_grid_sync().  launch_dependents lets the
+// NEXT kernel of the stream be scheduled as soon as all CTAs of this one have started (its launch latency hides behind this
+// kernel); wait blocks until every prerequisite grid has completed and its memory is visible, so data dependencies are those of
+// plain stream order.  Every thread executes both before anything else (also before any early exit: a kernel that finished
+// without waiting would release ITS dependents too early).  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct Intr { double fx, fy, cx, cy; };
 
 struct LossP { int kind; double a; };
@@ -379,6 +389,7 @@ __device__ inline void cam_table_row_g2o(const double* cam, double* ct) {
 }
 
 __global__ void k_cam_prep(const int n_cam, const double* __restrict__ cam, double* __restrict__ camtab, const int mode) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cam) return;
   if (mode) cam_table_row_g2o(cam + 6 * i, camtab + (size_t)CAMTAB * i);
@@ -391,6 +402,7 @@ __global__ void k_cam_prep(const int n_cam, const double* __restrict__ cam, doub
 __global__ void k_hmax(const int n_pt, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw, const int n_cam,
                        const uint8_t* __restrict__ cam_free, const double* __restrict__ Bc, const double* __restrict__ camtab,
                        unsigned long long* __restrict__ out) {
+  pdl_grid_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   double m = 0.0;
   if (t < n_pt) {
@@ -454,6 +466,7 @@ k_linearize_pm(const PmArgs A, const double4* __restrict__ pt, const double* __r
                double4* __restrict__ sp4, double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const int first,
                const int jacobi, const double min_diag, const double max_diag, const double inv_radius,
                double* __restrict__ part /* [grid][5] */) {
+  pdl_grid_sync();
   __shared__ double sm[5 * NT_PM / 32];
   __shared__ double smo[5];
   const int j = blockIdx.x * NT_PM + threadIdx.x;
@@ -537,6 +550,7 @@ __global__ void __launch_bounds__(NT_PM)
 k_point_damp(const int n_pt, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw,
              const double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const double inv_radius_arg,
              double* __restrict__ part /* [grid][1] notpd */, const LmCtl* __restrict__ ctl = nullptr) {
+  pdl_grid_sync();
   __shared__ double sm[NT_PM / 32];
   __shared__ double smo[1];
   if (ctl_skip(ctl, GATE_REDAMP)) return;
@@ -578,6 +592,7 @@ struct CmArgs {
 __global__ void __launch_bounds__(NT_HCM, 5)
 k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
                double* __restrict__ part /* [n_chunks][27] */, const LmCtl* __restrict__ ctl = nullptr) {
+  pdl_grid_sync();
   __shared__ double sm[27 * NT_HCM / 32];
   __shared__ double smo[27];
   if (ctl_skip(ctl, GATE_ACCEPTED)) return;
@@ -626,6 +641,7 @@ k_linearize_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double*
 __global__ void __launch_bounds__(NT_HCM, 4)
 k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
            const double* __restrict__ cinv, const double4* __restrict__ u0p, double* __restrict__ part /* [n_chunks][27] */) {
+  pdl_grid_sync();
   __shared__ double sm[27 * NT_HCM / 32];
   __shared__ double smo[27];
   const int ch = blockIdx.x;
@@ -680,6 +696,7 @@ k_schur_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __r
 __global__ void __launch_bounds__(NT_CM)
 k_spmv_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __restrict__ camtab,
           const double4* __restrict__ u4, const CgState* __restrict__ cg, const int li, double* __restrict__ part /* [n_chunks][6] */) {
+  pdl_grid_sync();
   __shared__ double sm[6 * NT_CM / 32];
   __shared__ double smo[6];
   if (cg && cg->done_at <= li) return;
@@ -728,6 +745,7 @@ k_spmv_cm(const CmArgs A, const double4* __restrict__ rec_cm, const double* __re
 template <int NV>
 __global__ void k_chunk_sum(const int n_cam, const int* __restrict__ cam_chunk_start, const double* __restrict__ part,
                             double* __restrict__ acc, const CgState* __restrict__ cg, const int li) {
+  pdl_grid_sync();
   if (cg && cg->done_at <= li) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_cam * NV) return;
@@ -752,6 +770,7 @@ k_point_pass(const PmArgs A, const double4* __restrict__ rec_pm, const double* _
              const double4* __restrict__ pt, double4* __restrict__ pt_c, const double* __restrict__ camtab_c,
              const double* __restrict__ Craw, const double4* __restrict__ lam4, const double inv_radius,
              double* __restrict__ part /* [grid][5] */) {
+  pdl_grid_sync();
   if (MODE == 0 && cg && cg->done_at <= li) return;
   const int j = blockIdx.x * NT_PM + threadIdx.x;
   double cost_c = 0.0, yn2 = 0.0, yg = 0.0, yly = 0.0, bad = 0.0;
@@ -828,6 +847,7 @@ struct ReduceMap { int n; int slot[8]; int is_max[8]; };
 __global__ void __launch_bounds__(NT_CAM)
 k_reduce_partials(const int rows, const int nv, const double* __restrict__ part, const ReduceMap M, double* __restrict__ scal,
                   const LmCtl* __restrict__ ctl = nullptr, const int gate = GATE_ALWAYS) {
+  pdl_grid_sync();
   __shared__ double sm[NT_CAM / 32];
   __shared__ double smo[1];
   if (ctl_skip(ctl, gate)) return;
@@ -851,6 +871,7 @@ k_reduce_partials(const int rows, const int nv, const double* __restrict__ part,
 __global__ void k_chunk_sum_lin(const int n_cam, const int* __restrict__ cam_chunk_start, const double* __restrict__ partA,
                                 const double* __restrict__ partB, double* __restrict__ accA, double* __restrict__ accB,
                                 const int rank, double* __restrict__ scal) {
+  pdl_grid_sync();
   if (blockIdx.x == 0 && threadIdx.x < MAX_WORLD) scal[S_GSLOT0 + threadIdx.x] = ((int)threadIdx.x == rank) ? scal[S_GMAX_P] : 0.0;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = n_cam * 27;
@@ -892,6 +913,7 @@ __global__ void k_expand(const long n_obs, const int* __restrict__ pm_cam, const
                          const int* __restrict__ pm2orig, const double4* __restrict__ rec_pm,
                          const double* __restrict__ camtab, const Intr K, double* __restrict__ res,
                          double* __restrict__ jc, double* __restrict__ jp) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_obs) return;
   const int i = pm_cam[k];
@@ -915,10 +937,12 @@ __global__ void k_expand(const long n_obs, const int* __restrict__ pm_cam, const
 // Index construction helpers
 // ---------------------------------------------------------------------------------------------
 __global__ void k_iota(const long n, int* out) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) out[k] = (int)k;
 }
 __global__ void k_check_sorted(const long n, const int* __restrict__ key, const int n_key, int* flags /* [0]=unsorted, [1]=out of range */) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int v = key[k];
@@ -926,11 +950,13 @@ __global__ void k_check_sorted(const long n, const int* __restrict__ key, const 
   if (k > 0 && key[k - 1] > v) flags[0] = 1;
 }
 __global__ void k_check_range(const long n, const int* __restrict__ key, const int n_key, int* flag) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n && (key[k] < 0 || key[k] >= n_key)) *flag = 1;
 }
 // start[s] = first k with key[k] >= s (key sorted ascending); start[n_seg] = n
 __global__ void k_segment_starts(const long n, const int* __restrict__ key, const int n_seg, int* __restrict__ start) {
+  pdl_grid_sync();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > n_seg) return;
   long lo = 0, hi = n;
@@ -940,6 +966,7 @@ __global__ void k_segment_starts(const long n, const int* __restrict__ key, cons
 __global__ void k_gather_obs(const long n, const int* __restrict__ perm, const int* __restrict__ cam_in, const int* __restrict__ pt_in,
                              const double* __restrict__ u_in, const double* __restrict__ v_in, int* __restrict__ cam_out,
                              int* __restrict__ pt_out, double2* __restrict__ uv_out) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const long o = perm ? perm[k] : k;
@@ -950,6 +977,7 @@ __global__ void k_gather_obs(const long n, const int* __restrict__ perm, const i
 // measurements in both orders, once they have arrived (the upload of u, v overlaps the index construction)
 __global__ void k_gather_uv(const long n, const int* __restrict__ pm2orig, const int* __restrict__ cm2pm, const double* __restrict__ u_in,
                             const double* __restrict__ v_in, double2* __restrict__ pm_uv, double2* __restrict__ cm_uv) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const long o = pm2orig ? pm2orig[k] : k;
@@ -960,6 +988,7 @@ __global__ void k_gather_uv(const long n, const int* __restrict__ pm2orig, const
 }
 __global__ void k_build_cm(const long n, const int* __restrict__ cm2pm, const int* __restrict__ pm_pt, const double2* __restrict__ pm_uv,
                            int* __restrict__ cm_pt, double2* __restrict__ cm_uv, int* __restrict__ pm2cm) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int o = cm2pm[k];
@@ -969,6 +998,7 @@ __global__ void k_build_cm(const long n, const int* __restrict__ cm2pm, const in
 }
 __global__ void k_free_flags(const int n, const int* __restrict__ start, const uint8_t* __restrict__ fixed, const int* __restrict__ new2old,
                              uint8_t* __restrict__ free_out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool seen = start[i + 1] > start[i];
@@ -977,12 +1007,14 @@ __global__ void k_free_flags(const int n, const int* __restrict__ start, const u
 // cnt[i] = local observations of camera i; cnt[n_cam] = local duplicate flag (all-reduced by the host when sharded)
 __global__ void k_counts(const int n_cam, const int* __restrict__ cam_start, const int* __restrict__ dup_flag, const int empty,
                          int* __restrict__ cnt) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_cam) cnt[i] = cam_start[i + 1] - cam_start[i];
   else if (i == n_cam) cnt[i] = (*dup_flag != 0) ? 1 : 0;
   else if (i == n_cam + 1) cnt[i] = empty;
 }
 __global__ void k_free_flags_cnt(const int n, const int* __restrict__ cnt, const uint8_t* __restrict__ fixed, uint8_t* __restrict__ free_out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) free_out[i] = (cnt[i] > 0 && !(fixed && fixed[i])) ? 1 : 0;
 }
@@ -991,12 +1023,14 @@ __global__ void k_free_flags_cnt(const int n, const int* __restrict__ cnt, const
 // .w carries sqrt(information weight) of the point's observations (1 when the caller gives none)
 __global__ void k_pack_pt(const int n, const double* __restrict__ pt3, const double* __restrict__ info, const int* __restrict__ new2old,
                           double4* __restrict__ pt4) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const size_t o = new2old ? new2old[j] : j;
   pt4[j] = make_double4(pt3[3 * o], pt3[3 * o + 1], pt3[3 * o + 2], info ? sqrt(fmax(info[o], 0.0)) : 1.0);
 }
 __global__ void k_unpack_pt(const int n, const double4* __restrict__ pt4, const int* __restrict__ new2old, double* __restrict__ pt3) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const size_t o = new2old ? new2old[j] : j;
@@ -1004,37 +1038,45 @@ __global__ void k_unpack_pt(const int n, const double4* __restrict__ pt4, const 
 }
 // first (smallest) camera index observing each point, from the caller's (possibly unsorted) observation list
 __global__ void k_first_cam(const long n, const int* __restrict__ obs_cam, const int* __restrict__ obs_pt, int* __restrict__ first_cam) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) atomicMin(first_cam + obs_pt[k], obs_cam[k]);
 }
 __global__ void k_fill_int(const int n, int* __restrict__ a, const int v) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
 }
 // number of points whose first camera is smaller than the previous observed point's (0 for creation-ordered ids)
 __global__ void k_count_descents(const int n, const int* __restrict__ first_cam, int* __restrict__ count) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j > 0 && j < n && first_cam[j] < first_cam[j - 1]) atomicAdd(count, 1);
 }
 __global__ void k_invert_perm(const int n, const int* __restrict__ new2old, int* __restrict__ old2new) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) old2new[new2old[j]] = j;
 }
 __global__ void k_relabel(const long n, const int* __restrict__ obs_pt, const int* __restrict__ old2new, int* __restrict__ out) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) out[k] = old2new[obs_pt[k]];
 }
 __global__ void k_scatter_u8(const int n, const uint8_t* __restrict__ in, const int* __restrict__ new2old, uint8_t* __restrict__ out) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) out[new2old ? new2old[j] : j] = in[j];
 }
 __global__ void k_scatter_f64(const int n, const double* __restrict__ in, const int* __restrict__ new2old, double* __restrict__ out) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) out[new2old ? new2old[j] : j] = in[j];
 }
 // Craw SoA (6 C + 3 g) -> explicit 3x3 / gradient in AoS for glba_linearize
 __global__ void k_unpack_pointblocks(const int n, const uint8_t* __restrict__ pt_free, const double* __restrict__ Craw,
                                      const int* __restrict__ new2old, double* __restrict__ hess /* 9 */, double* __restrict__ grad /* 3 */) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const size_t o = new2old ? new2old[j] : j;
@@ -1050,6 +1092,7 @@ __global__ void k_unpack_pointblocks(const int n, const uint8_t* __restrict__ pt
 __global__ void __launch_bounds__(NT_PM)
 k_cull(const PmArgs A, const double4* __restrict__ pt, const double* __restrict__ camtab, const int min_obs,
        const double max_mean_err, uint8_t* __restrict__ bad, double* __restrict__ mean_err) {
+  pdl_grid_sync();
   const int j = blockIdx.x * NT_PM + threadIdx.x;
   if (j >= A.n_pt) return;
   const int b = A.pt_start[j], e = A.pt_start[j + 1];

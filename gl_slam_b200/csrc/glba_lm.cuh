@@ -103,6 +103,7 @@ struct LmHook {
 __global__ void k_accept_copy(const LmCtl* __restrict__ ctl, const int n_cam, const int n_pt, const double* __restrict__ cam_c,
                               const double* __restrict__ camtab_c, const double4* __restrict__ pt_c, double* __restrict__ cam,
                               double* __restrict__ camtab, double4* __restrict__ pt) {
+  pdl_grid_sync();
   if (ctl_skip(ctl, GATE_ACCEPTED)) return;
   const long n1 = 6L * n_cam, n2 = n1 + (long)CAMTAB * n_cam, n3 = n2 + n_pt;
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n3; t += (long)gridDim.x * blockDim.x) {

@@ -19,6 +19,7 @@ namespace {
 
 __global__ void k_map_count(const long n, const int* __restrict__ o_kf, const int* __restrict__ o_pt, const uint8_t* __restrict__ bad,
                             const int first, const int window, int* __restrict__ cnt) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int f = o_kf[k] - first;
@@ -27,11 +28,13 @@ __global__ void k_map_count(const long n, const int* __restrict__ o_kf, const in
   if (!bad[j]) atomicAdd(cnt + j, 1);
 }
 __global__ void k_map_keep(const int n_pt, const int* __restrict__ cnt, const int min_obs, int* __restrict__ keep) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j <= n_pt) keep[j] = (j < n_pt && cnt[j] >= min_obs) ? 1 : 0;       // one past the end: the scan's total
 }
 __global__ void k_map_sel(const long n, const int* __restrict__ o_kf, const int* __restrict__ o_pt, const int* __restrict__ cnt,
                           const int min_obs, const int first, const int window, int* __restrict__ sel) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k > n) return;
   int v = 0;
@@ -41,6 +44,7 @@ __global__ void k_map_sel(const long n, const int* __restrict__ o_kf, const int*
 __global__ void k_map_gather_obs(const long n, const int* __restrict__ o_kf, const int* __restrict__ o_pt, const double2* __restrict__ o_uv,
                                  const int* __restrict__ sel, const int* __restrict__ pos, const int* __restrict__ local, const int first,
                                  int* __restrict__ w_cam, int* __restrict__ w_pt, double* __restrict__ w_u, double* __restrict__ w_v) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n || !sel[k]) return;
   const int d = pos[k];
@@ -49,6 +53,7 @@ __global__ void k_map_gather_obs(const long n, const int* __restrict__ o_kf, con
 }
 __global__ void k_map_gather_pt(const int n_pt, const int* __restrict__ keep, const int* __restrict__ local, const double* __restrict__ pt,
                                 double* __restrict__ w_pt, int* __restrict__ w_id) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_pt || !keep[j]) return;
   const int l = local[j];
@@ -56,6 +61,7 @@ __global__ void k_map_gather_pt(const int n_pt, const int* __restrict__ keep, co
   w_pt[3 * (size_t)l] = pt[3 * (size_t)j]; w_pt[3 * (size_t)l + 1] = pt[3 * (size_t)j + 1]; w_pt[3 * (size_t)l + 2] = pt[3 * (size_t)j + 2];
 }
 __global__ void k_map_scatter_pt(const int n, const int* __restrict__ w_id, const double* __restrict__ w_pt, double* __restrict__ pt) {
+  pdl_grid_sync();
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n) return;
   const size_t j = w_id[l];
@@ -63,19 +69,23 @@ __global__ void k_map_scatter_pt(const int n, const int* __restrict__ w_id, cons
 }
 // culling candidates: non-bad points whose earliest observation lies in keyframes [a, b]
 __global__ void k_map_first_kf(const long n, const int* __restrict__ o_kf, const int* __restrict__ o_pt, int* __restrict__ first) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) atomicMin(first + o_pt[k], o_kf[k]);
 }
 __global__ void k_map_keep_first(const int n_pt, const int* __restrict__ first, const uint8_t* __restrict__ bad, const int a, const int b,
                                  int* __restrict__ keep) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j <= n_pt) keep[j] = (j < n_pt && !bad[j] && first[j] >= a && first[j] <= b) ? 1 : 0;
 }
 __global__ void k_map_sel_kept(const long n, const int* __restrict__ o_pt, const int* __restrict__ keep, int* __restrict__ sel) {
+  pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k <= n) sel[k] = (k < n && keep[o_pt[k]]) ? 1 : 0;
 }
 __global__ void k_map_set_u8(const int n, const int* __restrict__ ids, const uint8_t v, uint8_t* __restrict__ a) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[ids[i]] = v;
 }
@@ -85,6 +95,7 @@ __global__ void k_map_set_u8(const int n, const int* __restrict__ ids, const uin
 // pose the caller saved before the write-back and the pose now in the map.  out[0..8] = dR (row-major), out[9..11] = dt.
 __global__ void k_map_delta(const double* __restrict__ cam, const int kf_last, const double* __restrict__ before /* R[9] t[3] */,
                             double* __restrict__ out) {
+  pdl_grid_sync();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double* c = cam + 6 * (size_t)kf_last;
   double Ra[9];
@@ -94,6 +105,7 @@ __global__ void k_map_delta(const double* __restrict__ cam, const int kf_last, c
 // points X <- dR X + dt (:931-944); keyframes R <- dR R, t <- dR t + dt (:945-968), stored back as (angle-axis, centre)
 __global__ void k_map_apply_delta(const double* __restrict__ d, const int n_kf, const int* __restrict__ kf_ids, double* __restrict__ cam,
                                   const int n_pt, const int* __restrict__ pt_ids, double* __restrict__ pt) {
+  pdl_grid_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n_pt) {
     double* X = pt + 3 * (size_t)pt_ids[t];

@@ -93,6 +93,7 @@ __device__ __forceinline__ void bulk_slice(void* dst, const void* base, const si
 __global__ void __launch_bounds__(NT_T)
 k_tile_meta(const int* __restrict__ tile_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, const int n_cam,
             int4* __restrict__ desc, int* __restrict__ cams /* pre-filled with -1 */, uint8_t* __restrict__ slot) {
+  pdl_grid_sync();
   __shared__ unsigned bm[BM_WORDS];
   __shared__ int pre[BM_WORDS];
   __shared__ int wsum[NT_T / 32];
@@ -231,6 +232,7 @@ k_lin_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ pt, con
            double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const int first, const int jacobi,
            const double min_diag, const double max_diag, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */,
            const RedArgs RA) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) unsigned char dsm_raw[];
   LinSmem& S = *reinterpret_cast<LinSmem*>(dsm_raw);
   if (ctl_skip(RA.ctl, RA.gate)) return;
@@ -431,6 +433,7 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
           // MODE 1 only:
           const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
           const double4* __restrict__ lam4, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) unsigned char dsm_raw[];
   PtSmem<MODE>& S = *reinterpret_cast<PtSmem<MODE>*>(dsm_raw);
   if (MODE == 0 && cg && cg->done_at <= li) return;

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(NT_POSE)
 k_pose_only(const int batch, double* __restrict__ cams, const int* __restrict__ offset, const double* __restrict__ Xall,
             const double* __restrict__ uvall, const Intr K, const PoseOpts O, uint8_t* __restrict__ usable,
             int* __restrict__ n_iters_out, double* __restrict__ final_cost, int* __restrict__ term_out, const PoseTrace tr) {
+  pdl_grid_sync();
   __shared__ double sm[29 * NT_POSE / 32];
   __shared__ double red[32];
   __shared__ double ct[CAMTAB], ctc[CAMTAB];

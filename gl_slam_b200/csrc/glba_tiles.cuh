@@ -77,6 +77,7 @@ struct RedArgs {
 template <int MAXCOL>
 __global__ void __launch_bounds__(NT_T)
 k_reduce_rows(const double* __restrict__ part, const int rows, double* __restrict__ part2 /* [grid][5] */, const RedArgs RA) {
+  pdl_grid_sync();
   __shared__ double sm[5 * NT_T / 32];
   __shared__ double smo[5];
   if (ctl_skip(RA.ctl, RA.gate)) return;
@@ -119,6 +120,7 @@ k_linearize_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ p
                  double4* __restrict__ rec_pm, double4* __restrict__ rec_cm, double* __restrict__ Craw, double4* __restrict__ sp4,
                  double4* __restrict__ lam4, double* __restrict__ cinv, double4* __restrict__ u0p, const int first, const int jacobi, const double min_diag,
                  const double max_diag, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+  pdl_grid_sync();
   constexpr int TILE_OBS = NT_T * OPT;
   extern __shared__ double dsm[];
   if (ctl_skip(RA.ctl, RA.gate)) return;
@@ -257,6 +259,7 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
              // MODE 1 only:
              const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
              const double4* __restrict__ lam4, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+  pdl_grid_sync();
   constexpr int TILE_OBS = NT_T * OPT;
   __shared__ double val[3][TILE_OBS];
   if (MODE == 1 && ctl_skip(RA.ctl, RA.gate)) return;
@@ -397,6 +400,7 @@ k_point_tile(const PmArgs A, const TileArgs T, const double4* __restrict__ rec_p
 // smallest camera index among a tile's observations
 __global__ void __launch_bounds__(NT_T)
 k_tile_cmin(const int* __restrict__ tile_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, int* __restrict__ tile_cmin) {
+  pdl_grid_sync();
   __shared__ int sm[NT_T / 32];
   const int j0 = tile_pt[blockIdx.x], j1 = tile_pt[blockIdx.x + 1];
   const int k0 = pt_start[j0], k1 = pt_start[j1];
@@ -411,6 +415,7 @@ k_tile_cmin(const int* __restrict__ tile_pt, const int* __restrict__ pt_start, c
 
 // ---- load-time helpers ------------------------------------------------------------------------
 __global__ void k_max_track(const int n_pt, const int* __restrict__ pt_start, int* out) {
+  pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   int len = (j < n_pt) ? pt_start[j + 1] - pt_start[j] : 0;
 #pragma unroll
@@ -419,6 +424,7 @@ __global__ void k_max_track(const int n_pt, const int* __restrict__ pt_start, in
 }
 // tile_pt[t] = first point whose first observation index is >= t*B  (t = 0..n_tiles), clamped to n_pt
 __global__ void k_tile_starts(const int n_tiles, const int B, const int n_pt, const int* __restrict__ pt_start, int* __restrict__ tile_pt) {
+  pdl_grid_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
   if (t == n_tiles) { tile_pt[t] = n_pt; return; }

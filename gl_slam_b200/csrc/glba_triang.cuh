@@ -38,6 +38,7 @@ __device__ __forceinline__ bool jacobi_pair(double (&A)[4][4], double (&V)[4][4]
 
 __global__ void k_triangulate(const int n, const TriArgs T, const double* __restrict__ p0, const double* __restrict__ p1,
                               double* __restrict__ X3 /* 3n: X/w */, uint8_t* __restrict__ keep) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double x0 = p0[2 * i], y0 = p0[2 * i + 1], x1 = p1[2 * i], y1 = p1[2 * i + 1];
