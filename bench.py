@@ -4,9 +4,10 @@
 Metric (BASELINE.json): BA observations/s over residual + Jacobian + Schur, and LM iterations/s.
 A *step* is one pass of linearise + Schur (K_A + K_B: residuals, robust weights, Jacobian records,
 Hessian blocks, damped point-block inverses, Schur-complement diagonal and reduced rhs) over the whole
-synthetic map, resident in HBM.  The workload is C4 of BASELINE.md §4 (1 800 cameras, 1 M points,
-~5 M observations): the largest config that names 1/2/4/8 GPUs; with --gpus N its point tracks are
-sharded N ways (strong scaling, one NCCL all-reduce of the camera blocks per pass).
+synthetic map, resident in HBM.  The workload is C4 of BASELINE.md §4 / SURVEY §8d (1 800 cameras on a 60x30 street grid — banded
+covisibility plus revisits —, 1 M points, ~5 M observations): the config BASELINE.json names for 1/2/4/8 GPUs.
+With --gpus N its point tracks are sharded N ways (STRONG scaling, as BASELINE.json states the config: "sharded 2/4/8
+GPUs"); the line also carries weak scaling (N x 30 streets) and, on 8 GPUs, BASELINE config 5 (C5) sharded 8 ways.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C5|C3|C2] [--impl reference]
 
@@ -86,16 +87,22 @@ def build_scene(workload, scale, **kw):
     return scene.config(workload, scale=scale, **kw)
 
 
-def algorithmic_bytes(n_obs, n_pt, n_cam):
-    """Per-launch algorithmic bytes of each hot kernel in THIS layout; every array counted once."""
+def algorithmic_bytes(n_obs, n_pt, n_cam, n_tiles=None):
+    """Per-launch algorithmic bytes of each hot kernel in THIS layout; every array counted once.
+    Large maps run the pipelined tile kernels (glba_pipe.cuh): a 1-byte camera slot per observation replaces the 4-byte
+    camera and point indices, per-tile metadata (descriptor 16 B + camera list 128 B) is counted per tile."""
+    if n_tiles is None:
+        n_tiles = n_obs // 497 + 1
+    meta = 144 * n_tiles
     return {
-        # read cam idx 4 + uv 16 + pm2cm 4; write two 32-B records | per point: read X 32 + CSR 4 + s 32, write C,g 72 + lam 32 + block 96
-        "linearize_pm": 88 * n_obs + 268 * n_pt + 192 * n_cam,
+        # per obs: read uv 16 + pm2cm 4 + slot 1, write two 32-B records | per point: read X 32 + CSR 4 + s 32 + free 1,
+        # write C,g 72 + lam 32 + block 96 | camera rows 96
+        "linearize_pm": 85 * n_obs + 269 * n_pt + 96 * n_cam + meta,
         "linearize_cm": 48 * n_obs + 216 * n_cam,                 # record 32 + uv 16
         "schur_cm": 116 * n_obs + 216 * n_cam,                    # record 32 + pt idx 4 + gathered Cinv,u0 80
-        "spmv_pm": 36 * n_obs + 84 * n_pt + 240 * n_cam,          # record 32 + cam idx 4 | Cinv 48 + CSR 4 + u 32
+        "spmv_pm": 33 * n_obs + 101 * n_pt + 128 * n_cam + meta,  # record 32 + slot 1 | Cinv 64 (two sectors) + CSR 4 + free 1 + u 32 | gather row 128
         "spmv_cm": 68 * n_obs + 48 * n_cam,                       # record 32 + pt idx 4 + gathered u 32
-        "backsub_cost": 56 * n_obs + 252 * n_pt + 432 * n_cam,    # record 32 + cam idx 4 (x2) + uv 16 | block 96, X 32+32, g 24, lam 32 ...
+        "backsub_cost": 49 * n_obs + 221 * n_pt + 224 * n_cam + meta,   # record 32 + uv 16 + slot 1 | block 96, X 32+32, g 24, lam 32, CSR 4, free 1
     }
 
 
@@ -139,7 +146,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="glba", choices=["glba", "reference"])
     ap.add_argument("--workload", default="C4")
@@ -148,9 +155,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lm-iters", type=int, default=6)
     ap.add_argument("--random-point-ids", action="store_true", help="diagnostic: number the map points at random instead of in creation order")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = every GPU owns a workload-sized arc of an N-times larger loop map (default); "
-                         "strong = the fixed workload map sharded N ways")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N>1: strong = the fixed workload map sharded N ways (default: what BASELINE.json's configs 4/5 state); "
+                         "weak = every GPU owns a workload-sized block of an N-times larger map")
+    ap.add_argument("--no-extras", action="store_true", help="N>1: skip the extra scaling measurements (weak scaling, C5 on 8 GPUs) and the sharded parity check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "glba" else args.warmup
     if args.impl == "reference":
@@ -196,51 +204,69 @@ def main():
     ctx = g.Context(device=local, rank=rank, world=world, nccl_id=nccl_id, stream=stream.cuda_stream)
     opt = g.options()                                   # reference settings: Cauchy(1.0), Ceres LM defaults
 
-    # ---- inputs resident in HBM ---------------------------------------------------------------------
-    def dev_t(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    d = {k: dev_t(getattr(prob, k)) for k in ("cam", "pt", "obs_cam", "obs_pt", "obs_u", "obs_v", "cam_fixed")}
-    ps = _abi.Problem()
-    ps.n_cam, ps.n_pt, ps.n_obs = prob.n_cam, prob.n_pt, prob.n_obs
-    ps.cam, ps.pt = d["cam"].data_ptr(), d["pt"].data_ptr()
-    ps.obs_cam, ps.obs_pt, ps.obs_u, ps.obs_v = d["obs_cam"].data_ptr(), d["obs_pt"].data_ptr(), d["obs_u"].data_ptr(), d["obs_v"].data_ptr()
-    ps.cam_fixed, ps.pt_fixed = d["cam_fixed"].data_ptr(), None
-    ps.fx, ps.fy, ps.cx, ps.cy = prob.K
-    ps.memspace = _abi.MEM_DEVICE
-    ctx.load(ps, opt)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- inputs resident in HBM ---------------------------------------------------------------------
+    def load_resident(pr, o):
+        keep = {k: torch.from_numpy(np.ascontiguousarray(getattr(pr, k))).to(dev) for k in ("cam", "pt", "obs_cam", "obs_pt", "obs_u", "obs_v", "cam_fixed")}
+        ps = _abi.Problem()
+        ps.n_cam, ps.n_pt, ps.n_obs = pr.n_cam, pr.n_pt, pr.n_obs
+        ps.cam, ps.pt = keep["cam"].data_ptr(), keep["pt"].data_ptr()
+        ps.obs_cam, ps.obs_pt, ps.obs_u, ps.obs_v = (keep[k].data_ptr() for k in ("obs_cam", "obs_pt", "obs_u", "obs_v"))
+        ps.cam_fixed, ps.pt_fixed = keep["cam_fixed"].data_ptr(), None
+        ps.fx, ps.fy, ps.cx, ps.cy = pr.K
+        ps.memspace = _abi.MEM_DEVICE
+        ctx.load(ps, o)
+        return keep
+
+    def time_steps(o, rad, steps, warmup):
+        """`steps` linearise+Schur passes over the resident map; device time (CUDA events on the context's stream), max over ranks."""
+        with torch.cuda.stream(stream):
+            for _ in range(max(warmup - 1, 0)):
+                ctx.linearize_resident(rad, o, want_cost=False)
+            barrier()
+            if warmup > 0:
+                # the last warm-up step runs after the barrier: ranks leave a host barrier tens of microseconds apart, and the
+                # all-reduce inside this step lines their DEVICE timelines up before the first timed event is recorded
+                ctx.linearize_resident(rad, o, want_cost=False)
+            l0 = g.kernel_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            th0 = time.perf_counter()
+            for _ in range(steps):
+                ctx.linearize_resident(rad, o, want_cost=False)
+            enq = (time.perf_counter() - th0) * 1e3 / steps      # host time to enqueue one step (no sync inside)
+            e1.record(stream)
+            barrier()
+            nl = g.kernel_launch_count() - l0
+            ms_ = e0.elapsed_time(e1)
+        t_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item()) / steps, nl, enq
+
+    # ---- N > 1, before anything is timed: sharded solves against the single-GPU solve and the CPU oracle ----------
+    sharded_parity = None
+    if world > 1 and not args.no_extras:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("mgpu_check", os.path.join(ROOT, "tools", "mgpu_check.py"))
+        mg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mg)
+        ok, cases = mg.run_cases(ctx, rank, world, local, dev)
+        sharded_parity = {"ok": bool(ok), "world": world, "cases": cases,
+                          "gate": "sharded solve vs the CPU oracle on the whole map: same iteration count, per-iteration cost 1e-9, cameras 1e-6, "
+                                  "points 1e-6; cameras bit-identical on every rank; gradient norms agree with the single-GPU solve"}
+
+    keep = load_resident(prob, opt)
     radius = opt.initial_radius
-    with torch.cuda.stream(stream):
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()             # before the barrier: starting the sampler costs rank 0 milliseconds the others would wait for
-        for _ in range(max(args.warmup - 1, 0)):
-            ctx.linearize_resident(radius, opt, want_cost=False)
-        barrier()
-        if args.warmup > 0:
-            # the last warm-up step runs after the barrier: ranks leave a host barrier tens of microseconds apart, and the
-            # all-reduce inside this step lines their DEVICE timelines up before the first timed event is recorded
-            ctx.linearize_resident(radius, opt, want_cost=False)
-        launches0 = g.kernel_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        th0 = time.perf_counter()
-        for _ in range(args.steps):
-            ctx.linearize_resident(radius, opt, want_cost=False)
-        host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # host time to enqueue one step (no sync inside)
-        e1.record(stream)
-        barrier()
-        launches = g.kernel_launch_count() - launches0
-        ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()             # before the first barrier: starting the sampler costs rank 0 milliseconds the others would wait for
+    ms_step, launches, host_enqueue_ms = time_steps(opt, radius, args.steps, args.warmup)
+    launches = launches
     value = n_obs_total / (ms_step * 1e-3)
     cost = ctx.linearize_resident(radius, opt, want_cost=True)
     clocks = sampler.stop() if rank == 0 else None
@@ -257,10 +283,15 @@ def main():
             kernels[name] = {"ms": kt[key], "algorithmic_bytes": ab[name], "gbs": gbs, "frac": gbs / peak}
     step_kernels = ["linearize_pm", "linearize_cm", "schur_cm"]
     dom = max(step_kernels, key=lambda k: kernels.get(k, {"ms": 0})["ms"]) if kernels else None
-    ncu_traffic = None
+    # kernel that actually runs for each roofline key (large maps: the pipelined tile kernels of glba_pipe.cuh)
+    KNAME = {"linearize_pm": "k_lin_pipe", "linearize_cm": "k_linearize_cm", "schur_cm": "k_schur_cm", "spmv_pm": "k_pt_pipe<0>",
+             "spmv_cm": "k_spmv_cm", "backsub_cost": "k_pt_pipe<1>"}
+    if prob.n_obs < 400000:
+        KNAME.update(linearize_pm="k_linearize_tile<1>", spmv_pm="k_point_tile<0,1>", backsub_cost="k_point_tile<1,1>")
+    ncu_traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            ncu_traffic = json.load(f).get(dom)
+            ncu_traffic = json.load(f).get(KNAME.get(dom))
     except Exception:
         pass
     kernels["small_kernels"] = {"ms": kt["small_kernels_ms"]}
@@ -269,7 +300,7 @@ def main():
         kernels["chunk_sum"] = {"ms": kt["chunk_sum_ms"]}
     roofline = None
     if dom:
-        roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+        roofline = {"kernel": KNAME[dom], "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": ncu_traffic, "peak_kind": peak_kind,
                     "step_bytes": sum(ab[k] for k in step_kernels),
                     "step_frac_of_peak": sum(ab[k] for k in step_kernels) / (ms_step * 1e-3) / 1e9 / peak,
@@ -298,6 +329,40 @@ def main():
               "device_ms": {k: s[k] for k in ("t_linearize_ms", "t_schur_ms", "t_solve_ms", "t_update_ms", "t_comm_ms")},
               "linearizations": s["n_linearizations"]}
         ctx.reset_resident()
+        if world == 1:
+            # the same iterations with the reduced system solved to parity precision (PCG 1e-13, no iteration cap)
+            popt = g.options(max_iters=min(args.lm_iters, 3), function_tol=0.0, parameter_tol=0.0, gradient_tol=0.0, cg_rel_tol=1e-13)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sp_ = ctx.solve_resident(popt)
+            torch.cuda.synchronize()
+            wp = time.perf_counter() - t0
+            lm["parity_mode"] = {"lm_iters_per_s": sp_["n_iters"] / wp, "iters": sp_["n_iters"], "cg_iters": sp_["cg_iters"][1:sp_["n_iters"] + 1],
+                                 "wall_s": wp, "mode": "PCG rel tol 1e-13 (the mode the parity tests run)"}
+            ctx.reset_resident()
+
+    # ---- N > 1: the other scaling measurements the round-1 review asked for, in the same run ------------------------
+    extras = None
+    if world > 1 and not args.no_extras and args.workload.upper() == "C4" and args.scaling == "strong":
+        extras = {}
+        def measure(pr, n_total, steps, o):
+            load_resident(pr, o)
+            ms_, _, _ = time_steps(o, o.initial_radius, steps, 3)
+            return {"value": n_total / (ms_ * 1e-3), "unit": UNIT, "ms_per_step": ms_, "n_obs": n_total}
+        pw = scene.config_weak("C4", world, rank, args.scale)
+        tot_w = torch.tensor([pw.n_obs], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot_w)
+        extras["weak_C4"] = dict(measure(pw, int(tot_w[0]), max(10, args.steps // 2), opt), n_cam=pw.n_cam,
+                                 workload=f"C4 x{world}: {pw.n_cam // 60} streets of 60 keyframes, every GPU owns the points of its own block of streets")
+        del pw
+        if world == 8 and args.scale == 1.0:
+            full5 = scene.config("C5")
+            p5 = scene.shard_by_point(full5, world, rank)[0]
+            o5 = g.options(loss=g.LOSS_HUBER)
+            extras["strong_C5"] = dict(measure(p5, full5.n_obs, max(10, args.steps // 4), o5), n_cam=full5.n_cam,
+                                       workload="C5 (10 000 cameras, 4 M points, 30 M observations, Huber, 10 % outliers) sharded 8 ways")
+            del full5, p5
+        keep = load_resident(prob, opt)          # back to the primary workload for the legs below
 
     # ---- e2e: the C-ABI call a GL-SLAM host makes, HOST buffers, copies inside the timed region ---------------
     e2e = None
@@ -336,6 +401,16 @@ def main():
                "call": "glba_linearize(host problem) -> cost, grad_cam, hess_cam, schur_diag, schur_rhs", "steps": k_e2e,
                "cost_matches_resident": bool(abs(ls.cost - cost) <= 1e-12 * abs(cost))}
         if world == 1:
+            # the API unit of the reference is a SOLVE (full_ba -> ceres::Solve): glba_solve from the same host arrays, upload,
+            # index build, LM iterations (the bench's inexact-Newton mode) and the refined state back on the host
+            sopt = g.options(max_iters=max(1, args.lm_iters), function_tol=0.0, parameter_tol=0.0, gradient_tol=0.0, cg_rel_tol=1e-2, cg_max_iters=40)
+            ctx2.solve(prob, sopt)
+            t0 = time.perf_counter()
+            _, ss = ctx2.solve(prob, sopt)
+            dts = time.perf_counter() - t0
+            e2e["solve"] = {"call": "glba_solve(host problem) -> refined cameras and points on the host", "wall_ms": dts * 1e3, "lm_iters": ss["n_iters"],
+                            "obs_x_iters_per_s": prob.n_obs * ss["n_iters"] / dts, "h2d_bytes": h2d, "d2h_bytes": 48 * prob.n_cam + 24 * prob.n_pt,
+                            "setup_ms": ss["t_setup_ms"], "cost": [ss["initial_cost"], ss["final_cost"]]}
             ctx2.close()
 
     # ---- the regime GL-SLAM actually runs: local-BA window C2 (host call, exact dense reduced solve) and pose-only BA ----
@@ -431,11 +506,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload if not weak else f"{args.workload} x{world} (every GPU owns a {args.workload}-sized arc of a {world}x larger loop map)", "n_cam": n_cam, "n_pt": n_pt_total, "n_obs": n_obs_total, "loss": "cauchy(1.0)",
+            "config": {"workload": args.workload if not weak else f"{args.workload} x{world} (every GPU owns a {args.workload}-sized block of a {world}x larger map)", "n_cam": n_cam, "n_pt": n_pt_total, "n_obs": n_obs_total, "loss": "cauchy(1.0)",
                        "sharding": f"point tracks over {world} GPU(s), cameras replicated", "l2": "inputs larger than L2 (no flush needed)"
                        if 116 * n_obs_total / world > 126e6 else "working set fits L2: latency-bound config",
                        "step": "linearise (residual, weight, Jacobian records, Hessian blocks) + Schur (point inverses, S diagonal, reduced rhs)"},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "lm": lm, "window": window,
+            "sharded_parity": sharded_parity, "scaling_extras": extras,
             "cost_at_initial_point": cost,
         }
         sys.stdout.flush()

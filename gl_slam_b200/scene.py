@@ -148,6 +148,130 @@ def make_scene(n_cam, n_pt, track_len, seed, *, step=0.8, yaw_per_frame=np.deg2r
     return prob
 
 
+def make_street_grid(n_rows, n_cols, n_pt, track_len, seed, *, step=0.8, gap=7.5, revisit_frac=0.35, depth=(10.0, 40.0), pixel_sigma=0.5,
+                     outlier_frac=0.0, outlier_px=(10.0, 50.0), rot_sigma=0.002, pos_sigma=0.03, pt_sigma=0.10, n_fixed=2, K=KITTI_K,
+                     min_parallax_deg=1.0, shard=0, row_range=None, return_gt=False):
+    """SURVEY §8d's C4: cameras on an n_rows x n_cols STREET GRID driven in serpentine order (row r is a street along +Z
+    at X = r * gap; even rows are driven towards +Z, odd rows back towards -Z, so keyframe ids run 0 .. n_rows*n_cols-1
+    along the path).  Covisibility is banded (consecutive keyframes of a street see a point ahead of them) PLUS revisits:
+    a fraction `revisit_frac` of the points lies between two neighbouring streets and is also seen, from the other side,
+    by keyframes of the next street — ids ~2*(n_cols - c) apart, so its track is a run of consecutive cameras plus a
+    second run far away in id: loop-closure structure in every tile of the map.
+    Every observation is inside the 1241 x 376 image with depth in `depth` by construction.  Point ids are in creation
+    order (sorted by first-observing keyframe, as GL-SLAM numbers map points).  row_range=(r0, r1) restricts the POINTS
+    to primary streets r0 <= r < r1 (weak-scaling shards); cameras are always the whole grid."""
+    rng_cam = np.random.default_rng([seed, 0])
+    rng = np.random.default_rng([seed, 1, shard])
+    fx, fy, cx, cy = K
+    n_cam = n_rows * n_cols
+    r_idx = np.repeat(np.arange(n_rows), n_cols)
+    c_idx = np.tile(np.arange(n_cols), n_rows)
+    sgn = np.where(r_idx % 2 == 0, 1.0, -1.0)                               # driving / viewing direction along Z
+    z_cam = np.where(r_idx % 2 == 0, c_idx, n_cols - 1 - c_idx) * step
+    cam_gt = np.zeros((n_cam, 6))
+    cam_gt[:, 1] = np.where(r_idx % 2 == 0, 0.0, np.pi - 1e-3) + rng_cam.normal(0.0, 0.01, n_cam)      # yaw about +Y
+    cam_gt[:, 3] = r_idx * gap
+    cam_gt[:, 5] = z_cam
+    tl = np.asarray(track_len(rng, n_pt), dtype=np.int64) if callable(track_len) else np.full(n_pt, int(track_len), dtype=np.int64)
+    tl = np.clip(tl, 2, 2 * n_cols)
+    r_lo, r_hi = (0, n_rows) if row_range is None else row_range
+    # per point: primary street, second street (revisit), run lengths, position; redraw what does not fit
+    r0 = np.zeros(n_pt, np.int64); r1 = np.zeros(n_pt, np.int64)
+    l1 = np.zeros(n_pt, np.int64); l2 = np.zeros(n_pt, np.int64)
+    c1 = np.zeros(n_pt, np.int64); c2 = np.zeros(n_pt, np.int64)            # first column (in id order) of each run
+    X = np.zeros((n_pt, 3))
+    todo = np.arange(n_pt)
+    cos_min = np.cos(np.deg2rad(min_parallax_deg))
+    d_near = (0.6 * depth[0], depth[0])                                      # closest allowed depth: one-street points / revisited points
+    d_far = (0.625 * depth[1], 0.75 * depth[1])
+    for _round in range(200):
+        m = todo.shape[0]
+        if m == 0:
+            break
+        pr = rng.integers(r_lo, r_hi, size=m)
+        rev = (rng.random(m) < revisit_frac) & (n_rows > 1)
+        nb = np.where(pr + 1 < n_rows, pr + 1, pr - 1)                      # the neighbouring street that revisits
+        dmin = np.where(rev, d_near[1], d_near[0]); dmax = np.where(rev, d_far[1], d_far[0])
+        slots = ((dmax - dmin) / step).astype(np.int64)
+        a = np.where(rev, np.maximum(1, tl[todo] // 2), tl[todo])
+        b = np.where(rev, tl[todo] - a, 0)
+        a = np.minimum(a, np.minimum(slots, max(1, n_cols - 3))); b = np.minimum(b, np.minimum(slots, max(1, n_cols - 3)))
+        s0 = np.where(pr % 2 == 0, 1.0, -1.0)
+        zp = rng.uniform(-0.7 * d_far[0], (n_cols - 1) * step + 0.7 * d_far[0], size=m)      # beyond the street ends too: every keyframe sees points
+        # street pr (viewing direction s0) sees the point from Z_cam = zp - s0 * d; the neighbour (direction -s0) from
+        # Z_cam = zp + s0 * d'.  Runs are consecutive grid positions.
+        d_last = dmin + rng.random(m) * np.maximum((slots - a) * step, 0.0)  # depth of the primary run's LAST (closest) camera
+        k_last = np.round((zp - s0 * d_last) / step).astype(np.int64)        # its grid slot along Z
+        k_first = k_last - (s0 * (a - 1)).astype(np.int64)                   # farthest camera (driven earlier)
+        ok = (np.minimum(k_first, k_last) >= 0) & (np.maximum(k_first, k_last) <= n_cols - 1)
+        zp = k_last * step + s0 * d_last                                     # snap the point: depths are exact
+        d2_near = dmin + rng.random(m) * np.maximum((slots - b) * step, 0.0)
+        k2_near = np.round((zp + s0 * d2_near) / step).astype(np.int64)      # neighbour run: closest camera ...
+        k2_far = k2_near + (s0 * (b - 1)).astype(np.int64)                   # ... and farthest (driven first on that street)
+        d2 = s0 * (k2_near * step - zp)
+        ok &= ~rev | ((np.minimum(k2_far, k2_near) >= 0) & (np.maximum(k2_far, k2_near) <= n_cols - 1) &
+                      (d2 >= dmin - 1e-9) & (d2 + (b - 1) * step <= dmax + 1e-9))
+        # lateral position: between the two streets for revisited points, else a fraction of the closest depth to either side
+        side = np.where(nb > pr, 1.0, -1.0)
+        ratio = rng.uniform(0.15, 0.72, size=m) * np.where(rng.random(m) < 0.5, 1.0, -1.0)
+        xp = np.where(rev, pr * gap + side * gap * rng.uniform(0.3, 0.7, size=m), pr * gap + ratio * d_last)
+        yp = rng.uniform(-0.22, 0.2, size=m) * np.where(rev, np.minimum(d_last, d2), d_last)
+        # parallax between the first and the last camera of the track (forward motion towards a point near the axis has none)
+        col_first = np.where(pr % 2 == 0, k_first, n_cols - 1 - k_first)
+        col_last = np.where(pr % 2 == 0, k_last, n_cols - 1 - k_last)
+        col2_near = np.where(nb % 2 == 0, k2_near, n_cols - 1 - k2_near)
+        col2_far = np.where(nb % 2 == 0, k2_far, n_cols - 1 - k2_far)
+        i_first = pr * n_cols + np.clip(col_first, 0, n_cols - 1)
+        i_last = np.where(rev, nb * n_cols + np.clip(col2_near, 0, n_cols - 1), pr * n_cols + np.clip(col_last, 0, n_cols - 1))
+        P = np.stack([xp, yp, zp], axis=1)
+        ra = P - cam_gt[i_first, 3:6]
+        rb = P - cam_gt[i_last, 3:6]
+        cosang = (ra * rb).sum(1) / (np.linalg.norm(ra, axis=1) * np.linalg.norm(rb, axis=1))
+        ok &= cosang <= cos_min
+        good = todo[ok]
+        r0[good] = pr[ok]; r1[good] = nb[ok]; l1[good] = a[ok]; l2[good] = b[ok]
+        c1[good] = np.minimum(col_first, col_last)[ok]
+        c2[good] = np.minimum(col2_far, col2_near)[ok]
+        X[good] = P[ok]
+        todo = todo[~ok]
+    if todo.shape[0]:
+        raise RuntimeError("street grid: could not place %d points" % todo.shape[0])
+    tl = l1 + l2
+    # creation order: ids sorted by the first-observing keyframe
+    first_cam = np.minimum(r0 * n_cols + c1, np.where(l2 > 0, r1 * n_cols + c2, n_cam))
+    order0 = np.argsort(first_cam, kind="stable")
+    r0, r1, l1, l2, c1, c2, X, tl = r0[order0], r1[order0], l1[order0], l2[order0], c1[order0], c2[order0], X[order0], tl[order0]
+    n_obs = int(tl.sum())
+    obs_pt = np.repeat(np.arange(n_pt, dtype=np.int64), tl)
+    first = np.cumsum(tl) - tl
+    within = np.arange(n_obs, dtype=np.int64) - np.repeat(first, tl)
+    in_first = within < np.repeat(l1, tl)
+    obs_cam = np.where(in_first, np.repeat(r0 * n_cols + c1, tl) + within, np.repeat(r1 * n_cols + c2, tl) + within - np.repeat(l1, tl))
+    order = np.lexsort((obs_cam, obs_pt))
+    obs_cam, obs_pt = obs_cam[order], obs_pt[order]
+    u, v, dep = project(cam_gt, X, obs_cam, obs_pt, K)
+    assert dep.min() > 1.0 and u.min() > -20 and u.max() < IMG_W + 20 and v.min() > -20 and v.max() < IMG_H + 20, \
+        (dep.min(), u.min(), u.max(), v.min(), v.max())
+    u = u + rng.normal(0.0, pixel_sigma, size=n_obs)
+    v = v + rng.normal(0.0, pixel_sigma, size=n_obs)
+    if outlier_frac > 0:
+        bad = rng.random(n_obs) < outlier_frac
+        mag = rng.uniform(outlier_px[0], outlier_px[1], size=n_obs)
+        ang = rng.uniform(0, 2 * np.pi, size=n_obs)
+        u = np.where(bad, u + mag * np.cos(ang), u)
+        v = np.where(bad, v + mag * np.sin(ang), v)
+    cam0 = cam_gt.copy()
+    cam0[n_fixed:, :3] += rng_cam.normal(0.0, rot_sigma, size=(n_cam - n_fixed, 3))
+    cam0[n_fixed:, 3:] += rng_cam.normal(0.0, pos_sigma, size=(n_cam - n_fixed, 3))
+    pt0 = X + rng.normal(0.0, pt_sigma, size=(n_pt, 3))
+    cam_fixed = np.zeros(n_cam, dtype=np.uint8)
+    cam_fixed[:n_fixed] = 1
+    prob = HostProblem(cam0, pt0, obs_cam.astype(np.int32), obs_pt.astype(np.int32), u, v, K, cam_fixed, None)
+    if return_gt:
+        return prob, cam_gt, X
+    return prob
+
+
 def _poisson_tracks(base, lam):
     return lambda rng, n: base + rng.poisson(lam, size=n)
 
@@ -165,7 +289,13 @@ def config(name, scale=1.0, **overrides):
     elif name == "C3":    # 200 frames, 200 k points, mean track 5 -> 1 M observations (as one problem)
         kw = dict(n_cam=200, n_pt=max(64, int(200000 * s)), track_len=_poisson_tracks(2, 3.0), seed=3,
                   rot_sigma=0.005, pos_sigma=0.05, pt_sigma=0.10)
-    elif name == "C4":    # 1 800 cameras on a closed loop, 1 M points, ~5 M observations
+    elif name == "C4":    # 1 800 cameras on a 60 x 30 street grid (banded covisibility + revisits), 1 M points, ~5 M observations
+        rows = max(2, int(round(30 * min(1.0, s * 4))))
+        kw = dict(n_rows=rows, n_cols=60, n_pt=max(64, int(1000000 * s)), track_len=_poisson_tracks(2, 3.0), seed=4,
+                  rot_sigma=0.002, pos_sigma=0.03, pt_sigma=0.10)
+        kw.update(overrides)
+        return make_street_grid(**kw)
+    elif name == "C4LOOP":    # round-1 stand-in for C4: 1 800 cameras on ONE closed loop (perfectly banded covisibility)
         kw = dict(n_cam=max(8, int(1800 * min(1.0, s * 4))), n_pt=max(64, int(1000000 * s)),
                   track_len=_poisson_tracks(2, 3.0), seed=4, loop=True, rot_sigma=0.002, pos_sigma=0.03, pt_sigma=0.10)
     elif name == "C5":    # 10 k cameras, 4 M points, ~30 M observations, 10 % outliers, Huber
@@ -185,6 +315,11 @@ def config_weak(name, world, rank, scale=1.0):
     name = name.upper()
     if name not in ("C4", "C5"):
         raise KeyError("weak scaling is defined for the loop maps C4 / C5")
+    if name == "C4":      # N x 30 streets of 60 keyframes; rank r owns the points whose primary street lies in its block of 30
+        rows1 = max(2, int(round(30 * min(1.0, scale * 4))))
+        return make_street_grid(n_rows=rows1 * world, n_cols=60, n_pt=max(64, int(1000000 * scale)), track_len=_poisson_tracks(2, 3.0), seed=4,
+                                rot_sigma=0.002, pos_sigma=0.03, pt_sigma=0.10, shard=rank,
+                                row_range=(rank * rows1, (rank + 1) * rows1) if world > 1 else None)
     base = dict(C4=(1800, 1000000, 3.0, 4, 0.0), C5=(10000, 4000000, 5.5, 5, 0.10))[name]
     n_cam1 = max(8, int(base[0] * min(1.0, scale * 4)))
     n_pt1 = max(64, int(base[1] * scale))
