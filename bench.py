@@ -296,7 +296,8 @@ def main():
         pass
     kernels["small_kernels"] = {"ms": kt["small_kernels_ms"]}
     if world > 1:
-        kernels["allreduce"] = {"ms": kt["allreduce_ms"], "bytes": 8 * (54 * prob.n_cam + 20)}
+        kernels["allreduce"] = {"ms": kt["allreduce_ms"], "bytes": kt["exchange_bytes"], "cameras_on_this_rank": kt["n_local_cams"],
+                                "cameras_exchanged": kt["n_shared_cams"], "layout": "owner-computes: only cameras observed by >= 2 ranks are exchanged"}
         kernels["chunk_sum"] = {"ms": kt["chunk_sum_ms"]}
     roofline = None
     if dom:
@@ -404,10 +405,18 @@ def main():
             # the API unit of the reference is a SOLVE (full_ba -> ceres::Solve): glba_solve from the same host arrays, upload,
             # index build, LM iterations (the bench's inexact-Newton mode) and the refined state back on the host
             sopt = g.options(max_iters=max(1, args.lm_iters), function_tol=0.0, parameter_tol=0.0, gradient_tol=0.0, cg_rel_tol=1e-2, cg_max_iters=40)
-            ctx2.solve(prob, sopt)
-            t0 = time.perf_counter()
-            _, ss = ctx2.solve(prob, sopt)
-            dts = time.perf_counter() - t0
+            cam_in, pt_in = host["cam"].clone(), host["pt"].clone()          # glba_solve refines cam / pt in place: restore them per call
+            summ = _abi.Summary()
+            def solve_once():
+                host["cam"].copy_(cam_in); host["pt"].copy_(pt_in)
+                t0_ = time.perf_counter()
+                st_ = g.lib().glba_solve(ctx2._h, C.byref(hs), C.byref(sopt), C.byref(summ))
+                assert st_ == 0, st_
+                return time.perf_counter() - t0_
+            solve_once()
+            dts = min(solve_once() for _ in range(2))
+            ss = summ.as_dict()
+            host["cam"].copy_(cam_in); host["pt"].copy_(pt_in)
             e2e["solve"] = {"call": "glba_solve(host problem) -> refined cameras and points on the host", "wall_ms": dts * 1e3, "lm_iters": ss["n_iters"],
                             "obs_x_iters_per_s": prob.n_obs * ss["n_iters"] / dts, "h2d_bytes": h2d, "d2h_bytes": 48 * prob.n_cam + 24 * prob.n_pt,
                             "setup_ms": ss["t_setup_ms"], "cost": [ss["initial_cost"], ss["final_cost"]]}

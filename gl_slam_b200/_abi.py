@@ -84,7 +84,8 @@ class Linearization(C.Structure):
 
 class KernelTimes(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("linearize_pm_ms", "linearize_cm_ms", "schur_cm_ms", "spmv_pm_ms", "spmv_cm_ms",
-                                          "backsub_cost_ms", "point_damp_ms", "small_kernels_ms", "allreduce_ms", "chunk_sum_ms")]
+                                          "backsub_cost_ms", "point_damp_ms", "small_kernels_ms", "allreduce_ms", "chunk_sum_ms",
+                                          "exchange_bytes")] + [("n_local_cams", C.c_int32), ("n_shared_cams", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
 #include "glba_kernels.cuh"
@@ -38,7 +39,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 }
 namespace {
-constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclSum = 0, kNcclMax = 2;   // ncclDataType_t / ncclRedOp_t values
+constexpr int kNcclFloat64 = 8, kNcclInt32 = 2, kNcclInt64 = 4, kNcclSum = 0, kNcclMax = 2;   // ncclDataType_t / ncclRedOp_t values
 struct NcclApi {
   void* h = nullptr;
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -111,6 +112,10 @@ struct glba_ctx {
   Buf hmax;                                   // GLBA_MODE_G2O: max Hessian diagonal (bit pattern of a double)
   Buf tile_cmin, tile_pt, xtab, partA, partB, partc, counters, cam_cnt, part_cm2, part_pm2;                                  // tiles, PCG gather table, camera-kernel partials
   bool use_tiles = false;
+  // sharded runs, "owner-computes" layout (see load_problem): this rank's problem holds only the cameras its own tracks observe
+  bool owner = false, want_owner = false;
+  int n_cam_g = 0, n_shared = 0, n_free_cam_g = 0;            // cameras of the whole map; cameras observed by more than one rank
+  Buf act_mask, g2l, l2g, cam_owned, cam_shared, sh_scan, xsend, xrecv, ocam_loc, cam_loc, cfix_loc, late;
   Buf lmctl, dsum;              // device-resident LM control (LmCtl) and summary trace (glba_summary) of the on-device loop
   bool env_host_lm = false;     // diagnostic: GLBA_HOST_LM=1 keeps the decisions on the host for small windows too
   bool use_pipe = false;        // large maps: persistent TMA-fed tile kernels (glba_pipe.cuh)
@@ -285,9 +290,11 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   ctx->loaded = false;
   ctx->ev_used = 0;
   mark(ctx, PH_SETUP);
-  const int n_cam = p->n_cam, n_pt = p->n_pt;
+  int n_cam = p->n_cam;
+  const int n_pt = p->n_pt;
   const long n = p->n_obs;
-  ctx->n_cam = n_cam; ctx->n_pt = n_pt; ctx->n_obs = n;
+  ctx->n_cam = n_cam; ctx->n_cam_g = n_cam; ctx->n_pt = n_pt; ctx->n_obs = n;
+  ctx->owner = false; ctx->n_shared = 0;
   ctx->K = Intr{p->fx, p->fy, p->cx, p->cy};
   cudaStream_t s = ctx->stream;
   const double *d_cam, *d_pt, *d_u, *d_v;
@@ -345,6 +352,54 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   CU(cudaStreamSynchronize(s));
   if (ctx->h_flags[1] || ctx->h_flags[2]) return fail(ctx, GLBA_E_INVALID_ARG, "observation index out of range");
   ctx->sorted_input = (ctx->h_flags[0] == 0);
+  // ---- sharded maps, "owner-computes" layout ---------------------------------------------------------------------------
+  // Round 1 replicated every camera-sized array on every rank and all-reduced all cameras' partial sums (6.2 MB per step at
+  // 8 x 1 800 cameras, of which a rank touched 1 800).  Here a rank's problem holds only the cameras ITS tracks observe
+  // (local camera ids), so every camera kernel and vector is local-sized.  Cameras observed by several ranks ("shared":
+  // shard boundaries, revisited streets, loop closures) have their partial sums exchanged through a compact buffer — one
+  // all-reduce per linearisation and one per PCG iteration, of n_shared rows —; every scalar counts a camera once, on its
+  // OWNER (the lowest rank that observes it).  Executable specification: tests/test_owner_computes_spec.py.
+  if (ctx->world > 1 && ctx->want_owner) {
+    const int n_cam_g = n_cam;
+    ENSURE(int, ctx->act_mask, (size_t)n_cam_g + 1); ENSURE(int, ctx->g2l, 2 * ((size_t)n_cam_g + 1)); ENSURE(int, ctx->sh_scan, 2 * ((size_t)n_cam_g + 1));
+    CU(cudaMemsetAsync(ctx->act_mask.p, 0, sizeof(int) * ((size_t)n_cam_g + 1), s));
+    if (n > 0) LAUNCH(k_act_mask, gb, 256, n, d_ocam, 1 << ctx->rank, ctx->act_mask.as<int>());
+    { int s__ = allreduce(ctx, ctx->act_mask.p, (size_t)n_cam_g, kNcclSum, kNcclInt32); if (s__) return s__; }
+    int* f_act = ctx->g2l.as<int>() + n_cam_g + 1;        // flags; the scans land in g2l[0..n_cam_g] / sh_scan[0..n_cam_g]
+    int* f_sh = ctx->sh_scan.as<int>() + n_cam_g + 1;
+    LAUNCH(k_own_flags, cdiv(n_cam_g + 1, 256), 256, n_cam_g, (const int*)ctx->act_mask.as<int>(), ctx->rank, f_act, f_sh);
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, f_act, ctx->g2l.as<int>(), n_cam_g + 1, s));
+    ENSURE(char, ctx->sort_tmp, tb);
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tb, f_act, ctx->g2l.as<int>(), n_cam_g + 1, s));
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tb, f_sh, ctx->sh_scan.as<int>(), n_cam_g + 1, s));
+    g_launches.fetch_add(2);
+    CU(cudaMemcpyAsync(ctx->h_flags, ctx->g2l.as<int>() + n_cam_g, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->h_flags + 1, ctx->sh_scan.as<int>() + n_cam_g, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const int n_act = ctx->h_flags[0];
+    ctx->n_shared = ctx->h_flags[1];
+    ENSURE(int, ctx->l2g, n_act); ENSURE(uint8_t, ctx->cam_owned, n_act); ENSURE(int, ctx->cam_shared, n_act);
+    ENSURE(int, ctx->ocam_loc, n); ENSURE(double, ctx->cam_loc, 6 * (size_t)n_act); ENSURE(uint8_t, ctx->cfix_loc, n_act);
+    if (staged) CU(cudaStreamWaitEvent(s, ctx->ev_copy[1], 0));      // camera parameters and fixed flags have arrived
+    CU(cudaMemsetAsync(ctx->flags.as<int>() + 7, 0, sizeof(int), s));
+    LAUNCH(k_own_build, cdiv(n_cam_g, 256), 256, n_cam_g, (const int*)ctx->act_mask.as<int>(), ctx->rank, (const int*)ctx->g2l.as<int>(),
+           (const int*)ctx->sh_scan.as<int>(), d_cfix, ctx->l2g.as<int>(), ctx->cam_owned.as<uint8_t>(), ctx->cam_shared.as<int>(), ctx->flags.as<int>() + 7);
+    // free cameras of the WHOLE map (every rank needs the same number: iteration caps, "nothing free")
+    { int s__ = allreduce(ctx, ctx->flags.as<int>() + 7, 1, kNcclSum, kNcclInt32); if (s__) return s__; }
+    CU(cudaMemcpyAsync(ctx->h_flags + 7, ctx->flags.as<int>() + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (n > 0) LAUNCH(k_relabel_cam, gb, 256, n, d_ocam, (const int*)ctx->g2l.as<int>(), ctx->ocam_loc.as<int>());
+    if (n_act) LAUNCH(k_gather_cam, cdiv(n_act, 256), 256, n_act, (const int*)ctx->l2g.as<int>(), d_cam, d_cfix, ctx->cam_loc.as<double>(), ctx->cfix_loc.as<uint8_t>());
+    CU(cudaStreamSynchronize(s));
+    ctx->n_free_cam_g = ctx->h_flags[7];
+    d_ocam = ctx->ocam_loc.as<int>(); d_cam = ctx->cam_loc.as<double>(); d_cfix = ctx->cfix_loc.as<uint8_t>();
+    n_cam = n_act; ctx->n_cam = n_act; ctx->owner = true;
+    const size_t xlen = 54 * (size_t)ctx->n_shared + NSCAL + 8;
+    ENSURE(double, ctx->xsend, xlen); ENSURE(double, ctx->xrecv, xlen); ENSURE(double, ctx->late, 2 * NLATE);
+    CU(cudaMemsetAsync(ctx->xsend.p, 0, sizeof(double) * xlen, s));     // rows of cameras this rank does not observe stay zero for good
+  }
   // ---- locality relabelling: the tile kernels stage a narrow window of cameras per tile and the camera-major gathers
   // want neighbouring observations to touch neighbouring points, both of which hold when point ids are ordered by their
   // first-observing camera (how GL-SLAM numbers map points).  If the caller's numbering is not like that (measured: 13 %
@@ -413,7 +468,12 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   if (n > 0 && n_cam <= DN_MAXCAM)
     LAUNCH(k_check_dup, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->flags.as<int>() + 3);
   LAUNCH(k_counts, cdiv(n_cam + 2, 256), 256, n_cam, (const int*)ctx->cam_start.as<int>(), (const int*)ctx->flags.as<int>() + 3, n > 0 ? 0 : 1, ctx->cam_cnt.as<int>());
-  if (ctx->world > 1) { int s__ = allreduce(ctx, ctx->cam_cnt.p, (size_t)n_cam + 2, kNcclSum, kNcclInt32); if (s__) return s__; }
+  if (ctx->world > 1) {
+    // owner layout: every local camera is observed here, only the duplicate / empty-shard flags are global
+    int s__ = ctx->owner ? allreduce(ctx, ctx->cam_cnt.as<int>() + n_cam, 2, kNcclSum, kNcclInt32)
+                         : allreduce(ctx, ctx->cam_cnt.p, (size_t)n_cam + 2, kNcclSum, kNcclInt32);
+    if (s__) return s__;
+  }
   if (staged) CU(cudaStreamWaitEvent(s, ctx->ev_copy[1], 0));   // cam_fixed / pt_fixed / cam / pt have arrived
   if (n_cam) LAUNCH(k_free_flags_cnt, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_cnt.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
   if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, n2o, ctx->pt_free.as<uint8_t>());
@@ -462,6 +522,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
     for (int b = h_start[i]; b < h_start[i + 1]; b += chunk) { cc.push_back(i); cb.push_back(b); ce.push_back(std::min(h_start[i + 1], b + chunk)); }
   }
   ccs[n_cam] = (int)cc.size();
+  if (ctx->owner) ctx->n_free_cam = ctx->n_free_cam_g;      // the same on every rank
   ctx->n_chunks = (int)cc.size();
   ENSURE(int, ctx->chunk_cam, cc.size()); ENSURE(int, ctx->chunk_begin, cc.size()); ENSURE(int, ctx->chunk_end, cc.size());
   ENSURE(int, ctx->cam_chunk_start, ccs.size());
@@ -641,7 +702,7 @@ void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius, con
 #define CAM_LIN_FIN_ARGS n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(), \
     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), \
     ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(), ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, \
-    o->max_lm_diagonal, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->d_scal, ctl, hk
+    o->max_lm_diagonal, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->d_scal, ctl, hk, ctx->owner ? (const uint8_t*)ctx->cam_owned.as<uint8_t>() : (const uint8_t*)nullptr
 void launch_cam_lin_fin(glba_ctx* ctx, const glba_options* o, int first, const LmCtl* ctl = nullptr, const LmHook* hook = nullptr) {
   const LmHook hk = hook ? *hook : LmHook{};
   const int c = ctx->cur, n_cam = ctx->n_cam;
@@ -651,7 +712,7 @@ void launch_cam_lin_fin(glba_ctx* ctx, const glba_options* o, int first, const L
 #define CAM_SCHUR_FIN_ARGS n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accB, \
     (const int*)ctx->cam_chunk_start.as<int>(), (const double*)part27, (const double*)ctx->Bc.as<double>(), (const double*)ctx->gc.as<double>(), \
     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(), ctx->rhs.as<double>(), ctx->partc.as<double>(), \
-    ctx->counters.as<unsigned>() + 1, ctx->d_scal
+    ctx->counters.as<unsigned>() + 1, ctx->d_scal, ctx->owner ? (const uint8_t*)ctx->cam_owned.as<uint8_t>() : (const uint8_t*)nullptr
 void launch_cam_schur_fin(glba_ctx* ctx, double radius, const double* part27) {
   const int c = ctx->cur, n_cam = ctx->n_cam;
   if (ctx->world > 1) LAUNCH(k_cam_schur_fin<false>, ctx->grid_c, NT_C, CAM_SCHUR_FIN_ARGS);
@@ -680,7 +741,18 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
     LAUNCH(k_chunk_sum_lin, cdiv((long)n_cam * (with_schur ? 54 : 27), 256) + (n_cam ? 0 : 1), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
            (const double*)ctx->part_cm.as<double>(), with_schur ? (const double*)ctx->part_cm2.as<double>() : (const double*)nullptr,
            ctx->d_accA, ctx->d_accB, ctx->rank, ctx->d_scal);
-    if (with_schur) AR(ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
+    if (ctx->owner) {
+      // compact exchange: the rows of the cameras several ranks observe + the point scalars, nothing else crosses NVLink
+      const int n_tail = S_GSLOT0 + MAX_WORLD;
+      const int gx = std::max(1, cdiv((long)n_cam * 54, 256));
+      LAUNCH(k_xch_pack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->d_accA,
+             with_schur ? (const double*)ctx->d_accB : (const double*)nullptr, ctx->n_shared, ctx->xsend.as<double>(), (const double*)ctx->d_scal, n_tail);
+      const int r = g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 54 * (size_t)ctx->n_shared + n_tail, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+      if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (linearise): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+      LAUNCH(k_xch_unpack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ctx->n_shared, ctx->d_accA,
+             with_schur ? ctx->d_accB : (double*)nullptr, ctx->d_scal, n_tail);
+    }
+    else if (with_schur) AR(ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     mark(ctx, with_schur ? PH_SCHUR : PH_LIN);
   }
@@ -719,7 +791,16 @@ int do_schur(glba_ctx* ctx, double radius) {
   if (ctx->world > 1) {
     LAUNCH(k_chunk_sum<27>, cdiv((long)n_cam * 27, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(),
            (const double*)ctx->part_cm2.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
-    AR(ctx->d_accB, 27 * (size_t)n_cam, kNcclSum);
+    if (ctx->owner) {
+      // same compact buffer as a linearisation (the A half travels too: it is unchanged and lands where it came from)
+      const int gx = std::max(1, cdiv((long)n_cam * 54, 256));
+      LAUNCH(k_xch_pack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->d_accA, (const double*)ctx->d_accB, ctx->n_shared,
+             ctx->xsend.as<double>(), (const double*)ctx->d_scal, 0);
+      const int r = g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 54 * (size_t)ctx->n_shared, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+      if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (Schur): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+      LAUNCH(k_xch_unpack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ctx->n_shared, (double*)nullptr,
+             ctx->d_accB, ctx->d_scal, 0);
+    } else AR(ctx->d_accB, 27 * (size_t)n_cam, kNcclSum);
   }
   if (n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
   ctx->schur_fresh = true;
@@ -728,30 +809,30 @@ int do_schur(glba_ctx* ctx, double radius) {
   return GLBA_OK;
 }
 
+// vectors of the single-reduction PCG (glba_cam.cuh): x = cg_x, r = cg_r, u = M^-1 r = cg_q, p = cg_p, s = S p = pg, w = S u = yg
 int launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, CgState* cg, int li) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
   launch_point_pass0(ctx, o, cg, li);
   LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
          (const double4*)ctx->u4.as<double4>(), (const CgState*)cg, li, ctx->part_cm.as<double>());
-  if (ctx->world > 1) {
-    LAUNCH(k_chunk_sum<6>, cdiv((long)n_cam * 6, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
-           ctx->yhat.as<double>(), (const CgState*)cg, li);
-    AR(ctx->yhat.as<double>(), 6 * (size_t)n_cam, kNcclSum);
-    LAUNCH(k_cg_q<false>, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->Bc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const double*)ctx->yhat.as<double>(),
-           (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), (const double*)ctx->cg_p.as<double>(),
-           ctx->cg_q.as<double>(), (const CgState*)cg, li, ctx->partA.as<double>());
+#define CG_W_ARGS n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Bc.as<double>(), \
+    (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), \
+    (const double*)ctx->cg_r.as<double>(), (const double*)ctx->cg_q.as<double>(), ctx->yg.as<double>(), cg, li
+#define CG_UPD_ARGS n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(), ctx->cg_q.as<double>(), ctx->yg.as<double>(), \
+    ctx->cg_p.as<double>(), ctx->pg.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->xtab.as<double>(), cg, li
+  if (ctx->owner) {
+    const int ns = ctx->n_shared;
+    LAUNCH(k_cg_w<true>, ctx->grid_c, NT_C, CG_W_ARGS, (const uint8_t*)ctx->cam_owned.as<uint8_t>(), (const int*)ctx->cam_shared.as<int>(),
+           ctx->xsend.as<double>(), ns, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
+    const int r = g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 6 * (size_t)ns + 2, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (PCG): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    LAUNCH(k_cg_update<true>, ctx->grid_c, NT_C, CG_UPD_ARGS, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ns);
   } else {
-    LAUNCH(k_cg_q<true>, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(),
-           (const double*)ctx->Bc.as<double>(), (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const double*)ctx->yhat.as<double>(),
-           (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), (const double*)ctx->cg_p.as<double>(),
-           ctx->cg_q.as<double>(), (const CgState*)cg, li, ctx->partA.as<double>());
+    LAUNCH(k_cg_w<false>, ctx->grid_c, NT_C, CG_W_ARGS, (const uint8_t*)nullptr, (const int*)nullptr, (double*)nullptr, 0,
+           ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
+    LAUNCH(k_cg_update<false>, ctx->grid_c, NT_C, CG_UPD_ARGS, (const int*)nullptr, (const double*)nullptr, 0);
   }
-  LAUNCH(k_cg_xr, ctx->grid_c, NT_C, n_cam, (const double*)ctx->Minv.as<double>(), (const double*)ctx->cg_p.as<double>(), ctx->cg_q.as<double>(),
-         ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), (const CgState*)cg, li, (const double*)ctx->partA.as<double>(), ctx->partB.as<double>());
-  LAUNCH(k_cg_p, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
-         ctx->xtab.as<double>(), cg, li, (const double*)ctx->partA.as<double>(), (const double*)ctx->partB.as<double>());
   return GLBA_OK;
 }
 
@@ -766,20 +847,23 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
     mark(ctx, -1);
     return GLBA_OK;
   }
+  if (ctx->world > 1 && !ctx->owner)
+    return fail(ctx, GLBA_E_UNSUPPORTED, "sharded PCG needs the owner-computes layout (load the problem with linsolve = PCG or > %d cameras)", DN_MAXCAM);
   const int dim = 6 * ctx->n_free_cam;
   const int max_it = o->cg_max_iters > 0 ? o->cg_max_iters : std::min(4000, 4 * dim);
   CgState* cg = ctx->cgst.as<CgState>();
   LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
-         (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->xtab.as<double>(), cg,
-         o->cg_rel_tol, max_it, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
+         (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
+         ctx->pg.as<double>(), ctx->xtab.as<double>(), cg, o->cg_rel_tol, max_it);
   const int poll = 8;
   int launched = 0;
+  // the stop test lags one product behind the update (single-reduction recurrence): max_it updates need max_it + 1 launches
   for (;;) {
-    for (int b = 0; b < poll && launched < max_it; ++b, ++launched) { const int s__ = launch_cg_iteration(ctx, o, radius, cg, launched); if (s__) return s__; }
+    for (int b = 0; b < poll && launched < max_it + 1; ++b, ++launched) { const int s__ = launch_cg_iteration(ctx, o, radius, cg, launched); if (s__) return s__; }
     CHECK_LAUNCHES();
     CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_cg->done_at <= launched || launched >= max_it) break;
+    if (ctx->h_cg->done_at <= launched || launched >= max_it + 1) break;
   }
   *iters = ctx->h_cg->iters;
   mark(ctx, -1);
@@ -816,6 +900,7 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius, const LmCtl* c
 }
 
 bool want_dense(const glba_ctx* ctx, const glba_options* o) {
+  if (ctx->owner) return false;          // owner-computes layout (sharded, PCG): n_cam is this rank's share, every rank must decide alike
   if (ctx->n_free_cam == 0 || ctx->n_cam > DN_MAXCAM || ctx->has_dup) return false;
   if (o->linsolve == GLBA_LINSOLVE_PCG) return false;
   if (o->linsolve == GLBA_LINSOLVE_DENSE) return true;
@@ -827,12 +912,29 @@ bool want_dense(const glba_ctx* ctx, const glba_options* o) {
 // gradient-tolerance decision (a rank leaving the loop alone would hang the others in their next collective).
 int read_scalars(glba_ctx* ctx) {
   CHECK_LAUNCHES();
+  double h_late[NLATE];
+  if (ctx->owner) {
+    // owner layout: the camera-derived scalars are per-rank partial sums (a camera counts on its owner) and the candidate-step
+    // sums cover this rank's points only: one small all-reduce completes both, out of place (the partials stay partial)
+    double* ls = ctx->late.as<double>();
+    LAUNCH(k_late_pack, 1, 32, (const double*)ctx->d_scal, ctx->rank, ls);
+    const int r = g_nccl.AllReduce(ls, ls + NLATE, (size_t)NLATE, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (scalars): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    CU(cudaMemcpyAsync(h_late, ls + NLATE, sizeof(h_late), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (ctx->world > 1) {
     double m = 0.0;
     for (int r = 0; r < ctx->world; ++r) m = std::max(m, ctx->h_scal[S_GSLOT0 + r]);
     ctx->h_scal[S_GMAX_P] = m;
+  }
+  if (ctx->owner) {
+    const int dst[10] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C, S_XN2_C, S_YN2_C, S_YG_C, S_YLY_C, S_NOTPD_C};
+    for (int q = 0; q < 10; ++q) ctx->h_scal[dst[q]] = h_late[q];
+    double m = 0.0;
+    for (int r = 0; r < ctx->world; ++r) m = std::max(m, h_late[10 + r]);
+    ctx->h_scal[S_GMAX_C] = m;
   }
   collect(ctx);
   return GLBA_OK;
@@ -846,9 +948,9 @@ int do_step(glba_ctx* ctx, const glba_options* o, double radius) {
   if (n_cam) LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
                     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, (const LmCtl*)nullptr);
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, (const LmCtl*)nullptr, ctx->owner ? (const uint8_t*)ctx->cam_owned.as<uint8_t>() : (const uint8_t*)nullptr);
   if (n_pt) launch_point_pass1(ctx, o, radius);
-  if (ctx->world > 1) AR(ctx->d_scal + S_COST_C, 5, kNcclSum);
+  if (ctx->world > 1 && !ctx->owner) AR(ctx->d_scal + S_COST_C, 5, kNcclSum);       // owner layout: read_scalars exchanges them
   mark(ctx, -1);
   return read_scalars(ctx);
 }
@@ -873,7 +975,7 @@ int enqueue_lm_iteration(glba_ctx* ctx, const glba_options* o, const LmCtl* ctl,
   if (n_cam) LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
                     (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
                     (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, ctl);
+                    ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, ctl, ctx->owner ? (const uint8_t*)ctx->cam_owned.as<uint8_t>() : (const uint8_t*)nullptr);
   LmHook hook; hook.ctl = ctx->lmctl.as<LmCtl>(); hook.sum = ctx->dsum.as<glba_summary>(); hook.P = P;
   if (n_pt) launch_point_pass1(ctx, o, radius, ctl, &hook);      // its last CTA takes the accept / reject decision (lm_decide)
   // accepted: candidate -> current, re-linearise (all three exit at once otherwise)
@@ -1075,20 +1177,42 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   return GLBA_OK;
 }
 
+// owner layout: every camera of the whole map from its owner rank (bit patterns summed as integers: x + 0 = x exactly)
+int gather_cameras(glba_ctx* ctx, const double* cam_local, Buf& out) {
+  ENSURE(double, out, 6 * (size_t)ctx->n_cam_g);
+  CU(cudaMemsetAsync(out.p, 0, sizeof(double) * 6 * (size_t)ctx->n_cam_g, ctx->stream));
+  if (ctx->n_cam) LAUNCH(k_scatter_rows, cdiv((long)ctx->n_cam * 6, 256), 256, ctx->n_cam, (const int*)ctx->l2g.as<int>(),
+                         (const uint8_t*)ctx->cam_owned.as<uint8_t>(), 1, cam_local, 6, out.as<double>());
+  return allreduce(ctx, out.p, 6 * (size_t)ctx->n_cam_g, kNcclSum, kNcclInt64);
+}
+
 int write_back(glba_ctx* ctx, double* cam, double* pt, int memspace) {
   const int c = ctx->cur;
   cudaStream_t s = ctx->stream;
+  const double* cam_src = ctx->cam[c].as<double>();
+  if (ctx->owner && cam) {
+    const int st = gather_cameras(ctx, cam_src, ctx->out_c);
+    if (st) return st;
+    cam_src = ctx->out_c.as<double>();
+  }
+  const size_t n_cam_out = ctx->owner ? (size_t)ctx->n_cam_g : (size_t)ctx->n_cam;
   if (memspace == GLBA_MEM_HOST) {
     ENSURE(double, ctx->out_a, 3 * (size_t)ctx->n_pt);
     if (ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), ctx->relabelled ? (const int*)ctx->new2old.as<int>() : nullptr, ctx->out_a.as<double>());
-    if (cam) CU(cudaMemcpyAsync(cam, ctx->cam[c].p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToHost, s));
+    if (cam) CU(cudaMemcpyAsync(cam, cam_src, sizeof(double) * 6 * n_cam_out, cudaMemcpyDeviceToHost, s));
     if (pt) CU(cudaMemcpyAsync(pt, ctx->out_a.p, sizeof(double) * 3 * ctx->n_pt, cudaMemcpyDeviceToHost, s));
   } else {
-    if (cam) CU(cudaMemcpyAsync(cam, ctx->cam[c].p, sizeof(double) * 6 * ctx->n_cam, cudaMemcpyDeviceToDevice, s));
+    if (cam) CU(cudaMemcpyAsync(cam, cam_src, sizeof(double) * 6 * n_cam_out, cudaMemcpyDeviceToDevice, s));
     if (pt && ctx->n_pt) LAUNCH(k_unpack_pt, cdiv(ctx->n_pt, 256), 256, ctx->n_pt, (const double4*)ctx->pt4[c].as<double4>(), ctx->relabelled ? (const int*)ctx->new2old.as<int>() : nullptr, pt);
   }
   CU(cudaStreamSynchronize(s));
   return GLBA_OK;
+}
+
+// Sharded maps that will be solved by PCG (more cameras than the dense path takes, or PCG requested) use the owner-computes
+// layout; small sharded windows keep the replicated layout of the exact dense solve.  Every rank decides alike.
+bool wants_owner_layout(const glba_ctx* ctx, const glba_problem* p, const glba_options* o) {
+  return ctx->world > 1 && p && (p->n_cam > DN_MAXCAM || o->linsolve == GLBA_LINSOLVE_PCG);
 }
 
 PoseOpts pose_opts(const glba_options* o) {
@@ -1193,7 +1317,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->cinv, &ctx->u0p, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1220,6 +1344,7 @@ int glba_load(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt) 
   if (st) return st;
   ctx->t_phase[PH_SETUP] = 0.0;
   ctx->mode = opt->mode;
+  ctx->want_owner = wants_owner_layout(ctx, prob, opt);
   st = load_problem(ctx, prob);
   if (st) return st;
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1271,8 +1396,8 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   if ((st = do_linearize_schur(ctx, opt, 1, radius))) return st;
   CgState* cg = ctx->cgst.as<CgState>();
   LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
-         (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_p.as<double>(), ctx->xtab.as<double>(), cg,
-         0.0, 1 << 30, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
+         (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
+         ctx->pg.as<double>(), ctx->xtab.as<double>(), cg, 0.0, 1 << 30);
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->ev_used = 0;
   EventPair ev;
@@ -1301,7 +1426,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   LAUNCH(k_cam_step2, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
          (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cg_x.as<double>(), (const double*)ctx->gc.as<double>(),
          (const double*)ctx->lamc.as<double>(), 1.0 / radius, ctx->cam[d].as<double>(), ctx->camtab[d].as<double>(), ctx->xtab.as<double>(),
-         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, (const LmCtl*)nullptr);
+         ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 3, ctx->d_scal, ctx->mode, (const LmCtl*)nullptr, ctx->owner ? (const uint8_t*)ctx->cam_owned.as<uint8_t>() : (const uint8_t*)nullptr);
   if ((st = timed([&] { launch_point_pass1(ctx, opt, radius); }, &out->backsub_cost_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_point_damp, cdiv(n_pt, NT_PM), NT_PM, n_pt, (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const double*)ctx->Craw.as<double>(),
            (const double4*)ctx->lam4.as<double4>(), ctx->cinv.as<double>(), ctx->u0p.as<double4>(), 1.0 / radius, ctx->part_pm.as<double>(), (const LmCtl*)nullptr); }, &out->point_damp_ms))) return st;
@@ -1311,7 +1436,19 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
     launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>()); }, &out->small_kernels_ms);
   if (st || ctx->world == 1) return st;
   // collective: every rank calls glba_time_kernels with the same reps
-  if ((st = timed([&] { (void)allreduce(ctx, ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum); }, &out->allreduce_ms))) return st;
+  out->n_local_cams = n_cam; out->n_shared_cams = ctx->owner ? ctx->n_shared : ctx->n_cam;
+  out->exchange_bytes = 8.0 * ((ctx->owner ? 54.0 * ctx->n_shared : 54.0 * n_cam) + S_GSLOT0 + MAX_WORLD);
+  if (ctx->owner) {
+    const int n_tail = S_GSLOT0 + MAX_WORLD;
+    const int gx = std::max(1, cdiv((long)n_cam * 54, 256));
+    st = timed([&] {
+      LAUNCH(k_xch_pack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->d_accA, (const double*)ctx->d_accB, ctx->n_shared,
+             ctx->xsend.as<double>(), (const double*)ctx->d_scal, n_tail);
+      (void)g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 54 * (size_t)ctx->n_shared + n_tail, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+      LAUNCH(k_xch_unpack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ctx->n_shared, ctx->d_accA,
+             ctx->d_accB, ctx->d_scal, n_tail); }, &out->allreduce_ms);
+    if (st) return st;
+  } else if ((st = timed([&] { (void)allreduce(ctx, ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum); }, &out->allreduce_ms))) return st;
   st = timed([&] {
     LAUNCH(k_chunk_sum_lin, cdiv((long)n_cam * 54, 256), 256, n_cam, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(),
            (const double*)ctx->part_cm2.as<double>(), ctx->d_accA, ctx->d_accB, ctx->rank, ctx->d_scal); }, &out->chunk_sum_ms);
@@ -1337,6 +1474,7 @@ int glba_solve(glba_ctx* ctx, const glba_problem* prob, const glba_options* opt,
   if (st) { summary->status = st; return st; }
   ctx->t_phase[PH_SETUP] = 0.0;
   ctx->mode = opt->mode;
+  ctx->want_owner = wants_owner_layout(ctx, prob, opt);
   st = load_problem(ctx, prob);
   if (st) { summary->status = st; return st; }
   st = run_lm(ctx, opt, summary);
@@ -1356,6 +1494,7 @@ int glba_linearize(glba_ctx* ctx, const glba_problem* prob, const glba_options* 
   if (st) return st;
   if (opt->mode != GLBA_MODE_CERES) return fail(ctx, GLBA_E_UNSUPPORTED, "glba_linearize reports blocks in the CERES formulation only");
   ctx->mode = GLBA_MODE_CERES;
+  ctx->want_owner = wants_owner_layout(ctx, prob, opt);
   if ((st = load_problem(ctx, prob))) return st;
   for (int q = 0; q < PH_COUNT; ++q) ctx->t_phase[q] = 0.0;
   if ((st = do_linearize_schur(ctx, opt, 1, radius))) return st;
@@ -1383,7 +1522,23 @@ int glba_linearize(glba_ctx* ctx, const glba_problem* prob, const glba_options* 
     if (out->grad_pt) CU(cudaMemcpyAsync(out->grad_pt, ctx->out_c.p, sizeof(double) * 3 * n_pt, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
   }
-  if (n_cam > 0) {
+  if (ctx->owner) {
+    // owner layout: the caller's per-camera arrays cover the whole map; this rank fills the rows of the cameras it observes
+    // (complete values: shared cameras were exchanged), the others are zero
+    const int ng = ctx->n_cam_g;
+    struct { double* host; const Buf* src; int width; } outs[4] = {{out->grad_cam, &ctx->gc, 6}, {out->hess_cam, &ctx->Bc, 36},
+                                                                  {out->schur_diag, &ctx->Md, 36}, {out->schur_rhs, &ctx->rhs, 6}};
+    for (auto& o4 : outs) {
+      if (!o4.host) continue;
+      ENSURE(double, ctx->out_b, (size_t)o4.width * ng);
+      CU(cudaMemsetAsync(ctx->out_b.p, 0, sizeof(double) * (size_t)o4.width * ng, s));
+      const bool have = (o4.width == 6 && o4.src == &ctx->gc) || (o4.src == &ctx->Bc) || ctx->n_free_cam > 0;
+      if (n_cam && have) LAUNCH(k_scatter_rows, cdiv((long)n_cam * o4.width, 256), 256, n_cam, (const int*)ctx->l2g.as<int>(),
+                                (const uint8_t*)ctx->cam_owned.as<uint8_t>(), 0, (const double*)o4.src->as<double>(), o4.width, ctx->out_b.as<double>());
+      CU(cudaMemcpyAsync(o4.host, ctx->out_b.p, sizeof(double) * (size_t)o4.width * ng, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+    }
+  } else if (n_cam > 0) {
     if (out->grad_cam) CU(cudaMemcpyAsync(out->grad_cam, ctx->gc.p, sizeof(double) * 6 * n_cam, cudaMemcpyDeviceToHost, s));
     if (out->hess_cam) CU(cudaMemcpyAsync(out->hess_cam, ctx->Bc.p, sizeof(double) * 36 * n_cam, cudaMemcpyDeviceToHost, s));
     if (ctx->n_free_cam > 0) {
@@ -1488,6 +1643,7 @@ int glba_cull_points(glba_ctx* ctx, const glba_problem* prob, int32_t min_obs, d
   if (!ctx || !bad) return GLBA_E_INVALID_ARG;
   CU(cudaSetDevice(ctx->device));
   ctx->mode = GLBA_MODE_CERES;
+  ctx->want_owner = false;
   ctx->allow_relabel = false;            // one pass over the tracks: renumbering would cost more than it saves
   int st = load_problem(ctx, prob);
   ctx->allow_relabel = true;

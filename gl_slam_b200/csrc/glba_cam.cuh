@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(NT_C)
 k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
               const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start, const double* __restrict__ part27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
               double* __restrict__ lamc, const int first, const int jacobi, const double min_diag, const double max_diag,
-              double* part, unsigned* counter, double* scal, const LmCtl* __restrict__ ctl = nullptr, const LmHook hook = LmHook{}) {
+              double* part, unsigned* counter, double* scal, const LmCtl* __restrict__ ctl = nullptr, const LmHook hook = LmHook{},
+              const uint8_t* __restrict__ owned = nullptr /* sharded: scalars count a camera on its owner rank only */) {
   pdl_grid_sync();
   __shared__ double sm[2 * NT_C / 32];
   if (ctl_skip(ctl, GATE_ACCEPTED)) return;
@@ -222,16 +223,17 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
 #pragma unroll
       for (int q = 0; q < 6; ++q) gh[q] = a[21 + q];
       apply_Tt(ct, gh, g6);
+      const bool mine = owned == nullptr || owned[i] != 0;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         gc[6 * i + r] = g6[r];
-        gmax = fmax(gmax, fabs(g6[r]));
+        if (mine) gmax = fmax(gmax, fabs(g6[r]));
         const double h = Bl[r * 7];
         double sv;
         if (first) { sv = jacobi ? 1.0 / (1.0 + sqrt(h)) : 1.0; sc[6 * i + r] = sv; } else sv = sc[6 * i + r];
         const double s2 = sv * sv;
         lamc[6 * i + r] = fmin(fmax(s2 * h, min_diag), max_diag) / s2;
-        xn2 += cam[6 * i + r] * cam[6 * i + r];
+        if (mine) xn2 += cam[6 * i + r] * cam[6 * i + r];
       }
     }
   }
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(NT_C)
 k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ acc27,
                 const int* __restrict__ cam_chunk_start, const double* __restrict__ part27,
                 const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
-                double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal) {
+                double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal,
+                const uint8_t* __restrict__ owned = nullptr) {
   pdl_grid_sync();
   __shared__ double sm[NT_C / 32];
   __shared__ double smo[1];
@@ -282,7 +285,7 @@ k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const dou
 #pragma unroll
       for (int q = 0; q < 36; ++q) M[q] = Ml[q];
       if (!inv6_spd_reg(Ml, Il)) {
-        notpd = 1.0;
+        if (owned == nullptr || owned[i] != 0) notpd = 1.0;
 #pragma unroll
         for (int q = 0; q < 36; ++q) Il[q] = 0.0;
       }
@@ -311,157 +314,167 @@ __device__ __forceinline__ void write_xtab(double* __restrict__ xr, const double
   xr[15] = (ct[CT_SV] != 0.0 || ct[CT_SV + 1] != 0.0 || ct[CT_SV + 2] != 0.0) ? 1.0 : 0.0;
 }
 
-// PCG start: x = 0, r = rhs, z = Minv r, p = z, rz = r.z
+// ---------------------------------------------------------------------------------------------
+// Block-Jacobi PCG on the implicit Schur complement, single-reduction (Chronopoulos-Gear) form:
+//     u = M^-1 r,  w = S u,  gamma' = r.u,  delta = u.w            <- ONE reduction point per iteration
+//     beta = gamma'/gamma,  alpha = gamma' / (delta - beta gamma'/alpha_prev)
+//     p = u + beta p,  s = w + beta s  (= S p),  x += alpha p,  r -= alpha s
+// Same iterates as textbook PCG; both dot products are available right after the product, so a sharded solve needs one
+// collective per iteration (payload: w on the cameras several ranks observe + the two scalars) and a single-GPU solve
+// two camera-sized launches (k_cg_w, k_cg_update) next to the two halves of the product.
+// Launch li of every kernel exits when cg->done_at <= li.  The stop test of iteration li uses gamma' = r_li . u_li, i.e.
+// it is the textbook test of iteration li-1 evaluated one product later (the price of the single reduction).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void minv_apply(const double* __restrict__ Mi, const double* rr, double* z) {
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sacc += Mi[a * 6 + c] * rr[c];
+    z[a] = sacc;
+  }
+}
+
+// x = 0, r = rhs, u = M^-1 r, p = s = 0, gather table <- T u
 __global__ void __launch_bounds__(NT_C)
 k_cg_start(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ Minv, const double* __restrict__ rhs,
-           double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double* __restrict__ xtab, CgState* cg,
-           const double tol, const int max_iters, double* part, unsigned* counter) {
+           double* __restrict__ x, double* __restrict__ r, double* __restrict__ u, double* __restrict__ p, double* __restrict__ sv,
+           double* __restrict__ xtab, CgState* cg, const double tol, const int max_iters) {
   pdl_grid_sync();
-  __shared__ double sm[NT_C / 32];
-  __shared__ double smo[1];
   const int i = blockIdx.x * NT_C + threadIdx.x;
-  double rz = 0.0;
   if (i < n_cam) {
     double rr[6], z[6];
-    const double* Mi = Minv + (size_t)36 * i;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) { rr[q] = rhs[6 * i + q]; x[6 * i + q] = 0.0; r[6 * i + q] = rr[q]; }
+    for (int q = 0; q < 6; ++q) { rr[q] = rhs[6 * i + q]; x[6 * i + q] = 0.0; r[6 * i + q] = rr[q]; p[6 * i + q] = 0.0; sv[6 * i + q] = 0.0; }
+    minv_apply(Minv + (size_t)36 * i, rr, z);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c];
-      z[a] = s; rz += s * rr[a]; p[6 * i + a] = s;
-    }
+    for (int q = 0; q < 6; ++q) u[6 * i + q] = z[q];
     write_xtab(xtab + (size_t)XTAB * i, camtab + (size_t)CAMTAB * i, z);
   }
-  const double v[1] = {rz};
-  const bool mx[1] = {false};
-  const int slot[1] = {-1};
-  const bool last = finish_scalars<1>(v, mx, slot, part, counter, nullptr, sm, smo);
-  if (last && threadIdx.x == 0) {
-    cg->rzbuf[0] = smo[0]; cg->rzbuf[1] = 0.0; cg->rz0 = smo[0]; cg->tol = tol;
-    cg->iters = 0; cg->max_iters = max_iters; cg->reason = 0;
-    cg->done_at = (smo[0] > 0.0) ? INT_MAX : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    cg->g[0] = 0.0; cg->g[1] = 0.0; cg->a[0] = 0.0; cg->a[1] = 0.0; cg->gamma0 = 0.0; cg->tol = tol;
+    cg->dot[0] = 0.0; cg->dot[1] = 0.0;
+    cg->iters = 0; cg->max_iters = max_iters; cg->reason = 0; cg->done_at = INT_MAX;
   }
 }
 
-// q_i = (B_i + lam/radius) p_i - T_i' yhat_i, partial p.q per CTA.  FUSE: yhat_i summed here from the chunk partials.
-template <bool FUSE>
+// w_i = (B_i + lam/radius) u_i - T_i' yhat_i (yhat_i summed here from the chunk partials of k_spmv_cm, in chunk order);
+// partial gamma' = r.u and delta = u.w per CTA, summed in CTA order by the last CTA.
+//   single GPU: the totals go to cg->dot.
+//   OWNER (sharded, glba.cu "owner-computes"): this rank holds only the cameras its tracks observe; w is PARTIAL on cameras
+//   other ranks observe too.  (B + lam) u and r.u are counted on the camera's owner rank only, u.w^rank on every rank
+//   (it is linear in the partial products).  The partial rows of shared cameras and the two partial scalars are written
+//   into the send buffer of the one all-reduce of the iteration.
+template <bool OWNER>
 __global__ void __launch_bounds__(NT_C)
-k_cg_q(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ Bc,
-       const double* __restrict__ lamc, const double inv_radius, const double* __restrict__ yhat, const int* __restrict__ cam_chunk_start,
-       const double* __restrict__ part6, const double* __restrict__ p, double* __restrict__ q, const CgState* __restrict__ cg, const int li,
-       double* __restrict__ partA) {
+k_cg_w(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ Bc,
+       const double* __restrict__ lamc, const double inv_radius, const int* __restrict__ cam_chunk_start, const double* __restrict__ part6,
+       const double* __restrict__ r, const double* __restrict__ u, double* __restrict__ w, CgState* cg, const int li,
+       const uint8_t* __restrict__ owned, const int* __restrict__ sh_of, double* __restrict__ xsend, const int n_shared,
+       double* part, unsigned* counter) {
   pdl_grid_sync();
-  __shared__ double sm[NT_C / 32];
-  __shared__ double smo[1];
+  __shared__ double sm[2 * NT_C / 32];
+  __shared__ double smo[2];
   if (cg->done_at <= li) return;
   const int i = blockIdx.x * NT_C + threadIdx.x;
-  double pq = 0.0;
+  double ru = 0.0, uw = 0.0;
   if (i < n_cam) {
-    if (!cam_free[i]) {
+    double wi[6] = {0, 0, 0, 0, 0, 0};
+    if (cam_free[i]) {
+      double yh[6] = {0, 0, 0, 0, 0, 0}, ty[6], ui[6];
+      int ch = cam_chunk_start[i];
+      const int ce = cam_chunk_start[i + 1];
+      for (; ch < ce; ++ch)
 #pragma unroll
-      for (int a = 0; a < 6; ++a) q[6 * i + a] = 0.0;
-    } else {
-      double yh[6], ty[6], pi[6];
-      if (FUSE) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) yh[a] = 0.0;
-        for (int ch = cam_chunk_start[i]; ch < cam_chunk_start[i + 1]; ++ch)
-#pragma unroll
-          for (int a = 0; a < 6; ++a) yh[a] += part6[(size_t)6 * ch + a];
-      } else {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) yh[a] = yhat[6 * (size_t)i + a];
-      }
+        for (int a = 0; a < 6; ++a) yh[a] += part6[(size_t)6 * ch + a];
       apply_Tt(camtab + (size_t)CAMTAB * i, yh, ty);
+      const bool mine = !OWNER || owned[i] != 0;
       const double* B = Bc + (size_t)36 * i;
 #pragma unroll
-      for (int a = 0; a < 6; ++a) pi[a] = p[6 * i + a];
+      for (int a = 0; a < 6; ++a) ui[a] = u[6 * i + a];
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        double s = lamc[6 * i + a] * inv_radius * pi[a];
+        double sacc = 0.0;
+        if (mine) {
+          sacc = lamc[6 * i + a] * inv_radius * ui[a];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) s += B[a * 6 + c] * pi[c];
-        s -= ty[a];
-        q[6 * i + a] = s; pq += s * pi[a];
+          for (int c = 0; c < 6; ++c) sacc += B[a * 6 + c] * ui[c];
+          ru += r[6 * i + a] * ui[a];
+        }
+        sacc -= ty[a];
+        wi[a] = sacc; uw += sacc * ui[a];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) w[6 * i + a] = wi[a];
+    if (OWNER) {
+      const int sidx = sh_of[i];
+      if (sidx >= 0) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) xsend[(size_t)6 * sidx + a] = wi[a];
       }
     }
   }
-  double v[1] = {pq};
-  block_reduce<1, NT_C>(v, sm, smo);
-  if (threadIdx.x == 0) partA[blockIdx.x] = smo[0];
+  const double v[2] = {ru, uw};
+  const bool mx[2] = {false, false};
+  const int slot[2] = {-1, -1};
+  const bool last = finish_scalars<2>(v, mx, slot, part, counter, nullptr, sm, smo);
+  if (last && threadIdx.x == 0) {
+    if (OWNER) { xsend[(size_t)6 * n_shared] = smo[0]; xsend[(size_t)6 * n_shared + 1] = smo[1]; }
+    else { cg->dot[0] = smo[0]; cg->dot[1] = smo[1]; }
+  }
 }
 
-__device__ __forceinline__ double sum_parts(const double* __restrict__ part, const int n, double* s_out) {
-  if (threadIdx.x == 0) { double s = 0.0; for (int b = 0; b < n; ++b) s += part[b]; *s_out = s; }
-  __syncthreads();
-  return *s_out;
-}
-
-// x += alpha p, r -= alpha q, z = Minv r (stored in q), partial r.z per CTA
+// the scalar recurrences and every vector update of the iteration; u = M^-1 r and the gather table for the next product
+template <bool OWNER>
 __global__ void __launch_bounds__(NT_C)
-k_cg_xr(const int n_cam, const double* __restrict__ Minv, const double* __restrict__ p, double* __restrict__ q, double* __restrict__ x,
-        double* __restrict__ r, const CgState* __restrict__ cg, const int li, const double* __restrict__ partA, double* __restrict__ partB) {
+k_cg_update(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ Minv, double* __restrict__ u, double* __restrict__ w,
+            double* __restrict__ p, double* __restrict__ sv, double* __restrict__ x, double* __restrict__ r, double* __restrict__ xtab,
+            CgState* cg, const int li, const int* __restrict__ sh_of, const double* __restrict__ xrecv, const int n_shared) {
   pdl_grid_sync();
-  __shared__ double sm[NT_C / 32];
-  __shared__ double smo[1];
-  __shared__ double s_pq;
   if (cg->done_at <= li) return;
-  const double pq = sum_parts(partA, gridDim.x, &s_pq);
-  const double alpha = (pq > 0.0) ? cg->rzbuf[li & 1] / pq : 0.0;
+  const double gp = OWNER ? xrecv[(size_t)6 * n_shared] : cg->dot[0];          // gamma' = r.u
+  const double dl = OWNER ? xrecv[(size_t)6 * n_shared + 1] : cg->dot[1];      // delta  = u.S u
+  const double g_old = cg->g[li & 1], a_old = cg->a[li & 1];
+  const double g0 = (li == 0) ? gp : cg->gamma0;
+  const bool first = (li == 0);
+  // every CTA takes the same decisions from the same numbers; CTA 0 publishes them for the launches behind
+  const bool zero_rhs = first && !(gp > 0.0);
+  const bool converged = !first && sqrt(gp) <= cg->tol * sqrt(g0);
+  const double beta = first ? 0.0 : ((g_old > 0.0) ? gp / g_old : 0.0);
+  const double denom = first ? dl : dl - beta * gp / a_old;
+  const bool breakdown = !(denom > 0.0);
+  const bool stop_now = zero_rhs || converged || breakdown;
+  const double alpha = stop_now ? 0.0 : gp / denom;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (first) cg->gamma0 = gp;
+    cg->g[(li + 1) & 1] = gp; cg->a[(li + 1) & 1] = alpha;
+    if (stop_now) { cg->done_at = li + 1; cg->reason = breakdown && !converged && !zero_rhs ? 2 : 1; cg->iters = li; }
+    else { cg->iters = li + 1; if (li + 1 >= cg->max_iters) { cg->done_at = li + 1; cg->reason = 3; } }
+  }
+  if (stop_now) return;
   const int i = blockIdx.x * NT_C + threadIdx.x;
-  double rz = 0.0;
-  if (i < n_cam) {
-    double rr[6];
-    const double* Mi = Minv + (size_t)36 * i;
+  if (i >= n_cam) return;
+  double wi[6], rr[6], z[6];
+  const int sidx = OWNER ? sh_of[i] : -1;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { x[6 * i + a] += alpha * p[6 * i + a]; rr[a] = r[6 * i + a] - alpha * q[6 * i + a]; r[6 * i + a] = rr[a]; }
+  for (int a = 0; a < 6; ++a) wi[a] = (sidx >= 0) ? xrecv[(size_t)6 * sidx + a] : w[6 * i + a];     // complete w on shared cameras
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s += Mi[a * 6 + c] * rr[c];
-      q[6 * i + a] = s; rz += s * rr[a];
-    }
+  for (int a = 0; a < 6; ++a) {
+    const double pn = u[6 * i + a] + beta * p[6 * i + a];
+    const double sn = wi[a] + beta * sv[6 * i + a];
+    p[6 * i + a] = pn; sv[6 * i + a] = sn;
+    x[6 * i + a] += alpha * pn;
+    rr[a] = r[6 * i + a] - alpha * sn; r[6 * i + a] = rr[a];
   }
-  double v[1] = {rz};
-  block_reduce<1, NT_C>(v, sm, smo);
-  if (threadIdx.x == 0) partB[blockIdx.x] = smo[0];
-}
-
-// p = z + beta p, gather table, stop test (CTA 0 publishes for launches li+1 onwards)
-__global__ void __launch_bounds__(NT_C)
-k_cg_p(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ z, double* __restrict__ p, double* __restrict__ xtab,
-       CgState* cg, const int li, const double* __restrict__ partA, const double* __restrict__ partB) {
-  pdl_grid_sync();
-  __shared__ double s_rz, s_pq;
-  if (cg->done_at <= li) return;
-  const double rz1 = sum_parts(partB, gridDim.x, &s_rz);
-  const double rz_old = cg->rzbuf[li & 1];
-  const double beta = (rz_old > 0.0) ? rz1 / rz_old : 0.0;
-  const int i = blockIdx.x * NT_C + threadIdx.x;
-  if (i < n_cam) {
-    double pn[6];
+  minv_apply(Minv + (size_t)36 * i, rr, z);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { pn[a] = z[6 * i + a] + beta * p[6 * i + a]; p[6 * i + a] = pn[a]; }
-    double t[6];
-    apply_T(camtab + (size_t)CAMTAB * i, pn, t);
-    double* xr = xtab + (size_t)XTAB * i;
+  for (int a = 0; a < 6; ++a) u[6 * i + a] = z[a];
+  double t[6];
+  apply_T(camtab + (size_t)CAMTAB * i, z, t);
+  double* xr = xtab + (size_t)XTAB * i;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) xr[a] = t[a];
-  }
-  if (blockIdx.x == 0) {
-    const double pq = sum_parts(partA, gridDim.x, &s_pq);
-    if (threadIdx.x == 0) {
-      cg->rzbuf[(li + 1) & 1] = rz1;
-      cg->iters = li + 1;
-      if (!(pq > 0.0)) { cg->done_at = li + 1; cg->reason = 2; }
-      else if (sqrt(rz1) <= cg->tol * sqrt(cg->rz0)) { cg->done_at = li + 1; cg->reason = 1; }
-      else if (li + 1 >= cg->max_iters) { cg->done_at = li + 1; cg->reason = 3; }
-    }
-  }
+  for (int a = 0; a < 6; ++a) xr[a] = t[a];
 }
 
 // candidate cameras cam_c = cam - y, their table, gather table [T y | R | sv] for the back-substitution,
@@ -470,7 +483,7 @@ __global__ void __launch_bounds__(NT_C)
 k_cam_step2(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
             const double* __restrict__ y, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius_arg,
             double* __restrict__ cam_c, double* __restrict__ camtab_c, double* __restrict__ xtab, double* part, unsigned* counter, double* scal,
-            const int mode, const LmCtl* __restrict__ ctl = nullptr) {
+            const int mode, const LmCtl* __restrict__ ctl = nullptr, const uint8_t* __restrict__ owned = nullptr) {
   pdl_grid_sync();
   __shared__ double sm[3 * NT_C / 32];
   if (ctl_skip(ctl, GATE_ALWAYS)) return;
@@ -481,11 +494,12 @@ k_cam_step2(const int n_cam, const uint8_t* __restrict__ cam_free, const double*
   if (i < n_cam) {
     double yi[6], cc[6];
     const bool f = cam_free[i] != 0;
+    const bool mine = owned == nullptr || owned[i] != 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       yi[a] = f ? y[6 * i + a] : 0.0;
       cc[a] = cam[6 * i + a] - yi[a];
-      yn2 += yi[a] * yi[a]; ygd += yi[a] * gc[6 * i + a]; yly += lamc[6 * i + a] * inv_radius * yi[a] * yi[a];
+      if (mine) { yn2 += yi[a] * yi[a]; ygd += yi[a] * gc[6 * i + a]; yly += lamc[6 * i + a] * inv_radius * yi[a] * yi[a]; }
     }
     const double* ct = camtab + (size_t)CAMTAB * i;
     if (mode == 0) {

@@ -70,10 +70,11 @@ struct Intr { double fx, fy, cx, cy; };
 struct LossP { int kind; double a; };
 
 struct CgState {
-  double rzbuf[2];   // r.z before launch li is rzbuf[li & 1]
-  double rz0, tol;
-  int done_at;       // kernels of PCG launch li exit when done_at <= li (published by launch done_at-1)
-  int reason;        // 1 converged, 2 breakdown (p'Sp <= 0), 3 iteration cap
+  double g[2], a[2];   // gamma = r.u and alpha of the previous iteration, as launch li reads them: g[li & 1], a[li & 1]
+  double gamma0, tol;
+  double dot[2];       // single GPU: gamma' = r.u and delta = u.S u of the current iteration (k_cg_w -> k_cg_update)
+  int done_at;         // kernels of PCG launch li exit when done_at <= li (published by launch done_at-1)
+  int reason;          // 1 converged, 2 breakdown (p'Sp <= 0), 3 iteration cap
   int iters, max_iters;
 };
 // Device-resident trust-region control (glba_lm.cuh): the decision kernel writes it, every kernel of an LM iteration that the
@@ -882,6 +883,99 @@ __global__ void k_chunk_sum_lin(const int n_cam, const int* __restrict__ cam_chu
   double s = 0.0;
   for (int ch = cam_chunk_start[cam]; ch < cam_chunk_start[cam + 1]; ++ch) s += part[(size_t)27 * ch + q];
   acc[t] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded runs, "owner-computes" layout (glba.cu, load_problem): a rank's problem holds only the cameras its own tracks observe.
+// mask[i] = OR over ranks of (1 << rank) for the ranks that observe camera i (built by a sum all-reduce of disjoint bits).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_act_mask(const long n, const int* __restrict__ obs_cam, const int bit, int* __restrict__ mask) {
+  pdl_grid_sync();
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) mask[obs_cam[k]] = bit;           // same value from every observation of the camera
+}
+__global__ void k_own_flags(const int n_cam, const int* __restrict__ mask, const int rank, int* __restrict__ f_act, int* __restrict__ f_sh) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_cam) return;
+  const int m = (i < n_cam) ? mask[i] : 0;
+  f_act[i] = (m >> rank) & 1;
+  f_sh[i] = (__popc(m) >= 2) ? 1 : 0;
+}
+// local camera a <-> global camera i; owner = lowest observing rank; shared slot (global order) or -1
+__global__ void k_own_build(const int n_cam, const int* __restrict__ mask, const int rank, const int* __restrict__ pos_act,
+                            const int* __restrict__ pos_sh, const uint8_t* __restrict__ fixed, int* __restrict__ l2g, uint8_t* __restrict__ owned,
+                            int* __restrict__ shared, int* __restrict__ n_free_owned) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cam) return;
+  const int m = mask[i];
+  if (!((m >> rank) & 1)) return;
+  const int a = pos_act[i];
+  l2g[a] = i;
+  const bool own = (__ffs(m) - 1) == rank;
+  owned[a] = own ? 1 : 0;
+  shared[a] = (__popc(m) >= 2) ? pos_sh[i] : -1;
+  if (own && !(fixed && fixed[i])) atomicAdd(n_free_owned, 1);
+}
+__global__ void k_relabel_cam(const long n, const int* __restrict__ obs_cam, const int* __restrict__ pos_act, int* __restrict__ out) {
+  pdl_grid_sync();
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = pos_act[obs_cam[k]];
+}
+__global__ void k_gather_cam(const int n_act, const int* __restrict__ l2g, const double* __restrict__ cam_g, const uint8_t* __restrict__ fix_g,
+                             double* __restrict__ cam_l, uint8_t* __restrict__ fix_l) {
+  pdl_grid_sync();
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_act) return;
+  const size_t i = l2g[a];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) cam_l[6 * (size_t)a + q] = cam_g[6 * i + q];
+  if (fix_l) fix_l[a] = fix_g ? fix_g[i] : 0;
+}
+// rows of `width` doubles per local camera -> rows of the global-camera-sized array `out` (stride out_stride); other rows untouched
+__global__ void k_scatter_rows(const int n_act, const int* __restrict__ l2g, const uint8_t* __restrict__ owned, const int only_owned,
+                               const double* __restrict__ in, const int width, double* __restrict__ out) {
+  pdl_grid_sync();
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)n_act * width) return;
+  const int a = (int)(t / width), q = (int)(t - (long)a * width);
+  if (only_owned && !owned[a]) return;
+  out[(size_t)l2g[a] * width + q] = in[t];
+}
+// exchange buffer of a linearisation: row s of a shared camera = its 27 (+27) partial sums; the tail carries the point scalars
+__global__ void k_xch_pack(const int n_act, const int* __restrict__ shared, const double* __restrict__ accA, const double* __restrict__ accB,
+                           const int n_shared, double* __restrict__ xsend, const double* __restrict__ scal, const int n_tail) {
+  pdl_grid_sync();
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_tail) xsend[(size_t)54 * n_shared + t] = scal[t];
+  if (t >= (long)n_act * 54) return;
+  const int a = (int)(t / 54), q = (int)(t - (long)a * 54);
+  const int sidx = shared[a];
+  if (sidx < 0) return;
+  xsend[(size_t)54 * sidx + q] = (q < 27) ? accA[(size_t)27 * a + q] : (accB ? accB[(size_t)27 * a + q - 27] : 0.0);
+}
+__global__ void k_xch_unpack(const int n_act, const int* __restrict__ shared, const double* __restrict__ xrecv, const int n_shared,
+                             double* __restrict__ accA, double* __restrict__ accB, double* __restrict__ scal, const int n_tail) {
+  pdl_grid_sync();
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_tail) scal[t] = xrecv[(size_t)54 * n_shared + t];
+  if (t >= (long)n_act * 54) return;
+  const int a = (int)(t / 54), q = (int)(t - (long)a * 54);
+  const int sidx = shared[a];
+  if (sidx < 0) return;
+  const double v = xrecv[(size_t)54 * sidx + q];
+  if (q < 27) { if (accA) accA[(size_t)27 * a + q] = v; } else if (accB) accB[(size_t)27 * a + q - 27] = v;
+}
+// scalars every rank needs before the host reads them: [0..4] the candidate-step sums over this rank's points,
+// [5..9] the camera sums counted on owned cameras, [10..10+MAX_WORLD) max |g_camera| in this rank's slot
+constexpr int NLATE = 10 + MAX_WORLD;
+__global__ void k_late_pack(const double* __restrict__ scal, const int rank, double* __restrict__ out) {
+  pdl_grid_sync();
+  const int t = threadIdx.x;
+  if (blockIdx.x != 0 || t >= NLATE) return;
+  const int src[10] = {S_COST_C, S_YN2_P, S_YG_P, S_YLY_P, S_BAD_C, S_XN2_C, S_YN2_C, S_YG_C, S_YLY_C, S_NOTPD_C};
+  out[t] = (t < 10) ? scal[src[t]] : ((t - 10 == rank) ? scal[S_GMAX_C] : 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------

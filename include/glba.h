@@ -221,6 +221,9 @@ typedef struct {
   double small_kernels_ms;  /* all camera-sized / reduction kernels of one linearise+Schur pass */
   double allreduce_ms;      /* world > 1: the one fused NCCL all-reduce of a linearise+Schur pass ([accB|accA|scalars]) */
   double chunk_sum_ms;      /* world > 1: the two per-camera chunk sums that feed it */
+  double exchange_bytes;    /* world > 1: payload of that all-reduce on this rank */
+  int32_t n_local_cams;     /* world > 1: cameras this rank holds (owner-computes layout: the ones its own tracks observe) */
+  int32_t n_shared_cams;    /* world > 1: cameras whose partial sums are exchanged (owner-computes: observed by >= 2 ranks) */
 } glba_kernel_times;
 
 void glba_default_options(glba_options* opt);
