@@ -115,7 +115,7 @@ struct glba_ctx {
   // sharded runs, "owner-computes" layout (see load_problem): this rank's problem holds only the cameras its own tracks observe
   bool owner = false, want_owner = false;
   int n_cam_g = 0, n_shared = 0, n_free_cam_g = 0;            // cameras of the whole map; cameras observed by more than one rank
-  Buf act_mask, g2l, l2g, cam_owned, cam_shared, sh_scan, xsend, xrecv, ocam_loc, cam_loc, cfix_loc, late;
+  Buf act_mask, g2l, l2g, cam_owned, cam_shared, sh_scan, xsend, xrecv, xsend6, ocam_loc, cam_loc, cfix_loc, late;
   Buf lmctl, dsum;              // device-resident LM control (LmCtl) and summary trace (glba_summary) of the on-device loop
   bool env_host_lm = false;     // diagnostic: GLBA_HOST_LM=1 keeps the decisions on the host for small windows too
   bool use_pipe = false;        // large maps: persistent TMA-fed tile kernels (glba_pipe.cuh)
@@ -398,7 +398,11 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
     n_cam = n_act; ctx->n_cam = n_act; ctx->owner = true;
     const size_t xlen = 54 * (size_t)ctx->n_shared + NSCAL + 8;
     ENSURE(double, ctx->xsend, xlen); ENSURE(double, ctx->xrecv, xlen); ENSURE(double, ctx->late, 2 * NLATE);
-    CU(cudaMemsetAsync(ctx->xsend.p, 0, sizeof(double) * xlen, s));     // rows of cameras this rank does not observe stay zero for good
+    // two send buffers (54-wide rows of a linearisation, 6-wide rows of a PCG iteration): in each, the rows of cameras this rank
+    // does not observe are zeroed here once and never written again
+    ENSURE(double, ctx->xsend6, 6 * (size_t)ctx->n_shared + 8);
+    CU(cudaMemsetAsync(ctx->xsend.p, 0, sizeof(double) * xlen, s));
+    CU(cudaMemsetAsync(ctx->xsend6.p, 0, sizeof(double) * (6 * (size_t)ctx->n_shared + 8), s));
   }
   // ---- locality relabelling: the tile kernels stage a narrow window of cameras per tile and the camera-major gathers
   // want neighbouring observations to touch neighbouring points, both of which hold when point ids are ordered by their
@@ -824,8 +828,8 @@ int launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, CgS
   if (ctx->owner) {
     const int ns = ctx->n_shared;
     LAUNCH(k_cg_w<true>, ctx->grid_c, NT_C, CG_W_ARGS, (const uint8_t*)ctx->cam_owned.as<uint8_t>(), (const int*)ctx->cam_shared.as<int>(),
-           ctx->xsend.as<double>(), ns, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
-    const int r = g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 6 * (size_t)ns + 2, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+           ctx->xsend6.as<double>(), ns, ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 2);
+    const int r = g_nccl.AllReduce(ctx->xsend6.p, ctx->xrecv.p, 6 * (size_t)ns + 2, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
     if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (PCG): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
     LAUNCH(k_cg_update<true>, ctx->grid_c, NT_C, CG_UPD_ARGS, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ns);
   } else {
@@ -1317,7 +1321,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->cinv, &ctx->u0p, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
