@@ -121,6 +121,12 @@ struct glba_ctx {
   bool use_pipe = false;        // large maps: persistent TMA-fed tile kernels (glba_pipe.cuh)
   bool env_pipe = true, env_force_large = false;
   Buf tile_desc, tile_cams, pm_slot;
+  // fused product (k_pt_pipe<2>): slot lists per tile, camera -> (tile, slot) list, per-tile sums, identity CSR
+  bool use_fused = false, env_fused = true;
+  Buf tile_sobs, tile_sstart, tp_key, tp_val, tp_key2, cam_tp, cam_tp_start, tpart, cam_iota;
+  Buf ovf_raw, ovf_k, ovf_c, ovf_key, ovf_key2, ovf_val, cam_ov, cam_ov_start;      // observations without a camera slot in their tile
+  int n_ovf = 0, ovf_cap = 0;
+  int occ_pt2 = 0;
   int occ_lin = 0, occ_pt0 = 0, occ_pt1 = 0;   // resident CTAs per SM of the pipelined kernels (occupancy API, per context)
   int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
   int n_tiles = 0, max_track = 0, grid_c = 0;
@@ -269,6 +275,9 @@ int set_func_attributes(glba_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_lin_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CU(cudaFuncSetAttribute(k_pt_pipe<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CU(cudaFuncSetAttribute(k_pt_pipe<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(k_pt_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<2>)));
+  CU(cudaFuncSetAttribute(k_pt_pipe<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_pt2, k_pt_pipe<2>, P_NT, sizeof(PtSmem<2>)));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_lin, k_lin_pipe, P_NT, sizeof(LinSmem)));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_pt0, k_pt_pipe<0>, P_NT, sizeof(PtSmem<0>)));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_pt1, k_pt_pipe<1>, P_NT, sizeof(PtSmem<1>)));
@@ -276,6 +285,7 @@ int set_func_attributes(glba_ctx* ctx) {
   if (const char* e = std::getenv("GLBA_OCC")) {          // diagnostic: cap the resident CTAs per SM of the pipelined kernels
     const int cap = std::max(1, std::atoi(e));
     ctx->occ_lin = std::min(ctx->occ_lin, cap); ctx->occ_pt0 = std::min(ctx->occ_pt0, cap); ctx->occ_pt1 = std::min(ctx->occ_pt1, cap);
+    ctx->occ_pt2 = std::min(ctx->occ_pt2, cap);
   }
   ctx->attr_done = true;
   return GLBA_OK;
@@ -340,9 +350,9 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(int, ctx->pm_cam, n); ENSURE(int, ctx->pm_pt, n); ENSURE(double2, ctx->pm_uv, n); ENSURE(int, ctx->pm2cm, n);
   ENSURE(int, ctx->pt_start, (size_t)n_pt + 1); ENSURE(int, ctx->cm_pt, n); ENSURE(double2, ctx->cm_uv, n); ENSURE(int, ctx->cm2pm, n);
   ENSURE(int, ctx->cam_start, (size_t)n_cam + 1); ENSURE(uint8_t, ctx->cam_free, n_cam); ENSURE(uint8_t, ctx->pt_free, n_pt);
-  ENSURE(int, ctx->keys_tmp, 2 * (size_t)n + 2); ENSURE(int, ctx->flags, 8);
+  ENSURE(int, ctx->keys_tmp, 2 * (size_t)n + 2); ENSURE(int, ctx->flags, 16);
   ENSURE(int, ctx->pm2orig, n);
-  CU(cudaMemsetAsync(ctx->flags.p, 0, 8 * sizeof(int), s));
+  CU(cudaMemsetAsync(ctx->flags.p, 0, 16 * sizeof(int), s));
   const int gb = cdiv(n, 256);
   if (n > 0) {
     LAUNCH(k_check_sorted, gb, 256, n, d_opt, n_pt, ctx->flags.as<int>());
@@ -510,8 +520,28 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   if (ctx->use_pipe) {      // per-tile descriptor, distinct-camera list and per-observation camera slot of the pipelined kernels
     ENSURE(int4, ctx->tile_desc, (size_t)ctx->n_tiles); ENSURE(int, ctx->tile_cams, (size_t)TSLOTS * ctx->n_tiles); ENSURE(uint8_t, ctx->pm_slot, n);
     CU(cudaMemsetAsync(ctx->tile_cams.p, 0xff, sizeof(int) * (size_t)TSLOTS * ctx->n_tiles, s));
+    ENSURE(uint16_t, ctx->tile_sobs, n); ENSURE(uint16_t, ctx->tile_sstart, (size_t)SSTART * ctx->n_tiles);
+    ctx->ovf_cap = (int)(n / 32 + 1024);
+    ENSURE(int, ctx->ovf_raw, ctx->ovf_cap);
+    CU(cudaMemsetAsync(ctx->flags.as<int>() + 8, 0, sizeof(int), s));
     LAUNCH(k_tile_meta, ctx->n_tiles, NT_T, (const int*)ctx->tile_pt.as<int>(), (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(), n_cam,
-           ctx->tile_desc.as<int4>(), ctx->tile_cams.as<int>(), ctx->pm_slot.as<uint8_t>());
+           ctx->tile_desc.as<int4>(), ctx->tile_cams.as<int>(), ctx->pm_slot.as<uint8_t>(), ctx->tile_sobs.as<uint16_t>(),
+           ctx->tile_sstart.as<uint16_t>(), ctx->flags.as<int>() + 8, ctx->ovf_raw.as<int>(), ctx->ovf_cap);
+    // camera -> (tile, slot) list of the fused product: stable sort of the tiles' camera lists by camera (unused slots last)
+    const size_t ntp = (size_t)TSLOTS * ctx->n_tiles;
+    ENSURE(int, ctx->tp_key, ntp); ENSURE(int, ctx->tp_val, ntp); ENSURE(int, ctx->tp_key2, ntp); ENSURE(int, ctx->cam_tp, ntp);
+    ENSURE(int, ctx->cam_tp_start, (size_t)n_cam + 2); ENSURE(double, ctx->tpart, 6 * ntp); ENSURE(int, ctx->cam_iota, (size_t)n_cam + 2);
+    LAUNCH(k_tp_keys, cdiv((long)ntp, 256), 256, (long)ntp, (const int*)ctx->tile_cams.as<int>(), n_cam, ctx->tp_key.as<int>(), ctx->tp_val.as<int>());
+    int bits_k = 1; while ((1L << bits_k) < (long)n_cam + 2 && bits_k < 31) ++bits_k;
+    size_t tb = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->tp_key.as<int>(), ctx->tp_key2.as<int>(), ctx->tp_val.as<int>(), ctx->cam_tp.as<int>(), (int)ntp, 0, bits_k, s));
+    ENSURE(char, ctx->sort_tmp, tb);
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->tp_key.as<int>(), ctx->tp_key2.as<int>(), ctx->tp_val.as<int>(), ctx->cam_tp.as<int>(), (int)ntp, 0, bits_k, s));
+    g_launches.fetch_add(1);
+    LAUNCH(k_segment_starts, cdiv(n_cam + 1, 256), 256, (long)ntp, (const int*)ctx->tp_key2.as<int>(), n_cam, ctx->cam_tp_start.as<int>());
+    LAUNCH(k_iota, cdiv(n_cam + 1, 256), 256, (long)n_cam + 1, ctx->cam_iota.as<int>());
+    CU(cudaMemcpyAsync(ctx->h_flags + 8, ctx->flags.as<int>() + 8, sizeof(int), cudaMemcpyDeviceToHost, s));      // read after the sync below
   }
   ctx->grid_c = std::max(1, cdiv(n_cam, NT_C));
   long per = (n + (long)ctx->n_sm * 8 - 1) / ((long)ctx->n_sm * 8);
@@ -537,6 +567,30 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   }
   CU(cudaMemcpyAsync(ctx->cam_chunk_start.p, ccs.data(), sizeof(int) * ccs.size(), cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));   // the host vectors go out of scope
+  // fused product only when every observation of the map found a camera slot in its tile (sharded: on every rank alike is
+  // not required, the two forms compute the same sums)
+  ctx->n_ovf = ctx->use_pipe ? ctx->h_flags[8] : 0;
+  ctx->use_fused = ctx->use_pipe && ctx->env_fused && ctx->n_ovf <= ctx->ovf_cap;
+  if (ctx->use_fused && ctx->n_ovf > 0) {
+    // observations whose camera found no slot in their tile: rows of ovf_c in ascending observation order, and per camera the
+    // list of its rows (both by radix sort: the order the tiles appended them in is irrelevant)
+    const int m = ctx->n_ovf;
+    ENSURE(int, ctx->ovf_k, m); ENSURE(double, ctx->ovf_c, 6 * (size_t)m); ENSURE(int, ctx->ovf_key, m); ENSURE(int, ctx->ovf_key2, m);
+    ENSURE(int, ctx->ovf_val, m); ENSURE(int, ctx->cam_ov, m); ENSURE(int, ctx->cam_ov_start, (size_t)n_cam + 2);
+    size_t tb = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, ctx->ovf_raw.as<int>(), ctx->ovf_k.as<int>(), m, 0, 32, s));
+    ENSURE(char, ctx->sort_tmp, tb);
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tb, ctx->ovf_raw.as<int>(), ctx->ovf_k.as<int>(), m, 0, 32, s));
+    LAUNCH(k_ovf_keys, cdiv(m, 256), 256, m, (const int*)ctx->ovf_k.as<int>(), (const int*)ctx->pm_cam.as<int>(), ctx->ovf_key.as<int>(), ctx->ovf_val.as<int>());
+    tb = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->ovf_key.as<int>(), ctx->ovf_key2.as<int>(), ctx->ovf_val.as<int>(), ctx->cam_ov.as<int>(), m, 0, 32, s));
+    ENSURE(char, ctx->sort_tmp, tb);
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->ovf_key.as<int>(), ctx->ovf_key2.as<int>(), ctx->ovf_val.as<int>(), ctx->cam_ov.as<int>(), m, 0, 32, s));
+    g_launches.fetch_add(2);
+    LAUNCH(k_segment_starts, cdiv(n_cam + 1, 256), 256, (long)m, (const int*)ctx->ovf_key2.as<int>(), n_cam, ctx->cam_ov_start.as<int>());
+  }
   // work buffers
   const int grid_pm = cdiv(n_pt, NT_PM);
   ENSURE(double4, ctx->rec_pm, n); ENSURE(double4, ctx->rec_cm, n);
@@ -602,7 +656,8 @@ CmArgs cm_args(glba_ctx* ctx) {
 }
 
 TileMeta tile_meta(glba_ctx* ctx) {
-  return TileMeta{ctx->tile_desc.as<int4>(), ctx->tile_cams.as<int>(), ctx->pm_slot.as<uint8_t>(), ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), ctx->n_tiles};
+  return TileMeta{ctx->tile_desc.as<int4>(), ctx->tile_cams.as<int>(), ctx->pm_slot.as<uint8_t>(), ctx->pm_cam.as<int>(), ctx->pm_pt.as<int>(), ctx->n_tiles,
+                  ctx->tile_sobs.as<uint16_t>(), ctx->tile_sstart.as<uint16_t>(), ctx->ovf_k.as<int>(), ctx->ovf_c.as<double>(), ctx->use_fused ? ctx->n_ovf : 0};
 }
 int pipe_grid(const glba_ctx* ctx, int occ) { return std::max(1, std::min(ctx->n_tiles, ctx->n_sm * occ)); }
 TileArgs tile_args(glba_ctx* ctx) { return TileArgs{ctx->tile_pt.as<int>(), ctx->pm_pt.as<int>(), ctx->tile_cmin.as<int>(), ctx->n_cam}; }
@@ -673,6 +728,15 @@ void launch_point_pass0(glba_ctx* ctx, const glba_options* o, const CgState* cg,
            (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(),
            ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr, (const double*)nullptr,
            (const double4*)nullptr, 0.0, (double*)nullptr);
+}
+
+// both halves of the implicit product in one pass over the point-major records (k_pt_pipe<2>): per-tile, per-camera-slot sums
+void launch_spmv_fused(glba_ctx* ctx, const glba_options* o, const CgState* cg, int li) {
+  const int c = ctx->cur;
+  LAUNCH_SMEM(k_pt_pipe<2>, pipe_grid(ctx, ctx->occ_pt2), P_NT, sizeof(PtSmem<2>), pm_args(ctx, o), tile_meta(ctx), (const double4*)ctx->rec_pm.as<double4>(),
+      (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->xtab.as<double>(), (const double*)ctx->cinv.as<double>(),
+      (const double4*)ctx->u0p.as<double4>(), ctx->u4.as<double4>(), cg, li, (const double4*)nullptr, (double4*)nullptr, (const double*)nullptr,
+      (const double*)nullptr, (const double4*)nullptr, 0.0, ctx->tpart.as<double>(), RedArgs{});
 }
 
 void launch_point_pass1(glba_ctx* ctx, const glba_options* o, double radius, const LmCtl* ctl = nullptr, const LmHook* hook = nullptr) {
@@ -817,11 +881,22 @@ int do_schur(glba_ctx* ctx, double radius) {
 int launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, CgState* cg, int li) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
-  launch_point_pass0(ctx, o, cg, li);
-  LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
-         (const double4*)ctx->u4.as<double4>(), (const CgState*)cg, li, ctx->part_cm.as<double>());
+  // yhat partials: either per chunk of the camera-major order (two-kernel product) or per camera from the fused tile kernel
+  const int* ysum_start = ctx->cam_chunk_start.as<int>();
+  const double* ysum_part = ctx->part_cm.as<double>();
+  if (ctx->use_fused) {
+    launch_spmv_fused(ctx, o, cg, li);
+    LAUNCH(k_cam_combine, cdiv((long)n_cam * 32, 256), 256, n_cam, (const int*)ctx->cam_tp_start.as<int>(), (const int*)ctx->cam_tp.as<int>(),
+           (const double*)ctx->tpart.as<double>(), ctx->n_ovf > 0 ? (const int*)ctx->cam_ov_start.as<int>() : (const int*)nullptr,
+           (const int*)ctx->cam_ov.as<int>(), (const double*)ctx->ovf_c.as<double>(), ctx->yhat.as<double>(), (const CgState*)cg, li);
+    ysum_start = ctx->cam_iota.as<int>(); ysum_part = ctx->yhat.as<double>();
+  } else {
+    launch_point_pass0(ctx, o, cg, li);
+    LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
+           (const double4*)ctx->u4.as<double4>(), (const CgState*)cg, li, ctx->part_cm.as<double>());
+  }
 #define CG_W_ARGS n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Bc.as<double>(), \
-    (const double*)ctx->lamc.as<double>(), 1.0 / radius, (const int*)ctx->cam_chunk_start.as<int>(), (const double*)ctx->part_cm.as<double>(), \
+    (const double*)ctx->lamc.as<double>(), 1.0 / radius, ysum_start, ysum_part, \
     (const double*)ctx->cg_r.as<double>(), (const double*)ctx->cg_q.as<double>(), ctx->yg.as<double>(), cg, li
 #define CG_UPD_ARGS n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(), ctx->cg_q.as<double>(), ctx->yg.as<double>(), \
     ctx->cg_p.as<double>(), ctx->pg.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->xtab.as<double>(), cg, li
@@ -859,6 +934,24 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
          (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
          ctx->pg.as<double>(), ctx->xtab.as<double>(), cg, o->cg_rel_tol, max_it);
+  if (std::getenv("GLBA_DEBUG_SPMV") && ctx->use_fused) {      // diagnostic: the fused product twice on the same input, compared bit for bit
+    std::vector<double> y1(6 * (size_t)n_cam), y2(6 * (size_t)n_cam), t1(6 * (size_t)TSLOTS * ctx->n_tiles), t2(t1.size());
+    for (int rep = 0; rep < 2; ++rep) {
+      launch_spmv_fused(ctx, o, cg, 0);
+      LAUNCH(k_cam_combine, cdiv((long)n_cam * 32, 256), 256, n_cam, (const int*)ctx->cam_tp_start.as<int>(), (const int*)ctx->cam_tp.as<int>(),
+             (const double*)ctx->tpart.as<double>(), ctx->n_ovf > 0 ? (const int*)ctx->cam_ov_start.as<int>() : (const int*)nullptr,
+             (const int*)ctx->cam_ov.as<int>(), (const double*)ctx->ovf_c.as<double>(), ctx->yhat.as<double>(), (const CgState*)cg, 0);
+      cudaMemcpyAsync(rep ? y2.data() : y1.data(), ctx->yhat.p, sizeof(double) * y1.size(), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaMemcpyAsync(rep ? t2.data() : t1.data(), ctx->tpart.p, sizeof(double) * t1.size(), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    size_t dy = 0, dt = 0, firstt = (size_t)-1;
+    for (size_t q = 0; q < y1.size(); ++q) dy += std::memcmp(&y1[q], &y2[q], 8) != 0;
+    for (size_t q = 0; q < t1.size(); ++q) if (std::memcmp(&t1[q], &t2[q], 8) != 0) { if (firstt == (size_t)-1) firstt = q; ++dt; }
+    fprintf(stderr, "[glba debug] fused product twice: %zu of %zu yhat entries differ, %zu of %zu tile sums differ (first at tile %zu slot %zu comp %zu: %.17g vs %.17g), n_ovf %d\n",
+            dy, y1.size(), dt, t1.size(), firstt == (size_t)-1 ? 0 : firstt / (6 * TSLOTS), firstt == (size_t)-1 ? 0 : (firstt / 6) % TSLOTS, firstt == (size_t)-1 ? 0 : firstt % 6,
+            firstt == (size_t)-1 ? 0.0 : t1[firstt], firstt == (size_t)-1 ? 0.0 : t2[firstt], ctx->n_ovf);
+  }
   const int poll = 8;
   int launched = 0;
   // the stop test lags one product behind the update (single-reduction recurrence): max_it updates need max_it + 1 launches
@@ -1293,6 +1386,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   g_pdl_max_grid = 2u * (unsigned)ctx->n_sm;
   if (const char* e = std::getenv("GLBA_PDL")) { g_pdl = (e[0] != '0'); if (e[0] == '2') g_pdl_max_grid = 0x7fffffffu; }   // diagnostic: 0 = plain launches, 2 = every launch
   if (const char* e = std::getenv("GLBA_HOST_LM")) ctx->env_host_lm = (e[0] == '1');   // diagnostic: host-side accept/reject for small windows
+  if (const char* e = std::getenv("GLBA_FUSED")) ctx->env_fused = (e[0] != '0');       // diagnostic: GLBA_FUSED=0 = two-kernel implicit product
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
@@ -1300,7 +1394,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   for (auto& e : ctx->ev_copy) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   if (cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * NSCAL) != cudaSuccess || cudaMallocHost((void**)&ctx->h_cg, sizeof(CgState)) != cudaSuccess ||
-      cudaMallocHost((void**)&ctx->h_flags, 8 * sizeof(int)) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
+      cudaMallocHost((void**)&ctx->h_flags, 16 * sizeof(int)) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   if (cfg->world > 1) {
     if (!cfg->nccl_unique_id || !g_nccl.load()) { glba_destroy(ctx); return GLBA_E_NCCL; }
     ncclUniqueId id; std::memcpy(&id, cfg->nccl_unique_id, sizeof(id));
@@ -1321,7 +1415,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->cinv, &ctx->u0p, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->tile_sobs, &ctx->tile_sstart, &ctx->tp_key, &ctx->tp_val, &ctx->tp_key2, &ctx->cam_tp, &ctx->cam_tp_start, &ctx->tpart, &ctx->cam_iota, &ctx->ovf_raw, &ctx->ovf_k, &ctx->ovf_c, &ctx->ovf_key, &ctx->ovf_key2, &ctx->ovf_val, &ctx->cam_ov, &ctx->cam_ov_start, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);

@@ -335,6 +335,40 @@ __device__ __forceinline__ void minv_apply(const double* __restrict__ Mi, const 
   }
 }
 
+// Fused product (k_pt_pipe<2>): the tile kernel leaves, per tile and camera slot, the six sums of that camera's observations
+// in the tile.  One warp per camera adds its entries (camera -> (tile, slot) list built at load time, tile order): lane-strided
+// partial sums + a fixed xor butterfly, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(256)
+k_cam_combine(const int n_cam, const int* __restrict__ cam_tp_start, const int* __restrict__ cam_tp, const double* __restrict__ tpart,
+              const int* __restrict__ cam_ov_start /* may be null */, const int* __restrict__ cam_ov, const double* __restrict__ ovf_c,
+              double* __restrict__ yhat, const CgState* __restrict__ cg, const int li) {
+  pdl_grid_sync();
+  if (cg && cg->done_at <= li) return;
+  const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_cam) return;
+  const int e0 = cam_tp_start[w], e1 = cam_tp_start[w + 1];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const double2* t = reinterpret_cast<const double2*>(tpart + (size_t)6 * cam_tp[e]);
+    const double2 a = t[0], b = t[1], c = t[2];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y;
+  }
+  if (cam_ov_start != nullptr)       // observations that found no slot in their tile, in observation order
+    for (int e = cam_ov_start[w] + lane; e < cam_ov_start[w + 1]; e += 32) {
+      const double* t = ovf_c + (size_t)6 * cam_ov[e];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[q] += t[q];
+    }
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) yhat[(size_t)6 * w + q] = acc[q];
+  }
+}
+
 // x = 0, r = rhs, u = M^-1 r, p = s = 0, gather table <- T u
 __global__ void __launch_bounds__(NT_C)
 k_cg_start(const int n_cam, const double* __restrict__ camtab, const double* __restrict__ Minv, const double* __restrict__ rhs,

@@ -1035,6 +1035,23 @@ __global__ void k_iota(const long n, int* out) {
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) out[k] = (int)k;
 }
+// keys of the camera -> (tile, slot) list: the camera of every (tile, slot) entry, n_cam for unused slots
+__global__ void k_tp_keys(const long n, const int* __restrict__ cams, const int n_cam, int* __restrict__ key, int* __restrict__ val) {
+  pdl_grid_sync();
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int c = cams[e];
+  key[e] = (c >= 0) ? c : n_cam;
+  val[e] = (int)e;
+}
+// camera of every overflow observation (keys of the camera -> overflow-row list)
+__global__ void k_ovf_keys(const int n, const int* __restrict__ ovf_k, const int* __restrict__ pm_cam, int* __restrict__ key, int* __restrict__ val) {
+  pdl_grid_sync();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  key[e] = pm_cam[ovf_k[e]];
+  val[e] = e;
+}
 __global__ void k_check_sorted(const long n, const int* __restrict__ key, const int n_key, int* flags /* [0]=unsorted, [1]=out of range */) {
   pdl_grid_sync();
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -43,7 +43,16 @@ struct TileMeta {
   const int* pm_cam;       // [n_obs] camera of every observation (fall-backs only)
   const int* pm_pt;        // [n_obs] point of every observation (fall-backs only)
   int n_tiles;
+  // fused product (k_pt_pipe<2>): the tile's observations grouped by camera slot
+  const uint16_t* sobs;    // [n_obs] tile-local observation indices, slot by slot (each tile owns positions [k0, k1))
+  const uint16_t* sstart;  // [n_tiles][SSTART] first list position of every slot, [TSLOTS] = end
+  // observations whose camera found no slot in their tile (a tile with more than TSLOTS distinct cameras; 0.1 % of the street
+  // grid): listed by ascending observation index; the fused product writes their contributions to ovf_c one by one
+  const int* ovf_k;        // [n_ovf] ascending
+  double* ovf_c;           // [n_ovf][6]
+  int n_ovf;
 };
+constexpr int SSTART = 40;                  // uint16 per tile: TSLOTS + 1 used, padded to 80 bytes (16-byte multiple)
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,12 +101,15 @@ __device__ __forceinline__ void bulk_slice(void* dst, const void* base, const si
 // Distinct cameras by a shared-memory bitmap over [base, base + 16 384): the rank of a camera's bit IS its slot.
 __global__ void __launch_bounds__(NT_T)
 k_tile_meta(const int* __restrict__ tile_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, const int n_cam,
-            int4* __restrict__ desc, int* __restrict__ cams /* pre-filled with -1 */, uint8_t* __restrict__ slot) {
+            int4* __restrict__ desc, int* __restrict__ cams /* pre-filled with -1 */, uint8_t* __restrict__ slot,
+            uint16_t* __restrict__ sobs, uint16_t* __restrict__ sstart, int* __restrict__ n_overflow, int* __restrict__ ovf_raw, const int ovf_cap) {
   pdl_grid_sync();
   __shared__ unsigned bm[BM_WORDS];
   __shared__ int pre[BM_WORDS];
   __shared__ int wsum[NT_T / 32];
   __shared__ int s_base;
+  __shared__ uint8_t s_slot[P_OBS];
+  __shared__ int s_cnt[TSLOTS], s_pos[TSLOTS + 1];
   const int t = blockIdx.x, tid = threadIdx.x;
   const int j0 = tile_pt[t], j1 = tile_pt[t + 1];
   const int k0 = pt_start[j0], k1 = pt_start[j1];
@@ -145,6 +157,30 @@ k_tile_meta(const int* __restrict__ tile_pt, const int* __restrict__ pt_start, c
       if (r < TSLOTS) { s = r; cams[(size_t)TSLOTS * t + r] = cam; }      // same value from every observation of the camera
     }
     slot[k] = (uint8_t)s;
+    if (k - k0 < P_OBS) s_slot[k - k0] = (uint8_t)s;
+    if (s == 255) { const int q = atomicAdd(n_overflow, 1); if (q < ovf_cap) ovf_raw[q] = k; }      // (sorted afterwards: order-independent)
+  }
+  // the tile's observations grouped by slot, in observation order inside a slot (fixed order: the per-camera sums of the
+  // fused product are reproducible): one thread per slot walks the tile
+  __syncthreads();
+  const int nobs = min(k1 - k0, P_OBS);
+  if (tid < TSLOTS) {
+    int c = 0;
+    for (int l = 0; l < nobs; ++l) c += (s_slot[l] == tid) ? 1 : 0;
+    s_cnt[tid] = c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int q = 0; q < TSLOTS; ++q) { s_pos[q] = acc; acc += s_cnt[q]; }
+    s_pos[TSLOTS] = acc;
+  }
+  __syncthreads();
+  if (tid <= TSLOTS) sstart[(size_t)SSTART * t + tid] = (uint16_t)s_pos[tid];
+  if (tid < TSLOTS) {
+    int pos = s_pos[tid];
+    for (int l = 0; l < nobs; ++l)
+      if (s_slot[l] == tid) sobs[k0 + pos++] = (uint16_t)l;
   }
 }
 
@@ -391,6 +427,8 @@ struct __align__(128) PtRing {
   double cs[MODE == 1 ? TSLOTS * CROW : 2];
   int ptst[NPCAP + 8];
   uint8_t slot[P_OBS + 16];
+  uint16_t sobs[MODE == 2 ? P_OBS + 8 : 8];   // fused product: observations by slot
+  uint16_t sstart[MODE == 2 ? SSTART : 8];
   int cams_next[TSLOTS];
   int4 desc_next;
   int4 desc;
@@ -400,22 +438,32 @@ struct __align__(128) PtSmem {
   PtRing<MODE> ring[2];
   double val[3][P_OBS];
   double4 ptc[MODE == 1 ? NPCAP : 1];       // candidate points of the tile (phase 3 re-reads them)
-  uint8_t pidx[MODE == 1 ? P_OBS : 16];     // local point index per observation (phase 3 only)
+  double us[MODE == 2 ? 3 * NPCAP : 2];     // fused product: u_j of the tile's points
+  // local point index per observation (phase 3).  MODE 1 has no barrier behind phase 3, so the next tile's indices (written
+  // before its first barrier) go to the other half: one copy per ring stage
+  uint8_t pidx[MODE == 1 ? 2 * P_OBS : (MODE == 2 ? P_OBS : 16)];
   double red[5 * P_NT / 32 + 8];
   uint64_t full[2];
 };
 
 template <int MODE>
-__device__ __forceinline__ void pt_issue_ring(PtRing<MODE>& R, uint64_t* bar, const int4 d, const int next_tile, const PmArgs& A,
-                                              const TileMeta& M, const double4* rec_pm) {
+__device__ __forceinline__ void pt_issue_ring(PtRing<MODE>& R, uint64_t* bar, const int4 d, const int this_tile, const int next_tile,
+                                              const PmArgs& A, const TileMeta& M, const double4* rec_pm) {
   R.desc = d;
   const int np = min(d.y - d.x, NPCAP);
   const unsigned b_rec = (unsigned)(d.w - d.z) * 32u;
   const unsigned b_next = next_tile < M.n_tiles ? (unsigned)(TSLOTS * 4 + 16) : 0u;
-  mbar_expect_tx(bar, b_rec + b_next + slice_bytes(A.pt_start, 4, d.x, d.x + np + 1) + slice_bytes(M.slot, 1, d.z, d.w));
+  const unsigned b_lists = (MODE == 2) ? slice_bytes(M.sobs, 2, d.z, d.w) + (unsigned)(SSTART * 2) : 0u;
+  // MODE 2 overwrites consumed records of this stage with generic stores: order them before the copy engine's writes
+  if (MODE == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(bar, b_rec + b_next + b_lists + slice_bytes(A.pt_start, 4, d.x, d.x + np + 1) + slice_bytes(M.slot, 1, d.z, d.w));
   if (b_next) {
     bulk_g2s(R.cams_next, M.cams + (size_t)TSLOTS * next_tile, TSLOTS * 4, bar);
     bulk_g2s(&R.desc_next, M.desc + next_tile, 16, bar);
+  }
+  if (MODE == 2) {
+    bulk_slice(R.sobs, M.sobs, 2, d.z, d.w, bar);
+    bulk_g2s(R.sstart, M.sstart + (size_t)SSTART * this_tile, SSTART * 2, bar);
   }
   if (b_rec) bulk_g2s(R.rec, rec_pm + d.z, b_rec, bar);
   bulk_slice(R.ptst, A.pt_start, 4, d.x, d.x + np + 1, bar);
@@ -424,6 +472,7 @@ __device__ __forceinline__ void pt_issue_ring(PtRing<MODE>& R, uint64_t* bar, co
 
 static_assert(sizeof(PtSmem<0>) + 1024 <= 233472 / 4, "k_pt_pipe<0>: four CTAs per SM");
 static_assert(sizeof(PtSmem<1>) + 1024 <= 233472 / 3, "k_pt_pipe<1>: three CTAs per SM");
+static_assert(sizeof(PtSmem<2>) + 1024 <= 233472 / 3, "k_pt_pipe<2>: three CTAs per SM");
 // xtab row of camera i: [xg(6) = T_i x_i | R_i (9) | small-angle flag] — 128 bytes, eight 16-byte pieces
 template <int MODE>
 __global__ void __launch_bounds__(P_NT)
@@ -432,11 +481,11 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
           const CgState* __restrict__ cg, const int li,
           // MODE 1 only:
           const double4* __restrict__ pt, double4* pt_c, const double* __restrict__ camtab_c, const double* __restrict__ Craw,
-          const double4* __restrict__ lam4, const double inv_radius_arg, double* __restrict__ part /* [grid][5] */, const RedArgs RA) {
+          const double4* __restrict__ lam4, const double inv_radius_arg, double* __restrict__ part /* [grid][5]; MODE 2: [n_tiles][TSLOTS][6] */, const RedArgs RA) {
   pdl_grid_sync();
   extern __shared__ __align__(128) unsigned char dsm_raw[];
   PtSmem<MODE>& S = *reinterpret_cast<PtSmem<MODE>*>(dsm_raw);
-  if (MODE == 0 && cg && cg->done_at <= li) return;
+  if (MODE != 1 && cg && cg->done_at <= li) return;
   if (MODE == 1 && ctl_skip(RA.ctl, RA.gate)) return;
   const double inv_radius = (MODE == 1) ? ctl_inv_radius(RA.ctl, inv_radius_arg) : inv_radius_arg;
   const int tid = threadIdx.x;
@@ -446,7 +495,7 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
   {
     RowFetch<8> FX;
     FX.fetch(M.cams + (size_t)TSLOTS * blockIdx.x, xtab, XTAB);
-    if (tid == 0) pt_issue_ring<MODE>(S.ring[0], &S.full[0], __ldg(M.desc + blockIdx.x), blockIdx.x + gridDim.x, A, M, rec_pm);
+    if (tid == 0) pt_issue_ring<MODE>(S.ring[0], &S.full[0], __ldg(M.desc + blockIdx.x), blockIdx.x, blockIdx.x + gridDim.x, A, M, rec_pm);
     FX.template store<XROW>(S.ring[0].xs);
     if (MODE == 1) {
       RowFetch<6> FC;
@@ -468,11 +517,12 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
     const int np = d.y - d.x, n = d.w - d.z;
     const int o_s = slice_off(M.slot, 1, k0), o_j = slice_off(A.pt_start, 4, j0);
     auto pts = [&](const int p) -> int { return (p <= NPCAP) ? R.ptst[o_j + p] : __ldg(A.pt_start + j0 + p); };
-    if (MODE == 1)
+    uint8_t* const pidx = S.pidx + (MODE == 1 ? s * P_OBS : 0);
+    if (MODE != 0)
       for (int p = tid; p < np; p += P_NT) {
         const int b = pts(p) - k0, e = pts(p + 1) - k0;
         const uint8_t pv = (uint8_t)(p < NPCAP ? p : 255);
-        for (int m = b; m < e; ++m) S.pidx[m] = pv;
+        for (int m = b; m < e; ++m) pidx[m] = pv;
       }
     __syncthreads();            // (A)
     RowFetch<8> FX;
@@ -482,7 +532,7 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
       FX.fetch(R.cams_next, xtab, XTAB);
       if (MODE == 1) FC.fetch(R.cams_next, camtab_c, CAMTAB);
     }
-    if (more && tid == 0) pt_issue_ring<MODE>(S.ring[s ^ 1], &S.full[s ^ 1], R.desc_next, tile + 2 * gridDim.x, A, M, rec_pm);
+    if (more && tid == 0) pt_issue_ring<MODE>(S.ring[s ^ 1], &S.full[s ^ 1], R.desc_next, tile + gridDim.x, tile + 2 * gridDim.x, A, M, rec_pm);
     // what phase 2 needs of this thread's point: requested now, consumed after phase 1
     double Ci_pre[6] = {0, 0, 0, 0, 0, 0};
     uint8_t free_pre = 0;
@@ -576,6 +626,9 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
       const double v2 = Ci[2] * t0 + Ci[4] * t1 + Ci[5] * t2;
       if (MODE == 0) {
         st4(u4 + j, make_double4(v0, v1, v2, 0.0));
+      } else if (MODE == 2) {
+        if (staged) { S.us[3 * p] = v0; S.us[3 * p + 1] = v1; S.us[3 * p + 2] = v2; }
+        else st4(u4 + j, make_double4(v0, v1, v2, 0.0));           // beyond the staged points: through global memory
       } else {
         const double y0 = u3[0] - v0, y1 = u3[1] - v1, y2 = u3[2] - v2;
         const double4 X = mine ? X_pre : ldg4(pt + j);
@@ -593,6 +646,72 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
         }
       }
     }
+    if (MODE == 2) {
+      // ---- camera half of the product, fused: yhat_i += J^' (J~p u_j) summed per camera SLOT of the tile -----------------
+      __syncthreads();                  // (C) u_j of the tile's points are in S.us
+#pragma unroll
+      for (int m = 0; m < P_OPT; ++m) {
+        const int l = m * P_NT + tid;
+        if (l < n) {
+          const double4 rec = R.rec[l];
+          const int sl = R.slot[o_s + l];
+          double Rm[9], sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
+          if (sl != 255) {
+            const double2* xr = reinterpret_cast<const double2*>(&R.xs[sl * XROW]);
+            const double2 a3 = xr[3], a4 = xr[4], a5 = xr[5], a6 = xr[6], a7 = xr[7];
+            Rm[0] = a3.x; Rm[1] = a3.y; Rm[2] = a4.x; Rm[3] = a4.y; Rm[4] = a5.x; Rm[5] = a5.y; Rm[6] = a6.x; Rm[7] = a6.y; Rm[8] = a7.x;
+            if (a7.y != 0.0) {
+              const double* ct = camtab + (size_t)CAMTAB * __ldg(M.pm_cam + k0 + l);
+              sv0 = ct[CT_SV]; sv1 = ct[CT_SV + 1]; sv2 = ct[CT_SV + 2];
+            }
+          } else {
+            const double* ct = camtab + (size_t)CAMTAB * __ldg(M.pm_cam + k0 + l);
+            double cc[3];
+            load_Rc(ct, Rm, cc);
+            if (ct[CT_SV] != 0.0 || ct[CT_SV + 1] != 0.0 || ct[CT_SV + 2] != 0.0) { sv0 = ct[CT_SV]; sv1 = ct[CT_SV + 1]; sv2 = ct[CT_SV + 2]; }
+          }
+          const int pl = pidx[l];
+          double u0, u1, u2;
+          if (pl != 255) { u0 = S.us[3 * pl]; u1 = S.us[3 * pl + 1]; u2 = S.us[3 * pl + 2]; }
+          else { const double4 uu = ld4(u4 + __ldg(M.pm_pt + k0 + l)); u0 = uu.x; u1 = uu.y; u2 = uu.z; }
+          double ap[3], bp[3], a[6], bb[6];
+          jp_rows(rec, Rm, A.K, ap, bp);
+          const double f0 = ap[0] * u0 + ap[1] * u1 + ap[2] * u2;
+          const double f1 = bp[0] * u0 + bp[1] * u1 + bp[2] * u2;
+          jhat_rows(rec, sv0, sv1, sv2, A.K, a, bb);
+          // the record has been consumed: its 32 bytes and two of the (free) val rows take the six contributions
+          double4 c03;
+          c03.x = a[0] * f0 + bb[0] * f1; c03.y = a[1] * f0 + bb[1] * f1; c03.z = a[2] * f0 + bb[2] * f1; c03.w = a[3] * f0;
+          const double c4 = bb[4] * f1, c5 = a[5] * f0 + bb[5] * f1;
+          if (sl != 255) {
+            R.rec[l] = c03;
+            S.val[0][l] = c4;
+            S.val[1][l] = c5;
+          } else {
+            // no slot: the contribution goes to this observation's row of the overflow list (binary search: rare path)
+            const int k = k0 + l;
+            int lo = 0, hi = M.n_ovf;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(M.ovf_k + mid) < k) lo = mid + 1; else hi = mid; }
+            double* oc = M.ovf_c + (size_t)6 * lo;
+            oc[0] = c03.x; oc[1] = c03.y; oc[2] = c03.z; oc[3] = c03.w; oc[4] = c4; oc[5] = c5;
+          }
+        }
+      }
+      // the stores above went into a ring stage the copy engine refills two tiles from now: order them before the async proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();                  // (D)
+      const int o_l = slice_off(M.sobs, 2, k0);
+      for (int e = tid; e < TSLOTS * 6; e += P_NT) {
+        const int sl = e / 6, comp = e - sl * 6;
+        const int q0 = R.sstart[sl], q1 = R.sstart[sl + 1];
+        double acc = 0.0;
+        for (int q = q0; q < q1; ++q) {
+          const int l = R.sobs[o_l + q];
+          acc += (comp < 4) ? reinterpret_cast<const double*>(&R.rec[l])[comp] : S.val[comp - 4][l];
+        }
+        part[((size_t)tile * TSLOTS + sl) * 6 + comp] = acc;
+      }
+    }
     if (MODE == 1) {
       __syncthreads();                  // (C) the tile's candidate points are in S.ptc (and in global for the fall-back)
       // ---- phase 3: candidate cost, one thread per observation ---------------------------------------------------
@@ -602,7 +721,7 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
         if (l < n) {
           const int k = k0 + l;
           const double2 uv = uv_pre[m];
-          const int pl = S.pidx[l];
+          const int pl = pidx[l];
           const double4 xc = (pl != 255) ? S.ptc[pl] : ld4(pt_c + __ldg(M.pm_pt + k));      // written by this CTA: coherent load
           const int sl = R.slot[o_s + l];
           double Rc[9], cc[3];

@@ -51,6 +51,26 @@ def test_whole_map_trajectory(ctx, oracle, cfg, kw):
     assert max(s["cg_iters"]) > 0
     check_trajectory(s, so)
     check_state(prob, got.cam, got.pt, ref.cam, ref.pt)
+    # the cost of a trial point (back-substitution kernel) and the cost of the same point once it is accepted and
+    # re-linearised (linearisation kernel) are two evaluations of one function: they must agree, and with the oracle's
+    for it in range(1, s["n_iters"] + 1):
+        if s["accepted"][it]:
+            assert abs(s["cost_candidate"][it] - s["cost"][it]) <= 1e-11 * s["cost"][it], (it, s["cost_candidate"][it], s["cost"][it])
+    assert np.allclose(s["cost_candidate"][1:s["n_iters"] + 1], so["cost_candidate"][1:so["n_iters"] + 1], rtol=1e-9)
+
+
+def test_large_map_solve_is_bitwise_reproducible(ctx):
+    """1.25 M observations through the pipelined kernels, inexact-Newton mode (truncated PCG amplifies any schedule-dependent
+    bit): two solves of the same problem must agree bit for bit, trial costs included."""
+    prob = scene.config("C4", scale=0.25)
+    opt = g.options(max_iters=5, function_tol=0.0, parameter_tol=0.0, gradient_tol=0.0, cg_rel_tol=1e-2, cg_max_iters=40)
+    a, sa = ctx.solve(prob, opt)
+    b, sb = ctx.solve(prob, opt)
+    assert sa["cost_candidate"] == sb["cost_candidate"] and sa["cost"] == sb["cost"] and sa["cg_iters"] == sb["cg_iters"]
+    assert np.array_equal(a.cam, b.cam) and np.array_equal(a.pt, b.pt)
+    for it in range(1, sa["n_iters"] + 1):
+        if sa["accepted"][it]:
+            assert abs(sa["cost_candidate"][it] - sa["cost"][it]) <= 1e-11 * sa["cost"][it]
 
 
 def test_c2_huber_with_outliers(ctx, oracle):
