@@ -122,7 +122,7 @@ struct glba_ctx {
   bool env_pipe = true, env_force_large = false;
   Buf tile_desc, tile_cams, pm_slot;
   // fused product (k_pt_pipe<2>): slot lists per tile, camera -> (tile, slot) list, per-tile sums, identity CSR
-  bool use_fused = false, env_fused = true;
+  bool use_fused = false, env_fused = false;      // measured slower than the two-kernel product (see k_pt_pipe<2>): opt-in with GLBA_FUSED=1
   Buf tile_sobs, tile_sstart, tp_key, tp_val, tp_key2, cam_tp, cam_tp_start, tpart, cam_iota;
   Buf ovf_raw, ovf_k, ovf_c, ovf_key, ovf_key2, ovf_val, cam_ov, cam_ov_start;      // observations without a camera slot in their tile
   int n_ovf = 0, ovf_cap = 0;
@@ -934,24 +934,6 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
          (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
          ctx->pg.as<double>(), ctx->xtab.as<double>(), cg, o->cg_rel_tol, max_it);
-  if (std::getenv("GLBA_DEBUG_SPMV") && ctx->use_fused) {      // diagnostic: the fused product twice on the same input, compared bit for bit
-    std::vector<double> y1(6 * (size_t)n_cam), y2(6 * (size_t)n_cam), t1(6 * (size_t)TSLOTS * ctx->n_tiles), t2(t1.size());
-    for (int rep = 0; rep < 2; ++rep) {
-      launch_spmv_fused(ctx, o, cg, 0);
-      LAUNCH(k_cam_combine, cdiv((long)n_cam * 32, 256), 256, n_cam, (const int*)ctx->cam_tp_start.as<int>(), (const int*)ctx->cam_tp.as<int>(),
-             (const double*)ctx->tpart.as<double>(), ctx->n_ovf > 0 ? (const int*)ctx->cam_ov_start.as<int>() : (const int*)nullptr,
-             (const int*)ctx->cam_ov.as<int>(), (const double*)ctx->ovf_c.as<double>(), ctx->yhat.as<double>(), (const CgState*)cg, 0);
-      cudaMemcpyAsync(rep ? y2.data() : y1.data(), ctx->yhat.p, sizeof(double) * y1.size(), cudaMemcpyDeviceToHost, ctx->stream);
-      cudaMemcpyAsync(rep ? t2.data() : t1.data(), ctx->tpart.p, sizeof(double) * t1.size(), cudaMemcpyDeviceToHost, ctx->stream);
-      cudaStreamSynchronize(ctx->stream);
-    }
-    size_t dy = 0, dt = 0, firstt = (size_t)-1;
-    for (size_t q = 0; q < y1.size(); ++q) dy += std::memcmp(&y1[q], &y2[q], 8) != 0;
-    for (size_t q = 0; q < t1.size(); ++q) if (std::memcmp(&t1[q], &t2[q], 8) != 0) { if (firstt == (size_t)-1) firstt = q; ++dt; }
-    fprintf(stderr, "[glba debug] fused product twice: %zu of %zu yhat entries differ, %zu of %zu tile sums differ (first at tile %zu slot %zu comp %zu: %.17g vs %.17g), n_ovf %d\n",
-            dy, y1.size(), dt, t1.size(), firstt == (size_t)-1 ? 0 : firstt / (6 * TSLOTS), firstt == (size_t)-1 ? 0 : (firstt / 6) % TSLOTS, firstt == (size_t)-1 ? 0 : firstt % 6,
-            firstt == (size_t)-1 ? 0.0 : t1[firstt], firstt == (size_t)-1 ? 0.0 : t2[firstt], ctx->n_ovf);
-  }
   const int poll = 8;
   int launched = 0;
   // the stop test lags one product behind the update (single-reduction recurrence): max_it updates need max_it + 1 launches
@@ -1386,7 +1368,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   g_pdl_max_grid = 2u * (unsigned)ctx->n_sm;
   if (const char* e = std::getenv("GLBA_PDL")) { g_pdl = (e[0] != '0'); if (e[0] == '2') g_pdl_max_grid = 0x7fffffffu; }   // diagnostic: 0 = plain launches, 2 = every launch
   if (const char* e = std::getenv("GLBA_HOST_LM")) ctx->env_host_lm = (e[0] == '1');   // diagnostic: host-side accept/reject for small windows
-  if (const char* e = std::getenv("GLBA_FUSED")) ctx->env_fused = (e[0] != '0');       // diagnostic: GLBA_FUSED=0 = two-kernel implicit product
+  if (const char* e = std::getenv("GLBA_FUSED")) ctx->env_fused = (e[0] == '1');       // experiment: GLBA_FUSED=1 = both halves of the implicit product in one tile kernel
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }

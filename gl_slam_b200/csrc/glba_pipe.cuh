@@ -648,6 +648,10 @@ k_pt_pipe(const PmArgs A, const TileMeta M, const double4* __restrict__ rec_pm, 
     }
     if (MODE == 2) {
       // ---- camera half of the product, fused: yhat_i += J^' (J~p u_j) summed per camera SLOT of the tile -----------------
+      // EXPERIMENT (GLBA_FUSED=1, off by default).  It removes k_spmv_cm and its 68 B/observation, but measured on C4 the PCG
+      // iteration got SLOWER (221 vs 156 us): the recomputation of the Jacobian rows, two more barriers per tile, the serial
+      // per-slot sums of phase 4 and 3 instead of 4 CTAs per SM cost more than the saved 58 us kernel.  Kept because it is
+      // parity-tested (same trajectories as the two-kernel product) and is the starting point for a cheaper slot reduction.
       __syncthreads();                  // (C) u_j of the tile's points are in S.us
 #pragma unroll
       for (int m = 0; m < P_OPT; ++m) {
