@@ -118,16 +118,23 @@ def ctx_large():
     # 32 distinct cameras (slot 255: global gather of the camera rows)
     ("scattered_cameras", dict(n_cam=90, n_pt=4000, track_len=lambda rng, n: 2 + rng.poisson(2.0, size=n), seed=9, loop=True,
                                creation_order=False, rot_sigma=0.002, pos_sigma=0.02), dict(max_iters=6)),
+    # the opt-in fused implicit product (GLBA_FUSED=1, k_pt_pipe<2>): per-tile slot sums ...
+    ("fused_banded", dict(n_cam=24, n_pt=3000, track_len=lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=41, rot_sigma=0.003, pos_sigma=0.03), {}),
+    # ... and its overflow rows (observations whose camera found no slot in their tile)
+    ("fused_scattered_cameras", dict(n_cam=90, n_pt=4000, track_len=lambda rng, n: 2 + rng.poisson(2.0, size=n), seed=9, loop=True,
+                                     creation_order=False, rot_sigma=0.002, pos_sigma=0.02), dict(max_iters=6)),
 ])
 def test_pipelined_tile_kernels_match_oracle(oracle, name, kw, okw):
     import os
     prob = scene.make_scene(**kw)
-    if name == "banded":
+    if name.endswith("banded"):
         prob.cam[2, :3] = 0.0                     # exactly-identity keyframe: the small-angle branch inside the tile kernels
     ref, so = oracle.solve(prob, oracle.options(**okw))
     os.environ["GLBA_TILE"] = "large"
-    if name == "scattered_cameras":
+    if name.endswith("scattered_cameras"):
         os.environ["GLBA_RELABEL"] = "0"
+    if name.startswith("fused"):
+        os.environ["GLBA_FUSED"] = "1"
     try:
         with g.Context(device=0) as c:
             got, s = c.solve(prob, g.options(linsolve=g.LINSOLVE_PCG, **okw))
@@ -135,7 +142,8 @@ def test_pipelined_tile_kernels_match_oracle(oracle, name, kw, okw):
     finally:
         os.environ.pop("GLBA_TILE", None)
         os.environ.pop("GLBA_RELABEL", None)
-    check_trajectory(s, so, rtol=1e-9 if name != "scattered_cameras" else 1e-8)
+        os.environ.pop("GLBA_FUSED", None)
+    check_trajectory(s, so, rtol=1e-9 if not name.endswith("scattered_cameras") else 1e-8)
     check_state(prob, got.cam, got.pt, ref.cam, ref.pt)
     O = oracle.linearize(prob, 1e4, oracle.options(**okw), per_obs=False)
     assert abs(L.cost - O.cost) <= 1e-12 * abs(O.cost)
