@@ -267,7 +267,7 @@ int validate_options(glba_ctx* ctx, const glba_options* o) {
 // context is created (a process may hold contexts on several devices, and on several threads).
 int set_func_attributes(glba_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double))));
-  CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DN_TP * DN_MAXCAM * 24 * 8 + 2048)));
+  CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)DN_TP * DN_MAXCAM * 24 + (size_t)(DN_MAXCAM * (DN_MAXCAM + 1) / 2) * 36) * 8 + DN_TP * 4 + 64)));
   CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
   CU(cudaFuncSetAttribute(k_lin_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinSmem)));
   CU(cudaFuncSetAttribute(k_pt_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<0>)));
@@ -954,7 +954,7 @@ int do_dense(glba_ctx* ctx, const glba_options* o, double radius, const LmCtl* c
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam;
   const int n = 6 * n_cam;
-  const size_t sm_schur = (size_t)DN_TP * n_cam * 24 * sizeof(double) + DN_TP * sizeof(unsigned) + 2 * (size_t)(n_cam * (n_cam + 1) / 2) + 16;
+  const size_t sm_schur = ((size_t)DN_TP * n_cam * 24 + (size_t)(n_cam * (n_cam + 1) / 2) * 36) * sizeof(double) + DN_TP * sizeof(unsigned) + 16;
   const size_t sm_solve = ((size_t)n * (n | 1) + 2 * (size_t)n) * sizeof(double);
   const int len = (n_cam * (n_cam + 1) / 2) * 36 + n;
   mark(ctx, PH_SCHUR);

@@ -16,7 +16,7 @@ namespace glba {
 
 constexpr int DN_MAXCAM = 16;            // reduced dimension <= 96
 constexpr int DN_NT = 256;
-constexpr int DN_TP = 64;                // points staged per tile (64 x n_cam x 192 B of shared memory: 196 KB at 16 cameras)
+constexpr int DN_TP = 40;                // points staged per tile (40 x n_cam x 192 B of shared memory: 123 KB at 16 cameras, beside 39 KB of accumulators)
 constexpr int DN_SLOTS = 4;              // threads that walk one point's track while staging
 constexpr int DN_PAIRS_PER_PASS = DN_NT / 36;                                                   // 7
 constexpr int DN_MAXQ = (DN_MAXCAM * (DN_MAXCAM + 1) / 2 + DN_PAIRS_PER_PASS - 1) / DN_PAIRS_PER_PASS;  // 20
@@ -47,22 +47,16 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
   double* V = dsm;                                   // [DN_TP][n_cam][18]
   double* Wu = V + (size_t)DN_TP * n_cam * 18;       // [DN_TP][n_cam][6]
   unsigned* pres = reinterpret_cast<unsigned*>(Wu + (size_t)DN_TP * n_cam * 6);   // [DN_TP]
+  double* Sacc = reinterpret_cast<double*>(pres + DN_TP + (DN_TP & 1));     // [n_pairs][36]: this CTA's copy of the block-upper S
+  __shared__ uint8_t plist[DN_TP][DN_MAXCAM];       // the cameras observing each staged point, ascending
+  __shared__ uint8_t pair_a[DN_MAXCAM * (DN_MAXCAM + 1) / 2], pair_b[DN_MAXCAM * (DN_MAXCAM + 1) / 2];
   const int tid = threadIdx.x;
-  const int sub = tid / 36, ent = tid - sub * 36;    // sub-CTA of 36 threads: one 6x6 block
-  const int rr = ent / 6, cc = ent - rr * 6;
-  const bool acc_active = sub < DN_PAIRS_PER_PASS;
-  double acc[DN_MAXQ];
-  unsigned pk_need[DN_MAXQ], pk_off[DN_MAXQ];        // per (thread, q): presence bits of the pair's two cameras, offsets of its two V rows
-#pragma unroll
-  for (int q = 0; q < DN_MAXQ; ++q) {
-    acc[q] = 0.0;
-    const int pr = sub + q * DN_PAIRS_PER_PASS;
-    int i = 0, rem = pr;
-    const bool ok = acc_active && pr < n_pairs;
-    if (ok) while (rem >= n_cam - i) { rem -= n_cam - i; ++i; }
-    const int k = i + rem;
-    pk_need[q] = ok ? ((1u << i) | (1u << k)) : 0xffffffffu;     // never satisfied: a mask has at most DN_MAXCAM bits
-    pk_off[q] = ok ? ((unsigned)(i * 18 + rr * 3) | ((unsigned)(k * 18 + cc * 3) << 16)) : 0u;
+  for (int t = tid; t < n_pairs * 36; t += DN_NT) Sacc[t] = 0.0;
+  // pair q of a point's camera list, a <= b, ordered by b then a: the first t(t+1)/2 entries are the pairs of a t-camera list
+  if (tid < DN_MAXCAM * (DN_MAXCAM + 1) / 2) {
+    int b2 = 0;
+    while ((b2 + 1) * (b2 + 2) / 2 <= tid) ++b2;
+    pair_a[tid] = (uint8_t)(tid - b2 * (b2 + 1) / 2); pair_b[tid] = (uint8_t)b2;
   }
   double racc = 0.0;                                 // thread t < 6*n_cam: rhs entry t
   const int p_begin = blockIdx.x * pts_per_cta;
@@ -73,7 +67,7 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
     if (tid < DN_TP) pres[tid] = 0u;
     __syncthreads();
     const int j = base + pl;
-    if (j < p_end && A.pt_free[j]) {
+    if (pl < DN_TP && j < p_end && A.pt_free[j]) {
       const int b = A.pt_start[j], e = A.pt_start[j + 1];
       for (int k = b + slot; k < e; k += DN_SLOTS) {
         const int i = A.pm_cam[k];
@@ -114,37 +108,43 @@ k_dense_schur(const PmArgs A, const int n_cam, const uint8_t* __restrict__ cam_f
       }
     }
     __syncthreads();
+    if (tid < DN_TP) {                                // camera list of every staged point
+      unsigned m = pres[tid];
+      int q = 0;
+      while (m) { const int i = __ffs(m) - 1; plist[tid][q++] = (uint8_t)i; m &= m - 1; }
+    }
+    __syncthreads();
+    // Accumulate point by point.  A point seen by t cameras contributes t(t+1)/2 blocks of 36 entries: those (pair, entry)
+    // tasks are spread over the CTA, every task adds into ITS accumulator in shared memory, and a barrier separates the
+    // points, so each accumulator receives its contributions in point order (fixed) and no two threads ever touch the same
+    // one at a time.  (The first version gave every thread a fixed set of pairs in registers and tested each point's
+    // presence mask against them: 82 % of the tests failed on 4-camera tracks and that loop was 80 % of the kernel.)
     const int np = min(DN_TP, p_end - base);
     for (int p = 0; p < np; ++p) {
       const unsigned mask = pres[p];
-      if (!mask) continue;
-      if (acc_active) {
+      if (mask) {                                     // uniform over the CTA
+        const int t = __popc(mask);
+        const int ntask = (t * (t + 1) / 2) * 36;
         const double* Vp = V + (size_t)p * n_cam * 18;
-#pragma unroll
-        for (int q = 0; q < DN_MAXQ; ++q) {
-          // the pair of this (thread, q) is the same for every point: it lives in a register (pk[q]), not in a shared table
-          const unsigned need = pk_need[q];
-          if ((mask & need) == need) {
-            const double* vi = Vp + (pk_off[q] & 0xffffu);
-            const double* vk = Vp + (pk_off[q] >> 16);
-            acc[q] += vi[0] * vk[0] + vi[1] * vk[1] + vi[2] * vk[2];
-          }
+        for (int task = tid; task < ntask; task += DN_NT) {
+          const int pi = task / 36, ent = task - pi * 36;
+          const int rr = ent / 6, cc = ent - rr * 6;
+          const int i = plist[p][pair_a[pi]], k = plist[p][pair_b[pi]];                  // the a-th and b-th observing cameras, i <= k
+          const int pr = i * n_cam - (i * (i - 1)) / 2 + (k - i);
+          const double* vi = Vp + i * 18 + rr * 3;
+          const double* vk = Vp + k * 18 + cc * 3;
+          Sacc[pr * 36 + ent] += vi[0] * vk[0] + vi[1] * vk[1] + vi[2] * vk[2];
+        }
+        if (tid < 6 * n_cam) {
+          const int i = tid / 6;
+          if ((mask >> i) & 1u) racc += Wu[((size_t)p * n_cam + i) * 6 + (tid - 6 * i)];
         }
       }
-      if (tid < 6 * n_cam) {
-        const int i = tid / 6;
-        if ((mask >> i) & 1u) racc += Wu[((size_t)p * n_cam + i) * 6 + (tid - 6 * i)];
-      }
+      __syncthreads();
     }
   }
   double* out = part + (size_t)blockIdx.x * ((size_t)n_pairs * 36 + 6 * n_cam);
-  if (acc_active) {
-#pragma unroll
-    for (int q = 0; q < DN_MAXQ; ++q) {
-      const int pr = sub + q * DN_PAIRS_PER_PASS;
-      if (pr < n_pairs) out[(size_t)pr * 36 + ent] = acc[q];
-    }
-  }
+  for (int t = tid; t < n_pairs * 36; t += DN_NT) out[t] = Sacc[t];
   if (tid < 6 * n_cam) out[(size_t)n_pairs * 36 + tid] = racc;
 }
 
@@ -166,8 +166,16 @@ __global__ void k_dense_reduce(const int n_parts, const int n_cam, const double*
   const bool valid = t < len;
   double s = 0.0;
   if (n_parts > 0) {
-    if (valid)
-      for (int g = sub; g < n_parts; g += 8) s += part[(size_t)g * len + t];
+    if (valid) {
+      // same summation order as one load at a time, four loads in flight
+      int g = sub;
+      for (; g + 24 < n_parts; g += 32) {
+        const double v0 = part[(size_t)g * len + t], v1 = part[(size_t)(g + 8) * len + t], v2 = part[(size_t)(g + 16) * len + t],
+                     v3 = part[(size_t)(g + 24) * len + t];
+        s += v0; s += v1; s += v2; s += v3;
+      }
+      for (; g < n_parts; g += 8) s += part[(size_t)g * len + t];
+    }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (valid && sub == 0) Sred[t] = s;

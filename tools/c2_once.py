@@ -3,4 +3,6 @@ import gl_slam_b200 as g
 from gl_slam_b200 import scene
 ctx = g.Context(0)
 p = scene.config("C2")
-ctx.solve(p); _, s = ctx.solve(p); print(s['n_iters'])
+for _ in range(3):
+    _, s = ctx.solve(p)
+print(s["n_iters"], s["final_cost"])
