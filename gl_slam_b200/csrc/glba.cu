@@ -84,6 +84,8 @@ struct glba_ctx {
   int device = 0, rank = 0, world = 1;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t side_stream = nullptr;          // camera finalisation of a linearisation, concurrent with the Schur pass (single GPU)
+  cudaEvent_t ev_side[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;          // host uploads of load_problem, overlapped with the index construction
   cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
   bool copies_in_flight = false;
@@ -175,7 +177,15 @@ int fail(glba_ctx* c, int code, const char* fmt, ...) {
 // launched before it are small (at most two CTAs per SM): that is the small-window solve; large maps launch plainly.
 bool g_pdl = true;
 unsigned g_pdl_max_grid = 296;
-thread_local bool g_prev_small = false;
+struct PrevLaunch { cudaStream_t stream; bool small; };
+thread_local PrevLaunch g_prev[4] = {{nullptr, false}, {nullptr, false}, {nullptr, false}, {nullptr, false}};     // per stream (a context uses two)
+inline bool& prev_small(cudaStream_t s) {
+  for (auto& e : g_prev) if (e.stream == s) return e.small;
+  static thread_local int next = 0;
+  PrevLaunch& e = g_prev[next++ & 3];
+  e.stream = s; e.small = false;
+  return e.small;
+}
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(cudaStream_t stream, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -184,8 +194,9 @@ inline void launch_kernel(cudaStream_t stream, void (*kernel)(KArgs...), dim3 gr
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   const bool small = grid.x * grid.y * grid.z <= g_pdl_max_grid;
-  cfg.attrs = attr; cfg.numAttrs = (g_pdl && small && g_prev_small) ? 1 : 0;
-  g_prev_small = small;
+  bool& prev = prev_small(stream);
+  cfg.attrs = attr; cfg.numAttrs = (g_pdl && small && prev) ? 1 : 0;
+  prev = small;
   (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);       // launch errors are sticky: check_launches() per phase
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
@@ -799,6 +810,19 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   if (n_pt) { const int s__ = launch_linearize_points(ctx, o, first, radius); if (s__) return s__; }
   if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>(), (const LmCtl*)nullptr);
+  // Single GPU, large maps: the camera finalisation of the linearisation (B_i, g_i, scaling, LM diagonal: ~11 us of dependent
+  // arithmetic on 29 CTAs) needs only k_linearize_cm's sums, so it runs on a side stream WHILE the Schur pass streams the
+  // records; the Schur finalisation waits for both.
+  const bool side = with_schur && !sharded && n_cam > 0 && ctx->n_chunks > 0 && ctx->n_obs >= 200000;
+  if (side) {
+    CU(cudaEventRecord(ctx->ev_side[0], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side[0], 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->side_stream;
+    launch_cam_lin_fin(ctx, o, first);
+    ctx->stream = main_stream;
+    CU(cudaEventRecord(ctx->ev_side[1], ctx->side_stream));
+  }
   if (with_schur) {
     mark(ctx, PH_SCHUR);
     if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
@@ -824,7 +848,8 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
     else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     mark(ctx, with_schur ? PH_SCHUR : PH_LIN);
   }
-  if (n_cam) launch_cam_lin_fin(ctx, o, first);
+  if (side) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side[1], 0));
+  else if (n_cam) launch_cam_lin_fin(ctx, o, first);
   if (with_schur && n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
   ctx->schur_fresh = with_schur;
   mark(ctx, -1);
@@ -1374,6 +1399,8 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
   else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GLBA_E_CUDA; } ctx->own_stream = true; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
+  for (auto& e : ctx->ev_side) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   for (auto& e : ctx->ev_copy) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
   if (cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * NSCAL) != cudaSuccess || cudaMallocHost((void**)&ctx->h_cg, sizeof(CgState)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_flags, 16 * sizeof(int)) != cudaSuccess) { glba_destroy(ctx); return GLBA_E_CUDA; }
@@ -1404,6 +1431,8 @@ void glba_destroy(glba_ctx* ctx) {
   if (ctx->h_cg) cudaFreeHost(ctx->h_cg);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  for (auto& e : ctx->ev_side) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->ev_copy) if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
