@@ -295,6 +295,16 @@ def main():
     except Exception:
         pass
     kernels["small_kernels"] = {"ms": kt["small_kernels_ms"]}
+    if kt["n_pair_blocks"] > 0:
+        # assembled reduced camera matrix (single GPU): per instance two 32-B records, the point's 48-B inverse block and its
+        # 16-B index entry; per block one 288-B store
+        pb = kt["n_pair_instances"] * (2 * 32 + 48 + 16) + kt["n_pair_blocks"] * 288
+        kernels["schur_pairs"] = {"ms": kt["schur_pairs_ms"], "instances": kt["n_pair_instances"], "blocks": kt["n_pair_blocks"],
+                                  "algorithmic_bytes": pb, "gbs": pb / (kt["schur_pairs_ms"] * 1e-3) / 1e9,
+                                  "frac": pb / (kt["schur_pairs_ms"] * 1e-3) / 1e9 / peak, "kernel": "k_schur_pairs, once per LM iteration"}
+        kernels["pcg_iteration"] = {"ms": kt["bsr_spmv_ms"], "kernel": "k_cg_bsr (cooperative, whole PCG in one launch): product on the blocks, "
+                                    "dot products, vector updates, two grid barriers", "block_bytes": kt["n_pair_blocks"] * 288}
+        kernels["pair_setup"] = {"ms": kt["pair_setup_ms"], "what": "structure of the loaded map (pair instances, radix sorts), once per load"}
     if world > 1:
         kernels["allreduce"] = {"ms": kt["allreduce_ms"], "bytes": kt["exchange_bytes"], "cameras_on_this_rank": kt["n_local_cams"],
                                 "cameras_exchanged": kt["n_shared_cams"], "layout": "owner-computes: only cameras observed by >= 2 ranks are exchanged"}
@@ -328,7 +338,9 @@ def main():
               "cg_iters": s["cg_iters"][1:], "cost": [s["initial_cost"], s["final_cost"]],
               "mode": "inexact Newton: PCG rel tol 1e-2, <= 40 iterations",
               "device_ms": {k: s[k] for k in ("t_linearize_ms", "t_schur_ms", "t_solve_ms", "t_update_ms", "t_comm_ms")},
-              "linearizations": s["n_linearizations"]}
+              "linearizations": s["n_linearizations"],
+              "reduced_system": ("assembled block-sparse matrix (glba_sparse.cuh): one assembly per LM iteration, PCG in one cooperative launch"
+                                 if kt["n_pair_blocks"] > 0 else "matrix-free product (two streaming passes per PCG iteration)")}
         ctx.reset_resident()
         if world == 1:
             # the same iterations with the reduced system solved to parity precision (PCG 1e-13, no iteration cap)

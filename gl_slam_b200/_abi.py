@@ -85,7 +85,9 @@ class Linearization(C.Structure):
 class KernelTimes(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("linearize_pm_ms", "linearize_cm_ms", "schur_cm_ms", "spmv_pm_ms", "spmv_cm_ms",
                                           "backsub_cost_ms", "point_damp_ms", "small_kernels_ms", "allreduce_ms", "chunk_sum_ms",
-                                          "exchange_bytes")] + [("n_local_cams", C.c_int32), ("n_shared_cams", C.c_int32)]
+                                          "exchange_bytes")] + [("n_local_cams", C.c_int32), ("n_shared_cams", C.c_int32)] + \
+               [(k, C.c_double) for k in ("schur_pairs_ms", "bsr_spmv_ms", "pair_setup_ms")] + \
+               [("n_pair_instances", C.c_int64), ("n_pair_blocks", C.c_int32), ("reserved_", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

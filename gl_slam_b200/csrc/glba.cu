@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
@@ -29,6 +30,7 @@
 #include "glba_tiles.cuh"
 #include "glba_pipe.cuh"
 #include "glba_cam.cuh"
+#include "glba_sparse.cuh"
 #include "glba_triang.cuh"
 
 using namespace glba;
@@ -129,6 +131,14 @@ struct glba_ctx {
   Buf ovf_raw, ovf_k, ovf_c, ovf_key, ovf_key2, ovf_val, cam_ov, cam_ov_start;      // observations without a camera slot in their tile
   int n_ovf = 0, ovf_cap = 0;
   int occ_pt2 = 0;
+  // explicit block-sparse reduced camera matrix (glba_sparse.cuh): structure built lazily at the first PCG solve of a loaded problem
+  bool env_explicit = true;      // diagnostic: GLBA_EXPLICIT=0 keeps the implicit (matrix-free) product
+  bool sp_tried = false, use_explicit = false;
+  int n_pairs = 0;
+  long long n_inst = 0;
+  Buf sp_cnt, sp_off, sp_key, sp_key2, sp_val, sp_inst, sp_ukey, sp_ucnt, sp_nruns, sp_pair_a, sp_pair_b, sp_pair_start;
+  Buf sp_ekey, sp_ekey2, sp_eval, sp_eval2, sp_erow, sp_ent, sp_row_start, sp_blocks, sp_part, sp_bar;
+  int cg_grid = 0;               // CTAs of the cooperative PCG kernel (all resident)
   int occ_lin = 0, occ_pt0 = 0, occ_pt1 = 0;   // resident CTAs per SM of the pipelined kernels (occupancy API, per context)
   int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
   int n_tiles = 0, max_track = 0, grid_c = 0;
@@ -503,6 +513,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   if (n_cam) LAUNCH(k_free_flags_cnt, cdiv(n_cam, 256), 256, n_cam, (const int*)ctx->cam_cnt.as<int>(), d_cfix, ctx->cam_free.as<uint8_t>());
   if (n_pt) LAUNCH(k_free_flags, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), d_pfix, n2o, ctx->pt_free.as<uint8_t>());
   ctx->has_dup = false;
+  ctx->sp_tried = false; ctx->use_explicit = false; ctx->n_pairs = 0; ctx->n_inst = 0;
   if (n > 0) LAUNCH(k_max_track, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), ctx->flags.as<int>() + 4);
   CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(ctx->h_flags + 5, ctx->cam_cnt.as<int>() + n_cam, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));   // global duplicate flag, #empty shards
@@ -902,6 +913,128 @@ int do_schur(glba_ctx* ctx, double radius) {
   return GLBA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Explicit block-sparse reduced camera matrix (glba_sparse.cuh).  ensure_explicit() builds the structure of the loaded
+// problem once (device sorts; two small read-backs for the counts); launch_schur_pairs() fills the blocks for the current
+// linearisation and damping.  Used on a single GPU when the structure is moderate: no duplicate (point, camera)
+// observations, at most 16 instances per observation (very long tracks make the assembly dearer than the products it
+// saves) and at most 1 GiB of blocks.  Everything else keeps the matrix-free product.
+// ---------------------------------------------------------------------------------------------
+int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
+  (void)o;
+  if (ctx->sp_tried) return GLBA_OK;
+  ctx->sp_tried = true; ctx->use_explicit = false;
+  const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
+  if (!ctx->env_explicit || ctx->world > 1 || ctx->has_dup || ctx->n_free_cam < 2 || n_pt == 0 || ctx->n_obs == 0) return GLBA_OK;
+  cudaStream_t s = ctx->stream;
+  mark(ctx, PH_SETUP);
+  ENSURE(long long, ctx->sp_cnt, (size_t)n_pt + 1); ENSURE(long long, ctx->sp_off, (size_t)n_pt + 1);
+  LAUNCH(k_pair_count, cdiv((long)n_pt + 1, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(),
+         (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const uint8_t*)ctx->pt_free.as<uint8_t>(), ctx->sp_cnt.as<long long>());
+  size_t tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->sp_cnt.as<long long>(), ctx->sp_off.as<long long>(), n_pt + 1, s));
+  ENSURE(char, ctx->sort_tmp, tb);
+  tb = ctx->sort_tmp.cap;
+  CU(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tb, ctx->sp_cnt.as<long long>(), ctx->sp_off.as<long long>(), n_pt + 1, s));
+  g_launches.fetch_add(1);
+  long long n_inst = 0;
+  CU(cudaMemcpyAsync(&n_inst, ctx->sp_off.as<long long>() + n_pt, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (n_inst <= 0 || n_inst > 16 * (long long)ctx->n_obs || n_inst > 0x7fffffffLL - 64) { mark(ctx, -1); return GLBA_OK; }
+  ENSURE(unsigned long long, ctx->sp_key, (size_t)n_inst); ENSURE(unsigned long long, ctx->sp_key2, (size_t)n_inst);
+  ENSURE(int4, ctx->sp_val, (size_t)n_inst); ENSURE(int4, ctx->sp_inst, (size_t)n_inst);
+  LAUNCH(k_pair_emit, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(),
+         (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const long long*)ctx->sp_off.as<long long>(), n_cam,
+         ctx->sp_key.as<unsigned long long>(), ctx->sp_val.as<int4>());
+  int bits = 1; while ((1ULL << bits) < (unsigned long long)n_cam * (unsigned long long)n_cam && bits < 63) ++bits;
+  tb = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
+                                     ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
+  ENSURE(char, ctx->sort_tmp, tb);
+  tb = ctx->sort_tmp.cap;
+  CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
+                                     ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
+  // distinct keys = blocks; run lengths = instances per block
+  ENSURE(unsigned long long, ctx->sp_ukey, (size_t)n_inst); ENSURE(int, ctx->sp_ucnt, (size_t)n_inst + 1); ENSURE(int, ctx->sp_nruns, 1);
+  tb = 0;
+  CU(cub::DeviceRunLengthEncode::Encode(nullptr, tb, ctx->sp_key2.as<unsigned long long>(), ctx->sp_ukey.as<unsigned long long>(), ctx->sp_ucnt.as<int>(),
+                                        ctx->sp_nruns.as<int>(), (int)n_inst, s));
+  ENSURE(char, ctx->sort_tmp, tb);
+  tb = ctx->sort_tmp.cap;
+  CU(cub::DeviceRunLengthEncode::Encode(ctx->sort_tmp.p, tb, ctx->sp_key2.as<unsigned long long>(), ctx->sp_ukey.as<unsigned long long>(), ctx->sp_ucnt.as<int>(),
+                                        ctx->sp_nruns.as<int>(), (int)n_inst, s));
+  g_launches.fetch_add(2);
+  int n_pairs = 0;
+  CU(cudaMemcpyAsync(&n_pairs, ctx->sp_nruns.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (n_pairs <= 0 || (size_t)n_pairs * 288 > ((size_t)1 << 30)) { mark(ctx, -1); return GLBA_OK; }
+  ENSURE(int, ctx->sp_pair_start, (size_t)n_pairs + 1);
+  CU(cudaMemsetAsync(ctx->sp_ucnt.as<int>() + n_pairs, 0, sizeof(int), s));
+  tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->sp_ucnt.as<int>(), ctx->sp_pair_start.as<int>(), n_pairs + 1, s));
+  ENSURE(char, ctx->sort_tmp, tb);
+  tb = ctx->sort_tmp.cap;
+  CU(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tb, ctx->sp_ucnt.as<int>(), ctx->sp_pair_start.as<int>(), n_pairs + 1, s));
+  // row lists: both triangles, sorted by (row, column)
+  const int n_ent = 2 * n_pairs;
+  ENSURE(int, ctx->sp_pair_a, n_pairs); ENSURE(int, ctx->sp_pair_b, n_pairs);
+  ENSURE(unsigned long long, ctx->sp_ekey, n_ent); ENSURE(unsigned long long, ctx->sp_ekey2, n_ent); ENSURE(int, ctx->sp_eval, n_ent); ENSURE(int, ctx->sp_eval2, n_ent);
+  ENSURE(int, ctx->sp_erow, n_ent); ENSURE(int2, ctx->sp_ent, n_ent); ENSURE(int, ctx->sp_row_start, (size_t)n_cam + 2);
+  LAUNCH(k_pair_rows, cdiv(n_pairs, 256), 256, n_pairs, (const unsigned long long*)ctx->sp_ukey.as<unsigned long long>(), n_cam, ctx->sp_pair_a.as<int>(),
+         ctx->sp_pair_b.as<int>(), ctx->sp_ekey.as<unsigned long long>(), ctx->sp_eval.as<int>());
+  tb = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->sp_ekey.as<unsigned long long>(), ctx->sp_ekey2.as<unsigned long long>(), ctx->sp_eval.as<int>(),
+                                     ctx->sp_eval2.as<int>(), n_ent, 0, bits, s));
+  ENSURE(char, ctx->sort_tmp, tb);
+  tb = ctx->sort_tmp.cap;
+  CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->sp_ekey.as<unsigned long long>(), ctx->sp_ekey2.as<unsigned long long>(), ctx->sp_eval.as<int>(),
+                                     ctx->sp_eval2.as<int>(), n_ent, 0, bits, s));
+  g_launches.fetch_add(3);
+  LAUNCH(k_pair_entries, cdiv(n_ent, 256), 256, n_ent, (const unsigned long long*)ctx->sp_ekey2.as<unsigned long long>(), (const int*)ctx->sp_eval2.as<int>(), n_cam,
+         ctx->sp_erow.as<int>(), ctx->sp_ent.as<int2>());
+  LAUNCH(k_segment_starts, cdiv(n_cam + 1, 256), 256, (long)n_ent, (const int*)ctx->sp_erow.as<int>(), n_cam, ctx->sp_row_start.as<int>());
+  ENSURE(double, ctx->sp_blocks, (size_t)36 * n_pairs);
+  // the PCG runs in one cooperative launch: every CTA must be resident
+  int coop = 0, occ = 0;
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_bsr, NT_CGP, 0));
+  if (!coop || occ < 1) { mark(ctx, -1); return GLBA_OK; }
+  ctx->cg_grid = std::max(1, std::min(ctx->n_sm, cdiv(n_cam, NT_CGP / 32)));
+  ENSURE(double, ctx->sp_part, 2 * (size_t)ctx->cg_grid); ENSURE(unsigned, ctx->sp_bar, 1);
+  CHECK_LAUNCHES();
+  // (the sort scratch stays allocated: a context that solves map after map would pay cudaMalloc / cudaFree of ~50 B per
+  // instance at every load: measured 190 ms against 7 ms on C4)
+  ctx->n_pairs = n_pairs; ctx->n_inst = n_inst; ctx->use_explicit = true;
+  mark(ctx, -1);
+  return GLBA_OK;
+}
+
+void launch_schur_pairs(glba_ctx* ctx) {
+  const int c = ctx->cur;
+  LAUNCH(k_schur_pairs, cdiv((long)ctx->n_pairs * 32, NT_SP), NT_SP, ctx->n_pairs, (const int*)ctx->sp_pair_a.as<int>(), (const int*)ctx->sp_pair_b.as<int>(),
+         (const int*)ctx->sp_pair_start.as<int>(), (const int4*)ctx->sp_inst.as<int4>(), (const double4*)ctx->rec_pm.as<double4>(),
+         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), ctx->K, ctx->sp_blocks.as<double>());
+}
+// the whole PCG in one cooperative launch (k_cg_bsr); cg receives iterations and stop reason
+int launch_cg_bsr(glba_ctx* ctx, const glba_options* o, int max_it) {
+  const int n_cam = ctx->n_cam;
+  CU(cudaMemsetAsync(ctx->sp_bar.p, 0, sizeof(unsigned), ctx->stream));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctx->cg_grid); cfg.blockDim = dim3(NT_CGP); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  prev_small(ctx->stream) = false;
+  CU(cudaLaunchKernelEx(&cfg, k_cg_bsr, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const int*)ctx->sp_row_start.as<int>(),
+                        (const int2*)ctx->sp_ent.as<int2>(), (const double*)ctx->sp_blocks.as<double>(), (const double*)ctx->Md.as<double>(),
+                        (const double*)ctx->Minv.as<double>(), (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(),
+                        ctx->cg_q.as<double>(), ctx->cg_p.as<double>(), ctx->pg.as<double>(), ctx->yg.as<double>(), ctx->sp_part.as<double>(),
+                        ctx->sp_bar.as<unsigned>(), ctx->cgst.as<CgState>(), o->cg_rel_tol, max_it));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return GLBA_OK;
+}
+
 // vectors of the single-reduction PCG (glba_cam.cuh): x = cg_x, r = cg_r, u = M^-1 r = cg_q, p = cg_p, s = S p = pg, w = S u = yg
 int launch_cg_iteration(glba_ctx* ctx, const glba_options* o, double radius, CgState* cg, int li) {
   const int c = ctx->cur;
@@ -956,6 +1089,18 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   const int dim = 6 * ctx->n_free_cam;
   const int max_it = o->cg_max_iters > 0 ? o->cg_max_iters : std::min(4000, 4 * dim);
   CgState* cg = ctx->cgst.as<CgState>();
+  if (ctx->use_explicit) {
+    // assembled reduced camera matrix: blocks for this linearisation and damping, then the whole PCG in one launch
+    mark(ctx, PH_SCHUR); launch_schur_pairs(ctx); mark(ctx, PH_SOLVE);
+    const int s__ = launch_cg_bsr(ctx, o, max_it); if (s__) return s__;
+    CHECK_LAUNCHES();
+    CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_cg->reason == 4) return fail(ctx, GLBA_E_CUDA, "PCG grid barrier timed out");
+    *iters = ctx->h_cg->iters;
+    mark(ctx, -1);
+    return GLBA_OK;
+  }
   LAUNCH(k_cg_start, ctx->grid_c, NT_C, n_cam, (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->Minv.as<double>(),
          (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(), ctx->cg_q.as<double>(), ctx->cg_p.as<double>(),
          ctx->pg.as<double>(), ctx->xtab.as<double>(), cg, o->cg_rel_tol, max_it);
@@ -1149,6 +1294,7 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   const bool dense = want_dense(ctx, o);
   if (o->linsolve == GLBA_LINSOLVE_DENSE && !dense && ctx->n_free_cam > 0)
     return fail(ctx, GLBA_E_UNSUPPORTED, "dense solve needs <= %d cameras and no duplicate (point,camera) observations", DN_MAXCAM);
+  if (!dense && ctx->n_free_cam > 0) { if ((st = ensure_explicit(ctx, o))) return st; }
   if ((st = do_linearize_impl(ctx, o, 1, radius, !dense && !g2o))) return st;
   bool fresh = true;        // point blocks are damped for the current radius
   if (g2o) {                // computeLambdaInit: lambda0 = tau * max diag H over the free vertices
@@ -1393,6 +1539,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   g_pdl_max_grid = 2u * (unsigned)ctx->n_sm;
   if (const char* e = std::getenv("GLBA_PDL")) { g_pdl = (e[0] != '0'); if (e[0] == '2') g_pdl_max_grid = 0x7fffffffu; }   // diagnostic: 0 = plain launches, 2 = every launch
   if (const char* e = std::getenv("GLBA_HOST_LM")) ctx->env_host_lm = (e[0] == '1');   // diagnostic: host-side accept/reject for small windows
+  if (const char* e = std::getenv("GLBA_EXPLICIT")) ctx->env_explicit = (e[0] != '0'); // diagnostic: GLBA_EXPLICIT=0 = matrix-free product on every map
   if (const char* e = std::getenv("GLBA_FUSED")) ctx->env_fused = (e[0] == '1');       // experiment: GLBA_FUSED=1 = both halves of the implicit product in one tile kernel
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
@@ -1424,7 +1571,10 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->cinv, &ctx->u0p, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->tile_sobs, &ctx->tile_sstart, &ctx->tp_key, &ctx->tp_val, &ctx->tp_key2, &ctx->cam_tp, &ctx->cam_tp_start, &ctx->tpart, &ctx->cam_iota, &ctx->ovf_raw, &ctx->ovf_k, &ctx->ovf_c, &ctx->ovf_key, &ctx->ovf_key2, &ctx->ovf_val, &ctx->cam_ov, &ctx->cam_ov_start, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax};
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->tile_sobs, &ctx->tile_sstart, &ctx->tp_key, &ctx->tp_val, &ctx->tp_key2, &ctx->cam_tp, &ctx->cam_tp_start, &ctx->tpart, &ctx->cam_iota, &ctx->ovf_raw, &ctx->ovf_k, &ctx->ovf_c, &ctx->ovf_key, &ctx->ovf_key2, &ctx->ovf_val, &ctx->cam_ov, &ctx->cam_ov_start, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax,
+                &ctx->sp_cnt, &ctx->sp_off, &ctx->sp_key, &ctx->sp_key2, &ctx->sp_val, &ctx->sp_inst, &ctx->sp_ukey, &ctx->sp_ucnt, &ctx->sp_nruns, &ctx->sp_pair_a,
+                &ctx->sp_pair_b, &ctx->sp_pair_start, &ctx->sp_ekey, &ctx->sp_ekey2, &ctx->sp_eval, &ctx->sp_eval2, &ctx->sp_erow, &ctx->sp_ent, &ctx->sp_row_start,
+                &ctx->sp_blocks, &ctx->sp_part, &ctx->sp_bar};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1543,7 +1693,33 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   st = timed([&] {
     launch_cam_lin_fin(ctx, opt, 0);
     launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>()); }, &out->small_kernels_ms);
-  if (st || ctx->world == 1) return st;
+  if (st) return st;
+  if (ctx->world == 1) {
+    // explicit reduced camera matrix: structure (once per load), assembly, product
+    if (!ctx->sp_tried) {
+      cudaEventRecord(e0, ctx->stream);
+      if ((st = ensure_explicit(ctx, opt))) return st;
+      cudaEventRecord(e1, ctx->stream);
+      if (cudaEventSynchronize(e1) != cudaSuccess) return GLBA_E_CUDA;
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+      out->pair_setup_ms = ms;
+    }
+    if (ctx->use_explicit) {
+      // the timed launches above left Schur sums where the linearisation's belong: a consistent pass first
+      if ((st = do_linearize_schur(ctx, opt, 0, radius))) return st;
+      CU(cudaStreamSynchronize(ctx->stream));
+      ctx->ev_used = 0;
+      if ((st = timed([&] { launch_schur_pairs(ctx); }, &out->schur_pairs_ms))) return st;
+      // one PCG iteration on the blocks: (time of 1 + 32 iterations - time of 1 iteration) / 32, tolerance 0 so that none stops early
+      glba_options ot = *opt; ot.cg_rel_tol = 0.0;
+      double t1 = 0.0, t33 = 0.0;
+      if ((st = timed([&] { (void)launch_cg_bsr(ctx, &ot, 1); }, &t1))) return st;
+      if ((st = timed([&] { (void)launch_cg_bsr(ctx, &ot, 33); }, &t33))) return st;
+      out->bsr_spmv_ms = (t33 - t1) / 32.0;
+      out->n_pair_instances = ctx->n_inst; out->n_pair_blocks = ctx->n_pairs;
+    }
+    return GLBA_OK;
+  }
   // collective: every rank calls glba_time_kernels with the same reps
   out->n_local_cams = n_cam; out->n_shared_cams = ctx->owner ? ctx->n_shared : ctx->n_cam;
   out->exchange_bytes = 8.0 * ((ctx->owner ? 54.0 * ctx->n_shared : 54.0 * n_cam) + S_GSLOT0 + MAX_WORLD);

@@ -1,0 +1,356 @@
+// glba_sparse.cuh — the reduced camera matrix as an explicit block-sparse matrix.
+//
+// The implicit product of glba_pipe.cuh / k_spmv_cm streams every observation twice per PCG iteration (0.13 ms on a 5 M
+// observation map).  A SLAM map has banded covisibility: camera a shares points with a few dozen cameras only, so the
+// off-diagonal blocks of S are few (C4: ~30 k blocks of 6x6, 8 MB) and one assembly per LM iteration (every observation
+// pair of every track, once) replaces the two streaming passes of EVERY PCG iteration by a product that reads 8 MB from L2.
+// This is what the reference's solvers do on the CPU (Ceres SPARSE_SCHUR / g2o's BlockSolver build the reduced camera
+// matrix; /root/reference/src/core/slam_core.cpp:1079-1082 selects SPARSE_SCHUR).
+//
+// The sums run in the "hat" space of the camera kernels (glba_cam.cuh), S = B + lam/radius - T' S^ T with
+//     S^_ab = sum over points j seen by a and b of  J^_a' (J~p_a Cinv_j J~p_b') J^_b      (6x6, a != b),
+// and the assembly kernel stores S_ab = -T_a' S^_ab T_b, so the PCG works on plain camera vectors: w_a = Md_a u_a + sum_b S_ab u_b
+// with Md_a = S_aa from k_cam_schur_fin.
+//
+// Structure (built once per loaded problem, on the device, lazily at the first PCG solve):
+//   instance = (observation of a, observation of b, point) for every unordered pair of observations of one point whose
+//              cameras are both free; sorted (stable radix sort) by the pair key a * n_cam + b with a < b, so the instances
+//              of a block are contiguous and in point order;
+//   block p  = one distinct key; pair_start[p] .. pair_start[p+1] its instances;
+//   row list = for camera a the entries (b, p, transposed?) of row a of S^, both triangles, sorted by b.
+// Every sum runs in a fixed order (lane-strided partial sums + xor butterfly): results do not depend on scheduling.
+#pragma once
+#include "glba_kernels.cuh"
+#include "glba_cam.cuh"
+
+namespace glba {
+
+// number of instances of point j: f (f - 1) / 2 with f = its observations in free cameras; cnt[n_pt] = 0
+__global__ void k_pair_count(const int n_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, const uint8_t* __restrict__ cam_free,
+                             const uint8_t* __restrict__ pt_free, long long* __restrict__ cnt) {
+  pdl_grid_sync();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n_pt) return;
+  long long f = 0;
+  if (j < n_pt && pt_free[j])
+    for (int o = pt_start[j]; o < pt_start[j + 1]; ++o) f += cam_free[pm_cam[o]] ? 1 : 0;
+  cnt[j] = f * (f - 1) / 2;
+}
+
+__global__ void k_pair_emit(const int n_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, const uint8_t* __restrict__ cam_free,
+                            const uint8_t* __restrict__ pt_free, const long long* __restrict__ off, const int n_cam,
+                            unsigned long long* __restrict__ key, int4* __restrict__ val) {
+  pdl_grid_sync();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pt || !pt_free[j]) return;
+  long long pos = off[j];
+  const int e = pt_start[j + 1];
+  for (int oa = pt_start[j]; oa < e; ++oa) {
+    const int a = pm_cam[oa];
+    if (!cam_free[a]) continue;
+    for (int ob = oa + 1; ob < e; ++ob) {
+      const int b = pm_cam[ob];
+      if (!cam_free[b]) continue;
+      const bool sw = a > b;
+      key[pos] = (unsigned long long)(sw ? b : a) * (unsigned long long)n_cam + (unsigned long long)(sw ? a : b);
+      val[pos] = make_int4(sw ? ob : oa, sw ? oa : ob, j, 0);
+      ++pos;
+    }
+  }
+}
+
+// distinct keys -> cameras of the block and its two row entries (upper: as stored, lower: transposed)
+__global__ void k_pair_rows(const int n_pairs, const unsigned long long* __restrict__ ukey, const int n_cam, int* __restrict__ pair_a,
+                            int* __restrict__ pair_b, unsigned long long* __restrict__ ent_key, int* __restrict__ ent_val) {
+  pdl_grid_sync();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const unsigned long long k = ukey[p];
+  const int a = (int)(k / (unsigned long long)n_cam), b = (int)(k % (unsigned long long)n_cam);
+  pair_a[p] = a; pair_b[p] = b;
+  ent_key[2 * (size_t)p] = k;                                                                   ent_val[2 * (size_t)p] = p;
+  ent_key[2 * (size_t)p + 1] = (unsigned long long)b * (unsigned long long)n_cam + (unsigned long long)a; ent_val[2 * (size_t)p + 1] = p | (int)0x80000000;
+}
+__global__ void k_pair_entries(const int n_ent, const unsigned long long* __restrict__ skey, const int* __restrict__ sval, const int n_cam,
+                               int* __restrict__ ent_row, int2* __restrict__ ent) {
+  pdl_grid_sync();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_ent) return;
+  const unsigned long long k = skey[e];
+  ent_row[e] = (int)(k / (unsigned long long)n_cam);
+  ent[e] = make_int2((int)(k % (unsigned long long)n_cam), sval[e]);
+}
+
+// One warp per block: S^_ab = sum over its instances of J^_a' E J^_b, E = J~p_a Cinv J~p_b' (2x2).
+// The instance list is a two-level gather (index entry -> two records + the point's inverse block) and the arithmetic per
+// instance is ~190 FP64 operations at 3 CTAs/SM: the first version waited on the scoreboard 65 % of the time (ncu), so the
+// loop is software-pipelined: index entries two trips ahead, records and inverse block one trip ahead.
+constexpr int NT_SP = 128;
+__device__ __forceinline__ void pair_accumulate(const double4 ra, const double4 rb, const double* Ci, const double* Ra, const double* Rb,
+                                                const double* sva, const double* svb, const Intr K, double* acc) {
+  double apa[3], bpa[3], apb[3], bpb[3];
+  jp_rows(ra, Ra, K, apa, bpa);
+  jp_rows(rb, Rb, K, apb, bpb);
+  const double t0 = Ci[0] * apb[0] + Ci[1] * apb[1] + Ci[2] * apb[2];
+  const double t1 = Ci[1] * apb[0] + Ci[3] * apb[1] + Ci[4] * apb[2];
+  const double t2 = Ci[2] * apb[0] + Ci[4] * apb[1] + Ci[5] * apb[2];
+  const double s0 = Ci[0] * bpb[0] + Ci[1] * bpb[1] + Ci[2] * bpb[2];
+  const double s1 = Ci[1] * bpb[0] + Ci[3] * bpb[1] + Ci[4] * bpb[2];
+  const double s2 = Ci[2] * bpb[0] + Ci[4] * bpb[1] + Ci[5] * bpb[2];
+  const double E00 = apa[0] * t0 + apa[1] * t1 + apa[2] * t2;
+  const double E01 = apa[0] * s0 + apa[1] * s1 + apa[2] * s2;
+  const double E10 = bpa[0] * t0 + bpa[1] * t1 + bpa[2] * t2;
+  const double E11 = bpa[0] * s0 + bpa[1] * s1 + bpa[2] * s2;
+  double aa[6], ba[6], ab[6], bb[6];
+  jhat_rows(ra, sva[0], sva[1], sva[2], K, aa, ba);
+  jhat_rows(rb, svb[0], svb[1], svb[2], K, ab, bb);
+  // E J^_b: rows ea = E00 a_b + E01 b_b, eb = E10 a_b + E11 b_b   (a_b[4] = b_b[3] = 0 structurally)
+  double ea[6], eb[6];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { ea[c] = E00 * ab[c] + E01 * bb[c]; eb[c] = E10 * ab[c] + E11 * bb[c]; }
+  ea[3] = E00 * ab[3]; eb[3] = E10 * ab[3];
+  ea[4] = E01 * bb[4]; eb[4] = E11 * bb[4];
+  ea[5] = E00 * ab[5] + E01 * bb[5]; eb[5] = E10 * ab[5] + E11 * bb[5];
+  // J^_a' (E J^_b): row r = a_a[r] ea + b_a[r] eb   (a_a[4] = b_a[3] = 0)
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      if (r == 3) acc[r * 6 + c] += aa[3] * ea[c];
+      else if (r == 4) acc[r * 6 + c] += ba[4] * eb[c];
+      else acc[r * 6 + c] += aa[r] * ea[c] + ba[r] * eb[c];
+    }
+}
+
+__global__ void __launch_bounds__(NT_SP, 3)
+k_schur_pairs(const int n_pairs, const int* __restrict__ pair_a, const int* __restrict__ pair_b, const int* __restrict__ pair_start,
+              const int4* __restrict__ inst, const double4* __restrict__ rec_pm, const double* __restrict__ camtab, const double* __restrict__ cinv,
+              const Intr K, double* __restrict__ blocks /* [n_pairs][36] */) {
+  pdl_grid_sync();
+  __shared__ double scam[NT_SP / 32][2][12];      // R[9], sv[3] of the warp's two cameras
+  const int wid = threadIdx.x >> 5;
+  const int p = (blockIdx.x * NT_SP + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= n_pairs) return;
+  const double* cta = camtab + (size_t)CAMTAB * pair_a[p];
+  const double* ctb = camtab + (size_t)CAMTAB * pair_b[p];
+  if (lane < 24) {
+    const int q = lane % 12;
+    scam[wid][lane / 12][q] = (lane < 12 ? cta : ctb)[q < 9 ? q : CT_SV + q - 9];
+  }
+  __syncwarp();
+  const double* Ra = scam[wid][0]; const double* sva = Ra + 9;
+  const double* Rb = scam[wid][1]; const double* svb = Rb + 9;
+  double acc[36];
+#pragma unroll
+  for (int q = 0; q < 36; ++q) acc[q] = 0.0;
+  const int i1 = pair_start[p + 1];
+  int i = pair_start[p] + lane;
+  if (i < i1) {
+    int4 in1 = __ldg(inst + min(i + 32, i1 - 1));
+    const int4 in0 = __ldg(inst + i);
+    double4 ra = ldg4(rec_pm + in0.x), rb = ldg4(rec_pm + in0.y);
+    double Ci[6];
+    load_cinv(cinv, in0.z, Ci);
+    for (; i < i1; i += 32) {
+      const int4 in2 = __ldg(inst + min(i + 64, i1 - 1));              // clamped: a harmless re-read past the lane's last trip
+      const double4 ra_n = ldg4(rec_pm + in1.x), rb_n = ldg4(rec_pm + in1.y);
+      double Ci_n[6];
+      load_cinv(cinv, in1.z, Ci_n);
+      pair_accumulate(ra, rb, Ci, Ra, Rb, sva, svb, K, acc);
+      ra = ra_n; rb = rb_n; in1 = in2;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) Ci[q] = Ci_n[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 36; ++q)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+  // every lane holds S^_ab; S_ab = -T_a' S^_ab T_b with T = blkdiag(G, R)  (all lanes alike: static register indexing)
+  double Ga[9], Gb[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { Ga[q] = cta[CT_G + q]; Gb[q] = ctb[CT_G + q]; }
+  double out[36];
+#pragma unroll
+  for (int I = 0; I < 2; ++I)
+#pragma unroll
+    for (int J = 0; J < 2; ++J) {
+      const double* L = I == 0 ? Ga : Ra;
+      const double* Rm = J == 0 ? Gb : Rb;
+      double t[9];       // t = S^_IJ Rm
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          t[r * 3 + c] = acc[(3 * I + r) * 6 + 3 * J] * Rm[c] + acc[(3 * I + r) * 6 + 3 * J + 1] * Rm[3 + c] + acc[(3 * I + r) * 6 + 3 * J + 2] * Rm[6 + c];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          out[(3 * I + r) * 6 + 3 * J + c] = -(L[r] * t[c] + L[3 + r] * t[3 + c] + L[6 + r] * t[6 + c]);
+    }
+  if (lane < 9) {       // lanes 0..8 write four values each (256-bit stores)
+    double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+    for (int l = 0; l < 9; ++l)
+      if (lane == l) v = make_double4(out[4 * l], out[4 * l + 1], out[4 * l + 2], out[4 * l + 3]);
+    st4(reinterpret_cast<double4*>(blocks + (size_t)36 * p) + lane, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole block-Jacobi PCG on the assembled matrix in ONE cooperative launch (one CTA per SM at most, all resident):
+// same single-reduction recurrence and stop rules as k_cg_w / k_cg_update (glba_cam.cuh), two grid barriers per iteration.
+//   phase 1 (one warp per camera row):  w_a = Md_a u_a + sum_b S_ab u_b,  partial gamma' = r.u and delta = u.w
+//   barrier; every CTA adds the CTA partials in the same fixed order and takes the same decisions
+//   phase 2 (lane 0 of the row's warp):  p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, u = Minv r
+//   barrier (u is read by other rows' products)
+// The blocks, Md and Minv are read through the non-coherent path and stay in L1 from the second iteration on; the vectors
+// other CTAs write (u) and the partials are read with ld.cg.  A row always belongs to the same warp.
+// The barrier is a monotonic counter (zeroed by the host before the launch); a waiter that spins implausibly long flags
+// reason 4 and leaves, so a scheduling accident cannot hang the device.
+// ---------------------------------------------------------------------------------------------
+constexpr int NT_CGP = 512;
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, const unsigned n_cta) {
+  __shared__ int ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += n_cta;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned spins = 0;
+    bool fine = true;
+    while (*reinterpret_cast<volatile unsigned*>(bar) < target) {
+      if (++spins > (1u << 22)) { fine = false; break; }
+    }
+    __threadfence();
+    ok = fine ? 1 : 0;
+  }
+  __syncthreads();
+  return ok != 0;
+}
+
+// lanes 0..5 of a warp own the six components of the row's vectors (the other lanes mirror lane 0 and store nothing)
+__device__ __forceinline__ double pick6(const double* a, const int q) {
+  double v = a[0];
+#pragma unroll
+  for (int c = 1; c < 6; ++c) v = (q == c) ? a[c] : v;
+  return v;
+}
+__device__ __forceinline__ double sum6_lanes(const double v) {        // v of lanes 0..5 added in lane order, result in every lane
+  double t = __shfl_sync(0xffffffffu, v, 0);
+#pragma unroll
+  for (int c = 1; c < 6; ++c) t += __shfl_sync(0xffffffffu, v, c);
+  return t;
+}
+__device__ __forceinline__ double row6_dot(const double* __restrict__ Mrow /* 6 values of row q */, const double v) {   // sum_c M[q][c] v_c, v_c from lane c
+  double t = 0.0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) t += __ldg(Mrow + c) * __shfl_sync(0xffffffffu, v, c);
+  return t;
+}
+
+__global__ void __launch_bounds__(NT_CGP, 1)
+k_cg_bsr(const int n_cam, const uint8_t* __restrict__ cam_free, const int* __restrict__ row_start, const int2* __restrict__ ent,
+         const double* __restrict__ blocks, const double* __restrict__ Md, const double* __restrict__ Minv, const double* __restrict__ rhs,
+         double* x, double* r, double* u, double* p, double* sv, double* w, double* part /* [gridDim.x][2] */, unsigned* bar,
+         CgState* cg, const double tol, const int max_iters) {
+  pdl_grid_sync();
+  (void)cam_free;        // rows of fixed cameras have no entries, Md = Minv = 0 and rhs = 0: they stay zero without a branch
+  __shared__ double sm_dot[2][NT_CGP / 32];
+  __shared__ double sm_tot[2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = lane < 6 ? lane : 0;
+  const bool owner = lane < 6;
+  const int gw = blockIdx.x * (NT_CGP / 32) + wid, nw = gridDim.x * (NT_CGP / 32);
+  unsigned target = 0;
+  // x = 0, r = rhs, u = Minv r, p = s = 0
+  for (int row = gw; row < n_cam; row += nw) {
+    const double rr = rhs[6 * row + q];
+    const double z = row6_dot(Minv + (size_t)36 * row + 6 * q, rr);
+    if (owner) { x[6 * row + q] = 0.0; r[6 * row + q] = rr; p[6 * row + q] = 0.0; sv[6 * row + q] = 0.0; u[6 * row + q] = z; }
+  }
+  int iters = 0, reason = 0;
+  bool alive = grid_barrier(bar, target, gridDim.x);
+  double g_old = 0.0, a_old = 0.0, g0 = 0.0;
+  for (int li = 0; alive; ++li) {
+    double ru = 0.0, uw = 0.0;
+    for (int row = gw; row < n_cam; row += nw) {
+      double acc[6] = {0, 0, 0, 0, 0, 0};
+      const int e1 = row_start[row + 1];
+      for (int e = row_start[row] + lane; e < e1; e += 32) {
+        const int2 en = __ldg(ent + e);
+        const double2* ub = reinterpret_cast<const double2*>(u + (size_t)6 * en.x);
+        const double2 x01 = __ldcg(ub), x23 = __ldcg(ub + 1), x45 = __ldcg(ub + 2);
+        const double xv[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
+        const double4* bp = reinterpret_cast<const double4*>(blocks + (size_t)36 * (en.y & 0x7fffffff));
+        double B[36];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double4 v = ldg4(bp + k); B[4 * k] = v.x; B[4 * k + 1] = v.y; B[4 * k + 2] = v.z; B[4 * k + 3] = v.w; }
+        if (en.y >= 0) {
+#pragma unroll
+          for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[rr] += B[rr * 6 + c] * xv[c];
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[c] += B[rr * 6 + c] * xv[rr];
+        }
+      }
+      const double uq = u[6 * row + q], rq = r[6 * row + q];       // written by this lane (phase 2 / start)
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      const double wq = pick6(acc, q) + row6_dot(Md + (size_t)36 * row + 6 * q, uq);
+      if (owner) w[6 * row + q] = wq;
+      ru += sum6_lanes(rq * uq);
+      uw += sum6_lanes(wq * uq);
+    }
+    if (lane == 0) { sm_dot[0][wid] = ru; sm_dot[1][wid] = uw; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int k = 0; k < NT_CGP / 32; ++k) { a += sm_dot[0][k]; b += sm_dot[1][k]; }
+      part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    }
+    if (!grid_barrier(bar, target, gridDim.x)) { reason = 4; break; }
+    if (wid == 0) {       // CTA partials in CTA order: lane-strided sums + butterfly, identical in every CTA
+      double a = 0.0, b = 0.0;
+      for (unsigned k = lane; k < gridDim.x; k += 32) { a += __ldcg(part + 2 * k); b += __ldcg(part + 2 * k + 1); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (lane == 0) { sm_tot[0] = a; sm_tot[1] = b; }
+    }
+    __syncthreads();
+    const double gp = sm_tot[0], dl = sm_tot[1];
+    const bool first = (li == 0);
+    if (first) g0 = gp;
+    const bool zero_rhs = first && !(gp > 0.0);
+    const bool converged = !first && sqrt(gp) <= tol * sqrt(g0);
+    const double beta = first ? 0.0 : ((g_old > 0.0) ? gp / g_old : 0.0);
+    const double denom = first ? dl : dl - beta * gp / a_old;
+    const bool breakdown = !(denom > 0.0);
+    if (zero_rhs || converged || breakdown) { iters = li; reason = (breakdown && !converged && !zero_rhs) ? 2 : 1; break; }
+    const double alpha = gp / denom;
+    g_old = gp; a_old = alpha;
+    for (int row = gw; row < n_cam; row += nw) {
+      const double pn = u[6 * row + q] + beta * p[6 * row + q];
+      const double sn = w[6 * row + q] + beta * sv[6 * row + q];
+      const double xn = x[6 * row + q] + alpha * pn;
+      const double rr = r[6 * row + q] - alpha * sn;
+      const double z = row6_dot(Minv + (size_t)36 * row + 6 * q, rr);
+      if (owner) { p[6 * row + q] = pn; sv[6 * row + q] = sn; x[6 * row + q] = xn; r[6 * row + q] = rr; u[6 * row + q] = z; }
+    }
+    iters = li + 1;
+    if (li + 1 >= max_iters) { reason = 3; break; }
+    if (!grid_barrier(bar, target, gridDim.x)) { reason = 4; break; }
+  }
+  if (!alive) reason = 4;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { cg->iters = iters; cg->reason = reason; cg->done_at = 0; cg->gamma0 = g0; cg->tol = tol; cg->max_iters = max_iters; }
+}
+
+}  // namespace glba

@@ -224,6 +224,13 @@ typedef struct {
   double exchange_bytes;    /* world > 1: payload of that all-reduce on this rank */
   int32_t n_local_cams;     /* world > 1: cameras this rank holds (owner-computes layout: the ones its own tracks observe) */
   int32_t n_shared_cams;    /* world > 1: cameras whose partial sums are exchanged (owner-computes: observed by >= 2 ranks) */
+  /* explicit block-sparse reduced camera matrix (single GPU, glba_sparse.cuh); zeros when the map keeps the matrix-free product */
+  double schur_pairs_ms;    /* assembly of the off-diagonal blocks, once per LM iteration */
+  double bsr_spmv_ms;       /* one PCG iteration of the cooperative kernel on the blocks (product + dot products + updates + two grid barriers) */
+  double pair_setup_ms;     /* structure of the loaded problem (sorts), once per load; 0 if it was already built */
+  int64_t n_pair_instances; /* (observation, observation) pairs summed by the assembly */
+  int32_t n_pair_blocks;    /* distinct off-diagonal 6x6 blocks (upper triangle) */
+  int32_t reserved_;
 } glba_kernel_times;
 
 void glba_default_options(glba_options* opt);

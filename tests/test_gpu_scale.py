@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import gl_slam_b200 as g
-from gl_slam_b200 import scene
+from gl_slam_b200 import _abi, scene
 
 from helpers import check_state, check_trajectory, rel_to_max
 
@@ -135,6 +135,7 @@ def test_pipelined_tile_kernels_match_oracle(oracle, name, kw, okw):
         os.environ["GLBA_RELABEL"] = "0"
     if name.startswith("fused"):
         os.environ["GLBA_FUSED"] = "1"
+    os.environ["GLBA_EXPLICIT"] = "0"             # these cases are about the matrix-free product of the tile kernels
     try:
         with g.Context(device=0) as c:
             got, s = c.solve(prob, g.options(linsolve=g.LINSOLVE_PCG, **okw))
@@ -143,6 +144,7 @@ def test_pipelined_tile_kernels_match_oracle(oracle, name, kw, okw):
         os.environ.pop("GLBA_TILE", None)
         os.environ.pop("GLBA_RELABEL", None)
         os.environ.pop("GLBA_FUSED", None)
+        os.environ.pop("GLBA_EXPLICIT", None)
     check_trajectory(s, so, rtol=1e-9 if not name.endswith("scattered_cameras") else 1e-8)
     check_state(prob, got.cam, got.pt, ref.cam, ref.pt)
     O = oracle.linearize(prob, 1e4, oracle.options(**okw), per_obs=False)
@@ -194,3 +196,53 @@ def test_device_lm_loop_matches_host_loop(oracle, kw, okw):
     assert np.allclose(dev.cam, host.cam, rtol=10 * tol, atol=1e-9) and np.allclose(dev.pt, host.pt, rtol=10 * tol, atol=1e-6)
     check_trajectory(sd, so, rtol=1e-9 if not rough else 1e-6)
     assert (sd["termination"], sd["stop_reason"]) == (so["termination"], so["stop_reason"])
+
+
+# ---- explicit block-sparse reduced camera matrix (glba_sparse.cuh) vs the matrix-free product ----------------------------
+def _solve_both_products(prob, **okw):
+    import os
+    with g.Context(device=0) as c:
+        exp, se = c.solve(prob, g.options(**okw))
+        kt = c.time_kernels(1e4, reps=1, opt=g.options(**okw))
+    os.environ["GLBA_EXPLICIT"] = "0"
+    try:
+        with g.Context(device=0) as c:
+            imp, si = c.solve(prob, g.options(**okw))
+    finally:
+        del os.environ["GLBA_EXPLICIT"]
+    return exp, se, imp, si, kt
+
+
+@pytest.mark.parametrize("name", ["street_grid", "loop_fixed_points", "g2o"])
+def test_explicit_reduced_matrix_matches_matrix_free_product(oracle, name):
+    """PCG on the assembled blocks (one assembly per LM iteration) and PCG on the matrix-free product solve the same system:
+    same trajectory as each other and as the oracle, at the parity tolerance; fixed cameras and fixed points carry no block."""
+    okw = dict(max_iters=5, linsolve=g.LINSOLVE_PCG, cg_rel_tol=1e-13)
+    if name == "street_grid":
+        prob = scene.make_street_grid(6, 20, 12000, track_len=lambda rng, n: 2 + rng.poisson(3.0, size=n), seed=3, rot_sigma=0.002, pos_sigma=0.03)
+        okw["loss"] = 1
+    elif name == "loop_fixed_points":
+        prob = scene.make_scene(40, 5000, lambda rng, n: 2 + rng.poisson(3.0, size=n), seed=12, loop=True, rot_sigma=0.003, pos_sigma=0.03)
+        prob.cam_fixed[:] = 0; prob.cam_fixed[[0, 7, 19]] = 1
+        prob.pt_fixed = np.zeros(prob.n_pt, np.uint8); prob.pt_fixed[::9] = 1
+    else:
+        prob = scene.as_g2o(scene.make_scene(24, 3000, lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=43, rot_sigma=0.003, pos_sigma=0.03))
+        okw.update(mode=_abi.MODE_G2O, loss=1, max_iters=6)
+    ref, so = oracle.solve(prob, oracle.options(**{k: v for k, v in okw.items() if k not in ("linsolve", "cg_rel_tol")}))
+    exp, se, imp, si, kt = _solve_both_products(prob, **okw)
+    assert kt["n_pair_blocks"] > 0 and kt["n_pair_instances"] > 0, kt      # the explicit path was really taken
+    check_trajectory(se, so)
+    check_trajectory(si, so)
+    check_state(prob, exp.cam, exp.pt, ref.cam, ref.pt)
+    assert list(se["accepted"]) == list(si["accepted"]) and se["n_iters"] == si["n_iters"]
+    assert np.allclose(se["cost"], si["cost"], rtol=1e-10, atol=1e-300)
+    assert np.allclose(exp.cam, imp.cam, rtol=1e-7, atol=1e-9)
+
+
+def test_explicit_reduced_matrix_is_bitwise_reproducible(ctx):
+    prob = scene.config("C4", scale=0.1)
+    opt = g.options(max_iters=4, function_tol=0.0, parameter_tol=0.0, gradient_tol=0.0, cg_rel_tol=1e-2, cg_max_iters=40)
+    a, sa = ctx.solve(prob, opt)
+    b, sb = ctx.solve(prob, opt)
+    assert sa["cost_candidate"] == sb["cost_candidate"] and sa["cost"] == sb["cost"] and sa["cg_iters"] == sb["cg_iters"]
+    assert np.array_equal(a.cam, b.cam) and np.array_equal(a.pt, b.pt)
