@@ -137,7 +137,9 @@ struct glba_ctx {
   int n_pairs = 0;
   long long n_inst = 0;
   Buf sp_cnt, sp_off, sp_key, sp_key2, sp_val, sp_inst, sp_ukey, sp_ucnt, sp_nruns, sp_pair_a, sp_pair_b, sp_pair_start;
-  Buf sp_ekey, sp_ekey2, sp_eval, sp_eval2, sp_erow, sp_ent, sp_row_start, sp_blocks, sp_part, sp_bar;
+  Buf sp_ekey, sp_ekey2, sp_eval, sp_eval2, sp_erow, sp_ent, sp_row_start, sp_blocks, sp_part, sp_bar, sp_pres, sp_gscan, sp_gkey, sp_gid, sp_vec;
+  int n_pairs_g = 0;             // blocks of the whole map (== n_pairs on one GPU)
+  size_t sp_xch_len = 0;         // doubles of [blocks | sharded: Md Minv rhs of the whole map]
   int cg_grid = 0;               // CTAs of the cooperative PCG kernel (all resident)
   int occ_lin = 0, occ_pt0 = 0, occ_pt1 = 0;   // resident CTAs per SM of the pipelined kernels (occupancy API, per context)
   int opt = OPT_LARGE;          // observations per thread of the tile kernels (tile capacity = NT_T * opt)
@@ -925,8 +927,19 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   if (ctx->sp_tried) return GLBA_OK;
   ctx->sp_tried = true; ctx->use_explicit = false;
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
-  if (!ctx->env_explicit || ctx->world > 1 || ctx->has_dup || ctx->n_free_cam < 2 || n_pt == 0 || ctx->n_obs == 0) return GLBA_OK;
+  const bool sharded = ctx->world > 1;
+  // every condition up to the veto below is the same on every rank of a sharded run (collectives follow)
+  if (!ctx->env_explicit || (sharded && !ctx->owner) || ctx->has_dup || ctx->n_free_cam < 2 || n_pt == 0 || ctx->n_obs == 0) return GLBA_OK;
+  const int n_cam_g = sharded ? ctx->n_cam_g : n_cam;            // cameras of the whole map: keys and rows are global
+  const long long K2 = (long long)n_cam_g * n_cam_g;
+  if (sharded && K2 > (1LL << 28)) return GLBA_OK;               // the union of the ranks' blocks goes through a presence table of n_cam^2 ints
+  int coop = 0, occ = 0;
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_bsr, NT_CGP, 0));
+  if (!coop || occ < 1) return GLBA_OK;                          // the PCG runs in one cooperative launch: every CTA must be resident
   cudaStream_t s = ctx->stream;
+  const int* l2g = sharded ? (const int*)ctx->l2g.as<int>() : (const int*)nullptr;
+  const int* g2l = sharded ? (const int*)ctx->g2l.as<int>() : (const int*)nullptr;
   mark(ctx, PH_SETUP);
   ENSURE(long long, ctx->sp_cnt, (size_t)n_pt + 1); ENSURE(long long, ctx->sp_off, (size_t)n_pt + 1);
   LAUNCH(k_pair_count, cdiv((long)n_pt + 1, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(),
@@ -940,48 +953,82 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   long long n_inst = 0;
   CU(cudaMemcpyAsync(&n_inst, ctx->sp_off.as<long long>() + n_pt, sizeof(long long), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  if (n_inst <= 0 || n_inst > 16 * (long long)ctx->n_obs || n_inst > 0x7fffffffLL - 64) { mark(ctx, -1); return GLBA_OK; }
-  ENSURE(unsigned long long, ctx->sp_key, (size_t)n_inst); ENSURE(unsigned long long, ctx->sp_key2, (size_t)n_inst);
-  ENSURE(int4, ctx->sp_val, (size_t)n_inst); ENSURE(int4, ctx->sp_inst, (size_t)n_inst);
-  LAUNCH(k_pair_emit, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(),
-         (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const long long*)ctx->sp_off.as<long long>(), n_cam,
-         ctx->sp_key.as<unsigned long long>(), ctx->sp_val.as<int4>());
-  int bits = 1; while ((1ULL << bits) < (unsigned long long)n_cam * (unsigned long long)n_cam && bits < 63) ++bits;
+  int veto = (n_inst > 16 * (long long)ctx->n_obs || n_inst > 0x7fffffffLL - 64 || (!sharded && n_inst <= 0)) ? 1 : 0;
+  if (sharded) {             // one rank's veto is everybody's
+    ENSURE(int, ctx->sp_nruns, 2);
+    CU(cudaMemcpyAsync(ctx->sp_nruns.as<int>() + 1, &veto, sizeof(int), cudaMemcpyHostToDevice, s));
+    { int s__ = allreduce(ctx, ctx->sp_nruns.as<int>() + 1, 1, kNcclMax, kNcclInt32); if (s__) return s__; }
+    CU(cudaMemcpyAsync(&veto, ctx->sp_nruns.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  if (veto) { mark(ctx, -1); return GLBA_OK; }
+  int bits = 1; while ((1ULL << bits) < (unsigned long long)K2 && bits < 63) ++bits;
+  int n_loc = 0;             // distinct blocks among this rank's tracks
+  ENSURE(unsigned long long, ctx->sp_ukey, (size_t)std::max<long long>(n_inst, 1)); ENSURE(int, ctx->sp_ucnt, (size_t)n_inst + 2); ENSURE(int, ctx->sp_nruns, 2);
+  if (n_inst > 0) {
+    ENSURE(unsigned long long, ctx->sp_key, (size_t)n_inst); ENSURE(unsigned long long, ctx->sp_key2, (size_t)n_inst);
+    ENSURE(int4, ctx->sp_val, (size_t)n_inst); ENSURE(int4, ctx->sp_inst, (size_t)n_inst);
+    LAUNCH(k_pair_emit, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(),
+           (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const long long*)ctx->sp_off.as<long long>(), n_cam_g, l2g,
+           ctx->sp_key.as<unsigned long long>(), ctx->sp_val.as<int4>());
+    tb = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
+                                       ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
+    ENSURE(char, ctx->sort_tmp, tb);
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
+                                       ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
+    // distinct keys = blocks; run lengths = instances per block
+    tb = 0;
+    CU(cub::DeviceRunLengthEncode::Encode(nullptr, tb, ctx->sp_key2.as<unsigned long long>(), ctx->sp_ukey.as<unsigned long long>(), ctx->sp_ucnt.as<int>(),
+                                          ctx->sp_nruns.as<int>(), (int)n_inst, s));
+    ENSURE(char, ctx->sort_tmp, tb);
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceRunLengthEncode::Encode(ctx->sort_tmp.p, tb, ctx->sp_key2.as<unsigned long long>(), ctx->sp_ukey.as<unsigned long long>(), ctx->sp_ucnt.as<int>(),
+                                          ctx->sp_nruns.as<int>(), (int)n_inst, s));
+    g_launches.fetch_add(2);
+    CU(cudaMemcpyAsync(&n_loc, ctx->sp_nruns.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  ENSURE(int, ctx->sp_pair_start, (size_t)n_loc + 1); ENSURE(int, ctx->sp_pair_a, std::max(n_loc, 1)); ENSURE(int, ctx->sp_pair_b, std::max(n_loc, 1));
+  CU(cudaMemsetAsync(ctx->sp_ucnt.as<int>() + n_loc, 0, sizeof(int), s));
   tb = 0;
-  CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
-                                     ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->sp_ucnt.as<int>(), ctx->sp_pair_start.as<int>(), n_loc + 1, s));
   ENSURE(char, ctx->sort_tmp, tb);
   tb = ctx->sort_tmp.cap;
-  CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
-                                     ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
-  // distinct keys = blocks; run lengths = instances per block
-  ENSURE(unsigned long long, ctx->sp_ukey, (size_t)n_inst); ENSURE(int, ctx->sp_ucnt, (size_t)n_inst + 1); ENSURE(int, ctx->sp_nruns, 1);
-  tb = 0;
-  CU(cub::DeviceRunLengthEncode::Encode(nullptr, tb, ctx->sp_key2.as<unsigned long long>(), ctx->sp_ukey.as<unsigned long long>(), ctx->sp_ucnt.as<int>(),
-                                        ctx->sp_nruns.as<int>(), (int)n_inst, s));
-  ENSURE(char, ctx->sort_tmp, tb);
-  tb = ctx->sort_tmp.cap;
-  CU(cub::DeviceRunLengthEncode::Encode(ctx->sort_tmp.p, tb, ctx->sp_key2.as<unsigned long long>(), ctx->sp_ukey.as<unsigned long long>(), ctx->sp_ucnt.as<int>(),
-                                        ctx->sp_nruns.as<int>(), (int)n_inst, s));
-  g_launches.fetch_add(2);
-  int n_pairs = 0;
-  CU(cudaMemcpyAsync(&n_pairs, ctx->sp_nruns.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  if (n_pairs <= 0 || (size_t)n_pairs * 288 > ((size_t)1 << 30)) { mark(ctx, -1); return GLBA_OK; }
-  ENSURE(int, ctx->sp_pair_start, (size_t)n_pairs + 1);
-  CU(cudaMemsetAsync(ctx->sp_ucnt.as<int>() + n_pairs, 0, sizeof(int), s));
-  tb = 0;
-  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->sp_ucnt.as<int>(), ctx->sp_pair_start.as<int>(), n_pairs + 1, s));
-  ENSURE(char, ctx->sort_tmp, tb);
-  tb = ctx->sort_tmp.cap;
-  CU(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tb, ctx->sp_ucnt.as<int>(), ctx->sp_pair_start.as<int>(), n_pairs + 1, s));
-  // row lists: both triangles, sorted by (row, column)
-  const int n_ent = 2 * n_pairs;
-  ENSURE(int, ctx->sp_pair_a, n_pairs); ENSURE(int, ctx->sp_pair_b, n_pairs);
+  CU(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tb, ctx->sp_ucnt.as<int>(), ctx->sp_pair_start.as<int>(), n_loc + 1, s));
+  g_launches.fetch_add(1);
+  if (n_loc) LAUNCH(k_pair_cams, cdiv(n_loc, 256), 256, n_loc, (const unsigned long long*)ctx->sp_ukey.as<unsigned long long>(), n_cam_g, g2l,
+                    ctx->sp_pair_a.as<int>(), ctx->sp_pair_b.as<int>());
+  // blocks of the whole map and this rank's place in them
+  int n_glob = n_loc;
+  const unsigned long long* gkey = ctx->sp_ukey.as<unsigned long long>();
+  if (sharded) {
+    ENSURE(int, ctx->sp_pres, (size_t)K2 + 1); ENSURE(int, ctx->sp_gscan, (size_t)K2 + 1); ENSURE(int, ctx->sp_gid, std::max(n_loc, 1));
+    CU(cudaMemsetAsync(ctx->sp_pres.p, 0, sizeof(int) * ((size_t)K2 + 1), s));
+    if (n_loc) LAUNCH(k_pair_mark, cdiv(n_loc, 256), 256, n_loc, (const unsigned long long*)ctx->sp_ukey.as<unsigned long long>(), ctx->sp_pres.as<int>());
+    { int s__ = allreduce(ctx, ctx->sp_pres.p, (size_t)K2, kNcclSum, kNcclInt32); if (s__) return s__; }
+    LAUNCH(k_pair_flag01, cdiv(K2 + 1, 256), 256, (long)K2, ctx->sp_pres.as<int>());
+    tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->sp_pres.as<int>(), ctx->sp_gscan.as<int>(), (int)(K2 + 1), s));
+    ENSURE(char, ctx->sort_tmp, tb);
+    tb = ctx->sort_tmp.cap;
+    CU(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, tb, ctx->sp_pres.as<int>(), ctx->sp_gscan.as<int>(), (int)(K2 + 1), s));
+    g_launches.fetch_add(1);
+    CU(cudaMemcpyAsync(&n_glob, ctx->sp_gscan.as<int>() + K2, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    ENSURE(unsigned long long, ctx->sp_gkey, std::max(n_glob, 1));
+    LAUNCH(k_pair_compact, cdiv(K2, 256), 256, (long)K2, (const int*)ctx->sp_pres.as<int>(), (const int*)ctx->sp_gscan.as<int>(), ctx->sp_gkey.as<unsigned long long>());
+    if (n_loc) LAUNCH(k_pair_gid, cdiv(n_loc, 256), 256, n_loc, (const unsigned long long*)ctx->sp_ukey.as<unsigned long long>(), (const int*)ctx->sp_gscan.as<int>(),
+                      ctx->sp_gid.as<int>());
+    gkey = ctx->sp_gkey.as<unsigned long long>();
+  }
+  if (n_glob <= 0 || (size_t)n_glob * 288 > ((size_t)1 << 30)) { mark(ctx, -1); return GLBA_OK; }      // n_glob is the same on every rank
+  // row lists of the whole map: both triangles, sorted by (row, column)
+  const int n_ent = 2 * n_glob;
   ENSURE(unsigned long long, ctx->sp_ekey, n_ent); ENSURE(unsigned long long, ctx->sp_ekey2, n_ent); ENSURE(int, ctx->sp_eval, n_ent); ENSURE(int, ctx->sp_eval2, n_ent);
-  ENSURE(int, ctx->sp_erow, n_ent); ENSURE(int2, ctx->sp_ent, n_ent); ENSURE(int, ctx->sp_row_start, (size_t)n_cam + 2);
-  LAUNCH(k_pair_rows, cdiv(n_pairs, 256), 256, n_pairs, (const unsigned long long*)ctx->sp_ukey.as<unsigned long long>(), n_cam, ctx->sp_pair_a.as<int>(),
-         ctx->sp_pair_b.as<int>(), ctx->sp_ekey.as<unsigned long long>(), ctx->sp_eval.as<int>());
+  ENSURE(int, ctx->sp_erow, n_ent); ENSURE(int2, ctx->sp_ent, n_ent); ENSURE(int, ctx->sp_row_start, (size_t)n_cam_g + 2);
+  LAUNCH(k_pair_rows, cdiv(n_glob, 256), 256, n_glob, gkey, n_cam_g, ctx->sp_ekey.as<unsigned long long>(), ctx->sp_eval.as<int>());
   tb = 0;
   CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->sp_ekey.as<unsigned long long>(), ctx->sp_ekey2.as<unsigned long long>(), ctx->sp_eval.as<int>(),
                                      ctx->sp_eval2.as<int>(), n_ent, 0, bits, s));
@@ -990,34 +1037,63 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->sp_ekey.as<unsigned long long>(), ctx->sp_ekey2.as<unsigned long long>(), ctx->sp_eval.as<int>(),
                                      ctx->sp_eval2.as<int>(), n_ent, 0, bits, s));
   g_launches.fetch_add(3);
-  LAUNCH(k_pair_entries, cdiv(n_ent, 256), 256, n_ent, (const unsigned long long*)ctx->sp_ekey2.as<unsigned long long>(), (const int*)ctx->sp_eval2.as<int>(), n_cam,
+  LAUNCH(k_pair_entries, cdiv(n_ent, 256), 256, n_ent, (const unsigned long long*)ctx->sp_ekey2.as<unsigned long long>(), (const int*)ctx->sp_eval2.as<int>(), n_cam_g,
          ctx->sp_erow.as<int>(), ctx->sp_ent.as<int2>());
-  LAUNCH(k_segment_starts, cdiv(n_cam + 1, 256), 256, (long)n_ent, (const int*)ctx->sp_erow.as<int>(), n_cam, ctx->sp_row_start.as<int>());
-  ENSURE(double, ctx->sp_blocks, (size_t)36 * n_pairs);
-  // the PCG runs in one cooperative launch: every CTA must be resident
-  int coop = 0, occ = 0;
-  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_bsr, NT_CGP, 0));
-  if (!coop || occ < 1) { mark(ctx, -1); return GLBA_OK; }
-  ctx->cg_grid = std::max(1, std::min(ctx->n_sm, cdiv(n_cam, NT_CGP / 32)));
+  LAUNCH(k_segment_starts, cdiv(n_cam_g + 1, 256), 256, (long)n_ent, (const int*)ctx->sp_erow.as<int>(), n_cam_g, ctx->sp_row_start.as<int>());
+  // blocks; sharded: followed by the whole map's Md | Minv | rhs rows (one all-reduce carries all four), and whole-map PCG vectors
+  ctx->sp_xch_len = (size_t)36 * n_glob + (sharded ? (size_t)78 * n_cam_g : 0);
+  ENSURE(double, ctx->sp_blocks, ctx->sp_xch_len);
+  if (sharded) ENSURE(double, ctx->sp_vec, (size_t)36 * n_cam_g);
+  ctx->cg_grid = std::max(1, std::min(ctx->n_sm, cdiv(n_cam_g, NT_CGP / 32)));
   ENSURE(double, ctx->sp_part, 2 * (size_t)ctx->cg_grid); ENSURE(unsigned, ctx->sp_bar, 1);
   CHECK_LAUNCHES();
   // (the sort scratch stays allocated: a context that solves map after map would pay cudaMalloc / cudaFree of ~50 B per
   // instance at every load: measured 190 ms against 7 ms on C4)
-  ctx->n_pairs = n_pairs; ctx->n_inst = n_inst; ctx->use_explicit = true;
+  ctx->n_pairs = n_loc; ctx->n_pairs_g = n_glob; ctx->n_inst = n_inst; ctx->use_explicit = true;
   mark(ctx, -1);
   return GLBA_OK;
 }
 
-void launch_schur_pairs(glba_ctx* ctx) {
+// blocks of the current linearisation and damping.  Sharded: this rank's partial blocks land in the whole map's numbering and
+// are summed over the ranks together with the owners' Md | Minv | rhs rows: one all-reduce per LM iteration, after which every
+// rank holds the complete reduced system and solves it redundantly (no collective inside the PCG).
+int launch_schur_pairs(glba_ctx* ctx) {
   const int c = ctx->cur;
-  LAUNCH(k_schur_pairs, cdiv((long)ctx->n_pairs * 32, NT_SP), NT_SP, ctx->n_pairs, (const int*)ctx->sp_pair_a.as<int>(), (const int*)ctx->sp_pair_b.as<int>(),
-         (const int*)ctx->sp_pair_start.as<int>(), (const int4*)ctx->sp_inst.as<int4>(), (const double4*)ctx->rec_pm.as<double4>(),
-         (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), ctx->K, ctx->sp_blocks.as<double>());
+  const bool sharded = ctx->world > 1;
+  if (sharded) CU(cudaMemsetAsync(ctx->sp_blocks.p, 0, sizeof(double) * ctx->sp_xch_len, ctx->stream));
+  if (ctx->n_pairs > 0)
+    LAUNCH(k_schur_pairs, cdiv((long)ctx->n_pairs * 32, NT_SP), NT_SP, ctx->n_pairs, (const int*)ctx->sp_pair_a.as<int>(), (const int*)ctx->sp_pair_b.as<int>(),
+           (const int*)ctx->sp_pair_start.as<int>(), (const int4*)ctx->sp_inst.as<int4>(), (const double4*)ctx->rec_pm.as<double4>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), ctx->K, sharded ? (const int*)ctx->sp_gid.as<int>() : (const int*)nullptr,
+           ctx->sp_blocks.as<double>());
+  if (sharded) {
+    const int n_cam = ctx->n_cam, n_cam_g = ctx->n_cam_g;
+    double* base = ctx->sp_blocks.as<double>() + (size_t)36 * ctx->n_pairs_g;
+    const int* l2g = ctx->l2g.as<int>();
+    const uint8_t* owned = ctx->cam_owned.as<uint8_t>();
+    LAUNCH(k_scatter_rows, cdiv((long)n_cam * 36, 256), 256, n_cam, l2g, owned, 1, (const double*)ctx->Md.as<double>(), 36, base);
+    LAUNCH(k_scatter_rows, cdiv((long)n_cam * 36, 256), 256, n_cam, l2g, owned, 1, (const double*)ctx->Minv.as<double>(), 36, base + (size_t)36 * n_cam_g);
+    LAUNCH(k_scatter_rows, cdiv((long)n_cam * 6, 256), 256, n_cam, l2g, owned, 1, (const double*)ctx->rhs.as<double>(), 6, base + (size_t)72 * n_cam_g);
+    AR(ctx->sp_blocks.p, ctx->sp_xch_len, kNcclSum);
+  }
+  return GLBA_OK;
 }
 // the whole PCG in one cooperative launch (k_cg_bsr); cg receives iterations and stop reason
 int launch_cg_bsr(glba_ctx* ctx, const glba_options* o, int max_it) {
-  const int n_cam = ctx->n_cam;
+  const bool sharded = ctx->world > 1;
+  const int n_rows = sharded ? ctx->n_cam_g : ctx->n_cam;
+  const double* base = ctx->sp_blocks.as<double>() + (size_t)36 * ctx->n_pairs_g;
+  const double* Md = sharded ? base : (const double*)ctx->Md.as<double>();
+  const double* Minv = sharded ? base + (size_t)36 * n_rows : (const double*)ctx->Minv.as<double>();
+  const double* rhs = sharded ? base + (size_t)72 * n_rows : (const double*)ctx->rhs.as<double>();
+  double* v = ctx->sp_vec.as<double>();
+  const size_t L = (size_t)6 * n_rows;
+  double* x = sharded ? v : ctx->cg_x.as<double>();
+  double* r = sharded ? v + L : ctx->cg_r.as<double>();
+  double* u = sharded ? v + 2 * L : ctx->cg_q.as<double>();
+  double* p = sharded ? v + 3 * L : ctx->cg_p.as<double>();
+  double* sv = sharded ? v + 4 * L : ctx->pg.as<double>();
+  double* w = sharded ? v + 5 * L : ctx->yg.as<double>();
   CU(cudaMemsetAsync(ctx->sp_bar.p, 0, sizeof(unsigned), ctx->stream));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctx->cg_grid); cfg.blockDim = dim3(NT_CGP); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
@@ -1026,12 +1102,12 @@ int launch_cg_bsr(glba_ctx* ctx, const glba_options* o, int max_it) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   prev_small(ctx->stream) = false;
-  CU(cudaLaunchKernelEx(&cfg, k_cg_bsr, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const int*)ctx->sp_row_start.as<int>(),
-                        (const int2*)ctx->sp_ent.as<int2>(), (const double*)ctx->sp_blocks.as<double>(), (const double*)ctx->Md.as<double>(),
-                        (const double*)ctx->Minv.as<double>(), (const double*)ctx->rhs.as<double>(), ctx->cg_x.as<double>(), ctx->cg_r.as<double>(),
-                        ctx->cg_q.as<double>(), ctx->cg_p.as<double>(), ctx->pg.as<double>(), ctx->yg.as<double>(), ctx->sp_part.as<double>(),
-                        ctx->sp_bar.as<unsigned>(), ctx->cgst.as<CgState>(), o->cg_rel_tol, max_it));
+  CU(cudaLaunchKernelEx(&cfg, k_cg_bsr, n_rows, (const uint8_t*)nullptr, (const int*)ctx->sp_row_start.as<int>(),
+                        (const int2*)ctx->sp_ent.as<int2>(), (const double*)ctx->sp_blocks.as<double>(), Md, Minv, rhs, x, r, u, p, sv, w,
+                        ctx->sp_part.as<double>(), ctx->sp_bar.as<unsigned>(), ctx->cgst.as<CgState>(), o->cg_rel_tol, max_it));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (sharded)       // this rank's cameras of the solution
+    LAUNCH(k_gather_rows, cdiv((long)ctx->n_cam * 6, 256), 256, ctx->n_cam, (const int*)ctx->l2g.as<int>(), (const double*)x, 6, ctx->cg_x.as<double>());
   return GLBA_OK;
 }
 
@@ -1091,7 +1167,9 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
   CgState* cg = ctx->cgst.as<CgState>();
   if (ctx->use_explicit) {
     // assembled reduced camera matrix: blocks for this linearisation and damping, then the whole PCG in one launch
-    mark(ctx, PH_SCHUR); launch_schur_pairs(ctx); mark(ctx, PH_SOLVE);
+    mark(ctx, PH_SCHUR);
+    { const int s__ = launch_schur_pairs(ctx); if (s__) return s__; }
+    mark(ctx, PH_SOLVE);
     const int s__ = launch_cg_bsr(ctx, o, max_it); if (s__) return s__;
     CHECK_LAUNCHES();
     CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1574,7 +1652,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->tile_sobs, &ctx->tile_sstart, &ctx->tp_key, &ctx->tp_val, &ctx->tp_key2, &ctx->cam_tp, &ctx->cam_tp_start, &ctx->tpart, &ctx->cam_iota, &ctx->ovf_raw, &ctx->ovf_k, &ctx->ovf_c, &ctx->ovf_key, &ctx->ovf_key2, &ctx->ovf_val, &ctx->cam_ov, &ctx->cam_ov_start, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax,
                 &ctx->sp_cnt, &ctx->sp_off, &ctx->sp_key, &ctx->sp_key2, &ctx->sp_val, &ctx->sp_inst, &ctx->sp_ukey, &ctx->sp_ucnt, &ctx->sp_nruns, &ctx->sp_pair_a,
                 &ctx->sp_pair_b, &ctx->sp_pair_start, &ctx->sp_ekey, &ctx->sp_ekey2, &ctx->sp_eval, &ctx->sp_eval2, &ctx->sp_erow, &ctx->sp_ent, &ctx->sp_row_start,
-                &ctx->sp_blocks, &ctx->sp_part, &ctx->sp_bar};
+                &ctx->sp_blocks, &ctx->sp_part, &ctx->sp_bar, &ctx->sp_pres, &ctx->sp_gscan, &ctx->sp_gkey, &ctx->sp_gid, &ctx->sp_vec};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1694,8 +1772,9 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
     launch_cam_lin_fin(ctx, opt, 0);
     launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>()); }, &out->small_kernels_ms);
   if (st) return st;
-  if (ctx->world == 1) {
-    // explicit reduced camera matrix: structure (once per load), assembly, product
+  {
+    // assembled reduced camera matrix: structure (once per load), assembly (sharded: incl. its all-reduce), one PCG iteration.
+    // Collective on a sharded map, like everything below.
     if (!ctx->sp_tried) {
       cudaEventRecord(e0, ctx->stream);
       if ((st = ensure_explicit(ctx, opt))) return st;
@@ -1709,17 +1788,17 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
       if ((st = do_linearize_schur(ctx, opt, 0, radius))) return st;
       CU(cudaStreamSynchronize(ctx->stream));
       ctx->ev_used = 0;
-      if ((st = timed([&] { launch_schur_pairs(ctx); }, &out->schur_pairs_ms))) return st;
+      if ((st = timed([&] { (void)launch_schur_pairs(ctx); }, &out->schur_pairs_ms))) return st;
       // one PCG iteration on the blocks: (time of 1 + 32 iterations - time of 1 iteration) / 32, tolerance 0 so that none stops early
       glba_options ot = *opt; ot.cg_rel_tol = 0.0;
       double t1 = 0.0, t33 = 0.0;
       if ((st = timed([&] { (void)launch_cg_bsr(ctx, &ot, 1); }, &t1))) return st;
       if ((st = timed([&] { (void)launch_cg_bsr(ctx, &ot, 33); }, &t33))) return st;
       out->bsr_spmv_ms = (t33 - t1) / 32.0;
-      out->n_pair_instances = ctx->n_inst; out->n_pair_blocks = ctx->n_pairs;
+      out->n_pair_instances = ctx->n_inst; out->n_pair_blocks = ctx->n_pairs_g;
     }
-    return GLBA_OK;
   }
+  if (ctx->world == 1) return GLBA_OK;
   // collective: every rank calls glba_time_kernels with the same reps
   out->n_local_cams = n_cam; out->n_shared_cams = ctx->owner ? ctx->n_shared : ctx->n_cam;
   out->exchange_bytes = 8.0 * ((ctx->owner ? 54.0 * ctx->n_shared : 54.0 * n_cam) + S_GSLOT0 + MAX_WORLD);

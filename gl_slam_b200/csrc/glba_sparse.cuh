@@ -38,7 +38,8 @@ __global__ void k_pair_count(const int n_pt, const int* __restrict__ pt_start, c
 }
 
 __global__ void k_pair_emit(const int n_pt, const int* __restrict__ pt_start, const int* __restrict__ pm_cam, const uint8_t* __restrict__ cam_free,
-                            const uint8_t* __restrict__ pt_free, const long long* __restrict__ off, const int n_cam,
+                            const uint8_t* __restrict__ pt_free, const long long* __restrict__ off, const int n_cam /* of the whole map */,
+                            const int* __restrict__ l2g /* sharded: local -> global camera (monotonic); else null */,
                             unsigned long long* __restrict__ key, int4* __restrict__ val) {
   pdl_grid_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,24 +53,64 @@ __global__ void k_pair_emit(const int n_pt, const int* __restrict__ pt_start, co
       const int b = pm_cam[ob];
       if (!cam_free[b]) continue;
       const bool sw = a > b;
-      key[pos] = (unsigned long long)(sw ? b : a) * (unsigned long long)n_cam + (unsigned long long)(sw ? a : b);
+      const int lo = sw ? b : a, hi = sw ? a : b;
+      key[pos] = (unsigned long long)(l2g ? l2g[lo] : lo) * (unsigned long long)n_cam + (unsigned long long)(l2g ? l2g[hi] : hi);
       val[pos] = make_int4(sw ? ob : oa, sw ? oa : ob, j, 0);
       ++pos;
     }
   }
 }
 
-// distinct keys -> cameras of the block and its two row entries (upper: as stored, lower: transposed)
-__global__ void k_pair_rows(const int n_pairs, const unsigned long long* __restrict__ ukey, const int n_cam, int* __restrict__ pair_a,
-                            int* __restrict__ pair_b, unsigned long long* __restrict__ ent_key, int* __restrict__ ent_val) {
+// distinct keys of this rank -> (local) cameras of the block
+__global__ void k_pair_cams(const int n_pairs, const unsigned long long* __restrict__ ukey, const int n_cam, const int* __restrict__ g2l /* or null */,
+                            int* __restrict__ pair_a, int* __restrict__ pair_b) {
   pdl_grid_sync();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   const unsigned long long k = ukey[p];
   const int a = (int)(k / (unsigned long long)n_cam), b = (int)(k % (unsigned long long)n_cam);
-  pair_a[p] = a; pair_b[p] = b;
+  pair_a[p] = g2l ? g2l[a] : a; pair_b[p] = g2l ? g2l[b] : b;
+}
+// distinct keys of the whole map -> the two row entries of every block (upper: as stored, lower: transposed)
+__global__ void k_pair_rows(const int n_pairs, const unsigned long long* __restrict__ ukey, const int n_cam,
+                            unsigned long long* __restrict__ ent_key, int* __restrict__ ent_val) {
+  pdl_grid_sync();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const unsigned long long k = ukey[p];
+  const int a = (int)(k / (unsigned long long)n_cam), b = (int)(k % (unsigned long long)n_cam);
   ent_key[2 * (size_t)p] = k;                                                                   ent_val[2 * (size_t)p] = p;
   ent_key[2 * (size_t)p + 1] = (unsigned long long)b * (unsigned long long)n_cam + (unsigned long long)a; ent_val[2 * (size_t)p + 1] = p | (int)0x80000000;
+}
+// sharded maps: the blocks of the whole map are the union of the ranks' blocks.  presence[key] (summed over ranks) -> 0/1,
+// its exclusive scan numbers the blocks in key order, identically on every rank.
+__global__ void k_pair_mark(const int n_pairs, const unsigned long long* __restrict__ ukey, int* __restrict__ pres) {
+  pdl_grid_sync();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pairs) pres[ukey[p]] = 1;
+}
+__global__ void k_pair_flag01(const long n, int* __restrict__ pres) {     // pres[n] = 0 closes the scan
+  pdl_grid_sync();
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= n) pres[k] = (k < n && pres[k] > 0) ? 1 : 0;
+}
+__global__ void k_pair_compact(const long n, const int* __restrict__ pres, const int* __restrict__ scan, unsigned long long* __restrict__ gkey) {
+  pdl_grid_sync();
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && pres[k]) gkey[scan[k]] = (unsigned long long)k;
+}
+__global__ void k_pair_gid(const int n_pairs, const unsigned long long* __restrict__ ukey, const int* __restrict__ scan, int* __restrict__ gid) {
+  pdl_grid_sync();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pairs) gid[p] = scan[ukey[p]];
+}
+// rows of `width` doubles: out[a] = in[l2g[a]]
+__global__ void k_gather_rows(const int n_act, const int* __restrict__ l2g, const double* __restrict__ in, const int width, double* __restrict__ out) {
+  pdl_grid_sync();
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)n_act * width) return;
+  const int a = (int)(t / width), q = (int)(t - (long)a * width);
+  out[t] = in[(size_t)l2g[a] * width + q];
 }
 __global__ void k_pair_entries(const int n_ent, const unsigned long long* __restrict__ skey, const int* __restrict__ sval, const int n_cam,
                                int* __restrict__ ent_row, int2* __restrict__ ent) {
@@ -125,7 +166,8 @@ __device__ __forceinline__ void pair_accumulate(const double4 ra, const double4 
 __global__ void __launch_bounds__(NT_SP, 3)
 k_schur_pairs(const int n_pairs, const int* __restrict__ pair_a, const int* __restrict__ pair_b, const int* __restrict__ pair_start,
               const int4* __restrict__ inst, const double4* __restrict__ rec_pm, const double* __restrict__ camtab, const double* __restrict__ cinv,
-              const Intr K, double* __restrict__ blocks /* [n_pairs][36] */) {
+              const Intr K, const int* __restrict__ gid /* sharded: block number in the whole map; else null */,
+              double* __restrict__ blocks /* [blocks of the whole map][36] */) {
   pdl_grid_sync();
   __shared__ double scam[NT_SP / 32][2][12];      // R[9], sv[3] of the warp's two cameras
   const int wid = threadIdx.x >> 5;
@@ -194,7 +236,7 @@ k_schur_pairs(const int n_pairs, const int* __restrict__ pair_a, const int* __re
 #pragma unroll
     for (int l = 0; l < 9; ++l)
       if (lane == l) v = make_double4(out[4 * l], out[4 * l + 1], out[4 * l + 2], out[4 * l + 3]);
-    st4(reinterpret_cast<double4*>(blocks + (size_t)36 * p) + lane, v);
+    st4(reinterpret_cast<double4*>(blocks + (size_t)36 * (gid ? gid[p] : p)) + lane, v);
   }
 }
 
