@@ -133,11 +133,15 @@ struct glba_ctx {
   int occ_pt2 = 0;
   // explicit block-sparse reduced camera matrix (glba_sparse.cuh): structure built lazily at the first PCG solve of a loaded problem
   bool env_explicit = true;      // diagnostic: GLBA_EXPLICIT=0 keeps the implicit (matrix-free) product
+  bool cg_reg = false;           // the loaded map runs the one-row-per-warp PCG kernel (k_cg_bsr<true>) on cg_grid_reg CTAs
+  int cg_grid_reg = 0;
+  bool env_cg_prof = false;      // diagnostic (GLBA_CG_PROF=1): per-phase cycle counts of the PCG kernel on stderr
+  bool env_cg_reg = true;        // diagnostic: GLBA_CG_REG=0 runs the general PCG kernel (several rows per warp, vectors in global memory) on small maps too
   bool sp_tried = false, use_explicit = false;
   int n_pairs = 0;
   long long n_inst = 0;
   Buf sp_cnt, sp_off, sp_key, sp_key2, sp_val, sp_inst, sp_ukey, sp_ucnt, sp_nruns, sp_pair_a, sp_pair_b, sp_pair_start;
-  Buf sp_ekey, sp_ekey2, sp_eval, sp_eval2, sp_erow, sp_ent, sp_row_start, sp_blocks, sp_part, sp_bar, sp_pres, sp_gscan, sp_gkey, sp_gid, sp_vec;
+  Buf sp_ekey, sp_ekey2, sp_eval, sp_eval2, sp_erow, sp_ent, sp_row_start, sp_blocks, sp_part, sp_bar, sp_pres, sp_gscan, sp_gkey, sp_gid, sp_vec, sp_prof, sp_cta_rows;
   int n_pairs_g = 0;             // blocks of the whole map (== n_pairs on one GPU)
   size_t sp_xch_len = 0;         // doubles of [blocks | sharded: Md Minv rhs of the whole map]
   int cg_grid = 0;               // CTAs of the cooperative PCG kernel (all resident)
@@ -292,6 +296,7 @@ int set_func_attributes(glba_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_linearize_tile<OPT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)8 * NT_T * OPT_LARGE * sizeof(double))));
   CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)DN_TP * DN_MAXCAM * 24 + (size_t)(DN_MAXCAM * (DN_MAXCAM + 1) / 2) * 36) * 8 + DN_TP * 4 + 64)));
   CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
+  CU(cudaFuncSetAttribute(k_cg_bsr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM_BYTES));
   CU(cudaFuncSetAttribute(k_lin_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinSmem)));
   CU(cudaFuncSetAttribute(k_pt_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<0>)));
   CU(cudaFuncSetAttribute(k_pt_pipe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<1>)));
@@ -935,7 +940,7 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   if (sharded && K2 > (1LL << 28)) return GLBA_OK;               // the union of the ranks' blocks goes through a presence table of n_cam^2 ints
   int coop = 0, occ = 0;
   CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_bsr, NT_CGP, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_bsr<false>, NT_CGP, 0));
   if (!coop || occ < 1) return GLBA_OK;                          // the PCG runs in one cooperative launch: every CTA must be resident
   cudaStream_t s = ctx->stream;
   const int* l2g = sharded ? (const int*)ctx->l2g.as<int>() : (const int*)nullptr;
@@ -1044,8 +1049,42 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   ctx->sp_xch_len = (size_t)36 * n_glob + (sharded ? (size_t)78 * n_cam_g : 0);
   ENSURE(double, ctx->sp_blocks, ctx->sp_xch_len);
   if (sharded) ENSURE(double, ctx->sp_vec, (size_t)36 * n_cam_g);
-  ctx->cg_grid = std::max(1, std::min(ctx->n_sm, cdiv(n_cam_g, NT_CGP / 32)));
-  ENSURE(double, ctx->sp_part, 2 * (size_t)ctx->cg_grid); ENSURE(unsigned, ctx->sp_bar, 1);
+  const int max_grid = std::min(ctx->n_sm, 256);            // (a lane of k_cg_bsr adds the partial sums of up to 8 CTAs)
+  ctx->cg_grid = std::max(1, std::min(max_grid, cdiv(n_cam_g, NT_CGP / 32)));
+  // Small maps (at most one row per warp of a full grid): the blocks of a CTA's rows stay in shared memory for the whole solve,
+  // so the rows are dealt out in contiguous ranges of (nearly) equal ENTRY count, at most NT_CGP/32 rows and CG_SMEM_CAP entries
+  // each.  With 16 consecutive rows per CTA the CTAs of revisited streets held 2.5x the average and every iteration waited for
+  // them (measured with GLBA_CG_PROF=1: 9 of 13 us).  Smallest feasible bound by bisection over a greedy split.
+  ctx->cg_reg = false;
+  if (ctx->env_cg_reg && n_cam_g <= max_grid * (NT_CGP / 32)) {
+    std::vector<int> rs((size_t)n_cam_g + 1);
+    CU(cudaMemcpyAsync(rs.data(), ctx->sp_row_start.p, sizeof(int) * rs.size(), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const int rows_per = NT_CGP / 32;
+    auto split = [&](int bound, std::vector<int>* out) -> int {
+      int ctas = 0, r = 0;
+      if (out) { out->clear(); out->push_back(0); }
+      while (r < n_cam_g) {
+        int cnt = 0, ent = 0;
+        while (r < n_cam_g && cnt < rows_per && (cnt == 0 || ent + (rs[r + 1] - rs[r]) <= bound)) { ent += rs[r + 1] - rs[r]; ++cnt; ++r; }
+        ++ctas;
+        if (out) out->push_back(r);
+      }
+      return ctas;
+    };
+    int lo = 1, hi = std::max(1, rs[n_cam_g]);
+    for (int r = 0; r < n_cam_g; ++r) lo = std::max(lo, rs[r + 1] - rs[r]);
+    while (lo < hi) { const int mid = lo + (hi - lo) / 2; if (split(mid, nullptr) <= max_grid) hi = mid; else lo = mid + 1; }
+    if (lo <= (int)CG_SMEM_CAP && split(lo, nullptr) <= max_grid) {
+      std::vector<int> cr;
+      ctx->cg_grid_reg = split(lo, &cr);
+      ENSURE(int, ctx->sp_cta_rows, cr.size());
+      CU(cudaMemcpyAsync(ctx->sp_cta_rows.p, cr.data(), sizeof(int) * cr.size(), cudaMemcpyHostToDevice, s));
+      CU(cudaStreamSynchronize(s));
+      ctx->cg_reg = true;
+    }
+  }
+  ENSURE(double, ctx->sp_part, 2 * (size_t)max_grid + 2); ENSURE(unsigned, ctx->sp_bar, 4); ENSURE(long long, ctx->sp_prof, 8);
   CHECK_LAUNCHES();
   // (the sort scratch stays allocated: a context that solves map after map would pay cudaMalloc / cudaFree of ~50 B per
   // instance at every load: measured 190 ms against 7 ms on C4)
@@ -1095,16 +1134,27 @@ int launch_cg_bsr(glba_ctx* ctx, const glba_options* o, int max_it) {
   double* sv = sharded ? v + 4 * L : ctx->pg.as<double>();
   double* w = sharded ? v + 5 * L : ctx->yg.as<double>();
   CU(cudaMemsetAsync(ctx->sp_bar.p, 0, sizeof(unsigned), ctx->stream));
+  const bool reg = ctx->cg_reg;          // one row per warp, vectors in registers, the CTA's blocks in shared memory
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ctx->cg_grid); cfg.blockDim = dim3(NT_CGP); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+  cfg.gridDim = dim3(reg ? ctx->cg_grid_reg : ctx->cg_grid); cfg.blockDim = dim3(NT_CGP); cfg.dynamicSmemBytes = reg ? CG_SMEM_BYTES : 0; cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   prev_small(ctx->stream) = false;
-  CU(cudaLaunchKernelEx(&cfg, k_cg_bsr, n_rows, (const uint8_t*)nullptr, (const int*)ctx->sp_row_start.as<int>(),
+  CU(cudaLaunchKernelEx(&cfg, reg ? k_cg_bsr<true> : k_cg_bsr<false>, n_rows, (const int*)ctx->sp_row_start.as<int>(),
                         (const int2*)ctx->sp_ent.as<int2>(), (const double*)ctx->sp_blocks.as<double>(), Md, Minv, rhs, x, r, u, p, sv, w,
-                        ctx->sp_part.as<double>(), ctx->sp_bar.as<unsigned>(), ctx->cgst.as<CgState>(), o->cg_rel_tol, max_it));
+                        ctx->sp_part.as<double>(), ctx->sp_bar.as<unsigned>(), ctx->cgst.as<CgState>(), o->cg_rel_tol, max_it,
+                        reg ? (int)CG_SMEM_CAP : 0, reg ? (const int*)ctx->sp_cta_rows.as<int>() : (const int*)nullptr,
+                        ctx->env_cg_prof ? ctx->sp_prof.as<long long>() : (long long*)nullptr));
+  if (ctx->env_cg_prof) {
+    long long h[8] = {0};
+    CU(cudaMemcpyAsync(h, ctx->sp_prof.p, sizeof(long long) * 7, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double it = (double)std::max<long long>(h[6], 1);
+    fprintf(stderr, "[glba] k_cg_bsr<%d> CTA 0 thread 0, cycles per iteration over %lld iterations: product %.0f | wait CTA %.0f | barrier 1 %.0f | totals %.0f | update %.0f | barrier 2 %.0f\n",
+            reg ? 1 : 0, h[6], h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it, h[5] / it);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (sharded)       // this rank's cameras of the solution
     LAUNCH(k_gather_rows, cdiv((long)ctx->n_cam * 6, 256), 256, ctx->n_cam, (const int*)ctx->l2g.as<int>(), (const double*)x, 6, ctx->cg_x.as<double>());
@@ -1618,6 +1668,8 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (const char* e = std::getenv("GLBA_PDL")) { g_pdl = (e[0] != '0'); if (e[0] == '2') g_pdl_max_grid = 0x7fffffffu; }   // diagnostic: 0 = plain launches, 2 = every launch
   if (const char* e = std::getenv("GLBA_HOST_LM")) ctx->env_host_lm = (e[0] == '1');   // diagnostic: host-side accept/reject for small windows
   if (const char* e = std::getenv("GLBA_EXPLICIT")) ctx->env_explicit = (e[0] != '0'); // diagnostic: GLBA_EXPLICIT=0 = matrix-free product on every map
+  if (const char* e = std::getenv("GLBA_CG_PROF")) ctx->env_cg_prof = (e[0] == '1');
+  if (const char* e = std::getenv("GLBA_CG_REG")) ctx->env_cg_reg = (e[0] != '0');     // diagnostic: general PCG kernel on every map
   if (const char* e = std::getenv("GLBA_FUSED")) ctx->env_fused = (e[0] == '1');       // experiment: GLBA_FUSED=1 = both halves of the implicit product in one tile kernel
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
@@ -1652,7 +1704,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->tile_sobs, &ctx->tile_sstart, &ctx->tp_key, &ctx->tp_val, &ctx->tp_key2, &ctx->cam_tp, &ctx->cam_tp_start, &ctx->tpart, &ctx->cam_iota, &ctx->ovf_raw, &ctx->ovf_k, &ctx->ovf_c, &ctx->ovf_key, &ctx->ovf_key2, &ctx->ovf_val, &ctx->cam_ov, &ctx->cam_ov_start, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax,
                 &ctx->sp_cnt, &ctx->sp_off, &ctx->sp_key, &ctx->sp_key2, &ctx->sp_val, &ctx->sp_inst, &ctx->sp_ukey, &ctx->sp_ucnt, &ctx->sp_nruns, &ctx->sp_pair_a,
                 &ctx->sp_pair_b, &ctx->sp_pair_start, &ctx->sp_ekey, &ctx->sp_ekey2, &ctx->sp_eval, &ctx->sp_eval2, &ctx->sp_erow, &ctx->sp_ent, &ctx->sp_row_start,
-                &ctx->sp_blocks, &ctx->sp_part, &ctx->sp_bar, &ctx->sp_pres, &ctx->sp_gscan, &ctx->sp_gkey, &ctx->sp_gid, &ctx->sp_vec};
+                &ctx->sp_blocks, &ctx->sp_part, &ctx->sp_bar, &ctx->sp_pres, &ctx->sp_gscan, &ctx->sp_gkey, &ctx->sp_gid, &ctx->sp_vec, &ctx->sp_prof, &ctx->sp_cta_rows};
   for (Buf* b : all) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);

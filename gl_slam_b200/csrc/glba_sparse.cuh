@@ -242,28 +242,52 @@ k_schur_pairs(const int n_pairs, const int* __restrict__ pair_a, const int* __re
 
 // ---------------------------------------------------------------------------------------------
 // The whole block-Jacobi PCG on the assembled matrix in ONE cooperative launch (one CTA per SM at most, all resident):
-// same single-reduction recurrence and stop rules as k_cg_w / k_cg_update (glba_cam.cuh), two grid barriers per iteration.
+// same single-reduction recurrence and stop rules as k_cg_w / k_cg_update (glba_cam.cuh), two grid-wide synchronisations
+// per iteration.
 //   phase 1 (one warp per camera row):  w_a = Md_a u_a + sum_b S_ab u_b,  partial gamma' = r.u and delta = u.w
-//   barrier; every CTA adds the CTA partials in the same fixed order and takes the same decisions
-//   phase 2 (lane 0 of the row's warp):  p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, u = Minv r
+//   exchange: every CTA publishes its two partial sums with a generation flag; warp 0 of every CTA waits for all flags and
+//             adds the partials in CTA order (lane-strided + butterfly): same totals, same decisions everywhere
+//   phase 2 (lanes 0..5 of the row's warp own the six components):  p = u + beta p, s = w + beta s, x += alpha p,
+//             r -= alpha s, u = Minv r
 //   barrier (u is read by other rows' products)
-// The blocks, Md and Minv are read through the non-coherent path and stay in L1 from the second iteration on; the vectors
-// other CTAs write (u) and the partials are read with ld.cg.  A row always belongs to the same warp.
-// The barrier is a monotonic counter (zeroed by the host before the launch); a waiter that spins implausibly long flags
-// reason 4 and leaves, so a scheduling accident cannot hang the device.
+// A row always belongs to the same warp.  REG: at most one row per warp (n_rows <= warps of the grid, e.g. 1 800 cameras on
+// 113 CTAs of 16 warps): the row's vectors live in registers for the whole solve; only u (every iteration) and x (at the end)
+// go to memory.  Otherwise the vectors are re-read from global memory by the lanes that wrote them.
+// The blocks, Md and Minv are read through the non-coherent path and stay in L1 from the second iteration on; what other CTAs
+// write (u, partials) is read with ld.cg after an acquire.  Flags and the barrier counter are monotonic (zeroed by the host
+// before the launch); a waiter that spins implausibly long flags reason 4 and leaves, so a scheduling accident cannot hang
+// the device.
 // ---------------------------------------------------------------------------------------------
 constexpr int NT_CGP = 512;
+constexpr unsigned CG_SPIN_LIMIT = 1u << 22;
+constexpr size_t CG_SMEM_CAP = 780;                                        // row entries per CTA kept in shared memory (292 B each)
+constexpr size_t CG_SMEM_BYTES = CG_SMEM_CAP * (36 * sizeof(double) + sizeof(int));
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, const unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// polls are relaxed loads (an acquire load invalidates the SM's L1 every time: ncu showed a CCTL.IVALL per poll); ONE fence
+// after the last poll orders everything behind it
 __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, const unsigned n_cta) {
   __shared__ int ok;
   __syncthreads();
   if (threadIdx.x == 0) {
     target += n_cta;
     __threadfence();
-    atomicAdd(bar, 1u);
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
     unsigned spins = 0;
     bool fine = true;
-    while (*reinterpret_cast<volatile unsigned*>(bar) < target) {
-      if (++spins > (1u << 22)) { fine = false; break; }
+    while (ld_relaxed_u32(bar) < target) {
+      if (++spins > CG_SPIN_LIMIT) { fine = false; break; }
     }
     __threadfence();
     ok = fine ? 1 : 0;
@@ -271,7 +295,6 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, co
   __syncthreads();
   return ok != 0;
 }
-
 // lanes 0..5 of a warp own the six components of the row's vectors (the other lanes mirror lane 0 and store nothing)
 __device__ __forceinline__ double pick6(const double* a, const int q) {
   double v = a[0];
@@ -285,89 +308,199 @@ __device__ __forceinline__ double sum6_lanes(const double v) {        // v of la
   for (int c = 1; c < 6; ++c) t += __shfl_sync(0xffffffffu, v, c);
   return t;
 }
-__device__ __forceinline__ double row6_dot(const double* __restrict__ Mrow /* 6 values of row q */, const double v) {   // sum_c M[q][c] v_c, v_c from lane c
+__device__ __forceinline__ double row6_dot_reg(const double* m /* 6 values of row q */, const double v) {   // sum_c M[q][c] v_c, v_c from lane c
   double t = 0.0;
 #pragma unroll
-  for (int c = 0; c < 6; ++c) t += __ldg(Mrow + c) * __shfl_sync(0xffffffffu, v, c);
+  for (int c = 0; c < 6; ++c) t += m[c] * __shfl_sync(0xffffffffu, v, c);
   return t;
 }
+__device__ __forceinline__ double row6_dot(const double* __restrict__ Mrow, const double v) {
+  double m[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) m[c] = __ldg(Mrow + c);
+  return row6_dot_reg(m, v);
+}
+// sum_b S_ab u_b over the entries of one row, all lanes; totals in every lane
+__device__ __forceinline__ void bsr_row(const int e0, const int e1, const int lane, const int2* __restrict__ ent, const double* __restrict__ blocks,
+                                        const double* u, double* acc) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int2 en = __ldg(ent + e);
+    const double2* ub = reinterpret_cast<const double2*>(u + (size_t)6 * en.x);
+    const double2 x01 = __ldcg(ub), x23 = __ldcg(ub + 1), x45 = __ldcg(ub + 2);
+    const double xv[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
+    const double4* bp = reinterpret_cast<const double4*>(blocks + (size_t)36 * (en.y & 0x7fffffff));
+    double B[36];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const double4 v = ldg4(bp + k); B[4 * k] = v.x; B[4 * k + 1] = v.y; B[4 * k + 2] = v.z; B[4 * k + 3] = v.w; }
+    if (en.y >= 0) {
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[rr] += B[rr * 6 + c] * xv[c];
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[c] += B[rr * 6 + c] * xv[rr];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+}
 
+// the same sum with the row's blocks in shared memory (entry le = e - E0 of the CTA, component-major); the gather of u for
+// the next trip is in flight while the current trip multiplies
+__device__ __forceinline__ void bsr_row_smem(const int e0, const int e1, const int E0, const int cap, const int lane, const double* sblk,
+                                             const int* scol, const double* u, double* acc) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+  int e = e0 + lane;
+  bool v = e < e1;
+  double2 n01 = make_double2(0.0, 0.0), n23 = n01, n45 = n01;
+  if (v) {
+    const double2* ub = reinterpret_cast<const double2*>(u + (size_t)6 * scol[e - E0]);
+    n01 = __ldcg(ub); n23 = __ldcg(ub + 1); n45 = __ldcg(ub + 2);
+  }
+  while (v) {
+    const double xv[6] = {n01.x, n01.y, n23.x, n23.y, n45.x, n45.y};
+    const int le = e - E0;
+    e += 32; v = e < e1;
+    if (v) {
+      const double2* ub = reinterpret_cast<const double2*>(u + (size_t)6 * scol[e - E0]);
+      n01 = __ldcg(ub); n23 = __ldcg(ub + 1); n45 = __ldcg(ub + 2);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[rr] += sblk[(size_t)(rr * 6 + c) * cap + le] * xv[c];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+}
+
+template <bool REG>
 __global__ void __launch_bounds__(NT_CGP, 1)
-k_cg_bsr(const int n_cam, const uint8_t* __restrict__ cam_free, const int* __restrict__ row_start, const int2* __restrict__ ent,
+k_cg_bsr(const int n_cam, const int* __restrict__ row_start, const int2* __restrict__ ent,
          const double* __restrict__ blocks, const double* __restrict__ Md, const double* __restrict__ Minv, const double* __restrict__ rhs,
-         double* x, double* r, double* u, double* p, double* sv, double* w, double* part /* [gridDim.x][2] */, unsigned* bar,
-         CgState* cg, const double tol, const int max_iters) {
+         double* x, double* r, double* u, double* p, double* sv, double* w, double* part /* [gridDim.x][2] */,
+         unsigned* sync /* barrier counter, zeroed before the launch */,
+         CgState* cg, const double tol, const int max_iters, const int cap /* REG: row entries the CTA keeps in shared memory */,
+         const int* __restrict__ cta_rows /* REG: rows [cta_rows[c], cta_rows[c+1]) of CTA c, at most one per warp, balanced by entry count */,
+         long long* prof /* diagnostic (GLBA_CG_PROF=1): SM cycles of CTA 0 per phase, summed over the iterations; else null */) {
   pdl_grid_sync();
-  (void)cam_free;        // rows of fixed cameras have no entries, Md = Minv = 0 and rhs = 0: they stay zero without a branch
+  // REG: the blocks of the CTA's rows, in row-entry order and already transposed where the entry is a lower-triangle one, live in
+  // shared memory for the whole solve (component-major: lane-consecutive entries hit consecutive banks), with their column
+  // indices.  Every grid synchronisation invalidates L1 (fence), so without this each iteration re-fetched ~90 KB per SM from
+  // L2 behind a two-level dependent load; entries beyond `cap` (none on C4: ~600 per CTA of ~790) are read from global memory.
+  extern __shared__ double sblk[];            // [36][cap] doubles, then cap ints
+  // rows of fixed cameras have no entries, Md = Minv = 0 and rhs = 0: they stay zero without a branch
   __shared__ double sm_dot[2][NT_CGP / 32];
   __shared__ double sm_tot[2];
+  __shared__ int sm_ok;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int q = lane < 6 ? lane : 0;
   const bool owner = lane < 6;
   const int gw = blockIdx.x * (NT_CGP / 32) + wid, nw = gridDim.x * (NT_CGP / 32);
+  unsigned* bar = sync;
   unsigned target = 0;
+  const int first = REG ? cta_rows[blockIdx.x] : 0, last = REG ? cta_rows[blockIdx.x + 1] : 0;
+  const bool has_row = REG ? (first + wid < last) : false;          // REG: this warp's only row
+  const int my = has_row ? first + wid : 0;
+  int re0 = 0, re1 = 0;
+  double xq = 0.0, rq = 0.0, uq = 0.0, pq = 0.0, sq = 0.0, wq = 0.0;
   // x = 0, r = rhs, u = Minv r, p = s = 0
-  for (int row = gw; row < n_cam; row += nw) {
-    const double rr = rhs[6 * row + q];
-    const double z = row6_dot(Minv + (size_t)36 * row + 6 * q, rr);
-    if (owner) { x[6 * row + q] = 0.0; r[6 * row + q] = rr; p[6 * row + q] = 0.0; sv[6 * row + q] = 0.0; u[6 * row + q] = z; }
+  double mdr[6] = {0, 0, 0, 0, 0, 0}, mir[6] = {0, 0, 0, 0, 0, 0};      // REG: rows q of the row's Md and Minv
+  int E0 = 0;
+  int* scol = reinterpret_cast<int*>(sblk + (size_t)36 * cap);
+  if (REG) {
+    E0 = row_start[first];
+    const int nloc = row_start[last] - E0;             // <= cap by construction of cta_rows
+    for (int i = threadIdx.x; i < nloc * 36; i += NT_CGP) {
+      const int le = i / 36, k = i - le * 36;
+      const int2 en = __ldg(ent + E0 + le);
+      const int kk = (en.y >= 0) ? k : (k % 6) * 6 + k / 6;          // lower-triangle entry: store the transpose
+      sblk[(size_t)kk * cap + le] = __ldg(blocks + (size_t)36 * (en.y & 0x7fffffff) + k);
+      if (k == 0) scol[le] = en.x;
+    }
+    __syncthreads();
+    if (has_row) {
+      re0 = row_start[my]; re1 = row_start[my + 1];
+      rq = rhs[6 * my + q];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { mdr[c] = __ldg(Md + (size_t)36 * my + 6 * q + c); mir[c] = __ldg(Minv + (size_t)36 * my + 6 * q + c); }
+      uq = row6_dot_reg(mir, rq);
+      if (owner) u[6 * my + q] = uq;
+    }
+  } else {
+    for (int row = gw; row < n_cam; row += nw) {
+      const double rr = rhs[6 * row + q];
+      const double z = row6_dot(Minv + (size_t)36 * row + 6 * q, rr);
+      if (owner) { x[6 * row + q] = 0.0; r[6 * row + q] = rr; p[6 * row + q] = 0.0; sv[6 * row + q] = 0.0; u[6 * row + q] = z; }
+    }
   }
   int iters = 0, reason = 0;
   bool alive = grid_barrier(bar, target, gridDim.x);
   double g_old = 0.0, a_old = 0.0, g0 = 0.0;
+  long long tprof[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+#define CG_PROF(slot) do { if (prof != nullptr) { const long long t__ = clock64(); tprof[slot] += t__ - tc; tc = t__; } } while (0)
   for (int li = 0; alive; ++li) {
     double ru = 0.0, uw = 0.0;
-    for (int row = gw; row < n_cam; row += nw) {
-      double acc[6] = {0, 0, 0, 0, 0, 0};
-      const int e1 = row_start[row + 1];
-      for (int e = row_start[row] + lane; e < e1; e += 32) {
-        const int2 en = __ldg(ent + e);
-        const double2* ub = reinterpret_cast<const double2*>(u + (size_t)6 * en.x);
-        const double2 x01 = __ldcg(ub), x23 = __ldcg(ub + 1), x45 = __ldcg(ub + 2);
-        const double xv[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
-        const double4* bp = reinterpret_cast<const double4*>(blocks + (size_t)36 * (en.y & 0x7fffffff));
-        double B[36];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { const double4 v = ldg4(bp + k); B[4 * k] = v.x; B[4 * k + 1] = v.y; B[4 * k + 2] = v.z; B[4 * k + 3] = v.w; }
-        if (en.y >= 0) {
-#pragma unroll
-          for (int rr = 0; rr < 6; ++rr)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc[rr] += B[rr * 6 + c] * xv[c];
-        } else {
-#pragma unroll
-          for (int rr = 0; rr < 6; ++rr)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] += B[rr * 6 + c] * xv[rr];
-        }
+    CG_PROF(5);
+    if (REG) {
+      if (has_row) {
+        double acc[6];
+        bsr_row_smem(re0, re1, E0, cap, lane, sblk, scol, u, acc);
+        wq = pick6(acc, q) + row6_dot_reg(mdr, uq);
+        ru = sum6_lanes(rq * uq);
+        uw = sum6_lanes(wq * uq);
       }
-      const double uq = u[6 * row + q], rq = r[6 * row + q];       // written by this lane (phase 2 / start)
-#pragma unroll
-      for (int k = 0; k < 6; ++k)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-      const double wq = pick6(acc, q) + row6_dot(Md + (size_t)36 * row + 6 * q, uq);
-      if (owner) w[6 * row + q] = wq;
-      ru += sum6_lanes(rq * uq);
-      uw += sum6_lanes(wq * uq);
+    } else {
+      for (int row = gw; row < n_cam; row += nw) {
+        const double uo = u[6 * row + q], ro = r[6 * row + q];       // written by this lane (phase 2 / start)
+        double acc[6];
+        bsr_row(row_start[row], row_start[row + 1], lane, ent, blocks, u, acc);
+        const double wo = pick6(acc, q) + row6_dot(Md + (size_t)36 * row + 6 * q, uo);
+        if (owner) w[6 * row + q] = wo;
+        ru += sum6_lanes(ro * uo);
+        uw += sum6_lanes(wo * uo);
+      }
     }
+    CG_PROF(0);                 // product + partial dot products of this warp
     if (lane == 0) { sm_dot[0][wid] = ru; sm_dot[1][wid] = uw; }
     __syncthreads();
+    CG_PROF(1);                 // waiting for the CTA's slowest warp
     if (threadIdx.x == 0) {
       double a = 0.0, b = 0.0;
 #pragma unroll
       for (int k = 0; k < NT_CGP / 32; ++k) { a += sm_dot[0][k]; b += sm_dot[1][k]; }
       part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
     }
-    if (!grid_barrier(bar, target, gridDim.x)) { reason = 4; break; }
-    if (wid == 0) {       // CTA partials in CTA order: lane-strided sums + butterfly, identical in every CTA
+    const bool bar_ok = grid_barrier(bar, target, gridDim.x);
+    CG_PROF(2);                 // grid barrier (incl. waiting for the slowest CTA)
+    if (wid == 0) {       // add the CTAs' partials in CTA order: lane-strided sums + butterfly, identical in every CTA
+      const bool fine = bar_ok;
       double a = 0.0, b = 0.0;
-      for (unsigned k = lane; k < gridDim.x; k += 32) { a += __ldcg(part + 2 * k); b += __ldcg(part + 2 * k + 1); }
+      double2 pv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {       // all of a lane's partials in flight together (cta = lane + 32 j < 256)
+        const unsigned k = lane + 32u * j;
+        pv[j] = (k < gridDim.x) ? __ldcg(reinterpret_cast<const double2*>(part) + k) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a += pv[j].x; b += pv[j].y; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-      if (lane == 0) { sm_tot[0] = a; sm_tot[1] = b; }
+      if (lane == 0) { sm_tot[0] = a; sm_tot[1] = b; sm_ok = fine ? 1 : 0; }
     }
     __syncthreads();
+    CG_PROF(3);                 // totals
+    if (!sm_ok) { reason = 4; break; }
     const double gp = sm_tot[0], dl = sm_tot[1];
     const bool first = (li == 0);
     if (first) g0 = gp;
@@ -379,19 +512,38 @@ k_cg_bsr(const int n_cam, const uint8_t* __restrict__ cam_free, const int* __res
     if (zero_rhs || converged || breakdown) { iters = li; reason = (breakdown && !converged && !zero_rhs) ? 2 : 1; break; }
     const double alpha = gp / denom;
     g_old = gp; a_old = alpha;
-    for (int row = gw; row < n_cam; row += nw) {
-      const double pn = u[6 * row + q] + beta * p[6 * row + q];
-      const double sn = w[6 * row + q] + beta * sv[6 * row + q];
-      const double xn = x[6 * row + q] + alpha * pn;
-      const double rr = r[6 * row + q] - alpha * sn;
-      const double z = row6_dot(Minv + (size_t)36 * row + 6 * q, rr);
-      if (owner) { p[6 * row + q] = pn; sv[6 * row + q] = sn; x[6 * row + q] = xn; r[6 * row + q] = rr; u[6 * row + q] = z; }
+    if (REG) {
+      if (has_row) {
+        pq = uq + beta * pq;
+        sq = wq + beta * sq;
+        xq += alpha * pq;
+        rq -= alpha * sq;
+        uq = row6_dot_reg(mir, rq);
+        if (owner) u[6 * my + q] = uq;
+      }
+    } else {
+      for (int row = gw; row < n_cam; row += nw) {
+        const double pn = u[6 * row + q] + beta * p[6 * row + q];
+        const double sn = w[6 * row + q] + beta * sv[6 * row + q];
+        const double xn = x[6 * row + q] + alpha * pn;
+        const double rr = r[6 * row + q] - alpha * sn;
+        const double z = row6_dot(Minv + (size_t)36 * row + 6 * q, rr);
+        if (owner) { p[6 * row + q] = pn; sv[6 * row + q] = sn; x[6 * row + q] = xn; r[6 * row + q] = rr; u[6 * row + q] = z; }
+      }
     }
     iters = li + 1;
+    CG_PROF(4);                 // vector updates
     if (li + 1 >= max_iters) { reason = 3; break; }
     if (!grid_barrier(bar, target, gridDim.x)) { reason = 4; break; }
   }
+  if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) prof[k] = tprof[k];
+    prof[6] = iters;
+  }
+#undef CG_PROF
   if (!alive) reason = 4;
+  if (REG && has_row && owner) x[6 * my + q] = xq;
   if (blockIdx.x == 0 && threadIdx.x == 0) { cg->iters = iters; cg->reason = reason; cg->done_at = 0; cg->gamma0 = g0; cg->tol = tol; cg->max_iters = max_iters; }
 }
 

@@ -199,11 +199,16 @@ def test_device_lm_loop_matches_host_loop(oracle, kw, okw):
 
 
 # ---- explicit block-sparse reduced camera matrix (glba_sparse.cuh) vs the matrix-free product ----------------------------
-def _solve_both_products(prob, **okw):
+def _solve_both_products(prob, general_kernel=False, **okw):
     import os
-    with g.Context(device=0) as c:
-        exp, se = c.solve(prob, g.options(**okw))
-        kt = c.time_kernels(1e4, reps=1, opt=g.options(**okw))
+    if general_kernel:
+        os.environ["GLBA_CG_REG"] = "0"      # the PCG kernel of maps with more rows than warps: several rows per warp, vectors in global memory
+    try:
+        with g.Context(device=0) as c:
+            exp, se = c.solve(prob, g.options(**okw))
+            kt = c.time_kernels(1e4, reps=1, opt=g.options(**okw))
+    finally:
+        os.environ.pop("GLBA_CG_REG", None)
     os.environ["GLBA_EXPLICIT"] = "0"
     try:
         with g.Context(device=0) as c:
@@ -213,12 +218,12 @@ def _solve_both_products(prob, **okw):
     return exp, se, imp, si, kt
 
 
-@pytest.mark.parametrize("name", ["street_grid", "loop_fixed_points", "g2o"])
+@pytest.mark.parametrize("name", ["street_grid", "street_grid_general_kernel", "loop_fixed_points", "g2o"])
 def test_explicit_reduced_matrix_matches_matrix_free_product(oracle, name):
     """PCG on the assembled blocks (one assembly per LM iteration) and PCG on the matrix-free product solve the same system:
     same trajectory as each other and as the oracle, at the parity tolerance; fixed cameras and fixed points carry no block."""
     okw = dict(max_iters=5, linsolve=g.LINSOLVE_PCG, cg_rel_tol=1e-13)
-    if name == "street_grid":
+    if name.startswith("street_grid"):
         prob = scene.make_street_grid(6, 20, 12000, track_len=lambda rng, n: 2 + rng.poisson(3.0, size=n), seed=3, rot_sigma=0.002, pos_sigma=0.03)
         okw["loss"] = 1
     elif name == "loop_fixed_points":
@@ -229,7 +234,7 @@ def test_explicit_reduced_matrix_matches_matrix_free_product(oracle, name):
         prob = scene.as_g2o(scene.make_scene(24, 3000, lambda rng, n: 3 + rng.poisson(3.0, size=n), seed=43, rot_sigma=0.003, pos_sigma=0.03))
         okw.update(mode=_abi.MODE_G2O, loss=1, max_iters=6)
     ref, so = oracle.solve(prob, oracle.options(**{k: v for k, v in okw.items() if k not in ("linsolve", "cg_rel_tol")}))
-    exp, se, imp, si, kt = _solve_both_products(prob, **okw)
+    exp, se, imp, si, kt = _solve_both_products(prob, general_kernel=name.endswith("general_kernel"), **okw)
     assert kt["n_pair_blocks"] > 0 and kt["n_pair_instances"] > 0, kt      # the explicit path was really taken
     check_trajectory(se, so)
     check_trajectory(si, so)
