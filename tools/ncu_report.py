@@ -6,13 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, out = sys.argv[1], sys.argv[2]
 G = os.path.join(ROOT, "gpurun_out")
 KERNELS = [("k_lin_pipe", "k_lin_pipe"), ("k_pt_pipeint0", "k_pt_pipe<0>"), ("k_pt_pipeint1", "k_pt_pipe<1>"), ("k_linearize_cm", "k_linearize_cm"),
-           ("k_schur_cm", "k_schur_cm"), ("k_spmv_cm", "k_spmv_cm")]
+           ("k_schur_cm", "k_schur_cm"), ("k_spmv_cm", "k_spmv_cm"), ("k_schur_pairs", "k_schur_pairs"), ("k_cg_bsr", "k_cg_bsr<1>")]
 WANT = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs"),
         ("launch__occupancy_limit_shared_mem", "CTAs/SM (smem)"), ("launch__occupancy_limit_registers", "CTAs/SM (regs)"),
         ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM written"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % of ncu peak"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots %"),
         ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe %"),
-        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts")]
+        ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts")]
 
 
 def launches(path):
@@ -52,7 +52,7 @@ def stalls(path):
     for r in data:
         op = r[1].strip().split()
         op = op[1] if op and op[0].startswith("@") else (op[0] if op else "")
-        for key in ("UBLKCP", "SYNCS", "LDG.E.ENL2.256", "STG.E.ENL2.256", "BAR.SYNC", "ACQBULK", "PREEXIT"):
+        for key in ("UBLKCP", "SYNCS", "LDG.E.ENL2.256", "STG.E.ENL2.256", "BAR.SYNC", "ACQBULK", "PREEXIT", "MEMBAR", "CCTL", "RED", "SHFL", "LDS"):
             if op.startswith(key):
                 sass[key] += 1
     return sorted(((n[6:], 100.0 * v / tot) for n, v in agg.items()), key=lambda x: -x[1])[:6], sass
