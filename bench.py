@@ -100,6 +100,7 @@ def algorithmic_bytes(n_obs, n_pt, n_cam, n_tiles=None):
         "linearize_pm": 85 * n_obs + 269 * n_pt + 96 * n_cam + meta,
         "linearize_cm": 48 * n_obs + 216 * n_cam,                 # record 32 + uv 16
         "schur_cm": 116 * n_obs + 216 * n_cam,                    # record 32 + pt idx 4 + gathered Cinv,u0 80
+        "cam_pipe": 132 * n_obs + 432 * n_cam,                    # both of the above in one kernel: the record is read once
         "spmv_pm": 33 * n_obs + 101 * n_pt + 128 * n_cam + meta,  # record 32 + slot 1 | Cinv 64 (two sectors) + CSR 4 + free 1 + u 32 | gather row 128
         "spmv_cm": 68 * n_obs + 48 * n_cam,                       # record 32 + pt idx 4 + gathered u 32
         "backsub_cost": 49 * n_obs + 221 * n_pt + 224 * n_cam + meta,   # record 32 + uv 16 + slot 1 | block 96, X 32+32, g 24, lam 32, CSR 4, free 1
@@ -281,10 +282,14 @@ def main():
         if kt[key] > 0:
             gbs = ab[name] / (kt[key] * 1e-3) / 1e9
             kernels[name] = {"ms": kt[key], "algorithmic_bytes": ab[name], "gbs": gbs, "frac": gbs / peak}
-    step_kernels = ["linearize_pm", "linearize_cm", "schur_cm"]
+    if kt["cam_pipe_ms"] > 0:        # large maps: the two camera-major passes run fused (glba_campipe.cuh)
+        gbs = ab["cam_pipe"] / (kt["cam_pipe_ms"] * 1e-3) / 1e9
+        kernels["cam_pipe"] = {"ms": kt["cam_pipe_ms"], "algorithmic_bytes": ab["cam_pipe"], "gbs": gbs, "frac": gbs / peak,
+                               "note": "what a linearisation with Schur pieces launches instead of linearize_cm + schur_cm (those remain for re-damping and are timed above for comparison)"}
+    step_kernels = ["linearize_pm", "cam_pipe"] if "cam_pipe" in kernels else ["linearize_pm", "linearize_cm", "schur_cm"]
     dom = max(step_kernels, key=lambda k: kernels.get(k, {"ms": 0})["ms"]) if kernels else None
     # kernel that actually runs for each roofline key (large maps: the pipelined tile kernels of glba_pipe.cuh)
-    KNAME = {"linearize_pm": "k_lin_pipe", "linearize_cm": "k_linearize_cm", "schur_cm": "k_schur_cm", "spmv_pm": "k_pt_pipe<0>",
+    KNAME = {"linearize_pm": "k_lin_pipe", "linearize_cm": "k_linearize_cm", "schur_cm": "k_schur_cm", "cam_pipe": "k_cam_pipe<2>", "spmv_pm": "k_pt_pipe<0>",
              "spmv_cm": "k_spmv_cm", "backsub_cost": "k_pt_pipe<1>"}
     if prob.n_obs < 400000:
         KNAME.update(linearize_pm="k_linearize_tile<1>", spmv_pm="k_point_tile<0,1>", backsub_cost="k_point_tile<1,1>")

@@ -87,7 +87,7 @@ class KernelTimes(C.Structure):
                                           "backsub_cost_ms", "point_damp_ms", "small_kernels_ms", "allreduce_ms", "chunk_sum_ms",
                                           "exchange_bytes")] + [("n_local_cams", C.c_int32), ("n_shared_cams", C.c_int32)] + \
                [(k, C.c_double) for k in ("schur_pairs_ms", "bsr_spmv_ms", "pair_setup_ms")] + \
-               [("n_pair_instances", C.c_int64), ("n_pair_blocks", C.c_int32), ("reserved_", C.c_int32)]
+               [("n_pair_instances", C.c_int64), ("n_pair_blocks", C.c_int32), ("reserved_", C.c_int32), ("cam_pipe_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -29,6 +29,7 @@
 #include "glba_dense.cuh"
 #include "glba_tiles.cuh"
 #include "glba_pipe.cuh"
+#include "glba_campipe.cuh"
 #include "glba_cam.cuh"
 #include "glba_sparse.cuh"
 #include "glba_triang.cuh"
@@ -124,6 +125,8 @@ struct glba_ctx {
   bool env_host_lm = false;     // diagnostic: GLBA_HOST_LM=1 keeps the decisions on the host for small windows too
   bool use_pipe = false;        // large maps: persistent TMA-fed tile kernels (glba_pipe.cuh)
   bool env_pipe = true, env_force_large = false;
+  int env_cp_occ = 2;           // diagnostic: GLBA_CP_OCC=3 = the 85-register build of k_cam_pipe (3 CTAs/SM)
+  bool env_campipe = true;      // diagnostic: GLBA_CAMPIPE=0 runs the two camera-major passes as separate kernels on large maps too
   Buf tile_desc, tile_cams, pm_slot;
   // fused product (k_pt_pipe<2>): slot lists per tile, camera -> (tile, slot) list, per-tile sums, identity CSR
   bool use_fused = false, env_fused = false;      // measured slower than the two-kernel product (see k_pt_pipe<2>): opt-in with GLBA_FUSED=1
@@ -297,6 +300,10 @@ int set_func_attributes(glba_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_dense_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)DN_TP * DN_MAXCAM * 24 + (size_t)(DN_MAXCAM * (DN_MAXCAM + 1) / 2) * 36) * 8 + DN_TP * 4 + 64)));
   CU(cudaFuncSetAttribute(k_dense_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)(6 * DN_MAXCAM) * (6 * DN_MAXCAM + 1) + 12 * DN_MAXCAM) * 8 + 1024)));
   CU(cudaFuncSetAttribute(k_cg_bsr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(k_cam_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CamSmem)));
+  CU(cudaFuncSetAttribute(k_cam_pipe<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(k_cam_pipe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CamSmem)));
+  CU(cudaFuncSetAttribute(k_cam_pipe<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CU(cudaFuncSetAttribute(k_lin_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinSmem)));
   CU(cudaFuncSetAttribute(k_pt_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<0>)));
   CU(cudaFuncSetAttribute(k_pt_pipe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem<1>)));
@@ -627,7 +634,7 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
   ENSURE(double, ctx->cinv, (size_t)PBLK * n_pt); ENSURE(double4, ctx->u4, n_pt);
   ENSURE(double, ctx->part_pm, 5 * (size_t)std::max(std::max(grid_pm, ctx->n_tiles), 1));
   ENSURE(double, ctx->xtab, (size_t)XTAB * n_cam); ENSURE(double, ctx->partA, ctx->grid_c); ENSURE(double, ctx->partB, ctx->grid_c);
-  ENSURE(double, ctx->partc, 4 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8); ENSURE(double, ctx->part_pm2, 5 * 64);
+  ENSURE(double, ctx->partc, 8 * (size_t)ctx->grid_c); ENSURE(unsigned, ctx->counters, 8); ENSURE(double, ctx->part_pm2, 5 * 64);
   CU(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned), s));
   ctx->timing = (n >= 200000) || ctx->env_timing; ENSURE(double, ctx->part_cm, 27 * (size_t)std::max(ctx->n_chunks, 1)); ENSURE(double, ctx->part_cm2, 27 * (size_t)std::max(ctx->n_chunks, 1));
   ENSURE(double, ctx->acc27, 54 * (size_t)n_cam + NSCAL);     // [Schur sums 27C | Hessian sums 27C | scalars]: contiguous for one all-reduce
@@ -826,12 +833,21 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
   mark(ctx, PH_LIN);
   const bool sharded = ctx->world > 1;
   if (n_pt) { const int s__ = launch_linearize_points(ctx, o, first, radius); if (s__) return s__; }
-  if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+  // Large maps, linearisation WITH Schur pieces: both camera-major passes in one TMA-fed kernel that reads the records once
+  // (glba_campipe.cuh); the two finalisations follow.
+  const bool fused_cm = with_schur && ctx->use_pipe && ctx->env_campipe && ctx->n_chunks > 0;
+  if (fused_cm) {
+    LAUNCH_SMEM(ctx->env_cp_occ == 3 ? k_cam_pipe<3> : k_cam_pipe<2>, ctx->n_chunks, CP_NT, sizeof(CamSmem), cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
+                (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(),
+                ctx->part_cm.as<double>(), ctx->part_cm2.as<double>());
+    mark(ctx, PH_SCHUR);
+  }
+  else if (ctx->n_chunks) LAUNCH(k_linearize_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                             (const double*)ctx->camtab[c].as<double>(), ctx->part_cm.as<double>(), (const LmCtl*)nullptr);
   // Single GPU, large maps: the camera finalisation of the linearisation (B_i, g_i, scaling, LM diagonal: ~11 us of dependent
   // arithmetic on 29 CTAs) needs only k_linearize_cm's sums, so it runs on a side stream WHILE the Schur pass streams the
   // records; the Schur finalisation waits for both.
-  const bool side = with_schur && !sharded && n_cam > 0 && ctx->n_chunks > 0 && ctx->n_obs >= 200000;
+  const bool side = with_schur && !fused_cm && !sharded && n_cam > 0 && ctx->n_chunks > 0 && ctx->n_obs >= 200000;
   if (side) {
     CU(cudaEventRecord(ctx->ev_side[0], ctx->stream));
     CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side[0], 0));
@@ -841,7 +857,7 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
     ctx->stream = main_stream;
     CU(cudaEventRecord(ctx->ev_side[1], ctx->side_stream));
   }
-  if (with_schur) {
+  if (with_schur && !fused_cm) {
     mark(ctx, PH_SCHUR);
     if (ctx->n_chunks) LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, cm_args(ctx), (const double4*)ctx->rec_cm.as<double4>(),
                               (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->part_cm2.as<double>());
@@ -866,9 +882,18 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
     else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     mark(ctx, with_schur ? PH_SCHUR : PH_LIN);
   }
-  if (side) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side[1], 0));
-  else if (n_cam) launch_cam_lin_fin(ctx, o, first);
-  if (with_schur && n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
+  if (fused_cm && !sharded && n_cam) {
+    // both sets of chunk sums arrived together: one launch finishes a camera twice
+    LAUNCH(k_cam_fin_both<true>, ctx->grid_c, NT_C, n_cam, (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const double*)ctx->cam[c].as<double>(),
+           (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->d_accA, (const double*)ctx->d_accB, (const int*)ctx->cam_chunk_start.as<int>(),
+           (const double*)ctx->part_cm.as<double>(), (const double*)ctx->part_cm2.as<double>(), ctx->Bc.as<double>(), ctx->gc.as<double>(), ctx->sc.as<double>(),
+           ctx->lamc.as<double>(), first, o->jacobi_scaling, o->min_lm_diagonal, o->max_lm_diagonal, 1.0 / radius, ctx->Md.as<double>(), ctx->Minv.as<double>(),
+           ctx->rhs.as<double>(), ctx->partc.as<double>(), ctx->counters.as<unsigned>() + 0, ctx->counters.as<unsigned>() + 1, ctx->d_scal, (const uint8_t*)nullptr);
+  } else {
+    if (side) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_side[1], 0));
+    else if (n_cam) launch_cam_lin_fin(ctx, o, first);
+    if (with_schur && n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
+  }
   ctx->schur_fresh = with_schur;
   mark(ctx, -1);
   CHECK_LAUNCHES();
@@ -1671,6 +1696,8 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (const char* e = std::getenv("GLBA_CG_PROF")) ctx->env_cg_prof = (e[0] == '1');
   if (const char* e = std::getenv("GLBA_CG_REG")) ctx->env_cg_reg = (e[0] != '0');     // diagnostic: general PCG kernel on every map
   if (const char* e = std::getenv("GLBA_FUSED")) ctx->env_fused = (e[0] == '1');       // experiment: GLBA_FUSED=1 = both halves of the implicit product in one tile kernel
+  if (const char* e = std::getenv("GLBA_CP_OCC")) ctx->env_cp_occ = std::atoi(e);
+  if (const char* e = std::getenv("GLBA_CAMPIPE")) ctx->env_campipe = (e[0] != '0');   // diagnostic: separate k_linearize_cm / k_schur_cm on large maps
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
   if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
@@ -1807,6 +1834,10 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
            ctx->part_cm.as<double>(), (const LmCtl*)nullptr); }, &out->linearize_cm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_schur_cm, ctx->n_chunks, NT_HCM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(), ctx->part_cm.as<double>()); }, &out->schur_cm_ms))) return st;
+  if (ctx->use_pipe && ctx->env_campipe)
+    if ((st = timed([&] { LAUNCH_SMEM(ctx->env_cp_occ == 3 ? k_cam_pipe<3> : k_cam_pipe<2>, ctx->n_chunks, CP_NT, sizeof(CamSmem), CA, (const double4*)ctx->rec_cm.as<double4>(),
+             (const double*)ctx->camtab[c].as<double>(), (const double*)ctx->cinv.as<double>(), (const double4*)ctx->u0p.as<double4>(),
+             ctx->part_cm.as<double>(), ctx->part_cm2.as<double>()); }, &out->cam_pipe_ms))) return st;
   if ((st = timed([&] { launch_point_pass0(ctx, opt, (const CgState*)nullptr, 0); }, &out->spmv_pm_ms))) return st;
   if ((st = timed([&] { LAUNCH(k_spmv_cm, ctx->n_chunks, NT_CM, CA, (const double4*)ctx->rec_cm.as<double4>(), (const double*)ctx->camtab[c].as<double>(),
            (const double4*)ctx->u4.as<double4>(), (const CgState*)nullptr, 0, ctx->part_cm.as<double>()); }, &out->spmv_cm_ms))) return st;

@@ -190,13 +190,12 @@ __device__ __forceinline__ void load_acc27(const int i, const int n_cam, const d
 
 // B_i = T' A T, g_i = T' ghat; Jacobi scale (iteration 0); lam_c = clamp(s^2 h)/s^2; |x_c|^2, max |g_c|.
 template <bool FUSE>
-__global__ void __launch_bounds__(NT_C)
-k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
+__device__ __forceinline__ void
+cam_lin_fin_body(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
               const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start, const double* __restrict__ part27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
               double* __restrict__ lamc, const int first, const int jacobi, const double min_diag, const double max_diag,
-              double* part, unsigned* counter, double* scal, const LmCtl* __restrict__ ctl = nullptr, const LmHook hook = LmHook{},
-              const uint8_t* __restrict__ owned = nullptr /* sharded: scalars count a camera on its owner rank only */) {
-  pdl_grid_sync();
+              double* part, unsigned* counter, double* scal, const LmCtl* __restrict__ ctl, const LmHook hook,
+              const uint8_t* __restrict__ owned /* sharded: scalars count a camera on its owner rank only */) {
   __shared__ double sm[2 * NT_C / 32];
   if (ctl_skip(ctl, GATE_ACCEPTED)) return;
   __shared__ double smo[2];
@@ -244,16 +243,25 @@ k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const doubl
   // device-resident LM loop: this was the last kernel of the re-linearisation after an accepted step
   if (last && threadIdx.x == 0 && hook.ctl != nullptr) { __threadfence(); lm_absorb(hook.ctl, hook.P, scal, hook.sum); }
 }
+template <bool FUSE>
+__global__ void __launch_bounds__(NT_C)
+k_cam_lin_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
+              const double* __restrict__ acc27, const int* __restrict__ cam_chunk_start, const double* __restrict__ part27, double* __restrict__ Bc, double* __restrict__ gc, double* __restrict__ sc,
+              double* __restrict__ lamc, const int first, const int jacobi, const double min_diag, const double max_diag,
+              double* part, unsigned* counter, double* scal, const LmCtl* __restrict__ ctl = nullptr, const LmHook hook = LmHook{},
+              const uint8_t* __restrict__ owned = nullptr) {
+  pdl_grid_sync();
+  cam_lin_fin_body<FUSE>(n_cam, cam_free, cam, camtab, acc27, cam_chunk_start, part27, Bc, gc, sc, lamc, first, jacobi, min_diag, max_diag, part, counter, scal, ctl, hook, owned);
+}
 
 // M_i = B_i + lam/radius - T' Mhat T (diagonal block of S), rhs_i = g_i - T' rhat, Minv_i.
 template <bool FUSE>
-__global__ void __launch_bounds__(NT_C)
-k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ acc27,
+__device__ __forceinline__ void
+cam_schur_fin_body(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ acc27,
                 const int* __restrict__ cam_chunk_start, const double* __restrict__ part27,
-                const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+                const double* Bc, const double* gc, const double* lamc, const double inv_radius,
                 double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal,
-                const uint8_t* __restrict__ owned = nullptr) {
-  pdl_grid_sync();
+                const uint8_t* __restrict__ owned) {
   __shared__ double sm[NT_C / 32];
   __shared__ double smo[1];
   __shared__ double stage[FUSE ? NT_C : 1][27];
@@ -302,6 +310,31 @@ k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const dou
   const bool mx[1] = {false};
   const int slot[1] = {S_NOTPD_C};
   finish_scalars<1>(v, mx, slot, part, counter, scal, sm, smo);
+}
+template <bool FUSE>
+__global__ void __launch_bounds__(NT_C)
+k_cam_schur_fin(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ camtab, const double* __restrict__ acc27,
+                const int* __restrict__ cam_chunk_start, const double* __restrict__ part27,
+                const double* __restrict__ Bc, const double* __restrict__ gc, const double* __restrict__ lamc, const double inv_radius,
+                double* __restrict__ Md, double* __restrict__ Minv, double* __restrict__ rhs, double* part, unsigned* counter, double* scal,
+                const uint8_t* __restrict__ owned = nullptr) {
+  pdl_grid_sync();
+  cam_schur_fin_body<FUSE>(n_cam, cam_free, camtab, acc27, cam_chunk_start, part27, Bc, gc, lamc, inv_radius, Md, Minv, rhs, part, counter, scal, owned);
+}
+// Both finalisations of a linearisation with Schur pieces in one launch (thread i finishes camera i twice: the Schur half reads
+// the B_i, g_i and LM diagonal the same thread has just written).  Used behind k_cam_pipe, where both sets of sums arrive together.
+template <bool FUSE>
+__global__ void __launch_bounds__(NT_C)
+k_cam_fin_both(const int n_cam, const uint8_t* __restrict__ cam_free, const double* __restrict__ cam, const double* __restrict__ camtab,
+               const double* __restrict__ accA, const double* __restrict__ accB, const int* __restrict__ cam_chunk_start, const double* __restrict__ partA,
+               const double* __restrict__ partB, double* Bc, double* gc, double* __restrict__ sc, double* lamc, const int first, const int jacobi,
+               const double min_diag, const double max_diag, const double inv_radius, double* __restrict__ Md, double* __restrict__ Minv,
+               double* __restrict__ rhs, double* part, unsigned* counter_lin, unsigned* counter_schur, double* scal, const uint8_t* __restrict__ owned) {
+  pdl_grid_sync();
+  cam_lin_fin_body<FUSE>(n_cam, cam_free, cam, camtab, accA, cam_chunk_start, partA, Bc, gc, sc, lamc, first, jacobi, min_diag, max_diag, part, counter_lin, scal,
+                         (const LmCtl*)nullptr, LmHook{}, owned);
+  __syncthreads();
+  cam_schur_fin_body<FUSE>(n_cam, cam_free, camtab, accB, cam_chunk_start, partB, Bc, gc, lamc, inv_radius, Md, Minv, rhs, part + 4 * gridDim.x, counter_schur, scal, owned);
 }
 
 __device__ __forceinline__ void write_xtab(double* __restrict__ xr, const double* ct, const double* x6) {

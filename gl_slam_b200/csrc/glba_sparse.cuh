@@ -163,7 +163,7 @@ __device__ __forceinline__ void pair_accumulate(const double4 ra, const double4 
     }
 }
 
-__global__ void __launch_bounds__(NT_SP, 3)
+__global__ void __launch_bounds__(NT_SP, 4)
 k_schur_pairs(const int n_pairs, const int* __restrict__ pair_a, const int* __restrict__ pair_b, const int* __restrict__ pair_start,
               const int4* __restrict__ inst, const double4* __restrict__ rec_pm, const double* __restrict__ camtab, const double* __restrict__ cinv,
               const Intr K, const int* __restrict__ gid /* sharded: block number in the whole map; else null */,

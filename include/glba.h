@@ -231,6 +231,7 @@ typedef struct {
   int64_t n_pair_instances; /* (observation, observation) pairs summed by the assembly */
   int32_t n_pair_blocks;    /* distinct off-diagonal 6x6 blocks (upper triangle) */
   int32_t reserved_;
+  double cam_pipe_ms;       /* large maps: both camera-major passes of a linearisation in one kernel (k_cam_pipe); 0 if the map runs them separately */
 } glba_kernel_times;
 
 void glba_default_options(glba_options* opt);

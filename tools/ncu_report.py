@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, out = sys.argv[1], sys.argv[2]
 G = os.path.join(ROOT, "gpurun_out")
 KERNELS = [("k_lin_pipe", "k_lin_pipe"), ("k_pt_pipeint0", "k_pt_pipe<0>"), ("k_pt_pipeint1", "k_pt_pipe<1>"), ("k_linearize_cm", "k_linearize_cm"),
-           ("k_schur_cm", "k_schur_cm"), ("k_spmv_cm", "k_spmv_cm"), ("k_schur_pairs", "k_schur_pairs"), ("k_cg_bsr", "k_cg_bsr<1>")]
+           ("k_schur_cm", "k_schur_cm"), ("k_spmv_cm", "k_spmv_cm"), ("k_schur_pairs", "k_schur_pairs"), ("k_cg_bsr", "k_cg_bsr<1>"), ("k_cam_pipe", "k_cam_pipe<2>")]
 WANT = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs"),
         ("launch__occupancy_limit_shared_mem", "CTAs/SM (smem)"), ("launch__occupancy_limit_registers", "CTAs/SM (regs)"),
         ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM written"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % of ncu peak"),

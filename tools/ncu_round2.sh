@@ -7,7 +7,7 @@ tag=${1:-r02}
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --lm-iters 2"
 $CMD > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${tag}_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv $CMD > /dev/null 2>&1
-for k in "k_lin_pipe" "k_pt_pipe<.int.0>" "k_pt_pipe<.int.1>" "k_linearize_cm" "k_schur_cm" "k_spmv_cm" "k_schur_pairs" "k_cg_bsr"; do
+for k in "k_lin_pipe" "k_pt_pipe<.int.0>" "k_pt_pipe<.int.1>" "k_linearize_cm" "k_schur_cm" "k_spmv_cm" "k_schur_pairs" "k_cg_bsr" "k_cam_pipe"; do
   n=$(echo $k | tr -d '<>.' )
   skip=2
   [ "$k" = "k_cg_bsr" ] && skip=8      # past the 1- and 33-iteration launches of glba_time_kernels: the first PCG of the LM solve (40 iterations)
