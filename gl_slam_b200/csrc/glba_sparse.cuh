@@ -242,34 +242,29 @@ k_schur_pairs(const int n_pairs, const int* __restrict__ pair_a, const int* __re
 
 // ---------------------------------------------------------------------------------------------
 // The whole block-Jacobi PCG on the assembled matrix in ONE cooperative launch (one CTA per SM at most, all resident):
-// same single-reduction recurrence and stop rules as k_cg_w / k_cg_update (glba_cam.cuh), two grid-wide synchronisations
-// per iteration.
-//   phase 1 (one warp per camera row):  w_a = Md_a u_a + sum_b S_ab u_b,  partial gamma' = r.u and delta = u.w
-//   exchange: every CTA publishes its two partial sums with a generation flag; warp 0 of every CTA waits for all flags and
-//             adds the partials in CTA order (lane-strided + butterfly): same totals, same decisions everywhere
+// same single-reduction recurrence and stop rules as k_cg_w / k_cg_update (glba_cam.cuh), two grid barriers per iteration.
+//   phase 1 (one warp per camera row):  w_a = Md_a u_a + sum_b S_ab u_b,  partial gamma' = r.u and delta = u.w per CTA
+//   barrier; warp 0 of every CTA adds the CTA partials in CTA order (lane-strided, all loads in flight + butterfly):
+//            the same totals and therefore the same decisions in every CTA
 //   phase 2 (lanes 0..5 of the row's warp own the six components):  p = u + beta p, s = w + beta s, x += alpha p,
-//             r -= alpha s, u = Minv r
+//            r -= alpha s, u = Minv r
 //   barrier (u is read by other rows' products)
-// A row always belongs to the same warp.  REG: at most one row per warp (n_rows <= warps of the grid, e.g. 1 800 cameras on
-// 113 CTAs of 16 warps): the row's vectors live in registers for the whole solve; only u (every iteration) and x (at the end)
-// go to memory.  Otherwise the vectors are re-read from global memory by the lanes that wrote them.
-// The blocks, Md and Minv are read through the non-coherent path and stay in L1 from the second iteration on; what other CTAs
-// write (u, partials) is read with ld.cg after an acquire.  Flags and the barrier counter are monotonic (zeroed by the host
-// before the launch); a waiter that spins implausibly long flags reason 4 and leaves, so a scheduling accident cannot hang
-// the device.
+// A row always belongs to the same warp.
+// REG (at most one row per warp: up to 16 rows per CTA on up to 148 CTAs): the row's vectors and its rows of Md / Minv live in
+//   registers for the whole solve, only u (every iteration) and x (at the end) go to memory; the blocks of the CTA's rows sit
+//   in shared memory in row-entry order, already transposed where the entry is a lower-triangle one; the host deals the rows
+//   out in contiguous ranges of (nearly) equal entry count (glba.cu, ensure_explicit).
+// otherwise: several rows per warp, vectors re-read from global memory by the lanes that wrote them, blocks through L2.
+// What other CTAs write (u, partial sums) is read with ld.cg.  A gpu-scope fence invalidates the SM's L1 (CCTL.IVALL), so
+// nothing read through L1 survives an iteration: that is why the REG form keeps the blocks in shared memory.
+// The barrier is a monotonic counter (zeroed by the host before the launch), polled with relaxed loads by one thread per CTA,
+// one fence before the arrival and one after the last poll (1.4 us on 113-148 CTAs: tools/micro/grid_barrier.cu); a waiter that
+// spins implausibly long flags reason 4 and leaves, so a scheduling accident cannot hang the device.
 // ---------------------------------------------------------------------------------------------
 constexpr int NT_CGP = 512;
 constexpr unsigned CG_SPIN_LIMIT = 1u << 22;
 constexpr size_t CG_SMEM_CAP = 780;                                        // row entries per CTA kept in shared memory (292 B each)
 constexpr size_t CG_SMEM_BYTES = CG_SMEM_CAP * (36 * sizeof(double) + sizeof(int));
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, const unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
