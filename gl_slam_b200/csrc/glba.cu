@@ -48,6 +48,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load() {
@@ -58,6 +59,7 @@ struct NcclApi {
     GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
     CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
     CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
     GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
     return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
@@ -93,6 +95,13 @@ struct glba_ctx {
   cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
   bool copies_in_flight = false;
   ncclComm_t comm = nullptr;
+  // peer exchange (k_xch_pack_p2p / k_xch_unpack_p2p): a buffer every rank of the node maps through CUDA IPC
+  bool env_p2p = false;                        // GLBA_P2P=1: the compact exchange over peer memory instead of ncclAllReduce (measured on par at 8 GPUs, slower at 2)
+  bool p2p_ok = false;
+  void* p2p_local = nullptr;                   // [slot 0 | slot 1 | flags | error]
+  void* p2p_peer[16] = {nullptr};              // the same allocation of every rank, in this process' address space
+  size_t p2p_cap = 0;                          // doubles per slot
+  unsigned p2p_seq = 0;                        // exchanges issued so far (same on every rank)
   std::string err;
   // problem
   bool loaded = false;
@@ -120,7 +129,7 @@ struct glba_ctx {
   // sharded runs, "owner-computes" layout (see load_problem): this rank's problem holds only the cameras its own tracks observe
   bool owner = false, want_owner = false;
   int n_cam_g = 0, n_shared = 0, n_free_cam_g = 0;            // cameras of the whole map; cameras observed by more than one rank
-  Buf act_mask, g2l, l2g, cam_owned, cam_shared, sh_scan, xsend, xrecv, xsend6, ocam_loc, cam_loc, cfix_loc, late;
+  Buf act_mask, g2l, l2g, cam_owned, cam_shared, sh_scan, xsend, xrecv, xsend6, ocam_loc, cam_loc, cfix_loc, late, sh2loc;
   Buf lmctl, dsum;              // device-resident LM control (LmCtl) and summary trace (glba_summary) of the on-device loop
   bool env_host_lm = false;     // diagnostic: GLBA_HOST_LM=1 keeps the decisions on the host for small windows too
   bool use_pipe = false;        // large maps: persistent TMA-fed tile kernels (glba_pipe.cuh)
@@ -435,6 +444,10 @@ int load_problem_impl(glba_ctx* ctx, const glba_problem* p) {
     // free cameras of the WHOLE map (every rank needs the same number: iteration caps, "nothing free")
     { int s__ = allreduce(ctx, ctx->flags.as<int>() + 7, 1, kNcclSum, kNcclInt32); if (s__) return s__; }
     CU(cudaMemcpyAsync(ctx->h_flags + 7, ctx->flags.as<int>() + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // shared slot -> local camera (or -1): the dense payload of the peer exchange
+    ENSURE(int, ctx->sh2loc, (size_t)ctx->n_shared + 1);
+    CU(cudaMemsetAsync(ctx->sh2loc.p, 0xff, sizeof(int) * ((size_t)ctx->n_shared + 1), s));
+    if (n_act) LAUNCH(k_xch_inverse, cdiv(n_act, 256), 256, n_act, (const int*)ctx->cam_shared.as<int>(), ctx->sh2loc.as<int>());
     if (n > 0) LAUNCH(k_relabel_cam, gb, 256, n, d_ocam, (const int*)ctx->g2l.as<int>(), ctx->ocam_loc.as<int>());
     if (n_act) LAUNCH(k_gather_cam, cdiv(n_act, 256), 256, n_act, (const int*)ctx->l2g.as<int>(), d_cam, d_cfix, ctx->cam_loc.as<double>(), ctx->cfix_loc.as<uint8_t>());
     CU(cudaStreamSynchronize(s));
@@ -826,6 +839,100 @@ void launch_cam_schur_fin(glba_ctx* ctx, double radius, const double* part27) {
 // Linearise (K_A + K_B blocks) and, if with_schur, the Schur pieces for `radius` in the same pass.  The Schur kernel
 // needs only point-local data, so when the map is sharded both sets of per-camera partial sums and the scalars travel
 // in ONE all-reduce, issued after both heavy kernels.
+// ---- peer exchange (opt-in, GLBA_P2P=1) --------------------------------------------------------
+// Measured on C4 (profiles/r02_p2p_ab.log): 2 GPUs 22 us per exchange against 15 us for ncclAllReduce (step 0.243 vs 0.238 ms);
+// 8 GPUs step 0.1352 vs 0.1370 ms.  Two extra launches and two system-scope fences cost what the posted NVLink stores save,
+// so NCCL stays the default; the form that would win pushes from the chunk-sum kernel and pops inside the finalisation.
+// Best effort at glba_create: any failure (no IPC, no peer access, more ranks than the table holds) leaves p2p_ok = false on
+// EVERY rank (agreed through one NCCL all-reduce) and the compact exchange keeps using ncclAllReduce.
+constexpr size_t kP2pCap = (size_t)1 << 17;       // doubles per (slot, source rank) area: 1 MB, 2 400 shared cameras
+// one allocation per rank: areas [slot 2][source rank 16][kP2pCap doubles] | flags [slot 2][source rank 16] | error word
+double* p2p_area(void* base, unsigned slot, int src) { return reinterpret_cast<double*>(base) + ((size_t)slot * P2P_MAX_WORLD + src) * kP2pCap; }
+unsigned* p2p_flags(void* base, unsigned slot) { return reinterpret_cast<unsigned*>(reinterpret_cast<double*>(base) + 2 * P2P_MAX_WORLD * kP2pCap) + slot * P2P_MAX_WORLD; }
+int* p2p_err(void* base) { return reinterpret_cast<int*>(p2p_flags(base, 0) + 2 * P2P_MAX_WORLD); }
+int setup_p2p(glba_ctx* ctx) {
+  ctx->p2p_ok = false;
+  if (ctx->world <= 1) return GLBA_OK;
+  int ok = (ctx->env_p2p && ctx->world <= P2P_MAX_WORLD && g_nccl.AllGather != nullptr) ? 1 : 0;
+  const size_t bytes = 2 * P2P_MAX_WORLD * kP2pCap * sizeof(double) + 1024;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc(&ctx->p2p_local, bytes) != cudaSuccess) { ctx->p2p_local = nullptr; ok = 0; (void)cudaGetLastError(); }
+  if (ok && (cudaMemset(ctx->p2p_local, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->p2p_local) != cudaSuccess)) { ok = 0; (void)cudaGetLastError(); }
+  // handles of all ranks (every rank takes part in the collectives whatever its own outcome)
+  Buf hb;
+  ENSURE(char, hb, sizeof(mine) * ((size_t)ctx->world + 1) + 64);
+  char* d_mine = hb.as<char>();
+  char* d_all = d_mine + sizeof(mine);
+  std::vector<cudaIpcMemHandle_t> all(ctx->world);
+  int rc = GLBA_OK;
+  if (g_nccl.AllGather != nullptr) {
+    if (cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        g_nccl.AllGather(d_mine, d_all, sizeof(mine), 1 /* ncclUint8 */, ctx->comm, ctx->stream) != 0 ||
+        cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GLBA_E_NCCL;
+  }
+  if (rc == GLBA_OK && ok) {
+    for (int r = 0; r < ctx->world && ok; ++r) {
+      if (r == ctx->rank) { ctx->p2p_peer[r] = ctx->p2p_local; continue; }
+      if (cudaIpcOpenMemHandle(&ctx->p2p_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ctx->p2p_peer[r] = nullptr; ok = 0; (void)cudaGetLastError(); }
+    }
+  }
+  // one rank's failure is everybody's
+  if (rc == GLBA_OK) {
+    int* d_ok = reinterpret_cast<int*>(d_mine);
+    if (cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        g_nccl.AllReduce(d_ok, d_ok, 1, kNcclInt32, 3 /* ncclMin */, ctx->comm, ctx->stream) != 0 ||
+        cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GLBA_E_NCCL;
+  }
+  release(hb);
+  if (rc != GLBA_OK) return fail(ctx, rc, "peer-exchange setup: collective failed");
+  ctx->p2p_ok = ok != 0;
+  ctx->p2p_cap = kP2pCap;
+  ctx->p2p_seq = 0;
+  return GLBA_OK;
+}
+void teardown_p2p(glba_ctx* ctx) {
+  for (int r = 0; r < 16; ++r)
+    if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_local) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+  if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+  ctx->p2p_local = nullptr; ctx->p2p_ok = false;
+}
+
+// The compact exchange of the owner-computes layout: rows of the shared cameras (A half, optionally B half) + n_tail scalars,
+// summed over the ranks, back into accA / accB / scal.  Peer memory when it is set up and the payload fits, NCCL otherwise.
+int owner_exchange(glba_ctx* ctx, bool with_a_out, bool with_b, int n_tail) {
+  const int n_cam = ctx->n_cam;
+  const int gx = std::max(1, cdiv((long)std::max(n_cam, 1) * 54, 256));
+  const size_t len = 54 * (size_t)ctx->n_shared + (size_t)n_tail;
+  const double* accB_in = with_b ? (const double*)ctx->d_accB : (const double*)nullptr;
+  double* accA_out = with_a_out ? ctx->d_accA : (double*)nullptr;
+  double* accB_out = with_b ? ctx->d_accB : (double*)nullptr;
+  if (ctx->p2p_ok && len <= ctx->p2p_cap) {
+    const unsigned seq = ++ctx->p2p_seq;
+    const unsigned slot = seq & 1u;
+    PeerTable P;
+    for (int r = 0; r < P2P_MAX_WORLD; ++r) {
+      void* base = r < ctx->world ? ctx->p2p_peer[r] : ctx->p2p_local;
+      P.area[r] = p2p_area(base, slot, ctx->rank);
+      P.flag[r] = p2p_flags(base, slot) + ctx->rank;
+    }
+    const int gd = std::max(1, cdiv((long)len, 256));
+    LAUNCH(k_xch_push, gd, 256, (const int*)ctx->sh2loc.as<int>(), (const double*)ctx->d_accA, accB_in, ctx->n_shared, (const double*)ctx->d_scal, n_tail, P, ctx->world,
+           ctx->counters.as<unsigned>() + 4, seq);
+    LAUNCH(k_xch_pop, gd, 256, (const int*)ctx->sh2loc.as<int>(), (const double*)p2p_area(ctx->p2p_local, slot, 0), (const unsigned*)p2p_flags(ctx->p2p_local, slot),
+           kP2pCap, ctx->world, seq, ctx->n_shared, accA_out, accB_out, ctx->d_scal, n_tail, p2p_err(ctx->p2p_local));
+    return GLBA_OK;
+  }
+  LAUNCH(k_xch_pack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->d_accA, accB_in, ctx->n_shared, ctx->xsend.as<double>(),
+         (const double*)ctx->d_scal, n_tail);
+  const int r = g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, len, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+  if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (compact exchange): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  LAUNCH(k_xch_unpack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ctx->n_shared, accA_out, accB_out, ctx->d_scal, n_tail);
+  return GLBA_OK;
+}
+
 int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double radius, bool with_schur) {
   const int c = ctx->cur;
   const int n_cam = ctx->n_cam, n_pt = ctx->n_pt;
@@ -869,14 +976,7 @@ int do_linearize_impl(glba_ctx* ctx, const glba_options* o, int first, double ra
            ctx->d_accA, ctx->d_accB, ctx->rank, ctx->d_scal);
     if (ctx->owner) {
       // compact exchange: the rows of the cameras several ranks observe + the point scalars, nothing else crosses NVLink
-      const int n_tail = S_GSLOT0 + MAX_WORLD;
-      const int gx = std::max(1, cdiv((long)n_cam * 54, 256));
-      LAUNCH(k_xch_pack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->d_accA,
-             with_schur ? (const double*)ctx->d_accB : (const double*)nullptr, ctx->n_shared, ctx->xsend.as<double>(), (const double*)ctx->d_scal, n_tail);
-      const int r = g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 54 * (size_t)ctx->n_shared + n_tail, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
-      if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (linearise): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
-      LAUNCH(k_xch_unpack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ctx->n_shared, ctx->d_accA,
-             with_schur ? ctx->d_accB : (double*)nullptr, ctx->d_scal, n_tail);
+      const int s__ = owner_exchange(ctx, true, with_schur, S_GSLOT0 + MAX_WORLD); if (s__) return s__;
     }
     else if (with_schur) AR(ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
     else AR(ctx->d_accA, 27 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum);
@@ -929,13 +1029,7 @@ int do_schur(glba_ctx* ctx, double radius) {
            (const double*)ctx->part_cm2.as<double>(), ctx->d_accB, (const CgState*)nullptr, 0);
     if (ctx->owner) {
       // same compact buffer as a linearisation (the A half travels too: it is unchanged and lands where it came from)
-      const int gx = std::max(1, cdiv((long)n_cam * 54, 256));
-      LAUNCH(k_xch_pack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->d_accA, (const double*)ctx->d_accB, ctx->n_shared,
-             ctx->xsend.as<double>(), (const double*)ctx->d_scal, 0);
-      const int r = g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 54 * (size_t)ctx->n_shared, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
-      if (r != 0) return fail(ctx, GLBA_E_NCCL, "ncclAllReduce (Schur): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
-      LAUNCH(k_xch_unpack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ctx->n_shared, (double*)nullptr,
-             ctx->d_accB, ctx->d_scal, 0);
+      const int s__ = owner_exchange(ctx, false, true, 0); if (s__) return s__;
     } else AR(ctx->d_accB, 27 * (size_t)n_cam, kNcclSum);
   }
   if (n_cam) launch_cam_schur_fin(ctx, radius, ctx->part_cm2.as<double>());
@@ -1325,7 +1419,10 @@ int read_scalars(glba_ctx* ctx) {
     CU(cudaMemcpyAsync(h_late, ls + NLATE, sizeof(h_late), cudaMemcpyDeviceToHost, ctx->stream));
   }
   CU(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, ctx->stream));
+  int p2p_failed = 0;
+  if (ctx->p2p_ok) CU(cudaMemcpyAsync(&p2p_failed, p2p_err(ctx->p2p_local), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (p2p_failed) return fail(ctx, GLBA_E_NCCL, "peer exchange: a rank did not publish its buffer within two minutes");
   if (ctx->world > 1) {
     double m = 0.0;
     for (int r = 0; r < ctx->world; ++r) m = std::max(m, ctx->h_scal[S_GSLOT0 + r]);
@@ -1697,6 +1794,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
   if (const char* e = std::getenv("GLBA_CG_REG")) ctx->env_cg_reg = (e[0] != '0');     // diagnostic: general PCG kernel on every map
   if (const char* e = std::getenv("GLBA_FUSED")) ctx->env_fused = (e[0] == '1');       // experiment: GLBA_FUSED=1 = both halves of the implicit product in one tile kernel
   if (const char* e = std::getenv("GLBA_CP_OCC")) ctx->env_cp_occ = std::atoi(e);
+  if (const char* e = std::getenv("GLBA_P2P")) ctx->env_p2p = (e[0] == '1');           // opt-in: peer-memory form of the compact exchange
   if (const char* e = std::getenv("GLBA_CAMPIPE")) ctx->env_campipe = (e[0] != '0');   // diagnostic: separate k_linearize_cm / k_schur_cm on large maps
   if (const char* e = std::getenv("GLBA_PIPE")) ctx->env_pipe = (e[0] != '0');         // diagnostic: GLBA_PIPE=0 runs the round-1 tile kernels on large maps
   if (const char* e = std::getenv("GLBA_TILE")) ctx->env_force_large = (e[0] == 'l');  // diagnostic: GLBA_TILE=large = large-map tiles for any size
@@ -1712,6 +1810,7 @@ int glba_create(const glba_device_cfg* cfg, glba_ctx** out) {
     if (!cfg->nccl_unique_id || !g_nccl.load()) { glba_destroy(ctx); return GLBA_E_NCCL; }
     ncclUniqueId id; std::memcpy(&id, cfg->nccl_unique_id, sizeof(id));
     if (g_nccl.CommInitRank(&ctx->comm, cfg->world, id, cfg->rank) != 0) { ctx->comm = nullptr; glba_destroy(ctx); return GLBA_E_NCCL; }
+    if (setup_p2p(ctx) != GLBA_OK) { glba_destroy(ctx); return GLBA_E_NCCL; }
   }
   *out = ctx;
   return GLBA_OK;
@@ -1728,7 +1827,7 @@ void glba_destroy(glba_ctx* ctx) {
                 &ctx->cam[0], &ctx->cam[1], &ctx->camtab[0], &ctx->camtab[1], &ctx->pt4[0], &ctx->pt4[1], &ctx->cam0, &ctx->pt40, &ctx->rec_pm, &ctx->rec_cm,
                 &ctx->Craw, &ctx->sp4, &ctx->lam4, &ctx->cinv, &ctx->u0p, &ctx->u4, &ctx->part_pm, &ctx->part_cm, &ctx->acc27, &ctx->yhat, &ctx->Bc, &ctx->gc, &ctx->sc,
                 &ctx->lamc, &ctx->Md, &ctx->Minv, &ctx->rhs, &ctx->cg_x, &ctx->cg_r, &ctx->cg_p, &ctx->cg_q, &ctx->pg, &ctx->yg, &ctx->cgst,
-                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->tile_sobs, &ctx->tile_sstart, &ctx->tp_key, &ctx->tp_val, &ctx->tp_key2, &ctx->cam_tp, &ctx->cam_tp_start, &ctx->tpart, &ctx->cam_iota, &ctx->ovf_raw, &ctx->ovf_k, &ctx->ovf_c, &ctx->ovf_key, &ctx->ovf_key2, &ctx->ovf_val, &ctx->cam_ov, &ctx->cam_ov_start, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax,
+                &ctx->out_a, &ctx->out_b, &ctx->out_c, &ctx->dn_part, &ctx->dn_red, &ctx->dn_full, &ctx->tile_pt, &ctx->xtab, &ctx->partA, &ctx->partB, &ctx->partc, &ctx->counters, &ctx->cam_cnt, &ctx->part_cm2, &ctx->part_pm2, &ctx->act_mask, &ctx->g2l, &ctx->l2g, &ctx->cam_owned, &ctx->cam_shared, &ctx->sh_scan, &ctx->xsend, &ctx->xrecv, &ctx->xsend6, &ctx->ocam_loc, &ctx->cam_loc, &ctx->cfix_loc, &ctx->late, &ctx->sh2loc, &ctx->lmctl, &ctx->dsum, &ctx->tile_cmin, &ctx->tile_desc, &ctx->tile_cams, &ctx->pm_slot, &ctx->tile_sobs, &ctx->tile_sstart, &ctx->tp_key, &ctx->tp_val, &ctx->tp_key2, &ctx->cam_tp, &ctx->cam_tp_start, &ctx->tpart, &ctx->cam_iota, &ctx->ovf_raw, &ctx->ovf_k, &ctx->ovf_c, &ctx->ovf_key, &ctx->ovf_key2, &ctx->ovf_val, &ctx->cam_ov, &ctx->cam_ov_start, &ctx->first_cam, &ctx->new2old, &ctx->old2new, &ctx->opt_relab, &ctx->hmax,
                 &ctx->sp_cnt, &ctx->sp_off, &ctx->sp_key, &ctx->sp_key2, &ctx->sp_val, &ctx->sp_inst, &ctx->sp_ukey, &ctx->sp_ucnt, &ctx->sp_nruns, &ctx->sp_pair_a,
                 &ctx->sp_pair_b, &ctx->sp_pair_start, &ctx->sp_ekey, &ctx->sp_ekey2, &ctx->sp_eval, &ctx->sp_eval2, &ctx->sp_erow, &ctx->sp_ent, &ctx->sp_row_start,
                 &ctx->sp_blocks, &ctx->sp_part, &ctx->sp_bar, &ctx->sp_pres, &ctx->sp_gscan, &ctx->sp_gkey, &ctx->sp_gid, &ctx->sp_vec, &ctx->sp_prof, &ctx->sp_cta_rows};
@@ -1737,6 +1836,7 @@ void glba_destroy(glba_ctx* ctx) {
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
   if (ctx->h_cg) cudaFreeHost(ctx->h_cg);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  teardown_p2p(ctx);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   for (auto& e : ctx->ev_side) if (e) cudaEventDestroy(e);
@@ -1886,14 +1986,7 @@ int glba_time_kernels(glba_ctx* ctx, const glba_options* opt, double radius, int
   out->n_local_cams = n_cam; out->n_shared_cams = ctx->owner ? ctx->n_shared : ctx->n_cam;
   out->exchange_bytes = 8.0 * ((ctx->owner ? 54.0 * ctx->n_shared : 54.0 * n_cam) + S_GSLOT0 + MAX_WORLD);
   if (ctx->owner) {
-    const int n_tail = S_GSLOT0 + MAX_WORLD;
-    const int gx = std::max(1, cdiv((long)n_cam * 54, 256));
-    st = timed([&] {
-      LAUNCH(k_xch_pack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->d_accA, (const double*)ctx->d_accB, ctx->n_shared,
-             ctx->xsend.as<double>(), (const double*)ctx->d_scal, n_tail);
-      (void)g_nccl.AllReduce(ctx->xsend.p, ctx->xrecv.p, 54 * (size_t)ctx->n_shared + n_tail, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
-      LAUNCH(k_xch_unpack, gx, 256, n_cam, (const int*)ctx->cam_shared.as<int>(), (const double*)ctx->xrecv.as<double>(), ctx->n_shared, ctx->d_accA,
-             ctx->d_accB, ctx->d_scal, n_tail); }, &out->allreduce_ms);
+    st = timed([&] { (void)owner_exchange(ctx, true, true, S_GSLOT0 + MAX_WORLD); }, &out->allreduce_ms);
     if (st) return st;
   } else if ((st = timed([&] { (void)allreduce(ctx, ctx->d_accB, 54 * (size_t)n_cam + S_GSLOT0 + MAX_WORLD, kNcclSum); }, &out->allreduce_ms))) return st;
   st = timed([&] {
