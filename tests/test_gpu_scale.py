@@ -251,3 +251,31 @@ def test_explicit_reduced_matrix_is_bitwise_reproducible(ctx):
     b, sb = ctx.solve(prob, opt)
     assert sa["cost_candidate"] == sb["cost_candidate"] and sa["cost"] == sb["cost"] and sa["cg_iters"] == sb["cg_iters"]
     assert np.array_equal(a.cam, b.cam) and np.array_equal(a.pt, b.pt)
+
+
+@pytest.mark.parametrize("name", ["two_free_cameras", "very_long_tracks", "no_shared_points"])
+def test_reduced_matrix_structure_edge_cases(oracle, name):
+    """Shapes at the edges of the assembled-matrix path: a single off-diagonal block; tracks so long that the assembly is
+    declined (more than 16 instances per observation: the matrix-free product runs); free cameras that share no point
+    (no instance at all: matrix-free).  Same trajectory as the oracle in every case."""
+    if name == "two_free_cameras":
+        prob = scene.make_scene(3, 600, 3, seed=21, rot_sigma=0.003, pos_sigma=0.03)
+        prob.cam_fixed[:] = 0; prob.cam_fixed[0] = 1
+        expect_blocks = 1
+    elif name == "very_long_tracks":
+        prob = scene.make_scene(40, 300, 36, seed=22, rot_sigma=0.002, pos_sigma=0.02)
+        expect_blocks = 0
+    else:
+        # two-view tracks over four cameras in a row, cameras 0 and 2 fixed: every point is seen by one fixed and one free
+        # camera, the two free cameras share no point
+        prob = scene.make_scene(4, 800, 2, seed=23, rot_sigma=0.003, pos_sigma=0.03)
+        prob.cam_fixed[:] = 0; prob.cam_fixed[[0, 2]] = 1
+        expect_blocks = 0
+    okw = dict(max_iters=5, linsolve=g.LINSOLVE_PCG)
+    ref, so = oracle.solve(prob, oracle.options(max_iters=5))
+    with g.Context(device=0) as c:
+        got, s = c.solve(prob, g.options(**okw))
+        kt = c.time_kernels(1e4, reps=1, opt=g.options(**okw))
+    assert kt["n_pair_blocks"] == expect_blocks, kt["n_pair_blocks"]
+    check_trajectory(s, so)
+    check_state(prob, got.cam, got.pt, ref.cam, ref.pt)
