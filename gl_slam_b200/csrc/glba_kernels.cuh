@@ -193,20 +193,25 @@ __device__ __forceinline__ void jhat_rows(const double4 rec, const double sv0, c
 // kernels are FP64-pipe co-limited (ncu: 46 % pipe at 37 % DRAM), so the symmetric updates below skip those terms:
 //   acc(r,c) += x_r a_c + y_r b_c   with (x,y) = (a,b) for J^'J^  or (E a-ish, E b-ish) for J^' E J^
 // 31/30 FMAs instead of 42.  Upper-triangular packing order as tri(r,c).
+// Two-term entries are written as two chained FMAs: `acc += x a + y b` compiles to DMUL + DFMA + DADD, three instructions of
+// the FP64 pipe these kernels are co-limited by, instead of two.
+__device__ __forceinline__ double fma2(const double x, const double a, const double y, const double b, const double acc) {
+  return fma(x, a, fma(y, b, acc));
+}
 __device__ __forceinline__ void acc_sym_sparse(double* acc, const double* x, const double* y, const double* a, const double* b) {
-  acc[0] += x[0] * a[0] + y[0] * b[0];  acc[1] += x[0] * a[1] + y[0] * b[1];  acc[2] += x[0] * a[2] + y[0] * b[2];
-  acc[3] += x[0] * a[3];                acc[4] += y[0] * b[4];                acc[5] += x[0] * a[5] + y[0] * b[5];
-  acc[6] += x[1] * a[1] + y[1] * b[1];  acc[7] += x[1] * a[2] + y[1] * b[2];  acc[8] += x[1] * a[3];
-  acc[9] += y[1] * b[4];                acc[10] += x[1] * a[5] + y[1] * b[5];
-  acc[11] += x[2] * a[2] + y[2] * b[2]; acc[12] += x[2] * a[3];               acc[13] += y[2] * b[4];
-  acc[14] += x[2] * a[5] + y[2] * b[5];
-  acc[15] += x[3] * a[3];               acc[16] += y[3] * b[4];               acc[17] += x[5] * a[3];   // (3,5) taken as (5,3)
-  acc[18] += y[4] * b[4];               acc[19] += y[5] * b[4];                                           // (4,5) taken as (5,4)
-  acc[20] += x[5] * a[5] + y[5] * b[5];
+  acc[0] = fma2(x[0], a[0], y[0], b[0], acc[0]);  acc[1] = fma2(x[0], a[1], y[0], b[1], acc[1]);  acc[2] = fma2(x[0], a[2], y[0], b[2], acc[2]);
+  acc[3] = fma(x[0], a[3], acc[3]);               acc[4] = fma(y[0], b[4], acc[4]);               acc[5] = fma2(x[0], a[5], y[0], b[5], acc[5]);
+  acc[6] = fma2(x[1], a[1], y[1], b[1], acc[6]);  acc[7] = fma2(x[1], a[2], y[1], b[2], acc[7]);  acc[8] = fma(x[1], a[3], acc[8]);
+  acc[9] = fma(y[1], b[4], acc[9]);               acc[10] = fma2(x[1], a[5], y[1], b[5], acc[10]);
+  acc[11] = fma2(x[2], a[2], y[2], b[2], acc[11]); acc[12] = fma(x[2], a[3], acc[12]);            acc[13] = fma(y[2], b[4], acc[13]);
+  acc[14] = fma2(x[2], a[5], y[2], b[5], acc[14]);
+  acc[15] = fma(x[3], a[3], acc[15]);             acc[16] = fma(y[3], b[4], acc[16]);             acc[17] = fma(x[5], a[3], acc[17]);   // (3,5) taken as (5,3)
+  acc[18] = fma(y[4], b[4], acc[18]);             acc[19] = fma(y[5], b[4], acc[19]);                                                   // (4,5) taken as (5,4)
+  acc[20] = fma2(x[5], a[5], y[5], b[5], acc[20]);
 }
 __device__ __forceinline__ void acc_vec_sparse(double* acc, const double* a, const double* b, const double f0, const double f1) {
-  acc[0] += a[0] * f0 + b[0] * f1; acc[1] += a[1] * f0 + b[1] * f1; acc[2] += a[2] * f0 + b[2] * f1;
-  acc[3] += a[3] * f0;             acc[4] += b[4] * f1;             acc[5] += a[5] * f0 + b[5] * f1;
+  acc[0] = fma2(a[0], f0, b[0], f1, acc[0]); acc[1] = fma2(a[1], f0, b[1], f1, acc[1]); acc[2] = fma2(a[2], f0, b[2], f1, acc[2]);
+  acc[3] = fma(a[3], f0, acc[3]);            acc[4] = fma(b[4], f1, acc[4]);            acc[5] = fma2(a[5], f0, b[5], f1, acc[5]);
 }
 
 // Rows of J~_p = w P R (2x3) from a record and R (row-major 3x3).
