@@ -1261,11 +1261,18 @@ int launch_cg_bsr(glba_ctx* ctx, const glba_options* o, int max_it) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   prev_small(ctx->stream) = false;
-  CU(cudaLaunchKernelEx(&cfg, reg ? k_cg_bsr<true> : k_cg_bsr<false>, n_rows, (const int*)ctx->sp_row_start.as<int>(),
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, reg ? k_cg_bsr<true> : k_cg_bsr<false>, n_rows, (const int*)ctx->sp_row_start.as<int>(),
                         (const int2*)ctx->sp_ent.as<int2>(), (const double*)ctx->sp_blocks.as<double>(), Md, Minv, rhs, x, r, u, p, sv, w,
                         ctx->sp_part.as<double>(), ctx->sp_bar.as<unsigned>(), ctx->cgst.as<CgState>(), o->cg_rel_tol, max_it,
                         reg ? (int)CG_SMEM_CAP : 0, reg ? (const int*)ctx->sp_cta_rows.as<int>() : (const int*)nullptr,
-                        ctx->env_cg_prof ? ctx->sp_prof.as<long long>() : (long long*)nullptr));
+                        ctx->env_cg_prof ? ctx->sp_prof.as<long long>() : (long long*)nullptr);
+  if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+    // the grid cannot be made resident here (SMs reserved by another client of the device): the caller falls back to the
+    // matrix-free product where it can
+    (void)cudaGetLastError();
+    return GLBA_E_UNSUPPORTED;
+  }
+  CU(le);
   if (ctx->env_cg_prof) {
     long long h[8] = {0};
     CU(cudaMemcpyAsync(h, ctx->sp_prof.p, sizeof(long long) * 7, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1339,7 +1346,12 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
     mark(ctx, PH_SCHUR);
     { const int s__ = launch_schur_pairs(ctx); if (s__) return s__; }
     mark(ctx, PH_SOLVE);
-    const int s__ = launch_cg_bsr(ctx, o, max_it); if (s__) return s__;
+    const int s__ = launch_cg_bsr(ctx, o, max_it);
+    if (s__ == GLBA_E_UNSUPPORTED && ctx->world == 1) {
+      ctx->use_explicit = false;             // this map keeps the matrix-free product from here on
+      return do_pcg(ctx, o, radius, iters);
+    }
+    if (s__) return s__;
     CHECK_LAUNCHES();
     CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
