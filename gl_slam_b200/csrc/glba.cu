@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1062,6 +1063,15 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_bsr<false>, NT_CGP, 0));
   if (!coop || occ < 1) return GLBA_OK;                          // the PCG runs in one cooperative launch: every CTA must be resident
   cudaStream_t s = ctx->stream;
+  // diagnostic (GLBA_CG_PROF=1): wall time of each stage of the structure build on stderr
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!ctx->env_cg_prof) return;
+    cudaStreamSynchronize(s);
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[glba] pair structure: %-28s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
   const int* l2g = sharded ? (const int*)ctx->l2g.as<int>() : (const int*)nullptr;
   const int* g2l = sharded ? (const int*)ctx->g2l.as<int>() : (const int*)nullptr;
   mark(ctx, PH_SETUP);
@@ -1085,6 +1095,7 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
     CU(cudaMemcpyAsync(&veto, ctx->sp_nruns.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
   }
+  lap("count + scan");
   if (veto) { mark(ctx, -1); return GLBA_OK; }
   int bits = 1; while ((1ULL << bits) < (unsigned long long)K2 && bits < 63) ++bits;
   int n_loc = 0;             // distinct blocks among this rank's tracks
@@ -1095,6 +1106,7 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
     LAUNCH(k_pair_emit, cdiv(n_pt, 256), 256, n_pt, (const int*)ctx->pt_start.as<int>(), (const int*)ctx->pm_cam.as<int>(),
            (const uint8_t*)ctx->cam_free.as<uint8_t>(), (const uint8_t*)ctx->pt_free.as<uint8_t>(), (const long long*)ctx->sp_off.as<long long>(), n_cam_g, l2g,
            ctx->sp_key.as<unsigned long long>(), ctx->sp_val.as<int4>());
+    lap("emit instances");
     tb = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
                                        ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
@@ -1102,6 +1114,7 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
     tb = ctx->sort_tmp.cap;
     CU(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tb, ctx->sp_key.as<unsigned long long>(), ctx->sp_key2.as<unsigned long long>(), ctx->sp_val.as<int4>(),
                                        ctx->sp_inst.as<int4>(), (int)n_inst, 0, bits, s));
+    lap("sort instances");
     // distinct keys = blocks; run lengths = instances per block
     tb = 0;
     CU(cub::DeviceRunLengthEncode::Encode(nullptr, tb, ctx->sp_key2.as<unsigned long long>(), ctx->sp_ukey.as<unsigned long long>(), ctx->sp_ucnt.as<int>(),
@@ -1124,6 +1137,7 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   g_launches.fetch_add(1);
   if (n_loc) LAUNCH(k_pair_cams, cdiv(n_loc, 256), 256, n_loc, (const unsigned long long*)ctx->sp_ukey.as<unsigned long long>(), n_cam_g, g2l,
                     ctx->sp_pair_a.as<int>(), ctx->sp_pair_b.as<int>());
+  lap("blocks (run lengths, scan)");
   // blocks of the whole map and this rank's place in them
   int n_glob = n_loc;
   const unsigned long long* gkey = ctx->sp_ukey.as<unsigned long long>();
@@ -1164,6 +1178,7 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
   LAUNCH(k_pair_entries, cdiv(n_ent, 256), 256, n_ent, (const unsigned long long*)ctx->sp_ekey2.as<unsigned long long>(), (const int*)ctx->sp_eval2.as<int>(), n_cam_g,
          ctx->sp_erow.as<int>(), ctx->sp_ent.as<int2>());
   LAUNCH(k_segment_starts, cdiv(n_cam_g + 1, 256), 256, (long)n_ent, (const int*)ctx->sp_erow.as<int>(), n_cam_g, ctx->sp_row_start.as<int>());
+  lap("row lists");
   // blocks; sharded: followed by the whole map's Md | Minv | rhs rows (one all-reduce carries all four), and whole-map PCG vectors
   ctx->sp_xch_len = (size_t)36 * n_glob + (sharded ? (size_t)78 * n_cam_g : 0);
   ENSURE(double, ctx->sp_blocks, ctx->sp_xch_len);
@@ -1204,6 +1219,7 @@ int ensure_explicit(glba_ctx* ctx, const glba_options* o) {
     }
   }
   ENSURE(double, ctx->sp_part, 2 * (size_t)max_grid + 2); ENSURE(unsigned, ctx->sp_bar, 4); ENSURE(long long, ctx->sp_prof, 8);
+  lap("buffers + row split");
   CHECK_LAUNCHES();
   // (the sort scratch stays allocated: a context that solves map after map would pay cudaMalloc / cudaFree of ~50 B per
   // instance at every load: measured 190 ms against 7 ms on C4)
