@@ -309,7 +309,8 @@ def main():
                                   "frac": pb / (kt["schur_pairs_ms"] * 1e-3) / 1e9 / peak, "kernel": "k_schur_pairs, once per LM iteration"}
         kernels["pcg_iteration"] = {"ms": kt["bsr_spmv_ms"], "kernel": "k_cg_bsr (cooperative, whole PCG in one launch): product on the blocks, "
                                     "dot products, vector updates, two grid barriers", "block_bytes": kt["n_pair_blocks"] * 288}
-        kernels["pair_setup"] = {"ms": kt["pair_setup_ms"], "what": "structure of the loaded map (pair instances, radix sorts), once per load"}
+        kernels["pair_setup"] = {"ms": kt["pair_setup_ms"], "what": "structure of the loaded map (pair instances, radix sorts), once per load; this figure is the FIRST build of the "
+                                 "context when it had to allocate its buffers (steady state on C4: 1.2 ms, tools/diag_pair_setup.py)"}
     if world > 1:
         kernels["allreduce"] = {"ms": kt["allreduce_ms"], "bytes": kt["exchange_bytes"], "cameras_on_this_rank": kt["n_local_cams"],
                                 "cameras_exchanged": kt["n_shared_cams"], "layout": "owner-computes: only cameras observed by >= 2 ranks are exchanged"}
