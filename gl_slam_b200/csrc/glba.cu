@@ -151,6 +151,7 @@ struct glba_ctx {
   bool env_cg_prof = false;      // diagnostic (GLBA_CG_PROF=1): per-phase cycle counts of the PCG kernel on stderr
   bool env_cg_reg = true;        // diagnostic: GLBA_CG_REG=0 runs the general PCG kernel (several rows per warp, vectors in global memory) on small maps too
   bool sp_tried = false, use_explicit = false;
+  bool cg_pending = false;       // h_cg of the last cooperative PCG is in flight: valid after the next stream synchronisation
   int n_pairs = 0;
   long long n_inst = 0;
   Buf sp_cnt, sp_off, sp_key, sp_key2, sp_val, sp_inst, sp_ukey, sp_ucnt, sp_nruns, sp_pair_a, sp_pair_b, sp_pair_start;
@@ -1369,10 +1370,11 @@ int do_pcg(glba_ctx* ctx, const glba_options* o, double radius, int* iters) {
     }
     if (s__) return s__;
     CHECK_LAUNCHES();
+    // the iteration count and stop reason travel with the step's scalars: no synchronisation of its own (run_lm reads h_cg
+    // after the read-back that follows the step)
     CU(cudaMemcpyAsync(ctx->h_cg, cg, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_cg->reason == 4) return fail(ctx, GLBA_E_CUDA, "PCG grid barrier timed out");
-    *iters = ctx->h_cg->iters;
+    ctx->cg_pending = true;
+    *iters = -1;
     mark(ctx, -1);
     return GLBA_OK;
   }
@@ -1572,6 +1574,7 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
   const bool dense = want_dense(ctx, o);
   if (o->linsolve == GLBA_LINSOLVE_DENSE && !dense && ctx->n_free_cam > 0)
     return fail(ctx, GLBA_E_UNSUPPORTED, "dense solve needs <= %d cameras and no duplicate (point,camera) observations", DN_MAXCAM);
+  ctx->cg_pending = false;
   if (!dense && ctx->n_free_cam > 0) { if ((st = ensure_explicit(ctx, o))) return st; }
   if ((st = do_linearize_impl(ctx, o, 1, radius, !dense && !g2o))) return st;
   bool fresh = true;        // point blocks are damped for the current radius
@@ -1638,6 +1641,12 @@ int run_lm(glba_ctx* ctx, const glba_options* o, glba_summary* sum) {
     }
     sum->cg_iters[it] = cg_it;
     if ((st = do_step(ctx, o, radius))) return st;
+    if (ctx->cg_pending) {       // the PCG's CgState arrived with the step's scalars
+      ctx->cg_pending = false;
+      if (ctx->h_cg->reason == 4) return fail(ctx, GLBA_E_CUDA, "PCG grid barrier timed out");
+      cg_it = ctx->h_cg->iters;
+      sum->cg_iters[it] = cg_it;
+    }
     if (pending) {
       // scalars of the linearisation that followed the previous accepted step arrived with this read-back
       if (!absorb_pending()) { --it; sum->termination = GLBA_TERM_FAILURE; sum->stop_reason = GLBA_STOP_NUMERIC; break; }
